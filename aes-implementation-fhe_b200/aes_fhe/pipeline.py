@@ -1,0 +1,286 @@
+"""AES-128 orchestration over the step classes.
+
+`AESPipeline` mirrors reference `pipeline.py:17-254` (constructor, primitive methods,
+`encrypt`, as-shipped `decrypt`, `_renorm_pair`, `_log_pair` and its tag names).  The
+drivers below it are the verified recipes of SURVEY.md Appendix C; they only *call* the
+pipeline's own primitives and never change a step class:
+
+  decrypt_readme_order   R1  README-order decryption (the shipped decrypt omits InvMixColumns, H6)
+  FipsDriver             R2  FIPS-197-exact flow: row-major packing + row-major ShiftRows (H5)
+  BatchedStateEncoder    R3  every stride slot carries an independent block (H7)
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .context import EngineContext
+from .steps import (AddRoundKey, InvMixColumnsFHE, InvShiftRows, MixColFinal, ShiftRows, StateEncoder,
+                    SubBytesLUT, XOR4LUT, from_zeta, to_zeta)
+
+Pair = Tuple[Any, Any]
+
+
+class AESPipeline:
+    def __init__(self, ctx: EngineContext, coeffs: Dict[str, Any], *,
+                 mixcolumns: Optional[MixColFinal] = None,
+                 inv_mixcolumns: Optional[InvMixColumnsFHE] = None,
+                 use_hard_renorm_between_steps: bool = False):
+        self.ctx = ctx
+        self.encoder = StateEncoder(ctx)
+        self.sc = ctx.engine.slot_count
+        self.stride = self.sc // 16
+        self.xor4 = XOR4LUT(ctx, coeffs["xor4"])
+        self.sub = SubBytesLUT(ctx, coeffs["sub_hi"], coeffs["sub_lo"])
+        self.isub = SubBytesLUT(ctx, coeffs["inv_sub_hi"], coeffs["inv_sub_lo"])
+        self.shift = ShiftRows(ctx)
+        self.invshift = InvShiftRows(ctx)
+        self.mix = mixcolumns if mixcolumns is not None else MixColFinal(ctx, self.xor4)
+        self.invmix = inv_mixcolumns if inv_mixcolumns is not None else InvMixColumnsFHE(ctx, self.xor4)
+        self.ark = AddRoundKey(self.xor4)
+        self.use_hard_renorm_between_steps = use_hard_renorm_between_steps
+        self._rk_cache: Optional[List[Pair]] = None
+
+    # ---- helpers (pipeline.py:65-98) ----
+    def _renorm_pair(self, hi, lo) -> Pair:
+        """Hard renorm ("snap"): decrypt, round every nibble to its codeword, re-encrypt."""
+        if not self.use_hard_renorm_between_steps:
+            return hi, lo
+        return self.encoder.encode(self.encoder.decode(hi, lo))
+
+    def _encode_key(self, key_bytes: np.ndarray) -> Pair:
+        assert key_bytes.shape == (16,)
+        return self.encoder.encode(key_bytes.astype(np.uint8))
+
+    def _prepare_round_keys(self, round_keys) -> List[Pair]:
+        if self._rk_cache is not None and len(self._rk_cache) == len(round_keys):
+            return self._rk_cache
+        self._rk_cache = [self._encode_key(np.asarray(rk, dtype=np.uint8)) for rk in round_keys]
+        return self._rk_cache
+
+    def _log_pair(self, dbg, tag: str, ct_hi, ct_lo, **meta) -> None:
+        if dbg is None:
+            return
+        entry = {"ct_hi": ct_hi, "ct_lo": ct_lo, "meta": meta}
+        try:
+            entry["plain"] = self.encoder.decode(ct_hi, ct_lo)
+        except Exception as e:  # same contract as the reference: never let logging kill the run
+            entry["plain"] = None
+            entry["plain_err"] = repr(e)
+        dbg[tag] = entry
+
+    # ---- primitives (pipeline.py:101-120) ----
+    def add_round_key(self, ct_hi, ct_lo, key_hi, key_lo) -> Pair:
+        return self.ark(ct_hi, ct_lo, key_hi, key_lo)
+
+    def sub_bytes(self, ct_hi, ct_lo) -> Pair:
+        return self.sub.apply(ct_hi, ct_lo)
+
+    def inv_sub_bytes(self, ct_hi, ct_lo) -> Pair:
+        return self.isub.apply(ct_hi, ct_lo)
+
+    def shift_rows(self, ct_hi, ct_lo) -> Pair:
+        return self.shift.apply(ct_hi, ct_lo)
+
+    def inv_shift_rows(self, ct_hi, ct_lo) -> Pair:
+        return self.invshift.apply(ct_hi, ct_lo)
+
+    def mix_columns(self, ct_hi, ct_lo) -> Pair:
+        return self.mix(ct_hi, ct_lo)
+
+    def inv_mix_columns(self, ct_hi, ct_lo) -> Pair:
+        return self.invmix(ct_hi, ct_lo)
+
+    # ---- one middle round, the unit BASELINE.json config 2 is quoted on (pipeline.py:143-151) ----
+    def encrypt_round(self, ct_hi, ct_lo, key_hi, key_lo) -> Pair:
+        ct_hi, ct_lo = self.sub_bytes(ct_hi, ct_lo)
+        ct_hi, ct_lo = self._renorm_pair(ct_hi, ct_lo)
+        ct_hi, ct_lo = self.shift_rows(ct_hi, ct_lo)
+        ct_hi, ct_lo = self.mix_columns(ct_hi, ct_lo)
+        ct_hi, ct_lo = self.add_round_key(ct_hi, ct_lo, key_hi, key_lo)
+        return self._renorm_pair(ct_hi, ct_lo)
+
+    # ---- full flows ----
+    def encrypt(self, state, round_keys, debug: Optional[Dict[str, Any]] = None) -> Pair:
+        if debug is not None:
+            debug.clear()
+        ct = self.encoder.encode(np.asarray(state, dtype=np.uint8))
+        self._log_pair(debug, "enc.input", *ct)
+        rk = self._prepare_round_keys(round_keys)
+        ct = self.add_round_key(*ct, *rk[0])
+        self._log_pair(debug, "enc.r0.ark", *ct)
+        ct = self._renorm_pair(*ct)
+        self._log_pair(debug, "enc.r0.renorm", *ct)
+        for r in range(1, 10):
+            ct = self.encrypt_round(*ct, *rk[r])
+        ct = self.sub_bytes(*ct)
+        self._log_pair(debug, "enc.final.sub", *ct)
+        ct = self._renorm_pair(*ct)
+        self._log_pair(debug, "enc.final.sub.renorm", *ct)
+        ct = self.shift_rows(*ct)
+        self._log_pair(debug, "enc.final.sr", *ct)
+        ct = self.add_round_key(*ct, *rk[10])
+        self._log_pair(debug, "enc.final.ark10", *ct)
+        ct = self._renorm_pair(*ct)
+        self._log_pair(debug, "enc.output", *ct)
+        return ct
+
+    def decrypt(self, ct_hi, ct_lo, round_keys, debug: Optional[Dict[str, Any]] = None) -> Pair:
+        """As shipped (pipeline.py:193-254): no InvMixColumns in the round loop."""
+        if debug is not None:
+            debug.clear()
+        rk = self._prepare_round_keys(round_keys)
+        ct = (ct_hi, ct_lo)
+        self._log_pair(debug, "dec.input", *ct)
+        ct = self.add_round_key(*ct, *rk[10])
+        self._log_pair(debug, "dec.init.ark10", *ct)
+        ct = self._renorm_pair(*ct)
+        self._log_pair(debug, "dec.init.ark10.renorm", *ct)
+        for r in range(9, 0, -1):
+            ct = self.inv_shift_rows(*ct)
+            ct = self.inv_sub_bytes(*ct)
+            ct = self._renorm_pair(*ct)
+            ct = self.add_round_key(*ct, *rk[r])
+            ct = self._renorm_pair(*ct)
+        ct = self.inv_shift_rows(*ct)
+        self._log_pair(debug, "dec.final.isr", *ct)
+        ct = self.inv_sub_bytes(*ct)
+        self._log_pair(debug, "dec.final.isb", *ct)
+        ct = self._renorm_pair(*ct)
+        self._log_pair(debug, "dec.final.isb.renorm", *ct)
+        ct = self.add_round_key(*ct, *rk[0])
+        self._log_pair(debug, "dec.final.ark0", *ct)
+        ct = self._renorm_pair(*ct)
+        self._log_pair(debug, "dec.output", *ct)
+        return ct
+
+
+# ------------------------------------------------------------------------------ drivers
+def decrypt_readme_order(pipe, ct_hi, ct_lo, round_keys) -> Pair:
+    """R1: inverse of the as-shipped `encrypt`, in the order the reference README lists
+    (README.md:85-95), using only the pipeline's own primitives."""
+    rk = pipe._prepare_round_keys(round_keys)
+    ct = pipe.add_round_key(ct_hi, ct_lo, *rk[10])
+    ct = pipe._renorm_pair(*ct)
+    for r in range(9, 0, -1):
+        ct = pipe.inv_shift_rows(*ct)
+        ct = pipe.inv_sub_bytes(*ct)
+        ct = pipe._renorm_pair(*ct)
+        ct = pipe.add_round_key(*ct, *rk[r])
+        ct = pipe._renorm_pair(*ct)
+        ct = pipe.inv_mix_columns(*ct)
+    ct = pipe.inv_shift_rows(*ct)
+    ct = pipe.inv_sub_bytes(*ct)
+    ct = pipe._renorm_pair(*ct)
+    ct = pipe.add_round_key(*ct, *rk[0])
+    return pipe._renorm_pair(*ct)
+
+
+ROWMAJOR = np.arange(16).reshape(4, 4).T.ravel()   # FIPS byte (column-first) index -> row-major position
+
+
+class RowMajorShiftRows:
+    """ShiftRows for row-major packing (position 4R+C): out(R,C) = in(R,(C+sign*R) mod 4).
+
+    Seven masked parts, depth 1, rotations by -/+R*stride and +/-(4-R)*stride.  With
+    `block=True` the masks cover the whole stride block so batched states survive (R3)."""
+
+    def __init__(self, ctx: EngineContext, inverse: bool = False, block: bool = False):
+        self.ctx = ctx
+        self.sc = ctx.engine.slot_count
+        self.stride = self.sc // 16
+        sgn = -1 if inverse else 1
+        self.parts = []      # (plaintext mask over *source* slots, rotation steps)
+        for R in range(4):
+            groups: Dict[int, List[int]] = {}
+            for C in range(4):
+                src = 4 * R + (C + sgn * R) % 4
+                groups.setdefault(((4 * R + C) - src) * self.stride, []).append(src)
+            for step, srcs in sorted(groups.items()):
+                m = np.zeros(self.sc, dtype=np.complex128)
+                for s in srcs:
+                    if block:
+                        m[s * self.stride:(s + 1) * self.stride] = 1.0
+                    else:
+                        m[s * self.stride] = 1.0
+                self.parts.append((ctx.encode(m), step))
+
+    def _apply_one(self, ct):
+        eng = self.ctx
+        out = eng.multiply(ct, 0.0)
+        for mask, step in self.parts:
+            part = eng.multiply(ct, mask)
+            if step:
+                part = eng.rotate(part, step)
+            out = eng.add(out, part)
+        return out
+
+    def apply(self, ct_hi, ct_lo) -> Pair:
+        return self._apply_one(ct_hi), self._apply_one(ct_lo)
+
+
+class BatchedStateEncoder:
+    """R3: `StateEncoder` interface with `stride` independent blocks per ciphertext pair.
+
+    encode((B,16)) places byte i of block b in slot i*stride+b (B <= stride, the rest is
+    padded with the zero byte codeword); a (16,) input (a round key) is broadcast to every b;
+    decode returns (stride,16)."""
+
+    def __init__(self, ctx: EngineContext):
+        self.ctx = ctx
+        self.sc = ctx.engine.slot_count
+        self.stride = self.sc // 16
+
+    def encode(self, state: np.ndarray) -> Pair:
+        st = np.asarray(state, dtype=np.uint8)
+        if st.ndim == 1:
+            st = np.broadcast_to(st, (self.stride, 16))
+        assert st.shape[1] == 16 and st.shape[0] <= self.stride
+        full = np.zeros((self.stride, 16), dtype=np.uint8)
+        full[:st.shape[0]] = st
+        # slot i*stride + b  <-  byte i of block b
+        hi = to_zeta((full >> 4) & 0xF, 16).T.reshape(-1)
+        lo = to_zeta(full & 0xF, 16).T.reshape(-1)
+        return self.ctx.encrypt(hi.astype(np.complex128)), self.ctx.encrypt(lo.astype(np.complex128))
+
+    def decode(self, ct_hi, ct_lo) -> np.ndarray:
+        hi = from_zeta(self.ctx.decrypt(ct_hi), 16).reshape(16, self.stride).T
+        lo = from_zeta(self.ctx.decrypt(ct_lo), 16).reshape(16, self.stride).T
+        return ((hi.astype(np.uint8) << 4) | lo).astype(np.uint8)
+
+
+class FipsDriver:
+    """R2 (+R3 when batched=True): FIPS-197-exact AES-128 on an unchanged `AESPipeline`.
+
+    State and round keys are fed transposed (row-major), `pipe.shift`/`pipe.invshift`
+    instances are replaced by row-major versions; MixColFinal / InvMixColumnsFHE, which
+    already assume row-major packing, run untouched."""
+
+    def __init__(self, pipe: AESPipeline, batched: bool = False):
+        self.pipe = pipe
+        self.batched = batched
+        pipe.shift = RowMajorShiftRows(pipe.ctx, inverse=False, block=batched)
+        pipe.invshift = RowMajorShiftRows(pipe.ctx, inverse=True, block=batched)
+        if batched:
+            enc = BatchedStateEncoder(pipe.ctx)
+            pipe.encoder = enc
+            pipe.mix.enc = enc
+            pipe.invmix.enc = enc
+
+    @staticmethod
+    def _perm(x: np.ndarray) -> np.ndarray:
+        return np.asarray(x, dtype=np.uint8)[..., ROWMAJOR]
+
+    def encrypt(self, blocks: np.ndarray, round_keys) -> Pair:
+        rks = [self._perm(rk) for rk in round_keys]
+        return self.pipe.encrypt(self._perm(blocks), rks)
+
+    def decrypt(self, ct_hi, ct_lo, round_keys) -> Pair:
+        rks = [self._perm(rk) for rk in round_keys]
+        return decrypt_readme_order(self.pipe, ct_hi, ct_lo, rks)
+
+    def decode(self, ct_hi, ct_lo) -> np.ndarray:
+        out = self.pipe.encoder.decode(ct_hi, ct_lo)
+        inv = np.argsort(ROWMAJOR)
+        return out[..., inv]

@@ -1,0 +1,380 @@
+"""AES-128 round steps on Zeta16-encoded CKKS ciphertext pairs (hi nibble, lo nibble).
+
+Host-side mirror of the reference's L2 step classes.  Each class keeps the reference's
+name, constructor and call signature and issues the *same sequence of engine calls*
+through `EngineContext` (verified op-for-op by `tests/test_trace_equivalence.py` against
+the reference's own files on a tracing backend), so that the workload measured on the
+B200 engine is the reference's workload:
+
+  StateEncoder        <- state_encoder.py:8-38     XOR4LUT          <- xor4_lut.py:10-77
+  AddRoundKey         <- add_round_key.py:138-144  SubBytesLUT      <- sub_bytes_lut.py:8-73
+  ShiftRows           <- shift_rows.py:7-56        InvShiftRows     <- inv_shiftrows.py:9-47
+  MixColFinal         <- mixcol_final.py:41-165    InvMixColumnsFHE <- invmixcolumns_fhe.py:34-170
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import tables
+from .context import EngineContext
+
+Pair = Tuple[Any, Any]
+
+
+def to_zeta(values: np.ndarray, modulus: int = 16) -> np.ndarray:
+    """k -> exp(-2 pi i k / modulus)   (utils.py:9-12)."""
+    return np.exp(-2j * np.pi / modulus) ** (np.asarray(values) % modulus)
+
+
+def from_zeta(z: np.ndarray, modulus: int = 16) -> np.ndarray:
+    """Nearest codeword index from the argument only (utils.py:15-19)."""
+    k = -np.angle(z) * modulus / (2 * np.pi)
+    return np.mod(np.rint(k), modulus).astype(np.uint8)
+
+
+class StateEncoder:
+    """16 bytes <-> two ciphertexts; byte i sits in slot i*stride, every other slot is 1.0."""
+
+    def __init__(self, ctx: EngineContext):
+        self.ctx = ctx
+        self.sc = ctx.engine.slot_count
+        self.stride = self.sc // 16
+
+    def encode(self, state: np.ndarray) -> Pair:
+        assert state.shape == (16,)
+        pos = np.arange(16) * self.stride
+        vecs = []
+        for nib in ((state >> 4) & 0x0F, state & 0x0F):
+            v = np.ones(self.sc, dtype=np.complex128)
+            v[pos] = to_zeta(nib.astype(np.uint8), 16)
+            vecs.append(v)
+        return self.ctx.encrypt(vecs[0]), self.ctx.encrypt(vecs[1])
+
+    def decode(self, ct_hi, ct_lo) -> np.ndarray:
+        pos = np.arange(16) * self.stride
+        hi = from_zeta(self.ctx.decrypt(ct_hi)[pos], 16)
+        lo = from_zeta(self.ctx.decrypt(ct_lo)[pos], 16)
+        return ((hi.astype(np.uint8) << 4) | lo).astype(np.uint8)
+
+
+def _const_pt(ctx: EngineContext, sc: int, c: complex):
+    return ctx.encode(np.full(sc, c, dtype=np.complex128))
+
+
+class XOR4LUT:
+    """a xor b on nibbles as sum_{p,q} c[p,q] A^p B^q over the zeta16 power bases."""
+
+    def __init__(self, ctx: EngineContext, coeffs: np.ndarray):
+        self.ctx = ctx
+        self.sc = ctx.engine.slot_count
+        self.coeffs = coeffs
+        self.pt: Dict[Tuple[int, int], Any] = {
+            (p, q): _const_pt(ctx, self.sc, coeffs[p, q])
+            for p in range(16) for q in range(16) if abs(coeffs[p, q]) > 1e-12
+        }
+
+    def _build_power_basis_16(self, ct) -> Dict[int, Any]:
+        eng = self.ctx
+
+        def quiet_intt(x):
+            try:
+                return eng.to_intt(x)
+            except RuntimeError:
+                return x
+
+        # recovery ladder of xor4_lut.py:31-51: plain try, coefficient form, bootstrap
+        try:
+            pos = eng.make_power_basis(ct, 8)
+        except RuntimeError:
+            ct = quiet_intt(ct)
+            try:
+                pos = eng.make_power_basis(ct, 8)
+            except RuntimeError:
+                ct = eng.bootstrap(quiet_intt(ct))
+                pos = eng.make_power_basis(ct, 8)
+        basis = {0: eng.add_plain(eng.sub(ct, ct), 1.0)}   # "encrypted 1" without spending a level
+        basis.update({k: pos[k - 1] for k in range(1, 9)})
+        for k in range(9, 16):
+            basis[k] = eng.conjugate(pos[15 - k])
+        return basis
+
+    def apply(self, a_ct, b_ct):
+        eng = self.ctx
+        A = self._build_power_basis_16(a_ct)
+        B = self._build_power_basis_16(b_ct)
+        acc = eng.sub(A[0], A[0])
+        for (p, q), pt in self.pt.items():
+            prod = eng.multiply(A[p], B[q])
+            acc = eng.add(acc, eng.multiply(prod, pt))
+        return acc
+
+    __call__ = apply
+
+
+class AddRoundKey:
+    def __init__(self, xor4: XOR4LUT):
+        self.xor4 = xor4
+
+    def __call__(self, ct_hi, ct_lo, key_hi, key_lo) -> Pair:
+        return self.xor4.apply(ct_hi, key_hi), self.xor4.apply(ct_lo, key_lo)
+
+
+class SubBytesLUT:
+    """S-box as two degree-255 polynomials in b = zeta256^byte sharing one power basis.
+    (reference class `SubBytesLUTFastCached`, imported by pipeline.py:9 as `SubBytesLUT`)."""
+
+    def __init__(self, ctx: EngineContext, hi_coeffs: np.ndarray, lo_coeffs: np.ndarray):
+        self.ctx = ctx
+        self.sc = ctx.engine.slot_count
+        self.hi = np.array(hi_coeffs, dtype=np.complex128)
+        self.lo = np.array(lo_coeffs, dtype=np.complex128)
+        tol = 1e-12
+        self.ks_hi = [k for k, c in enumerate(self.hi) if abs(c) > tol]
+        self.ks_lo = [k for k, c in enumerate(self.lo) if abs(c) > tol]
+        union = sorted(set(self.ks_hi) | set(self.ks_lo))
+        self.ks_union = [k for k in union if k != 0]
+        self.deg256 = min(max(union) if union else 0, 128)
+        self.pt_hi = {k: _const_pt(ctx, self.sc, self.hi[k]) for k in self.ks_hi}
+        self.pt_lo = {k: _const_pt(ctx, self.sc, self.lo[k]) for k in self.ks_lo}
+        self.c0_hi = self.hi[0] if len(self.hi) else 0j
+        self.c0_lo = self.lo[0] if len(self.lo) else 0j
+        # lift polynomial zeta16^l -> zeta256^l (16-point inverse DFT)
+        w256 = np.exp(-2j * np.pi / 256)
+        lift = np.fft.ifft(np.array([w256 ** k for k in range(16)], dtype=np.complex128))
+        self.ks_lift = [k for k, c in enumerate(lift) if abs(c) > tol and k != 0]
+        self.deg16 = min(max(self.ks_lift) if self.ks_lift else 0, 8)
+        self.pt_lift = {k: _const_pt(ctx, self.sc, lift[k]) for k in self.ks_lift}
+        self.c0_lift = lift[0]
+
+    def apply(self, ct_hi, ct_lo) -> Pair:
+        eng = self.ctx
+        lifted = eng.add_plain(eng.multiply(ct_lo, 0.0), self.c0_lift)
+        pos16 = eng.make_power_basis(ct_lo, self.deg16) if self.deg16 > 0 else []
+        for k in self.ks_lift:
+            bk = pos16[k - 1] if k <= len(pos16) else eng.conjugate(pos16[15 - k])
+            lifted = eng.add(lifted, eng.multiply(bk, self.pt_lift[k]))
+        ct_b = eng.multiply(ct_hi, lifted)                       # zeta256^byte
+        pos256 = eng.make_power_basis(ct_b, self.deg256) if self.deg256 > 0 else []
+        out_hi = eng.add_plain(eng.multiply(ct_b, 0.0), self.c0_hi)
+        out_lo = eng.add_plain(eng.multiply(ct_b, 0.0), self.c0_lo)
+        for k in self.ks_union:
+            bk = pos256[k - 1] if k <= len(pos256) else eng.conjugate(pos256[255 - k])
+            if k in self.pt_hi:
+                out_hi = eng.add(out_hi, eng.multiply(bk, self.pt_hi[k]))
+            if k in self.pt_lo:
+                out_lo = eng.add(out_lo, eng.multiply(bk, self.pt_lo[k]))
+        return out_hi, out_lo
+
+
+class _MaskedRowRotate:
+    """sum_r rotate(ct * rowmask_r, sign * 4 r stride) for column-first packing (row r = slots r+4c)."""
+
+    sign = -1
+
+    def __init__(self, ctx: EngineContext):
+        self.ctx = ctx
+        self.sc = ctx.engine.slot_count
+        self.stride = self.sc // 16
+        self._pt_masks: List[Any] = []
+        for r in range(4):
+            m = np.zeros(self.sc, dtype=np.complex128)
+            m[(r + 4 * np.arange(4)) * self.stride] = 1.0
+            self._pt_masks.append(ctx.encode(m))
+        self._rot_steps = [self.sign * r * 4 * self.stride for r in range(4)]
+
+    def _apply_one(self, ct):
+        eng = self.ctx
+        out = eng.multiply(ct, 0.0)
+        for mask, step in zip(self._pt_masks, self._rot_steps):
+            part = eng.multiply(ct, mask)
+            if step != 0:
+                part = eng.rotate(part, step)
+            out = eng.add(out, part)
+        return out
+
+    def apply(self, ct_hi, ct_lo) -> Pair:
+        return self._apply_one(ct_hi), self._apply_one(ct_lo)
+
+
+class ShiftRows(_MaskedRowRotate):
+    sign = -1
+
+
+class InvShiftRows(_MaskedRowRotate):
+    sign = +1
+
+
+class _GFTables:
+    """Lazy (mult, which) -> {(p,q): plaintext} cache (mixcol_final.py:19-37)."""
+
+    def __init__(self):
+        self.pt_cache: Dict[Tuple[int, str], Dict[Tuple[int, int], Any]] = {}
+
+    def load_plaintexts(self, ctx: EngineContext, mult: int, which: str):
+        key = (mult, which)
+        if key not in self.pt_cache:
+            sc = ctx.engine.slot_count
+            self.pt_cache[key] = {(p, q): _const_pt(ctx, sc, c) for p, q, c in tables.gf_mult_entries(mult, which)}
+        return self.pt_cache[key]
+
+
+class _MixBase:
+    """Shared machinery of MixColFinal / InvMixColumnsFHE: zeta16 bases, bivariate GF LUTs,
+    row-major column shifts, XOR accumulation with hard renorm, final bootstraps."""
+
+    def __init__(self, ctx: EngineContext, xor4: XOR4LUT):
+        self.ctx = ctx
+        self.xor4 = xor4
+        self.sc = ctx.engine.slot_count
+        self._coeffs = _GFTables()
+
+    def _basis16(self, ct) -> Dict[int, Any]:
+        eng = self.ctx
+        try:
+            pos = eng.make_power_basis(ct, 8)
+        except RuntimeError:
+            ct = eng.bootstrap(ct)
+            pos = eng.make_power_basis(ct, 8)
+        basis = {0: eng.add_plain(eng.multiply(ct, 0.0), 1.0)}
+        basis.update({k: pos[k - 1] for k in range(1, 9)})
+        for k in range(9, 16):
+            basis[k] = eng.conjugate(pos[15 - k])
+        return basis
+
+    def _eval2(self, ct_hi, ct_lo, mult: int, which: str):
+        eng = self.ctx
+        bx = self._basis16(ct_hi)
+        by = self._basis16(ct_lo)
+        pts = self._coeffs.load_plaintexts(eng, mult, which)
+        acc = eng.multiply(ct_hi, 0.0)
+        for (p, q), pt in pts.items():
+            t = eng.multiply(bx[p], by[q])
+            t = eng.multiply(t, pt)
+            acc = eng.add(acc, t)
+        return acc
+
+    def _gf(self, mult: int, ct_hi, ct_lo) -> Pair:
+        return self._eval2(ct_hi, ct_lo, mult, "hi"), self._eval2(ct_hi, ct_lo, mult, "lo")
+
+    def _col_shift_rowmajor(self, ct, k_up: int):
+        return self.ctx.rotate(ct, -4 * k_up * self.stride)
+
+    def _shifts(self, ct_hi, ct_lo):
+        return [(self._col_shift_rowmajor(ct_hi, k), self._col_shift_rowmajor(ct_lo, k)) for k in (1, 2, 3)]
+
+    def _xor_pair(self, a: Pair, b: Pair) -> Pair:
+        return self.xor4.apply(a[0], b[0]), self.xor4.apply(a[1], b[1])
+
+
+class MixColFinal(_MixBase):
+    """out = 2*x xor 3*rot1(x) xor rot2(x) xor rot3(x), rot_k = rotate by -4k*stride."""
+
+    def __init__(self, ctx: EngineContext, xor4: XOR4LUT, stride: Optional[int] = None):
+        super().__init__(ctx, xor4)
+        self.stride = stride if stride is not None else self.sc // 16
+        self.enc = StateEncoder(ctx)
+        self.zero_hi, self.zero_lo = self.enc.encode(np.zeros(16, dtype=np.uint8))
+
+    def gf_mult_2(self, ct_hi, ct_lo) -> Pair:
+        return self._gf(2, ct_hi, ct_lo)
+
+    def gf_mult_3(self, ct_hi, ct_lo) -> Pair:
+        return self._gf(3, ct_hi, ct_lo)
+
+    def _renorm_pair(self, hi, lo) -> Pair:
+        return self.enc.encode(self.enc.decode(hi, lo))
+
+    def _xor_ct(self, a, b):
+        return self.xor4.apply(a, b)
+
+    def __call__(self, ct_hi, ct_lo, do_final_bootstrap: bool = True,
+                 debug: Optional[Dict[str, Any]] = None) -> Pair:
+        log = debug.__setitem__ if isinstance(debug, dict) else (lambda k, v: None)
+        r1, r2, r3 = self._shifts(ct_hi, ct_lo)
+        log("rotc1", r1), log("rotc2", r2), log("rotc3", r3), log("in", (ct_hi, ct_lo))
+        two = self.gf_mult_2(ct_hi, ct_lo)
+        thr = self.gf_mult_3(*r1)
+        log("two", two), log("thr", thr)
+        acc = self._xor_pair(two, thr)
+        log("acc1", acc)
+        acc = self._renorm_pair(*acc)
+        acc = self._xor_pair(acc, r2)
+        log("acc2", acc)
+        acc = self._renorm_pair(*acc)
+        acc = self._xor_pair(acc, r3)
+        acc = self._renorm_pair(*acc)
+        log("acc3", acc)
+        out_hi, out_lo = acc
+        if do_final_bootstrap:
+            out_hi = self.ctx.bootstrap(self.ctx.to_intt(out_hi))
+            out_lo = self.ctx.bootstrap(self.ctx.to_intt(out_lo))
+            log("out", (out_hi, out_lo))
+        return out_hi, out_lo
+
+
+class InvMixColumnsFHE(_MixBase):
+    """out = 14*x xor 11*rot1(x) xor 13*rot2(x) xor 9*rot3(x)."""
+
+    def __init__(self, ctx: EngineContext, xor4: XOR4LUT, use_hard_renorm: bool = True):
+        super().__init__(ctx, xor4)
+        self.stride = self.sc // 16
+        self.enc = StateEncoder(ctx)
+        self.use_hard_renorm = use_hard_renorm
+        self._pt_row: List[Any] = []
+        for r in range(4):
+            m = np.zeros(self.sc, dtype=np.complex128)
+            m[(r + 4 * np.arange(4)) * self.stride] = 1.0
+            self._pt_row.append(ctx.encode(m))
+
+    def gf_mult_9(self, h, l) -> Pair:
+        return self._gf(9, h, l)
+
+    def gf_mult_11(self, h, l) -> Pair:
+        return self._gf(11, h, l)
+
+    def gf_mult_13(self, h, l) -> Pair:
+        return self._gf(13, h, l)
+
+    def gf_mult_14(self, h, l) -> Pair:
+        return self._gf(14, h, l)
+
+    def _rot_rows_in_col(self, ct, k_rows: int):
+        eng = self.ctx
+        parts = [eng.rotate(eng.multiply(ct, m), k_rows * self.stride) for m in self._pt_row]
+        out = eng.multiply(ct, 0.0)
+        for p in parts:
+            out = eng.add(out, p)
+        return out
+
+    def _renorm_pair(self, hi, lo) -> Pair:
+        if not self.use_hard_renorm:
+            return hi, lo
+        return self.enc.encode(self.enc.decode(hi, lo))
+
+    def _xor(self, a, b):
+        return self.xor4.apply(a, b)
+
+    def __call__(self, ct_hi, ct_lo, do_final_bootstrap: bool = True,
+                 debug: Optional[Dict[str, Any]] = None) -> Pair:
+        log = debug.__setitem__ if debug is not None else (lambda k, v: None)
+        r1, r2, r3 = self._shifts(ct_hi, ct_lo)
+        log("rotc1", r1), log("rotc2", r2), log("rotc3", r3)
+        e14 = self.gf_mult_14(ct_hi, ct_lo); log("mul14", e14)
+        e11 = self.gf_mult_11(*r1); log("mul11", e11)
+        e13 = self.gf_mult_13(*r2); log("mul13", e13)
+        e9 = self.gf_mult_9(*r3); log("mul9", e9)
+        acc = self._xor_pair(e14, e11)
+        log("acc1", acc)
+        acc = self._renorm_pair(*acc)
+        acc = self._xor_pair(acc, e13)
+        log("acc2", acc)
+        acc = self._renorm_pair(*acc)
+        acc = self._xor_pair(acc, e9)
+        out_h, out_l = self._renorm_pair(*acc)
+        if do_final_bootstrap:
+            out_h = self.ctx.bootstrap(out_h)
+            out_l = self.ctx.bootstrap(out_l)
+        log("out", (out_h, out_l))
+        return out_h, out_l

@@ -1,0 +1,179 @@
+"""Host logic above the engine boundary, on the tier-A slot stand-in (no GPU needed).
+
+Pins (i) decoded bytes per `_log_pair` tag against the fixtures generated from the UNCHANGED
+reference modules (tests/golden/make_golden.py), (ii) the full engine-call trace of our
+mirror against the reference's trace digest op-for-op, (iii) the FIPS-197 and batched
+drivers against `cryptography`'s AES-ECB.
+"""
+import json
+from collections import Counter
+from pathlib import Path
+
+import numpy as np
+import pytest
+from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+
+import aes_fhe
+import refload
+from oracle import slot_standin as ss
+
+GOLD = json.load(open(Path(__file__).parent / "golden" / "aes_reference_golden.json"))
+SLOTS = GOLD["slots"]
+
+
+def build(slots=SLOTS, trace=True, **kw):
+    ctx = aes_fhe.EngineContext(1, mode="cpu", thread_count=4, backend=ss, slot_count=slots, **kw)
+    ctx.engine.trace_enabled = trace
+    co = aes_fhe.load_all_coeffs()
+    x4 = aes_fhe.XOR4LUT(ctx, co["xor4"])
+    pipe = aes_fhe.AESPipeline(ctx, co, mixcolumns=aes_fhe.MixColFinal(ctx, x4),
+                               inv_mixcolumns=aes_fhe.InvMixColumnsFHE(ctx, x4), use_hard_renorm_between_steps=True)
+    return ctx, pipe
+
+
+def ops(eng):
+    c = Counter()
+    for (_, op), n in eng.counters.items():
+        c[op] += n
+    return dict(sorted(c.items()))
+
+
+def ecb(key: bytes, data: bytes) -> bytes:
+    e = Cipher(algorithms.AES(key), modes.ECB()).encryptor()
+    return e.update(data) + e.finalize()
+
+
+@pytest.fixture(scope="module")
+def built():
+    return build()
+
+
+def test_construction_trace_matches_reference(built):
+    ctx, _ = build()
+    assert ctx.engine.trace_digest() == GOLD["construct"]["digest"]
+    assert ops(ctx.engine) == GOLD["construct"]["ops"]
+
+
+@pytest.mark.parametrize("case", ["fips_c1", "seed7"])
+def test_as_shipped_encrypt_decrypt_bytes_and_trace(built, case):
+    ctx, pipe = built
+    g = GOLD["cases"][case]
+    key = np.frombuffer(bytes.fromhex(g["key"]), dtype=np.uint8)
+    pt = np.frombuffer(bytes.fromhex(g["pt"]), dtype=np.uint8)
+    rks = aes_fhe.expand_aes128_key(key)
+    pipe._rk_cache = None
+    ctx.engine.reset_trace()
+    dbg = {}
+    ct = pipe.encrypt(pt.copy(), rks, dbg)
+    assert {t: bytes(e["plain"]).hex() for t, e in dbg.items()} == g["enc_tags"]
+    assert ctx.engine.trace_digest() == g["enc_digest"]
+    assert ops(ctx.engine) == g["enc_ops"]
+    ctx.engine.reset_trace()
+    dbg = {}
+    pipe.decrypt(*ct, rks, dbg)
+    assert {t: bytes(e["plain"]).hex() for t, e in dbg.items()} == g["dec_tags"]
+    assert ctx.engine.trace_digest() == g["dec_digest"]
+    # R1 driver inverts the as-shipped encrypt
+    back = aes_fhe.decrypt_readme_order(pipe, *ct, rks)
+    assert bytes(pipe.encoder.decode(*back)).hex() == g["pt"]
+
+
+@pytest.mark.parametrize("prim", sorted(GOLD["primitives"]))
+def test_primitive_trace_and_bytes(built, prim):
+    ctx, pipe = built
+    g = GOLD["primitives"][prim]
+    st = np.frombuffer(bytes.fromhex(g["state"]), dtype=np.uint8).copy()
+    ky = np.frombuffer(bytes.fromhex(g["key"]), dtype=np.uint8).copy()
+    if prim == "inv_mix_columns":
+        pipe.invmix._coeffs.pt_cache.clear()    # the golden run met InvMixColumns with a cold GF-table cache
+    ctx.engine.reset_trace()
+    c = pipe.encoder.encode(st)
+    k = pipe.encoder.encode(ky)
+    res = pipe.add_round_key(*c, *k) if prim == "add_round_key" else getattr(pipe, prim)(*c)
+    assert ctx.engine.trace_digest() == g["digest"]
+    assert ops(ctx.engine) == g["ops"]
+    assert bytes(pipe.encoder.decode(*res)).hex() == g["out"]
+
+
+def test_survey_appendix_b_op_counts():
+    e = GOLD["cases"]["fips_c1"]["enc_ops"]
+    assert (e["mul_cc"], e["conj"], e["rotate"], e["mul_cp"], e["bootstrap"]) == (9753, 2908, 114, 12165, 18)
+
+
+@pytest.mark.parametrize("case", ["fips_c1", "seed7"])
+def test_fips_driver_r2(case):
+    g = GOLD["cases"][case]
+    ctx, pipe = build(trace=False)
+    drv = aes_fhe.FipsDriver(pipe)
+    key = np.frombuffer(bytes.fromhex(g["key"]), dtype=np.uint8)
+    pt = np.frombuffer(bytes.fromhex(g["pt"]), dtype=np.uint8)
+    rks = aes_fhe.expand_aes128_key(key)
+    ct = drv.encrypt(pt, rks)
+    assert bytes(drv.decode(*ct)).hex() == g["fips_ct"]
+    back = drv.decrypt(*ct, rks)
+    assert bytes(drv.decode(*back)).hex() == g["pt"]
+
+
+def test_batched_driver_r3_every_block_is_fips():
+    ctx, pipe = build(slots=16 * 8, trace=False)        # stride 8 -> 8 independent blocks
+    drv = aes_fhe.FipsDriver(pipe, batched=True)
+    rng = np.random.default_rng(3)
+    blocks = rng.integers(0, 256, (8, 16), dtype=np.uint8)
+    key = rng.integers(0, 256, 16, dtype=np.uint8)
+    rks = aes_fhe.expand_aes128_key(key)
+    ct = drv.encrypt(blocks, rks)
+    got = drv.decode(*ct)
+    for b in range(8):
+        assert bytes(got[b]) == ecb(bytes(key), bytes(blocks[b]))
+    back = drv.decode(*drv.decrypt(*ct, rks))
+    assert np.array_equal(back, blocks)
+
+
+def test_level_exhaustion_raises_runtimeerror_and_ladder_recovers():
+    # callers' control flow depends on RuntimeError (xor4_lut.py:33-51): start below the needed depth
+    ctx, pipe = build(trace=False, fresh_level=2, boot_level=14)
+    st = np.arange(16, dtype=np.uint8)
+    c = pipe.encoder.encode(st)
+    k = pipe.encoder.encode(st[::-1].copy())
+    out = pipe.add_round_key(*c, *k)            # ladder bootstraps internally
+    assert np.array_equal(pipe.encoder.decode(*out), st ^ st[::-1])
+    assert ctx.bootstrap_stats()["count"] > 0
+    with pytest.raises(RuntimeError):
+        pipe.sub_bytes(*pipe.encoder.encode(st))   # no ladder in SubBytes (sub_bytes_lut.py:46-73)
+
+
+def _live_reference_pipeline(ref, slots):
+    d = ref.coeff_dir
+    lut = ref.lut
+    co = {"xor4": lut.load_coeff2d(d / "xor4_coeffs.json", 16), "sub_hi": lut.load_coeff1d(d / "mod256_to_16_hi.json"),
+          "sub_lo": lut.load_coeff1d(d / "mod256_to_16_lo.json"),
+          "inv_sub_hi": lut.load_coeff1d(d / "inv_mod256_to_16_hi.json"),
+          "inv_sub_lo": lut.load_coeff1d(d / "inv_mod256_to_16_lo.json")}
+    ctx = ref.engine_context.EngineContext(1, mode="cpu", thread_count=4)
+    ctx.engine.slot_count = slots
+    ctx.engine.trace_enabled = True
+    x4 = ref.xor4_lut.XOR4LUT(ctx, co["xor4"])
+    pipe = ref.pipeline.AESPipeline(ctx, co, mixcolumns=ref.mixcol_final.MixColFinal(ctx, x4),
+                                    inv_mixcolumns=ref.invmixcolumns_fhe.InvMixColumnsFHE(ctx, x4),
+                                    use_hard_renorm_between_steps=True)
+    return ctx, pipe
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not mounted")
+def test_mirror_trace_equals_unchanged_reference_live():
+    """Same check as the golden digests, but live against the reference files (build container only),
+    on fresh random inputs."""
+    ref = refload.load(ss)
+    rctx, rpipe = _live_reference_pipeline(ref, 64)
+    mctx, mpipe = build(slots=64)
+    rctx.engine.reset_trace(), mctx.engine.reset_trace()
+    rng = np.random.default_rng(11)
+    key = rng.integers(0, 256, 16, dtype=np.uint8)
+    pt = rng.integers(0, 256, 16, dtype=np.uint8)
+    rks = aes_fhe.expand_aes128_key(key)
+    r = rpipe.encrypt(pt.copy(), rks)
+    m = mpipe.encrypt(pt.copy(), rks)
+    assert rctx.engine.trace_digest() == mctx.engine.trace_digest()
+    assert np.array_equal(rpipe.encoder.decode(*r), mpipe.encoder.decode(*m))
+    assert np.array_equal(rpipe.inv_mix_columns(*r)[0].v, mpipe.inv_mix_columns(*m)[0].v)
+    assert rctx.engine.trace_digest() == mctx.engine.trace_digest()
