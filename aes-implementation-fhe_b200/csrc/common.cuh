@@ -1,0 +1,79 @@
+// common.cuh -- 64-bit modular arithmetic shared by every kernel of the CKKS engine.
+//
+// All residues are canonical uint64 in [0,q), q < 2^62 (so 4q fits a word and the Harvey lazy
+// butterflies of ntt.cu are safe).  Two multiplication flavours:
+//   * shoup_mul:   x * w mod q for a *precomputed* w with companion w' = floor(w 2^64 / q)
+//                  (1 mul.hi + 2 mul.lo), used for twiddles and per-limb scalars;
+//   * barrett_mul: a * b mod q for two variable operands, single-word Barrett on the
+//                  128-bit product with a per-modulus shift (2 mul.hi + 2 mul.lo).
+// The per-modulus constants live in a small global-memory table (ModConst[], L1/const-cache
+// resident; every CTA works on one limb so the lookups are warp-uniform).
+#pragma once
+#include "platform.cuh"
+
+#define CKKS_MAX_MODULI 64
+
+// per-modulus constants, indexed by global modulus index (q_0..q_L, then p_0..p_{K-1})
+struct ModConst {
+    u64 q;
+    u64 mu;      // floor(2^(k+63)/q), k = bitlen(q): mulhi(z >> (k-1), mu) = floor(z/q) - {0,1,2}
+    u32 k1;      // k - 1
+    u32 pad;
+    u64 ninv;    // N^-1 mod q
+    u64 ninv_s;  // Shoup companion of ninv
+    u64 w1n;     // psi^-bitrev(1) * N^-1 (last inverse-NTT stage twiddle with the 1/N folded in)
+    u64 w1n_s;
+};
+
+// list of modulus indices a batched kernel works on: row r of a [rows][N] array is a residue
+// polynomial modulo mc[idx[r]].  Passed by value (no H2D copy per launch).
+struct LimbList {
+    int n;
+    unsigned char idx[CKKS_MAX_MODULI];
+};
+// per-row scalars with Shoup companions, passed by value
+struct ScalarList {
+    u64 v[CKKS_MAX_MODULI];
+    u64 vs[CKKS_MAX_MODULI];
+};
+
+__device__ __forceinline__ u64 add_mod(u64 a, u64 b, u64 q) {
+    u64 s = a + b;
+    return s >= q ? s - q : s;
+}
+__device__ __forceinline__ u64 sub_mod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+__device__ __forceinline__ u64 neg_mod(u64 a, u64 q) { return a ? q - a : 0; }
+
+// x * w mod q, result in [0, 2q)   (x arbitrary 64-bit, w < q)
+__device__ __forceinline__ u64 shoup_mul_lazy(u64 x, u64 w, u64 ws, u64 q) {
+    u64 h = mulhi64(ws, x);
+    return w * x - h * q;
+}
+__device__ __forceinline__ u64 shoup_mul(u64 x, u64 w, u64 ws, u64 q) {
+    u64 r = shoup_mul_lazy(x, w, ws, q);
+    return r >= q ? r - q : r;
+}
+
+// reduce the 128-bit value z = (hi,lo) with z >> (k-1) < 2^64 to [0,q); up to `8q` of slack is
+// folded by conditional subtractions so sums of a few products (< 16 q^2) are accepted.
+__device__ __forceinline__ u64 barrett_reduce128(u64 hi, u64 lo, const ModConst& m) {
+    u64 x = (lo >> m.k1) | (hi << (64 - m.k1));       // floor(z / 2^(k-1)); k1 in [1,63]
+    u64 qh = mulhi64(x, m.mu);
+    u64 r = lo - qh * m.q;
+    if (r >= 8 * m.q) r -= 8 * m.q;
+    if (r >= 4 * m.q) r -= 4 * m.q;
+    if (r >= 2 * m.q) r -= 2 * m.q;
+    if (r >= m.q) r -= m.q;
+    return r;
+}
+__device__ __forceinline__ u64 barrett_mul(u64 a, u64 b, const ModConst& m) {
+    return barrett_reduce128(mulhi64(a, b), a * b, m);
+}
+// reduce one word x < 2^64 modulo q (via the same Barrett constant)
+__device__ __forceinline__ u64 barrett_reduce64(u64 x, const ModConst& m) { return barrett_reduce128(0, x, m); }
+
+__device__ __forceinline__ void mac128(u64& hi, u64& lo, u64 a, u64 b) {
+    u64 pl = a * b, ph = mulhi64(a, b);
+    lo += pl;
+    hi += ph + (lo < pl);
+}

@@ -1,0 +1,999 @@
+// engine.cu -- host orchestration of the CKKS engine: parameters, tables, keys, encode/encrypt/
+// decrypt, arithmetic with canonical-scale level alignment, hybrid key switching, Galois maps.
+// Restated independently (same written spec) by oracle/ckks_oracle.py, against
+// which every integer result here is checked bit-for-bit.
+#include "engine.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+#include <set>
+
+long g_launch_count = 0;
+#ifdef CKKS_EMU
+thread_local emu_uint3 blockIdx, threadIdx;
+thread_local dim3 blockDim, gridDim;
+#endif
+
+namespace ckks {
+
+typedef unsigned __int128 u128;
+
+// ------------------------------------------------------------------ host modular helpers
+u64 mulmod_h(u64 a, u64 b, u64 q) { return (u64)(((u128)a * b) % q); }
+u64 powmod_h(u64 a, u64 e, u64 q) {
+    u64 r = 1 % q;
+    a %= q;
+    while (e) {
+        if (e & 1) r = mulmod_h(r, a, q);
+        a = mulmod_h(a, a, q);
+        e >>= 1;
+    }
+    return r;
+}
+u64 invmod_h(u64 a, u64 q) { return powmod_h(a % q, q - 2, q); }
+u64 shoup_h(u64 w, u64 q) { return (u64)((((u128)w) << 64) / q); }
+static u64 mix64_h(u64 z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+u64 rand64_h(u64 seed, u64 stream, u64 idx) { return mix64_h(mix64_h(seed + stream * 0xD1342543DE82EF95ull) + idx); }
+static u64 bitrev_h(u64 x, int bits) {
+    u64 r = 0;
+    for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+}
+static u64 stream_id(u64 kind, u64 a = 0, u64 b = 0) { return (kind << 48) | (a << 16) | b; }
+enum { ST_SK = 1, ST_PK_A, ST_PK_E, ST_EVK_A, ST_EVK_E, ST_ENC_V, ST_ENC_E0, ST_ENC_E1 };
+
+// ------------------------------------------------------------------ prime chain (spec S1)
+static bool is_prime_h(u64 n) {
+    if (n < 2) return false;
+    static const u64 small[] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37};
+    for (u64 p : small)
+        if (n % p == 0) return n == p;
+    u64 d = n - 1;
+    int r = 0;
+    while ((d & 1) == 0) { d >>= 1; r++; }
+    for (u64 a : small) {   // deterministic for n < 3.3e24
+        u64 x = powmod_h(a, d, n);
+        if (x == 1 || x == n - 1) continue;
+        bool comp = true;
+        for (int i = 0; i < r - 1; i++) {
+            x = mulmod_h(x, x, n);
+            if (x == n - 1) { comp = false; break; }
+        }
+        if (comp) return false;
+    }
+    return true;
+}
+static std::vector<u64> primes_below(u64 bound, u64 step, int count, std::set<u64>& used) {
+    std::vector<u64> out;
+    u64 c = (bound - 2) / step * step + 1;
+    while ((int)out.size() < count) {
+        if (!used.count(c) && is_prime_h(c)) { out.push_back(c); used.insert(c); }
+        c -= step;
+    }
+    return out;
+}
+static u64 prime_nearest(double target, u64 step, std::set<u64>& used) {
+    const i64 k0 = (i64)nearbyint((target - 1.0) / (double)step);
+    for (i64 d = 0; d < (1 << 20); d++) {
+        for (int s = 0; s < (d ? 2 : 1); s++) {
+            const i64 k = s == 0 ? k0 - d : k0 + d;
+            if (k <= 0) continue;
+            const u64 c = (u64)k * step + 1;
+            if (c > 2 && !used.count(c) && is_prime_h(c)) { used.insert(c); return c; }
+        }
+    }
+    throw std::runtime_error("no prime found");
+}
+static std::vector<double> canonical_scales(const std::vector<u64>& q, int scale_bits) {
+    const int L = (int)q.size() - 1;
+    std::vector<double> s(L + 1);
+    s[L] = ldexp(1.0, scale_bits);
+    for (int l = L; l >= 1; l--) s[l - 1] = s[l] * s[l] / (double)q[l];
+    return s;
+}
+
+Params default_params(int logn, int levels, int scale_bits, int q0_bits, int p_bits, int dnum, int hamming,
+                      int fresh_level) {
+    Params P;
+    P.logn = logn;
+    P.scale_bits = scale_bits;
+    P.hamming = hamming;
+    const u64 step = 2ull << logn;
+    std::set<u64> used;
+    const int nq = levels + 1;
+    P.alpha = (nq + dnum - 1) / dnum;
+    const int digit_bits = q0_bits + (P.alpha - 1) * scale_bits;
+    const int K = (digit_bits + 1 + (p_bits - 1) - 1) / (p_bits - 1);
+    P.p = primes_below(1ull << p_bits, step, K, used);
+    P.q.assign(nq, 0);
+    P.q[0] = primes_below(1ull << q0_bits, step, 1, used)[0];
+    const double delta = ldexp(1.0, scale_bits);
+    double s = delta;
+    for (int l = levels; l >= 1; l--) {
+        const double target = s * s / delta;
+        P.q[l] = prime_nearest(target, step, used);
+        s = s * s / (double)P.q[l];
+    }
+    P.fresh_level = fresh_level < 0 ? levels : std::min(fresh_level, levels);
+    return P;
+}
+
+// ------------------------------------------------------------------ construction
+static u64 find_psi(u64 q, int logn) {
+    const u64 twoN = 2ull << logn, N = 1ull << logn;
+    for (u64 x = 2;; x++) {
+        const u64 r = powmod_h(x, (q - 1) / twoN, q);
+        if (powmod_h(r, N, q) == q - 1) return r;
+    }
+}
+
+template <typename T>
+static T* upload(Engine* E, const std::vector<T>& h, std::vector<void*>& owned) {
+    T* d = (T*)dev::alloc(h.size() * sizeof(T), E->st);
+    dev::h2d(d, h.data(), h.size() * sizeof(T), E->st);
+    dev::sync(E->st);
+    owned.push_back(d);
+    return d;
+}
+
+Engine::Engine(const Params& P) : prm(P) {
+    if (prm.logn != 16 && prm.logn != 12) throw std::runtime_error("engine: logn must be 16 (or 12 for tests)");
+    if (prm.q.empty() || prm.p.empty()) throw std::runtime_error("engine: empty modulus chain");
+    dev::set_device(prm.device);
+    dev::pool_setup(prm.device);
+    st = dev::stream_create();
+    mod = prm.q;
+    mod.insert(mod.end(), prm.p.begin(), prm.p.end());
+    if ((int)mod.size() > CKKS_MAX_MODULI) throw std::runtime_error("engine: too many moduli");
+    if (prm.alpha > BC_MAX_SRC || K() > BC_MAX_SRC) throw std::runtime_error("engine: digit too wide");
+    if (L() + 1 + K() > BC_MAX_TGT) throw std::runtime_error("engine: too many conversion targets");
+    if ((dnum()) > NTT_MAX_Z) throw std::runtime_error("engine: dnum too large");
+    scales = canonical_scales(prm.q, prm.scale_bits);
+    const size_t n = N();
+    const int nm = nmod();
+    std::vector<ModConst> mc(nm);
+    std::vector<u64> fwd((size_t)nm * n), fwd_s((size_t)nm * n), inv((size_t)nm * n), inv_s((size_t)nm * n);
+    psi.resize(nm);
+    Jroot.resize(nm);
+    for (int i = 0; i < nm; i++) {
+        const u64 q = mod[i];
+        if (q >> 61) throw std::runtime_error("engine: moduli must be below 2^61");
+        if ((q - 1) % (2 * n)) throw std::runtime_error("engine: modulus is not 1 mod 2N");
+        psi[i] = find_psi(q, prm.logn);
+        Jroot[i] = powmod_h(psi[i], n / 2, q);
+        const u64 ipsi = invmod_h(psi[i], q);
+        u64 pw = 1, ipw = 1;
+        u64 *F = &fwd[(size_t)i * n], *Fs = &fwd_s[(size_t)i * n], *I = &inv[(size_t)i * n], *Is = &inv_s[(size_t)i * n];
+        for (size_t e = 0; e < n; e++) {
+            const size_t k = bitrev_h(e, prm.logn);
+            F[k] = pw; Fs[k] = shoup_h(pw, q);
+            I[k] = ipw; Is[k] = shoup_h(ipw, q);
+            pw = mulmod_h(pw, psi[i], q);
+            ipw = mulmod_h(ipw, ipsi, q);
+        }
+        ModConst& m = mc[i];
+        m.q = q;
+        int k = 64 - __builtin_clzll(q);
+        m.k1 = k - 1;
+        m.pad = 0;
+        m.mu = (u64)((((u128)1) << (k + 63)) / q);
+        m.ninv = invmod_h(n % q, q);
+        m.ninv_s = shoup_h(m.ninv, q);
+        m.w1n = mulmod_h(I[1], m.ninv, q);
+        m.w1n_s = shoup_h(m.w1n, q);
+    }
+    d_fwd = upload(this, fwd, owned);
+    d_fwd_s = upload(this, fwd_s, owned);
+    d_inv = upload(this, inv, owned);
+    d_inv_s = upload(this, inv_s, owned);
+    d_mc = upload(this, mc, owned);
+    tabs = NttTables{d_fwd, d_fwd_s, d_inv, d_inv_s, d_mc, prm.logn};
+    ks = KShape{d_mc, prm.logn};
+    // canonical-embedding tables (spec S9)
+    const size_t M = 2 * n, ns = n / 2;
+    std::vector<u32> rot(ns);
+    u64 pw = 1;
+    for (size_t j = 0; j < ns; j++) { rot[j] = (u32)pw; pw = (pw * 5) % M; }
+    std::vector<double> ksi(2 * (M + 1));
+    for (size_t k = 0; k <= M; k++) {
+        const double ang = 2.0 * M_PI * (double)k / (double)M;
+        ksi[2 * k] = cos(ang);
+        ksi[2 * k + 1] = sin(ang);
+    }
+    // per-level scalar tables: P^-1 mod q_i, q_l^-1 mod q_i (i < l)
+    {
+        std::vector<int> qi = mods_q(L());
+        std::vector<u64> pinv(L() + 1);
+        for (int i = 0; i <= L(); i++) {
+            u64 pp = 1;
+            for (u64 pk_ : prm.p) pp = mulmod_h(pp, pk_ % mod[i], mod[i]);
+            pinv[i] = invmod_h(pp, mod[i]);
+        }
+        scalar_list(pinv, qi, sl_pinv);
+        sl_qinv.resize(L() + 1);
+        for (int l = 1; l <= L(); l++) {
+            std::vector<int> lo = mods_q(l - 1);
+            std::vector<u64> inv(l);
+            for (int i = 0; i < l; i++) inv[i] = invmod_h(mod[l] % mod[i], mod[i]);
+            scalar_list(inv, lo, sl_qinv[l]);
+        }
+    }
+    d_rot = upload(this, rot, owned);
+    d_ksi = upload(this, ksi, owned);
+    std::vector<int> flag(1, 0);
+    d_flag = upload(this, flag, owned);
+}
+
+Engine::~Engine() {
+    try { dev::sync(st); } catch (...) {}
+    for (auto& kv : gkeys) dev::free(kv.second.d, st);
+    for (auto& kv : perms) dev::free(kv.second, st);
+    for (auto& kv : modup_tabs) { dev::free((void*)kv.second.hat, st); dev::free((void*)kv.second.hat_s, st); }
+    for (auto& kv : moddown_tabs) { dev::free((void*)kv.second.hat, st); dev::free((void*)kv.second.hat_s, st); }
+    dev::free(relin.d, st);
+    dev::free(sk_ntt, st);
+    dev::free(pk, st);
+    for (void* p : owned) dev::free(p, st);
+    boot.reset();
+    try { dev::sync(st); } catch (...) {}
+    dev::stream_destroy(st);
+}
+
+// ------------------------------------------------------------------ memory
+u64* Engine::alloc(size_t words) { return (u64*)dev::alloc(words * sizeof(u64), st); }
+void Engine::release(void* p) { dev::free(p, st); }
+Ct* Engine::new_ct(int npoly, int level) {
+    Ct* c = new Ct();
+    c->npoly = npoly;
+    c->level = level;
+    c->d = alloc((size_t)npoly * (level + 1) * N());
+    return c;
+}
+void Engine::free_ct(Ct* c) {
+    if (!c) return;
+    for (auto& kv : c->lowered) free_ct(kv.second);
+    release(c->d);
+    delete c;
+}
+void Engine::free_pt(Pt* p) {
+    if (!p) return;
+    release(p->d);
+    delete p;
+}
+
+// ------------------------------------------------------------------ limb helpers
+std::vector<int> Engine::mods_q(int level) const {
+    std::vector<int> v(level + 1);
+    for (int i = 0; i <= level; i++) v[i] = i;
+    return v;
+}
+std::vector<int> Engine::mods_qp(int level) const {
+    std::vector<int> v = mods_q(level);
+    for (int k = 0; k < K(); k++) v.push_back(L() + 1 + k);
+    return v;
+}
+LimbList Engine::limb_list(const std::vector<int>& mods) const {
+    LimbList l;
+    memset(&l, 0, sizeof(l));
+    l.n = (int)mods.size();
+    for (int i = 0; i < l.n; i++) l.idx[i] = (unsigned char)mods[i];
+    return l;
+}
+void Engine::scalar_list(const std::vector<u64>& vals, const std::vector<int>& mods, ScalarList& out) const {
+    memset(&out, 0, sizeof(out));
+    for (size_t i = 0; i < mods.size(); i++) {
+        const u64 q = mod[mods[i]];
+        out.v[i] = vals[i] % q;
+        out.vs[i] = shoup_h(out.v[i], q);
+    }
+}
+static u64 signed_residue(i64 x, u64 q) {
+    const u64 r = (u64)(x < 0 ? -(u128)(i64)x : (u128)x) % q;   // |x| < 2^63
+    return (x < 0 && r) ? q - r : r;
+}
+void Engine::const_residues(double re, double im, double scale, const std::vector<int>& mods, ScalarList& cp,
+                            ScalarList& cm) const {
+    const double a = nearbyint(re * scale), b = nearbyint(im * scale);
+    if (!(fabs(a) < 9.0e18) || !(fabs(b) < 9.0e18)) throw std::runtime_error("constant does not fit 63 bits at this scale");
+    const i64 R = (i64)a, I = (i64)b;
+    std::vector<u64> vp(mods.size()), vm(mods.size());
+    for (size_t i = 0; i < mods.size(); i++) {
+        const u64 q = mod[mods[i]];
+        const u64 r = signed_residue(R, q), ij = mulmod_h(signed_residue(I, q), Jroot[mods[i]], q);
+        vp[i] = (r + ij) % q;
+        vm[i] = (r + q - ij) % q;
+    }
+    scalar_list(vp, mods, cp);
+    scalar_list(vm, mods, cm);
+}
+
+void Engine::ntt_rows(u64* data, const std::vector<int>& rows, const std::vector<int>& mods, bool inverse, int nz,
+                      size_t zstride) {
+    if (rows.empty() || nz == 0) return;
+    if (nz > NTT_MAX_Z) {   // split long batches
+        for (int z0 = 0; z0 < nz; z0 += NTT_MAX_Z)
+            ntt_rows(data + z0 * zstride, rows, mods, inverse, std::min(NTT_MAX_Z, nz - z0), zstride);
+        return;
+    }
+    NttJob J;
+    memset(&J, 0, sizeof(J));
+    J.n = (int)rows.size();
+    J.nz = nz;
+    J.szs = J.dzs = zstride;
+    for (int z = 0; z < nz; z++)
+        for (int i = 0; i < J.n; i++) {
+            J.rows[z][i] = J.srows[z][i] = (unsigned char)rows[i];
+            J.mods[z][i] = (unsigned char)mods[i];
+        }
+    if (inverse) ntt_inverse(data, data, J, tabs, st);
+    else ntt_forward(data, data, J, tabs, st);
+    n_ntt_limbs += (long)J.n * nz;
+}
+
+// ------------------------------------------------------------------ Galois maps (spec S4)
+u64 Engine::galois_for_rotation(long steps) const {
+    const long n = (long)slots();
+    long r = steps % n;
+    if (r < 0) r += n;
+    const u64 e = (u64)((n - r) % n);
+    return powmod_h(5, e, 2 * N());
+}
+const u32* Engine::galois_perm(u64 g) {
+    auto it = perms.find(g);
+    if (it != perms.end()) return it->second;
+    const size_t n = N(), M = 2 * n;
+    std::vector<u32> h(n);
+    for (size_t k = 0; k < n; k++) {
+        const u64 e = (2 * bitrev_h(k, prm.logn) + 1) * g % M;
+        h[k] = (u32)bitrev_h((e - 1) / 2, prm.logn);
+    }
+    u32* d = (u32*)dev::alloc(n * sizeof(u32), st);
+    dev::h2d(d, h.data(), n * sizeof(u32), st);
+    dev::sync(st);
+    perms[g] = d;
+    return d;
+}
+void Engine::automorph(u64* out, const u64* in, int rows, int npoly, u64 g) {
+    const size_t stride = (size_t)rows * N();
+    launch_permute(ks, out, in, galois_perm(g), rows, npoly, PolyStride{stride, stride, 0}, st);
+}
+
+// ------------------------------------------------------------------ keys (spec S8)
+void Engine::keygen_secret() {
+    const size_t n = N();
+    const int h = prm.hamming;
+    std::vector<u32> perm(n);
+    sk_coef.assign(n, 0);
+    for (size_t k = 0; k < n; k++) perm[k] = (u32)k;
+    const u64 sid = stream_id(ST_SK);
+    for (int i = 0; i < h; i++) {
+        const u64 j = i + rand64_h(prm.seed, sid, (u64)i) % (n - i);
+        std::swap(perm[i], perm[j]);
+        sk_coef[perm[i]] = (rand64_h(prm.seed, sid, (u64)h + i) & 1) ? 1 : -1;
+    }
+    i64* d_s = (i64*)dev::alloc(n * sizeof(i64), st);
+    dev::h2d(d_s, sk_coef.data(), n * sizeof(i64), st);
+    std::vector<int> all(nmod());
+    for (int i = 0; i < nmod(); i++) all[i] = i;
+    if (!sk_ntt) sk_ntt = alloc((size_t)nmod() * n);
+    launch_reduce_i64(ks, sk_ntt, d_s, limb_list(all), st);
+    ntt_rows(sk_ntt, all, all, false);
+    dev::sync(st);
+    dev::free(d_s, st);
+    has_sk = true;
+}
+
+void Engine::keygen_public() {
+    if (!has_sk) throw std::runtime_error("public key needs a secret key");
+    const size_t n = N();
+    const int nq = L() + 1;
+    std::vector<int> idx = mods_q(L());
+    LimbList ll = limb_list(idx);
+    if (!pk) pk = alloc((size_t)2 * nq * n);
+    u64* b = pk;
+    u64* a = pk + (size_t)nq * n;
+    u64* e = alloc((size_t)nq * n);
+    launch_sample_uniform(ks, a, ll, prm.seed, stream_id(ST_PK_A), st);
+    launch_sample_small(ks, e, ll, prm.seed, stream_id(ST_PK_E), 0, st);
+    ntt_rows(e, idx, idx, false);
+    PolyStride z{0, 0, 0};
+    launch_mul(ks, b, a, sk_ntt, ll, 1, z, st);         // a*s  (sk rows 0..L line up with q rows)
+    launch_sub(ks, b, e, b, ll, 1, z, st);              // e - a*s
+    release(e);
+    has_pk = true;
+}
+
+// evk[j] = (-a_j s + e_j + P * F_j * s_from,  a_j) over Q_L u P; F_j = CRT selector of digit j
+EvalKey Engine::make_switch_key(u64 key_id, const u64* s_from_ntt) {
+    if (!has_sk) throw std::runtime_error("switching key needs a secret key");
+    const size_t n = N();
+    const int rows = nmod();
+    std::vector<int> idx = mods_qp(L());           // == 0..nmod-1
+    LimbList ll = limb_list(idx);
+    const int dn = dnum();
+    EvalKey key;
+    key.d = alloc((size_t)dn * 2 * rows * n);
+    u64* e = alloc((size_t)rows * n);
+    u64* t = alloc((size_t)rows * n);
+    PolyStride z{0, 0, 0};
+    for (int j = 0; j < dn; j++) {
+        u64* b = key.d + ((size_t)j * 2) * rows * n;
+        u64* a = b + (size_t)rows * n;
+        launch_sample_uniform(ks, a, ll, prm.seed, stream_id(ST_EVK_A, key_id, j), st);
+        launch_sample_small(ks, e, ll, prm.seed, stream_id(ST_EVK_E, key_id, j), 0, st);
+        ntt_rows(e, idx, idx, false);
+        launch_mul(ks, b, a, sk_ntt, ll, 1, z, st);
+        launch_sub(ks, b, e, b, ll, 1, z, st);
+        std::vector<u64> fac(rows, 0);
+        for (int i = j * prm.alpha; i < std::min((j + 1) * prm.alpha, L() + 1); i++) {
+            u64 pp = 1;
+            for (u64 pk_ : prm.p) pp = mulmod_h(pp, pk_ % mod[i], mod[i]);
+            fac[i] = pp;
+        }
+        ScalarList sc;
+        scalar_list(fac, idx, sc);
+        launch_mul_scalar(ks, t, s_from_ntt, ll, sc, 1, z, st);
+        launch_add(ks, b, b, t, ll, 1, z, st);
+    }
+    release(e);
+    release(t);
+    return key;
+}
+
+void Engine::keygen_relin() {
+    const size_t n = N();
+    std::vector<int> idx = mods_qp(L());
+    u64* s2 = alloc((size_t)nmod() * n);
+    launch_mul(ks, s2, sk_ntt, sk_ntt, limb_list(idx), 1, PolyStride{0, 0, 0}, st);
+    if (relin.d) release(relin.d);
+    relin = make_switch_key(0, s2);
+    release(s2);
+    has_relin = true;
+}
+
+EvalKey* Engine::galois_key(u64 g) {
+    auto it = gkeys.find(g);
+    if (it != gkeys.end()) return &it->second;
+    u64* sg = alloc((size_t)nmod() * N());
+    automorph(sg, sk_ntt, nmod(), 1, g);
+    EvalKey k = make_switch_key(g, sg);
+    release(sg);
+    gkeys[g] = k;
+    return &gkeys[g];
+}
+
+// ------------------------------------------------------------------ encode / encrypt / decrypt (spec S9, S10)
+void Engine::encode_coeffs_dev(i64* out_dev, const double* z_host, double scale) {
+    const size_t ns = slots();
+    double* z = (double*)dev::alloc(2 * ns * sizeof(double), st);
+    double* w = (double*)dev::alloc(2 * ns * sizeof(double), st);
+    dev::h2d(z, z_host, 2 * ns * sizeof(double), st);
+    launch_special_ifft(ks, w, z, d_rot, d_ksi, st);
+    launch_round_coeffs(ks, out_dev, w, scale, d_flag, st);
+    int flag = 0;
+    dev::d2h(&flag, d_flag, sizeof(int), st);
+    dev::sync(st);
+    dev::free(z, st);
+    dev::free(w, st);
+    if (flag) {
+        int zero = 0;
+        dev::h2d(d_flag, &zero, sizeof(int), st);
+        dev::sync(st);
+        throw std::runtime_error("plaintext coefficient does not fit 62 bits");
+    }
+}
+
+Pt* Engine::encode(const double* z, int level) {
+    if (level < 0 || level > L()) throw std::runtime_error("encode: bad level");
+    const size_t n = N();
+    i64* coef = (i64*)dev::alloc(n * sizeof(i64), st);
+    encode_coeffs_dev(coef, z, scales[level]);
+    Pt* p = new Pt();
+    p->level = level;
+    p->d = alloc((size_t)(level + 1) * n);
+    std::vector<int> idx = mods_q(level);
+    launch_reduce_i64(ks, p->d, coef, limb_list(idx), st);
+    ntt_rows(p->d, idx, idx, false);
+    dev::free(coef, st);
+    return p;
+}
+
+Ct* Engine::encrypt(const double* z, int level) {
+    if (!has_pk) throw std::runtime_error("encrypt needs a public key");
+    if (level < 0) level = prm.fresh_level;
+    if (level > L()) throw std::runtime_error("encrypt: bad level");
+    const size_t n = N();
+    const int nl = level + 1, nq = L() + 1;
+    std::vector<int> idx = mods_q(level);
+    LimbList ll = limb_list(idx);
+    i64* coef = (i64*)dev::alloc(n * sizeof(i64), st);
+    encode_coeffs_dev(coef, z, scales[level]);
+    const u64 k = enc_counter++;
+    // t[0] = v, t[1] = e0 + m, t[2] = e1  (coefficient domain), one batched NTT for all three
+    u64* t = alloc((size_t)3 * nl * n);
+    const size_t ps = (size_t)nl * n;
+    launch_sample_small(ks, t, ll, prm.seed, stream_id(ST_ENC_V, k), 1, st);
+    launch_sample_small(ks, t + ps, ll, prm.seed, stream_id(ST_ENC_E0, k), 0, st);
+    launch_sample_small(ks, t + 2 * ps, ll, prm.seed, stream_id(ST_ENC_E1, k), 0, st);
+    u64* m = alloc(ps);
+    launch_reduce_i64(ks, m, coef, ll, st);
+    PolyStride z0{0, 0, 0};
+    launch_add(ks, t + ps, t + ps, m, ll, 1, z0, st);
+    ntt_rows(t, idx, idx, false, 3, ps);
+    Ct* c = new_ct(2, level);
+    // c_k = v * pk_k + t[k+1]
+    launch_mul(ks, c->d, t, pk, ll, 2, PolyStride{ps, 0, (size_t)nq * n}, st);
+    launch_add(ks, c->d, c->d, t + ps, ll, 2, PolyStride{ps, ps, ps}, st);
+    release(t);
+    release(m);
+    dev::free(coef, st);
+    return c;
+}
+
+void Engine::decrypt(const Ct* c, double* z_out) {
+    if (!has_sk) throw std::runtime_error("decrypt needs a secret key");
+    const size_t n = N(), ns = slots();
+    const size_t ps = (size_t)(c->level + 1) * n;
+    std::vector<int> idx{0};
+    LimbList ll = limb_list(idx);
+    PolyStride z0{0, 0, 0};
+    u64* t = alloc(n);
+    u64* sp = alloc(n);
+    u64* tmp = alloc(n);
+    dev::d2d(t, c->d, n * sizeof(u64), st);
+    dev::d2d(sp, sk_ntt, n * sizeof(u64), st);
+    for (int k = 1; k < c->npoly; k++) {
+        launch_mul(ks, tmp, c->d + k * ps, sp, ll, 1, z0, st);
+        launch_add(ks, t, t, tmp, ll, 1, z0, st);
+        if (k + 1 < c->npoly) launch_mul(ks, sp, sp, sk_ntt, ll, 1, z0, st);
+    }
+    ntt_rows(t, idx, idx, true);
+    double* w = (double*)dev::alloc(2 * ns * sizeof(double), st);
+    double* zz = (double*)dev::alloc(2 * ns * sizeof(double), st);
+    launch_center_to_w(ks, w, t, 0, scales[c->level], st);
+    launch_special_fft(ks, zz, w, d_rot, d_ksi, st);
+    dev::d2h(z_out, zz, 2 * ns * sizeof(double), st);
+    dev::sync(st);
+    release(t); release(sp); release(tmp);
+    dev::free(w, st); dev::free(zz, st);
+}
+
+// ------------------------------------------------------------------ basis conversion tables (spec S5)
+BaseConvTable Engine::make_bc_table(const std::vector<int>& src, const std::vector<int>& srow,
+                                    const std::vector<int>& tgt, const std::vector<int>& orow) {
+    BaseConvTable T;
+    memset(&T, 0, sizeof(T));
+    T.ns = (int)src.size();
+    T.nt = (int)tgt.size();
+    std::vector<u64> hat((size_t)T.ns * T.nt), hat_s((size_t)T.ns * T.nt);
+    for (int i = 0; i < T.ns; i++) {
+        T.src[i] = (unsigned char)src[i];
+        T.srow[i] = (unsigned char)srow[i];
+        const u64 qi = mod[src[i]];
+        u64 prod = 1;
+        for (int j = 0; j < T.ns; j++)
+            if (j != i) prod = mulmod_h(prod, mod[src[j]] % qi, qi);
+        T.hatinv[i] = invmod_h(prod, qi);
+        T.hatinv_s[i] = shoup_h(T.hatinv[i], qi);
+        for (int t = 0; t < T.nt; t++) {
+            const u64 qt = mod[tgt[t]];
+            u64 pr = 1;
+            for (int j = 0; j < T.ns; j++)
+                if (j != i) pr = mulmod_h(pr, mod[src[j]] % qt, qt);
+            hat[(size_t)i * T.nt + t] = pr;
+            hat_s[(size_t)i * T.nt + t] = shoup_h(pr, qt);
+        }
+    }
+    for (int t = 0; t < T.nt; t++) { T.tgt[t] = (unsigned char)tgt[t]; T.orow[t] = (unsigned char)orow[t]; }
+    u64* dh = alloc(hat.size());
+    u64* dhs = alloc(hat.size());
+    dev::h2d(dh, hat.data(), hat.size() * sizeof(u64), st);
+    dev::h2d(dhs, hat_s.data(), hat.size() * sizeof(u64), st);
+    dev::sync(st);
+    T.hat = dh;
+    T.hat_s = dhs;
+    return T;
+}
+
+// digit j of level `level`: source rows j*alpha.. in the coefficient buffer [level+1][N]; targets are
+// every other modulus of Q_level u P, written to row (its position in mods_qp(level)) of ext[j]
+const BaseConvTable& Engine::modup_table(int level, int digit) {
+    auto key = std::make_pair(level, digit);
+    auto it = modup_tabs.find(key);
+    if (it != modup_tabs.end()) return it->second;
+    std::vector<int> qp = mods_qp(level);
+    std::vector<int> src, srow, tgt, orow;
+    const int lo = digit * prm.alpha, hi = std::min((digit + 1) * prm.alpha, level + 1);
+    for (int i = lo; i < hi; i++) { src.push_back(i); srow.push_back(i); }
+    for (int r = 0; r < (int)qp.size(); r++)
+        if (qp[r] < lo || qp[r] >= hi) { tgt.push_back(qp[r]); orow.push_back(r); }
+    modup_tabs[key] = make_bc_table(src, srow, tgt, orow);
+    return modup_tabs[key];
+}
+// P -> Q_level: sources are rows level+1.. of the accumulator, targets rows 0..level of the output
+const BaseConvTable& Engine::moddown_table(int level) {
+    auto it = moddown_tabs.find(level);
+    if (it != moddown_tabs.end()) return it->second;
+    std::vector<int> src, srow, tgt, orow;
+    for (int k = 0; k < K(); k++) { src.push_back(L() + 1 + k); srow.push_back(level + 1 + k); }
+    for (int i = 0; i <= level; i++) { tgt.push_back(i); orow.push_back(i); }
+    moddown_tabs[level] = make_bc_table(src, srow, tgt, orow);
+    return moddown_tabs[level];
+}
+
+// ------------------------------------------------------------------ hybrid key switching (spec S5, S6)
+Decomp Engine::decompose(const u64* d, int level) {
+    const size_t n = N();
+    const int nq = level + 1, rows = nq + K();
+    const int beta = (nq + prm.alpha - 1) / prm.alpha;
+    Decomp D;
+    D.level = level;
+    D.beta = beta;
+    D.ext = alloc((size_t)beta * rows * n);
+    // coefficient form of all q-limbs
+    u64* coef = alloc((size_t)nq * n);
+    {
+        NttJob J;
+        memset(&J, 0, sizeof(J));
+        J.n = nq; J.nz = 1;
+        for (int i = 0; i < nq; i++) { J.rows[0][i] = J.srows[0][i] = (unsigned char)i; J.mods[0][i] = (unsigned char)i; }
+        ntt_inverse(d, coef, J, tabs, st);
+        n_ntt_limbs += nq;
+    }
+    // per digit: fast basis conversion of its limbs to every other modulus of Q_level u P; the
+    // digit's own limbs are copied from the NTT-domain input
+    NttJob J;
+    memset(&J, 0, sizeof(J));
+    J.nz = beta;
+    J.szs = J.dzs = (size_t)rows * n;
+    for (int j = 0; j < beta; j++) {
+        const BaseConvTable& T = modup_table(level, j);
+        launch_base_convert(ks, D.ext + (size_t)j * rows * n, coef, T, 1, 0, 0, st);
+        const int lo = j * prm.alpha, hi = std::min((j + 1) * prm.alpha, nq);
+        dev::d2d(D.ext + ((size_t)j * rows + lo) * n, d + (size_t)lo * n, (size_t)(hi - lo) * n * sizeof(u64), st);
+        J.n = std::max(J.n, T.nt);
+        J.cnt[j] = (unsigned char)T.nt;
+        for (int t = 0; t < T.nt; t++) {
+            J.rows[j][t] = J.srows[j][t] = T.orow[t];
+            J.mods[j][t] = T.tgt[t];
+        }
+        n_ntt_limbs += T.nt;
+    }
+    // one batched forward NTT over the converted rows of all digits (z = digit)
+    ntt_forward(D.ext, D.ext, J, tabs, st);
+    release(coef);
+    return D;
+}
+
+void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out) {
+    const size_t n = N();
+    const int level = D.level, nq = level + 1, rows = nq + K();
+    std::vector<int> qp = mods_qp(level);
+    LimbList ll = limb_list(qp);
+    LimbList er = limb_list(qp);                 // evk rows are indexed by global modulus index
+    u64* acc = alloc((size_t)2 * rows * n);
+    launch_ks_inner(ks, acc, D.ext, evk->d, perm, ll, er, D.beta, nmod(), st);
+    // ModDown: floor(acc / P)
+    std::vector<int> prow, pmod;
+    for (int k = 0; k < K(); k++) { prow.push_back(nq + k); pmod.push_back(L() + 1 + k); }
+    ntt_rows(acc, prow, pmod, true, 2, (size_t)rows * n);
+    u64* conv = alloc((size_t)2 * nq * n);
+    launch_base_convert(ks, conv, acc, moddown_table(level), 2, (size_t)rows * n, (size_t)nq * n, st);
+    std::vector<int> qi = mods_q(level);
+    ntt_rows(conv, qi, qi, false, 2, (size_t)nq * n);
+    launch_sub_mul_scalar(ks, out, acc, conv, limb_list(qi), sl_pinv, 2,
+                          PolyStride{(size_t)nq * n, (size_t)rows * n, (size_t)nq * n}, st);
+    release(acc);
+    release(conv);
+    n_keyswitch++;
+}
+
+void Engine::key_switch(const u64* d, int level, const EvalKey* evk, u64* out) {
+    Decomp D = decompose(d, level);
+    ks_apply(D, evk, nullptr, out);
+    release(D.ext);
+}
+
+// ------------------------------------------------------------------ rescale / level management (spec S6)
+void Engine::need_levels(int level, int need, const char* what) const {
+    if (level < need)
+        throw LevelError(std::string(what) + ": ciphertext level should be positive for multiplication (level " +
+                         std::to_string(level) + ", need " + std::to_string(need) + ")");
+}
+
+// in: [npoly][level+1][N] -> out: [npoly][level][N]
+void Engine::rescale_into(u64* out, const u64* in, int npoly, int level) {
+    const size_t n = N();
+    const int nl = level + 1;
+    u64* last = alloc((size_t)npoly * n);
+    {
+        NttJob J;
+        memset(&J, 0, sizeof(J));
+        J.n = 1; J.nz = npoly;
+        J.szs = (size_t)nl * n;
+        J.dzs = n;
+        for (int z = 0; z < npoly; z++) { J.srows[z][0] = (unsigned char)level; J.rows[z][0] = 0; J.mods[z][0] = (unsigned char)level; }
+        if (npoly > NTT_MAX_Z) throw std::runtime_error("rescale: too many polynomials");
+        ntt_inverse(in, last, J, tabs, st);
+        n_ntt_limbs += npoly;
+    }
+    std::vector<int> lo = mods_q(level - 1);
+    LimbList ll = limb_list(lo);
+    u64* delta = alloc((size_t)npoly * level * n);
+    launch_rescale_delta(ks, delta, last, ll, level, npoly, PolyStride{(size_t)level * n, n, 0}, st);
+    ntt_rows(delta, lo, lo, false, npoly, (size_t)level * n);
+    launch_sub_mul_scalar(ks, out, in, delta, ll, sl_qinv[level], npoly,
+                          PolyStride{(size_t)level * n, (size_t)nl * n, (size_t)level * n}, st);
+    release(last);
+    release(delta);
+    n_rescale++;
+}
+
+Ct* Engine::rescale(const Ct* c) {
+    need_levels(c->level, 1, "rescale");
+    Ct* r = new_ct(c->npoly, c->level - 1);
+    rescale_into(r->d, c->d, c->npoly, c->level);
+    return r;
+}
+
+Ct* Engine::drop_to(const Ct* a, int level) {
+    if (level > a->level) throw std::runtime_error("drop_to: cannot raise a level");
+    const size_t n = N();
+    Ct* r = new_ct(a->npoly, level);
+    for (int k = 0; k < a->npoly; k++)
+        dev::d2d(r->d + (size_t)k * (level + 1) * n, a->d + (size_t)k * (a->level + 1) * n,
+                 (size_t)(level + 1) * n * sizeof(u64), st);
+    return r;
+}
+
+Ct* Engine::copy(const Ct* a) { return drop_to(a, a->level); }
+
+// canonical-scale alignment: drop to target+1, multiply by round(S_t q_{t+1} / S_l), rescale
+Ct* Engine::level_down(Ct* c, int target) {
+    if (target == c->level) return c;
+    if (target > c->level || target < 0) throw std::runtime_error("level_down: bad target");
+    for (auto& kv : c->lowered)
+        if (kv.first == target) return kv.second;
+    const size_t n = N();
+    const int t1 = target + 1;
+    std::vector<int> idx = mods_q(t1);
+    const double kf = nearbyint(scales[target] * (double)mod[t1] / scales[c->level]);
+    const u64 k = (u64)kf;
+    std::vector<u64> kv(idx.size(), k);
+    ScalarList sc;
+    scalar_list(kv, idx, sc);
+    u64* tmp = alloc((size_t)c->npoly * (t1 + 1) * n);
+    launch_mul_scalar(ks, tmp, c->d, limb_list(idx), sc, c->npoly,
+                      PolyStride{(size_t)(t1 + 1) * n, (size_t)(c->level + 1) * n, 0}, st);
+    Ct* r = new_ct(c->npoly, target);
+    rescale_into(r->d, tmp, c->npoly, t1);
+    release(tmp);
+    c->lowered.push_back(std::make_pair(target, r));
+    return r;
+}
+
+// ------------------------------------------------------------------ homomorphic ops
+Ct* Engine::add(Ct* a, Ct* b) {
+    const int l = std::min(a->level, b->level);
+    a = level_down(a, l);
+    b = level_down(b, l);
+    const size_t ps = (size_t)(l + 1) * N();
+    const int np = std::max(a->npoly, b->npoly), nmin = std::min(a->npoly, b->npoly);
+    Ct* r = new_ct(np, l);
+    launch_add(ks, r->d, a->d, b->d, limb_list(mods_q(l)), nmin, PolyStride{ps, ps, ps}, st);
+    if (np > nmin) {
+        const Ct* big = a->npoly > b->npoly ? a : b;
+        dev::d2d(r->d + nmin * ps, big->d + nmin * ps, (np - nmin) * ps * sizeof(u64), st);
+    }
+    return r;
+}
+Ct* Engine::sub(Ct* a, Ct* b) {
+    const int l = std::min(a->level, b->level);
+    a = level_down(a, l);
+    b = level_down(b, l);
+    const size_t ps = (size_t)(l + 1) * N();
+    const int np = std::max(a->npoly, b->npoly), nmin = std::min(a->npoly, b->npoly);
+    Ct* r = new_ct(np, l);
+    LimbList ll = limb_list(mods_q(l));
+    launch_sub(ks, r->d, a->d, b->d, ll, nmin, PolyStride{ps, ps, ps}, st);
+    if (np > nmin) {
+        if (a->npoly > b->npoly) dev::d2d(r->d + nmin * ps, a->d + nmin * ps, (np - nmin) * ps * sizeof(u64), st);
+        else launch_neg(ks, r->d + nmin * ps, b->d + nmin * ps, ll, np - nmin, PolyStride{ps, ps, 0}, st);
+    }
+    return r;
+}
+Ct* Engine::negate(const Ct* a) {
+    const size_t ps = (size_t)(a->level + 1) * N();
+    Ct* r = new_ct(a->npoly, a->level);
+    launch_neg(ks, r->d, a->d, limb_list(mods_q(a->level)), a->npoly, PolyStride{ps, ps, 0}, st);
+    return r;
+}
+
+Ct* Engine::mul_norelin(Ct* a, Ct* b) {
+    if (a->npoly != 2 || b->npoly != 2) throw PolyCountError("multiply: operands should have 2 polynomials");
+    const int l = std::min(a->level, b->level);
+    need_levels(l, 1, "multiply");
+    a = level_down(a, l);
+    b = level_down(b, l);
+    const size_t n = N();
+    u64* t = alloc((size_t)3 * (l + 1) * n);
+    launch_tensor(ks, t, a->d, b->d, limb_list(mods_q(l)), st);
+    Ct* r = new_ct(3, l - 1);
+    rescale_into(r->d, t, 3, l);
+    release(t);
+    return r;
+}
+
+Ct* Engine::relinearize(const Ct* t) {
+    if (t->npoly != 3) throw PolyCountError("relinearize: ciphertext should have 3 polynomials");
+    if (!has_relin) throw std::runtime_error("relinearize needs a relinearisation key");
+    const int l = t->level;
+    const size_t ps = (size_t)(l + 1) * N();
+    Ct* r = new_ct(2, l);
+    key_switch(t->d + 2 * ps, l, &relin, r->d);
+    launch_add(ks, r->d, r->d, t->d, limb_list(mods_q(l)), 2, PolyStride{ps, ps, ps}, st);
+    return r;
+}
+
+Ct* Engine::mul(Ct* a, Ct* b) {
+    if (a->npoly != 2 || b->npoly != 2) throw PolyCountError("multiply: operands should have 2 polynomials");
+    if (!has_relin) throw std::runtime_error("multiply needs a relinearisation key");
+    const int l = std::min(a->level, b->level);
+    need_levels(l, 1, "multiply");
+    a = level_down(a, l);
+    b = level_down(b, l);
+    const size_t n = N(), ps = (size_t)(l + 1) * n;
+    LimbList ll = limb_list(mods_q(l));
+    u64* t = alloc(3 * ps);
+    launch_tensor(ks, t, a->d, b->d, ll, st);
+    u64* k2 = alloc(2 * ps);
+    key_switch(t + 2 * ps, l, &relin, k2);
+    launch_add(ks, k2, k2, t, ll, 2, PolyStride{ps, ps, ps}, st);
+    Ct* r = new_ct(2, l - 1);
+    rescale_into(r->d, k2, 2, l);
+    release(t);
+    release(k2);
+    n_mul_cc++;
+    return r;
+}
+
+Ct* Engine::mul_const(const Ct* a, double re, double im) {
+    need_levels(a->level, 1, "multiply");
+    const int l = a->level;
+    const size_t ps = (size_t)(l + 1) * N();
+    std::vector<int> idx = mods_q(l);
+    ScalarList cp, cm;
+    const_residues(re, im, scales[l], idx, cp, cm);
+    u64* t = alloc((size_t)a->npoly * ps);
+    launch_mul_const(ks, t, a->d, limb_list(idx), cp, cm, a->npoly, PolyStride{ps, ps, 0}, st);
+    Ct* r = new_ct(a->npoly, l - 1);
+    rescale_into(r->d, t, a->npoly, l);
+    release(t);
+    return r;
+}
+
+Ct* Engine::mul_plain(const Ct* a, const Pt* p) {
+    need_levels(a->level, 1, "multiply");
+    if (p->level != a->level) throw std::runtime_error("mul_plain: plaintext must be encoded at the ciphertext level");
+    const int l = a->level;
+    const size_t ps = (size_t)(l + 1) * N();
+    u64* t = alloc((size_t)a->npoly * ps);
+    launch_mul(ks, t, a->d, p->d, limb_list(mods_q(l)), a->npoly, PolyStride{ps, ps, 0}, st);
+    Ct* r = new_ct(a->npoly, l - 1);
+    rescale_into(r->d, t, a->npoly, l);
+    release(t);
+    return r;
+}
+
+Ct* Engine::mul_i(const Ct* a, int sign) {
+    const int l = a->level;
+    const size_t ps = (size_t)(l + 1) * N();
+    std::vector<int> idx = mods_q(l);
+    std::vector<u64> vp(idx.size()), vm(idx.size());
+    for (size_t i = 0; i < idx.size(); i++) {
+        const u64 q = mod[idx[i]], j = Jroot[idx[i]];
+        vp[i] = sign >= 0 ? j : q - j;
+        vm[i] = sign >= 0 ? q - j : j;
+    }
+    ScalarList cp, cm;
+    scalar_list(vp, idx, cp);
+    scalar_list(vm, idx, cm);
+    Ct* r = new_ct(a->npoly, l);
+    launch_mul_const(ks, r->d, a->d, limb_list(idx), cp, cm, a->npoly, PolyStride{ps, ps, 0}, st);
+    return r;
+}
+
+Ct* Engine::add_const(const Ct* a, double re, double im) {
+    const int l = a->level;
+    const size_t ps = (size_t)(l + 1) * N();
+    std::vector<int> idx = mods_q(l);
+    ScalarList cp, cm;
+    const_residues(re, im, scales[l], idx, cp, cm);
+    Ct* r = new_ct(a->npoly, l);
+    launch_add_const(ks, r->d, a->d, limb_list(idx), cp, cm, st);
+    dev::d2d(r->d + ps, a->d + ps, (size_t)(a->npoly - 1) * ps * sizeof(u64), st);
+    return r;
+}
+
+Ct* Engine::add_plain(const Ct* a, const Pt* p) {
+    if (p->level != a->level) throw std::runtime_error("add_plain: plaintext must be encoded at the ciphertext level");
+    const int l = a->level;
+    const size_t ps = (size_t)(l + 1) * N();
+    Ct* r = new_ct(a->npoly, l);
+    launch_add(ks, r->d, a->d, p->d, limb_list(mods_q(l)), 1, PolyStride{0, 0, 0}, st);
+    dev::d2d(r->d + ps, a->d + ps, (size_t)(a->npoly - 1) * ps * sizeof(u64), st);
+    return r;
+}
+
+Ct* Engine::apply_galois(const Ct* a, u64 g) {
+    if (a->npoly != 2) throw PolyCountError("rotate/conjugate: ciphertext should have 2 polynomials");
+    const int l = a->level;
+    const size_t ps = (size_t)(l + 1) * N();
+    EvalKey* key = galois_key(g);
+    u64* t = alloc(2 * ps);
+    automorph(t, a->d, l + 1, 2, g);
+    Ct* r = new_ct(2, l);
+    key_switch(t + ps, l, key, r->d);
+    launch_add(ks, r->d, r->d, t, limb_list(mods_q(l)), 1, PolyStride{0, 0, 0}, st);
+    release(t);
+    return r;
+}
+Ct* Engine::rotate(const Ct* a, long steps) {
+    const long n = (long)slots();
+    if (((steps % n) + n) % n == 0) return copy(a);
+    return apply_galois(a, galois_for_rotation(steps));
+}
+Ct* Engine::conjugate(const Ct* a) { return apply_galois(a, galois_conj()); }
+
+// hoisted rotations: one ModUp of c1, then per step the Galois gather is fused into the inner product
+std::vector<Ct*> Engine::rotate_hoisted(const Ct* a, const std::vector<long>& steps) {
+    if (a->npoly != 2) throw PolyCountError("rotate: ciphertext should have 2 polynomials");
+    const int l = a->level;
+    const size_t ps = (size_t)(l + 1) * N();
+    const long n = (long)slots();
+    std::vector<Ct*> out;
+    Decomp D;
+    bool have = false;
+    LimbList ll = limb_list(mods_q(l));
+    for (long s : steps) {
+        if (((s % n) + n) % n == 0) { out.push_back(copy(a)); continue; }
+        if (!have) { D = decompose(a->d + ps, l); have = true; }
+        const u64 g = galois_for_rotation(s);
+        EvalKey* key = galois_key(g);
+        const u32* perm = galois_perm(g);
+        Ct* r = new_ct(2, l);
+        ks_apply(D, key, perm, r->d);
+        u64* t = alloc(ps);
+        automorph(t, a->d, l + 1, 1, g);
+        launch_add(ks, r->d, r->d, t, ll, 1, PolyStride{0, 0, 0}, st);
+        release(t);
+        out.push_back(r);
+    }
+    if (have) release(D.ext);
+    return out;
+}
+
+// [a^1 .. a^degree], a^k = a^(k//2) * a^((k+1)//2)  (depth ceil(log2 k))
+std::vector<Ct*> Engine::power_basis(Ct* a, int degree) {
+    if (degree < 1) throw std::runtime_error("make_power_basis: degree must be positive");
+    int depth = 0;
+    while ((1 << depth) < degree) depth++;
+    need_levels(a->level, depth, "make_power_basis");
+    std::vector<Ct*> out;
+    out.push_back(copy(a));
+    try {
+        for (int k = 2; k <= degree; k++) out.push_back(mul(out[k / 2 - 1], out[(k + 1) / 2 - 1]));
+    } catch (...) {
+        for (Ct* c : out) free_ct(c);
+        throw;
+    }
+    return out;
+}
+
+}  // namespace ckks

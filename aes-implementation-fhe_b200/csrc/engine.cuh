@@ -1,0 +1,212 @@
+// engine.cuh -- host-side CKKS evaluation engine driving the sm_100a kernels.
+//
+// One Engine per GPU, one CUDA stream per Engine; every operation is enqueued asynchronously
+// and is out-of-place (inputs are immutable: the reference callers alias ciphertexts freely,
+// SURVEY.md 8b).  Polynomials live in HBM as [limb][N] uint64 residues in the NTT domain
+// (bit-reversed order); a ciphertext is [npoly][level+1][N] contiguous.  Scratch and results
+// come from the stream-ordered CUDA memory pool (no cudaMalloc on the hot path).
+//
+// Scale policy (DESIGN.md spec S1): one canonical scale per level, S[L] = 2^scale_bits,
+// S[l-1] = S[l]^2 / q_l.  Every ciphertext at level l has exactly scale S[l]; plaintext operands
+// of a multiplication are encoded at S[l] so the rescaled product lands on S[l-1]; operands of
+// different levels are aligned by level_down() (limb drop + one integer multiply + one rescale).
+#pragma once
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "ntt.cuh"
+
+namespace ckks {
+
+// error classes the C ABI maps to status codes (and the Python shim to RuntimeError strings,
+// reference engine_context.py:139-145,184-195)
+struct LevelError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct FormError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct PolyCountError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+struct Ct {
+    int npoly = 2;
+    int level = 0;
+    u64* d = nullptr;                               // [npoly][level+1][N], NTT domain
+    std::vector<std::pair<int, Ct*>> lowered;       // memoised level_down() results (owned)
+};
+struct Pt {
+    int level = 0;
+    u64* d = nullptr;                               // [level+1][N], NTT domain, scale S[level]
+};
+struct EvalKey {
+    u64* d = nullptr;                               // [dnum][2][L+1+K][N]
+};
+// ModUp result: every digit of a polynomial extended to Q_level u P, NTT domain
+struct Decomp {
+    int level = 0, beta = 0;
+    u64* ext = nullptr;                             // [beta][level+1+K][N]
+};
+
+struct BootParams {
+    int enabled = 0;
+    int cts_groups = 3, stc_groups = 3;             // matrices the (i)DFT is factored into
+    int K = 25;                                     // bound on |I| in t = m + q0 I
+    int cheb_degree = 63;
+    int double_angle = 2;
+};
+
+struct Params {
+    int logn = 16;
+    std::vector<u64> q, p;                          // q_0..q_L ; p_0..p_{K-1}
+    int scale_bits = 50;
+    int alpha = 1;                                  // q-limbs per key-switch digit
+    int hamming = 192;
+    int fresh_level = 0;                            // level of fresh encryptions (<= L)
+    u64 seed = 1;
+    int device = 0;
+    BootParams boot;
+};
+
+// Deterministic prime chain (DESIGN.md spec S1; restated independently in oracle/params.py)
+Params default_params(int logn, int levels, int scale_bits, int q0_bits, int p_bits, int dnum, int hamming,
+                      int fresh_level);
+
+struct BootPlan;   // bootstrap.cu
+
+class Engine {
+  public:
+    explicit Engine(const Params& P);
+    ~Engine();
+    Engine(const Engine&) = delete;
+
+    // ---- parameters
+    int L() const { return (int)prm.q.size() - 1; }
+    int K() const { return (int)prm.p.size(); }
+    int nmod() const { return L() + 1 + K(); }
+    int dnum() const { return (L() + 1 + prm.alpha - 1) / prm.alpha; }
+    size_t N() const { return (size_t)1 << prm.logn; }
+    size_t slots() const { return N() / 2; }
+    double scale_at(int level) const { return scales[level]; }
+    Params prm;
+    std::vector<double> scales;
+    dev_stream st = 0;
+
+    // ---- memory
+    u64* alloc(size_t words);
+    void release(void* p);
+    Ct* new_ct(int npoly, int level);
+    void free_ct(Ct* c);
+    void free_pt(Pt* p);
+    void sync() { dev::sync(st); }
+
+    // ---- keys (spec S8)
+    void keygen_secret();
+    void keygen_public();
+    void keygen_relin();
+    EvalKey* galois_key(u64 g);                 // generated on first use from sk, cached
+    u64 galois_for_rotation(long steps) const;  // rotate(ct,+r) == np.roll(slots,+r)
+    u64 galois_conj() const { return 2ull * N() - 1; }
+    bool has_sk = false, has_pk = false, has_relin = false;
+
+    // ---- encode / encrypt / decrypt (host pointers: interleaved re,im doubles, n = N/2 slots)
+    Pt* encode(const double* z, int level);
+    Ct* encrypt(const double* z, int level);
+    void decrypt(const Ct* c, double* z_out);
+
+    // ---- homomorphic ops (all out of place)
+    Ct* add(Ct* a, Ct* b);
+    Ct* sub(Ct* a, Ct* b);
+    Ct* negate(const Ct* a);
+    Ct* mul(Ct* a, Ct* b);                       // tensor + relinearise + rescale
+    Ct* mul_norelin(Ct* a, Ct* b);               // tensor + rescale, 3 polynomials
+    Ct* relinearize(const Ct* t);                // 3 -> 2 polynomials, same level
+    Ct* rescale(const Ct* c);
+    Ct* level_down(Ct* c, int target);           // memoised on c
+    Ct* mul_const(const Ct* a, double re, double im);   // consumes one level
+    Ct* mul_plain(const Ct* a, const Pt* p);            // consumes one level; p at a.level
+    Ct* mul_i(const Ct* a, int sign);                   // exact multiply by +-i, no level
+    Ct* add_const(const Ct* a, double re, double im);
+    Ct* add_plain(const Ct* a, const Pt* p);
+    Ct* rotate(const Ct* a, long steps);
+    Ct* conjugate(const Ct* a);
+    Ct* apply_galois(const Ct* a, u64 g);
+    std::vector<Ct*> rotate_hoisted(const Ct* a, const std::vector<long>& steps);
+    std::vector<Ct*> power_basis(Ct* a, int degree);
+    Ct* copy(const Ct* a);
+    Ct* lut2(const std::vector<Ct*>& A, const std::vector<Ct*>& B, const int* p, const int* q, const double* coef,
+             int nterms);
+    std::vector<Ct*> lut1(const std::vector<Ct*>& X, const double* coef, int nout);
+    Ct* drop_to(const Ct* a, int level);         // plain limb drop (scale unchanged): internal/bootstrap use
+
+    // ---- bootstrapping (bootstrap.cu)
+    void bootstrap_setup();
+    Ct* bootstrap(Ct* a);
+    int boot_out_level() const;
+    Ct* mod_raise(Ct* a);
+    std::unique_ptr<BootPlan> boot;
+
+    // ---- low-level pieces (exposed through the C ABI for parity tests against the oracle)
+    void ntt_rows(u64* data, const std::vector<int>& rows, const std::vector<int>& mods, bool inverse, int nz = 1,
+                  size_t zstride = 0);
+    Decomp decompose(const u64* d, int level);
+    void ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out /* [2][level+1][N] */);
+    void key_switch(const u64* d, int level, const EvalKey* evk, u64* out);
+    void automorph(u64* out, const u64* in, int rows, int npoly, u64 g);
+    const u32* galois_perm(u64 g);
+    std::vector<int> mods_q(int level) const;
+    std::vector<int> mods_qp(int level) const;
+    LimbList limb_list(const std::vector<int>& mods) const;
+    void const_residues(double re, double im, double scale, const std::vector<int>& mods, ScalarList& cp,
+                        ScalarList& cm) const;
+    void scalar_list(const std::vector<u64>& vals, const std::vector<int>& mods, ScalarList& out) const;
+    const BaseConvTable& modup_table(int level, int digit);
+    const BaseConvTable& moddown_table(int level);
+    const std::vector<i64>& sk_host() const { return sk_coef; }
+    const u64* sk_dev() const { return sk_ntt; }
+    const u64* pk_dev() const { return pk; }
+    const EvalKey* relin_key() const { return &relin; }
+    const std::vector<u64>& moduli() const { return mod; }
+    NttTables tabs{};
+    KShape ks{};
+    long n_keyswitch = 0, n_ntt_limbs = 0, n_rescale = 0, n_mul_cc = 0, n_boot = 0;
+
+  private:
+    std::vector<u64> mod;                  // all moduli, global index
+    std::vector<u64> psi;
+    std::vector<u64> Jroot;                // psi^(N/2)
+    std::vector<i64> sk_coef;
+    u64 *d_fwd = nullptr, *d_fwd_s = nullptr, *d_inv = nullptr, *d_inv_s = nullptr;
+    ModConst* d_mc = nullptr;
+    u64* sk_ntt = nullptr;                 // [nmod][N]
+    u64* pk = nullptr;                     // [2][L+1][N]
+    EvalKey relin;
+    std::map<u64, EvalKey> gkeys;
+    std::map<u64, u32*> perms;
+    std::map<std::pair<int, int>, BaseConvTable> modup_tabs;
+    std::map<int, BaseConvTable> moddown_tabs;
+    std::vector<void*> owned;              // device tables freed in the destructor
+    u32* d_rot = nullptr;
+    double* d_ksi = nullptr;
+    int* d_flag = nullptr;
+    u64 enc_counter = 0;
+    ScalarList sl_pinv;                    // P^-1 mod q_i
+    std::vector<ScalarList> sl_qinv;       // [l]: q_l^-1 mod q_i, i < l
+
+    EvalKey make_switch_key(u64 key_id, const u64* s_from_ntt);
+    BaseConvTable make_bc_table(const std::vector<int>& src, const std::vector<int>& srow,
+                                const std::vector<int>& tgt, const std::vector<int>& orow);
+    void encode_coeffs_dev(i64* out_dev, const double* z_host, double scale);
+    void rescale_into(u64* out, const u64* in, int npoly, int level);
+    void need_levels(int level, int need, const char* what) const;
+};
+
+u64 mulmod_h(u64 a, u64 b, u64 q);
+u64 powmod_h(u64 a, u64 e, u64 q);
+u64 invmod_h(u64 a, u64 q);
+u64 shoup_h(u64 w, u64 q);
+u64 rand64_h(u64 seed, u64 stream, u64 idx);
+
+
+}  // namespace ckks

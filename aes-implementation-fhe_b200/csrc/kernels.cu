@@ -1,0 +1,404 @@
+// kernels.cu -- element-wise, permutation, basis-conversion, sampling and embedding kernels.
+//
+// All RNS kernels work on "limb batches": row r of a [rows][N] uint64 array is a residue
+// polynomial modulo mc[L.idx[r]].  Every kernel is HBM-bound streaming work except
+// base_convert (integer-pipe bound: ns*(nt+1) Shoup multiplications per coefficient).
+// Grids are rows x N/256 CTAs (x npoly); a 22-limb ciphertext gives 11 264 CTAs, i.e. many
+// waves over 148 SMs, and all global accesses are unit-stride 8-byte per lane.
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+// ------------------------------------------------------------------ element-wise
+enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2 };
+// blockIdx.z selects the polynomial; each pointer has its own polynomial stride (elements)
+template <int OP>
+__global__ void k_binop(KShape S, u64* __restrict__ out, const u64* __restrict__ a, const u64* __restrict__ b,
+                        LimbList L, PolyStride ps) {
+    const int row = blockIdx.y;
+    const ModConst m = S.mc[L.idx[row]];
+    FOR_THREADS {
+        const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
+        const u64 x = a[i + blockIdx.z * ps.a], y = b[i + blockIdx.z * ps.b];
+        out[i + blockIdx.z * ps.out] =
+            OP == OP_ADD ? add_mod(x, y, m.q) : OP == OP_SUB ? sub_mod(x, y, m.q) : barrett_mul(x, y, m);
+    }
+}
+__global__ void k_neg(KShape S, u64* __restrict__ out, const u64* __restrict__ a, LimbList L, PolyStride ps) {
+    const int row = blockIdx.y;
+    const u64 q = S.mc[L.idx[row]].q;
+    FOR_THREADS {
+        const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
+        out[i + blockIdx.z * ps.out] = neg_mod(a[i + blockIdx.z * ps.a], q);
+    }
+}
+
+// out[r] = a[r] * s[r]  (per-row scalar with Shoup companion)
+__global__ void k_mul_scalar(KShape S, u64* __restrict__ out, const u64* __restrict__ a, LimbList L, ScalarList Sc,
+                             PolyStride ps) {
+    const int row = blockIdx.y;
+    const u64 q = S.mc[L.idx[row]].q;
+    FOR_THREADS {
+        const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
+        out[i + blockIdx.z * ps.out] = shoup_mul(a[i + blockIdx.z * ps.a], Sc.v[row], Sc.vs[row], q);
+    }
+}
+
+// out[r] = (a[r] - b[r]) * s[r]
+__global__ void k_sub_mul_scalar(KShape S, u64* __restrict__ out, const u64* __restrict__ a,
+                                 const u64* __restrict__ b, LimbList L, ScalarList Sc, PolyStride ps) {
+    const int row = blockIdx.y;
+    const u64 q = S.mc[L.idx[row]].q;
+    FOR_THREADS {
+        const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
+        out[i + blockIdx.z * ps.out] =
+            shoup_mul(sub_mod(a[i + blockIdx.z * ps.a], b[i + blockIdx.z * ps.b], q), Sc.v[row], Sc.vs[row], q);
+    }
+}
+
+// multiply by the constant polynomial R + I X^(N/2): first half of the bit-reversed NTT array sees cp, second half cm
+template <int ACC>
+__global__ void k_mul_const(KShape S, u64* __restrict__ out, const u64* __restrict__ a, LimbList L, ScalarList CP,
+                            ScalarList CM, PolyStride ps) {
+    const int row = blockIdx.y;
+    const u64 q = S.mc[L.idx[row]].q;
+    const bool lo = blockIdx.x < (gridDim.x >> 1);
+    const u64 c = lo ? CP.v[row] : CM.v[row], cs = lo ? CP.vs[row] : CM.vs[row];
+    FOR_THREADS {
+        const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
+        const u64 t = shoup_mul(a[i + blockIdx.z * ps.a], c, cs, q);
+        u64* o = out + i + blockIdx.z * ps.out;
+        *o = ACC ? add_mod(*o, t, q) : t;
+    }
+}
+__global__ void k_add_const(KShape S, u64* __restrict__ out, const u64* __restrict__ a, LimbList L, ScalarList CP,
+                            ScalarList CM) {
+    const int row = blockIdx.y;
+    const u64 q = S.mc[L.idx[row]].q;
+    const u64 c = blockIdx.x < (gridDim.x >> 1) ? CP.v[row] : CM.v[row];
+    FOR_THREADS {
+        const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
+        out[i] = add_mod(a[i], c, q);
+    }
+}
+
+// tensor product of two 2-polynomial ciphertexts, nl limbs each: d0=a0 b0, d1=a0 b1+a1 b0, d2=a1 b1
+__global__ void k_tensor(KShape S, u64* __restrict__ d, const u64* __restrict__ a, const u64* __restrict__ b,
+                         LimbList L, int nl) {
+    const int row = blockIdx.y;
+    const ModConst m = S.mc[L.idx[row]];
+    const size_t P = (size_t)nl << S.logn;
+    FOR_THREADS {
+        const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
+        const u64 a0 = a[i], a1 = a[i + P], b0 = b[i], b1 = b[i + P];
+        d[i] = barrett_mul(a0, b0, m);
+        u64 hi = 0, lo = 0;
+        mac128(hi, lo, a0, b1);
+        mac128(hi, lo, a1, b0);
+        d[i + P] = barrett_reduce128(hi, lo, m);
+        d[i + 2 * P] = barrett_mul(a1, b1, m);
+    }
+}
+
+// out[r][k] = a[r][perm[k]]
+__global__ void k_permute(KShape S, u64* __restrict__ out, const u64* __restrict__ a, const u32* __restrict__ perm,
+                          PolyStride ps) {
+    FOR_THREADS {
+        const u32 k = blockIdx.x * TPB + threadIdx.x;
+        const size_t base = (size_t)blockIdx.y << S.logn;
+        out[base + blockIdx.z * ps.out + k] = a[base + blockIdx.z * ps.a + ldg(perm + k)];
+    }
+}
+
+// key-switch inner product over `beta` digits.  ext: [beta][rows][N]; evk: [dnum][2][evk_rows][N];
+// working row r uses evk row ERow.idx[r].  acc: [2][rows][N].  If perm != null the digits are read
+// through the Galois gather (hoisted rotation: automorphism applied after the decomposition).
+__global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restrict__ ext, const u64* __restrict__ evk,
+                           const u32* __restrict__ perm, LimbList L, LimbList ERow, int beta, int rows, int evk_rows) {
+    const int row = blockIdx.y;
+    const ModConst m = S.mc[L.idx[row]];
+    const size_t er = ERow.idx[row];
+    const size_t N = (size_t)1 << S.logn;
+    FOR_THREADS {
+        const u32 k = blockIdx.x * TPB + threadIdx.x;
+        const u32 ks = perm ? ldg(perm + k) : k;
+        u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+        for (int j = 0; j < beta; j++) {
+            const u64 x = ext[((size_t)j * rows + row) * N + ks];
+            const u64* e = evk + ((size_t)j * 2 * evk_rows + er) * N + k;
+            mac128(h0, l0, x, ldg(e));
+            mac128(h1, l1, x, ldg(e + (size_t)evk_rows * N));
+            if ((j & 3) == 3 && j + 1 < beta) {      // keep the 128-bit sums below 4 q^2 (61-bit moduli)
+                l0 = barrett_reduce128(h0, l0, m); h0 = 0;
+                l1 = barrett_reduce128(h1, l1, m); h1 = 0;
+            }
+        }
+        acc[(size_t)row * N + k] = barrett_reduce128(h0, l0, m);
+        acc[((size_t)rows + row) * N + k] = barrett_reduce128(h1, l1, m);
+    }
+}
+
+// ------------------------------------------------------------------ fast basis conversion (spec S5)
+// in: coefficient-domain residues, source i in row T.srow[i]; out row T.orow[t] for target t.
+// One thread per coefficient, blockIdx.y picks a chunk of BC_CHUNK target moduli.
+// y_i = x_i * hatinv_i mod s_i is recomputed per chunk (cheap next to the traffic).
+__global__ void k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in, BaseConvTable T,
+                               size_t in_zs, size_t out_zs) {
+    const size_t N = (size_t)1 << S.logn;
+    FOR_THREADS {
+        const u32 k = blockIdx.x * TPB + threadIdx.x;
+        const u64* src = in + blockIdx.z * in_zs;
+        u64* dst = out + blockIdx.z * out_zs;
+        u64 y[BC_MAX_SRC];
+#pragma unroll
+        for (int i = 0; i < BC_MAX_SRC; i++)
+            if (i < T.ns) y[i] = shoup_mul(src[(size_t)T.srow[i] * N + k], T.hatinv[i], T.hatinv_s[i], S.mc[T.src[i]].q);
+        const int t0 = blockIdx.y * BC_CHUNK;
+        const int t1 = t0 + BC_CHUNK < T.nt ? t0 + BC_CHUNK : T.nt;
+        for (int t = t0; t < t1; t++) {
+            const ModConst m = S.mc[T.tgt[t]];
+            u64 lo = 0;
+#pragma unroll
+            for (int i = 0; i < BC_MAX_SRC; i++)
+                if (i < T.ns) {
+                    // canonical products (< q_t < 2^61): eight of them fit a word, then fold
+                    lo += shoup_mul(y[i], ldg(T.hat + i * T.nt + t), ldg(T.hat_s + i * T.nt + t), m.q);
+                    if ((i & 7) == 7) lo = barrett_reduce64(lo, m);
+                }
+            dst[(size_t)T.orow[t] * N + k] = barrett_reduce64(lo, m);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ rescale helpers (spec S6)
+// t = (last + h) mod q_l (coefficient domain, single limb) -> delta[i] = (t mod q_i) - (h mod q_i)
+__global__ void k_rescale_delta(KShape S, u64* __restrict__ delta, const u64* __restrict__ last, LimbList L,
+                                int last_mod, PolyStride ps) {
+    const int row = blockIdx.y;
+    const ModConst m = S.mc[L.idx[row]];
+    const u64 ql = S.mc[last_mod].q;
+    const u64 h = ql >> 1;
+    FOR_THREADS {
+        const u32 k = blockIdx.x * TPB + threadIdx.x;
+        u64 t = last[k + blockIdx.z * ps.a] + h;
+        t = t >= ql ? t - ql : t;
+        const u64 r = barrett_reduce64(t, m), hm = barrett_reduce64(h, m);
+        delta[((size_t)row << S.logn) + k + blockIdx.z * ps.out] = sub_mod(r, hm, m.q);
+    }
+}
+
+// centred lift of a single coefficient-domain limb (mod q_src) into every row modulus (ModRaise)
+__global__ void k_center_lift(KShape S, u64* __restrict__ out, const u64* __restrict__ in, LimbList L, int src_mod,
+                              PolyStride ps) {
+    const int row = blockIdx.y;
+    const ModConst m = S.mc[L.idx[row]];
+    const u64 qs = S.mc[src_mod].q;
+    FOR_THREADS {
+        const u32 k = blockIdx.x * TPB + threadIdx.x;
+        const u64 v = in[k + blockIdx.z * ps.a];
+        u64 r;
+        if (v > (qs >> 1)) r = neg_mod(barrett_reduce64(qs - v, m), m.q);
+        else r = barrett_reduce64(v, m);
+        out[((size_t)row << S.logn) + k + blockIdx.z * ps.out] = r;
+    }
+}
+
+// ------------------------------------------------------------------ sampling (spec S8)
+__device__ __forceinline__ u64 mix64(u64 z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ u64 rand64(u64 seed, u64 stream, u64 idx) {
+    return mix64(mix64(seed + stream * 0xD1342543DE82EF95ull) + idx);
+}
+__global__ void k_sample_uniform(KShape S, u64* __restrict__ out, LimbList L, u64 seed, u64 stream) {
+    const int row = blockIdx.y;
+    const int mod = L.idx[row];
+    const u64 q = S.mc[mod].q;
+    const u64 bound = (u64)0 - ((u64)0 - q) % q;
+    FOR_THREADS {
+        const u64 k = blockIdx.x * TPB + threadIdx.x;
+        u64 r = 0;
+        for (int t = 0; t < 8; t++) {
+            r = rand64(seed, stream, ((((u64)mod) << S.logn) + k) * 8 + t);
+            if (bound == 0 || r < bound) break;
+        }
+        out[((size_t)row << S.logn) + k] = r % q;
+    }
+}
+// kind 0: centred binomial (21+21 bits); kind 1: ternary {-1,0,1} w.p. 1/4,1/2,1/4.  Same value in every row.
+__global__ void k_sample_small(KShape S, u64* __restrict__ out, LimbList L, u64 seed, u64 stream, int kind) {
+    const int row = blockIdx.y;
+    const u64 q = S.mc[L.idx[row]].q;
+    FOR_THREADS {
+        const u64 k = blockIdx.x * TPB + threadIdx.x;
+        const u64 r = rand64(seed, stream, k);
+        int v = kind == 0 ? popc64(r & 0x1FFFFF) - popc64((r >> 21) & 0x1FFFFF) : (int)(r & 1) - (int)((r >> 1) & 1);
+        out[((size_t)row << S.logn) + k] = v < 0 ? q - (u64)(-v) : (u64)v;
+    }
+}
+// signed 64-bit coefficients -> residues in every row
+__global__ void k_reduce_i64(KShape S, u64* __restrict__ out, const i64* __restrict__ v, LimbList L) {
+    const int row = blockIdx.y;
+    const ModConst m = S.mc[L.idx[row]];
+    FOR_THREADS {
+        const u32 k = blockIdx.x * TPB + threadIdx.x;
+        const i64 x = v[k];
+        const u64 r = barrett_reduce64(x < 0 ? (u64)(-x) : (u64)x, m);
+        out[((size_t)row << S.logn) + k] = (x < 0) ? neg_mod(r, m.q) : r;
+    }
+}
+
+// ------------------------------------------------------------------ canonical embedding (spec S9), fp64, no FMA contraction
+// one butterfly stage of the "special FFT" on n = N/2 complex values (v: interleaved re,im)
+__global__ void k_fft_stage(KShape S, double* __restrict__ v, const u32* __restrict__ rot,
+                            const double* __restrict__ ksi, int len, int inverse) {
+    FOR_THREADS {
+        const int b = blockIdx.x * TPB + threadIdx.x;     // butterfly index in [0, n/2)
+        const int lenh = len >> 1, lenq = len << 2, gap = (2 << S.logn) / lenq;
+        const int j = b % lenh, i = (b / lenh) * len;
+        const int p0 = i + j, p1 = p0 + lenh;
+        const int rj = rot[j] % lenq;
+        const int idx = (inverse ? (lenq - rj) : rj) * gap;
+        const double wr = ksi[2 * idx], wi = ksi[2 * idx + 1];
+        const double ar = v[2 * p0], ai = v[2 * p0 + 1], br = v[2 * p1], bi = v[2 * p1 + 1];
+        if (!inverse) {
+            const double tr = fsub_rn(fmul_rn(br, wr), fmul_rn(bi, wi));
+            const double ti = fadd_rn(fmul_rn(br, wi), fmul_rn(bi, wr));
+            v[2 * p0] = fadd_rn(ar, tr); v[2 * p0 + 1] = fadd_rn(ai, ti);
+            v[2 * p1] = fsub_rn(ar, tr); v[2 * p1 + 1] = fsub_rn(ai, ti);
+        } else {
+            const double dr = fsub_rn(ar, br), di = fsub_rn(ai, bi);
+            v[2 * p0] = fadd_rn(ar, br); v[2 * p0 + 1] = fadd_rn(ai, bi);
+            v[2 * p1] = fsub_rn(fmul_rn(dr, wr), fmul_rn(di, wi));
+            v[2 * p1 + 1] = fadd_rn(fmul_rn(dr, wi), fmul_rn(di, wr));
+        }
+    }
+}
+__global__ void k_bitrev_copy(KShape S, double* __restrict__ out, const double* __restrict__ in, double mul) {
+    FOR_THREADS {
+        const u32 i = blockIdx.x * TPB + threadIdx.x;      // n = N/2 complex values
+        const u32 j = brev32(i) >> (32 - (S.logn - 1));
+        out[2 * j] = fmul_rn(in[2 * i], mul);
+        out[2 * j + 1] = fmul_rn(in[2 * i + 1], mul);
+    }
+}
+// w (n complex) * scale, round half-even -> N signed coefficients; flags overflow
+__global__ void k_round_coeffs(KShape S, i64* __restrict__ out, const double* __restrict__ w, double scale,
+                               int* __restrict__ flag) {
+    const u32 n = 1u << (S.logn - 1);
+    FOR_THREADS {
+        const u32 k = blockIdx.x * TPB + threadIdx.x;      // k < n
+        const double a = fmul_rn(w[2 * k], scale), b = fmul_rn(w[2 * k + 1], scale);
+        if (!(fabs(a) < 4.0e18) || !(fabs(b) < 4.0e18)) { *flag = 1; out[k] = 0; out[k + n] = 0; }
+        else { out[k] = d2ll_rn(a); out[k + n] = d2ll_rn(b); }
+    }
+}
+// centred lift of limb 0 coefficients -> w = coef / scale
+__global__ void k_center_to_w(KShape S, double* __restrict__ w, const u64* __restrict__ coef, int mod, double scale) {
+    const u32 n = 1u << (S.logn - 1);
+    const u64 q = S.mc[mod].q, half = q >> 1;
+    FOR_THREADS {
+        const u32 k = blockIdx.x * TPB + threadIdx.x;      // k < n
+        const u64 a = coef[k], b = coef[k + n];
+        const double da = a > half ? -(double)(q - a) : (double)a;
+        const double db = b > half ? -(double)(q - b) : (double)b;
+        w[2 * k] = fdiv_rn(da, scale);
+        w[2 * k + 1] = fdiv_rn(db, scale);
+    }
+}
+
+inline dim3 grid3(KShape S, int rows, int npoly = 1) { return dim3((1u << S.logn) / TPB, rows, npoly); }
+
+}  // namespace
+
+// ============================================================================ host wrappers
+void launch_add(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, int npoly, PolyStride ps, dev_stream st) {
+    if (L.n) LAUNCH(k_binop<OP_ADD>, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, b, L, ps);
+}
+void launch_sub(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, int npoly, PolyStride ps, dev_stream st) {
+    if (L.n) LAUNCH(k_binop<OP_SUB>, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, b, L, ps);
+}
+void launch_mul(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, int npoly, PolyStride ps, dev_stream st) {
+    if (L.n) LAUNCH(k_binop<OP_MUL>, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, b, L, ps);
+}
+void launch_neg(KShape S, u64* out, const u64* a, const LimbList& L, int npoly, PolyStride ps, dev_stream st) {
+    if (L.n) LAUNCH(k_neg, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, L, ps);
+}
+void launch_mul_scalar(KShape S, u64* out, const u64* a, const LimbList& L, const ScalarList& Sc, int npoly, PolyStride ps,
+                       dev_stream st) {
+    if (L.n) LAUNCH(k_mul_scalar, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, L, Sc, ps);
+}
+void launch_sub_mul_scalar(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, const ScalarList& Sc,
+                           int npoly, PolyStride ps, dev_stream st) {
+    if (L.n) LAUNCH(k_sub_mul_scalar, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, b, L, Sc, ps);
+}
+void launch_mul_const(KShape S, u64* out, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM,
+                      int npoly, PolyStride ps, dev_stream st) {
+    if (L.n) LAUNCH(k_mul_const<0>, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, L, CP, CM, ps);
+}
+void launch_mac_const(KShape S, u64* acc, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM,
+                      int npoly, PolyStride ps, dev_stream st) {
+    if (L.n) LAUNCH(k_mul_const<1>, grid3(S, L.n, npoly), dim3(TPB), st, S, acc, a, L, CP, CM, ps);
+}
+void launch_add_const(KShape S, u64* out, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM,
+                      dev_stream st) {
+    if (L.n) LAUNCH(k_add_const, grid3(S, L.n), dim3(TPB), st, S, out, a, L, CP, CM);
+}
+void launch_tensor(KShape S, u64* d, const u64* a, const u64* b, const LimbList& L, dev_stream st) {
+    if (L.n) LAUNCH(k_tensor, grid3(S, L.n), dim3(TPB), st, S, d, a, b, L, L.n);
+}
+void launch_permute(KShape S, u64* out, const u64* a, const u32* perm, int rows, int npoly, PolyStride ps, dev_stream st) {
+    if (rows) LAUNCH(k_permute, grid3(S, rows, npoly), dim3(TPB), st, S, out, a, perm, ps);
+}
+void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* evk, const u32* perm, const LimbList& L,
+                     const LimbList& ERow, int beta, int evk_rows, dev_stream st) {
+    if (L.n) LAUNCH(k_ks_inner, grid3(S, L.n), dim3(TPB), st, S, acc, ext, evk, perm, L, ERow, beta, L.n, evk_rows);
+}
+void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable& T, int nz, size_t in_zs, size_t out_zs,
+                         dev_stream st) {
+    if (!T.nt || !nz) return;
+    dim3 g((1u << S.logn) / TPB, (T.nt + BC_CHUNK - 1) / BC_CHUNK, nz);
+    LAUNCH(k_base_convert, g, dim3(TPB), st, S, out, in, T, in_zs, out_zs);
+}
+void launch_rescale_delta(KShape S, u64* delta, const u64* last, const LimbList& L, int last_mod, int npoly, PolyStride ps,
+                          dev_stream st) {
+    if (L.n) LAUNCH(k_rescale_delta, grid3(S, L.n, npoly), dim3(TPB), st, S, delta, last, L, last_mod, ps);
+}
+void launch_center_lift(KShape S, u64* out, const u64* in, const LimbList& L, int src_mod, int npoly, PolyStride ps,
+                        dev_stream st) {
+    if (L.n) LAUNCH(k_center_lift, grid3(S, L.n, npoly), dim3(TPB), st, S, out, in, L, src_mod, ps);
+}
+void launch_sample_uniform(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, dev_stream st) {
+    if (L.n) LAUNCH(k_sample_uniform, grid3(S, L.n), dim3(TPB), st, S, out, L, seed, stream);
+}
+void launch_sample_small(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, int kind, dev_stream st) {
+    if (L.n) LAUNCH(k_sample_small, grid3(S, L.n), dim3(TPB), st, S, out, L, seed, stream, kind);
+}
+void launch_reduce_i64(KShape S, u64* out, const i64* v, const LimbList& L, dev_stream st) {
+    if (L.n) LAUNCH(k_reduce_i64, grid3(S, L.n), dim3(TPB), st, S, out, v, L);
+}
+// decode direction: w (n complex, natural order) -> z in `out`
+void launch_special_fft(KShape S, double* out, const double* w, const u32* rot, const double* ksi, dev_stream st) {
+    const int n = 1 << (S.logn - 1);
+    LAUNCH(k_bitrev_copy, dim3(n / TPB), dim3(TPB), st, S, out, w, 1.0);
+    for (int len = 2; len <= n; len <<= 1)
+        LAUNCH(k_fft_stage, dim3(n / 2 / TPB), dim3(TPB), st, S, out, rot, ksi, len, 0);
+}
+// encode direction: z -> w (includes 1/n); `z` is overwritten as scratch
+void launch_special_ifft(KShape S, double* out, double* z, const u32* rot, const double* ksi, dev_stream st) {
+    const int n = 1 << (S.logn - 1);
+    for (int len = n; len >= 2; len >>= 1)
+        LAUNCH(k_fft_stage, dim3(n / 2 / TPB), dim3(TPB), st, S, z, rot, ksi, len, 1);
+    LAUNCH(k_bitrev_copy, dim3(n / TPB), dim3(TPB), st, S, out, z, 1.0 / (double)n);
+}
+void launch_round_coeffs(KShape S, i64* out, const double* w, double scale, int* flag, dev_stream st) {
+    LAUNCH(k_round_coeffs, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, out, w, scale, flag);
+}
+void launch_center_to_w(KShape S, double* w, const u64* coef, int mod, double scale, dev_stream st) {
+    LAUNCH(k_center_to_w, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, w, coef, mod, scale);
+}

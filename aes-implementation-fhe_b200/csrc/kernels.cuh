@@ -1,0 +1,53 @@
+// kernels.cuh -- launch wrappers for the streaming RNS kernels (see kernels.cu).
+#pragma once
+#include "common.cuh"
+
+#define BC_MAX_SRC 16
+#define BC_MAX_TGT 48
+#define BC_CHUNK 8
+
+// element strides between consecutive polynomials (blockIdx.z) for each pointer of a kernel
+struct PolyStride {
+    size_t out, a, b;
+};
+// fast basis conversion {src} -> {tgt}; hat/hat_s are device arrays [ns][nt]
+struct BaseConvTable {
+    int ns, nt;
+    unsigned char src[BC_MAX_SRC];     // modulus index of source row i
+    unsigned char srow[BC_MAX_SRC];    // input row of source i
+    unsigned char tgt[BC_MAX_TGT];     // modulus index of target t
+    unsigned char orow[BC_MAX_TGT];    // output row of target t
+    u64 hatinv[BC_MAX_SRC], hatinv_s[BC_MAX_SRC];
+    const u64* hat;
+    const u64* hat_s;
+};
+// shape shared by all kernels: N coefficients per row, modulus table
+struct KShape {
+    const ModConst* mc;
+    int logn;
+};
+
+void launch_add(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, int npoly, PolyStride ps, dev_stream st);
+void launch_sub(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, int npoly, PolyStride ps, dev_stream st);
+void launch_mul(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, int npoly, PolyStride ps, dev_stream st);
+void launch_neg(KShape S, u64* out, const u64* a, const LimbList& L, int npoly, PolyStride ps, dev_stream st);
+void launch_mul_scalar(KShape S, u64* out, const u64* a, const LimbList& L, const ScalarList& Sc, int npoly, PolyStride ps, dev_stream st);
+void launch_sub_mul_scalar(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, const ScalarList& Sc, int npoly, PolyStride ps, dev_stream st);
+void launch_mul_const(KShape S, u64* out, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM, int npoly, PolyStride ps, dev_stream st);
+void launch_mac_const(KShape S, u64* acc, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM, int npoly, PolyStride ps, dev_stream st);
+void launch_add_const(KShape S, u64* out, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM, dev_stream st);
+void launch_tensor(KShape S, u64* d, const u64* a, const u64* b, const LimbList& L, dev_stream st);
+void launch_permute(KShape S, u64* out, const u64* a, const u32* perm, int rows, int npoly, PolyStride ps, dev_stream st);
+// acc[2][rows][N] = sum_j ext[j][rows][N] * evk[j][2][evk_rows][N]; ERow maps working row -> evk row
+void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* evk, const u32* perm, const LimbList& L, const LimbList& ERow, int beta, int evk_rows, dev_stream st);
+// nz independent conversions: slice z reads in + z*in_zs, writes out + z*out_zs
+void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable& T, int nz, size_t in_zs, size_t out_zs, dev_stream st);
+void launch_rescale_delta(KShape S, u64* delta, const u64* last, const LimbList& L, int last_mod, int npoly, PolyStride ps, dev_stream st);
+void launch_center_lift(KShape S, u64* out, const u64* in, const LimbList& L, int src_mod, int npoly, PolyStride ps, dev_stream st);
+void launch_sample_uniform(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, dev_stream st);
+void launch_sample_small(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, int kind, dev_stream st);
+void launch_reduce_i64(KShape S, u64* out, const i64* v, const LimbList& L, dev_stream st);
+void launch_special_fft(KShape S, double* out, const double* w, const u32* rot, const double* ksi, dev_stream st);
+void launch_special_ifft(KShape S, double* out, double* z, const u32* rot, const double* ksi, dev_stream st);
+void launch_round_coeffs(KShape S, i64* out, const double* w, double scale, int* flag, dev_stream st);
+void launch_center_to_w(KShape S, double* w, const u64* coef, int mod, double scale, dev_stream st);

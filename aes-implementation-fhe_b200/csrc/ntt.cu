@@ -1,0 +1,310 @@
+// ntt.cu -- negacyclic NTT / iNTT, 64-bit RNS limbs, sm_100a.  N = 2^16 (product) and 2^12 (tests).
+//
+// Layout of the transform.  The length-N Cooley-Tukey NTT with the psi-powers table in
+// bit-reversed order (DESIGN.md spec S3, same table as oracle/ckks_ref.c:ref_ntt_tables) is
+// split into two passes over the limb viewed as an R x 256 row-major matrix (R = N/256):
+//
+//   pass A  stages 1..log R          butterflies couple whole rows: "columns"
+//   pass B  stages log R+1..log N    butterflies stay inside one contiguous 256-element row
+//
+// No transposition and no extra inter-pass twiddle multiply is needed in this formulation:
+// the bit-reversed table is self-similar, a radix-16 sub-transform rooted at table index X
+// uses entries (X << s) + g, s = 0..3 (forward) -- for N = 2^16: X = 1, 16+rh, 256+R, 4096+16R+jh
+// for the four register rounds.  Each thread keeps 16 coefficients in registers for 4 stages
+// (Harvey lazy butterflies, values in [0,4q)), with ONE shared-memory exchange per pass.
+// Global accesses are 128-byte coalesced in both passes; pass B stages its stores through
+// shared memory (padded 1-in-16 so the 64-bit accesses are bank-conflict free).
+//
+// Algorithmic bytes: 2*N*8 = 1 MiB per limb-NTT at N = 2^16; actual DRAM traffic
+// is 2 MiB if the intermediate misses L2, ~1 MiB when the batch fits the 126 MB L2 (in-place).
+#include "ntt.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
+
+// Forward radix-16 block rooted at table index X: 4 CT stages on x[0..15], lazy in [0,4q).
+__device__ __forceinline__ void fwd16(u64 (&x)[16], u32 X, const u64* __restrict__ W, const u64* __restrict__ Ws,
+                                      u64 q) {
+    const u64 q2 = 2 * q;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const int span = 8 >> s;
+        u64 w[8], ws[8];
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+            if (g < (1 << s)) { w[g] = ldg(W + (X << s) + g); ws[g] = ldg(Ws + (X << s) + g); }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int g = i / span, k0 = g * 2 * span + (i % span), k1 = k0 + span;
+            u64 u = x[k0];
+            u = u >= q2 ? u - q2 : u;
+            const u64 v = shoup_mul_lazy(x[k1], w[g], ws[g], q);
+            x[k0] = u + v;
+            x[k1] = u - v + q2;
+        }
+    }
+}
+
+// Inverse radix-16 block rooted at X: 4 GS stages, values kept in [0,2q).
+// If FINAL, the last stage folds in N^-1 (scaling the sum by ninv and the twiddle by ninv).
+template <bool FINAL>
+__device__ __forceinline__ void inv16(u64 (&x)[16], u32 X, const u64* __restrict__ W, const u64* __restrict__ Ws,
+                                      u64 q, u64 ninv, u64 ninv_s, u64 w1n, u64 w1n_s) {
+    const u64 q2 = 2 * q;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const int span = 1 << s;
+        u64 w[8], ws[8];
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+            if (g < (8 >> s)) {
+                if (FINAL && s == 3) { w[g] = w1n; ws[g] = w1n_s; }
+                else { w[g] = ldg(W + (X << (3 - s)) + g); ws[g] = ldg(Ws + (X << (3 - s)) + g); }
+            }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int g = i / span, k0 = g * 2 * span + (i % span), k1 = k0 + span;
+            const u64 u = x[k0], v = x[k1];
+            u64 sum = u + v;
+            sum = sum >= q2 ? sum - q2 : sum;
+            if (FINAL && s == 3) sum = shoup_mul_lazy(sum, ninv, ninv_s, q);
+            x[k0] = sum;
+            x[k1] = shoup_mul_lazy(u - v + q2, w[g], ws[g], q);
+        }
+    }
+}
+
+__device__ __forceinline__ u64 canon4(u64 v, u64 q) {
+    v = v >= 2 * q ? v - 2 * q : v;
+    return v >= q ? v - q : v;
+}
+__device__ __forceinline__ u64 canon2(u64 v, u64 q) { return v >= q ? v - q : v; }
+
+// ---------------------------------------------------------------- forward, pass A (columns)
+// LOGR = 8: R = 256 rows, tile = 16 columns x 256 rows, two radix-16 rounds (X = 1, then 16 + rr).
+// LOGR = 4: R = 16 rows,  tile = 256 columns x 16 rows, one radix-16 round (X = 1).
+template <int LOGR>
+__global__ void __launch_bounds__(kThreads, 2)
+ntt_fwd_passA(const u64* __restrict__ src, u64* __restrict__ dst, NttJob J, NttTables T) {
+    constexpr int RG = (1 << LOGR) / 16;          // row groups per column: 16 or 1
+    constexpr int TC = kThreads / RG;             // columns per CTA: 16 or 256
+    CKKS_SHARED u64 sm[LOGR == 8 ? 256 * 16 : 1];
+    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
+    const int limb = J.rows[blockIdx.z][blockIdx.y], slimb = J.srows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const size_t N = (size_t)1 << T.logn;
+    src += blockIdx.z * J.szs;
+    dst += blockIdx.z * J.dzs;
+    const u64 q = T.mc[mod].q;
+    const u64* W = T.fwd + (size_t)mod * N;
+    const u64* Ws = T.fwd_s + (size_t)mod * N;
+    if (LOGR == 8) {
+        FOR_THREADS {
+            const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
+            const size_t sbase = (size_t)slimb * N + tile * TC + c;
+            u64 x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = src[sbase + (size_t)(rr + 16 * k) * 256];
+            fwd16(x, 1u, W, Ws, q);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sm[(rr + 16 * k) * TC + c] = x[k];
+        }
+        BLOCK_SYNC;
+        FOR_THREADS {
+            const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
+            const size_t base = (size_t)limb * N + tile * TC + c;
+            u64 x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = sm[(16 * rr + k) * TC + c];
+            fwd16(x, 16u + rr, W, Ws, q);
+#pragma unroll
+            for (int k = 0; k < 16; k++) dst[base + (size_t)(16 * rr + k) * 256] = x[k];   // lazy [0,4q)
+        }
+    } else {
+        FOR_THREADS {
+            const size_t base = (size_t)limb * N + threadIdx.x, sbase = (size_t)slimb * N + threadIdx.x;
+            u64 x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = src[sbase + (size_t)k * 256];
+            fwd16(x, 1u, W, Ws, q);
+#pragma unroll
+            for (int k = 0; k < 16; k++) dst[base + (size_t)k * 256] = x[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- forward, pass B (rows)
+// 16 rows of 256 per CTA; row with global index Rg is rooted at table index R + Rg.
+__global__ void __launch_bounds__(kThreads, 2)
+ntt_fwd_passB(u64* __restrict__ data, NttJob J, NttTables T) {
+    CKKS_SHARED u64 sm[16 * 256 + 16 * 16];
+    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
+    const int limb = J.rows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const size_t N = (size_t)1 << T.logn;
+    const u32 Rn = (u32)(N >> 8);
+    data += blockIdx.z * J.dzs;
+    const u64 q = T.mc[mod].q;
+    const u64* W = T.fwd + (size_t)mod * N;
+    const u64* Ws = T.fwd_s + (size_t)mod * N;
+    u64* g = data + (size_t)limb * N + (size_t)tile * 16 * 256;
+    FOR_THREADS {
+        const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
+        const u32 R = tile * 16 + row;
+        u64 x[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = g[row * 256 + jj + 16 * k];
+        fwd16(x, Rn + R, W, Ws, q);
+#pragma unroll
+        for (int k = 0; k < 16; k++) sm[pad16(row * 256 + jj + 16 * k)] = x[k];
+    }
+    BLOCK_SYNC;
+    FOR_THREADS {
+        const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
+        const u32 R = tile * 16 + row;
+        u64 x[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = sm[pad16(row * 256 + 16 * jj + k)];
+        fwd16(x, 16u * (Rn + R) + jj, W, Ws, q);
+        // each thread rewrites exactly the 16 slots it just read, so no barrier is needed before this store
+#pragma unroll
+        for (int k = 0; k < 16; k++) sm[pad16(row * 256 + 16 * jj + k)] = canon4(x[k], q);
+    }
+    BLOCK_SYNC;
+    FOR_THREADS {
+#pragma unroll
+        for (int k = 0; k < 16; k++) g[k * 256 + threadIdx.x] = sm[pad16(k * 256 + threadIdx.x)];
+    }
+}
+
+// ---------------------------------------------------------------- inverse, pass B^-1 (rows)
+__global__ void __launch_bounds__(kThreads, 2)
+ntt_inv_passB(const u64* __restrict__ src, u64* __restrict__ dst, NttJob J, NttTables T) {
+    CKKS_SHARED u64 sm[16 * 256 + 16 * 16];
+    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
+    const int limb = J.rows[blockIdx.z][blockIdx.y], slimb = J.srows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const size_t N = (size_t)1 << T.logn;
+    const u32 Rn = (u32)(N >> 8);
+    src += blockIdx.z * J.szs;
+    dst += blockIdx.z * J.dzs;
+    const u64 q = T.mc[mod].q;
+    const u64* W = T.inv + (size_t)mod * N;
+    const u64* Ws = T.inv_s + (size_t)mod * N;
+    const size_t off = (size_t)limb * N + (size_t)tile * 16 * 256;
+    const size_t soff = (size_t)slimb * N + (size_t)tile * 16 * 256;
+    FOR_THREADS {
+#pragma unroll
+        for (int k = 0; k < 16; k++) sm[pad16(k * 256 + threadIdx.x)] = src[soff + k * 256 + threadIdx.x];
+    }
+    BLOCK_SYNC;
+    FOR_THREADS {
+        const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
+        const u32 R = tile * 16 + row;
+        u64 x[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = sm[pad16(row * 256 + 16 * jj + k)];
+        inv16<false>(x, 16u * (Rn + R) + jj, W, Ws, q, 0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 16; k++) sm[pad16(row * 256 + 16 * jj + k)] = x[k];
+    }
+    BLOCK_SYNC;
+    FOR_THREADS {
+        const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
+        const u32 R = tile * 16 + row;
+        u64 x[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = sm[pad16(row * 256 + jj + 16 * k)];
+        inv16<false>(x, Rn + R, W, Ws, q, 0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 16; k++) dst[off + row * 256 + jj + 16 * k] = x[k];       // lazy [0,2q)
+    }
+}
+
+// ---------------------------------------------------------------- inverse, pass A^-1 (columns)
+template <int LOGR>
+__global__ void __launch_bounds__(kThreads, 2)
+ntt_inv_passA(u64* __restrict__ data, NttJob J, NttTables T) {
+    constexpr int RG = (1 << LOGR) / 16;
+    constexpr int TC = kThreads / RG;
+    CKKS_SHARED u64 sm[LOGR == 8 ? 256 * 16 : 1];
+    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
+    const int limb = J.rows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const size_t N = (size_t)1 << T.logn;
+    data += blockIdx.z * J.dzs;
+    const ModConst mc = T.mc[mod];
+    const u64 q = mc.q;
+    const u64* W = T.inv + (size_t)mod * N;
+    const u64* Ws = T.inv_s + (size_t)mod * N;
+    if (LOGR == 8) {
+        FOR_THREADS {
+            const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
+            const size_t base = (size_t)limb * N + tile * TC + c;
+            u64 x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = data[base + (size_t)(16 * rr + k) * 256];
+            inv16<false>(x, 16u + rr, W, Ws, q, 0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sm[(16 * rr + k) * TC + c] = x[k];
+        }
+        BLOCK_SYNC;
+        FOR_THREADS {
+            const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
+            const size_t base = (size_t)limb * N + tile * TC + c;
+            u64 x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = sm[(rr + 16 * k) * TC + c];
+            inv16<true>(x, 1u, W, Ws, q, mc.ninv, mc.ninv_s, mc.w1n, mc.w1n_s);
+#pragma unroll
+            for (int k = 0; k < 16; k++) data[base + (size_t)(rr + 16 * k) * 256] = canon2(x[k], q);
+        }
+    } else {
+        FOR_THREADS {
+            const size_t base = (size_t)limb * N + threadIdx.x;
+            u64 x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = data[base + (size_t)k * 256];
+            inv16<true>(x, 1u, W, Ws, q, mc.ninv, mc.ninv_s, mc.w1n, mc.w1n_s);
+#pragma unroll
+            for (int k = 0; k < 16; k++) data[base + (size_t)k * 256] = canon2(x[k], q);
+        }
+    }
+}
+
+}  // namespace
+
+void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st) {
+    if (J.n == 0 || J.nz == 0) return;
+    const unsigned R = 1u << (T.logn - 8);
+    dim3 gridB(R / 16, J.n, J.nz);
+    if (T.logn == 16) {
+        dim3 gridA(16, J.n, J.nz);
+        LAUNCH(ntt_fwd_passA<8>, gridA, dim3(kThreads), st, src, dst, J, T);
+    } else if (T.logn == 12) {
+        dim3 gridA(1, J.n, J.nz);
+        LAUNCH(ntt_fwd_passA<4>, gridA, dim3(kThreads), st, src, dst, J, T);
+    } else {
+        throw std::runtime_error("ntt: only N = 2^16 and N = 2^12 are built");
+    }
+    LAUNCH(ntt_fwd_passB, gridB, dim3(kThreads), st, dst, J, T);
+}
+
+void ntt_inverse(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st) {
+    if (J.n == 0 || J.nz == 0) return;
+    const unsigned R = 1u << (T.logn - 8);
+    dim3 gridB(R / 16, J.n, J.nz);
+    LAUNCH(ntt_inv_passB, gridB, dim3(kThreads), st, src, dst, J, T);
+    if (T.logn == 16) {
+        dim3 gridA(16, J.n, J.nz);
+        LAUNCH(ntt_inv_passA<8>, gridA, dim3(kThreads), st, dst, J, T);
+    } else if (T.logn == 12) {
+        dim3 gridA(1, J.n, J.nz);
+        LAUNCH(ntt_inv_passA<4>, gridA, dim3(kThreads), st, dst, J, T);
+    } else {
+        throw std::runtime_error("ntt: only N = 2^16 and N = 2^12 are built");
+    }
+}

@@ -1,0 +1,30 @@
+// ntt.cuh -- host entry points of the negacyclic NTT (see ntt.cu).
+#pragma once
+#include "common.cuh"
+
+// device tables, [n_moduli][N] each: psi powers in bit-reversed order and their Shoup companions
+struct NttTables {
+    const u64* fwd;
+    const u64* fwd_s;
+    const u64* inv;
+    const u64* inv_s;
+    const ModConst* mc;
+    int logn;
+};
+
+// One batched transform: for z-slice z, item i reads source row srows[z][i] of src + z*szs and
+// writes destination row rows[z][i] of dst + z*dzs (elements); the residues are modulo
+// mc[mods[z][i]].  The first pass goes src -> dst, the second runs in place on dst; src may equal dst
+// when srows == rows.
+#define NTT_MAX_Z 6
+struct NttJob {
+    int n, nz;
+    size_t szs, dzs;
+    unsigned char mods[NTT_MAX_Z][CKKS_MAX_MODULI];
+    unsigned char rows[NTT_MAX_Z][CKKS_MAX_MODULI];
+    unsigned char srows[NTT_MAX_Z][CKKS_MAX_MODULI];
+    unsigned char cnt[NTT_MAX_Z];     // items of slice z (0 = all n); CTAs beyond it exit at once
+};
+
+void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st);
+void ntt_inverse(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st);

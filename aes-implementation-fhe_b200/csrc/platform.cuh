@@ -1,0 +1,209 @@
+// platform.cuh -- the one place that knows whether this translation unit is compiled by nvcc for
+// sm_100a (the product) or by g++ with -DCKKS_EMU (tests/emu: a CPU *emulation of the CUDA
+// execution model* that runs the very same kernel and host-orchestration source so the
+// `-m "not gpu"` tests can check it against the oracle in a container without a GPU).
+//
+// The emulation build is test infrastructure: it is compiled only by tests/emu/build.py into
+// tests/emu/, the product loader (desilofhe/_capi.py) never looks there, and bench.py /
+// __graft_entry__.smoke() refuse to run on it.  There is no CPU fallback in the product.
+//
+// Kernel style that makes both builds possible without a fibre scheduler:
+//   * 1-D thread blocks only;
+//   * per-thread code sits inside FOR_THREADS { ... } regions; BLOCK_SYNC separates regions;
+//   * nothing thread-dependent lives across a BLOCK_SYNC except in __shared__ memory
+//     (block-uniform values may be declared outside the regions).
+// Under nvcc FOR_THREADS is empty and BLOCK_SYNC is __syncthreads(); under CKKS_EMU FOR_THREADS is a
+// loop over threadIdx.x and BLOCK_SYNC is nothing (regions run to completion one after another).
+#pragma once
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <stdexcept>
+#include <string>
+
+typedef unsigned long long u64;
+typedef long long i64;
+typedef unsigned int u32;
+
+extern long g_launch_count;   // kernels launched by this library (bench.py reports it as gpu_launches)
+
+#ifndef CKKS_EMU
+// =================================================================================== CUDA
+#include <cuda_runtime.h>
+
+#define FOR_THREADS
+#define BLOCK_SYNC __syncthreads()
+#define LAUNCH(kern, grid, block, stream, ...) (++g_launch_count, kern<<<grid, block, 0, stream>>>(__VA_ARGS__))
+#define CKKS_SHARED __shared__
+
+#define CUDA_CHECK(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) +       \
+                                     " at " #expr);                                               \
+    } while (0)
+
+typedef cudaStream_t dev_stream;
+
+namespace dev {
+inline const char* backend_name() { return "cuda-sm_100a"; }
+inline void set_device(int id) { CUDA_CHECK(cudaSetDevice(id)); }
+inline dev_stream stream_create() {
+    dev_stream s;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    return s;
+}
+inline void stream_destroy(dev_stream s) { cudaStreamDestroy(s); }
+inline void pool_setup(int device) {
+    cudaMemPool_t pool;
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;   // never give memory back to the driver: the arena is reused
+    CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+}
+inline void* alloc(size_t bytes, dev_stream s) {
+    void* p = nullptr;
+    CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 8, s));
+    return p;
+}
+inline void free(void* p, dev_stream s) {
+    if (p) cudaFreeAsync(p, s);
+}
+inline void h2d(void* d, const void* h, size_t bytes, dev_stream s) {
+    CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
+}
+inline void d2h(void* h, const void* d, size_t bytes, dev_stream s) {
+    CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
+}
+inline void d2d(void* o, const void* i, size_t bytes, dev_stream s) {
+    CUDA_CHECK(cudaMemcpyAsync(o, i, bytes, cudaMemcpyDeviceToDevice, s));
+}
+inline void zero(void* d, size_t bytes, dev_stream s) { CUDA_CHECK(cudaMemsetAsync(d, 0, bytes, s)); }
+inline void sync(dev_stream s) { CUDA_CHECK(cudaStreamSynchronize(s)); }
+inline void check_last(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA launch error in ") + what + ": " + cudaGetErrorString(e));
+}
+inline void* host_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    CUDA_CHECK(cudaMallocHost(&p, bytes));
+    return p;
+}
+inline void host_free_pinned(void* p) { cudaFreeHost(p); }
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    void start(dev_stream s) {
+        if (!a) { CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b)); }
+        CUDA_CHECK(cudaEventRecord(a, s));
+    }
+    float stop_ms(dev_stream s) {
+        CUDA_CHECK(cudaEventRecord(b, s));
+        CUDA_CHECK(cudaEventSynchronize(b));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+        return ms;
+    }
+};
+}  // namespace dev
+
+__device__ __forceinline__ u64 mulhi64(u64 a, u64 b) { return __umul64hi(a, b); }
+__device__ __forceinline__ double fmul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double fadd_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double fsub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double fdiv_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ u32 brev32(u32 x) { return __brev(x); }
+__device__ __forceinline__ int popc64(u64 x) { return __popcll(x); }
+__device__ __forceinline__ i64 d2ll_rn(double x) { return __double2ll_rn(x); }
+template <typename T>
+__device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+
+#else
+// =================================================================================== emulation (tests only)
+#include <math.h>
+#include <time.h>
+
+struct emu_uint3 { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+extern thread_local emu_uint3 blockIdx, threadIdx;
+extern thread_local dim3 blockDim, gridDim;
+
+#define __global__ static
+#define __device__ static
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define CKKS_SHARED static thread_local
+#define FOR_THREADS for (threadIdx.x = 0; threadIdx.x < blockDim.x; ++threadIdx.x)
+#define BLOCK_SYNC ((void)0)
+
+typedef int dev_stream;
+
+namespace emu {
+template <typename F>
+inline void launch(dim3 grid, dim3 block, F body) {
+    const long total = (long)grid.x * grid.y * grid.z;
+#pragma omp parallel for schedule(static)
+    for (long b = 0; b < total; b++) {
+        gridDim = grid;
+        blockDim = block;
+        blockIdx.x = (unsigned)(b % grid.x);
+        blockIdx.y = (unsigned)((b / grid.x) % grid.y);
+        blockIdx.z = (unsigned)(b / ((long)grid.x * grid.y));
+        threadIdx.x = threadIdx.y = threadIdx.z = 0;
+        body();
+    }
+}
+}  // namespace emu
+#define LAUNCH(kern, grid, block, stream, ...) (++g_launch_count, emu::launch(grid, block, [=]() { kern(__VA_ARGS__); }))
+
+namespace dev {
+inline const char* backend_name() { return "emulation (tests only)"; }
+inline void set_device(int) {}
+inline dev_stream stream_create() { return 0; }
+inline void stream_destroy(dev_stream) {}
+inline void pool_setup(int) {}
+inline void* alloc(size_t bytes, dev_stream) {
+    void* p = ::malloc(bytes ? bytes : 8);
+    if (!p) throw std::runtime_error("emulation: out of memory");
+    return p;
+}
+inline void free(void* p, dev_stream) { ::free(p); }
+inline void h2d(void* d, const void* h, size_t bytes, dev_stream) { memcpy(d, h, bytes); }
+inline void d2h(void* h, const void* d, size_t bytes, dev_stream) { memcpy(h, d, bytes); }
+inline void d2d(void* o, const void* i, size_t bytes, dev_stream) { memmove(o, i, bytes); }
+inline void zero(void* d, size_t bytes, dev_stream) { memset(d, 0, bytes); }
+inline void sync(dev_stream) {}
+inline void check_last(const char*) {}
+inline void* host_alloc_pinned(size_t bytes) { return ::malloc(bytes); }
+inline void host_free_pinned(void* p) { ::free(p); }
+struct Timer {
+    struct timespec t0;
+    void start(dev_stream) { clock_gettime(CLOCK_MONOTONIC, &t0); }
+    float stop_ms(dev_stream) {
+        struct timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        return (float)((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+    }
+};
+}  // namespace dev
+
+static inline u64 mulhi64(u64 a, u64 b) { return (u64)(((unsigned __int128)a * b) >> 64); }
+static inline double fmul_rn(double a, double b) { return a * b; }   // built with -ffp-contract=off
+static inline double fadd_rn(double a, double b) { return a + b; }
+static inline double fsub_rn(double a, double b) { return a - b; }
+static inline double fdiv_rn(double a, double b) { return a / b; }
+static inline u32 brev32(u32 x) {
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    return (x >> 16) | (x << 16);
+}
+static inline int popc64(u64 x) { return __builtin_popcountll(x); }
+static inline i64 d2ll_rn(double x) { return (i64)nearbyint(x); }
+template <typename T>
+static inline T ldg(const T* p) { return *p; }
+#endif

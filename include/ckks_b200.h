@@ -1,0 +1,141 @@
+/* ckks_b200.h -- C ABI of the B200-native CKKS evaluation engine (libckks_b200.so).
+ *
+ * Drop-in boundary for the one thing the reference's AES-on-CKKS stack calls: the `desilofhe.Engine`
+ * methods reached through reference `engine_context.py` (the only file that touches the backend,
+ * SURVEY.md 8b).  Each entry point cites the reference interface it replaces.  Plain pointers,
+ * sizes and opaque handles only -- no torch / C++ types.  The Python shim
+ * `aes-implementation-fhe_b200/desilofhe/` binds these with ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - Every function returns an int status: 0 ok, CKKS_ERR_LEVEL (levels exhausted: the shim raises
+ *     RuntimeError("... level should be positive ..."), the string the reference's recovery ladders
+ *     match, xor4_lut.py:33-51, engine_context.py:184-195), CKKS_ERR_FORM ("... NTT ..."),
+ *     CKKS_ERR_POLYS ("... should have 3 polynomials", engine_context.py:139-145), CKKS_ERR_OTHER.
+ *     ckks_last_error() returns the message of the last failure on the calling thread.
+ *   - All operations are out of place; inputs are never modified (the reference aliases
+ *     ciphertexts freely).  Results are new handles owned by the caller (ckks_ct_free / ckks_pt_free).
+ *   - Slot vectors are interleaved (re, im) doubles, slot_count = N/2 complex values.
+ *   - One engine = one GPU + one CUDA stream; calls are asynchronous on that stream except
+ *     ckks_decrypt / ckks_ct_export / ckks_sync, which synchronise.
+ */
+#ifndef CKKS_B200_H
+#define CKKS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ckks_engine ckks_engine;
+typedef struct ckks_ct ckks_ct;     /* ciphertext: 2 (or 3, before relinearisation) polynomials over Q_level */
+typedef struct ckks_pt ckks_pt;     /* encoded plaintext polynomial at one level */
+
+enum { CKKS_OK = 0, CKKS_ERR_LEVEL = 1, CKKS_ERR_FORM = 2, CKKS_ERR_POLYS = 3, CKKS_ERR_OTHER = 4 };
+
+const char* ckks_last_error(void);
+const char* ckks_backend(void);          /* "cuda-sm_100a" for the product library */
+long ckks_launch_count(void);            /* kernels launched by this library so far (bench.py gpu_launches) */
+
+/* ---- engine construction: replaces desilofhe.Engine(...) (engine_context.py:17-42).
+ * `_default` derives the deterministic prime chain of DESIGN.md spec S1 (q0 | L scale primes | K special). */
+int ckks_engine_create_default(int logn, int levels, int scale_bits, int q0_bits, int p_bits, int dnum,
+                               int hamming_weight, int fresh_level, uint64_t seed, int device_id,
+                               ckks_engine** out);
+int ckks_engine_create(int logn, const uint64_t* q, int nq, const uint64_t* p, int np, int scale_bits, int alpha,
+                       int hamming_weight, int fresh_level, uint64_t seed, int device_id, ckks_engine** out);
+void ckks_engine_destroy(ckks_engine* e);
+int ckks_sync(ckks_engine* e);
+/* engine.slot_count (read at pipeline.py:39, xor4_lut.py:16, state_encoder.py:14, ...) */
+int ckks_slot_count(const ckks_engine* e);
+/* parameter introspection: any out pointer may be NULL; q_out/p_out/scales_out need nq/np/nq entries */
+int ckks_get_params(const ckks_engine* e, int* logn, int* nq, int* np, int* alpha, int* fresh_level,
+                    uint64_t* q_out, uint64_t* p_out, double* scales_out);
+
+/* ---- keys: create_secret_key / create_public_key / create_relinearization_key /
+ * create_conjugation_key / create_rotation_key / create_bootstrap_key (engine_context.py:44-50).
+ * Keys live inside the engine; Galois keys for other steps are derived on first use. */
+int ckks_keygen_secret(ckks_engine* e);
+int ckks_keygen_public(ckks_engine* e);
+int ckks_keygen_relin(ckks_engine* e);
+int ckks_keygen_conjugation(ckks_engine* e);
+int ckks_keygen_rotation(ckks_engine* e, const long* steps, int nsteps);
+int ckks_keygen_bootstrap(ckks_engine* e);
+
+/* ---- data movement: encode / encrypt / decrypt (engine_context.py:56-63) */
+int ckks_encode(ckks_engine* e, const double* slots_re_im, int level, ckks_pt** out);
+int ckks_encrypt(ckks_engine* e, const double* slots_re_im, int level /* <0: fresh level */, ckks_ct** out);
+int ckks_decrypt(ckks_engine* e, const ckks_ct* ct, double* slots_re_im_out);
+void ckks_ct_free(ckks_engine* e, ckks_ct* ct);
+void ckks_pt_free(ckks_engine* e, ckks_pt* pt);
+int ckks_ct_level(const ckks_ct* ct);
+int ckks_ct_npoly(const ckks_ct* ct);
+int ckks_pt_level(const ckks_pt* pt);
+
+/* ---- arithmetic: multiply / add / subtract / add_plain (engine_context.py:65-98).
+ * Binary operations align levels themselves (xor4_lut.py:69-73 adds ciphertexts 5-13 levels apart);
+ * every multiply consumes exactly one level and rescales. */
+int ckks_add(ckks_engine* e, ckks_ct* a, ckks_ct* b, ckks_ct** out);
+int ckks_sub(ckks_engine* e, ckks_ct* a, ckks_ct* b, ckks_ct** out);
+int ckks_negate(ckks_engine* e, const ckks_ct* a, ckks_ct** out);
+int ckks_mul(ckks_engine* e, ckks_ct* a, ckks_ct* b, ckks_ct** out);           /* multiply(a, b, relin_key) */
+int ckks_mul_norelin(ckks_engine* e, ckks_ct* a, ckks_ct* b, ckks_ct** out);   /* multiply(a, b): 3 polynomials */
+int ckks_relinearize(ckks_engine* e, const ckks_ct* a, ckks_ct** out);         /* engine_context.py:134-145 */
+int ckks_mul_const(ckks_engine* e, const ckks_ct* a, double re, double im, ckks_ct** out);  /* multiply(ct, float | constant plaintext) */
+int ckks_mul_plain(ckks_engine* e, const ckks_ct* a, const ckks_pt* p, ckks_ct** out);      /* multiply(ct, plaintext) */
+int ckks_add_const(ckks_engine* e, const ckks_ct* a, double re, double im, ckks_ct** out);  /* add_plain(ct, float) */
+int ckks_add_plain(ckks_engine* e, const ckks_ct* a, const ckks_pt* p, ckks_ct** out);      /* add(ct, plaintext) */
+int ckks_mul_i(ckks_engine* e, const ckks_ct* a, int sign, ckks_ct** out);                  /* exact multiply by +-i */
+int ckks_level_down(ckks_engine* e, ckks_ct* a, int level, ckks_ct** out);
+
+/* make_power_basis(ct, degree, relin_key) -> [ct^1 .. ct^degree] (engine_context.py:100-101) */
+int ckks_power_basis(ckks_engine* e, ckks_ct* a, int degree, ckks_ct** out /* degree handles */);
+/* conjugate(ct, conj_key) (engine_context.py:103-104) */
+int ckks_conjugate(ckks_engine* e, const ckks_ct* a, ckks_ct** out);
+/* rotate(ct, rot_key, steps): out = np.roll(slots, steps) (engine_context.py:127-132, shift_rows.py:35-37) */
+int ckks_rotate(ckks_engine* e, const ckks_ct* a, long steps, ckks_ct** out);
+/* several rotations of one ciphertext sharing one ModUp (mixcol_final.py:124-126, invmixcolumns_fhe.py:140-142) */
+int ckks_rotate_hoisted(ckks_engine* e, const ckks_ct* a, const long* steps, int nsteps, ckks_ct** out);
+
+/* Fused sparse LUT evaluation (xor4_lut.py:63-74, mixcol_final.py:80-99, invmixcolumns_fhe.py:76-90):
+ * out = sum_t c_t * A[p_t] * B[q_t] over the two 16-element power bases (NULL entries are unused),
+ * one tensor accumulation, ONE relinearisation, two rescales: result at min level - 2. */
+int ckks_lut2(ckks_engine* e, ckks_ct* const* A, ckks_ct* const* B, int nbasis, const int* p, const int* q,
+              const double* coef_re_im, int nterms, ckks_ct** out);
+/* Fused 1-D LUT (sub_bytes_lut.py:63-71): out_j = sum_k c_{j,k} X[k] for nout outputs sharing the basis. */
+int ckks_lut1(ckks_engine* e, ckks_ct* const* X, int nbasis, const double* coef_re_im /* [nout][nbasis][2] */,
+              int nout, ckks_ct** out);
+
+/* bootstrap(ct, relin, conj, bootstrap_key) (engine_context.py:147-162) */
+int ckks_bootstrap(ckks_engine* e, ckks_ct* a, ckks_ct** out);
+int ckks_bootstrap_out_level(const ckks_engine* e);
+
+/* ---- counters (per engine): key switches, limb-NTTs, rescales, ct*ct multiplications, bootstraps */
+int ckks_counters(const ckks_engine* e, long* out5);
+
+/* ---- raw access for the bit-exact parity tests against oracle/ (tests/ only; not used by the shim's hot path) */
+int ckks_ct_export(ckks_engine* e, const ckks_ct* ct, uint64_t* out /* [npoly][level+1][N] */);
+int ckks_ct_import(ckks_engine* e, int npoly, int level, const uint64_t* data, ckks_ct** out);
+int ckks_pt_export(ckks_engine* e, const ckks_pt* pt, uint64_t* out /* [level+1][N] */);
+int ckks_export_secret(ckks_engine* e, int64_t* coef_out /* [N] */);
+int ckks_export_public(ckks_engine* e, uint64_t* out /* [2][L+1][N] */);
+int ckks_export_switch_key(ckks_engine* e, uint64_t galois_or_0_for_relin, uint64_t* out /* [dnum][2][L+1+K][N] */);
+int ckks_test_ntt(ckks_engine* e, uint64_t* data /* [nrows][N], host, in place */, int nrows, const int* mods, int inverse);
+int ckks_test_automorph(ckks_engine* e, uint64_t* data /* [nrows][N] host, in place */, int nrows, uint64_t galois);
+int ckks_test_key_switch(ckks_engine* e, const uint64_t* poly /* [level+1][N] */, int level,
+                         uint64_t galois_or_0_for_relin, uint64_t* out /* [2][level+1][N] */);
+uint64_t ckks_galois_for_rotation(const ckks_engine* e, long steps);
+
+/* ---- timing helpers for bench.py: device-side timing on the engine's own stream (torch.cuda.Event only
+ * sees torch's current stream) */
+int ckks_timer_start(ckks_engine* e);
+int ckks_timer_stop_ms(ckks_engine* e, float* ms_out);
+/* micro-benchmarks on resident random data: returns average milliseconds per call over `iters` calls */
+int ckks_bench_ntt(ckks_engine* e, int nlimbs, int batches, int inverse, int iters, float* ms_out);
+int ckks_bench_rotate(ckks_engine* e, int level, int iters, float* ms_out);
+int ckks_bench_mul(ckks_engine* e, int level, int iters, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

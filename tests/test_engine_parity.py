@@ -1,0 +1,190 @@
+"""Bit-exact parity of the engine against the integer oracle (oracle/ckks_oracle.py) under identical
+parameters, keys and seed: parameters, keys, encrypt, decode, multiply, rotate, conjugate, constants,
+level alignment, power basis, raw NTT / automorphism / key-switch.
+
+The same test bodies run twice: on the emulation build of the CUDA sources (CPU, N = 2^12) and, marked
+`gpu`, on the product library on a B200 (N = 2^12 and N = 2^16).
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import backend
+from oracle.ckks_oracle import OracleCKKS
+from oracle.params import make_params
+
+CASES = [
+    pytest.param(("emu", 12, 6), id="emu-n12"),
+    pytest.param(("cuda", 12, 6), id="cuda-n12", marks=pytest.mark.gpu),
+    pytest.param(("cuda", 16, 5), id="cuda-n16", marks=pytest.mark.gpu),
+]
+
+
+class Pair:
+    def __init__(self, which, logn, levels, seed=5):
+        mod = backend.use_emulation() if which == "emu" else backend.use_cuda()
+        self.eng = mod.Engine(logn=logn, levels=levels, dnum=3, hamming_weight=64, seed=seed)
+        self.params = make_params(logn=logn, levels=levels, dnum=3, hamming_weight=64)
+        self.orc = OracleCKKS(self.params, seed=seed)
+        self.N = 1 << logn
+        self.n = self.N // 2
+        self.lib = self.eng._lib
+        self.sk = self.eng.create_secret_key()
+        self.pk = self.eng.create_public_key(self.sk)
+        self.rk = self.eng.create_relinearization_key(self.sk)
+        self.orc.keygen_secret()
+        self.orc.keygen_public()
+        self.orc.keygen_relin()
+
+    def export(self, ct):
+        a = np.zeros((ct.polynomial_count, ct.level + 1, self.N), dtype=np.uint64)
+        assert self.lib.ckks_ct_export(self.eng._ptr, ct._h, a) == 0
+        return a
+
+
+@pytest.fixture(scope="module", params=CASES)
+def pair(request):
+    which, logn, levels = request.param
+    return Pair(which, logn, levels)
+
+
+def test_parameters_agree(pair):
+    P = pair.eng.params()
+    assert P["q"] == pair.params.q and P["p"] == pair.params.p
+    assert P["scales"] == pair.params.scales
+    assert P["alpha"] == pair.params.alpha
+    assert all(x % (2 * pair.N) == 1 for x in P["q"] + P["p"])
+
+
+def test_keys_bit_exact(pair):
+    s = np.zeros(pair.N, dtype=np.int64)
+    pair.lib.ckks_export_secret(pair.eng._ptr, s)
+    assert np.array_equal(s, pair.orc.sk_coef)
+    assert int(np.abs(s).sum()) == 64
+    pk = np.zeros((2, pair.params.L + 1, pair.N), dtype=np.uint64)
+    pair.lib.ckks_export_public(pair.eng._ptr, pk)
+    assert np.array_equal(pk, pair.orc.pk)
+    ev = np.zeros(pair.orc.evk[0].shape, dtype=np.uint64)
+    pair.lib.ckks_export_switch_key(pair.eng._ptr, 0, ev)
+    assert np.array_equal(ev, pair.orc.evk[0])
+
+
+def test_raw_ntt_roundtrip_and_parity(pair):
+    rng = np.random.default_rng(1)
+    mods = list(range(len(pair.orc.moduli)))
+    a = np.stack([rng.integers(0, m, pair.N, dtype=np.uint64) for m in pair.orc.moduli])
+    b = a.copy()
+    marr = np.asarray(mods, dtype=np.int32)
+    assert pair.lib.ckks_test_ntt(pair.eng._ptr, b, len(mods), marr, 0) == 0
+    assert np.array_equal(b, pair.orc.ntt(a, mods))
+    assert pair.lib.ckks_test_ntt(pair.eng._ptr, b, len(mods), marr, 1) == 0
+    assert np.array_equal(b, a)
+    # edge values: 0, 1, q-1
+    e = np.zeros_like(a)
+    for i, m in enumerate(pair.orc.moduli):
+        e[i, 0], e[i, 1], e[i, -1] = 1, m - 1, m - 1
+    f = e.copy()
+    pair.lib.ckks_test_ntt(pair.eng._ptr, f, len(mods), marr, 0)
+    assert np.array_equal(f, pair.orc.ntt(e, mods))
+
+
+def test_raw_automorphism(pair):
+    rng = np.random.default_rng(2)
+    a = np.stack([rng.integers(0, m, pair.N, dtype=np.uint64) for m in pair.orc.moduli[:3]])
+    for g in (pair.orc.galois_for_rotation(1), pair.orc.galois_for_rotation(-7), pair.orc.galois_conj()):
+        b = a.copy()
+        assert pair.lib.ckks_test_automorph(pair.eng._ptr, b, 3, g) == 0
+        assert np.array_equal(b, pair.orc.automorph(a, g))
+    assert pair.lib.ckks_galois_for_rotation(pair.eng._ptr, 5) == pair.orc.galois_for_rotation(5)
+    assert pair.lib.ckks_galois_for_rotation(pair.eng._ptr, -5) == pair.orc.galois_for_rotation(-5)
+
+
+@pytest.mark.parametrize("level_off", [0, 2])
+def test_raw_key_switch(pair, level_off):
+    rng = np.random.default_rng(3)
+    level = pair.params.L - level_off
+    poly = np.stack([rng.integers(0, pair.params.q[i], pair.N, dtype=np.uint64) for i in range(level + 1)])
+    out = np.zeros((2, level + 1, pair.N), dtype=np.uint64)
+    assert pair.lib.ckks_test_key_switch(pair.eng._ptr, poly, level, 0, out) == 0
+    k0, k1 = pair.orc.key_switch(poly, level, 0)
+    assert np.array_equal(out[0], k0) and np.array_equal(out[1], k1)
+
+
+def test_encrypt_decrypt(pair):
+    rng = np.random.default_rng(0)
+    z = rng.normal(size=pair.n) + 1j * rng.normal(size=pair.n)
+    ct, oc = pair.eng.encrypt(z), pair.orc.encrypt(z)
+    assert np.array_equal(pair.export(ct), oc.c)
+    d, od = pair.eng.decrypt(ct), pair.orc.decrypt(oc)
+    assert np.array_equal(d, od)                      # fp64 embedding is bit-exact too (no FMA contraction)
+    assert np.abs(d - z).max() < 1e-8
+
+
+def test_homomorphic_ops_bit_exact(pair):
+    rng = np.random.default_rng(4)
+    eng, orc = pair.eng, pair.orc
+    z1 = np.exp(2j * np.pi * rng.random(pair.n))
+    z2 = np.exp(2j * np.pi * rng.random(pair.n))
+    c1, c2 = eng.encrypt(z1), eng.encrypt(z2)
+    o1, o2 = orc.encrypt(z1), orc.encrypt(z2)
+    m, om = eng.multiply(c1, c2, pair.rk), orc.mul_ct(o1, o2)
+    assert np.array_equal(pair.export(m), om.c)
+    assert np.abs(eng.decrypt(m) - z1 * z2).max() < 1e-7
+    for steps in (1, -3, pair.n // 4, 0):
+        r, orr = eng.rotate(c1, None, steps), orc.rotate(o1, steps)
+        assert np.array_equal(pair.export(r), orr.c)
+        assert np.abs(eng.decrypt(r) - np.roll(z1, steps)).max() < 1e-7      # SURVEY App. A-6 direction
+    cj, ocj = eng.conjugate(c1), orc.conjugate(o1)
+    assert np.array_equal(pair.export(cj), ocj.c)
+    assert np.abs(eng.decrypt(cj) - np.conj(z1)).max() < 1e-7
+    k, ok = eng.multiply(c1, 0.25 - 95.47j), orc.mul_const(o1, 0.25 - 95.47j)
+    assert np.array_equal(pair.export(k), ok.c)
+    # level alignment: level L-1 product plus a fresh level-L ciphertext
+    a, oa = eng.add(m, c1), orc.add_ct(om, o1)
+    assert np.array_equal(pair.export(a), oa.c)
+    s, os_ = eng.subtract(c2, m), orc.sub_ct(o2, om)
+    assert np.array_equal(pair.export(s), os_.c)
+    ac, oac = eng.add(c1, 1.0), orc.add_const(o1, 1.0)
+    assert np.array_equal(pair.export(ac), oac.c)
+    mask = (np.arange(pair.n) % 3 == 0).astype(np.complex128)
+    mp, omp = eng.multiply(c1, eng.encode(mask)), orc.mul_plain_vec(o1, mask)
+    assert np.array_equal(pair.export(mp), omp.c)
+    assert np.abs(eng.decrypt(mp) - z1 * mask).max() < 1e-7
+    z0 = eng.multiply(c1, 0.0)
+    assert z0.level == c1.level - 1 and np.abs(eng.decrypt(z0)).max() < 1e-9
+
+
+def test_power_basis_and_level_errors(pair):
+    rng = np.random.default_rng(6)
+    eng, orc = pair.eng, pair.orc
+    z = np.exp(2j * np.pi * rng.random(pair.n))
+    c, o = eng.encrypt(z), orc.encrypt(z)
+    pb, opb = eng.make_power_basis(c, 8, pair.rk), orc.power_basis(o, 8)
+    for x, y in zip(pb, opb):
+        assert np.array_equal(pair.export(x), y.c)
+    assert [x.level for x in pb] == [c.level - d for d in (0, 1, 2, 2, 3, 3, 3, 3)]
+    assert np.abs(eng.decrypt(pb[7]) - z ** 8).max() < 1e-6
+    low = eng.level_down(c, 1)
+    with pytest.raises(RuntimeError) as ei:
+        eng.make_power_basis(low, 8, pair.rk)
+    assert "level" in str(ei.value) and "positive" in str(ei.value)
+    bottom = eng.level_down(c, 0)
+    with pytest.raises(RuntimeError, match="positive"):
+        eng.multiply(bottom, bottom, pair.rk)
+    t3 = eng.multiply(c, c)                                   # no relin key: 3 polynomials
+    assert t3.polynomial_count == 3
+    r2 = eng.relinearize(t3, pair.rk)
+    assert np.abs(eng.decrypt(r2) - z * z).max() < 1e-7 and np.abs(eng.decrypt(t3) - z * z).max() < 1e-7
+    with pytest.raises(RuntimeError, match="should have 3 polynomials"):
+        eng.relinearize(c, pair.rk)
+
+
+def test_hoisted_rotations_decrypt(pair):
+    rng = np.random.default_rng(8)
+    z = np.exp(2j * np.pi * rng.random(pair.n))
+    c = pair.eng.encrypt(z)
+    steps = [pair.n // 4, pair.n // 2, 3 * pair.n // 4, 0, -1]
+    outs = pair.eng.rotate_many(c, None, steps)
+    for s, r in zip(steps, outs):
+        assert np.abs(pair.eng.decrypt(r) - np.roll(z, s)).max() < 1e-7
