@@ -94,6 +94,13 @@ int ckks_keygen_rotation(ckks_engine* e, const long* steps, int nsteps) {
         }
     });
 }
+int ckks_set_bootstrap_params(ckks_engine* e, int K, int deg, int r, int cts, int stc) {
+    return guard([&] {
+        if (e->E->boot) throw std::runtime_error("bootstrap key already created");
+        BootParams& b = e->E->prm.boot;
+        b.K = K; b.cheb_degree = deg; b.double_angle = r; b.cts_groups = cts; b.stc_groups = stc;
+    });
+}
 int ckks_keygen_bootstrap(ckks_engine* e) { return guard([&] { e->E->bootstrap_setup(); }); }
 
 int ckks_encode(ckks_engine* e, const double* z, int level, ckks_pt** out) {

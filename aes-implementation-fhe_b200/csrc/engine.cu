@@ -232,6 +232,7 @@ Engine::Engine(const Params& P) : prm(P) {
 
 Engine::~Engine() {
     try { dev::sync(st); } catch (...) {}
+    bootstrap_teardown();
     for (auto& kv : gkeys) dev::free(kv.second.d, st);
     for (auto& kv : perms) dev::free(kv.second, st);
     for (auto& kv : modup_tabs) { dev::free((void*)kv.second.hat, st); dev::free((void*)kv.second.hat_s, st); }
@@ -240,7 +241,6 @@ Engine::~Engine() {
     dev::free(sk_ntt, st);
     dev::free(pk, st);
     for (void* p : owned) dev::free(p, st);
-    boot.reset();
     try { dev::sync(st); } catch (...) {}
     dev::stream_destroy(st);
 }

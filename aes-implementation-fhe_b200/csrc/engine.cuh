@@ -54,7 +54,7 @@ struct BootParams {
     int cts_groups = 3, stc_groups = 3;             // matrices the (i)DFT is factored into
     int K = 25;                                     // bound on |I| in t = m + q0 I
     int cheb_degree = 63;
-    int double_angle = 2;
+    int double_angle = 3;
 };
 
 struct Params {
@@ -142,6 +142,7 @@ class Engine {
 
     // ---- bootstrapping (bootstrap.cu)
     void bootstrap_setup();
+    void bootstrap_teardown();
     Ct* bootstrap(Ct* a);
     int boot_out_level() const;
     Ct* mod_raise(Ct* a);

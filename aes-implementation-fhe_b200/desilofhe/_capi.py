@@ -61,6 +61,7 @@ def load():
         "ckks_keygen_secret": (i32, [vp]), "ckks_keygen_public": (i32, [vp]), "ckks_keygen_relin": (i32, [vp]),
         "ckks_keygen_conjugation": (i32, [vp]), "ckks_keygen_rotation": (i32, [vp, lngp, i32]),
         "ckks_keygen_bootstrap": (i32, [vp]),
+        "ckks_set_bootstrap_params": (i32, [vp, i32, i32, i32, i32, i32]),
         "ckks_encode": (i32, [vp, dp, i32, pp]),
         "ckks_encrypt": (i32, [vp, dp, i32, pp]),
         "ckks_decrypt": (i32, [vp, vp, dp]),

@@ -61,6 +61,8 @@ int ckks_keygen_relin(ckks_engine* e);
 int ckks_keygen_conjugation(ckks_engine* e);
 int ckks_keygen_rotation(ckks_engine* e, const long* steps, int nsteps);
 int ckks_keygen_bootstrap(ckks_engine* e);
+/* optional, before ckks_keygen_bootstrap: |I| bound K, Chebyshev degree, double-angle steps, matrices per DFT */
+int ckks_set_bootstrap_params(ckks_engine* e, int K, int cheb_degree, int double_angle, int cts_groups, int stc_groups);
 
 /* ---- data movement: encode / encrypt / decrypt (engine_context.py:56-63) */
 int ckks_encode(ckks_engine* e, const double* slots_re_im, int level, ckks_pt** out);
