@@ -181,7 +181,6 @@ static LinearPlan make_linear(Engine& E, const Diags& D, int level) {
 }
 
 // ------------------------------------------------------------------ evaluation helpers
-namespace {
 struct Arena {                      // temporaries of one bootstrap; everything but the result is freed
     Engine& E;
     std::vector<Ct*> v;
@@ -193,7 +192,6 @@ struct Arena {                      // temporaries of one bootstrap; everything 
     }
     ~Arena() { for (Ct* c : v) E.free_ct(c); }
 };
-}  // namespace
 
 static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
     if (a->level != P.level) throw std::runtime_error("bootstrap: linear transform applied at the wrong level");
@@ -347,8 +345,7 @@ Ct* Engine::mod_raise(Ct* a) {
         memset(&J, 0, sizeof(J));
         J.n = 1; J.nz = 2;
         J.szs = n; J.dzs = n;
-        ntt_inverse(low->d, coef, J, tabs, st);
-        n_ntt_limbs += 2;
+        run_ntt(low->d, coef, J, true, 2);
     }
     Ct* r = new_ct(2, top);
     std::vector<int> idx = mods_q(top);

@@ -279,6 +279,10 @@ uint64_t ckks_galois_for_rotation(const ckks_engine* e, long steps) { return e->
 int ckks_timer_start(ckks_engine* e) { return guard([&] { e->timer.start(e->E->st); }); }
 int ckks_timer_stop_ms(ckks_engine* e, float* ms) { return guard([&] { *ms = e->timer.stop_ms(e->E->st); }); }
 
+int ckks_profile_ntt_begin(ckks_engine* e) { return guard([&] { e->E->profile_begin(); }); }
+int ckks_profile_ntt_end(ckks_engine* e, double* ms, long* calls, long* limbs) {
+    return guard([&] { e->E->profile_end(ms, calls, limbs); });
+}
 int ckks_bench_ntt(ckks_engine* e, int nlimbs, int batches, int inverse, int iters, float* ms_out) {
     return guard([&] {
         Engine& E = *e->E;

@@ -331,9 +331,35 @@ void Engine::ntt_rows(u64* data, const std::vector<int>& rows, const std::vector
             J.rows[z][i] = J.srows[z][i] = (unsigned char)rows[i];
             J.mods[z][i] = (unsigned char)mods[i];
         }
-    if (inverse) ntt_inverse(data, data, J, tabs, st);
-    else ntt_forward(data, data, J, tabs, st);
-    n_ntt_limbs += (long)J.n * nz;
+    run_ntt(data, data, J, inverse, (long)J.n * nz);
+}
+
+// every NTT launch goes through here: limb accounting and, when profiling, a CUDA-event pair per call on the
+// engine's stream (bench.py's roofline leg: average duration and algorithmic bytes of the NTT kernels)
+void Engine::run_ntt(const u64* src, u64* dst, const NttJob& J, bool inverse, long limbs) {
+    dev::Timer* t = nullptr;
+    if (prof_on) {
+        if (prof_used == prof_timers.size()) prof_timers.emplace_back();
+        t = &prof_timers[prof_used++];
+        t->start(st);
+    }
+    if (inverse) ntt_inverse(src, dst, J, tabs, st);
+    else ntt_forward(src, dst, J, tabs, st);
+    if (t) { t->mark_stop(st); prof_limbs += limbs; prof_calls++; }
+    n_ntt_limbs += limbs;
+}
+void Engine::profile_begin() {
+    prof_on = true;
+    prof_used = 0;
+    prof_limbs = prof_calls = 0;
+    prof_ms = 0;
+}
+void Engine::profile_end(double* ms, long* calls, long* limbs) {
+    dev::sync(st);
+    double total = prof_ms;
+    for (size_t i = 0; i < prof_used; i++) total += prof_timers[i].elapsed_ms();
+    prof_on = false;
+    *ms = total; *calls = prof_calls; *limbs = prof_limbs;
 }
 
 // ------------------------------------------------------------------ Galois maps (spec S4)
@@ -643,8 +669,7 @@ Decomp Engine::decompose(const u64* d, int level) {
         memset(&J, 0, sizeof(J));
         J.n = nq; J.nz = 1;
         for (int i = 0; i < nq; i++) { J.rows[0][i] = J.srows[0][i] = (unsigned char)i; J.mods[0][i] = (unsigned char)i; }
-        ntt_inverse(d, coef, J, tabs, st);
-        n_ntt_limbs += nq;
+        run_ntt(d, coef, J, true, nq);
     }
     // per digit: fast basis conversion of its limbs to every other modulus of Q_level u P; the
     // digit's own limbs are copied from the NTT-domain input
@@ -652,6 +677,7 @@ Decomp Engine::decompose(const u64* d, int level) {
     memset(&J, 0, sizeof(J));
     J.nz = beta;
     J.szs = J.dzs = (size_t)rows * n;
+    long modup_limbs = 0;
     for (int j = 0; j < beta; j++) {
         const BaseConvTable& T = modup_table(level, j);
         launch_base_convert(ks, D.ext + (size_t)j * rows * n, coef, T, 1, 0, 0, st);
@@ -663,10 +689,10 @@ Decomp Engine::decompose(const u64* d, int level) {
             J.rows[j][t] = J.srows[j][t] = T.orow[t];
             J.mods[j][t] = T.tgt[t];
         }
-        n_ntt_limbs += T.nt;
+        modup_limbs += T.nt;
     }
     // one batched forward NTT over the converted rows of all digits (z = digit)
-    ntt_forward(D.ext, D.ext, J, tabs, st);
+    run_ntt(D.ext, D.ext, J, false, modup_limbs);
     release(coef);
     return D;
 }
@@ -720,8 +746,7 @@ void Engine::rescale_into(u64* out, const u64* in, int npoly, int level) {
         J.dzs = n;
         for (int z = 0; z < npoly; z++) { J.srows[z][0] = (unsigned char)level; J.rows[z][0] = 0; J.mods[z][0] = (unsigned char)level; }
         if (npoly > NTT_MAX_Z) throw std::runtime_error("rescale: too many polynomials");
-        ntt_inverse(in, last, J, tabs, st);
-        n_ntt_limbs += npoly;
+        run_ntt(in, last, J, true, npoly);
     }
     std::vector<int> lo = mods_q(level - 1);
     LimbList ll = limb_list(lo);

@@ -151,6 +151,9 @@ class Engine {
     // ---- low-level pieces (exposed through the C ABI for parity tests against the oracle)
     void ntt_rows(u64* data, const std::vector<int>& rows, const std::vector<int>& mods, bool inverse, int nz = 1,
                   size_t zstride = 0);
+    void run_ntt(const u64* src, u64* dst, const NttJob& J, bool inverse, long limbs);
+    void profile_begin();
+    void profile_end(double* ms, long* calls, long* limbs);
     Decomp decompose(const u64* d, int level);
     void ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out /* [2][level+1][N] */);
     void key_switch(const u64* d, int level, const EvalKey* evk, u64* out);
@@ -192,6 +195,11 @@ class Engine {
     double* d_ksi = nullptr;
     int* d_flag = nullptr;
     u64 enc_counter = 0;
+    bool prof_on = false;
+    std::vector<dev::Timer> prof_timers;
+    size_t prof_used = 0;
+    long prof_limbs = 0, prof_calls = 0;
+    double prof_ms = 0;
     ScalarList sl_pinv;                    // P^-1 mod q_i
     std::vector<ScalarList> sl_qinv;       // [l]: q_l^-1 mod q_i, i < l
 

@@ -104,6 +104,13 @@ struct Timer {
         CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
         return ms;
     }
+    void mark_stop(dev_stream s) { CUDA_CHECK(cudaEventRecord(b, s)); }
+    float elapsed_ms() {
+        CUDA_CHECK(cudaEventSynchronize(b));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+        return ms;
+    }
 };
 }  // namespace dev
 
@@ -182,11 +189,10 @@ inline void host_free_pinned(void* p) { ::free(p); }
 struct Timer {
     struct timespec t0;
     void start(dev_stream) { clock_gettime(CLOCK_MONOTONIC, &t0); }
-    float stop_ms(dev_stream) {
-        struct timespec t1;
-        clock_gettime(CLOCK_MONOTONIC, &t1);
-        return (float)((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
-    }
+    struct timespec t1s;
+    float stop_ms(dev_stream s) { mark_stop(s); return elapsed_ms(); }
+    void mark_stop(dev_stream) { clock_gettime(CLOCK_MONOTONIC, &t1s); }
+    float elapsed_ms() { return (float)((t1s.tv_sec - t0.tv_sec) * 1e3 + (t1s.tv_nsec - t0.tv_nsec) * 1e-6); }
 };
 }  // namespace dev
 

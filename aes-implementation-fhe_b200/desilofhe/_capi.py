@@ -96,6 +96,8 @@ def load():
         "ckks_galois_for_rotation": (u64, [vp, lng]),
         "ckks_timer_start": (i32, [vp]),
         "ckks_timer_stop_ms": (i32, [vp, C.POINTER(C.c_float)]),
+        "ckks_profile_ntt_begin": (i32, [vp]),
+        "ckks_profile_ntt_end": (i32, [vp, C.POINTER(dbl), C.POINTER(lng), C.POINTER(lng)]),
         "ckks_bench_ntt": (i32, [vp, i32, i32, i32, i32, C.POINTER(C.c_float)]),
         "ckks_bench_rotate": (i32, [vp, i32, i32, C.POINTER(C.c_float)]),
         "ckks_bench_mul": (i32, [vp, i32, i32, C.POINTER(C.c_float)]),

@@ -132,6 +132,10 @@ uint64_t ckks_galois_for_rotation(const ckks_engine* e, long steps);
  * sees torch's current stream) */
 int ckks_timer_start(ckks_engine* e);
 int ckks_timer_stop_ms(ckks_engine* e, float* ms_out);
+/* per-call CUDA-event timing of every NTT launch between begin and end (bench.py roofline leg):
+ * total milliseconds inside NTT kernels, number of batched calls, number of limb transforms */
+int ckks_profile_ntt_begin(ckks_engine* e);
+int ckks_profile_ntt_end(ckks_engine* e, double* ms_out, long* calls_out, long* limbs_out);
 /* micro-benchmarks on resident random data: returns average milliseconds per call over `iters` calls */
 int ckks_bench_ntt(ckks_engine* e, int nlimbs, int batches, int inverse, int iters, float* ms_out);
 int ckks_bench_rotate(ckks_engine* e, int level, int iters, float* ms_out);

@@ -1,0 +1,138 @@
+"""The AES-on-CKKS host stack on the real engine arithmetic (BASELINE.json configs 1, 2, 3, 5).
+
+Byte-level truth: FIPS-197 (via `cryptography` AES-ECB and the plain round model of bench.py) and the
+reference-semantics slot stand-in (oracle/slot_standin.py, pinned to the unchanged reference modules by
+tests/golden).  CPU cases run the emulation build at N = 2^12; `gpu` cases run the product library at N = 2^16.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+
+import backend
+import aes_fhe
+from bench import plain_round
+from oracle import slot_standin as ss
+
+CASES = [
+    pytest.param(("emu", 12, 64), id="emu-n12"),
+    pytest.param(("cuda", 16, 192), id="cuda-n16", marks=pytest.mark.gpu),
+]
+
+
+def ecb(key: bytes, data: bytes) -> bytes:
+    e = Cipher(algorithms.AES(key), modes.ECB()).encryptor()
+    return e.update(data) + e.finalize()
+
+
+def make_pipe(ctx):
+    co = aes_fhe.load_all_coeffs()
+    x4 = aes_fhe.XOR4LUT(ctx, co["xor4"])
+    return aes_fhe.AESPipeline(ctx, co, mixcolumns=aes_fhe.MixColFinal(ctx, x4),
+                               inv_mixcolumns=aes_fhe.InvMixColumnsFHE(ctx, x4), use_hard_renorm_between_steps=True)
+
+
+@pytest.fixture(scope="module", params=CASES)
+def boot_ctx(request):
+    which, logn, hw = request.param
+    mod = backend.use_emulation() if which == "emu" else backend.use_cuda()
+    ctx = aes_fhe.EngineContext(1, mode="gpu", thread_count=1, backend=mod, logn=logn, levels=21, fresh_level=14,
+                                hamming_weight=hw)
+    return which, ctx
+
+
+def test_bootstrap_precision_and_levels(boot_ctx):
+    which, ctx = boot_ctx
+    eng = ctx.engine
+    n = eng.slot_count
+    rng = np.random.default_rng(0)
+    z = np.exp(2j * np.pi * rng.random(n))
+    out = ctx.bootstrap(ctx.to_intt(ctx.encrypt(z)))
+    assert out.level == eng._lib.ckks_bootstrap_out_level(eng._ptr) >= 5         # >= 5 after bootstrap
+    err = np.abs(ctx.decrypt(out) - z).max()
+    assert err < 2e-3, err                  # stated tolerance: 9 bits worst case at N = 2^16
+    # the state encoding: ones everywhere, codewords on the stride grid
+    v = np.ones(n, dtype=np.complex128)
+    v[:: n // 16] = np.exp(-2j * np.pi * np.arange(16) / 16)
+    err2 = np.abs(ctx.decrypt(ctx.bootstrap(ctx.encrypt(v))) - v).max()
+    assert err2 < 2e-3, err2
+    assert ctx.bootstrap_stats()["count"] == 2
+
+
+def test_config1_ark_subbytes_fips_vector(boot_ctx):
+    """configs[0]: AddRoundKey + SubBytes on the FIPS-197 C.1 state."""
+    which, ctx = boot_ctx
+    pipe = make_pipe(ctx)
+    key = np.frombuffer(bytes.fromhex("000102030405060708090a0b0c0d0e0f"), dtype=np.uint8)
+    pt = np.frombuffer(bytes.fromhex("00112233445566778899aabbccddeeff"), dtype=np.uint8)
+    sbox, _ = aes_fhe.tables.sbox_tables()
+    c0 = ctx.engine.counters()
+    a = pipe.add_round_key(*pipe.encoder.encode(pt), *pipe.encoder.encode(key))
+    assert bytes(pipe.encoder.decode(*a)).hex() == "00102030405060708090a0b0c0d0e0f0"    # golden enc.r0.ark
+    stride = ctx.engine.slot_count // 16
+    assert abs(np.abs(ctx.decrypt(a[0])[::stride][:16]) - 256.0).max() < 1e-3           # H3: XOR output modulus 256
+    s = pipe.sub_bytes(*pipe._renorm_pair(*a))
+    assert bytes(pipe.encoder.decode(*s)) == bytes(sbox[pt ^ key])
+    c1 = ctx.engine.counters()
+    assert c1["mul_cc"] - c0["mul_cc"] == 291                 # 291 ct*ct, 162 conjugations
+    assert c1["keyswitch"] - c0["keyswitch"] == 291 + 162
+    # per-stage slots against the reference-semantics stand-in: stated tolerance 1e-4 on unit-modulus slots
+    sctx = aes_fhe.EngineContext(1, mode="cpu", thread_count=1, backend=ss, slot_count=ctx.engine.slot_count)
+    sp = make_pipe(sctx)
+    ref = sp.sub_bytes(*sp._renorm_pair(*sp.add_round_key(*sp.encoder.encode(pt), *sp.encoder.encode(key))))
+    for got, want in zip(s, ref):
+        assert np.abs(ctx.decrypt(got)[::stride][:16] - sctx.decrypt(want)[::stride][:16]).max() < 1e-4
+
+
+def test_config2_one_round_as_shipped_matches_standin(boot_ctx):
+    """configs[1] on the as-shipped flow (column-first ShiftRows + row-major MixColumns): bytes must equal
+    the reference-semantics stand-in running the same unchanged flow."""
+    which, ctx = boot_ctx
+    pipe = make_pipe(ctx)
+    rng = np.random.RandomState(0)
+    state, key = rng.randint(0, 256, 16).astype(np.uint8), rng.randint(0, 256, 16).astype(np.uint8)
+    c0 = ctx.engine.counters()
+    out = pipe.encrypt_round(*pipe.encoder.encode(state), *pipe.encoder.encode(key))
+    c1 = ctx.engine.counters()
+    sctx = aes_fhe.EngineContext(1, mode="cpu", thread_count=1, backend=ss, slot_count=ctx.engine.slot_count)
+    sp = make_pipe(sctx)
+    want = sp.encoder.decode(*sp.encrypt_round(*sp.encoder.encode(state), *sp.encoder.encode(key)))
+    assert bytes(pipe.encoder.decode(*out)) == bytes(want)
+    assert c1["bootstrap"] - c0["bootstrap"] == 2
+    assert c1["mul_cc"] - c0["mul_cc"] == 1034 + 2 * 38      # SURVEY App. B round count + EvalMod multiplications
+
+
+def test_config5_batched_fips_round(boot_ctx):
+    """configs[4] shape: every stride position carries an independent block; one FIPS-197 round (R2+R3 driver)."""
+    which, ctx = boot_ctx
+    pipe = make_pipe(ctx)
+    drv = aes_fhe.FipsDriver(pipe, batched=True)
+    stride = ctx.engine.slot_count // 16
+    rng = np.random.default_rng(5)
+    blocks = rng.integers(0, 256, (stride, 16), dtype=np.uint8)
+    key = np.frombuffer(bytes.fromhex("000102030405060708090a0b0c0d0e0f"), dtype=np.uint8)
+    rks = aes_fhe.expand_aes128_key(key)
+    rk_ct = pipe._prepare_round_keys([drv._perm(rk) for rk in rks])
+    out = pipe.encrypt_round(*pipe.encoder.encode(drv._perm(blocks)), *rk_ct[1])
+    assert np.array_equal(drv.decode(*out), plain_round(blocks, rks[1]))
+
+
+@pytest.mark.gpu
+def test_config3_full_fips_encryption_gpu():
+    """configs[2]: full AES-128 encryption of 2048 packed blocks with 18 bootstraps, bit-exact with FIPS-197."""
+    mod = backend.use_cuda()
+    ctx = aes_fhe.EngineContext(1, mode="gpu", thread_count=1, backend=mod, logn=16, levels=21, fresh_level=14)
+    pipe = make_pipe(ctx)
+    drv = aes_fhe.FipsDriver(pipe, batched=True)
+    stride = ctx.engine.slot_count // 16
+    rng = np.random.default_rng(7)
+    blocks = rng.integers(0, 256, (stride, 16), dtype=np.uint8)
+    blocks[0] = np.frombuffer(bytes.fromhex("00112233445566778899aabbccddeeff"), dtype=np.uint8)
+    key = bytes.fromhex("000102030405060708090a0b0c0d0e0f")
+    rks = aes_fhe.expand_aes128_key(np.frombuffer(key, dtype=np.uint8))
+    got = drv.decode(*drv.encrypt(blocks, rks))
+    assert bytes(got[0]).hex() == "69c4e0d86a7b0430d8cdb78070b4c55a"                     # FIPS-197 C.1
+    want = np.frombuffer(ecb(key, blocks.tobytes()), dtype=np.uint8).reshape(stride, 16)
+    assert np.array_equal(got, want)
+    assert ctx.bootstrap_stats()["count"] == 18
