@@ -25,7 +25,7 @@ def _load_backend(backend):
 class EngineContext:
     def __init__(self, signature: int, *, max_level: int = 17, use_bootstrap: bool = True,
                  use_multiparty: bool = False, mode: str = "cpu", device_id: int = 0,
-                 thread_count: int, backend=None, **engine_kwargs):
+                 thread_count: int, backend=None, fused: bool = True, **engine_kwargs):
         be = _load_backend(backend)
         self._ct_type = be.Ciphertext
         common = dict(mode=mode, use_multiparty=use_multiparty, thread_count=thread_count,
@@ -47,6 +47,9 @@ class EngineContext:
         self.conjugation_key = eng.create_conjugation_key(self.secret_key)
         self.rotation_key = eng.create_rotation_key(self.secret_key)
         self.bootstrap_key = eng.create_bootstrap_key(self.secret_key)
+        # fused entry points of the B200 engine (hoisted rotations, fused LUT multiply-accumulate); a backend that
+        # only has the reference surface (or `fused=False`) is driven call for call exactly as the reference does
+        self.fused = bool(fused) and all(hasattr(eng, n) for n in ("lut2", "lincomb", "rotate_many"))
         self._bs_count = 0
         self._bs_total_s = 0.0
 
@@ -105,6 +108,18 @@ class EngineContext:
 
     def rotate(self, ct, steps: int):
         return self.engine.rotate(ct, self.rotation_key, steps)
+
+    # ---- fused entry points (only when the backend has them; see `self.fused`) ----
+    def rotate_many(self, ct, steps):
+        if self.fused:
+            return self.engine.rotate_many(ct, self.rotation_key, list(steps))
+        return [self.rotate(ct, s) for s in steps]
+
+    def lut2(self, basis_a, basis_b, terms):
+        return self.engine.lut2(basis_a, basis_b, terms)
+
+    def lincomb(self, cts, coeffs):
+        return self.engine.lincomb(cts, coeffs)
 
     def relinearize(self, ct):
         try:

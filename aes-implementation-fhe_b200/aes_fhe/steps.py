@@ -74,6 +74,7 @@ class XOR4LUT:
             (p, q): _const_pt(ctx, self.sc, coeffs[p, q])
             for p in range(16) for q in range(16) if abs(coeffs[p, q]) > 1e-12
         }
+        self.terms = [(p, q, complex(coeffs[p, q])) for (p, q) in self.pt]
 
     def _build_power_basis_16(self, ct) -> Dict[int, Any]:
         eng = self.ctx
@@ -104,6 +105,9 @@ class XOR4LUT:
         eng = self.ctx
         A = self._build_power_basis_16(a_ct)
         B = self._build_power_basis_16(b_ct)
+        if getattr(eng, "fused", False):
+            # same polynomial, one tensor accumulation and ONE relinearisation (csrc/lut.cu) instead of 64
+            return eng.lut2([A.get(k) for k in range(16)], [B.get(k) for k in range(16)], self.terms)
         acc = eng.sub(A[0], A[0])
         for (p, q), pt in self.pt.items():
             prod = eng.multiply(A[p], B[q])
@@ -147,9 +151,32 @@ class SubBytesLUT:
         self.deg16 = min(max(self.ks_lift) if self.ks_lift else 0, 8)
         self.pt_lift = {k: _const_pt(ctx, self.sc, lift[k]) for k in self.ks_lift}
         self.c0_lift = lift[0]
+        self._lift = lift
+        self.ks_hi_nz = [k for k in self.ks_hi if k != 0]
+        self.ks_lo_nz = [k for k in self.ks_lo if k != 0]
+
+    def _poly_fused(self, pos: List[Any], period: int, coeffs, ks, c0):
+        """c0 + sum_k c_k X^k with X^(period-k) = conj(X^k):  sum_{k<=len(pos)} c_k X^k + conj(sum conj(c_k) X^(period-k)).
+        One fused linear combination per half and ONE conjugation, instead of one conjugation per high power."""
+        eng = self.ctx
+        direct = [k for k in ks if k <= len(pos)]
+        mirror = [k for k in ks if k > len(pos)]
+        acc = eng.lincomb([pos[k - 1] for k in direct], [coeffs[k] for k in direct]) if direct else None
+        if mirror:
+            m = eng.conjugate(eng.lincomb([pos[period - k - 1] for k in mirror], [np.conj(coeffs[k]) for k in mirror]))
+            acc = m if acc is None else eng.add(acc, m)
+        return eng.add_plain(acc, c0)
 
     def apply(self, ct_hi, ct_lo) -> Pair:
         eng = self.ctx
+        if getattr(eng, "fused", False):
+            pos16 = eng.make_power_basis(ct_lo, self.deg16)
+            lift = self._lift
+            lifted = self._poly_fused(pos16, 16, lift, self.ks_lift, self.c0_lift)
+            ct_b = eng.multiply(ct_hi, lifted)
+            pos256 = eng.make_power_basis(ct_b, self.deg256)
+            return (self._poly_fused(pos256, 256, self.hi, self.ks_hi_nz, self.c0_hi),
+                    self._poly_fused(pos256, 256, self.lo, self.ks_lo_nz, self.c0_lo))
         lifted = eng.add_plain(eng.multiply(ct_lo, 0.0), self.c0_lift)
         pos16 = eng.make_power_basis(ct_lo, self.deg16) if self.deg16 > 0 else []
         for k in self.ks_lift:
@@ -243,8 +270,12 @@ class _MixBase:
             basis[k] = eng.conjugate(pos[15 - k])
         return basis
 
-    def _eval2(self, ct_hi, ct_lo, mult: int, which: str):
+    def _eval2(self, ct_hi, ct_lo, mult: int, which: str, bases=None):
         eng = self.ctx
+        if getattr(eng, "fused", False):
+            bx, by = bases if bases is not None else (self._basis16(ct_hi), self._basis16(ct_lo))
+            terms = [(p, q, complex(c)) for p, q, c in tables.gf_mult_entries(mult, which)]
+            return eng.lut2([bx.get(k) for k in range(16)], [by.get(k) for k in range(16)], terms)
         bx = self._basis16(ct_hi)
         by = self._basis16(ct_lo)
         pts = self._coeffs.load_plaintexts(eng, mult, which)
@@ -256,12 +287,20 @@ class _MixBase:
         return acc
 
     def _gf(self, mult: int, ct_hi, ct_lo) -> Pair:
+        if getattr(self.ctx, "fused", False):
+            # the reference rebuilds both 16-power bases for the hi and the lo table (mixcol_final.py:82-83);
+            # they are identical, so the fused path builds them once
+            bases = (self._basis16(ct_hi), self._basis16(ct_lo))
+            return (self._eval2(ct_hi, ct_lo, mult, "hi", bases), self._eval2(ct_hi, ct_lo, mult, "lo", bases))
         return self._eval2(ct_hi, ct_lo, mult, "hi"), self._eval2(ct_hi, ct_lo, mult, "lo")
 
     def _col_shift_rowmajor(self, ct, k_up: int):
         return self.ctx.rotate(ct, -4 * k_up * self.stride)
 
     def _shifts(self, ct_hi, ct_lo):
+        if getattr(self.ctx, "fused", False):      # rot1..3 of one ciphertext share one ModUp (hoisting)
+            steps = [-4 * k * self.stride for k in (1, 2, 3)]
+            return list(zip(self.ctx.rotate_many(ct_hi, steps), self.ctx.rotate_many(ct_lo, steps)))
         return [(self._col_shift_rowmajor(ct_hi, k), self._col_shift_rowmajor(ct_lo, k)) for k in (1, 2, 3)]
 
     def _xor_pair(self, a: Pair, b: Pair) -> Pair:

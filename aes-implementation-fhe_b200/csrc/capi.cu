@@ -164,12 +164,11 @@ int ckks_lut2(ckks_engine* e, ckks_ct* const* A, ckks_ct* const* B, int nbasis, 
         *out = H(e->E->lut2(a, b, p, q, coef, nterms));
     });
 }
-int ckks_lut1(ckks_engine* e, ckks_ct* const* X, int nbasis, const double* coef, int nout, ckks_ct** out) {
+int ckks_lincomb(ckks_engine* e, ckks_ct* const* X, int n, const double* coef, ckks_ct** out) {
     return guard([&] {
-        std::vector<Ct*> x(nbasis);
-        for (int i = 0; i < nbasis; i++) x[i] = C(X[i]);
-        std::vector<Ct*> v = e->E->lut1(x, coef, nout);
-        for (int i = 0; i < nout; i++) out[i] = H(v[i]);
+        std::vector<Ct*> x(n);
+        for (int i = 0; i < n; i++) x[i] = C(X[i]);
+        *out = H(e->E->lincomb(x, coef, n));
     });
 }
 int ckks_bootstrap(ckks_engine* e, ckks_ct* a, ckks_ct** out) { return guard([&] { *out = H(e->E->bootstrap(C(a))); }); }

@@ -237,6 +237,8 @@ Engine::~Engine() {
     for (auto& kv : perms) dev::free(kv.second, st);
     for (auto& kv : modup_tabs) { dev::free((void*)kv.second.hat, st); dev::free((void*)kv.second.hat_s, st); }
     for (auto& kv : moddown_tabs) { dev::free((void*)kv.second.hat, st); dev::free((void*)kv.second.hat_s, st); }
+    for (auto& kv : const_tabs) dev::free(kv.second, st);
+    for (auto& kv : index_tabs) dev::free(kv.second, st);
     dev::free(relin.d, st);
     dev::free(sk_ntt, st);
     dev::free(pk, st);

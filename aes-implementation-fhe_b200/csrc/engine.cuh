@@ -137,7 +137,8 @@ class Engine {
     Ct* copy(const Ct* a);
     Ct* lut2(const std::vector<Ct*>& A, const std::vector<Ct*>& B, const int* p, const int* q, const double* coef,
              int nterms);
-    std::vector<Ct*> lut1(const std::vector<Ct*>& X, const double* coef, int nout);
+    Ct* lincomb(const std::vector<Ct*>& X, const double* coef, int n);
+    const u64* const_table(const double* coef_re_im, int n, int scale_level, int level);
     Ct* drop_to(const Ct* a, int level);         // plain limb drop (scale unchanged): internal/bootstrap use
 
     // ---- bootstrapping (bootstrap.cu)
@@ -190,6 +191,8 @@ class Engine {
     std::map<u64, u32*> perms;
     std::map<std::pair<int, int>, BaseConvTable> modup_tabs;
     std::map<int, BaseConvTable> moddown_tabs;
+    std::map<u64, u64*> const_tabs;                 // LUT constants by content hash
+    std::map<u64, unsigned char*> index_tabs;       // LUT term index lists
     std::vector<void*> owned;              // device tables freed in the destructor
     u32* d_rot = nullptr;
     double* d_ksi = nullptr;

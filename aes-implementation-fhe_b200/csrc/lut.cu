@@ -1,8 +1,251 @@
-// lut.cu -- fused sparse LUT evaluation (placeholder until the fused kernels land)
+// lut.cu -- fused sparse multiply-accumulate over ciphertext power bases (the LUT polynomials of the
+// Zeta16 encoding: reference xor4_lut.py:63-74, mixcol_final.py:80-99, invmixcolumns_fhe.py:76-90,
+// sub_bytes_lut.py:63-71).
+//
+//   lut2:    sum_t c_t * A[p_t] (x) B[q_t]   as ONE 3-polynomial accumulation, ONE relinearisation and two
+//            rescales, instead of one ct*ct multiplication (key switch + rescale) per term.  Terms are
+//            grouped by p:  sum_p A_p (x) (sum_q c_pq B_q), so the kernel does |P| tensor products.
+//   lincomb: sum_k c_k * X[k] with one rescale per distinct input level (not one per term).
+//
+// Constants follow spec S7 (two scalars per limb).  Algorithmic bytes of k_lut2:
+// 2(|P|+|Q|)(l+1) N w read + 3(l+1) N w written.
+#include <algorithm>
+
 #include "engine.cuh"
-namespace ckks {
-Ct* Engine::lut2(const std::vector<Ct*>&, const std::vector<Ct*>&, const int*, const int*, const double*, int) {
-    throw std::runtime_error("lut2: not built yet");
+
+#define LUT_MAX_BASIS 16
+#define LINCOMB_MAX 128
+
+struct Lut2Args {
+    const u64* a[LUT_MAX_BASIS];       // basis ciphertexts, all at the same level: [2][rows][N]
+    const u64* b[LUT_MAX_BASIS];
+    const unsigned char* tp;           // [nterms] p index, sorted by p
+    const unsigned char* tq;           // [nterms]
+    const u64* consts;                 // [rows][2 halves][nterms][2] = {c, shoup(c)}
+    int nterms, rows;
+};
+struct LinCombArgs {
+    const u64* x[LINCOMB_MAX];         // [npoly][rows][N] each (same level)
+    const u64* consts;                 // [rows][2][nterms][2]
+    int nterms, rows;
+};
+
+namespace {
+
+// d[3][rows][N] = sum over p-groups of A_p (x) (sum_q c_pq B_q)
+__global__ void __launch_bounds__(256)
+k_lut2(KShape S, u64* __restrict__ d, Lut2Args G, LimbList L) {
+    const int row = blockIdx.y;
+    const ModConst m = S.mc[L.idx[row]];
+    const size_t N = (size_t)1 << S.logn, P = (size_t)G.rows << S.logn;
+    const int half = blockIdx.x < (gridDim.x >> 1) ? 0 : 1;
+    const u64* cst = G.consts + ((size_t)(row * 2 + half) * G.nterms) * 2;
+    FOR_THREADS {
+        const size_t i = (size_t)row * N + blockIdx.x * 256 + threadIdx.x;
+        u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0, h2 = 0, l2 = 0;
+        int t = 0, groups = 0;
+        while (t < G.nterms) {
+            const int p = ldg(G.tp + t);
+            u64 u0 = 0, u1 = 0;
+            int cnt = 0;
+            for (; t < G.nterms && ldg(G.tp + t) == p; t++) {
+                const u64* bq = G.b[ldg(G.tq + t)];
+                const u64 c = ldg(cst + 2 * t), cs = ldg(cst + 2 * t + 1);
+                u0 += shoup_mul(ldg(bq + i), c, cs, m.q);
+                u1 += shoup_mul(ldg(bq + i + P), c, cs, m.q);
+                if ((++cnt & 7) == 0) { u0 = barrett_reduce64(u0, m); u1 = barrett_reduce64(u1, m); }
+            }
+            u0 = barrett_reduce64(u0, m);
+            u1 = barrett_reduce64(u1, m);
+            const u64 a0 = ldg(G.a[p] + i), a1 = ldg(G.a[p] + i + P);
+            mac128(h0, l0, a0, u0);
+            mac128(h1, l1, a0, u1);
+            mac128(h1, l1, a1, u0);
+            mac128(h2, l2, a1, u1);
+            if ((++groups & 1) == 0) {                 // keep the 128-bit sums below 4 q^2
+                l0 = barrett_reduce128(h0, l0, m); h0 = 0;
+                l1 = barrett_reduce128(h1, l1, m); h1 = 0;
+                l2 = barrett_reduce128(h2, l2, m); h2 = 0;
+            }
+        }
+        d[i] = barrett_reduce128(h0, l0, m);
+        d[i + P] = barrett_reduce128(h1, l1, m);
+        d[i + 2 * P] = barrett_reduce128(h2, l2, m);
+    }
 }
-std::vector<Ct*> Engine::lut1(const std::vector<Ct*>&, const double*, int) { throw std::runtime_error("lut1: not built yet"); }
+
+// out[poly][rows][N] = sum_t x_t * c_t  (blockIdx.z = polynomial)
+__global__ void __launch_bounds__(256)
+k_lincomb(KShape S, u64* __restrict__ out, LinCombArgs G, LimbList L) {
+    const int row = blockIdx.y;
+    const ModConst m = S.mc[L.idx[row]];
+    const size_t N = (size_t)1 << S.logn, P = (size_t)G.rows << S.logn;
+    const int half = blockIdx.x < (gridDim.x >> 1) ? 0 : 1;
+    const u64* cst = G.consts + ((size_t)(row * 2 + half) * G.nterms) * 2;
+    FOR_THREADS {
+        const size_t i = blockIdx.z * P + (size_t)row * N + blockIdx.x * 256 + threadIdx.x;
+        u64 acc = 0;
+        for (int t = 0; t < G.nterms; t++) {
+            acc += shoup_mul(ldg(G.x[t] + i), ldg(cst + 2 * t), ldg(cst + 2 * t + 1), m.q);
+            if ((t & 7) == 7) acc = barrett_reduce64(acc, m);
+        }
+        out[i] = barrett_reduce64(acc, m);
+    }
+}
+
+}  // namespace
+
+namespace ckks {
+
+// device table of constants {c, shoup(c)} laid out [row][half][term]; cached by content
+const u64* Engine::const_table(const double* coef_re_im, int n, int scale_level, int level) {
+    // FNV-1a over the coefficient bytes + shape
+    u64 h = 1469598103934665603ull;
+    const unsigned char* bytes = reinterpret_cast<const unsigned char*>(coef_re_im);
+    for (size_t i = 0; i < (size_t)n * 16; i++) { h ^= bytes[i]; h *= 1099511628211ull; }
+    h ^= (u64)n * 0x9E3779B97F4A7C15ull + ((u64)scale_level << 20) + ((u64)level << 8);
+    auto it = const_tabs.find(h);
+    if (it != const_tabs.end()) return it->second;
+    const int rows = level + 1;
+    std::vector<int> idx = mods_q(level);
+    std::vector<u64> host((size_t)rows * 2 * n * 2);
+    ScalarList cp, cm;
+    for (int t = 0; t < n; t++) {
+        const_residues(coef_re_im[2 * t], coef_re_im[2 * t + 1], scales[scale_level], idx, cp, cm);
+        for (int r = 0; r < rows; r++) {
+            u64* p0 = &host[(((size_t)r * 2 + 0) * n + t) * 2];
+            u64* p1 = &host[(((size_t)r * 2 + 1) * n + t) * 2];
+            p0[0] = cp.v[r]; p0[1] = cp.vs[r];
+            p1[0] = cm.v[r]; p1[1] = cm.vs[r];
+        }
+    }
+    u64* d = alloc(host.size());
+    dev::h2d(d, host.data(), host.size() * sizeof(u64), st);
+    dev::sync(st);
+    const_tabs[h] = d;
+    return d;
+}
+
+Ct* Engine::lut2(const std::vector<Ct*>& A, const std::vector<Ct*>& B, const int* p, const int* q, const double* coef,
+                 int nterms) {
+    if (!has_relin) throw std::runtime_error("lut2 needs a relinearisation key");
+    if (nterms < 1) throw std::runtime_error("lut2: empty term list");
+    if ((int)A.size() > LUT_MAX_BASIS || A.size() != B.size()) throw std::runtime_error("lut2: bad basis size");
+    // sort terms by p (stable), find the common level
+    std::vector<int> order(nterms);
+    for (int t = 0; t < nterms; t++) order[t] = t;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return p[x] < p[y]; });
+    int level = L();
+    for (int t = 0; t < nterms; t++) {
+        if (p[t] < 0 || p[t] >= (int)A.size() || q[t] < 0 || q[t] >= (int)B.size() || !A[p[t]] || !B[q[t]])
+            throw std::runtime_error("lut2: term refers to a missing basis element");
+        if (A[p[t]]->npoly != 2 || B[q[t]]->npoly != 2) throw PolyCountError("lut2: operands should have 2 polynomials");
+        level = std::min(level, std::min(A[p[t]]->level, B[q[t]]->level));
+    }
+    need_levels(level, 2, "lut2");
+    Lut2Args G;
+    memset(&G, 0, sizeof(G));
+    std::vector<unsigned char> tp(nterms), tq(nterms);
+    std::vector<double> cs(2 * (size_t)nterms);
+    for (int t = 0; t < nterms; t++) {
+        const int s = order[t];
+        tp[t] = (unsigned char)p[s];
+        tq[t] = (unsigned char)q[s];
+        cs[2 * t] = coef[2 * s];
+        cs[2 * t + 1] = coef[2 * s + 1];
+        G.a[p[s]] = level_down(A[p[s]], level)->d;
+        G.b[q[s]] = level_down(B[q[s]], level)->d;
+    }
+    // constants at scale S[level-1]: S_l^2 * S_{l-1} / (q_l q_{l-1}) = S_{l-2}
+    G.consts = const_table(cs.data(), nterms, level - 1, level);
+    // term index lists: cached next to the constants (same content hash + tag)
+    std::vector<double> tagged(2 * (size_t)nterms);
+    for (int t = 0; t < nterms; t++) { tagged[2 * t] = tp[t]; tagged[2 * t + 1] = tq[t]; }
+    u64 h = 1469598103934665603ull;
+    for (int t = 0; t < nterms; t++) { h ^= tp[t] + 256u * tq[t] + 65536u * (u64)t; h *= 1099511628211ull; }
+    auto it = index_tabs.find(h);
+    if (it == index_tabs.end()) {
+        unsigned char* dtab = (unsigned char*)dev::alloc(2 * (size_t)nterms, st);
+        dev::h2d(dtab, tp.data(), nterms, st);
+        dev::h2d(dtab + nterms, tq.data(), nterms, st);
+        dev::sync(st);
+        it = index_tabs.emplace(h, dtab).first;
+    }
+    G.tp = it->second;
+    G.tq = it->second + nterms;
+    G.nterms = nterms;
+    G.rows = level + 1;
+    const size_t n = N(), ps = (size_t)(level + 1) * n;
+    LimbList ll = limb_list(mods_q(level));
+    u64* d = alloc(3 * ps);
+    LAUNCH(k_lut2, dim3((unsigned)(n / 256), level + 1), dim3(256), st, ks, d, G, ll);
+    // one relinearisation, then two rescales
+    u64* k2 = alloc(2 * ps);
+    key_switch(d + 2 * ps, level, &relin, k2);
+    launch_add(ks, k2, k2, d, ll, 2, PolyStride{ps, ps, ps}, st);
+    u64* r1 = alloc((size_t)2 * level * n);
+    rescale_into(r1, k2, 2, level);
+    Ct* out = new_ct(2, level - 2);
+    rescale_into(out->d, r1, 2, level - 1);
+    release(d);
+    release(k2);
+    release(r1);
+    n_mul_cc++;
+    return out;
+}
+
+// sum_k c_k X_k: one fused multiply-accumulate and one rescale per distinct input level, partial sums added
+// from the highest level down (each addition aligns the running sum by one level_down)
+Ct* Engine::lincomb(const std::vector<Ct*>& X, const double* coef, int n) {
+    if (n < 1) throw std::runtime_error("lincomb: empty");
+    std::map<int, std::vector<int>, std::greater<int>> by_level;
+    int npoly = X[0]->npoly;
+    for (int k = 0; k < n; k++) {
+        if (!X[k]) throw std::runtime_error("lincomb: missing ciphertext");
+        if (X[k]->npoly != npoly) throw PolyCountError("lincomb: mixed polynomial counts");
+        need_levels(X[k]->level, 1, "lincomb");
+        by_level[X[k]->level].push_back(k);
+    }
+    Ct* acc = nullptr;
+    for (auto& kv : by_level) {
+        const int level = kv.first;
+        const size_t nn = N(), ps = (size_t)(level + 1) * nn;
+        LimbList ll = limb_list(mods_q(level));
+        u64* sum = nullptr;                                  // un-rescaled partial sum at this level
+        for (size_t off = 0; off < kv.second.size(); off += LINCOMB_MAX) {
+            const int cnt = (int)std::min((size_t)LINCOMB_MAX, kv.second.size() - off);
+            LinCombArgs G;
+            memset(&G, 0, sizeof(G));
+            std::vector<double> cs(2 * (size_t)cnt);
+            for (int t = 0; t < cnt; t++) {
+                const int k = kv.second[off + t];
+                G.x[t] = X[k]->d;
+                cs[2 * t] = coef[2 * k];
+                cs[2 * t + 1] = coef[2 * k + 1];
+            }
+            G.consts = const_table(cs.data(), cnt, level, level);
+            G.nterms = cnt;
+            G.rows = level + 1;
+            u64* part = alloc((size_t)npoly * ps);
+            LAUNCH(k_lincomb, dim3((unsigned)(nn / 256), level + 1, npoly), dim3(256), st, ks, part, G, ll);
+            if (!sum) sum = part;
+            else {
+                launch_add(ks, sum, sum, part, ll, npoly, PolyStride{ps, ps, ps}, st);
+                release(part);
+            }
+        }
+        Ct* r = new_ct(npoly, level - 1);
+        rescale_into(r->d, sum, npoly, level);
+        release(sum);
+        if (!acc) acc = r;
+        else {
+            Ct* s = add(acc, r);
+            free_ct(acc);
+            free_ct(r);
+            acc = s;
+        }
+    }
+    return acc;
+}
+
 }  // namespace ckks

@@ -16,7 +16,7 @@ as thin ctypes calls into `libckks_b200.so` (hand-written sm_100a CUDA; `include
     (2 291 of the reference's 2 303 plaintexts are constants).
 
 Beyond the reference surface the engine offers fused entry points the host mirror uses when present:
-`rotate_many` (hoisted rotations), `lut2` / `lut1` (fused sparse LUT multiply-accumulate).
+`rotate_many` (hoisted rotations), `lut2` / `lincomb` (fused sparse LUT multiply-accumulate).
 """
 from __future__ import annotations
 
@@ -319,11 +319,9 @@ class Engine:
         c = np.asarray([complex(t[2]) for t in terms], dtype=np.complex128)
         return self._new(self._lib.ckks_lut2, A, B, nb, p, q, c.view(np.float64), len(terms))
 
-    def lut1(self, basis: Sequence[Ciphertext], coeffs: np.ndarray) -> List[Ciphertext]:
-        """out_j = sum_k coeffs[j, k] * basis[k]; all outputs share the basis."""
-        nb = len(basis)
-        X = (C.c_void_p * nb)(*[c._h for c in basis])
-        cf = np.ascontiguousarray(np.asarray(coeffs, dtype=np.complex128).reshape(-1, nb))
-        out = (C.c_void_p * cf.shape[0])()
-        _capi.check(self._lib.ckks_lut1(self._ptr, X, nb, cf.view(np.float64), cf.shape[0], out))
-        return [Ciphertext(self, out[i]) for i in range(cf.shape[0])]
+    def lincomb(self, cts: Sequence[Ciphertext], coeffs) -> Ciphertext:
+        """sum_k coeffs[k] * cts[k]: one fused multiply-accumulate + one rescale per distinct input level."""
+        n = len(cts)
+        X = (C.c_void_p * n)(*[c._h for c in cts])
+        cf = np.ascontiguousarray(np.asarray(coeffs, dtype=np.complex128).reshape(n))
+        return self._new(self._lib.ckks_lincomb, X, n, cf.view(np.float64))

@@ -80,7 +80,7 @@ def load():
         "ckks_rotate": (i32, [vp, vp, lng, pp]),
         "ckks_rotate_hoisted": (i32, [vp, vp, lngp, i32, pp]),
         "ckks_lut2": (i32, [vp, pp, pp, i32, i32p, i32p, dp, i32, pp]),
-        "ckks_lut1": (i32, [vp, pp, i32, dp, i32, pp]),
+        "ckks_lincomb": (i32, [vp, pp, i32, dp, pp]),
         "ckks_bootstrap": (i32, [vp, vp, pp]),
         "ckks_bootstrap_out_level": (i32, [vp]),
         "ckks_counters": (i32, [vp, lngp]),

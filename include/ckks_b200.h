@@ -104,9 +104,9 @@ int ckks_rotate_hoisted(ckks_engine* e, const ckks_ct* a, const long* steps, int
  * one tensor accumulation, ONE relinearisation, two rescales: result at min level - 2. */
 int ckks_lut2(ckks_engine* e, ckks_ct* const* A, ckks_ct* const* B, int nbasis, const int* p, const int* q,
               const double* coef_re_im, int nterms, ckks_ct** out);
-/* Fused 1-D LUT (sub_bytes_lut.py:63-71): out_j = sum_k c_{j,k} X[k] for nout outputs sharing the basis. */
-int ckks_lut1(ckks_engine* e, ckks_ct* const* X, int nbasis, const double* coef_re_im /* [nout][nbasis][2] */,
-              int nout, ckks_ct** out);
+/* Fused linear combination (sub_bytes_lut.py:49-54,63-71): out = sum_k c_k X[k]; one multiply-accumulate kernel and one
+ * rescale per distinct input level instead of one multiply+rescale per term; result at (lowest input level - 1). */
+int ckks_lincomb(ckks_engine* e, ckks_ct* const* X, int n, const double* coef_re_im /* [n][2] */, ckks_ct** out);
 
 /* bootstrap(ct, relin, conj, bootstrap_key) (engine_context.py:147-162) */
 int ckks_bootstrap(ckks_engine* e, ckks_ct* a, ckks_ct** out);

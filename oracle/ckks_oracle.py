@@ -505,3 +505,82 @@ class OracleCKKS:
         for k in range(2, degree + 1):
             out.append(self.mul_ct(out[k // 2 - 1], out[(k + 1) // 2 - 1]))
         return out
+
+    # ------------------------------------------------------------------ fused LUT evaluation (csrc/lut.cu)
+    def _mul_const_raw(self, poly: np.ndarray, c: complex, scale: float, idx) -> np.ndarray:
+        cp, cm = self.const_residues(complex(c), scale, idx)
+        out = np.empty_like(poly)
+        self.lib.ref_mul_const_batch(out, np.ascontiguousarray(poly), cp, cm, len(idx), self.N, self._mods(idx))
+        return out
+
+    def lut2(self, A: Dict[int, Ct], B: Dict[int, Ct], terms) -> Ct:
+        """sum_t c_t A[p_t] (x) B[q_t]: terms grouped by p, constants at scale S[l-1], ONE relinearisation,
+        two rescales -> level l-2 (same spec as Engine::lut2)."""
+        level = min(min(A[p].level, B[q].level) for p, q, _ in terms)
+        if level < 2:
+            raise RuntimeError("ciphertext level should be positive for multiplication")
+        idx = self._idx_q(level)
+        order = sorted(range(len(terms)), key=lambda t: terms[t][0])        # stable
+        d = np.zeros((3, level + 1, self.N), dtype=np.uint64)
+        mods = self._mods(idx)
+        k = 0
+        while k < len(order):
+            p = terms[order[k]][0]
+            u0 = np.zeros((level + 1, self.N), dtype=np.uint64)
+            u1 = np.zeros((level + 1, self.N), dtype=np.uint64)
+            while k < len(order) and terms[order[k]][0] == p:
+                _, q, c = terms[order[k]]
+                b = self.level_down(B[q], level)
+                u0 = self.add(u0, self._mul_const_raw(b.c[0], c, self.scales[level - 1], idx), idx)
+                u1 = self.add(u1, self._mul_const_raw(b.c[1], c, self.scales[level - 1], idx), idx)
+                k += 1
+            a = self.level_down(A[p], level)
+            a0, a1 = np.ascontiguousarray(a.c[0]), np.ascontiguousarray(a.c[1])
+            self.lib.ref_muladd_batch(d[0], a0, u0, len(idx), self.N, mods)
+            self.lib.ref_muladd_batch(d[1], a0, u1, len(idx), self.N, mods)
+            self.lib.ref_muladd_batch(d[1], a1, u0, len(idx), self.N, mods)
+            self.lib.ref_muladd_batch(d[2], a1, u1, len(idx), self.N, mods)
+        self.counters["mul_cc"] = self.counters.get("mul_cc", 0) + 1
+        t = Ct(d, level, self.scales[level] ** 2 * self.scales[level - 1])
+        r = self.rescale(self.rescale(self.relinearize(t)))
+        r.scale = self.scales[r.level]
+        return r
+
+    def lincomb(self, X: Sequence[Ct], coeffs) -> Ct:
+        """sum_k c_k X_k: per distinct level one un-rescaled multiply-accumulate and one rescale; partial sums are
+        added from the highest level down (same spec as Engine::lincomb)."""
+        by_level: Dict[int, List[int]] = {}
+        for k, x in enumerate(X):
+            if x.level < 1:
+                raise RuntimeError("ciphertext level should be positive for multiplication")
+            by_level.setdefault(x.level, []).append(k)
+        acc = None
+        for level in sorted(by_level, reverse=True):
+            idx = self._idx_q(level)
+            npoly = X[by_level[level][0]].c.shape[0]
+            s = np.zeros((npoly, level + 1, self.N), dtype=np.uint64)
+            for k in by_level[level]:
+                for j in range(npoly):
+                    s[j] = self.add(s[j], self._mul_const_raw(X[k].c[j], complex(coeffs[k]), self.scales[level], idx), idx)
+            r = self.rescale(Ct(s, level, self.scales[level] ** 2))
+            r.scale = self.scales[r.level]
+            acc = r if acc is None else self.add_ct(acc, r)
+        return acc
+
+    def rotate_hoisted(self, a: Ct, steps: Sequence[int]) -> List[Ct]:
+        """Rotations sharing one ModUp: the Galois gather is applied to the decomposed digits (csrc: rotate_hoisted)."""
+        idx = self._idx_q(a.level)
+        digits = None
+        out = []
+        for s in steps:
+            if s % self.n == 0:
+                out.append(a)
+                continue
+            if digits is None:
+                digits = self.mod_up(a.c[1], a.level)
+            g = self.galois_for_rotation(s)
+            if g not in self.evk:
+                self.keygen_galois(g)
+            k0, k1 = self.key_switch(None, a.level, g, digits=[self.automorph(d, g) for d in digits])
+            out.append(Ct(np.stack([self.add(self.automorph(a.c[0], g), k0, idx), k1]), a.level, a.scale))
+        return out

@@ -60,9 +60,12 @@ def test_bootstrap_precision_and_levels(boot_ctx):
     assert ctx.bootstrap_stats()["count"] == 2
 
 
-def test_config1_ark_subbytes_fips_vector(boot_ctx):
-    """configs[0]: AddRoundKey + SubBytes on the FIPS-197 C.1 state."""
+@pytest.mark.parametrize("fused", [False, True], ids=["call-for-call", "fused"])
+def test_config1_ark_subbytes_fips_vector(boot_ctx, fused):
+    """configs[0]: AddRoundKey + SubBytes on the FIPS-197 C.1 state, once issuing the reference's
+    engine calls one for one and once through the fused LUT entry points."""
     which, ctx = boot_ctx
+    ctx.fused = fused
     pipe = make_pipe(ctx)
     key = np.frombuffer(bytes.fromhex("000102030405060708090a0b0c0d0e0f"), dtype=np.uint8)
     pt = np.frombuffer(bytes.fromhex("00112233445566778899aabbccddeeff"), dtype=np.uint8)
@@ -75,26 +78,33 @@ def test_config1_ark_subbytes_fips_vector(boot_ctx):
     s = pipe.sub_bytes(*pipe._renorm_pair(*a))
     assert bytes(pipe.encoder.decode(*s)) == bytes(sbox[pt ^ key])
     c1 = ctx.engine.counters()
-    assert c1["mul_cc"] - c0["mul_cc"] == 291                 # 291 ct*ct, 162 conjugations
-    assert c1["keyswitch"] - c0["keyswitch"] == 291 + 162
+    if not fused:
+        assert c1["mul_cc"] - c0["mul_cc"] == 291             # 291 ct*ct, 162 conjugations
+        assert c1["keyswitch"] - c0["keyswitch"] == 291 + 162
+    else:
+        assert c1["mul_cc"] - c0["mul_cc"] == 4 * 7 + 2 + 135     # 4 power bases + 2 fused XOR4 + SubBytes
+        assert c1["keyswitch"] - c0["keyswitch"] == 165 + 4 * 7 + 3   # + basis conjugations + 3 in SubBytes
     # per-stage slots against the reference-semantics stand-in: stated tolerance 1e-4 on unit-modulus slots
     sctx = aes_fhe.EngineContext(1, mode="cpu", thread_count=1, backend=ss, slot_count=ctx.engine.slot_count)
     sp = make_pipe(sctx)
     ref = sp.sub_bytes(*sp._renorm_pair(*sp.add_round_key(*sp.encoder.encode(pt), *sp.encoder.encode(key))))
     for got, want in zip(s, ref):
         assert np.abs(ctx.decrypt(got)[::stride][:16] - sctx.decrypt(want)[::stride][:16]).max() < 1e-4
+    ctx.fused = True
 
 
 def test_config2_one_round_as_shipped_matches_standin(boot_ctx):
     """configs[1] on the as-shipped flow (column-first ShiftRows + row-major MixColumns): bytes must equal
     the reference-semantics stand-in running the same unchanged flow."""
     which, ctx = boot_ctx
+    ctx.fused = False                                           # the reference's calls, one for one
     pipe = make_pipe(ctx)
     rng = np.random.RandomState(0)
     state, key = rng.randint(0, 256, 16).astype(np.uint8), rng.randint(0, 256, 16).astype(np.uint8)
     c0 = ctx.engine.counters()
     out = pipe.encrypt_round(*pipe.encoder.encode(state), *pipe.encoder.encode(key))
     c1 = ctx.engine.counters()
+    ctx.fused = True
     sctx = aes_fhe.EngineContext(1, mode="cpu", thread_count=1, backend=ss, slot_count=ctx.engine.slot_count)
     sp = make_pipe(sctx)
     want = sp.encoder.decode(*sp.encrypt_round(*sp.encoder.encode(state), *sp.encoder.encode(key)))

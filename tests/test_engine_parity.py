@@ -184,7 +184,60 @@ def test_hoisted_rotations_decrypt(pair):
     rng = np.random.default_rng(8)
     z = np.exp(2j * np.pi * rng.random(pair.n))
     c = pair.eng.encrypt(z)
+    pair.orc.encrypt(z)                      # keeps the two encryption counters (spec S8 stream ids) in step
     steps = [pair.n // 4, pair.n // 2, 3 * pair.n // 4, 0, -1]
     outs = pair.eng.rotate_many(c, None, steps)
     for s, r in zip(steps, outs):
         assert np.abs(pair.eng.decrypt(r) - np.roll(z, s)).max() < 1e-7
+
+
+def test_hoisted_rotations_bit_exact(pair):
+    rng = np.random.default_rng(9)
+    z = np.exp(2j * np.pi * rng.random(pair.n))
+    c, o = pair.eng.encrypt(z), pair.orc.encrypt(z)
+    steps = [pair.n // 4, -2, 0]
+    for got, want in zip(pair.eng.rotate_many(c, None, steps), pair.orc.rotate_hoisted(o, steps)):
+        assert np.array_equal(pair.export(got), want.c)
+
+
+def test_fused_lut2_bit_exact_and_equals_termwise(pair):
+    """ckks_lut2 (one relinearisation) against the oracle restatement, and against the reference's term-by-term
+    evaluation order (xor4_lut.py:63-74) on decrypted slots."""
+    rng = np.random.default_rng(10)
+    eng, orc = pair.eng, pair.orc
+    za, zb = np.exp(2j * np.pi * rng.random(pair.n)), np.exp(2j * np.pi * rng.random(pair.n))
+    ca, cb, oa, ob = eng.encrypt(za), eng.encrypt(zb), orc.encrypt(za), orc.encrypt(zb)
+    pa, pb = eng.make_power_basis(ca, 4, pair.rk), eng.make_power_basis(cb, 4, pair.rk)
+    opa, opb = orc.power_basis(oa, 4), orc.power_basis(ob, 4)
+    A = [None] + pa + [eng.conjugate(pa[0])]
+    B = [None] + pb + [eng.conjugate(pb[0])]
+    OA = {i + 1: x for i, x in enumerate(opa)}
+    OB = {i + 1: x for i, x in enumerate(opb)}
+    OA[5], OB[5] = orc.conjugate(opa[0]), orc.conjugate(opb[0])
+    terms = [(1, 1, 0.5 - 0.25j), (3, 2, -95.47j), (1, 4, 2.0), (5, 5, 1.0 + 1.0j), (2, 3, -0.125), (3, 1, 7.0)]
+    got = eng.lut2(A, B, terms)
+    want = orc.lut2(OA, OB, terms)
+    assert got.level == want.level == min(x.level for x in pa + pb) - 2
+    assert np.array_equal(pair.export(got), want.c)
+    P = {1: za, 2: za ** 2, 3: za ** 3, 4: za ** 4, 5: np.conj(za)}
+    Q = {1: zb, 2: zb ** 2, 3: zb ** 3, 4: zb ** 4, 5: np.conj(zb)}
+    ref = sum(c * P[p] * Q[q] for p, q, c in terms)
+    assert np.abs(eng.decrypt(got) - ref).max() < 1e-6
+    # term-by-term, as the reference loop does
+    acc = eng.subtract(A[1], A[1])
+    for p, q, c in terms:
+        acc = eng.add(acc, eng.multiply(eng.multiply(A[p], B[q], pair.rk), eng.encode(np.full(pair.n, c))))
+    assert np.abs(eng.decrypt(acc) - eng.decrypt(got)).max() < 1e-6
+
+
+def test_fused_lincomb_bit_exact(pair):
+    rng = np.random.default_rng(11)
+    eng, orc = pair.eng, pair.orc
+    z = np.exp(2j * np.pi * rng.random(pair.n))
+    c, o = eng.encrypt(z), orc.encrypt(z)
+    pb, opb = eng.make_power_basis(c, 5, pair.rk), orc.power_basis(o, 5)      # levels L, L-1, L-2, L-2, L-3
+    coef = np.array([0.5, -1.25 + 2j, 3.0j, 0.0625, -7.5 - 0.5j])
+    got, want = eng.lincomb(pb, coef), orc.lincomb(opb, coef)
+    assert np.array_equal(pair.export(got), want.c)
+    assert got.level == pb[-1].level - 1
+    assert np.abs(eng.decrypt(got) - sum(coef[k] * z ** (k + 1) for k in range(5))).max() < 1e-6
