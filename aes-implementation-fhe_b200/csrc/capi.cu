@@ -94,6 +94,27 @@ int ckks_keygen_rotation(ckks_engine* e, const long* steps, int nsteps) {
         }
     });
 }
+int ckks_set_keys_external(ckks_engine* e, int external) {
+    e->E->keys_external = external != 0;
+    return CKKS_OK;
+}
+int ckks_switch_key_ids(ckks_engine* e, uint64_t* ids_out, int capacity, int* count) {
+    return guard([&] {
+        std::vector<u64> ids = e->E->switch_key_ids();
+        *count = (int)ids.size();
+        for (int i = 0; i < (int)ids.size() && i < capacity; i++) ids_out[i] = ids[i];
+    });
+}
+int ckks_switch_key_buffer(ckks_engine* e, uint64_t id, void** ptr, size_t* bytes) {
+    return guard([&] {
+        size_t words = 0;
+        u64* p = e->E->switch_key_buffer(id, &words);
+        if (!p) throw std::runtime_error("no such switching key");
+        e->E->sync();
+        *ptr = p;
+        *bytes = words * sizeof(u64);
+    });
+}
 int ckks_set_bootstrap_params(ckks_engine* e, int K, int deg, int r, int cts, int stc) {
     return guard([&] {
         if (e->E->boot) throw std::runtime_error("bootstrap key already created");

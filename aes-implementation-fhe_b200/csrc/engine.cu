@@ -216,6 +216,13 @@ Engine::Engine(const Params& P) : prm(P) {
             pinv[i] = invmod_h(pp, mod[i]);
         }
         scalar_list(pinv, qi, sl_pinv);
+        std::vector<u64> pm(L() + 1);
+        for (int i = 0; i <= L(); i++) {
+            u64 pp = 1;
+            for (u64 pk_ : prm.p) pp = mulmod_h(pp, pk_ % mod[i], mod[i]);
+            pm[i] = pp;
+        }
+        scalar_list(pm, qi, sl_pmodq);
         sl_qinv.resize(L() + 1);
         for (int l = 1; l <= L(); l++) {
             std::vector<int> lo = mods_q(l - 1);
@@ -238,6 +245,8 @@ Engine::~Engine() {
     for (auto& kv : modup_tabs) { dev::free((void*)kv.second.hat, st); dev::free((void*)kv.second.hat_s, st); }
     for (auto& kv : moddown_tabs) { dev::free((void*)kv.second.hat, st); dev::free((void*)kv.second.hat_s, st); }
     for (auto& kv : const_tabs) dev::free(kv.second, st);
+    for (auto& kv : modup_dev) dev::free(kv.second, st);
+    for (auto& kv : moddown_dev) dev::free(kv.second, st);
     for (auto& kv : index_tabs) dev::free(kv.second, st);
     dev::free(relin.d, st);
     dev::free(sk_ntt, st);
@@ -447,6 +456,7 @@ EvalKey Engine::make_switch_key(u64 key_id, const u64* s_from_ntt) {
     const int dn = dnum();
     EvalKey key;
     key.d = alloc((size_t)dn * 2 * rows * n);
+    if (keys_external) return key;                 // content arrives by broadcast from the rank that generated it
     u64* e = alloc((size_t)rows * n);
     u64* t = alloc((size_t)rows * n);
     PolyStride z{0, 0, 0};
@@ -483,6 +493,19 @@ void Engine::keygen_relin() {
     relin = make_switch_key(0, s2);
     release(s2);
     has_relin = true;
+}
+
+std::vector<u64> Engine::switch_key_ids() const {
+    std::vector<u64> ids;
+    if (relin.d) ids.push_back(0);
+    for (auto& kv : gkeys) ids.push_back(kv.first);
+    return ids;
+}
+u64* Engine::switch_key_buffer(u64 id, size_t* words) {
+    *words = (size_t)dnum() * 2 * nmod() * N();
+    if (id == 0) return relin.d;
+    auto it = gkeys.find(id);
+    return it == gkeys.end() ? nullptr : it->second.d;
 }
 
 EvalKey* Engine::galois_key(u64 g) {
@@ -644,15 +667,60 @@ const BaseConvTable& Engine::modup_table(int level, int digit) {
     modup_tabs[key] = make_bc_table(src, srow, tgt, orow);
     return modup_tabs[key];
 }
-// P -> Q_level: sources are rows level+1.. of the accumulator, targets rows 0..level of the output
-const BaseConvTable& Engine::moddown_table(int level) {
-    auto it = moddown_tabs.find(level);
+// {q_{level-drop+1} .. q_level} u P  ->  Q_{level-drop}: sources are rows level-drop+1..level and level+1.. of the
+// accumulator, targets rows 0..level-drop of the output.  drop = 0 is the plain ModDown by P; drop = 1, 2 also
+// divide by the last one or two ciphertext primes (merged rescale, spec S6b).
+const BaseConvTable& Engine::moddown_table(int level, int drop) {
+    const int key = level * 4 + drop;
+    auto it = moddown_tabs.find(key);
     if (it != moddown_tabs.end()) return it->second;
     std::vector<int> src, srow, tgt, orow;
+    for (int i = level - drop + 1; i <= level; i++) { src.push_back(i); srow.push_back(i); }
     for (int k = 0; k < K(); k++) { src.push_back(L() + 1 + k); srow.push_back(level + 1 + k); }
-    for (int i = 0; i <= level; i++) { tgt.push_back(i); orow.push_back(i); }
-    moddown_tabs[level] = make_bc_table(src, srow, tgt, orow);
-    return moddown_tabs[level];
+    for (int i = 0; i <= level - drop; i++) { tgt.push_back(i); orow.push_back(i); }
+    moddown_tabs[key] = make_bc_table(src, srow, tgt, orow);
+    return moddown_tabs[key];
+}
+// (P * q_{level-drop+1} .. q_level)^-1 mod q_i, i <= level - drop
+const ScalarList& Engine::moddown_inv(int level, int drop) {
+    const int key = level * 4 + drop;
+    auto it = moddown_invs.find(key);
+    if (it != moddown_invs.end()) return it->second;
+    std::vector<int> qi = mods_q(level - drop);
+    std::vector<u64> inv(qi.size());
+    for (size_t i = 0; i < qi.size(); i++) {
+        const u64 q = mod[qi[i]];
+        u64 pp = 1;
+        for (u64 pk_ : prm.p) pp = mulmod_h(pp, pk_ % q, q);
+        for (int j = level - drop + 1; j <= level; j++) pp = mulmod_h(pp, mod[j] % q, q);
+        inv[i] = invmod_h(pp, q);
+    }
+    scalar_list(inv, qi, moddown_invs[key]);
+    return moddown_invs[key];
+}
+
+const BaseConvTable* Engine::modup_tables_dev(int level) {
+    auto it = modup_dev.find(level);
+    if (it != modup_dev.end()) return it->second;
+    const int beta = (level + 1 + prm.alpha - 1) / prm.alpha;
+    std::vector<BaseConvTable> h(beta);
+    for (int j = 0; j < beta; j++) h[j] = modup_table(level, j);
+    BaseConvTable* d = (BaseConvTable*)dev::alloc(beta * sizeof(BaseConvTable), st);
+    dev::h2d(d, h.data(), beta * sizeof(BaseConvTable), st);
+    dev::sync(st);
+    modup_dev[level] = d;
+    return d;
+}
+const BaseConvTable* Engine::moddown_table_dev(int level, int drop) {
+    const int key = level * 4 + drop;
+    auto it = moddown_dev.find(key);
+    if (it != moddown_dev.end()) return it->second;
+    BaseConvTable h = moddown_table(level, drop);
+    BaseConvTable* d = (BaseConvTable*)dev::alloc(sizeof(BaseConvTable), st);
+    dev::h2d(d, &h, sizeof(BaseConvTable), st);
+    dev::sync(st);
+    moddown_dev[key] = d;
+    return d;
 }
 
 // ------------------------------------------------------------------ hybrid key switching (spec S5, S6)
@@ -664,6 +732,7 @@ Decomp Engine::decompose(const u64* d, int level) {
     D.level = level;
     D.beta = beta;
     D.ext = alloc((size_t)beta * rows * n);
+    D.own = d;
     // coefficient form of all q-limbs
     u64* coef = alloc((size_t)nq * n);
     {
@@ -673,18 +742,17 @@ Decomp Engine::decompose(const u64* d, int level) {
         for (int i = 0; i < nq; i++) { J.rows[0][i] = J.srows[0][i] = (unsigned char)i; J.mods[0][i] = (unsigned char)i; }
         run_ntt(d, coef, J, true, nq);
     }
-    // per digit: fast basis conversion of its limbs to every other modulus of Q_level u P; the
-    // digit's own limbs are copied from the NTT-domain input
+    // fast basis conversion of every digit to the other moduli of Q_level u P: one launch, z = digit.  The digit's own
+    // limbs are never copied: the inner product reads them from the NTT-domain input (Decomp::own).
     NttJob J;
     memset(&J, 0, sizeof(J));
     J.nz = beta;
     J.szs = J.dzs = (size_t)rows * n;
     long modup_limbs = 0;
+    int max_nt = 0;
     for (int j = 0; j < beta; j++) {
         const BaseConvTable& T = modup_table(level, j);
-        launch_base_convert(ks, D.ext + (size_t)j * rows * n, coef, T, 1, 0, 0, st);
-        const int lo = j * prm.alpha, hi = std::min((j + 1) * prm.alpha, nq);
-        dev::d2d(D.ext + ((size_t)j * rows + lo) * n, d + (size_t)lo * n, (size_t)(hi - lo) * n * sizeof(u64), st);
+        max_nt = std::max(max_nt, T.nt);
         J.n = std::max(J.n, T.nt);
         J.cnt[j] = (unsigned char)T.nt;
         for (int t = 0; t < T.nt; t++) {
@@ -693,33 +761,39 @@ Decomp Engine::decompose(const u64* d, int level) {
         }
         modup_limbs += T.nt;
     }
+    launch_base_convert(ks, D.ext, coef, modup_tables_dev(level), 1, max_nt, beta, 0, (size_t)rows * n, st);
     // one batched forward NTT over the converted rows of all digits (z = digit)
     run_ntt(D.ext, D.ext, J, false, modup_limbs);
     release(coef);
     return D;
 }
 
-void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out) {
+// inner product with the key, then ONE division by P * q_{level-drop+1..level}: out is [2][level+1-drop][N].
+// addend ([2][level+1][N], e.g. the (d0, d1) of a tensor product) is folded in as P * addend before the division.
+void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out, const u64* addend, int drop) {
     const size_t n = N();
-    const int level = D.level, nq = level + 1, rows = nq + K();
+    const int level = D.level, nq = level + 1, rows = nq + K(), nout = nq - drop;
+    if (nout < 1) throw LevelError("key switch: ciphertext level should be positive for this rescale");
     std::vector<int> qp = mods_qp(level);
     LimbList ll = limb_list(qp);
     LimbList er = limb_list(qp);                 // evk rows are indexed by global modulus index
     u64* acc = alloc((size_t)2 * rows * n);
-    launch_ks_inner(ks, acc, D.ext, evk->d, perm, ll, er, D.beta, nmod(), st);
-    // ModDown: floor(acc / P)
+    launch_ks_inner(ks, acc, D.ext, D.own, evk->d, perm, ll, er, D.beta, nmod(), nq, prm.alpha, addend, sl_pmodq, st);
+    // coefficient form of the limbs that are divided out
     std::vector<int> prow, pmod;
+    for (int i = level - drop + 1; i <= level; i++) { prow.push_back(i); pmod.push_back(i); }
     for (int k = 0; k < K(); k++) { prow.push_back(nq + k); pmod.push_back(L() + 1 + k); }
     ntt_rows(acc, prow, pmod, true, 2, (size_t)rows * n);
-    u64* conv = alloc((size_t)2 * nq * n);
-    launch_base_convert(ks, conv, acc, moddown_table(level), 2, (size_t)rows * n, (size_t)nq * n, st);
-    std::vector<int> qi = mods_q(level);
-    ntt_rows(conv, qi, qi, false, 2, (size_t)nq * n);
-    launch_sub_mul_scalar(ks, out, acc, conv, limb_list(qi), sl_pinv, 2,
-                          PolyStride{(size_t)nq * n, (size_t)rows * n, (size_t)nq * n}, st);
+    u64* conv = alloc((size_t)2 * nout * n);
+    launch_base_convert(ks, conv, acc, moddown_table_dev(level, drop), 0, nout, 2, (size_t)rows * n, (size_t)nout * n, st);
+    std::vector<int> qi = mods_q(level - drop);
+    ntt_rows(conv, qi, qi, false, 2, (size_t)nout * n);
+    launch_sub_mul_scalar(ks, out, acc, conv, limb_list(qi), moddown_inv(level, drop), 2,
+                          PolyStride{(size_t)nout * n, (size_t)rows * n, (size_t)nout * n}, st);
     release(acc);
     release(conv);
     n_keyswitch++;
+    if (drop) n_rescale++;
 }
 
 void Engine::key_switch(const u64* d, int level, const EvalKey* evk, u64* out) {
@@ -879,13 +953,12 @@ Ct* Engine::mul(Ct* a, Ct* b) {
     LimbList ll = limb_list(mods_q(l));
     u64* t = alloc(3 * ps);
     launch_tensor(ks, t, a->d, b->d, ll, st);
-    u64* k2 = alloc(2 * ps);
-    key_switch(t + 2 * ps, l, &relin, k2);
-    launch_add(ks, k2, k2, t, ll, 2, PolyStride{ps, ps, ps}, st);
+    // relinearisation and rescale in one division: (<digits(d2), rlk> + P (d0, d1)) / (P q_l)   (spec S6b)
+    Decomp D = decompose(t + 2 * ps, l);
     Ct* r = new_ct(2, l - 1);
-    rescale_into(r->d, k2, 2, l);
+    ks_apply(D, &relin, nullptr, r->d, t, 1);
+    release(D.ext);
     release(t);
-    release(k2);
     n_mul_cc++;
     return r;
 }

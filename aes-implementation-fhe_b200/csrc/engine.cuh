@@ -46,7 +46,8 @@ struct EvalKey {
 // ModUp result: every digit of a polynomial extended to Q_level u P, NTT domain
 struct Decomp {
     int level = 0, beta = 0;
-    u64* ext = nullptr;                             // [beta][level+1+K][N]
+    u64* ext = nullptr;                             // [beta][level+1+K][N]; a digit's own rows are not filled
+    const u64* own = nullptr;                       // the NTT-domain input [level+1][N] (read for own rows)
 };
 
 struct BootParams {
@@ -109,6 +110,9 @@ class Engine {
     u64 galois_for_rotation(long steps) const;  // rotate(ct,+r) == np.roll(slots,+r)
     u64 galois_conj() const { return 2ull * N() - 1; }
     bool has_sk = false, has_pk = false, has_relin = false;
+    bool keys_external = false;                 // switching keys are allocated but not sampled: filled by a broadcast
+    std::vector<u64> switch_key_ids() const;    // 0 = relinearisation key, else Galois element
+    u64* switch_key_buffer(u64 id, size_t* words);
 
     // ---- encode / encrypt / decrypt (host pointers: interleaved re,im doubles, n = N/2 slots)
     Pt* encode(const double* z, int level);
@@ -156,7 +160,8 @@ class Engine {
     void profile_begin();
     void profile_end(double* ms, long* calls, long* limbs);
     Decomp decompose(const u64* d, int level);
-    void ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out /* [2][level+1][N] */);
+    void ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out /* [2][level+1-drop][N] */,
+                  const u64* addend = nullptr, int drop = 0);
     void key_switch(const u64* d, int level, const EvalKey* evk, u64* out);
     void automorph(u64* out, const u64* in, int rows, int npoly, u64 g);
     const u32* galois_perm(u64 g);
@@ -167,7 +172,10 @@ class Engine {
                         ScalarList& cm) const;
     void scalar_list(const std::vector<u64>& vals, const std::vector<int>& mods, ScalarList& out) const;
     const BaseConvTable& modup_table(int level, int digit);
-    const BaseConvTable& moddown_table(int level);
+    const BaseConvTable& moddown_table(int level, int drop = 0);
+    const ScalarList& moddown_inv(int level, int drop);
+    const BaseConvTable* modup_tables_dev(int level);
+    const BaseConvTable* moddown_table_dev(int level, int drop = 0);
     const std::vector<i64>& sk_host() const { return sk_coef; }
     const u64* sk_dev() const { return sk_ntt; }
     const u64* pk_dev() const { return pk; }
@@ -191,6 +199,7 @@ class Engine {
     std::map<u64, u32*> perms;
     std::map<std::pair<int, int>, BaseConvTable> modup_tabs;
     std::map<int, BaseConvTable> moddown_tabs;
+    std::map<int, BaseConvTable*> modup_dev, moddown_dev;   // device copies ([beta] per level / one per level)
     std::map<u64, u64*> const_tabs;                 // LUT constants by content hash
     std::map<u64, unsigned char*> index_tabs;       // LUT term index lists
     std::vector<void*> owned;              // device tables freed in the destructor
@@ -204,6 +213,8 @@ class Engine {
     long prof_limbs = 0, prof_calls = 0;
     double prof_ms = 0;
     ScalarList sl_pinv;                    // P^-1 mod q_i
+    ScalarList sl_pmodq;                   // P mod q_i
+    std::map<int, ScalarList> moddown_invs; // (level, drop) -> (P q_dropped)^-1 mod q_i
     std::vector<ScalarList> sl_qinv;       // [l]: q_l^-1 mod q_i, i < l
 
     EvalKey make_switch_key(u64 key_id, const u64* s_from_ntt);

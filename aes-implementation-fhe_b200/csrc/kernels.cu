@@ -16,7 +16,7 @@ enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2 };
 // blockIdx.z selects the polynomial; each pointer has its own polynomial stride (elements)
 template <int OP>
 __global__ void k_binop(KShape S, u64* __restrict__ out, const u64* __restrict__ a, const u64* __restrict__ b,
-                        LimbList L, PolyStride ps) {
+                        const GRID_CONST LimbList L, PolyStride ps) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
     FOR_THREADS {
@@ -26,7 +26,7 @@ __global__ void k_binop(KShape S, u64* __restrict__ out, const u64* __restrict__
             OP == OP_ADD ? add_mod(x, y, m.q) : OP == OP_SUB ? sub_mod(x, y, m.q) : barrett_mul(x, y, m);
     }
 }
-__global__ void k_neg(KShape S, u64* __restrict__ out, const u64* __restrict__ a, LimbList L, PolyStride ps) {
+__global__ void k_neg(KShape S, u64* __restrict__ out, const u64* __restrict__ a, const GRID_CONST LimbList L, PolyStride ps) {
     const int row = blockIdx.y;
     const u64 q = S.mc[L.idx[row]].q;
     FOR_THREADS {
@@ -36,7 +36,7 @@ __global__ void k_neg(KShape S, u64* __restrict__ out, const u64* __restrict__ a
 }
 
 // out[r] = a[r] * s[r]  (per-row scalar with Shoup companion)
-__global__ void k_mul_scalar(KShape S, u64* __restrict__ out, const u64* __restrict__ a, LimbList L, ScalarList Sc,
+__global__ void k_mul_scalar(KShape S, u64* __restrict__ out, const u64* __restrict__ a, const GRID_CONST LimbList L, const GRID_CONST ScalarList Sc,
                              PolyStride ps) {
     const int row = blockIdx.y;
     const u64 q = S.mc[L.idx[row]].q;
@@ -48,7 +48,7 @@ __global__ void k_mul_scalar(KShape S, u64* __restrict__ out, const u64* __restr
 
 // out[r] = (a[r] - b[r]) * s[r]
 __global__ void k_sub_mul_scalar(KShape S, u64* __restrict__ out, const u64* __restrict__ a,
-                                 const u64* __restrict__ b, LimbList L, ScalarList Sc, PolyStride ps) {
+                                 const u64* __restrict__ b, const GRID_CONST LimbList L, const GRID_CONST ScalarList Sc, PolyStride ps) {
     const int row = blockIdx.y;
     const u64 q = S.mc[L.idx[row]].q;
     FOR_THREADS {
@@ -60,8 +60,8 @@ __global__ void k_sub_mul_scalar(KShape S, u64* __restrict__ out, const u64* __r
 
 // multiply by the constant polynomial R + I X^(N/2): first half of the bit-reversed NTT array sees cp, second half cm
 template <int ACC>
-__global__ void k_mul_const(KShape S, u64* __restrict__ out, const u64* __restrict__ a, LimbList L, ScalarList CP,
-                            ScalarList CM, PolyStride ps) {
+__global__ void k_mul_const(KShape S, u64* __restrict__ out, const u64* __restrict__ a, const GRID_CONST LimbList L, const GRID_CONST ScalarList CP,
+                            const GRID_CONST ScalarList CM, PolyStride ps) {
     const int row = blockIdx.y;
     const u64 q = S.mc[L.idx[row]].q;
     const bool lo = blockIdx.x < (gridDim.x >> 1);
@@ -73,8 +73,8 @@ __global__ void k_mul_const(KShape S, u64* __restrict__ out, const u64* __restri
         *o = ACC ? add_mod(*o, t, q) : t;
     }
 }
-__global__ void k_add_const(KShape S, u64* __restrict__ out, const u64* __restrict__ a, LimbList L, ScalarList CP,
-                            ScalarList CM) {
+__global__ void k_add_const(KShape S, u64* __restrict__ out, const u64* __restrict__ a, const GRID_CONST LimbList L, const GRID_CONST ScalarList CP,
+                            const GRID_CONST ScalarList CM) {
     const int row = blockIdx.y;
     const u64 q = S.mc[L.idx[row]].q;
     const u64 c = blockIdx.x < (gridDim.x >> 1) ? CP.v[row] : CM.v[row];
@@ -86,7 +86,7 @@ __global__ void k_add_const(KShape S, u64* __restrict__ out, const u64* __restri
 
 // tensor product of two 2-polynomial ciphertexts, nl limbs each: d0=a0 b0, d1=a0 b1+a1 b0, d2=a1 b1
 __global__ void k_tensor(KShape S, u64* __restrict__ d, const u64* __restrict__ a, const u64* __restrict__ b,
-                         LimbList L, int nl) {
+                         const GRID_CONST LimbList L, int nl) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
     const size_t P = (size_t)nl << S.logn;
@@ -113,20 +113,27 @@ __global__ void k_permute(KShape S, u64* __restrict__ out, const u64* __restrict
 }
 
 // key-switch inner product over `beta` digits.  ext: [beta][rows][N]; evk: [dnum][2][evk_rows][N];
-// working row r uses evk row ERow.idx[r].  acc: [2][rows][N].  If perm != null the digits are read
-// through the Galois gather (hoisted rotation: automorphism applied after the decomposition).
-__global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restrict__ ext, const u64* __restrict__ evk,
-                           const u32* __restrict__ perm, LimbList L, LimbList ERow, int beta, int rows, int evk_rows) {
+// working row r uses evk row ERow.idx[r].  acc: [2][rows][N].  Row r < nq belongs to digit r / alpha: for that
+// digit the value is the NTT-domain input itself (`own`, [nq][N]) -- ext never holds a copy of it.
+// If perm != null the digits are read through the Galois gather (hoisted rotation: automorphism applied after
+// the decomposition).
+// If addend != null ([2][nq][N], NTT domain) the q rows also receive P * addend (merged relinearisation:
+// acc = <digits, evk> + P (d0, d1), so that one ModDown by P q_l .. also performs the rescale, spec S6b).
+__global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restrict__ ext, const u64* __restrict__ own,
+                           const u64* __restrict__ evk, const u32* __restrict__ perm, const GRID_CONST LimbList L,
+                           const GRID_CONST LimbList ERow, int beta, int rows, int evk_rows, int nq, int alpha,
+                           const u64* __restrict__ addend, const GRID_CONST ScalarList PmodQ) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
     const size_t er = ERow.idx[row];
     const size_t N = (size_t)1 << S.logn;
+    const int jown = row < nq ? row / alpha : -1;
     FOR_THREADS {
         const u32 k = blockIdx.x * TPB + threadIdx.x;
         const u32 ks = perm ? ldg(perm + k) : k;
         u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
         for (int j = 0; j < beta; j++) {
-            const u64 x = ext[((size_t)j * rows + row) * N + ks];
+            const u64 x = j == jown ? own[(size_t)row * N + ks] : ext[((size_t)j * rows + row) * N + ks];
             const u64* e = evk + ((size_t)j * 2 * evk_rows + er) * N + k;
             mac128(h0, l0, x, ldg(e));
             mac128(h1, l1, x, ldg(e + (size_t)evk_rows * N));
@@ -135,8 +142,13 @@ __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restric
                 l1 = barrett_reduce128(h1, l1, m); h1 = 0;
             }
         }
-        acc[(size_t)row * N + k] = barrett_reduce128(h0, l0, m);
-        acc[((size_t)rows + row) * N + k] = barrett_reduce128(h1, l1, m);
+        u64 r0 = barrett_reduce128(h0, l0, m), r1 = barrett_reduce128(h1, l1, m);
+        if (addend != nullptr && row < nq) {
+            r0 = add_mod(r0, shoup_mul(addend[(size_t)row * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+            r1 = add_mod(r1, shoup_mul(addend[((size_t)nq + row) * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+        }
+        acc[(size_t)row * N + k] = r0;
+        acc[((size_t)rows + row) * N + k] = r1;
     }
 }
 
@@ -144,9 +156,14 @@ __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restric
 // in: coefficient-domain residues, source i in row T.srow[i]; out row T.orow[t] for target t.
 // One thread per coefficient, blockIdx.y picks a chunk of BC_CHUNK target moduli.
 // y_i = x_i * hatinv_i mod s_i is recomputed per chunk (cheap next to the traffic).
-__global__ void k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in, BaseConvTable T,
-                               size_t in_zs, size_t out_zs) {
+__global__ void k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in,
+                               const BaseConvTable* __restrict__ tabs, int tab_zstride, size_t in_zs, size_t out_zs) {
     const size_t N = (size_t)1 << S.logn;
+    const BaseConvTable& T = tabs[blockIdx.z * tab_zstride];      // slice z uses its own table (digit) or a shared one
+    const int ns = T.ns, nt = T.nt;
+    const int t0 = blockIdx.y * BC_CHUNK;
+    if (t0 >= nt) return;
+    const int t1 = t0 + BC_CHUNK < nt ? t0 + BC_CHUNK : nt;
     FOR_THREADS {
         const u32 k = blockIdx.x * TPB + threadIdx.x;
         const u64* src = in + blockIdx.z * in_zs;
@@ -154,17 +171,15 @@ __global__ void k_base_convert(KShape S, u64* __restrict__ out, const u64* __res
         u64 y[BC_MAX_SRC];
 #pragma unroll
         for (int i = 0; i < BC_MAX_SRC; i++)
-            if (i < T.ns) y[i] = shoup_mul(src[(size_t)T.srow[i] * N + k], T.hatinv[i], T.hatinv_s[i], S.mc[T.src[i]].q);
-        const int t0 = blockIdx.y * BC_CHUNK;
-        const int t1 = t0 + BC_CHUNK < T.nt ? t0 + BC_CHUNK : T.nt;
+            if (i < ns) y[i] = shoup_mul(src[(size_t)T.srow[i] * N + k], T.hatinv[i], T.hatinv_s[i], S.mc[T.src[i]].q);
         for (int t = t0; t < t1; t++) {
             const ModConst m = S.mc[T.tgt[t]];
             u64 lo = 0;
 #pragma unroll
             for (int i = 0; i < BC_MAX_SRC; i++)
-                if (i < T.ns) {
+                if (i < ns) {
                     // canonical products (< q_t < 2^61): eight of them fit a word, then fold
-                    lo += shoup_mul(y[i], ldg(T.hat + i * T.nt + t), ldg(T.hat_s + i * T.nt + t), m.q);
+                    lo += shoup_mul(y[i], ldg(T.hat + i * nt + t), ldg(T.hat_s + i * nt + t), m.q);
                     if ((i & 7) == 7) lo = barrett_reduce64(lo, m);
                 }
             dst[(size_t)T.orow[t] * N + k] = barrett_reduce64(lo, m);
@@ -174,7 +189,7 @@ __global__ void k_base_convert(KShape S, u64* __restrict__ out, const u64* __res
 
 // ------------------------------------------------------------------ rescale helpers (spec S6)
 // t = (last + h) mod q_l (coefficient domain, single limb) -> delta[i] = (t mod q_i) - (h mod q_i)
-__global__ void k_rescale_delta(KShape S, u64* __restrict__ delta, const u64* __restrict__ last, LimbList L,
+__global__ void k_rescale_delta(KShape S, u64* __restrict__ delta, const u64* __restrict__ last, const GRID_CONST LimbList L,
                                 int last_mod, PolyStride ps) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
@@ -190,7 +205,7 @@ __global__ void k_rescale_delta(KShape S, u64* __restrict__ delta, const u64* __
 }
 
 // centred lift of a single coefficient-domain limb (mod q_src) into every row modulus (ModRaise)
-__global__ void k_center_lift(KShape S, u64* __restrict__ out, const u64* __restrict__ in, LimbList L, int src_mod,
+__global__ void k_center_lift(KShape S, u64* __restrict__ out, const u64* __restrict__ in, const GRID_CONST LimbList L, int src_mod,
                               PolyStride ps) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
@@ -215,7 +230,7 @@ __device__ __forceinline__ u64 mix64(u64 z) {
 __device__ __forceinline__ u64 rand64(u64 seed, u64 stream, u64 idx) {
     return mix64(mix64(seed + stream * 0xD1342543DE82EF95ull) + idx);
 }
-__global__ void k_sample_uniform(KShape S, u64* __restrict__ out, LimbList L, u64 seed, u64 stream) {
+__global__ void k_sample_uniform(KShape S, u64* __restrict__ out, const GRID_CONST LimbList L, u64 seed, u64 stream) {
     const int row = blockIdx.y;
     const int mod = L.idx[row];
     const u64 q = S.mc[mod].q;
@@ -231,7 +246,7 @@ __global__ void k_sample_uniform(KShape S, u64* __restrict__ out, LimbList L, u6
     }
 }
 // kind 0: centred binomial (21+21 bits); kind 1: ternary {-1,0,1} w.p. 1/4,1/2,1/4.  Same value in every row.
-__global__ void k_sample_small(KShape S, u64* __restrict__ out, LimbList L, u64 seed, u64 stream, int kind) {
+__global__ void k_sample_small(KShape S, u64* __restrict__ out, const GRID_CONST LimbList L, u64 seed, u64 stream, int kind) {
     const int row = blockIdx.y;
     const u64 q = S.mc[L.idx[row]].q;
     FOR_THREADS {
@@ -242,7 +257,7 @@ __global__ void k_sample_small(KShape S, u64* __restrict__ out, LimbList L, u64 
     }
 }
 // signed 64-bit coefficients -> residues in every row
-__global__ void k_reduce_i64(KShape S, u64* __restrict__ out, const i64* __restrict__ v, LimbList L) {
+__global__ void k_reduce_i64(KShape S, u64* __restrict__ out, const i64* __restrict__ v, const GRID_CONST LimbList L) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
     FOR_THREADS {
@@ -355,15 +370,18 @@ void launch_tensor(KShape S, u64* d, const u64* a, const u64* b, const LimbList&
 void launch_permute(KShape S, u64* out, const u64* a, const u32* perm, int rows, int npoly, PolyStride ps, dev_stream st) {
     if (rows) LAUNCH(k_permute, grid3(S, rows, npoly), dim3(TPB), st, S, out, a, perm, ps);
 }
-void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* evk, const u32* perm, const LimbList& L,
-                     const LimbList& ERow, int beta, int evk_rows, dev_stream st) {
-    if (L.n) LAUNCH(k_ks_inner, grid3(S, L.n), dim3(TPB), st, S, acc, ext, evk, perm, L, ERow, beta, L.n, evk_rows);
+void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u64* evk, const u32* perm,
+                     const LimbList& L, const LimbList& ERow, int beta, int evk_rows, int nq, int alpha,
+                     const u64* addend, const ScalarList& PmodQ, dev_stream st) {
+    if (L.n)
+        LAUNCH(k_ks_inner, grid3(S, L.n), dim3(TPB), st, S, acc, ext, own, evk, perm, L, ERow, beta, L.n, evk_rows, nq,
+               alpha, addend, PmodQ);
 }
-void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable& T, int nz, size_t in_zs, size_t out_zs,
-                         dev_stream st) {
-    if (!T.nt || !nz) return;
-    dim3 g((1u << S.logn) / TPB, (T.nt + BC_CHUNK - 1) / BC_CHUNK, nz);
-    LAUNCH(k_base_convert, g, dim3(TPB), st, S, out, in, T, in_zs, out_zs);
+void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int max_nt,
+                         int nz, size_t in_zs, size_t out_zs, dev_stream st) {
+    if (!max_nt || !nz) return;
+    dim3 g((1u << S.logn) / TPB, (max_nt + BC_CHUNK - 1) / BC_CHUNK, nz);
+    LAUNCH(k_base_convert, g, dim3(TPB), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs);
 }
 void launch_rescale_delta(KShape S, u64* delta, const u64* last, const LimbList& L, int last_mod, int npoly, PolyStride ps,
                           dev_stream st) {

@@ -2,8 +2,8 @@
 // Zeta16 encoding: reference xor4_lut.py:63-74, mixcol_final.py:80-99, invmixcolumns_fhe.py:76-90,
 // sub_bytes_lut.py:63-71).
 //
-//   lut2:    sum_t c_t * A[p_t] (x) B[q_t]   as ONE 3-polynomial accumulation, ONE relinearisation and two
-//            rescales, instead of one ct*ct multiplication (key switch + rescale) per term.  Terms are
+//   lut2:    sum_t c_t * A[p_t] (x) B[q_t]   as ONE 3-polynomial accumulation and ONE relinearisation whose ModDown
+//            also divides by the two rescale primes, instead of one ct*ct multiplication (key switch + rescale) per term.  Terms are
 //            grouped by p:  sum_p A_p (x) (sum_q c_pq B_q), so the kernel does |P| tensor products.
 //   lincomb: sum_k c_k * X[k] with one rescale per distinct input level (not one per term).
 //
@@ -34,7 +34,7 @@ namespace {
 
 // d[3][rows][N] = sum over p-groups of A_p (x) (sum_q c_pq B_q)
 __global__ void __launch_bounds__(256)
-k_lut2(KShape S, u64* __restrict__ d, Lut2Args G, LimbList L) {
+k_lut2(KShape S, u64* __restrict__ d, const GRID_CONST Lut2Args G, const GRID_CONST LimbList L) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
     const size_t N = (size_t)1 << S.logn, P = (size_t)G.rows << S.logn;
@@ -76,7 +76,7 @@ k_lut2(KShape S, u64* __restrict__ d, Lut2Args G, LimbList L) {
 
 // out[poly][rows][N] = sum_t x_t * c_t  (blockIdx.z = polynomial)
 __global__ void __launch_bounds__(256)
-k_lincomb(KShape S, u64* __restrict__ out, LinCombArgs G, LimbList L) {
+k_lincomb(KShape S, u64* __restrict__ out, const GRID_CONST LinCombArgs G, const GRID_CONST LimbList L) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
     const size_t N = (size_t)1 << S.logn, P = (size_t)G.rows << S.logn;
@@ -179,17 +179,12 @@ Ct* Engine::lut2(const std::vector<Ct*>& A, const std::vector<Ct*>& B, const int
     LimbList ll = limb_list(mods_q(level));
     u64* d = alloc(3 * ps);
     LAUNCH(k_lut2, dim3((unsigned)(n / 256), level + 1), dim3(256), st, ks, d, G, ll);
-    // one relinearisation, then two rescales
-    u64* k2 = alloc(2 * ps);
-    key_switch(d + 2 * ps, level, &relin, k2);
-    launch_add(ks, k2, k2, d, ll, 2, PolyStride{ps, ps, ps}, st);
-    u64* r1 = alloc((size_t)2 * level * n);
-    rescale_into(r1, k2, 2, level);
+    // ONE relinearisation merged with BOTH rescales: (<digits(d2), rlk> + P (d0, d1)) / (P q_l q_{l-1})   (spec S6b)
+    Decomp D = decompose(d + 2 * ps, level);
     Ct* out = new_ct(2, level - 2);
-    rescale_into(out->d, r1, 2, level - 1);
+    ks_apply(D, &relin, nullptr, out->d, d, 2);
+    release(D.ext);
     release(d);
-    release(k2);
-    release(r1);
     n_mul_cc++;
     return out;
 }

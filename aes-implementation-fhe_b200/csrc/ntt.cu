@@ -88,7 +88,7 @@ __device__ __forceinline__ u64 canon2(u64 v, u64 q) { return v >= q ? v - q : v;
 // LOGR = 4: R = 16 rows,  tile = 256 columns x 16 rows, one radix-16 round (X = 1).
 template <int LOGR>
 __global__ void __launch_bounds__(kThreads, 2)
-ntt_fwd_passA(const u64* __restrict__ src, u64* __restrict__ dst, NttJob J, NttTables T) {
+ntt_fwd_passA(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
     constexpr int RG = (1 << LOGR) / 16;          // row groups per column: 16 or 1
     constexpr int TC = kThreads / RG;             // columns per CTA: 16 or 256
     CKKS_SHARED u64 sm[LOGR == 8 ? 256 * 16 : 1];
@@ -139,7 +139,7 @@ ntt_fwd_passA(const u64* __restrict__ src, u64* __restrict__ dst, NttJob J, NttT
 // ---------------------------------------------------------------- forward, pass B (rows)
 // 16 rows of 256 per CTA; row with global index Rg is rooted at table index R + Rg.
 __global__ void __launch_bounds__(kThreads, 2)
-ntt_fwd_passB(u64* __restrict__ data, NttJob J, NttTables T) {
+ntt_fwd_passB(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
     CKKS_SHARED u64 sm[16 * 256 + 16 * 16];
     if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
     const int limb = J.rows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
@@ -182,7 +182,7 @@ ntt_fwd_passB(u64* __restrict__ data, NttJob J, NttTables T) {
 
 // ---------------------------------------------------------------- inverse, pass B^-1 (rows)
 __global__ void __launch_bounds__(kThreads, 2)
-ntt_inv_passB(const u64* __restrict__ src, u64* __restrict__ dst, NttJob J, NttTables T) {
+ntt_inv_passB(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
     CKKS_SHARED u64 sm[16 * 256 + 16 * 16];
     if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
     const int limb = J.rows[blockIdx.z][blockIdx.y], slimb = J.srows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
@@ -227,7 +227,7 @@ ntt_inv_passB(const u64* __restrict__ src, u64* __restrict__ dst, NttJob J, NttT
 // ---------------------------------------------------------------- inverse, pass A^-1 (columns)
 template <int LOGR>
 __global__ void __launch_bounds__(kThreads, 2)
-ntt_inv_passA(u64* __restrict__ data, NttJob J, NttTables T) {
+ntt_inv_passA(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
     constexpr int RG = (1 << LOGR) / 16;
     constexpr int TC = kThreads / RG;
     CKKS_SHARED u64 sm[LOGR == 8 ? 256 * 16 : 1];

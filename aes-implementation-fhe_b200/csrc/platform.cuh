@@ -36,6 +36,7 @@ extern long g_launch_count;   // kernels launched by this library (bench.py repo
 #define BLOCK_SYNC __syncthreads()
 #define LAUNCH(kern, grid, block, stream, ...) (++g_launch_count, kern<<<grid, block, 0, stream>>>(__VA_ARGS__))
 #define CKKS_SHARED __shared__
+#define GRID_CONST __grid_constant__
 
 #define CUDA_CHECK(expr)                                                                          \
     do {                                                                                          \
@@ -143,6 +144,7 @@ extern thread_local dim3 blockDim, gridDim;
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define CKKS_SHARED static thread_local
+#define GRID_CONST
 #define FOR_THREADS for (threadIdx.x = 0; threadIdx.x < blockDim.x; ++threadIdx.x)
 #define BLOCK_SYNC ((void)0)
 

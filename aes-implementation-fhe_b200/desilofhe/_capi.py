@@ -61,6 +61,9 @@ def load():
         "ckks_keygen_secret": (i32, [vp]), "ckks_keygen_public": (i32, [vp]), "ckks_keygen_relin": (i32, [vp]),
         "ckks_keygen_conjugation": (i32, [vp]), "ckks_keygen_rotation": (i32, [vp, lngp, i32]),
         "ckks_keygen_bootstrap": (i32, [vp]),
+        "ckks_set_keys_external": (i32, [vp, i32]),
+        "ckks_switch_key_ids": (i32, [vp, u64p, i32, C.POINTER(i32)]),
+        "ckks_switch_key_buffer": (i32, [vp, u64, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "ckks_set_bootstrap_params": (i32, [vp, i32, i32, i32, i32, i32]),
         "ckks_encode": (i32, [vp, dp, i32, pp]),
         "ckks_encrypt": (i32, [vp, dp, i32, pp]),

@@ -61,6 +61,13 @@ int ckks_keygen_relin(ckks_engine* e);
 int ckks_keygen_conjugation(ckks_engine* e);
 int ckks_keygen_rotation(ckks_engine* e, const long* steps, int nsteps);
 int ckks_keygen_bootstrap(ckks_engine* e);
+/* Multi-GPU key distribution (one broadcast of the evaluation keys from rank 0 at setup, no per-round
+ * exchange).  With external = 1 the keygen_* calls for switching keys (relin, conjugation, rotation, bootstrap) only
+ * allocate; the caller fills the buffers (NCCL broadcast over NVLink) before the first evaluation.  The secret and
+ * public keys are always derived from the seed. */
+int ckks_set_keys_external(ckks_engine* e, int external);
+int ckks_switch_key_ids(ckks_engine* e, uint64_t* ids_out, int capacity, int* count);   /* 0 = relinearisation key */
+int ckks_switch_key_buffer(ckks_engine* e, uint64_t id, void** device_ptr, size_t* bytes);
 /* optional, before ckks_keygen_bootstrap: |I| bound K, Chebyshev degree, double-angle steps, matrices per DFT */
 int ckks_set_bootstrap_params(ckks_engine* e, int K, int cheb_degree, int double_angle, int cts_groups, int stc_groups);
 

@@ -337,20 +337,24 @@ class OracleCKKS:
             out.append(full)
         return out
 
-    def mod_down(self, acc: np.ndarray, level: int) -> np.ndarray:
-        """[level+1+K][N] over Q_level u P  ->  floor(acc / P) over Q_level (NTT domain)."""
-        qi = self._idx_q(level)
-        pi = list(range(self.L + 1, self.L + 1 + self.K))
+    def mod_down(self, acc: np.ndarray, level: int, drop: int = 0) -> np.ndarray:
+        """[level+1+K][N] over Q_level u P  ->  floor(acc / (P q_{level-drop+1} .. q_level)) over Q_{level-drop}
+        (NTT domain).  drop = 0 is the plain ModDown; drop = 1, 2 merge one or two rescales into it (spec S6b)."""
         nq = level + 1
-        coefP = self.intt(acc[nq:], pi)
-        conv = self.ntt(self._baseconv(coefP, pi, qi), qi)
-        Pprod = 1
-        for x in self.p:
-            Pprod *= x
-        pinv = [pow(Pprod % self.moduli[i], -1, self.moduli[i]) for i in qi]
-        return self.mul_scalar(self.sub(acc[:nq], conv, qi), pinv, qi)
+        keep = self._idx_q(level - drop)
+        src_mods = list(range(level - drop + 1, level + 1)) + list(range(self.L + 1, self.L + 1 + self.K))
+        src_rows = list(range(level - drop + 1, level + 1)) + list(range(nq, nq + self.K))
+        coef = self.intt(acc[src_rows], src_mods)
+        conv = self.ntt(self._baseconv(coef, src_mods, keep), keep)
+        D = 1
+        for i in src_mods:
+            D *= self.moduli[i]
+        inv = [pow(D % self.moduli[i], -1, self.moduli[i]) for i in keep]
+        return self.mul_scalar(self.sub(acc[:len(keep)], conv, keep), inv, keep)
 
-    def key_switch(self, d: np.ndarray, level: int, key_id: int, digits: Optional[List[np.ndarray]] = None):
+    def key_switch(self, d: np.ndarray, level: int, key_id: int, digits: Optional[List[np.ndarray]] = None,
+                   addend: Optional[np.ndarray] = None, drop: int = 0):
+        """addend = (d0, d1) over Q_level is folded in as P * addend before the division (merged relinearisation)."""
         self.counters["keyswitch"] = self.counters.get("keyswitch", 0) + 1
         qp = self._idx_qp(level)
         rows = list(range(level + 1)) + list(range(self.L + 1, self.L + 1 + self.K))   # rows into evk's limb axis
@@ -362,7 +366,15 @@ class OracleCKKS:
         for j, ext in enumerate(digits):
             self.lib.ref_muladd_batch(acc0, ext, np.ascontiguousarray(evk[j, 0][rows]), len(qp), self.N, mods)
             self.lib.ref_muladd_batch(acc1, ext, np.ascontiguousarray(evk[j, 1][rows]), len(qp), self.N, mods)
-        return self.mod_down(acc0, level), self.mod_down(acc1, level)
+        if addend is not None:
+            qi = self._idx_q(level)
+            Pprod = 1
+            for x in self.p:
+                Pprod *= x
+            pm = [Pprod % self.moduli[i] for i in qi]
+            acc0[:level + 1] = self.add(acc0[:level + 1], self.mul_scalar(addend[0], pm, qi), qi)
+            acc1[:level + 1] = self.add(acc1[:level + 1], self.mul_scalar(addend[1], pm, qi), qi)
+        return self.mod_down(acc0, level, drop), self.mod_down(acc1, level, drop)
 
     # ------------------------------------------------------------------ rescale / level management (spec S6)
     def rescale_poly(self, c: np.ndarray, level: int) -> np.ndarray:
@@ -475,9 +487,9 @@ class OracleCKKS:
         if min(a.level, b.level) < 1:
             raise RuntimeError("ciphertext level should be positive for multiplication")
         self.counters["mul_cc"] = self.counters.get("mul_cc", 0) + 1
-        r = self.rescale(self.relinearize(self.tensor(a, b)))
-        r.scale = self.scales[r.level]
-        return r
+        t = self.tensor(a, b)
+        k0, k1 = self.key_switch(t.c[2], t.level, RELIN_ID, addend=t.c[:2], drop=1)      # spec S6b
+        return Ct(np.stack([k0, k1]), t.level - 1, self.scales[t.level - 1])
 
     def apply_galois(self, a: Ct, g: int) -> Ct:
         if g not in self.evk:
@@ -541,10 +553,8 @@ class OracleCKKS:
             self.lib.ref_muladd_batch(d[1], a1, u0, len(idx), self.N, mods)
             self.lib.ref_muladd_batch(d[2], a1, u1, len(idx), self.N, mods)
         self.counters["mul_cc"] = self.counters.get("mul_cc", 0) + 1
-        t = Ct(d, level, self.scales[level] ** 2 * self.scales[level - 1])
-        r = self.rescale(self.rescale(self.relinearize(t)))
-        r.scale = self.scales[r.level]
-        return r
+        k0, k1 = self.key_switch(d[2], level, RELIN_ID, addend=d[:2], drop=2)             # spec S6b
+        return Ct(np.stack([k0, k1]), level - 2, self.scales[level - 2])
 
     def lincomb(self, X: Sequence[Ct], coeffs) -> Ct:
         """sum_k c_k X_k: per distinct level one un-rescaled multiply-accumulate and one rescale; partial sums are
