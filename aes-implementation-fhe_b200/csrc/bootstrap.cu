@@ -205,20 +205,25 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
     LimbList ll = E.limb_list(E.mods_q(P.level));
     Ct* acc = nullptr;
     for (const BsgsRow& R : P.rows) {
-        // inner = sum_i diag_i (.) baby_i, un-rescaled (scale S_l^2), one rescale per matrix at the end
+        // inner = sum_i diag_i (.) baby_i in one fused multiply-accumulate, un-rescaled (scale S_l^2): one rescale
+        // per matrix at the end
         Ct* inner = A.keep(E.new_ct(2, P.level));
-        bool first = true;
-        u64* tmp = E.alloc(2 * ps);
-        for (const BsgsTerm& T : R.terms) {
-            Ct* b = baby[T.i];
-            if (first) launch_mul(E.ks, inner->d, b->d, T.pt->d, ll, 2, PolyStride{ps, ps, 0}, E.st);
+        u64* tmp = nullptr;
+        for (size_t off = 0; off < R.terms.size(); off += 16) {
+            std::vector<const Ct*> xs;
+            std::vector<const Pt*> ps_;
+            for (size_t t = off; t < std::min(R.terms.size(), off + 16); t++) {
+                xs.push_back(baby[R.terms[t].i]);
+                ps_.push_back(R.terms[t].pt);
+            }
+            if (off == 0) E.diag_mac(inner->d, xs, ps_, P.level);
             else {
-                launch_mul(E.ks, tmp, b->d, T.pt->d, ll, 2, PolyStride{ps, ps, 0}, E.st);
+                if (!tmp) tmp = E.alloc(2 * ps);
+                E.diag_mac(tmp, xs, ps_, P.level);
                 launch_add(E.ks, inner->d, inner->d, tmp, ll, 2, PolyStride{ps, ps, ps}, E.st);
             }
-            first = false;
         }
-        E.release(tmp);
+        if (tmp) E.release(tmp);
         if (R.giant % (long)E.slots()) inner = A.keep(E.rotate(inner, -R.giant));
         if (!acc) acc = inner;
         else {
@@ -247,12 +252,16 @@ static Ct* cheb_eval(Engine& E, Arena& A, Ct* x, const std::vector<double>& coef
     std::function<Res(const std::vector<double>&)> rec = [&](const std::vector<double>& c) -> Res {
         const int d = (int)c.size() - 1;
         if (d < m) {
-            Ct* acc = nullptr;
+            // leaf: sum_k c_k T_k as one fused linear combination (one rescale per distinct level of the T_k)
+            std::vector<Ct*> xs;
+            std::vector<double> cs;
             for (int k = 1; k <= d; k++) {
                 if (fabs(c[k]) < 1e-300) continue;
-                Ct* t = A.keep(E.mul_const(get(k), c[k], 0.0));
-                acc = acc ? A.keep(E.add(acc, t)) : t;
+                xs.push_back(get(k));
+                cs.push_back(c[k]);
+                cs.push_back(0.0);
             }
+            Ct* acc = xs.empty() ? nullptr : A.keep(E.lincomb(xs, cs.data(), (int)xs.size()));
             return Res{acc, c[0]};
         }
         int g = m;

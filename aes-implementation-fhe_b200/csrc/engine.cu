@@ -749,10 +749,8 @@ Decomp Engine::decompose(const u64* d, int level) {
     J.nz = beta;
     J.szs = J.dzs = (size_t)rows * n;
     long modup_limbs = 0;
-    int max_nt = 0;
     for (int j = 0; j < beta; j++) {
         const BaseConvTable& T = modup_table(level, j);
-        max_nt = std::max(max_nt, T.nt);
         J.n = std::max(J.n, T.nt);
         J.cnt[j] = (unsigned char)T.nt;
         for (int t = 0; t < T.nt; t++) {
@@ -761,7 +759,15 @@ Decomp Engine::decompose(const u64* d, int level) {
         }
         modup_limbs += T.nt;
     }
-    launch_base_convert(ks, D.ext, coef, modup_tables_dev(level), 1, max_nt, beta, 0, (size_t)rows * n, st);
+    {
+        // all digits but the last have alpha sources; the last may have fewer (its own template instance)
+        const BaseConvTable* tabs = modup_tables_dev(level);
+        const int ns_last = nq - (beta - 1) * prm.alpha;
+        const int nfull = ns_last == prm.alpha ? beta : beta - 1;
+        if (nfull) launch_base_convert(ks, D.ext, coef, tabs, 1, prm.alpha, nfull, 0, (size_t)rows * n, st);
+        if (nfull < beta)
+            launch_base_convert(ks, D.ext + (size_t)nfull * rows * n, coef, tabs + nfull, 1, ns_last, 1, 0, (size_t)rows * n, st);
+    }
     // one batched forward NTT over the converted rows of all digits (z = digit)
     run_ntt(D.ext, D.ext, J, false, modup_limbs);
     release(coef);
@@ -785,7 +791,7 @@ void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64*
     for (int k = 0; k < K(); k++) { prow.push_back(nq + k); pmod.push_back(L() + 1 + k); }
     ntt_rows(acc, prow, pmod, true, 2, (size_t)rows * n);
     u64* conv = alloc((size_t)2 * nout * n);
-    launch_base_convert(ks, conv, acc, moddown_table_dev(level, drop), 0, nout, 2, (size_t)rows * n, (size_t)nout * n, st);
+    launch_base_convert(ks, conv, acc, moddown_table_dev(level, drop), 0, K() + drop, 2, (size_t)rows * n, (size_t)nout * n, st);
     std::vector<int> qi = mods_q(level - drop);
     ntt_rows(conv, qi, qi, false, 2, (size_t)nout * n);
     launch_sub_mul_scalar(ks, out, acc, conv, limb_list(qi), moddown_inv(level, drop), 2,

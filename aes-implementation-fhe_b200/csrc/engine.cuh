@@ -142,6 +142,7 @@ class Engine {
     Ct* lut2(const std::vector<Ct*>& A, const std::vector<Ct*>& B, const int* p, const int* q, const double* coef,
              int nterms);
     Ct* lincomb(const std::vector<Ct*>& X, const double* coef, int n);
+    void diag_mac(u64* out, const std::vector<const Ct*>& x, const std::vector<const Pt*>& p, int level);
     const u64* const_table(const double* coef_re_im, int n, int scale_level, int level);
     Ct* drop_to(const Ct* a, int level);         // plain limb drop (scale unchanged): internal/bootstrap use
 

@@ -154,35 +154,50 @@ __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restric
 
 // ------------------------------------------------------------------ fast basis conversion (spec S5)
 // in: coefficient-domain residues, source i in row T.srow[i]; out row T.orow[t] for target t.
-// One thread per coefficient, blockIdx.y picks a chunk of BC_CHUNK target moduli.
-// y_i = x_i * hatinv_i mod s_i is recomputed per chunk (cheap next to the traffic).
-__global__ void k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in,
-                               const BaseConvTable* __restrict__ tabs, int tab_zstride, size_t in_zs, size_t out_zs) {
+// One thread per coefficient computes ALL targets: y_i = x_i * hatinv_i mod s_i once, then for every target a
+// 128-bit multiply-accumulate sum_i y_i * hat[i][t] with ONE reduction at the end (no per-term reduction, no Shoup
+// companion loads).  The hat matrix and 2^64 mod q_t sit in shared memory (broadcast reads).  NS is a template
+// parameter so the source loop is fully unrolled without predicated-off iterations.  Integer-pipe bound.
+template <int NS>
+__global__ void __launch_bounds__(TPB)
+k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in, const BaseConvTable* __restrict__ tabs,
+               int tab_zstride, size_t in_zs, size_t out_zs) {
+    CKKS_SHARED u64 s_hat[BC_MAX_TGT * NS];
+    CKKS_SHARED u64 s_r64[BC_MAX_TGT];
     const size_t N = (size_t)1 << S.logn;
     const BaseConvTable& T = tabs[blockIdx.z * tab_zstride];      // slice z uses its own table (digit) or a shared one
-    const int ns = T.ns, nt = T.nt;
-    const int t0 = blockIdx.y * BC_CHUNK;
-    if (t0 >= nt) return;
-    const int t1 = t0 + BC_CHUNK < nt ? t0 + BC_CHUNK : nt;
+    const int nt = T.nt;
+    FOR_THREADS {
+        for (int e = threadIdx.x; e < nt * NS; e += TPB) {
+            const int t = e / NS, i = e - t * NS;
+            s_hat[e] = ldg(T.hat + i * nt + t);
+        }
+        for (int t = threadIdx.x; t < nt; t += TPB) {
+            const ModConst m = S.mc[T.tgt[t]];
+            s_r64[t] = barrett_reduce128(1, 0, m);                // 2^64 mod q_t
+        }
+    }
+    BLOCK_SYNC;
     FOR_THREADS {
         const u32 k = blockIdx.x * TPB + threadIdx.x;
         const u64* src = in + blockIdx.z * in_zs;
         u64* dst = out + blockIdx.z * out_zs;
-        u64 y[BC_MAX_SRC];
+        u64 y[NS];
 #pragma unroll
-        for (int i = 0; i < BC_MAX_SRC; i++)
-            if (i < ns) y[i] = shoup_mul(src[(size_t)T.srow[i] * N + k], T.hatinv[i], T.hatinv_s[i], S.mc[T.src[i]].q);
-        for (int t = t0; t < t1; t++) {
+        for (int i = 0; i < NS; i++)
+            y[i] = shoup_mul(src[(size_t)T.srow[i] * N + k], T.hatinv[i], T.hatinv_s[i], S.mc[T.src[i]].q);
+        for (int t = 0; t < nt; t++) {
             const ModConst m = S.mc[T.tgt[t]];
-            u64 lo = 0;
+            u64 hi = 0, lo = 0;
 #pragma unroll
-            for (int i = 0; i < BC_MAX_SRC; i++)
-                if (i < ns) {
-                    // canonical products (< q_t < 2^61): eight of them fit a word, then fold
-                    lo += shoup_mul(y[i], ldg(T.hat + i * nt + t), ldg(T.hat_s + i * nt + t), m.q);
-                    if ((i & 7) == 7) lo = barrett_reduce64(lo, m);
-                }
-            dst[(size_t)T.orow[t] * N + k] = barrett_reduce64(lo, m);
+            for (int i = 0; i < NS; i++) mac128(hi, lo, y[i], s_hat[t * NS + i]);
+            // (hi, lo) < NS * 2^122: fold the high word through 2^64 mod q_t, then one Barrett reduction
+            const u64 h1 = barrett_reduce64(hi, m);
+            u64 h2 = 0, l2 = lo;
+            const u64 pl = h1 * s_r64[t];
+            l2 += pl;
+            h2 = mulhi64(h1, s_r64[t]) + (l2 < pl);
+            dst[(size_t)T.orow[t] * N + k] = barrett_reduce128(h2, l2, m);
         }
     }
 }
@@ -377,11 +392,17 @@ void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u
         LAUNCH(k_ks_inner, grid3(S, L.n), dim3(TPB), st, S, acc, ext, own, evk, perm, L, ERow, beta, L.n, evk_rows, nq,
                alpha, addend, PmodQ);
 }
-void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int max_nt,
+void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns,
                          int nz, size_t in_zs, size_t out_zs, dev_stream st) {
-    if (!max_nt || !nz) return;
-    dim3 g((1u << S.logn) / TPB, (max_nt + BC_CHUNK - 1) / BC_CHUNK, nz);
-    LAUNCH(k_base_convert, g, dim3(TPB), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs);
+    if (!nz) return;
+    dim3 g((1u << S.logn) / TPB, 1, nz);
+#define BC_CASE(n) case n: LAUNCH(k_base_convert<n>, g, dim3(TPB), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs); break;
+    switch (ns) {
+        BC_CASE(1) BC_CASE(2) BC_CASE(3) BC_CASE(4) BC_CASE(5) BC_CASE(6) BC_CASE(7) BC_CASE(8) BC_CASE(9) BC_CASE(10)
+        BC_CASE(11) BC_CASE(12) BC_CASE(13) BC_CASE(14) BC_CASE(15) BC_CASE(16)
+        default: throw std::runtime_error("base_convert: unsupported source count");
+    }
+#undef BC_CASE
 }
 void launch_rescale_delta(KShape S, u64* delta, const u64* last, const LimbList& L, int last_mod, int npoly, PolyStride ps,
                           dev_stream st) {

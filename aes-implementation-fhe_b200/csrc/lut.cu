@@ -30,7 +30,30 @@ struct LinCombArgs {
     int nterms, rows;
 };
 
+struct DiagMacArgs {
+    const u64* x[16];                  // ciphertexts [2][rows][N]
+    const u64* p[16];                  // plaintext polynomials [rows][N]
+    int nterms, rows;
+};
+
 namespace {
+
+// out[poly][rows][N] = sum_t x_t[poly] * p_t   (BSGS inner sum of a linear transform, un-rescaled; blockIdx.z = poly)
+__global__ void __launch_bounds__(256)
+k_diag_mac(KShape S, u64* __restrict__ out, const GRID_CONST DiagMacArgs G, const GRID_CONST LimbList L) {
+    const int row = blockIdx.y;
+    const ModConst m = S.mc[L.idx[row]];
+    const size_t N = (size_t)1 << S.logn, P = (size_t)G.rows << S.logn;
+    FOR_THREADS {
+        const size_t i = (size_t)row * N + blockIdx.x * 256 + threadIdx.x;
+        u64 hi = 0, lo = 0;
+        for (int t = 0; t < G.nterms; t++) {
+            mac128(hi, lo, ldg(G.x[t] + blockIdx.z * P + i), ldg(G.p[t] + i));
+            if ((t & 3) == 3 && t + 1 < G.nterms) { lo = barrett_reduce128(hi, lo, m); hi = 0; }
+        }
+        out[blockIdx.z * P + i] = barrett_reduce128(hi, lo, m);
+    }
+}
 
 // d[3][rows][N] = sum over p-groups of A_p (x) (sum_q c_pq B_q)
 __global__ void __launch_bounds__(256)
@@ -187,6 +210,21 @@ Ct* Engine::lut2(const std::vector<Ct*>& A, const std::vector<Ct*>& B, const int
     release(d);
     n_mul_cc++;
     return out;
+}
+
+// out = sum_t x_t (.) p_t for up to 16 (ciphertext, plaintext) pairs at the same level, no rescale
+void Engine::diag_mac(u64* out, const std::vector<const Ct*>& x, const std::vector<const Pt*>& p, int level) {
+    if (x.empty() || x.size() != p.size() || x.size() > 16) throw std::runtime_error("diag_mac: 1..16 terms");
+    DiagMacArgs G;
+    memset(&G, 0, sizeof(G));
+    for (size_t t = 0; t < x.size(); t++) {
+        if (x[t]->level != level || p[t]->level != level || x[t]->npoly != 2) throw std::runtime_error("diag_mac: level mismatch");
+        G.x[t] = x[t]->d;
+        G.p[t] = p[t]->d;
+    }
+    G.nterms = (int)x.size();
+    G.rows = level + 1;
+    LAUNCH(k_diag_mac, dim3((unsigned)(N() / 256), level + 1, 2), dim3(256), st, ks, out, G, limb_list(mods_q(level)));
 }
 
 // sum_k c_k X_k: one fused multiply-accumulate and one rescale per distinct input level, partial sums added

@@ -22,6 +22,9 @@
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef NTT_MIN_BLOCKS
+#define NTT_MIN_BLOCKS 4      // register cap 64: no spills to speak of, 32 resident warps per SM instead of 16
+#endif
 
 __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
 
@@ -87,7 +90,7 @@ __device__ __forceinline__ u64 canon2(u64 v, u64 q) { return v >= q ? v - q : v;
 // LOGR = 8: R = 256 rows, tile = 16 columns x 256 rows, two radix-16 rounds (X = 1, then 16 + rr).
 // LOGR = 4: R = 16 rows,  tile = 256 columns x 16 rows, one radix-16 round (X = 1).
 template <int LOGR>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS)
 ntt_fwd_passA(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
     constexpr int RG = (1 << LOGR) / 16;          // row groups per column: 16 or 1
     constexpr int TC = kThreads / RG;             // columns per CTA: 16 or 256
@@ -138,7 +141,7 @@ ntt_fwd_passA(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CON
 
 // ---------------------------------------------------------------- forward, pass B (rows)
 // 16 rows of 256 per CTA; row with global index Rg is rooted at table index R + Rg.
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS)
 ntt_fwd_passB(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
     CKKS_SHARED u64 sm[16 * 256 + 16 * 16];
     if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
@@ -181,7 +184,7 @@ ntt_fwd_passB(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
 }
 
 // ---------------------------------------------------------------- inverse, pass B^-1 (rows)
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS)
 ntt_inv_passB(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
     CKKS_SHARED u64 sm[16 * 256 + 16 * 16];
     if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
@@ -226,7 +229,7 @@ ntt_inv_passB(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CON
 
 // ---------------------------------------------------------------- inverse, pass A^-1 (columns)
 template <int LOGR>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS)
 ntt_inv_passA(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
     constexpr int RG = (1 << LOGR) / 16;
     constexpr int TC = kThreads / RG;
