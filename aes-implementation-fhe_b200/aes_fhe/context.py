@@ -54,8 +54,16 @@ class EngineContext:
         self._bs_total_s = 0.0
 
     # ---- data movement (engine_context.py:56-63) ----
-    def encrypt(self, data: np.ndarray):
+    def encrypt(self, data: np.ndarray, level=None):
+        """`level` (fused mode only) asks the engine to encrypt at a lower level than the fresh level when the caller
+        knows how many levels the next steps consume: same plaintext, fewer limbs to carry (the reference engine has
+        no such argument and always encrypts at the top)."""
+        if level is not None and self.fused:
+            return self.engine.encrypt(data, self.public_key, level=int(level))
         return self.engine.encrypt(data, self.public_key)
+
+    def level_down(self, ct, level: int):
+        return self.engine.level_down(ct, level) if self.fused and ct.level > level else ct
 
     def decrypt(self, ct) -> np.ndarray:
         return self.engine.decrypt(ct, self.secret_key)

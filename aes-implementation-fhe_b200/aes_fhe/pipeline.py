@@ -16,8 +16,8 @@ from typing import Any, Dict, List, Optional, Tuple
 import numpy as np
 
 from .context import EngineContext
-from .steps import (AddRoundKey, InvMixColumnsFHE, InvShiftRows, MixColFinal, ShiftRows, StateEncoder,
-                    SubBytesLUT, XOR4LUT, from_zeta, to_zeta)
+from .steps import (GF_DEPTH, SHIFTROWS_DEPTH, SUBBYTES_DEPTH, XOR4_DEPTH, AddRoundKey, InvMixColumnsFHE, InvShiftRows,
+                    MixColFinal, ShiftRows, StateEncoder, SubBytesLUT, XOR4LUT, from_zeta, to_zeta)
 
 Pair = Tuple[Any, Any]
 
@@ -43,10 +43,13 @@ class AESPipeline:
         self._rk_cache: Optional[List[Pair]] = None
 
     # ---- helpers (pipeline.py:65-98) ----
-    def _renorm_pair(self, hi, lo) -> Pair:
-        """Hard renorm ("snap"): decrypt, round every nibble to its codeword, re-encrypt."""
+    def _renorm_pair(self, hi, lo, depth=None) -> Pair:
+        """Hard renorm ("snap"): decrypt, round every nibble to its codeword, re-encrypt.  `depth` = levels the steps
+        up to the next renorm consume; in fused mode the re-encryption happens at that level instead of the top."""
         if not self.use_hard_renorm_between_steps:
             return hi, lo
+        if depth is not None and getattr(self.ctx, "fused", False):
+            return self.encoder.encode(self.encoder.decode(hi, lo), level=depth)
         return self.encoder.encode(self.encoder.decode(hi, lo))
 
     def _encode_key(self, key_bytes: np.ndarray) -> Pair:
@@ -95,11 +98,12 @@ class AESPipeline:
     # ---- one middle round, the unit BASELINE.json config 2 is quoted on (pipeline.py:143-151) ----
     def encrypt_round(self, ct_hi, ct_lo, key_hi, key_lo) -> Pair:
         ct_hi, ct_lo = self.sub_bytes(ct_hi, ct_lo)
-        ct_hi, ct_lo = self._renorm_pair(ct_hi, ct_lo)
+        # next renorm comes after ShiftRows, the GF LUTs and the first XOR4 of MixColumns
+        ct_hi, ct_lo = self._renorm_pair(ct_hi, ct_lo, depth=SHIFTROWS_DEPTH + GF_DEPTH + XOR4_DEPTH)
         ct_hi, ct_lo = self.shift_rows(ct_hi, ct_lo)
         ct_hi, ct_lo = self.mix_columns(ct_hi, ct_lo)
         ct_hi, ct_lo = self.add_round_key(ct_hi, ct_lo, key_hi, key_lo)
-        return self._renorm_pair(ct_hi, ct_lo)
+        return self._renorm_pair(ct_hi, ct_lo, depth=SUBBYTES_DEPTH)
 
     # ---- full flows ----
     def encrypt(self, state, round_keys, debug: Optional[Dict[str, Any]] = None) -> Pair:
@@ -110,13 +114,13 @@ class AESPipeline:
         rk = self._prepare_round_keys(round_keys)
         ct = self.add_round_key(*ct, *rk[0])
         self._log_pair(debug, "enc.r0.ark", *ct)
-        ct = self._renorm_pair(*ct)
+        ct = self._renorm_pair(*ct, depth=SUBBYTES_DEPTH)
         self._log_pair(debug, "enc.r0.renorm", *ct)
         for r in range(1, 10):
             ct = self.encrypt_round(*ct, *rk[r])
         ct = self.sub_bytes(*ct)
         self._log_pair(debug, "enc.final.sub", *ct)
-        ct = self._renorm_pair(*ct)
+        ct = self._renorm_pair(*ct, depth=SHIFTROWS_DEPTH + XOR4_DEPTH)
         self._log_pair(debug, "enc.final.sub.renorm", *ct)
         ct = self.shift_rows(*ct)
         self._log_pair(debug, "enc.final.sr", *ct)
@@ -232,7 +236,7 @@ class BatchedStateEncoder:
         self.sc = ctx.engine.slot_count
         self.stride = self.sc // 16
 
-    def encode(self, state: np.ndarray) -> Pair:
+    def encode(self, state: np.ndarray, level=None) -> Pair:
         st = np.asarray(state, dtype=np.uint8)
         if st.ndim == 1:
             st = np.broadcast_to(st, (self.stride, 16))
@@ -242,7 +246,10 @@ class BatchedStateEncoder:
         # slot i*stride + b  <-  byte i of block b
         hi = to_zeta((full >> 4) & 0xF, 16).T.reshape(-1)
         lo = to_zeta(full & 0xF, 16).T.reshape(-1)
-        return self.ctx.encrypt(hi.astype(np.complex128)), self.ctx.encrypt(lo.astype(np.complex128))
+        if level is None:
+            return self.ctx.encrypt(hi.astype(np.complex128)), self.ctx.encrypt(lo.astype(np.complex128))
+        return (self.ctx.encrypt(hi.astype(np.complex128), level=level),
+                self.ctx.encrypt(lo.astype(np.complex128), level=level))
 
     def decode(self, ct_hi, ct_lo) -> np.ndarray:
         hi = from_zeta(self.ctx.decrypt(ct_hi), 16).reshape(16, self.stride).T

@@ -22,6 +22,12 @@ from .context import EngineContext
 
 Pair = Tuple[Any, Any]
 
+# multiplicative depths of the steps, used for the encryption-level hints of the fused mode
+XOR4_DEPTH = 5          # power basis 3 + product 1 + constant 1
+GF_DEPTH = 5
+SUBBYTES_DEPTH = 13
+SHIFTROWS_DEPTH = 1
+
 
 def to_zeta(values: np.ndarray, modulus: int = 16) -> np.ndarray:
     """k -> exp(-2 pi i k / modulus)   (utils.py:9-12)."""
@@ -42,7 +48,7 @@ class StateEncoder:
         self.sc = ctx.engine.slot_count
         self.stride = self.sc // 16
 
-    def encode(self, state: np.ndarray) -> Pair:
+    def encode(self, state: np.ndarray, level=None) -> Pair:
         assert state.shape == (16,)
         pos = np.arange(16) * self.stride
         vecs = []
@@ -50,7 +56,9 @@ class StateEncoder:
             v = np.ones(self.sc, dtype=np.complex128)
             v[pos] = to_zeta(nib.astype(np.uint8), 16)
             vecs.append(v)
-        return self.ctx.encrypt(vecs[0]), self.ctx.encrypt(vecs[1])
+        if level is None:
+            return self.ctx.encrypt(vecs[0]), self.ctx.encrypt(vecs[1])
+        return self.ctx.encrypt(vecs[0], level=level), self.ctx.encrypt(vecs[1], level=level)
 
     def decode(self, ct_hi, ct_lo) -> np.ndarray:
         pos = np.arange(16) * self.stride
@@ -103,6 +111,10 @@ class XOR4LUT:
 
     def apply(self, a_ct, b_ct):
         eng = self.ctx
+        if getattr(eng, "fused", False):
+            # build both power bases at the common level (a cached round-key ciphertext may sit far above the state)
+            lvl = min(a_ct.level, b_ct.level)
+            a_ct, b_ct = eng.level_down(a_ct, lvl), eng.level_down(b_ct, lvl)
         A = self._build_power_basis_16(a_ct)
         B = self._build_power_basis_16(b_ct)
         if getattr(eng, "fused", False):
@@ -322,7 +334,9 @@ class MixColFinal(_MixBase):
     def gf_mult_3(self, ct_hi, ct_lo) -> Pair:
         return self._gf(3, ct_hi, ct_lo)
 
-    def _renorm_pair(self, hi, lo) -> Pair:
+    def _renorm_pair(self, hi, lo, depth=None) -> Pair:
+        if depth is not None and getattr(self.ctx, "fused", False):
+            return self.enc.encode(self.enc.decode(hi, lo), level=depth)
         return self.enc.encode(self.enc.decode(hi, lo))
 
     def _xor_ct(self, a, b):
@@ -338,12 +352,12 @@ class MixColFinal(_MixBase):
         log("two", two), log("thr", thr)
         acc = self._xor_pair(two, thr)
         log("acc1", acc)
-        acc = self._renorm_pair(*acc)
+        acc = self._renorm_pair(*acc, depth=XOR4_DEPTH)
         acc = self._xor_pair(acc, r2)
         log("acc2", acc)
-        acc = self._renorm_pair(*acc)
+        acc = self._renorm_pair(*acc, depth=XOR4_DEPTH)
         acc = self._xor_pair(acc, r3)
-        acc = self._renorm_pair(*acc)
+        acc = self._renorm_pair(*acc, depth=0 if do_final_bootstrap else None)     # the bootstrap starts from level 0
         log("acc3", acc)
         out_hi, out_lo = acc
         if do_final_bootstrap:
@@ -387,9 +401,11 @@ class InvMixColumnsFHE(_MixBase):
             out = eng.add(out, p)
         return out
 
-    def _renorm_pair(self, hi, lo) -> Pair:
+    def _renorm_pair(self, hi, lo, depth=None) -> Pair:
         if not self.use_hard_renorm:
             return hi, lo
+        if depth is not None and getattr(self.ctx, "fused", False):
+            return self.enc.encode(self.enc.decode(hi, lo), level=depth)
         return self.enc.encode(self.enc.decode(hi, lo))
 
     def _xor(self, a, b):
@@ -406,12 +422,12 @@ class InvMixColumnsFHE(_MixBase):
         e9 = self.gf_mult_9(*r3); log("mul9", e9)
         acc = self._xor_pair(e14, e11)
         log("acc1", acc)
-        acc = self._renorm_pair(*acc)
+        acc = self._renorm_pair(*acc, depth=XOR4_DEPTH)
         acc = self._xor_pair(acc, e13)
         log("acc2", acc)
-        acc = self._renorm_pair(*acc)
+        acc = self._renorm_pair(*acc, depth=XOR4_DEPTH)
         acc = self._xor_pair(acc, e9)
-        out_h, out_l = self._renorm_pair(*acc)
+        out_h, out_l = self._renorm_pair(*acc, depth=0 if do_final_bootstrap else None)
         if do_final_bootstrap:
             out_h = self.ctx.bootstrap(out_h)
             out_l = self.ctx.bootstrap(out_l)

@@ -23,7 +23,7 @@ namespace {
 
 constexpr int kThreads = 256;
 #ifndef NTT_MIN_BLOCKS
-#define NTT_MIN_BLOCKS 4      // register cap 64: no spills to speak of, 32 resident warps per SM instead of 16
+#define NTT_MIN_BLOCKS 3      // register cap 80, no spills; measured best of {2,3,4,5} (profiles/r1_ntt_occupancy_sweep.txt)
 #endif
 
 __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
