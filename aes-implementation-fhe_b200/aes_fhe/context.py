@@ -123,6 +123,12 @@ class EngineContext:
             return self.engine.rotate_many(ct, self.rotation_key, list(steps))
         return [self.rotate(ct, s) for s in steps]
 
+    def pair_map(self, fn, first, second):
+        """(fn(*first), fn(*second)); on the B200 engine the two independent calls run on two stream lanes."""
+        if self.fused and hasattr(self.engine, "pair_map"):
+            return self.engine.pair_map(fn, first, second)
+        return fn(*first), fn(*second)
+
     def lut2(self, basis_a, basis_b, terms):
         return self.engine.lut2(basis_a, basis_b, terms)
 

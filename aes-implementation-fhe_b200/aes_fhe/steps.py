@@ -134,6 +134,9 @@ class AddRoundKey:
         self.xor4 = xor4
 
     def __call__(self, ct_hi, ct_lo, key_hi, key_lo) -> Pair:
+        ctx = self.xor4.ctx
+        if getattr(ctx, "fused", False):      # the two nibble planes never interact inside XOR4: overlap them
+            return ctx.pair_map(self.xor4.apply, (ct_hi, key_hi), (ct_lo, key_lo))
         return self.xor4.apply(ct_hi, key_hi), self.xor4.apply(ct_lo, key_lo)
 
 
@@ -187,8 +190,8 @@ class SubBytesLUT:
             lifted = self._poly_fused(pos16, 16, lift, self.ks_lift, self.c0_lift)
             ct_b = eng.multiply(ct_hi, lifted)
             pos256 = eng.make_power_basis(ct_b, self.deg256)
-            return (self._poly_fused(pos256, 256, self.hi, self.ks_hi_nz, self.c0_hi),
-                    self._poly_fused(pos256, 256, self.lo, self.ks_lo_nz, self.c0_lo))
+            return eng.pair_map(self._poly_fused, (pos256, 256, self.hi, self.ks_hi_nz, self.c0_hi),
+                                (pos256, 256, self.lo, self.ks_lo_nz, self.c0_lo))
         lifted = eng.add_plain(eng.multiply(ct_lo, 0.0), self.c0_lift)
         pos16 = eng.make_power_basis(ct_lo, self.deg16) if self.deg16 > 0 else []
         for k in self.ks_lift:
@@ -302,8 +305,8 @@ class _MixBase:
         if getattr(self.ctx, "fused", False):
             # the reference rebuilds both 16-power bases for the hi and the lo table (mixcol_final.py:82-83);
             # they are identical, so the fused path builds them once
-            bases = (self._basis16(ct_hi), self._basis16(ct_lo))
-            return (self._eval2(ct_hi, ct_lo, mult, "hi", bases), self._eval2(ct_hi, ct_lo, mult, "lo", bases))
+            bases = self.ctx.pair_map(self._basis16, (ct_hi,), (ct_lo,))
+            return self.ctx.pair_map(self._eval2, (ct_hi, ct_lo, mult, "hi", bases), (ct_hi, ct_lo, mult, "lo", bases))
         return self._eval2(ct_hi, ct_lo, mult, "hi"), self._eval2(ct_hi, ct_lo, mult, "lo")
 
     def _col_shift_rowmajor(self, ct, k_up: int):
@@ -316,6 +319,8 @@ class _MixBase:
         return [(self._col_shift_rowmajor(ct_hi, k), self._col_shift_rowmajor(ct_lo, k)) for k in (1, 2, 3)]
 
     def _xor_pair(self, a: Pair, b: Pair) -> Pair:
+        if getattr(self.ctx, "fused", False):
+            return self.ctx.pair_map(self.xor4.apply, (a[0], b[0]), (a[1], b[1]))
         return self.xor4.apply(a[0], b[0]), self.xor4.apply(a[1], b[1])
 
 
@@ -361,8 +366,8 @@ class MixColFinal(_MixBase):
         log("acc3", acc)
         out_hi, out_lo = acc
         if do_final_bootstrap:
-            out_hi = self.ctx.bootstrap(self.ctx.to_intt(out_hi))
-            out_lo = self.ctx.bootstrap(self.ctx.to_intt(out_lo))
+            boot = lambda c: self.ctx.bootstrap(self.ctx.to_intt(c))
+            out_hi, out_lo = self.ctx.pair_map(boot, (out_hi,), (out_lo,))
             log("out", (out_hi, out_lo))
         return out_hi, out_lo
 
@@ -429,7 +434,6 @@ class InvMixColumnsFHE(_MixBase):
         acc = self._xor_pair(acc, e9)
         out_h, out_l = self._renorm_pair(*acc, depth=0 if do_final_bootstrap else None)
         if do_final_bootstrap:
-            out_h = self.ctx.bootstrap(out_h)
-            out_l = self.ctx.bootstrap(out_l)
+            out_h, out_l = self.ctx.pair_map(self.ctx.bootstrap, (out_h,), (out_l,))
         log("out", (out_h, out_l))
         return out_h, out_l

@@ -66,6 +66,9 @@ void ckks_engine_destroy(ckks_engine* e) {
     delete e->E;
     delete e;
 }
+int ckks_fork(ckks_engine* e) { return guard([&] { e->E->fork(); }); }
+int ckks_set_lane(ckks_engine* e, int lane) { return guard([&] { e->E->set_lane(lane); }); }
+int ckks_join(ckks_engine* e) { return guard([&] { e->E->join(); }); }
 int ckks_sync(ckks_engine* e) { return guard([&] { e->E->sync(); }); }
 int ckks_slot_count(const ckks_engine* e) { return (int)e->E->slots(); }
 int ckks_get_params(const ckks_engine* e, int* logn, int* nq, int* np, int* alpha, int* fresh_level, uint64_t* q_out,

@@ -147,7 +147,9 @@ Engine::Engine(const Params& P) : prm(P) {
     if (prm.q.empty() || prm.p.empty()) throw std::runtime_error("engine: empty modulus chain");
     dev::set_device(prm.device);
     dev::pool_setup(prm.device);
-    st = dev::stream_create();
+    st = st_main = dev::stream_create();
+    st_lane[0] = dev::stream_create();
+    st_lane[1] = dev::stream_create();
     mod = prm.q;
     mod.insert(mod.end(), prm.p.begin(), prm.p.end());
     if ((int)mod.size() > CKKS_MAX_MODULI) throw std::runtime_error("engine: too many moduli");
@@ -238,7 +240,7 @@ Engine::Engine(const Params& P) : prm(P) {
 }
 
 Engine::~Engine() {
-    try { dev::sync(st); } catch (...) {}
+    try { if (in_fork) join(); sync(); } catch (...) {}
     bootstrap_teardown();
     for (auto& kv : gkeys) dev::free(kv.second.d, st);
     for (auto& kv : perms) dev::free(kv.second, st);
@@ -252,8 +254,40 @@ Engine::~Engine() {
     dev::free(sk_ntt, st);
     dev::free(pk, st);
     for (void* p : owned) dev::free(p, st);
-    try { dev::sync(st); } catch (...) {}
-    dev::stream_destroy(st);
+    try { sync(); } catch (...) {}
+    dev::stream_destroy(st_main);
+    dev::stream_destroy(st_lane[0]);
+    dev::stream_destroy(st_lane[1]);
+}
+
+// ------------------------------------------------------------------ lanes
+void Engine::sync() {
+    dev::sync(st_main);
+    dev::sync(st_lane[0]);
+    dev::sync(st_lane[1]);
+}
+void Engine::fork() {
+    if (in_fork) throw std::runtime_error("fork: already forked");
+    dev::stream_wait(st_lane[0], st_main);
+    dev::stream_wait(st_lane[1], st_main);
+    in_fork = true;
+}
+void Engine::set_lane(int lane) {
+    if (!in_fork) throw std::runtime_error("set_lane outside fork/join");
+    if (lane < 0 || lane > 1) throw std::runtime_error("set_lane: lane must be 0 or 1");
+    cur_lane = lane;
+    st = st_lane[lane];
+}
+void Engine::join() {
+    if (!in_fork) return;
+    dev::stream_wait(st_main, st_lane[0]);
+    dev::stream_wait(st_main, st_lane[1]);
+    st = st_main;
+    cur_lane = -1;
+    in_fork = false;
+    std::vector<Ct*> d;
+    d.swap(deferred_free);
+    for (Ct* c : d) free_ct(c);
 }
 
 // ------------------------------------------------------------------ memory
@@ -263,11 +297,16 @@ Ct* Engine::new_ct(int npoly, int level) {
     Ct* c = new Ct();
     c->npoly = npoly;
     c->level = level;
+    c->lane = cur_lane;
     c->d = alloc((size_t)npoly * (level + 1) * N());
     return c;
 }
 void Engine::free_ct(Ct* c) {
     if (!c) return;
+    if (in_fork && c->lane != cur_lane) {          // another lane (or the main stream) may still be reading it
+        deferred_free.push_back(c);
+        return;
+    }
     for (auto& kv : c->lowered) free_ct(kv.second);
     release(c->d);
     delete c;
@@ -515,6 +554,7 @@ EvalKey* Engine::galois_key(u64 g) {
     automorph(sg, sk_ntt, nmod(), 1, g);
     EvalKey k = make_switch_key(g, sg);
     release(sg);
+    dev::sync(st);                                  // first use may come from the other lane
     gkeys[g] = k;
     return &gkeys[g];
 }
@@ -764,9 +804,10 @@ Decomp Engine::decompose(const u64* d, int level) {
         const BaseConvTable* tabs = modup_tables_dev(level);
         const int ns_last = nq - (beta - 1) * prm.alpha;
         const int nfull = ns_last == prm.alpha ? beta : beta - 1;
-        if (nfull) launch_base_convert(ks, D.ext, coef, tabs, 1, prm.alpha, nfull, 0, (size_t)rows * n, st);
+        if (nfull) launch_base_convert(ks, D.ext, coef, tabs, 1, prm.alpha, rows, nfull, 0, (size_t)rows * n, st);
         if (nfull < beta)
-            launch_base_convert(ks, D.ext + (size_t)nfull * rows * n, coef, tabs + nfull, 1, ns_last, 1, 0, (size_t)rows * n, st);
+            launch_base_convert(ks, D.ext + (size_t)nfull * rows * n, coef, tabs + nfull, 1, ns_last, rows, 1, 0,
+                                (size_t)rows * n, st);
     }
     // one batched forward NTT over the converted rows of all digits (z = digit)
     run_ntt(D.ext, D.ext, J, false, modup_limbs);
@@ -791,7 +832,8 @@ void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64*
     for (int k = 0; k < K(); k++) { prow.push_back(nq + k); pmod.push_back(L() + 1 + k); }
     ntt_rows(acc, prow, pmod, true, 2, (size_t)rows * n);
     u64* conv = alloc((size_t)2 * nout * n);
-    launch_base_convert(ks, conv, acc, moddown_table_dev(level, drop), 0, K() + drop, 2, (size_t)rows * n, (size_t)nout * n, st);
+    launch_base_convert(ks, conv, acc, moddown_table_dev(level, drop), 0, K() + drop, nout, 2, (size_t)rows * n,
+                        (size_t)nout * n, st);
     std::vector<int> qi = mods_q(level - drop);
     ntt_rows(conv, qi, qi, false, 2, (size_t)nout * n);
     launch_sub_mul_scalar(ks, out, acc, conv, limb_list(qi), moddown_inv(level, drop), 2,
@@ -866,7 +908,11 @@ Ct* Engine::level_down(Ct* c, int target) {
     if (target == c->level) return c;
     if (target > c->level || target < 0) throw std::runtime_error("level_down: bad target");
     for (auto& kv : c->lowered)
-        if (kv.first == target) return kv.second;
+        if (kv.first == target) {
+            // a copy memoised by the other lane has not necessarily been computed yet on the device
+            if (in_fork && kv.second->lane >= 0 && kv.second->lane != cur_lane) dev::sync(st_lane[kv.second->lane]);
+            return kv.second;
+        }
     const size_t n = N();
     const int t1 = target + 1;
     std::vector<int> idx = mods_q(t1);

@@ -34,6 +34,7 @@ struct Ct {
     int npoly = 2;
     int level = 0;
     u64* d = nullptr;                               // [npoly][level+1][N], NTT domain
+    int lane = -1;                                  // stream lane that produced it (-1: the main stream)
     std::vector<std::pair<int, Ct*>> lowered;       // memoised level_down() results (owned)
 };
 struct Pt {
@@ -100,7 +101,18 @@ class Engine {
     Ct* new_ct(int npoly, int level);
     void free_ct(Ct* c);
     void free_pt(Pt* p);
-    void sync() { dev::sync(st); }
+    void sync();
+
+    // ---- lanes: two extra streams for the independent halves of a ciphertext pair (hi / lo nibble).  fork() orders both
+    // lanes after the main stream, set_lane() makes every following call enqueue on that lane, join() orders the main
+    // stream after both.  Ciphertexts freed while another lane is current are released at the join.
+    void fork();
+    void set_lane(int lane);
+    void join();
+    dev_stream st_main = 0, st_lane[2] = {0, 0};
+    int cur_lane = -1;
+    bool in_fork = false;
+    std::vector<Ct*> deferred_free;
 
     // ---- keys (spec S8)
     void keygen_secret();

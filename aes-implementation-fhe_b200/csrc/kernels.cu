@@ -167,6 +167,10 @@ k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in, cons
     const size_t N = (size_t)1 << S.logn;
     const BaseConvTable& T = tabs[blockIdx.z * tab_zstride];      // slice z uses its own table (digit) or a shared one
     const int nt = T.nt;
+    // blockIdx.y picks a chunk of BC_CHUNK targets: more CTAs in flight for the small launches of a key switch; the
+    // NS multiplications for y are repeated per chunk (NS of NS*(BC_CHUNK+1))
+    const int tbeg = blockIdx.y * BC_CHUNK, tend = tbeg + BC_CHUNK < nt ? tbeg + BC_CHUNK : nt;
+    if (tbeg >= nt) return;
     FOR_THREADS {
         for (int e = threadIdx.x; e < nt * NS; e += TPB) {
             const int t = e / NS, i = e - t * NS;
@@ -186,7 +190,7 @@ k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in, cons
 #pragma unroll
         for (int i = 0; i < NS; i++)
             y[i] = shoup_mul(src[(size_t)T.srow[i] * N + k], T.hatinv[i], T.hatinv_s[i], S.mc[T.src[i]].q);
-        for (int t = 0; t < nt; t++) {
+        for (int t = tbeg; t < tend; t++) {
             const ModConst m = S.mc[T.tgt[t]];
             u64 hi = 0, lo = 0;
 #pragma unroll
@@ -393,9 +397,9 @@ void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u
                alpha, addend, PmodQ);
 }
 void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns,
-                         int nz, size_t in_zs, size_t out_zs, dev_stream st) {
-    if (!nz) return;
-    dim3 g((1u << S.logn) / TPB, 1, nz);
+                         int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st) {
+    if (!nz || !max_nt) return;
+    dim3 g((1u << S.logn) / TPB, (max_nt + BC_CHUNK - 1) / BC_CHUNK, nz);
 #define BC_CASE(n) case n: LAUNCH(k_base_convert<n>, g, dim3(TPB), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs); break;
     switch (ns) {
         BC_CASE(1) BC_CASE(2) BC_CASE(3) BC_CASE(4) BC_CASE(5) BC_CASE(6) BC_CASE(7) BC_CASE(8) BC_CASE(9) BC_CASE(10)

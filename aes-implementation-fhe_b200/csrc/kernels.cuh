@@ -4,7 +4,7 @@
 
 #define BC_MAX_SRC 16
 #define BC_MAX_TGT 48
-#define BC_CHUNK 8
+#define BC_CHUNK 6
 
 // element strides between consecutive polynomials (blockIdx.z) for each pointer of a kernel
 struct PolyStride {
@@ -41,8 +41,8 @@ void launch_permute(KShape S, u64* out, const u64* a, const u32* perm, int rows,
 // acc[2][rows][N] = sum_j ext[j][rows][N] * evk[j][2][evk_rows][N]; ERow maps working row -> evk row
 void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u64* evk, const u32* perm, const LimbList& L, const LimbList& ERow, int beta, int evk_rows, int nq, int alpha, const u64* addend, const ScalarList& PmodQ, dev_stream st);
 // nz independent conversions: slice z reads in + z*in_zs, writes out + z*out_zs, with table tabs_dev[z*tab_zstride]
-// (device memory); every table of the launch has exactly `ns` sources
-void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns, int nz, size_t in_zs, size_t out_zs, dev_stream st);
+// (device memory); every table of the launch has exactly `ns` sources and at most `max_nt` targets
+void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns, int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st);
 void launch_rescale_delta(KShape S, u64* delta, const u64* last, const LimbList& L, int last_mod, int npoly, PolyStride ps, dev_stream st);
 void launch_center_lift(KShape S, u64* out, const u64* in, const LimbList& L, int src_mod, int npoly, PolyStride ps, dev_stream st);
 void launch_sample_uniform(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, dev_stream st);

@@ -86,6 +86,14 @@ inline void check_last(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA launch error in ") + what + ": " + cudaGetErrorString(e));
 }
+// order `waiter` after everything enqueued on `src` so far (fork/join of the engine's lanes)
+inline void stream_wait(dev_stream waiter, dev_stream src) {
+    cudaEvent_t ev;
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(ev, src));
+    CUDA_CHECK(cudaStreamWaitEvent(waiter, ev, 0));
+    CUDA_CHECK(cudaEventDestroy(ev));     // released once the wait has been satisfied
+}
 inline void* host_alloc_pinned(size_t bytes) {
     void* p = nullptr;
     CUDA_CHECK(cudaMallocHost(&p, bytes));
@@ -186,6 +194,7 @@ inline void d2d(void* o, const void* i, size_t bytes, dev_stream) { memmove(o, i
 inline void zero(void* d, size_t bytes, dev_stream) { memset(d, 0, bytes); }
 inline void sync(dev_stream) {}
 inline void check_last(const char*) {}
+inline void stream_wait(dev_stream, dev_stream) {}
 inline void* host_alloc_pinned(size_t bytes) { return ::malloc(bytes); }
 inline void host_free_pinned(void* p) { ::free(p); }
 struct Timer {

@@ -96,6 +96,7 @@ class Plaintext:
         if h is None:
             out = C.c_void_p()
             _capi.check(self._eng._lib.ckks_encode(self._eng._ptr, self.vec.view(np.float64), level, C.byref(out)))
+            self._eng.sync()          # a cached encoding may next be read from the other stream lane
             h = self._enc[level] = out.value
         return h
 
@@ -189,6 +190,19 @@ class Engine:
 
     def sync(self):
         _capi.check(self._lib.ckks_sync(self._ptr))
+
+    def pair_map(self, fn, first, second):
+        """(fn(*first), fn(*second)) with the two calls enqueued on two CUDA stream lanes so the device overlaps them:
+        the hi- and lo-nibble ciphertexts of a state never interact inside XOR4 / bootstrap."""
+        _capi.check(self._lib.ckks_fork(self._ptr))
+        try:
+            _capi.check(self._lib.ckks_set_lane(self._ptr, 0))
+            a = fn(*first)
+            _capi.check(self._lib.ckks_set_lane(self._ptr, 1))
+            b = fn(*second)
+        finally:
+            _capi.check(self._lib.ckks_join(self._ptr))
+        return a, b
 
     # ------------------------------------------------------------------ multi-GPU key distribution (SURVEY.md 8e)
     def set_keys_external(self, external: bool):
