@@ -205,9 +205,9 @@ def run_ours(args) -> None:
     io = {"h2d": 0, "d2h": 0}
     enc0, dec0 = ctx.encrypt, ctx.decrypt
 
-    def enc(v):
+    def enc(v, level=None):
         io["h2d"] += eng.slot_count * 16
-        return enc0(v)
+        return enc0(v, level=level)
 
     def dec(c):
         io["d2h"] += eng.slot_count * 16

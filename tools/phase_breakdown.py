@@ -59,8 +59,7 @@ def main(reps: int = 3):
         a = phase("renorm", lambda: mix._renorm_pair(*a))
         a = phase("mix.xor", lambda: mix._xor_pair(a, r3))
         a = phase("renorm", lambda: mix._renorm_pair(*a))
-        b0 = phase("bootstrap", lambda: ctx.bootstrap(a[0]))
-        b1 = phase("bootstrap", lambda: ctx.bootstrap(a[1]))
+        b0, b1 = phase("bootstrap", lambda: ctx.pair_map(ctx.bootstrap, (a[0],), (a[1],)))
         ct = phase("add_round_key", lambda: pipe.add_round_key(b0, b1, *rk[1]))
         ct = phase("renorm", lambda: pipe._renorm_pair(*ct))
     total = sum(v["s"] for v in acc.values())
