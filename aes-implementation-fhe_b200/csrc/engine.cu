@@ -254,6 +254,7 @@ Engine::~Engine() {
     dev::free(sk_ntt, st);
     dev::free(pk, st);
     for (void* p : owned) dev::free(p, st);
+    try { trim_pools(); } catch (...) {}
     try { sync(); } catch (...) {}
     dev::stream_destroy(st_main);
     dev::stream_destroy(st_lane[0]);
@@ -271,6 +272,7 @@ void Engine::fork() {
     dev::stream_wait(st_lane[0], st_main);
     dev::stream_wait(st_lane[1], st_main);
     in_fork = true;
+    fork_epoch++;
 }
 void Engine::set_lane(int lane) {
     if (!in_fork) throw std::runtime_error("set_lane outside fork/join");
@@ -288,23 +290,58 @@ void Engine::join() {
     std::vector<Ct*> d;
     d.swap(deferred_free);
     for (Ct* c : d) free_ct(c);
+    std::vector<Pt*> dp;
+    dp.swap(deferred_free_pt);
+    for (Pt* p : dp) free_pt(p);
 }
 
 // ------------------------------------------------------------------ memory
-u64* Engine::alloc(size_t words) { return (u64*)dev::alloc(words * sizeof(u64), st); }
-void Engine::release(void* p) { dev::free(p, st); }
+u64* Engine::alloc(size_t words) {
+    const size_t bytes = ((words * sizeof(u64)) + 511) & ~(size_t)511;
+    LanePool& P = pools[cur_lane + 1];
+    auto it = P.free.find(bytes);
+    if (it != P.free.end() && !it->second.empty()) {
+        void* p = it->second.back();
+        it->second.pop_back();
+        P.cached -= bytes;
+        return (u64*)p;
+    }
+    void* p = dev::alloc(bytes, st);
+    alloc_bytes[p] = bytes;
+    return (u64*)p;
+}
+void Engine::release(void* p) {
+    if (!p) return;
+    auto it = alloc_bytes.find(p);
+    if (it == alloc_bytes.end()) { dev::free(p, st); return; }
+    LanePool& P = pools[cur_lane + 1];
+    P.free[it->second].push_back(p);
+    P.cached += it->second;
+    if (P.cached > ((size_t)48 << 30)) trim_pools();
+}
+// give everything cached back to the driver pool (only when a lane hoards more than 48 GiB, and at teardown)
+void Engine::trim_pools() {
+    sync();
+    for (LanePool& P : pools) {
+        for (auto& kv : P.free)
+            for (void* p : kv.second) { alloc_bytes.erase(p); dev::free(p, st_main); }
+        P.free.clear();
+        P.cached = 0;
+    }
+}
 Ct* Engine::new_ct(int npoly, int level) {
     Ct* c = new Ct();
     c->npoly = npoly;
     c->level = level;
     c->lane = cur_lane;
+    c->epoch = fork_epoch;
     c->d = alloc((size_t)npoly * (level + 1) * N());
     return c;
 }
 void Engine::free_ct(Ct* c) {
     if (!c) return;
-    if (in_fork && c->lane != cur_lane) {          // another lane (or the main stream) may still be reading it
-        deferred_free.push_back(c);
+    if (in_fork && !(c->lane == cur_lane && c->epoch == fork_epoch)) {
+        deferred_free.push_back(c);                // another lane may still be reading it: released at the join
         return;
     }
     for (auto& kv : c->lowered) free_ct(kv.second);
@@ -313,6 +350,7 @@ void Engine::free_ct(Ct* c) {
 }
 void Engine::free_pt(Pt* p) {
     if (!p) return;
+    if (in_fork) { deferred_free_pt.push_back(p); return; }
     release(p->d);
     delete p;
 }

@@ -12,6 +12,7 @@
 // different levels are aligned by level_down() (limb drop + one integer multiply + one rescale).
 #pragma once
 #include <map>
+#include <unordered_map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -35,6 +36,7 @@ struct Ct {
     int level = 0;
     u64* d = nullptr;                               // [npoly][level+1][N], NTT domain
     int lane = -1;                                  // stream lane that produced it (-1: the main stream)
+    long epoch = 0;                                 // fork region it was produced in
     std::vector<std::pair<int, Ct*>> lowered;       // memoised level_down() results (owned)
 };
 struct Pt {
@@ -112,7 +114,16 @@ class Engine {
     dev_stream st_main = 0, st_lane[2] = {0, 0};
     int cur_lane = -1;
     bool in_fork = false;
+    long fork_epoch = 0;
     std::vector<Ct*> deferred_free;
+    std::vector<Pt*> deferred_free_pt;
+    // stream-ordered caching arena: a released buffer goes to the free list of the lane it is released on and is handed
+    // out again to later work on the SAME stream (stream order makes that safe), so the hot path makes no
+    // cudaMallocAsync / cudaFreeAsync calls at all
+    struct LanePool { std::map<size_t, std::vector<void*>> free; size_t cached = 0; };
+    LanePool pools[3];
+    std::map<void*, size_t> alloc_bytes;
+    void trim_pools();
 
     // ---- keys (spec S8)
     void keygen_secret();
