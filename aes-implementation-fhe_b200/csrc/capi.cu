@@ -203,6 +203,13 @@ int ckks_counters(const ckks_engine* e, long* o) {
     return CKKS_OK;
 }
 
+int ckks_arena_stats(const ckks_engine* e, long* driver_allocs, size_t* arena_bytes, size_t* cached_bytes) {
+    *driver_allocs = e->E->n_driver_allocs;
+    *arena_bytes = e->E->driver_bytes;
+    *cached_bytes = e->E->pools[0].cached + e->E->pools[1].cached + e->E->pools[2].cached;
+    return CKKS_OK;
+}
+
 // ---------------------------------------------------------------- raw access (tests)
 int ckks_ct_export(ckks_engine* e, const ckks_ct* ct, uint64_t* out) {
     return guard([&] {

@@ -273,6 +273,19 @@ void Engine::fork() {
     dev::stream_wait(st_lane[1], st_main);
     in_fork = true;
     fork_epoch++;
+    // both lanes are ordered after the main stream now, so the main stream's cached buffers are safe for either lane:
+    // deal them out alternately (they come back at the join), otherwise the lanes would keep drawing fresh memory
+    bool flip = false;
+    for (auto& kv : pools[0].free) {
+        for (void* p : kv.second) {
+            LanePool& P = pools[flip ? 2 : 1];
+            P.free[kv.first].push_back(p);
+            P.cached += kv.first;
+            flip = !flip;
+        }
+        kv.second.clear();
+    }
+    pools[0].cached = 0;
 }
 void Engine::set_lane(int lane) {
     if (!in_fork) throw std::runtime_error("set_lane outside fork/join");
@@ -287,6 +300,16 @@ void Engine::join() {
     st = st_main;
     cur_lane = -1;
     in_fork = false;
+    // the main stream is ordered after both lanes: their cached buffers return to the main pool
+    for (int l = 1; l <= 2; l++) {
+        for (auto& kv : pools[l].free) {
+            std::vector<void*>& dst = pools[0].free[kv.first];
+            dst.insert(dst.end(), kv.second.begin(), kv.second.end());
+            pools[0].cached += kv.first * kv.second.size();
+            kv.second.clear();
+        }
+        pools[l].cached = 0;
+    }
     std::vector<Ct*> d;
     d.swap(deferred_free);
     for (Ct* c : d) free_ct(c);
@@ -296,8 +319,20 @@ void Engine::join() {
 }
 
 // ------------------------------------------------------------------ memory
+// size classes: whole limbs (N words), rounded up along 1, 2, 3, 4, 6, 8, 12, 16, 24, 32, ... so that the many
+// slightly different buffer shapes of a key switch recycle each other's memory (at most 1/3 slack)
+static size_t size_class_limbs(size_t limbs) {
+    size_t c = 1;
+    while (c < limbs) {
+        const size_t mid = c + c / 2;
+        if (c >= 2 && mid >= limbs) return mid;
+        c *= 2;
+    }
+    return c;
+}
 u64* Engine::alloc(size_t words) {
-    const size_t bytes = ((words * sizeof(u64)) + 511) & ~(size_t)511;
+    const size_t limbs = (words + N() - 1) / N();
+    const size_t bytes = size_class_limbs(limbs ? limbs : 1) * N() * sizeof(u64);
     LanePool& P = pools[cur_lane + 1];
     auto it = P.free.find(bytes);
     if (it != P.free.end() && !it->second.empty()) {
@@ -308,6 +343,8 @@ u64* Engine::alloc(size_t words) {
     }
     void* p = dev::alloc(bytes, st);
     alloc_bytes[p] = bytes;
+    n_driver_allocs++;
+    driver_bytes += bytes;
     return (u64*)p;
 }
 void Engine::release(void* p) {
@@ -324,7 +361,7 @@ void Engine::trim_pools() {
     sync();
     for (LanePool& P : pools) {
         for (auto& kv : P.free)
-            for (void* p : kv.second) { alloc_bytes.erase(p); dev::free(p, st_main); }
+            for (void* p : kv.second) { alloc_bytes.erase(p); dev::free(p, st_main); driver_bytes -= kv.first; }
         P.free.clear();
         P.cached = 0;
     }

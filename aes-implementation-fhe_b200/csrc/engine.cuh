@@ -124,6 +124,8 @@ class Engine {
     LanePool pools[3];
     std::map<void*, size_t> alloc_bytes;
     void trim_pools();
+    long n_driver_allocs = 0;
+    size_t driver_bytes = 0;
 
     // ---- keys (spec S8)
     void keygen_secret();

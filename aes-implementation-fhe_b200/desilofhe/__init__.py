@@ -188,6 +188,11 @@ class Engine:
         return dict(zip(("keyswitch", "ntt_limbs", "rescale", "mul_cc", "bootstrap"), (int(x) for x in o)),
                     launches=int(self._lib.ckks_launch_count()))
 
+    def arena_stats(self) -> dict:
+        a, b, c = C.c_long(), C.c_size_t(), C.c_size_t()
+        self._lib.ckks_arena_stats(self._ptr, C.byref(a), C.byref(b), C.byref(c))
+        return {"driver_allocs": a.value, "arena_bytes": b.value, "cached_bytes": c.value}
+
     def sync(self):
         _capi.check(self._lib.ckks_sync(self._ptr))
 

@@ -88,6 +88,7 @@ def load():
         "ckks_bootstrap": (i32, [vp, vp, pp]),
         "ckks_bootstrap_out_level": (i32, [vp]),
         "ckks_counters": (i32, [vp, lngp]),
+        "ckks_arena_stats": (i32, [vp, C.POINTER(lng), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
         "ckks_ct_export": (i32, [vp, vp, u64p]),
         "ckks_ct_import": (i32, [vp, i32, i32, u64p, pp]),
         "ckks_pt_export": (i32, [vp, vp, u64p]),

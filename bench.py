@@ -324,7 +324,7 @@ def run_ours(args) -> None:
                            "exceeds the 126 MB L2; no explicit flush"},
                 "s_per_round": s_round, "bytes_exact_vs_fips197_round": ok,
                 "key_switches_per_step": ks_round, "bootstraps_per_step": (c1["bootstrap"] - c0["bootstrap"]) // args.steps,
-                "rotations_per_s_equiv": ks_round / s_round,
+                "rotations_per_s_equiv": ks_round / s_round, "arena": eng.arena_stats(),
                 "e2e": e2e, "gpu_launches": int(launches) * args.steps, "clocks": clk, "roofline": roofline,
                 "cpu_baseline": cpu}
         if dry:

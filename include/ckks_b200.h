@@ -128,6 +128,9 @@ int ckks_bootstrap_out_level(const ckks_engine* e);
 /* ---- counters (per engine): key switches, limb-NTTs, rescales, ct*ct multiplications, bootstraps */
 int ckks_counters(const ckks_engine* e, long* out5);
 
+/* arena statistics: driver allocations made so far, bytes held by the arena, bytes sitting in its free lists */
+int ckks_arena_stats(const ckks_engine* e, long* driver_allocs, size_t* arena_bytes, size_t* cached_bytes);
+
 /* ---- raw access for the bit-exact parity tests against oracle/ (tests/ only; not used by the shim's hot path) */
 int ckks_ct_export(ckks_engine* e, const ckks_ct* ct, uint64_t* out /* [npoly][level+1][N] */);
 int ckks_ct_import(ckks_engine* e, int npoly, int level, const uint64_t* data, ckks_ct** out);
