@@ -123,6 +123,14 @@ class EngineContext:
             return self.engine.rotate_many(ct, self.rotation_key, list(steps))
         return [self.rotate(ct, s) for s in steps]
 
+    def snap_zeta16(self, ct, level=None, stride: int = 1):
+        """Device-side hard renorm of one ciphertext (fused mode): decrypt, snap to codewords, re-encrypt."""
+        return self.engine.snap_zeta16(ct, -1 if level is None else int(level), stride)
+
+    @property
+    def device_renorm(self) -> bool:
+        return self.fused and hasattr(self.engine, "snap_zeta16")
+
     def pair_map(self, fn, first, second):
         """(fn(*first), fn(*second)); on the B200 engine the two independent calls run on two stream lanes."""
         if self.fused and hasattr(self.engine, "pair_map"):

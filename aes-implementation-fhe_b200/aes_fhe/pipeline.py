@@ -48,8 +48,8 @@ class AESPipeline:
         up to the next renorm consume; in fused mode the re-encryption happens at that level instead of the top."""
         if not self.use_hard_renorm_between_steps:
             return hi, lo
-        if depth is not None and getattr(self.ctx, "fused", False):
-            return self.encoder.encode(self.encoder.decode(hi, lo), level=depth)
+        if getattr(self.ctx, "fused", False):
+            return self.encoder.renorm(hi, lo, level=depth)
         return self.encoder.encode(self.encoder.decode(hi, lo))
 
     def _encode_key(self, key_bytes: np.ndarray) -> Pair:
@@ -250,6 +250,12 @@ class BatchedStateEncoder:
             return self.ctx.encrypt(hi.astype(np.complex128)), self.ctx.encrypt(lo.astype(np.complex128))
         return (self.ctx.encrypt(hi.astype(np.complex128), level=level),
                 self.ctx.encrypt(lo.astype(np.complex128), level=level))
+
+    def renorm(self, ct_hi, ct_lo, level=None) -> Pair:
+        """encode(decode(hi, lo)) for the batched layout: every slot is snapped; stays on the device when it can."""
+        if getattr(self.ctx, "device_renorm", False):
+            return self.ctx.pair_map(self.ctx.snap_zeta16, (ct_hi, level, 1), (ct_lo, level, 1))
+        return self.encode(self.decode(ct_hi, ct_lo), level=level)
 
     def decode(self, ct_hi, ct_lo) -> np.ndarray:
         hi = from_zeta(self.ctx.decrypt(ct_hi), 16).reshape(16, self.stride).T

@@ -60,6 +60,12 @@ class StateEncoder:
             return self.ctx.encrypt(vecs[0]), self.ctx.encrypt(vecs[1])
         return self.ctx.encrypt(vecs[0], level=level), self.ctx.encrypt(vecs[1], level=level)
 
+    def renorm(self, ct_hi, ct_lo, level=None) -> Pair:
+        """encode(decode(hi, lo)): on the B200 engine without leaving the device (slots off the stride grid -> 1.0)."""
+        if getattr(self.ctx, "device_renorm", False):
+            return self.ctx.pair_map(self.ctx.snap_zeta16, (ct_hi, level, self.stride), (ct_lo, level, self.stride))
+        return self.encode(self.decode(ct_hi, ct_lo), level=level)
+
     def decode(self, ct_hi, ct_lo) -> np.ndarray:
         pos = np.arange(16) * self.stride
         hi = from_zeta(self.ctx.decrypt(ct_hi)[pos], 16)
@@ -340,8 +346,8 @@ class MixColFinal(_MixBase):
         return self._gf(3, ct_hi, ct_lo)
 
     def _renorm_pair(self, hi, lo, depth=None) -> Pair:
-        if depth is not None and getattr(self.ctx, "fused", False):
-            return self.enc.encode(self.enc.decode(hi, lo), level=depth)
+        if getattr(self.ctx, "fused", False):
+            return self.enc.renorm(hi, lo, level=depth)
         return self.enc.encode(self.enc.decode(hi, lo))
 
     def _xor_ct(self, a, b):
@@ -409,8 +415,8 @@ class InvMixColumnsFHE(_MixBase):
     def _renorm_pair(self, hi, lo, depth=None) -> Pair:
         if not self.use_hard_renorm:
             return hi, lo
-        if depth is not None and getattr(self.ctx, "fused", False):
-            return self.enc.encode(self.enc.decode(hi, lo), level=depth)
+        if getattr(self.ctx, "fused", False):
+            return self.enc.renorm(hi, lo, level=depth)
         return self.enc.encode(self.enc.decode(hi, lo))
 
     def _xor(self, a, b):

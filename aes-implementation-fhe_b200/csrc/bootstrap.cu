@@ -203,12 +203,20 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
     for (size_t t = 0; t < rot.size(); t++) baby[P.babies[t]] = A.keep(rot[t]);
     const size_t ps = (size_t)(P.level + 1) * E.N();
     LimbList ll = E.limb_list(E.mods_q(P.level));
-    Ct* acc = nullptr;
+    // Giant steps with ONE ModDown for the whole matrix ("double hoisting"): every rotated inner sum contributes
+    //   sigma_g(c0) in Q_l   and   <ModUp(sigma_g(c1)), rtk_g> in Q_l u P,
+    // the Q_l u P parts are accumulated and divided by P once; the un-rotated row (giant 0) is added as it is.
+    const size_t n = E.N();
+    const int rows = P.level + 1 + E.K();
+    u64* accqp = nullptr;                       // [2][rows][N]
+    Ct* sum = A.keep(E.new_ct(2, P.level));     // running sum of the Q_l parts: (sigma(c0) terms + row 0, row 0's c1)
+    bool sum_init = false;
+    u64* tmp = nullptr;
+    u64* rbuf = nullptr;
     for (const BsgsRow& R : P.rows) {
         // inner = sum_i diag_i (.) baby_i in one fused multiply-accumulate, un-rescaled (scale S_l^2): one rescale
         // per matrix at the end
         Ct* inner = A.keep(E.new_ct(2, P.level));
-        u64* tmp = nullptr;
         for (size_t off = 0; off < R.terms.size(); off += 16) {
             std::vector<const Ct*> xs;
             std::vector<const Pt*> ps_;
@@ -223,16 +231,35 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
                 launch_add(E.ks, inner->d, inner->d, tmp, ll, 2, PolyStride{ps, ps, ps}, E.st);
             }
         }
-        if (tmp) E.release(tmp);
-        if (R.giant % (long)E.slots()) inner = A.keep(E.rotate(inner, -R.giant));
-        if (!acc) acc = inner;
-        else {
-            Ct* s = A.keep(E.new_ct(2, P.level));
-            launch_add(E.ks, s->d, acc->d, inner->d, ll, 2, PolyStride{ps, ps, ps}, E.st);
-            acc = s;
+        if (R.giant % (long)E.slots() == 0) {
+            if (!sum_init) { dev::d2d(sum->d, inner->d, 2 * ps * sizeof(u64), E.st); sum_init = true; }
+            else launch_add(E.ks, sum->d, sum->d, inner->d, ll, 2, PolyStride{ps, ps, ps}, E.st);
+            continue;
         }
+        const u64 g = E.galois_for_rotation(-R.giant);
+        EvalKey* key = E.galois_key(g);
+        if (!rbuf) rbuf = E.alloc(2 * ps);
+        E.automorph(rbuf, inner->d, P.level + 1, 2, g);                      // (sigma(c0), sigma(c1))
+        Decomp D = E.decompose(rbuf + ps, P.level);
+        if (!accqp) { accqp = E.alloc((size_t)2 * rows * n); E.ks_inner(D, key, nullptr, accqp, nullptr, false); }
+        else E.ks_inner(D, key, nullptr, accqp, nullptr, true);
+        E.release(D.ext);
+        if (!sum_init) {
+            dev::d2d(sum->d, rbuf, ps * sizeof(u64), E.st);
+            dev::zero(sum->d + ps, ps * sizeof(u64), E.st);
+            sum_init = true;
+        } else launch_add(E.ks, sum->d, sum->d, rbuf, ll, 1, PolyStride{0, 0, 0}, E.st);
     }
-    return A.keep(E.rescale(acc));
+    if (tmp) E.release(tmp);
+    if (rbuf) E.release(rbuf);
+    if (accqp) {
+        u64* down = E.alloc(2 * ps);
+        E.ks_moddown(accqp, P.level, 0, down);
+        launch_add(E.ks, sum->d, sum->d, down, ll, 2, PolyStride{ps, ps, ps}, E.st);
+        E.release(down);
+        E.release(accqp);
+    }
+    return A.keep(E.rescale(sum));
 }
 
 static Ct* cheb_eval(Engine& E, Arena& A, Ct* x, const std::vector<double>& coef, int m) {

@@ -35,6 +35,13 @@ extern "C" {
 const char* ckks_last_error(void) { return g_err.c_str(); }
 const char* ckks_backend(void) { return dev::backend_name(); }
 long ckks_launch_count(void) { return g_launch_count; }
+double ckks_launch_host_ms(void) {
+#ifdef CKKS_TIME_LAUNCHES
+    return g_launch_host_ns * 1e-6;
+#else
+    return -1.0;
+#endif
+}
 
 int ckks_engine_create_default(int logn, int levels, int scale_bits, int q0_bits, int p_bits, int dnum, int hamming,
                                int fresh_level, uint64_t seed, int device, ckks_engine** out) {
@@ -134,6 +141,9 @@ int ckks_encrypt(ckks_engine* e, const double* z, int level, ckks_ct** out) {
     return guard([&] { *out = H(e->E->encrypt(z, level)); });
 }
 int ckks_decrypt(ckks_engine* e, const ckks_ct* ct, double* z) { return guard([&] { e->E->decrypt(C(ct), z); }); }
+int ckks_snap_zeta16(ckks_engine* e, const ckks_ct* ct, int level, int stride, ckks_ct** out) {
+    return guard([&] { *out = H(e->E->snap_zeta16(C(ct), level, stride)); });
+}
 void ckks_ct_free(ckks_engine* e, ckks_ct* ct) { e->E->free_ct(C(ct)); }
 void ckks_pt_free(ckks_engine* e, ckks_pt* pt) { e->E->free_pt(reinterpret_cast<Pt*>(pt)); }
 int ckks_ct_level(const ckks_ct* ct) { return C(ct)->level; }

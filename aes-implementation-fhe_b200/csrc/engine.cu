@@ -10,6 +10,9 @@
 #include <set>
 
 long g_launch_count = 0;
+#ifdef CKKS_TIME_LAUNCHES
+double g_launch_host_ns = 0;
+#endif
 #ifdef CKKS_EMU
 thread_local emu_uint3 blockIdx, threadIdx;
 thread_local dim3 blockDim, gridDim;
@@ -232,6 +235,14 @@ Engine::Engine(const Params& P) : prm(P) {
             for (int i = 0; i < l; i++) inv[i] = invmod_h(mod[l] % mod[i], mod[i]);
             scalar_list(inv, lo, sl_qinv[l]);
         }
+    }
+    {
+        std::vector<double> z16(32);
+        for (int k = 0; k < 16; k++) {
+            z16[2 * k] = cos(-2.0 * M_PI * k / 16.0);
+            z16[2 * k + 1] = sin(-2.0 * M_PI * k / 16.0);
+        }
+        d_zeta16 = upload(this, z16, owned);
     }
     d_rot = upload(this, rot, owned);
     d_ksi = upload(this, ksi, owned);
@@ -635,24 +646,30 @@ EvalKey* Engine::galois_key(u64 g) {
 }
 
 // ------------------------------------------------------------------ encode / encrypt / decrypt (spec S9, S10)
-void Engine::encode_coeffs_dev(i64* out_dev, const double* z_host, double scale) {
+// z_dev: 2n doubles on the device (overwritten as scratch) -> N signed coefficients
+void Engine::encode_coeffs_from_dev(i64* out_dev, double* z_dev, double scale, bool check) {
     const size_t ns = slots();
-    double* z = (double*)dev::alloc(2 * ns * sizeof(double), st);
-    double* w = (double*)dev::alloc(2 * ns * sizeof(double), st);
-    dev::h2d(z, z_host, 2 * ns * sizeof(double), st);
-    launch_special_ifft(ks, w, z, d_rot, d_ksi, st);
+    double* w = (double*)alloc(2 * ns);
+    launch_special_ifft(ks, w, z_dev, d_rot, d_ksi, st);
     launch_round_coeffs(ks, out_dev, w, scale, d_flag, st);
+    release(w);
+    if (!check) return;
     int flag = 0;
     dev::d2h(&flag, d_flag, sizeof(int), st);
     dev::sync(st);
-    dev::free(z, st);
-    dev::free(w, st);
     if (flag) {
         int zero = 0;
         dev::h2d(d_flag, &zero, sizeof(int), st);
         dev::sync(st);
         throw std::runtime_error("plaintext coefficient does not fit 62 bits");
     }
+}
+void Engine::encode_coeffs_dev(i64* out_dev, const double* z_host, double scale) {
+    const size_t ns = slots();
+    double* z = (double*)alloc(2 * ns);
+    dev::h2d(z, z_host, 2 * ns * sizeof(double), st);
+    try { encode_coeffs_from_dev(out_dev, z, scale, true); } catch (...) { release(z); throw; }
+    release(z);
 }
 
 Pt* Engine::encode(const double* z, int level) {
@@ -674,12 +691,19 @@ Ct* Engine::encrypt(const double* z, int level) {
     if (!has_pk) throw std::runtime_error("encrypt needs a public key");
     if (level < 0) level = prm.fresh_level;
     if (level > L()) throw std::runtime_error("encrypt: bad level");
+    i64* coef = (i64*)alloc(N());
+    try { encode_coeffs_dev(coef, z, scales[level]); } catch (...) { release(coef); throw; }
+    Ct* c = encrypt_coeffs(coef, level);
+    release(coef);
+    return c;
+}
+
+// public-key encryption of N signed message coefficients already on the device (spec S8, S10)
+Ct* Engine::encrypt_coeffs(const i64* coef, int level) {
     const size_t n = N();
     const int nl = level + 1, nq = L() + 1;
     std::vector<int> idx = mods_q(level);
     LimbList ll = limb_list(idx);
-    i64* coef = (i64*)dev::alloc(n * sizeof(i64), st);
-    encode_coeffs_dev(coef, z, scales[level]);
     const u64 k = enc_counter++;
     // t[0] = v, t[1] = e0 + m, t[2] = e1  (coefficient domain), one batched NTT for all three
     u64* t = alloc((size_t)3 * nl * n);
@@ -698,11 +722,11 @@ Ct* Engine::encrypt(const double* z, int level) {
     launch_add(ks, c->d, c->d, t + ps, ll, 2, PolyStride{ps, ps, ps}, st);
     release(t);
     release(m);
-    dev::free(coef, st);
     return c;
 }
 
-void Engine::decrypt(const Ct* c, double* z_out) {
+// secret-key decryption to slot values left ON THE DEVICE (2n doubles, caller releases)
+double* Engine::decrypt_to_dev(const Ct* c) {
     if (!has_sk) throw std::runtime_error("decrypt needs a secret key");
     const size_t n = N(), ns = slots();
     const size_t ps = (size_t)(c->level + 1) * n;
@@ -720,14 +744,36 @@ void Engine::decrypt(const Ct* c, double* z_out) {
         if (k + 1 < c->npoly) launch_mul(ks, sp, sp, sk_ntt, ll, 1, z0, st);
     }
     ntt_rows(t, idx, idx, true);
-    double* w = (double*)dev::alloc(2 * ns * sizeof(double), st);
-    double* zz = (double*)dev::alloc(2 * ns * sizeof(double), st);
+    double* w = (double*)alloc(2 * ns);
+    double* zz = (double*)alloc(2 * ns);
     launch_center_to_w(ks, w, t, 0, scales[c->level], st);
     launch_special_fft(ks, zz, w, d_rot, d_ksi, st);
-    dev::d2h(z_out, zz, 2 * ns * sizeof(double), st);
-    dev::sync(st);
     release(t); release(sp); release(tmp);
-    dev::free(w, st); dev::free(zz, st);
+    release(w);
+    return zz;
+}
+
+// hard renorm without leaving the device (reference pipeline.py:65-69 does decrypt -> host snap -> encrypt):
+// decrypt, snap every slot to the nearest zeta_16 codeword, re-encrypt at `level`
+Ct* Engine::snap_zeta16(const Ct* a, int level, int stride) {
+    if (!has_pk) throw std::runtime_error("renorm needs a public key");
+    if (level < 0) level = prm.fresh_level;
+    if (level > L()) throw std::runtime_error("renorm: bad level");
+    double* zz = decrypt_to_dev(a);
+    launch_snap_zeta16(ks, zz, d_zeta16, stride < 1 ? 1 : stride, st);
+    i64* coef = (i64*)alloc(N());
+    encode_coeffs_from_dev(coef, zz, scales[level], false);       // unit-modulus slots cannot overflow
+    Ct* c = encrypt_coeffs(coef, level);
+    release(coef);
+    release(zz);
+    return c;
+}
+
+void Engine::decrypt(const Ct* c, double* z_out) {
+    double* zz = decrypt_to_dev(c);
+    dev::d2h(z_out, zz, 2 * slots() * sizeof(double), st);
+    dev::sync(st);
+    release(zz);
 }
 
 // ------------------------------------------------------------------ basis conversion tables (spec S5)
@@ -890,17 +936,23 @@ Decomp Engine::decompose(const u64* d, int level) {
     return D;
 }
 
-// inner product with the key, then ONE division by P * q_{level-drop+1..level}: out is [2][level+1-drop][N].
-// addend ([2][level+1][N], e.g. the (d0, d1) of a tensor product) is folded in as P * addend before the division.
-void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out, const u64* addend, int drop) {
-    const size_t n = N();
-    const int level = D.level, nq = level + 1, rows = nq + K(), nout = nq - drop;
-    if (nout < 1) throw LevelError("key switch: ciphertext level should be positive for this rescale");
+// <digits, evk> (+ P * addend) into acc = [2][level+1+K][N] over Q_level u P; with accumulate the result is added to
+// what acc already holds (several key switches sharing ONE ModDown)
+void Engine::ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64* acc, const u64* addend, bool accumulate) {
+    const int level = D.level, nq = level + 1;
     std::vector<int> qp = mods_qp(level);
     LimbList ll = limb_list(qp);
     LimbList er = limb_list(qp);                 // evk rows are indexed by global modulus index
-    u64* acc = alloc((size_t)2 * rows * n);
-    launch_ks_inner(ks, acc, D.ext, D.own, evk->d, perm, ll, er, D.beta, nmod(), nq, prm.alpha, addend, sl_pmodq, st);
+    launch_ks_inner(ks, acc, D.ext, D.own, evk->d, perm, ll, er, D.beta, nmod(), nq, prm.alpha, addend, sl_pmodq,
+                    accumulate ? 1 : 0, st);
+    n_keyswitch++;
+}
+
+// ONE division of acc by P * q_{level-drop+1..level}: out is [2][level+1-drop][N] (acc is used as scratch)
+void Engine::ks_moddown(u64* acc, int level, int drop, u64* out) {
+    const size_t n = N();
+    const int nq = level + 1, rows = nq + K(), nout = nq - drop;
+    if (nout < 1) throw LevelError("key switch: ciphertext level should be positive for this rescale");
     // coefficient form of the limbs that are divided out
     std::vector<int> prow, pmod;
     for (int i = level - drop + 1; i <= level; i++) { prow.push_back(i); pmod.push_back(i); }
@@ -913,10 +965,18 @@ void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64*
     ntt_rows(conv, qi, qi, false, 2, (size_t)nout * n);
     launch_sub_mul_scalar(ks, out, acc, conv, limb_list(qi), moddown_inv(level, drop), 2,
                           PolyStride{(size_t)nout * n, (size_t)rows * n, (size_t)nout * n}, st);
-    release(acc);
     release(conv);
-    n_keyswitch++;
     if (drop) n_rescale++;
+}
+
+// inner product with the key, then ONE division by P * q_{level-drop+1..level}: out is [2][level+1-drop][N].
+// addend ([2][level+1][N], e.g. the (d0, d1) of a tensor product) is folded in as P * addend before the division.
+void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out, const u64* addend, int drop) {
+    const int rows = D.level + 1 + K();
+    u64* acc = alloc((size_t)2 * rows * N());
+    ks_inner(D, evk, perm, acc, addend, false);
+    ks_moddown(acc, D.level, drop, out);
+    release(acc);
 }
 
 void Engine::key_switch(const u64* d, int level, const EvalKey* evk, u64* out) {

@@ -143,6 +143,9 @@ class Engine {
     Pt* encode(const double* z, int level);
     Ct* encrypt(const double* z, int level);
     void decrypt(const Ct* c, double* z_out);
+    double* decrypt_to_dev(const Ct* c);
+    Ct* encrypt_coeffs(const i64* coef_dev, int level);
+    Ct* snap_zeta16(const Ct* a, int level, int stride);   // decrypt, snap to zeta_16 codewords, re-encrypt: all on device
 
     // ---- homomorphic ops (all out of place)
     Ct* add(Ct* a, Ct* b);
@@ -189,6 +192,8 @@ class Engine {
     void ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out /* [2][level+1-drop][N] */,
                   const u64* addend = nullptr, int drop = 0);
     void key_switch(const u64* d, int level, const EvalKey* evk, u64* out);
+    void ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64* acc, const u64* addend, bool accumulate);
+    void ks_moddown(u64* acc, int level, int drop, u64* out);
     void automorph(u64* out, const u64* in, int rows, int npoly, u64 g);
     const u32* galois_perm(u64 g);
     std::vector<int> mods_q(int level) const;
@@ -231,6 +236,7 @@ class Engine {
     std::vector<void*> owned;              // device tables freed in the destructor
     u32* d_rot = nullptr;
     double* d_ksi = nullptr;
+    double* d_zeta16 = nullptr;
     int* d_flag = nullptr;
     u64 enc_counter = 0;
     bool prof_on = false;
@@ -247,6 +253,7 @@ class Engine {
     BaseConvTable make_bc_table(const std::vector<int>& src, const std::vector<int>& srow,
                                 const std::vector<int>& tgt, const std::vector<int>& orow);
     void encode_coeffs_dev(i64* out_dev, const double* z_host, double scale);
+    void encode_coeffs_from_dev(i64* out_dev, double* z_dev, double scale, bool check);
     void rescale_into(u64* out, const u64* in, int npoly, int level);
     void need_levels(int level, int need, const char* what) const;
 };

@@ -122,7 +122,7 @@ __global__ void k_permute(KShape S, u64* __restrict__ out, const u64* __restrict
 __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restrict__ ext, const u64* __restrict__ own,
                            const u64* __restrict__ evk, const u32* __restrict__ perm, const GRID_CONST LimbList L,
                            const GRID_CONST LimbList ERow, int beta, int rows, int evk_rows, int nq, int alpha,
-                           const u64* __restrict__ addend, const GRID_CONST ScalarList PmodQ) {
+                           const u64* __restrict__ addend, const GRID_CONST ScalarList PmodQ, int accumulate) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
     const size_t er = ERow.idx[row];
@@ -146,6 +146,10 @@ __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restric
         if (addend != nullptr && row < nq) {
             r0 = add_mod(r0, shoup_mul(addend[(size_t)row * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
             r1 = add_mod(r1, shoup_mul(addend[((size_t)nq + row) * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+        }
+        if (accumulate) {          // several key switches summed before ONE ModDown (giant steps of a linear transform)
+            r0 = add_mod(r0, acc[(size_t)row * N + k], m.q);
+            r1 = add_mod(r1, acc[((size_t)rows + row) * N + k], m.q);
         }
         acc[(size_t)row * N + k] = r0;
         acc[((size_t)rows + row) * N + k] = r1;
@@ -346,6 +350,23 @@ __global__ void k_center_to_w(KShape S, double* __restrict__ w, const u64* __res
     }
 }
 
+// hard renorm on the device: every slot is replaced by the nearest zeta_16 codeword exp(-2 pi i k / 16) (angle only,
+// reference utils.py:15-19); with stride > 1 only slots j = 0 mod stride carry data and the others are set to 1.0
+// (reference state_encoder.py:23-27)
+__global__ void k_snap_zeta16(KShape S, double* __restrict__ z, const double* __restrict__ table, int stride) {
+    FOR_THREADS {
+        const u32 j = blockIdx.x * TPB + threadIdx.x;
+        if (stride > 1 && (j % (u32)stride) != 0) { z[2 * j] = 1.0; z[2 * j + 1] = 0.0; }
+        else {
+            const double ang = atan2(z[2 * j + 1], z[2 * j]);
+            int k = (int)rint(-ang * (16.0 / (2.0 * 3.14159265358979323846)));
+            k = ((k % 16) + 16) % 16;
+            z[2 * j] = table[2 * k];
+            z[2 * j + 1] = table[2 * k + 1];
+        }
+    }
+}
+
 inline dim3 grid3(KShape S, int rows, int npoly = 1) { return dim3((1u << S.logn) / TPB, rows, npoly); }
 
 }  // namespace
@@ -391,10 +412,10 @@ void launch_permute(KShape S, u64* out, const u64* a, const u32* perm, int rows,
 }
 void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u64* evk, const u32* perm,
                      const LimbList& L, const LimbList& ERow, int beta, int evk_rows, int nq, int alpha,
-                     const u64* addend, const ScalarList& PmodQ, dev_stream st) {
+                     const u64* addend, const ScalarList& PmodQ, int accumulate, dev_stream st) {
     if (L.n)
         LAUNCH(k_ks_inner, grid3(S, L.n), dim3(TPB), st, S, acc, ext, own, evk, perm, L, ERow, beta, L.n, evk_rows, nq,
-               alpha, addend, PmodQ);
+               alpha, addend, PmodQ, accumulate);
 }
 void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns,
                          int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st) {
@@ -438,6 +459,9 @@ void launch_special_ifft(KShape S, double* out, double* z, const u32* rot, const
     for (int len = n; len >= 2; len >>= 1)
         LAUNCH(k_fft_stage, dim3(n / 2 / TPB), dim3(TPB), st, S, z, rot, ksi, len, 1);
     LAUNCH(k_bitrev_copy, dim3(n / TPB), dim3(TPB), st, S, out, z, 1.0 / (double)n);
+}
+void launch_snap_zeta16(KShape S, double* z, const double* table, int stride, dev_stream st) {
+    LAUNCH(k_snap_zeta16, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, z, table, stride);
 }
 void launch_round_coeffs(KShape S, i64* out, const double* w, double scale, int* flag, dev_stream st) {
     LAUNCH(k_round_coeffs, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, out, w, scale, flag);

@@ -34,7 +34,18 @@ extern long g_launch_count;   // kernels launched by this library (bench.py repo
 
 #define FOR_THREADS
 #define BLOCK_SYNC __syncthreads()
+#ifdef CKKS_TIME_LAUNCHES
+#include <time.h>
+extern double g_launch_host_ns;
+struct LaunchTimer {
+    timespec t0;
+    LaunchTimer() { clock_gettime(CLOCK_MONOTONIC, &t0); }
+    ~LaunchTimer() { timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1); g_launch_host_ns += (t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec); }
+};
+#define LAUNCH(kern, grid, block, stream, ...) do { LaunchTimer _lt; ++g_launch_count; kern<<<grid, block, 0, stream>>>(__VA_ARGS__); } while (0)
+#else
 #define LAUNCH(kern, grid, block, stream, ...) (++g_launch_count, kern<<<grid, block, 0, stream>>>(__VA_ARGS__))
+#endif
 #define CKKS_SHARED __shared__
 #define GRID_CONST __grid_constant__
 

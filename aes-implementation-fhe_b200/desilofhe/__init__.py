@@ -391,6 +391,10 @@ class Engine:
         c = np.asarray([complex(t[2]) for t in terms], dtype=np.complex128)
         return self._new(self._lib.ckks_lut2, A, B, nb, p, q, c.view(np.float64), len(terms))
 
+    def snap_zeta16(self, ct: Ciphertext, level: int = -1, stride: int = 1) -> Ciphertext:
+        """Hard renorm on the device: decrypt, snap each slot to the nearest zeta_16 codeword, re-encrypt at `level`."""
+        return self._new(self._lib.ckks_snap_zeta16, ct._h, int(level), int(stride))
+
     def lincomb(self, cts: Sequence[Ciphertext], coeffs) -> Ciphertext:
         """sum_k coeffs[k] * cts[k]: one fused multiply-accumulate + one rescale per distinct input level."""
         n = len(cts)

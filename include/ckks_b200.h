@@ -81,6 +81,10 @@ int ckks_set_bootstrap_params(ckks_engine* e, int K, int cheb_degree, int double
 int ckks_encode(ckks_engine* e, const double* slots_re_im, int level, ckks_pt** out);
 int ckks_encrypt(ckks_engine* e, const double* slots_re_im, int level /* <0: fresh level */, ckks_ct** out);
 int ckks_decrypt(ckks_engine* e, const ckks_ct* ct, double* slots_re_im_out);
+/* The reference's hard renorm (pipeline.py:65-69: decrypt, snap every nibble to its zeta_16 codeword, re-encrypt) done
+ * without leaving the device: no D2H/H2D of the 512 KiB slot vector.  stride > 1 reproduces StateEncoder's layout
+ * (data on slots 0 mod stride, 1.0 elsewhere, state_encoder.py:23-27); level < 0 means the fresh level. */
+int ckks_snap_zeta16(ckks_engine* e, const ckks_ct* ct, int level, int stride, ckks_ct** out);
 void ckks_ct_free(ckks_engine* e, ckks_ct* ct);
 void ckks_pt_free(ckks_engine* e, ckks_pt* pt);
 int ckks_ct_level(const ckks_ct* ct);

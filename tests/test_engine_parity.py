@@ -241,3 +241,26 @@ def test_fused_lincomb_bit_exact(pair):
     assert np.array_equal(pair.export(got), want.c)
     assert got.level == pb[-1].level - 1
     assert np.abs(eng.decrypt(got) - sum(coef[k] * z ** (k + 1) for k in range(5))).max() < 1e-6
+
+
+def test_device_renorm_equals_host_renorm(pair):
+    """ckks_snap_zeta16 (decrypt, snap, re-encrypt on the device) == the reference's host renorm (pipeline.py:65-69)."""
+    rng = np.random.default_rng(12)
+    eng = pair.eng
+    k = rng.integers(0, 16, pair.n)
+    z = np.exp(-2j * np.pi * k / 16) * (1 + 0.05 * rng.normal(size=pair.n)) * np.exp(1j * 0.08 * rng.normal(size=pair.n))
+    c = eng.encrypt(z)
+    pair.orc.encrypt(z)
+    out = eng.snap_zeta16(c, level=3)
+    pair.orc._enc_counter += 1
+    assert out.level == 3
+    got = eng.decrypt(out)
+    want = np.exp(-2j * np.pi * (np.rint(-np.angle(z) * 16 / (2 * np.pi)) % 16) / 16)
+    assert np.abs(got - want).max() < 1e-8
+    stride = pair.n // 16
+    out2 = eng.snap_zeta16(c, level=-1, stride=stride)
+    pair.orc._enc_counter += 1
+    got2 = eng.decrypt(out2)
+    want2 = np.ones(pair.n, dtype=np.complex128)
+    want2[::stride] = want[::stride]
+    assert np.abs(got2 - want2).max() < 1e-8
