@@ -137,6 +137,12 @@ class EngineContext:
             return self.engine.pair_map(fn, first, second)
         return fn(*first), fn(*second)
 
+    def lane_map(self, fn, arg_tuples):
+        """[fn(*a) for a in arg_tuples], each call on its own stream lane when the backend has lanes."""
+        if self.fused and hasattr(self.engine, "lane_map"):
+            return self.engine.lane_map(fn, arg_tuples)
+        return [fn(*a) for a in arg_tuples]
+
     def lut2(self, basis_a, basis_b, terms):
         return self.engine.lut2(basis_a, basis_b, terms)
 

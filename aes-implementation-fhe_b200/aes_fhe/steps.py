@@ -111,6 +111,10 @@ class XOR4LUT:
                 pos = eng.make_power_basis(ct, 8)
         basis = {0: eng.add_plain(eng.sub(ct, ct), 1.0)}   # "encrypted 1" without spending a level
         basis.update({k: pos[k - 1] for k in range(1, 9)})
+        if getattr(eng, "fused", False):                     # the seven conjugations are independent
+            conj = eng.lane_map(eng.conjugate, [(pos[15 - k],) for k in range(9, 16)])
+            basis.update({k: conj[k - 9] for k in range(9, 16)})
+            return basis
         for k in range(9, 16):
             basis[k] = eng.conjugate(pos[15 - k])
         return basis
@@ -121,8 +125,10 @@ class XOR4LUT:
             # build both power bases at the common level (a cached round-key ciphertext may sit far above the state)
             lvl = min(a_ct.level, b_ct.level)
             a_ct, b_ct = eng.level_down(a_ct, lvl), eng.level_down(b_ct, lvl)
-        A = self._build_power_basis_16(a_ct)
-        B = self._build_power_basis_16(b_ct)
+            A, B = eng.pair_map(self._build_power_basis_16, (a_ct,), (b_ct,))     # independent: two stream lanes
+        else:
+            A = self._build_power_basis_16(a_ct)
+            B = self._build_power_basis_16(b_ct)
         if getattr(eng, "fused", False):
             # same polynomial, one tensor accumulation and ONE relinearisation (csrc/lut.cu) instead of 64
             return eng.lut2([A.get(k) for k in range(16)], [B.get(k) for k in range(16)], self.terms)
@@ -287,6 +293,10 @@ class _MixBase:
             pos = eng.make_power_basis(ct, 8)
         basis = {0: eng.add_plain(eng.multiply(ct, 0.0), 1.0)}
         basis.update({k: pos[k - 1] for k in range(1, 9)})
+        if getattr(eng, "fused", False):
+            conj = eng.lane_map(eng.conjugate, [(pos[15 - k],) for k in range(9, 16)])
+            basis.update({k: conj[k - 9] for k in range(9, 16)})
+            return basis
         for k in range(9, 16):
             basis[k] = eng.conjugate(pos[15 - k])
         return basis

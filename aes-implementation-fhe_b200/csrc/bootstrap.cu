@@ -400,8 +400,15 @@ Ct* Engine::bootstrap(Ct* a) {
     Ct* cj = A.keep(conjugate(t));
     Ct* re = A.keep(add(t, cj));
     Ct* im = A.keep(mul_i(A.keep(sub(t, cj)), -1));
-    re = eval_mod(*this, A, re, B);
-    im = eval_mod(*this, A, im, B);
+    // the two halves are independent: evaluate them on two stream lanes
+    fork(2);
+    try {
+        set_lane(0);
+        re = eval_mod(*this, A, re, B);
+        set_lane(1);
+        im = eval_mod(*this, A, im, B);
+    } catch (...) { join(); throw; }
+    join();
     t = A.keep(add(re, A.keep(mul_i(im, +1))));
     if (t->level < B.stc[0].level) throw std::runtime_error("bootstrap: level accounting is off");
     if (t->level > B.stc[0].level) t = level_down(t, B.stc[0].level);     // memoised on (and owned by) its parent

@@ -73,7 +73,7 @@ void ckks_engine_destroy(ckks_engine* e) {
     delete e->E;
     delete e;
 }
-int ckks_fork(ckks_engine* e) { return guard([&] { e->E->fork(); }); }
+int ckks_fork(ckks_engine* e, int lanes) { return guard([&] { e->E->fork(lanes); }); }
 int ckks_set_lane(ckks_engine* e, int lane) { return guard([&] { e->E->set_lane(lane); }); }
 int ckks_join(ckks_engine* e) { return guard([&] { e->E->join(); }); }
 int ckks_sync(ckks_engine* e) { return guard([&] { e->E->sync(); }); }
@@ -216,7 +216,8 @@ int ckks_counters(const ckks_engine* e, long* o) {
 int ckks_arena_stats(const ckks_engine* e, long* driver_allocs, size_t* arena_bytes, size_t* cached_bytes) {
     *driver_allocs = e->E->n_driver_allocs;
     *arena_bytes = e->E->driver_bytes;
-    *cached_bytes = e->E->pools[0].cached + e->E->pools[1].cached + e->E->pools[2].cached;
+    *cached_bytes = 0;
+    for (int i = 0; i < Engine::kMaxLanes; i++) *cached_bytes += e->E->pools[i].cached;
     return CKKS_OK;
 }
 

@@ -150,9 +150,8 @@ Engine::Engine(const Params& P) : prm(P) {
     if (prm.q.empty() || prm.p.empty()) throw std::runtime_error("engine: empty modulus chain");
     dev::set_device(prm.device);
     dev::pool_setup(prm.device);
-    st = st_main = dev::stream_create();
-    st_lane[0] = dev::stream_create();
-    st_lane[1] = dev::stream_create();
+    st = streams[0] = dev::stream_create();
+    lane_made[0] = lane_busy[0] = true;
     mod = prm.q;
     mod.insert(mod.end(), prm.p.begin(), prm.p.end());
     if ((int)mod.size() > CKKS_MAX_MODULI) throw std::runtime_error("engine: too many moduli");
@@ -251,7 +250,7 @@ Engine::Engine(const Params& P) : prm(P) {
 }
 
 Engine::~Engine() {
-    try { if (in_fork) join(); sync(); } catch (...) {}
+    try { while (in_fork()) join(); sync(); } catch (...) {}
     bootstrap_teardown();
     for (auto& kv : gkeys) dev::free(kv.second.d, st);
     for (auto& kv : perms) dev::free(kv.second, st);
@@ -267,66 +266,75 @@ Engine::~Engine() {
     for (void* p : owned) dev::free(p, st);
     try { trim_pools(); } catch (...) {}
     try { sync(); } catch (...) {}
-    dev::stream_destroy(st_main);
-    dev::stream_destroy(st_lane[0]);
-    dev::stream_destroy(st_lane[1]);
+    for (int i = 0; i < kMaxLanes; i++)
+        if (lane_made[i]) dev::stream_destroy(streams[i]);
 }
 
 // ------------------------------------------------------------------ lanes
 void Engine::sync() {
-    dev::sync(st_main);
-    dev::sync(st_lane[0]);
-    dev::sync(st_lane[1]);
+    for (int i = 0; i < kMaxLanes; i++)
+        if (lane_made[i]) dev::sync(streams[i]);
 }
-void Engine::fork() {
-    if (in_fork) throw std::runtime_error("fork: already forked");
-    dev::stream_wait(st_lane[0], st_main);
-    dev::stream_wait(st_lane[1], st_main);
-    in_fork = true;
-    fork_epoch++;
-    // both lanes are ordered after the main stream now, so the main stream's cached buffers are safe for either lane:
-    // deal them out alternately (they come back at the join), otherwise the lanes would keep drawing fresh memory
-    bool flip = false;
-    for (auto& kv : pools[0].free) {
+void Engine::fork(int k) {
+    if (k < 1) throw std::runtime_error("fork: need at least one lane");
+    Frame F;
+    F.parent = cur_lane;
+    F.epoch = ++epoch_counter;
+    for (int i = 1; i < kMaxLanes && (int)F.lanes.size() < k; i++) {
+        if (lane_busy[i]) continue;
+        if (!lane_made[i]) { streams[i] = dev::stream_create(); lane_made[i] = true; }
+        lane_busy[i] = true;
+        F.lanes.push_back(i);
+    }
+    if ((int)F.lanes.size() < k) {
+        for (int l : F.lanes) lane_busy[l] = false;
+        throw std::runtime_error("fork: out of stream lanes");
+    }
+    for (int l : F.lanes) dev::stream_wait(streams[l], streams[F.parent]);
+    // every lane is ordered after the parent stream now, so the parent's cached buffers are safe for any of them:
+    // deal them out round-robin (they come back at the join), otherwise the lanes would keep drawing fresh memory
+    size_t turn = 0;
+    LanePool& PP = pools[F.parent];
+    for (auto& kv : PP.free) {
         for (void* p : kv.second) {
-            LanePool& P = pools[flip ? 2 : 1];
+            LanePool& P = pools[F.lanes[turn++ % F.lanes.size()]];
             P.free[kv.first].push_back(p);
             P.cached += kv.first;
-            flip = !flip;
         }
         kv.second.clear();
     }
-    pools[0].cached = 0;
+    PP.cached = 0;
+    frames.push_back(std::move(F));
+    set_lane(0);
 }
-void Engine::set_lane(int lane) {
-    if (!in_fork) throw std::runtime_error("set_lane outside fork/join");
-    if (lane < 0 || lane > 1) throw std::runtime_error("set_lane: lane must be 0 or 1");
-    cur_lane = lane;
-    st = st_lane[lane];
+void Engine::set_lane(int i) {
+    if (frames.empty()) throw std::runtime_error("set_lane outside fork/join");
+    Frame& F = frames.back();
+    if (i < 0 || i >= (int)F.lanes.size()) throw std::runtime_error("set_lane: no such lane in this fork");
+    cur_lane = F.lanes[i];
+    st = streams[cur_lane];
 }
 void Engine::join() {
-    if (!in_fork) return;
-    dev::stream_wait(st_main, st_lane[0]);
-    dev::stream_wait(st_main, st_lane[1]);
-    st = st_main;
-    cur_lane = -1;
-    in_fork = false;
-    // the main stream is ordered after both lanes: their cached buffers return to the main pool
-    for (int l = 1; l <= 2; l++) {
+    if (frames.empty()) return;
+    Frame F = std::move(frames.back());
+    frames.pop_back();
+    // the parent is ordered after every lane: their cached buffers return to the parent's pool
+    LanePool& PP = pools[F.parent];
+    for (int l : F.lanes) {
+        dev::stream_wait(streams[F.parent], streams[l]);
         for (auto& kv : pools[l].free) {
-            std::vector<void*>& dst = pools[0].free[kv.first];
+            std::vector<void*>& dst = PP.free[kv.first];
             dst.insert(dst.end(), kv.second.begin(), kv.second.end());
-            pools[0].cached += kv.first * kv.second.size();
+            PP.cached += kv.first * kv.second.size();
             kv.second.clear();
         }
         pools[l].cached = 0;
+        lane_busy[l] = false;
     }
-    std::vector<Ct*> d;
-    d.swap(deferred_free);
-    for (Ct* c : d) free_ct(c);
-    std::vector<Pt*> dp;
-    dp.swap(deferred_free_pt);
-    for (Pt* p : dp) free_pt(p);
+    cur_lane = F.parent;
+    st = streams[cur_lane];
+    for (Ct* c : F.dct) free_ct(c);        // re-examined in the enclosing frame (may be deferred again)
+    for (Pt* p : F.dpt) free_pt(p);
 }
 
 // ------------------------------------------------------------------ memory
@@ -344,7 +352,7 @@ static size_t size_class_limbs(size_t limbs) {
 u64* Engine::alloc(size_t words) {
     const size_t limbs = (words + N() - 1) / N();
     const size_t bytes = size_class_limbs(limbs ? limbs : 1) * N() * sizeof(u64);
-    LanePool& P = pools[cur_lane + 1];
+    LanePool& P = pools[cur_lane];
     auto it = P.free.find(bytes);
     if (it != P.free.end() && !it->second.empty()) {
         void* p = it->second.back();
@@ -362,7 +370,7 @@ void Engine::release(void* p) {
     if (!p) return;
     auto it = alloc_bytes.find(p);
     if (it == alloc_bytes.end()) { dev::free(p, st); return; }
-    LanePool& P = pools[cur_lane + 1];
+    LanePool& P = pools[cur_lane];
     P.free[it->second].push_back(p);
     P.cached += it->second;
     if (P.cached > ((size_t)48 << 30)) trim_pools();
@@ -372,7 +380,7 @@ void Engine::trim_pools() {
     sync();
     for (LanePool& P : pools) {
         for (auto& kv : P.free)
-            for (void* p : kv.second) { alloc_bytes.erase(p); dev::free(p, st_main); driver_bytes -= kv.first; }
+            for (void* p : kv.second) { alloc_bytes.erase(p); dev::free(p, streams[0]); driver_bytes -= kv.first; }
         P.free.clear();
         P.cached = 0;
     }
@@ -382,14 +390,14 @@ Ct* Engine::new_ct(int npoly, int level) {
     c->npoly = npoly;
     c->level = level;
     c->lane = cur_lane;
-    c->epoch = fork_epoch;
+    c->epoch = cur_epoch();
     c->d = alloc((size_t)npoly * (level + 1) * N());
     return c;
 }
 void Engine::free_ct(Ct* c) {
     if (!c) return;
-    if (in_fork && !(c->lane == cur_lane && c->epoch == fork_epoch)) {
-        deferred_free.push_back(c);                // another lane may still be reading it: released at the join
+    if (in_fork() && !(c->lane == cur_lane && c->epoch == cur_epoch())) {
+        frames.back().dct.push_back(c);            // another lane may still be reading it: released at the join
         return;
     }
     for (auto& kv : c->lowered) free_ct(kv.second);
@@ -398,7 +406,7 @@ void Engine::free_ct(Ct* c) {
 }
 void Engine::free_pt(Pt* p) {
     if (!p) return;
-    if (in_fork) { deferred_free_pt.push_back(p); return; }
+    if (in_fork()) { frames.back().dpt.push_back(p); return; }
     release(p->d);
     delete p;
 }
@@ -1045,7 +1053,7 @@ Ct* Engine::level_down(Ct* c, int target) {
     for (auto& kv : c->lowered)
         if (kv.first == target) {
             // a copy memoised by the other lane has not necessarily been computed yet on the device
-            if (in_fork && kv.second->lane >= 0 && kv.second->lane != cur_lane) dev::sync(st_lane[kv.second->lane]);
+            if (in_fork() && kv.second->lane != cur_lane && lane_made[kv.second->lane]) dev::sync(streams[kv.second->lane]);
             return kv.second;
         }
     const size_t n = N();
@@ -1272,12 +1280,25 @@ std::vector<Ct*> Engine::power_basis(Ct* a, int degree) {
     int depth = 0;
     while ((1 << depth) < degree) depth++;
     need_levels(a->level, depth, "make_power_basis");
-    std::vector<Ct*> out;
-    out.push_back(copy(a));
+    std::vector<Ct*> out(degree, nullptr);
+    out[0] = copy(a);
+    bool forked = false;
     try {
-        for (int k = 2; k <= degree; k++) out.push_back(mul(out[k / 2 - 1], out[(k + 1) / 2 - 1]));
+        // generation g holds the powers 2^(g-1) < k <= 2^g; they only need powers of earlier generations, so the
+        // products of one generation are independent: up to 8 of them run on separate stream lanes
+        for (int lo = 1; lo < degree; lo *= 2) {
+            const int hi = std::min(2 * lo, degree), cnt = hi - lo;
+            const int lanes = std::min(cnt, 8);
+            if (lanes > 1) { fork(lanes); forked = true; }
+            for (int k = lo + 1; k <= hi; k++) {
+                if (lanes > 1) set_lane((k - lo - 1) % lanes);
+                out[k - 1] = mul(out[k / 2 - 1], out[(k + 1) / 2 - 1]);
+            }
+            if (lanes > 1) { join(); forked = false; }
+        }
     } catch (...) {
-        for (Ct* c : out) free_ct(c);
+        if (forked) join();
+        for (Ct* c : out) if (c) free_ct(c);
         throw;
     }
     return out;

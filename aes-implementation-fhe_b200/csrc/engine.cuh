@@ -35,7 +35,7 @@ struct Ct {
     int npoly = 2;
     int level = 0;
     u64* d = nullptr;                               // [npoly][level+1][N], NTT domain
-    int lane = -1;                                  // stream lane that produced it (-1: the main stream)
+    int lane = 0;                                   // stream lane that produced it (0: the main stream)
     long epoch = 0;                                 // fork region it was produced in
     std::vector<std::pair<int, Ct*>> lowered;       // memoised level_down() results (owned)
 };
@@ -105,23 +105,35 @@ class Engine {
     void free_pt(Pt* p);
     void sync();
 
-    // ---- lanes: two extra streams for the independent halves of a ciphertext pair (hi / lo nibble).  fork() orders both
-    // lanes after the main stream, set_lane() makes every following call enqueue on that lane, join() orders the main
-    // stream after both.  Ciphertexts freed while another lane is current are released at the join.
-    void fork();
-    void set_lane(int lane);
+    // ---- lanes: independent pieces of work (the hi / lo nibble planes, the two power bases of an XOR4, the products of
+    // one generation of a power basis) are enqueued on separate CUDA streams so the device overlaps their small kernels.
+    // fork(k) takes k helper streams ordered after the current one, set_lane(i) routes the following calls to lane i,
+    // join() orders the parent after all lanes.  Forks nest.  A ciphertext released while another lane may still read it
+    // is held until the join of the frame.
+    static const int kMaxLanes = 40;
+    struct LanePool { std::map<size_t, std::vector<void*>> free; size_t cached = 0; };
+    struct Frame {
+        int parent = 0;
+        long epoch = 0;
+        std::vector<int> lanes;
+        std::vector<Ct*> dct;
+        std::vector<Pt*> dpt;
+    };
+    void fork(int k = 2);
+    void set_lane(int i);
     void join();
-    dev_stream st_main = 0, st_lane[2] = {0, 0};
-    int cur_lane = -1;
-    bool in_fork = false;
-    long fork_epoch = 0;
-    std::vector<Ct*> deferred_free;
-    std::vector<Pt*> deferred_free_pt;
+    bool in_fork() const { return !frames.empty(); }
+    dev_stream streams[kMaxLanes] = {};
+    bool lane_made[kMaxLanes] = {};
+    bool lane_busy[kMaxLanes] = {};
+    int cur_lane = 0;                      // 0 = the main stream
+    long epoch_counter = 0;
+    std::vector<Frame> frames;
+    long cur_epoch() const { return frames.empty() ? 0 : frames.back().epoch; }
     // stream-ordered caching arena: a released buffer goes to the free list of the lane it is released on and is handed
     // out again to later work on the SAME stream (stream order makes that safe), so the hot path makes no
-    // cudaMallocAsync / cudaFreeAsync calls at all
-    struct LanePool { std::map<size_t, std::vector<void*>> free; size_t cached = 0; };
-    LanePool pools[3];
+    // cudaMallocAsync / cudaFreeAsync calls at all; fork deals the parent's cached buffers to the lanes, join returns them
+    LanePool pools[kMaxLanes];
     std::map<void*, size_t> alloc_bytes;
     void trim_pools();
     long n_driver_allocs = 0;

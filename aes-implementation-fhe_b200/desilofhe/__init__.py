@@ -196,17 +196,25 @@ class Engine:
     def sync(self):
         _capi.check(self._lib.ckks_sync(self._ptr))
 
-    def pair_map(self, fn, first, second):
-        """(fn(*first), fn(*second)) with the two calls enqueued on two CUDA stream lanes so the device overlaps them:
-        the hi- and lo-nibble ciphertexts of a state never interact inside XOR4 / bootstrap."""
-        _capi.check(self._lib.ckks_fork(self._ptr))
+    def lane_map(self, fn, arg_tuples):
+        """[fn(*args) for args in arg_tuples] with every call enqueued on its own CUDA stream lane, so the device
+        overlaps the (small) kernels of independent pieces of work.  Inputs must have been produced before this call
+        (or inside the same lane); results may be used after it returns.  Nests."""
+        args = list(arg_tuples)
+        if len(args) < 2:
+            return [fn(*a) for a in args]
+        _capi.check(self._lib.ckks_fork(self._ptr, len(args)))
+        out = []
         try:
-            _capi.check(self._lib.ckks_set_lane(self._ptr, 0))
-            a = fn(*first)
-            _capi.check(self._lib.ckks_set_lane(self._ptr, 1))
-            b = fn(*second)
+            for i, a in enumerate(args):
+                _capi.check(self._lib.ckks_set_lane(self._ptr, i))
+                out.append(fn(*a))
         finally:
             _capi.check(self._lib.ckks_join(self._ptr))
+        return out
+
+    def pair_map(self, fn, first, second):
+        a, b = self.lane_map(fn, [first, second])
         return a, b
 
     # ------------------------------------------------------------------ multi-GPU key distribution (SURVEY.md 8e)

@@ -46,10 +46,11 @@ int ckks_engine_create(int logn, const uint64_t* q, int nq, const uint64_t* p, i
                        int hamming_weight, int fresh_level, uint64_t seed, int device_id, ckks_engine** out);
 void ckks_engine_destroy(ckks_engine* e);
 int ckks_sync(ckks_engine* e);
-/* Two stream lanes for the independent halves of a ciphertext pair (the hi- and lo-nibble ciphertexts never interact
- * inside XOR4 / bootstrap, xor4_lut.py:63-74, mixcol_final.py:158-163): fork orders both lanes after the main stream,
- * set_lane(0|1) routes the following calls, join orders the main stream after both lanes. */
-int ckks_fork(ckks_engine* e);
+/* Stream lanes for independent pieces of work (the hi- and lo-nibble ciphertexts never interact inside XOR4 / bootstrap,
+ * xor4_lut.py:63-74, mixcol_final.py:158-163; the two power bases of an XOR4 are independent, xor4_lut.py:65-66):
+ * fork(k) orders k helper streams after the current one, set_lane(i) routes the following calls to lane i, join orders
+ * the parent stream after all lanes.  Forks nest. */
+int ckks_fork(ckks_engine* e, int lanes);
 int ckks_set_lane(ckks_engine* e, int lane);
 int ckks_join(ckks_engine* e);
 /* engine.slot_count (read at pipeline.py:39, xor4_lut.py:16, state_encoder.py:14, ...) */
