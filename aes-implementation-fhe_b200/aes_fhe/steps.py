@@ -22,6 +22,11 @@ from .context import EngineContext
 
 Pair = Tuple[Any, Any]
 
+import os as _os
+# tuning switches for the stream-lane granularity (measured choices recorded in profiles/README.md)
+LANES_CONJ = _os.environ.get("AESFHE_LANES_CONJ", "1") == "1"
+LANES_AB = _os.environ.get("AESFHE_LANES_AB", "1") == "1"
+
 # multiplicative depths of the steps, used for the encryption-level hints of the fused mode
 XOR4_DEPTH = 5          # power basis 3 + product 1 + constant 1
 GF_DEPTH = 5
@@ -111,7 +116,7 @@ class XOR4LUT:
                 pos = eng.make_power_basis(ct, 8)
         basis = {0: eng.add_plain(eng.sub(ct, ct), 1.0)}   # "encrypted 1" without spending a level
         basis.update({k: pos[k - 1] for k in range(1, 9)})
-        if getattr(eng, "fused", False):                     # the seven conjugations are independent
+        if getattr(eng, "fused", False) and LANES_CONJ:      # the seven conjugations are independent
             conj = eng.lane_map(eng.conjugate, [(pos[15 - k],) for k in range(9, 16)])
             basis.update({k: conj[k - 9] for k in range(9, 16)})
             return basis
@@ -125,6 +130,7 @@ class XOR4LUT:
             # build both power bases at the common level (a cached round-key ciphertext may sit far above the state)
             lvl = min(a_ct.level, b_ct.level)
             a_ct, b_ct = eng.level_down(a_ct, lvl), eng.level_down(b_ct, lvl)
+        if getattr(eng, "fused", False) and LANES_AB:
             A, B = eng.pair_map(self._build_power_basis_16, (a_ct,), (b_ct,))     # independent: two stream lanes
         else:
             A = self._build_power_basis_16(a_ct)
@@ -293,7 +299,7 @@ class _MixBase:
             pos = eng.make_power_basis(ct, 8)
         basis = {0: eng.add_plain(eng.multiply(ct, 0.0), 1.0)}
         basis.update({k: pos[k - 1] for k in range(1, 9)})
-        if getattr(eng, "fused", False):
+        if getattr(eng, "fused", False) and LANES_CONJ:
             conj = eng.lane_map(eng.conjugate, [(pos[15 - k],) for k in range(9, 16)])
             basis.update({k: conj[k - 9] for k in range(9, 16)})
             return basis

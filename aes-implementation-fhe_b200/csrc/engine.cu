@@ -290,20 +290,9 @@ void Engine::fork(int k) {
         for (int l : F.lanes) lane_busy[l] = false;
         throw std::runtime_error("fork: out of stream lanes");
     }
+    // every lane is ordered after the parent stream from here on, and the parent enqueues nothing until the join, so a
+    // lane may take cached buffers from the pools of its ancestors (see alloc); sibling pools stay private
     for (int l : F.lanes) dev::stream_wait(streams[l], streams[F.parent]);
-    // every lane is ordered after the parent stream now, so the parent's cached buffers are safe for any of them:
-    // deal them out round-robin (they come back at the join), otherwise the lanes would keep drawing fresh memory
-    size_t turn = 0;
-    LanePool& PP = pools[F.parent];
-    for (auto& kv : PP.free) {
-        for (void* p : kv.second) {
-            LanePool& P = pools[F.lanes[turn++ % F.lanes.size()]];
-            P.free[kv.first].push_back(p);
-            P.cached += kv.first;
-        }
-        kv.second.clear();
-    }
-    PP.cached = 0;
     frames.push_back(std::move(F));
     set_lane(0);
 }
@@ -352,13 +341,19 @@ static size_t size_class_limbs(size_t limbs) {
 u64* Engine::alloc(size_t words) {
     const size_t limbs = (words + N() - 1) / N();
     const size_t bytes = size_class_limbs(limbs ? limbs : 1) * N() * sizeof(u64);
-    LanePool& P = pools[cur_lane];
-    auto it = P.free.find(bytes);
-    if (it != P.free.end() && !it->second.empty()) {
-        void* p = it->second.back();
-        it->second.pop_back();
-        P.cached -= bytes;
-        return (u64*)p;
+    // own pool first, then the pools of the enclosing frames' parent streams (idle and ordered before this lane)
+    int lane = cur_lane;
+    for (int depth = (int)frames.size(); depth >= 0; depth--) {
+        LanePool& P = pools[lane];
+        auto it = P.free.find(bytes);
+        if (it != P.free.end() && !it->second.empty()) {
+            void* p = it->second.back();
+            it->second.pop_back();
+            P.cached -= bytes;
+            return (u64*)p;
+        }
+        if (depth == 0) break;
+        lane = frames[depth - 1].parent;
     }
     void* p = dev::alloc(bytes, st);
     alloc_bytes[p] = bytes;
