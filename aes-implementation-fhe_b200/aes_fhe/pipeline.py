@@ -165,18 +165,28 @@ def decrypt_readme_order(pipe, ct_hi, ct_lo, round_keys) -> Pair:
     """R1: inverse of the as-shipped `encrypt`, in the order the reference README lists
     (README.md:85-95), using only the pipeline's own primitives."""
     rk = pipe._prepare_round_keys(round_keys)
+    need = SHIFTROWS_DEPTH + SUBBYTES_DEPTH           # levels InvShiftRows + InvSubBytes consume
+
+    def refill(ct):
+        # InvMixColumns ends with a bootstrap; an engine whose bootstrap returns fewer than 14 levels re-encrypts here
+        # (SURVEY.md App. B: "post-bootstrap level >= 14, or >= 5 if the decrypt driver renorms instead")
+        lvl = getattr(ct[0], "level", None)
+        if pipe.use_hard_renorm_between_steps and lvl is not None and lvl < need:
+            return pipe._renorm_pair(*ct, depth=need)
+        return ct
+
     ct = pipe.add_round_key(ct_hi, ct_lo, *rk[10])
-    ct = pipe._renorm_pair(*ct)
+    ct = pipe._renorm_pair(*ct, depth=need)
     for r in range(9, 0, -1):
         ct = pipe.inv_shift_rows(*ct)
         ct = pipe.inv_sub_bytes(*ct)
-        ct = pipe._renorm_pair(*ct)
+        ct = pipe._renorm_pair(*ct, depth=XOR4_DEPTH)
         ct = pipe.add_round_key(*ct, *rk[r])
-        ct = pipe._renorm_pair(*ct)
-        ct = pipe.inv_mix_columns(*ct)
+        ct = pipe._renorm_pair(*ct, depth=GF_DEPTH + XOR4_DEPTH)
+        ct = refill(pipe.inv_mix_columns(*ct))
     ct = pipe.inv_shift_rows(*ct)
     ct = pipe.inv_sub_bytes(*ct)
-    ct = pipe._renorm_pair(*ct)
+    ct = pipe._renorm_pair(*ct, depth=XOR4_DEPTH)
     ct = pipe.add_round_key(*ct, *rk[0])
     return pipe._renorm_pair(*ct)
 

@@ -146,3 +146,49 @@ def test_config3_full_fips_encryption_gpu():
     want = np.frombuffer(ecb(key, blocks.tobytes()), dtype=np.uint8).reshape(stride, 16)
     assert np.array_equal(got, want)
     assert ctx.bootstrap_stats()["count"] == 18
+
+
+@pytest.mark.gpu
+def test_config4_roundtrip_decrypt_gpu():
+    """configs[3]: encrypt -> decrypt round trip (README-order decryption with InvMixColumns GF9/11/13/14 LUTs and
+    InvSubBytes) on 2048 packed blocks: decrypt(FIPS ciphertext) == plaintext, 18 more bootstraps."""
+    mod = backend.use_cuda()
+    ctx = aes_fhe.EngineContext(1, mode="gpu", thread_count=1, backend=mod, logn=16, levels=21, fresh_level=14)
+    pipe = make_pipe(ctx)
+    drv = aes_fhe.FipsDriver(pipe, batched=True)
+    stride = ctx.engine.slot_count // 16
+    rng = np.random.default_rng(11)
+    blocks = rng.integers(0, 256, (stride, 16), dtype=np.uint8)
+    key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+    rks = aes_fhe.expand_aes128_key(np.frombuffer(key, dtype=np.uint8))
+    cipher = np.frombuffer(ecb(key, blocks.tobytes()), dtype=np.uint8).reshape(stride, 16)
+    ct = pipe.encoder.encode(drv._perm(cipher))               # start from the true AES ciphertext
+    got = drv.decode(*drv.decrypt(*ct, rks))
+    assert np.array_equal(got, blocks)
+    assert ctx.bootstrap_stats()["count"] == 18
+
+
+def test_inverse_round_pieces_on_engine(boot_ctx):
+    """InvShiftRows + InvSubBytes + InvMixColumns (fused GF 9/11/13/14 LUTs) on the engine against the plain model."""
+    which, ctx = boot_ctx
+    pipe = make_pipe(ctx)
+    drv = aes_fhe.FipsDriver(pipe, batched=True)
+    stride = ctx.engine.slot_count // 16
+    rng = np.random.default_rng(3)
+    blocks = rng.integers(0, 256, (stride, 16), dtype=np.uint8)
+    sbox, isbox = aes_fhe.tables.sbox_tables()
+    ct = pipe.encoder.encode(drv._perm(blocks), level=14)
+    out = pipe.inv_sub_bytes(*pipe.inv_shift_rows(*ct))
+    idx = np.array([(i - 4 * (i % 4)) % 16 for i in range(16)])            # InvShiftRows on column-first bytes
+    assert np.array_equal(drv.decode(*out), isbox[blocks[:, idx]])
+    mixed = pipe.inv_mix_columns(*pipe.encoder.encode(drv._perm(blocks), level=10))
+    gm = lambda m: np.array([aes_fhe.tables.gf_mul(x, m) for x in range(256)], dtype=np.uint8)
+    m9, m11, m13, m14 = gm(9), gm(11), gm(13), gm(14)
+    want = np.zeros_like(blocks)
+    for c in range(4):
+        a = [blocks[:, 4 * c + r] for r in range(4)]
+        want[:, 4 * c + 0] = m14[a[0]] ^ m11[a[1]] ^ m13[a[2]] ^ m9[a[3]]
+        want[:, 4 * c + 1] = m9[a[0]] ^ m14[a[1]] ^ m11[a[2]] ^ m13[a[3]]
+        want[:, 4 * c + 2] = m13[a[0]] ^ m9[a[1]] ^ m14[a[2]] ^ m11[a[3]]
+        want[:, 4 * c + 3] = m11[a[0]] ^ m13[a[1]] ^ m9[a[2]] ^ m14[a[3]]
+    assert np.array_equal(drv.decode(*mixed), want)
