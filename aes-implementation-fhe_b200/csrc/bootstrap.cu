@@ -206,56 +206,95 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
     // Giant steps with ONE ModDown for the whole matrix ("double hoisting"): every rotated inner sum contributes
     //   sigma_g(c0) in Q_l   and   <ModUp(sigma_g(c1)), rtk_g> in Q_l u P,
     // the Q_l u P parts are accumulated and divided by P once; the un-rotated row (giant 0) is added as it is.
+    // The rows are independent: they are dealt to up to 4 stream lanes, each with its own pair of accumulators, which
+    // are summed after the join.
     const size_t n = E.N();
     const int rows = P.level + 1 + E.K();
-    u64* accqp = nullptr;                       // [2][rows][N]
-    Ct* sum = A.keep(E.new_ct(2, P.level));     // running sum of the Q_l parts: (sigma(c0) terms + row 0, row 0's c1)
+    const int nl = (int)std::min<size_t>(P.rows.size(), 4);
+    struct LaneAcc { u64* accqp = nullptr; u64* sum = nullptr; u64* tmp = nullptr; u64* rbuf = nullptr; };
+    std::vector<LaneAcc> LA(nl);
+    for (const BsgsRow& R : P.rows)
+        if (R.giant % (long)E.slots()) {
+            E.galois_key(E.galois_for_rotation(-R.giant));
+            E.galois_perm(E.galois_for_rotation(-R.giant));
+        }
+    if (nl > 1) E.fork(nl);
+    try {
+        for (size_t ri = 0; ri < P.rows.size(); ri++) {
+            const BsgsRow& R = P.rows[ri];
+            LaneAcc& S = LA[ri % nl];
+            if (nl > 1) E.set_lane((int)(ri % nl));
+            // inner = sum_i diag_i (.) baby_i in one fused multiply-accumulate, un-rescaled (scale S_l^2): one rescale
+            // per matrix at the end
+            u64* inner = E.alloc(2 * ps);
+            for (size_t off = 0; off < R.terms.size(); off += 16) {
+                std::vector<const Ct*> xs;
+                std::vector<const Pt*> ps_;
+                for (size_t t = off; t < std::min(R.terms.size(), off + 16); t++) {
+                    xs.push_back(baby[R.terms[t].i]);
+                    ps_.push_back(R.terms[t].pt);
+                }
+                if (off == 0) E.diag_mac(inner, xs, ps_, P.level);
+                else {
+                    if (!S.tmp) S.tmp = E.alloc(2 * ps);
+                    E.diag_mac(S.tmp, xs, ps_, P.level);
+                    launch_add(E.ks, inner, inner, S.tmp, ll, 2, PolyStride{ps, ps, ps}, E.st);
+                }
+            }
+            if (R.giant % (long)E.slots() == 0) {
+                if (!S.sum) { S.sum = inner; inner = nullptr; }
+                else launch_add(E.ks, S.sum, S.sum, inner, ll, 2, PolyStride{ps, ps, ps}, E.st);
+            } else {
+                const u64 g = E.galois_for_rotation(-R.giant);
+                EvalKey* key = E.galois_key(g);
+                if (!S.rbuf) S.rbuf = E.alloc(2 * ps);
+                E.automorph(S.rbuf, inner, P.level + 1, 2, g);                  // (sigma(c0), sigma(c1))
+                Decomp D = E.decompose(S.rbuf + ps, P.level);
+                if (!S.accqp) {
+                    S.accqp = E.alloc((size_t)2 * rows * n);
+                    E.ks_inner(D, key, nullptr, S.accqp, nullptr, false);
+                } else E.ks_inner(D, key, nullptr, S.accqp, nullptr, true);
+                E.release(D.ext);
+                if (!S.sum) {
+                    S.sum = E.alloc(2 * ps);
+                    dev::d2d(S.sum, S.rbuf, ps * sizeof(u64), E.st);
+                    dev::zero(S.sum + ps, ps * sizeof(u64), E.st);
+                } else launch_add(E.ks, S.sum, S.sum, S.rbuf, ll, 1, PolyStride{0, 0, 0}, E.st);
+            }
+            if (inner) E.release(inner);
+        }
+        for (int l = 0; l < nl; l++) {                 // lane scratch goes back to the lane it came from
+            if (nl > 1) E.set_lane(l);
+            if (LA[l].tmp) E.release(LA[l].tmp);
+            if (LA[l].rbuf) E.release(LA[l].rbuf);
+        }
+    } catch (...) { if (nl > 1) E.join(); throw; }
+    if (nl > 1) E.join();
+    // combine the lanes' accumulators on the parent stream
+    u64* accqp = nullptr;
+    Ct* sum = A.keep(E.new_ct(2, P.level));
     bool sum_init = false;
-    u64* tmp = nullptr;
-    u64* rbuf = nullptr;
-    for (const BsgsRow& R : P.rows) {
-        // inner = sum_i diag_i (.) baby_i in one fused multiply-accumulate, un-rescaled (scale S_l^2): one rescale
-        // per matrix at the end
-        Ct* inner = A.keep(E.new_ct(2, P.level));
-        for (size_t off = 0; off < R.terms.size(); off += 16) {
-            std::vector<const Ct*> xs;
-            std::vector<const Pt*> ps_;
-            for (size_t t = off; t < std::min(R.terms.size(), off + 16); t++) {
-                xs.push_back(baby[R.terms[t].i]);
-                ps_.push_back(R.terms[t].pt);
-            }
-            if (off == 0) E.diag_mac(inner->d, xs, ps_, P.level);
+    LimbList llqp = E.limb_list(E.mods_qp(P.level));
+    const size_t psqp = (size_t)rows * n;
+    for (int l = 0; l < nl; l++) {
+        if (LA[l].accqp) {
+            if (!accqp) accqp = LA[l].accqp;
             else {
-                if (!tmp) tmp = E.alloc(2 * ps);
-                E.diag_mac(tmp, xs, ps_, P.level);
-                launch_add(E.ks, inner->d, inner->d, tmp, ll, 2, PolyStride{ps, ps, ps}, E.st);
+                launch_add(E.ks, accqp, accqp, LA[l].accqp, llqp, 2, PolyStride{psqp, psqp, psqp}, E.st);
+                E.release(LA[l].accqp);
             }
         }
-        if (R.giant % (long)E.slots() == 0) {
-            if (!sum_init) { dev::d2d(sum->d, inner->d, 2 * ps * sizeof(u64), E.st); sum_init = true; }
-            else launch_add(E.ks, sum->d, sum->d, inner->d, ll, 2, PolyStride{ps, ps, ps}, E.st);
-            continue;
+        if (LA[l].sum) {
+            if (!sum_init) { dev::d2d(sum->d, LA[l].sum, 2 * ps * sizeof(u64), E.st); sum_init = true; }
+            else launch_add(E.ks, sum->d, sum->d, LA[l].sum, ll, 2, PolyStride{ps, ps, ps}, E.st);
+            E.release(LA[l].sum);
         }
-        const u64 g = E.galois_for_rotation(-R.giant);
-        EvalKey* key = E.galois_key(g);
-        if (!rbuf) rbuf = E.alloc(2 * ps);
-        E.automorph(rbuf, inner->d, P.level + 1, 2, g);                      // (sigma(c0), sigma(c1))
-        Decomp D = E.decompose(rbuf + ps, P.level);
-        if (!accqp) { accqp = E.alloc((size_t)2 * rows * n); E.ks_inner(D, key, nullptr, accqp, nullptr, false); }
-        else E.ks_inner(D, key, nullptr, accqp, nullptr, true);
-        E.release(D.ext);
-        if (!sum_init) {
-            dev::d2d(sum->d, rbuf, ps * sizeof(u64), E.st);
-            dev::zero(sum->d + ps, ps * sizeof(u64), E.st);
-            sum_init = true;
-        } else launch_add(E.ks, sum->d, sum->d, rbuf, ll, 1, PolyStride{0, 0, 0}, E.st);
     }
-    if (tmp) E.release(tmp);
-    if (rbuf) E.release(rbuf);
     if (accqp) {
         u64* down = E.alloc(2 * ps);
         E.ks_moddown(accqp, P.level, 0, down);
-        launch_add(E.ks, sum->d, sum->d, down, ll, 2, PolyStride{ps, ps, ps}, E.st);
+        if (sum_init) launch_add(E.ks, sum->d, sum->d, down, ll, 2, PolyStride{ps, ps, ps}, E.st);
+        else dev::d2d(sum->d, down, 2 * ps * sizeof(u64), E.st);
         E.release(down);
         E.release(accqp);
     }
@@ -265,16 +304,28 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
 static Ct* cheb_eval(Engine& E, Arena& A, Ct* x, const std::vector<double>& coef, int m) {
     std::map<int, Ct*> T;
     T[1] = x;
-    std::function<Ct*(int)> get = [&](int k) -> Ct* {
-        auto it = T.find(k);
-        if (it != T.end()) return it->second;
+    auto make = [&](int k) -> Ct* {
         const int a = (k + 1) / 2, b = k / 2;                    // T_{a+b} = 2 T_a T_b - T_{a-b}
-        Ct* prod = A.keep(E.mul(get(a), get(b)));
+        Ct* prod = A.keep(E.mul(T.at(a), T.at(b)));
         Ct* two = A.keep(E.add(prod, prod));
-        Ct* r = a == b ? A.keep(E.add_const(two, -1.0, 0.0)) : A.keep(E.sub(two, get(a - b)));
-        T[k] = r;
-        return r;
+        return a == b ? A.keep(E.add_const(two, -1.0, 0.0)) : A.keep(E.sub(two, T.at(a - b)));
     };
+    // baby steps T_2..T_m by generation (2^(g-1) < k <= 2^g only needs earlier generations): one stream lane per product
+    for (int lo = 1; lo < m; lo *= 2) {
+        const int hi = std::min(2 * lo, m), cnt = hi - lo;
+        std::vector<Ct*> made(cnt, nullptr);
+        if (cnt > 1) E.fork(cnt);
+        try {
+            for (int k = lo + 1; k <= hi; k++) {
+                if (cnt > 1) E.set_lane(k - lo - 1);
+                made[k - lo - 1] = make(k);
+            }
+        } catch (...) { if (cnt > 1) E.join(); throw; }
+        if (cnt > 1) E.join();
+        for (int k = lo + 1; k <= hi; k++) T[k] = made[k - lo - 1];
+    }
+    for (int g = 2 * m; g <= (int)coef.size() - 1; g *= 2) T[g] = make(g);     // giants T_2m, T_4m, ..
+    auto get = [&](int k) -> Ct* { return T.at(k); };
     struct Res { Ct* ct; double c0; };
     std::function<Res(const std::vector<double>&)> rec = [&](const std::vector<double>& c) -> Res {
         const int d = (int)c.size() - 1;
@@ -296,7 +347,16 @@ static Ct* cheb_eval(Engine& E, Arena& A, Ct* x, const std::vector<double>& coef
         std::vector<double> q(d - g + 1, 0.0), r(c.begin(), c.begin() + g);
         q[0] = c[g];
         for (int k = g + 1; k <= d; k++) { q[k - g] = 2 * c[k]; r[2 * g - k] -= c[k]; }
-        Res Q = rec(q), R = rec(r);
+        // the quotient and remainder sub-polynomials are independent: two stream lanes
+        Res Q{nullptr, 0.0}, R{nullptr, 0.0};
+        E.fork(2);
+        try {
+            E.set_lane(0);
+            Q = rec(q);
+            E.set_lane(1);
+            R = rec(r);
+        } catch (...) { E.join(); throw; }
+        E.join();
         Ct* Tg = get(g);
         Ct* t = Q.ct ? A.keep(E.mul(Q.ct, Tg)) : nullptr;
         if (Q.c0 != 0.0) {

@@ -1247,25 +1247,40 @@ std::vector<Ct*> Engine::rotate_hoisted(const Ct* a, const std::vector<long>& st
     const int l = a->level;
     const size_t ps = (size_t)(l + 1) * N();
     const long n = (long)slots();
-    std::vector<Ct*> out;
-    Decomp D;
-    bool have = false;
-    LimbList ll = limb_list(mods_q(l));
-    for (long s : steps) {
-        if (((s % n) + n) % n == 0) { out.push_back(copy(a)); continue; }
-        if (!have) { D = decompose(a->d + ps, l); have = true; }
-        const u64 g = galois_for_rotation(s);
-        EvalKey* key = galois_key(g);
-        const u32* perm = galois_perm(g);
-        Ct* r = new_ct(2, l);
-        ks_apply(D, key, perm, r->d);
-        u64* t = alloc(ps);
-        automorph(t, a->d, l + 1, 1, g);
-        launch_add(ks, r->d, r->d, t, ll, 1, PolyStride{0, 0, 0}, st);
-        release(t);
-        out.push_back(r);
+    std::vector<Ct*> out(steps.size(), nullptr);
+    std::vector<size_t> work;
+    for (size_t i = 0; i < steps.size(); i++) {
+        if (((steps[i] % n) + n) % n == 0) out[i] = copy(a);
+        else work.push_back(i);
     }
-    if (have) release(D.ext);
+    if (work.empty()) return out;
+    LimbList ll = limb_list(mods_q(l));
+    Decomp D = decompose(a->d + ps, l);
+    for (size_t i : work) { galois_key(galois_for_rotation(steps[i])); galois_perm(galois_for_rotation(steps[i])); }
+    // the rotations only read the shared decomposition: one stream lane each (up to 8)
+    const int lanes = (int)std::min<size_t>(work.size(), 8);
+    if (lanes > 1) fork(lanes);
+    try {
+        for (size_t w = 0; w < work.size(); w++) {
+            if (lanes > 1) set_lane((int)(w % lanes));
+            const size_t i = work[w];
+            const u64 g = galois_for_rotation(steps[i]);
+            Ct* r = new_ct(2, l);
+            ks_apply(D, galois_key(g), galois_perm(g), r->d);
+            u64* t = alloc(ps);
+            automorph(t, a->d, l + 1, 1, g);
+            launch_add(ks, r->d, r->d, t, ll, 1, PolyStride{0, 0, 0}, st);
+            release(t);
+            out[i] = r;
+        }
+    } catch (...) {
+        if (lanes > 1) join();
+        release(D.ext);
+        for (Ct* c : out) if (c) free_ct(c);
+        throw;
+    }
+    if (lanes > 1) join();
+    release(D.ext);
     return out;
 }
 
