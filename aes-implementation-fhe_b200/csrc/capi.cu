@@ -74,6 +74,12 @@ void ckks_engine_destroy(ckks_engine* e) {
     delete e;
 }
 int ckks_fork(ckks_engine* e, int lanes) { return guard([&] { e->E->fork(lanes); }); }
+int ckks_set_lanes_enabled(ckks_engine* e, int on) {
+    return guard([&] {
+        if (e->E->in_fork()) throw std::runtime_error("cannot switch lanes inside a fork");
+        e->E->lanes_on = on != 0;
+    });
+}
 int ckks_set_lane(ckks_engine* e, int lane) { return guard([&] { e->E->set_lane(lane); }); }
 int ckks_join(ckks_engine* e) { return guard([&] { e->E->join(); }); }
 int ckks_sync(ckks_engine* e) { return guard([&] { e->E->sync(); }); }

@@ -280,6 +280,12 @@ void Engine::fork(int k) {
     Frame F;
     F.parent = cur_lane;
     F.epoch = ++epoch_counter;
+    if (!lanes_on) {                       // serial mode: every "lane" is the parent stream itself
+        F.lanes.assign(k, cur_lane);
+        F.serial = true;
+        frames.push_back(std::move(F));
+        return;
+    }
     for (int i = 1; i < kMaxLanes && (int)F.lanes.size() < k; i++) {
         if (lane_busy[i]) continue;
         if (!lane_made[i]) { streams[i] = dev::stream_create(); lane_made[i] = true; }
@@ -309,6 +315,7 @@ void Engine::join() {
     frames.pop_back();
     // the parent is ordered after every lane: their cached buffers return to the parent's pool
     LanePool& PP = pools[F.parent];
+    if (F.serial) F.lanes.clear();
     for (int l : F.lanes) {
         dev::stream_wait(streams[F.parent], streams[l]);
         for (auto& kv : pools[l].free) {

@@ -115,6 +115,7 @@ class Engine {
     struct Frame {
         int parent = 0;
         long epoch = 0;
+        bool serial = false;
         std::vector<int> lanes;
         std::vector<Ct*> dct;
         std::vector<Pt*> dpt;
@@ -123,6 +124,7 @@ class Engine {
     void set_lane(int i);
     void join();
     bool in_fork() const { return !frames.empty(); }
+    bool lanes_on = true;                  // false: forks run serially on the parent stream (A/B timing, profiling)
     dev_stream streams[kMaxLanes] = {};
     bool lane_made[kMaxLanes] = {};
     bool lane_busy[kMaxLanes] = {};

@@ -43,7 +43,14 @@ __device__ __forceinline__ u64 shoup_mul_lazy4(u64 x, u64 w, u64 ws, u64 q) {
 // Moduli below 2^52 (the scale primes) take the SMALL path: no per-stage correction at all.  Forward values grow by
 // at most 4q per stage (<= 65q < 2^59 after 16 stages); inverse sums double per stage and are folded back at the pass
 // boundary (<= 2^9 q after 8 stages).  The 60/61-bit moduli (q_0, special primes) keep the Harvey [0,4q) / [0,2q) forms.
+#ifndef NTT_VARIANT
+#define NTT_VARIANT 0
+#endif
+#if NTT_VARIANT == 2
+#define NTT_SMALL_BITS 0          // experiment: no modulus takes the SMALL path
+#else
 #define NTT_SMALL_BITS 52
+#endif
 
 // Forward radix-16 block rooted at table index X: 4 CT stages on x[0..15].
 template <bool SMALL>
@@ -113,6 +120,16 @@ __device__ __forceinline__ void inv16(u64 (&x)[16], u32 X, const u64* __restrict
     }
 }
 
+// fold a lazy value below 2^7 q (forward SMALL path: <= 65q) to [0,q) by a chain of conditional subtractions: ALU-pipe
+// work only, no multiplies (the Barrett variant costs five more IMAD-class instructions per value)
+__device__ __forceinline__ u64 canon128(u64 v, u64 q) {
+#pragma unroll
+    for (int s = 6; s >= 0; s--) {
+        const u64 m = q << s;
+        v = v >= m ? v - m : v;
+    }
+    return v;
+}
 __device__ __forceinline__ u64 canon4(u64 v, u64 q) {
     v = v >= 2 * q ? v - 2 * q : v;
     return v >= q ? v - q : v;
@@ -206,7 +223,11 @@ __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int
         // each thread rewrites exactly the 16 slots it just read, so no barrier is needed before this store
 #pragma unroll
         for (int k = 0; k < 16; k++)
+#if NTT_VARIANT == 1
+            sm[pad16(row * 256 + 16 * jj + k)] = SMALL ? canon128(x[k], q) : canon4(x[k], q);
+#else
             sm[pad16(row * 256 + 16 * jj + k)] = SMALL ? barrett_reduce64(x[k], mc) : canon4(x[k], q);
+#endif
     }
     BLOCK_SYNC;
     FOR_THREADS {

@@ -196,6 +196,10 @@ class Engine:
     def sync(self):
         _capi.check(self._lib.ckks_sync(self._ptr))
 
+    def set_lanes_enabled(self, on: bool):
+        """False: every fork runs serially on the parent stream (used to time kernels in isolation)."""
+        _capi.check(self._lib.ckks_set_lanes_enabled(self._ptr, int(bool(on))))
+
     def lane_map(self, fn, arg_tuples):
         """[fn(*args) for args in arg_tuples] with every call enqueued on its own CUDA stream lane, so the device
         overlaps the (small) kernels of independent pieces of work.  Inputs must have been produced before this call

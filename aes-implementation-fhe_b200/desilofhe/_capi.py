@@ -56,7 +56,7 @@ def load():
         "ckks_engine_create": (i32, [i32, u64p, i32, u64p, i32, i32, i32, i32, i32, u64, i32, pp]),
         "ckks_engine_destroy": (None, [vp]),
         "ckks_sync": (i32, [vp]),
-        "ckks_fork": (i32, [vp, i32]), "ckks_set_lane": (i32, [vp, i32]), "ckks_join": (i32, [vp]),
+        "ckks_fork": (i32, [vp, i32]), "ckks_set_lane": (i32, [vp, i32]), "ckks_set_lanes_enabled": (i32, [vp, i32]), "ckks_join": (i32, [vp]),
         "ckks_slot_count": (i32, [vp]),
         "ckks_get_params": (i32, [vp] + [C.POINTER(i32)] * 5 + [vp, vp, vp]),
         "ckks_keygen_secret": (i32, [vp]), "ckks_keygen_public": (i32, [vp]), "ckks_keygen_relin": (i32, [vp]),

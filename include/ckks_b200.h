@@ -52,6 +52,7 @@ int ckks_sync(ckks_engine* e);
  * the parent stream after all lanes.  Forks nest. */
 int ckks_fork(ckks_engine* e, int lanes);
 int ckks_set_lane(ckks_engine* e, int lane);
+int ckks_set_lanes_enabled(ckks_engine* e, int on);   /* 0: forks run serially on the parent stream (profiling, A/B) */
 int ckks_join(ckks_engine* e);
 /* engine.slot_count (read at pipeline.py:39, xor4_lut.py:16, state_encoder.py:14, ...) */
 int ckks_slot_count(const ckks_engine* e);
