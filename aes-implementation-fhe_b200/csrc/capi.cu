@@ -44,9 +44,11 @@ double ckks_launch_host_ms(void) {
 }
 
 int ckks_engine_create_default(int logn, int levels, int scale_bits, int q0_bits, int p_bits, int dnum, int hamming,
-                               int fresh_level, uint64_t seed, int device, ckks_engine** out) {
+                               int fresh_level, int top_levels, int top_bits, uint64_t seed, int device,
+                               ckks_engine** out) {
     return guard([&] {
-        Params prm = default_params(logn, levels, scale_bits, q0_bits, p_bits, dnum, hamming, fresh_level);
+        Params prm = default_params(logn, levels, scale_bits, q0_bits, p_bits, dnum, hamming, fresh_level, top_levels,
+                                    top_bits);
         prm.seed = seed;
         prm.device = device;
         *out = new ckks_engine{new Engine(prm), {}};
@@ -54,6 +56,7 @@ int ckks_engine_create_default(int logn, int levels, int scale_bits, int q0_bits
 }
 int ckks_engine_create(int logn, const uint64_t* q, int nq, const uint64_t* p, int np, int scale_bits, int alpha,
                        int hamming, int fresh_level, uint64_t seed, int device, ckks_engine** out) {
+    // explicit chain: S[L] = 2^scale_bits, the lower scales follow from the primes (spec S1)
     return guard([&] {
         Params prm;
         prm.logn = logn;

@@ -93,36 +93,52 @@ static u64 prime_nearest(double target, u64 step, std::set<u64>& used) {
     }
     throw std::runtime_error("no prime found");
 }
-static std::vector<double> canonical_scales(const std::vector<u64>& q, int scale_bits) {
+static std::vector<double> canonical_scales(const std::vector<u64>& q, int top_scale_bits) {
     const int L = (int)q.size() - 1;
     std::vector<double> s(L + 1);
-    s[L] = ldexp(1.0, scale_bits);
+    s[L] = ldexp(1.0, top_scale_bits);
     for (int l = L; l >= 1; l--) s[l - 1] = s[l] * s[l] / (double)q[l];
     return s;
 }
 
+// top_levels > 0: the highest `top_levels` levels carry the larger scale 2^top_bits (CoeffToSlot runs there: its error is
+// governed by the plaintext / rescale precision relative to the huge ModRaise values); the scale then descends to
+// 2^scale_bits as fast as primes below 2^60.5 allow.  top_levels = 0 is the uniform chain.
 Params default_params(int logn, int levels, int scale_bits, int q0_bits, int p_bits, int dnum, int hamming,
-                      int fresh_level) {
+                      int fresh_level, int top_levels, int top_bits) {
     Params P;
     P.logn = logn;
     P.scale_bits = scale_bits;
+    P.top_levels = top_levels;
+    P.top_bits = top_bits;
     P.hamming = hamming;
     const u64 step = 2ull << logn;
     std::set<u64> used;
     const int nq = levels + 1;
     P.alpha = (nq + dnum - 1) / dnum;
-    const int digit_bits = q0_bits + (P.alpha - 1) * scale_bits;
-    const int K = (digit_bits + 1 + (p_bits - 1) - 1) / (p_bits - 1);
-    P.p = primes_below(1ull << p_bits, step, K, used);
+    // the special primes (largest below 2^p_bits) never collide with the chain (which stays below 2^60.5 < 2^p_bits - ..):
+    // reserve a generous set first so `used` protects them, then cut it down to the K the widest digit needs
+    std::vector<u64> reserve = primes_below(1ull << p_bits, step, 16, used);
     P.q.assign(nq, 0);
     P.q[0] = primes_below(1ull << q0_bits, step, 1, used)[0];
-    const double delta = ldexp(1.0, scale_bits);
-    double s = delta;
+    const double delta = ldexp(1.0, scale_bits), hi = ldexp(1.0, top_bits), cap = pow(2.0, 60.5);
+    double s = top_levels > 0 ? hi : delta;
     for (int l = levels; l >= 1; l--) {
-        const double target = s * s / delta;
+        const double want = (top_levels > 0 && l - 1 > levels - top_levels) ? hi : delta;   // desired S_{l-1}
+        const double next = std::max(want, s * s / cap);
+        const double target = s * s / next;
         P.q[l] = prime_nearest(target, step, used);
         s = s * s / (double)P.q[l];
     }
+    // P must dominate the widest key-switch digit (alpha consecutive limbs): sum of the limbs' bit lengths
+    int digit_bits = 0;
+    for (int j = 0; j * P.alpha < nq; j++) {
+        int bits = 0;
+        for (int i = j * P.alpha; i < std::min((j + 1) * P.alpha, nq); i++) bits += 64 - __builtin_clzll(P.q[i]);
+        digit_bits = std::max(digit_bits, bits);
+    }
+    const int K = (digit_bits + 1 + (p_bits - 1) - 1) / (p_bits - 1);
+    P.p.assign(reserve.begin(), reserve.begin() + K);
     P.fresh_level = fresh_level < 0 ? levels : std::min(fresh_level, levels);
     return P;
 }
@@ -158,7 +174,7 @@ Engine::Engine(const Params& P) : prm(P) {
     if (prm.alpha > BC_MAX_SRC || K() > BC_MAX_SRC) throw std::runtime_error("engine: digit too wide");
     if (L() + 1 + K() > BC_MAX_TGT) throw std::runtime_error("engine: too many conversion targets");
     if ((dnum()) > NTT_MAX_Z) throw std::runtime_error("engine: dnum too large");
-    scales = canonical_scales(prm.q, prm.scale_bits);
+    scales = canonical_scales(prm.q, prm.top_levels > 0 ? prm.top_bits : prm.scale_bits);
     const size_t n = N();
     const int nm = nmod();
     std::vector<ModConst> mc(nm);
@@ -788,9 +804,17 @@ void Engine::decrypt(const Ct* c, double* z_out) {
 
 // ------------------------------------------------------------------ basis conversion tables (spec S5)
 BaseConvTable Engine::make_bc_table(const std::vector<int>& src, const std::vector<int>& srow,
-                                    const std::vector<int>& tgt, const std::vector<int>& orow) {
+                                    const std::vector<int>& tgt, const std::vector<int>& orow, bool exact) {
     BaseConvTable T;
     memset(&T, 0, sizeof(T));
+    T.exact = exact ? 1 : 0;
+    for (size_t i = 0; i < src.size(); i++) T.inv_src[i] = 1.0 / (double)mod[src[i]];
+    for (size_t t = 0; t < tgt.size(); t++) {
+        const u64 qt = mod[tgt[t]];
+        u64 D = 1;
+        for (int sidx : src) D = mulmod_h(D, mod[sidx] % qt, qt);
+        T.negD[t] = (qt - D) % qt;
+    }
     T.ns = (int)src.size();
     T.nt = (int)tgt.size();
     std::vector<u64> hat((size_t)T.ns * T.nt), hat_s((size_t)T.ns * T.nt);
@@ -849,7 +873,7 @@ const BaseConvTable& Engine::moddown_table(int level, int drop) {
     for (int i = level - drop + 1; i <= level; i++) { src.push_back(i); srow.push_back(i); }
     for (int k = 0; k < K(); k++) { src.push_back(L() + 1 + k); srow.push_back(level + 1 + k); }
     for (int i = 0; i <= level - drop; i++) { tgt.push_back(i); orow.push_back(i); }
-    moddown_tabs[key] = make_bc_table(src, srow, tgt, orow);
+    moddown_tabs[key] = make_bc_table(src, srow, tgt, orow, true);     // exact, centred: an unbiased division by P
     return moddown_tabs[key];
 }
 // (P * q_{level-drop+1} .. q_level)^-1 mod q_i, i <= level - drop

@@ -65,6 +65,7 @@ struct Params {
     int logn = 16;
     std::vector<u64> q, p;                          // q_0..q_L ; p_0..p_{K-1}
     int scale_bits = 50;
+    int top_levels = 0, top_bits = 0;               // S[L] = 2^top_bits when top_levels > 0 (see default_params)
     int alpha = 1;                                  // q-limbs per key-switch digit
     int hamming = 192;
     int fresh_level = 0;                            // level of fresh encryptions (<= L)
@@ -75,7 +76,7 @@ struct Params {
 
 // Deterministic prime chain (DESIGN.md spec S1; restated independently in oracle/params.py)
 Params default_params(int logn, int levels, int scale_bits, int q0_bits, int p_bits, int dnum, int hamming,
-                      int fresh_level);
+                      int fresh_level, int top_levels = 0, int top_bits = 0);
 
 struct BootPlan;   // bootstrap.cu
 
@@ -265,7 +266,7 @@ class Engine {
 
     EvalKey make_switch_key(u64 key_id, const u64* s_from_ntt);
     BaseConvTable make_bc_table(const std::vector<int>& src, const std::vector<int>& srow,
-                                const std::vector<int>& tgt, const std::vector<int>& orow);
+                                const std::vector<int>& tgt, const std::vector<int>& orow, bool exact = false);
     void encode_coeffs_dev(i64* out_dev, const double* z_host, double scale);
     void encode_coeffs_from_dev(i64* out_dev, double* z_dev, double scale, bool check);
     void rescale_into(u64* out, const u64* in, int npoly, int level);

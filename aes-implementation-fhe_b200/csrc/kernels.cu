@@ -191,14 +191,19 @@ k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in, cons
         const u64* src = in + blockIdx.z * in_zs;
         u64* dst = out + blockIdx.z * out_zs;
         u64 y[NS];
+        double v = 0.0;
 #pragma unroll
-        for (int i = 0; i < NS; i++)
+        for (int i = 0; i < NS; i++) {
             y[i] = shoup_mul(src[(size_t)T.srow[i] * N + k], T.hatinv[i], T.hatinv_s[i], S.mc[T.src[i]].q);
+            v = fadd_rn(v, fmul_rn(ull2d_rn(y[i]), T.inv_src[i]));
+        }
+        const u64 u = T.exact ? (u64)d2ll_rn(v) : 0;       // overflow count of the fast conversion (0..NS)
         for (int t = tbeg; t < tend; t++) {
             const ModConst m = S.mc[T.tgt[t]];
             u64 hi = 0, lo = 0;
 #pragma unroll
             for (int i = 0; i < NS; i++) mac128(hi, lo, y[i], s_hat[t * NS + i]);
+            if (T.exact) mac128(hi, lo, u, T.negD[t]);      // - u * D  (mod q_t)
             // (hi, lo) < NS * 2^122: fold the high word through 2^64 mod q_t, then one Barrett reduction
             const u64 h1 = barrett_reduce64(hi, m);
             u64 h2 = 0, l2 = lo;

@@ -20,6 +20,11 @@ struct BaseConvTable {
     u64 hatinv[BC_MAX_SRC], hatinv_s[BC_MAX_SRC];
     const u64* hat;
     const u64* hat_s;
+    // exact mode (ModDown): the overflow count u = round(sum_i y_i / s_i) is computed in fp64 and u * D is taken out,
+    // so the conversion returns the CENTRED residue of the input modulo D = prod s_i (spec S5')
+    int exact;
+    double inv_src[BC_MAX_SRC];        // 1 / s_i
+    u64 negD[BC_MAX_TGT];              // q_t - (D mod q_t)
 };
 // shape shared by all kernels: N coefficients per row, modulus table
 struct KShape {

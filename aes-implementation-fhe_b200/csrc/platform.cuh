@@ -142,6 +142,7 @@ __device__ __forceinline__ double fdiv_rn(double a, double b) { return __ddiv_rn
 __device__ __forceinline__ u32 brev32(u32 x) { return __brev(x); }
 __device__ __forceinline__ int popc64(u64 x) { return __popcll(x); }
 __device__ __forceinline__ i64 d2ll_rn(double x) { return __double2ll_rn(x); }
+__device__ __forceinline__ double ull2d_rn(u64 x) { return __ull2double_rn(x); }
 template <typename T>
 __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
 
@@ -232,6 +233,7 @@ static inline u32 brev32(u32 x) {
 }
 static inline int popc64(u64 x) { return __builtin_popcountll(x); }
 static inline i64 d2ll_rn(double x) { return (i64)nearbyint(x); }
+static inline double ull2d_rn(u64 x) { return (double)x; }
 template <typename T>
 static inline T ldg(const T* p) { return *p; }
 #endif

@@ -34,7 +34,9 @@ __all__ = ["Engine", "Ciphertext", "Plaintext", "SecretKey", "PublicKey", "Relin
            "RotationKey", "BootstrapKey"]
 
 # parameter sets (DESIGN.md "Parameters"): N = 2^16, q0 ~ 2^60, scale primes ~ 2^50, special primes ~ 2^61
-DEFAULTS = dict(logn=16, levels=21, scale_bits=50, q0_bits=60, p_bits=61, dnum=3, hamming_weight=192)
+DEFAULTS = dict(logn=16, levels=21, scale_bits=50, q0_bits=60, p_bits=61, dnum=3, hamming_weight=192,
+                top_levels=0, top_bits=58)
+TOP_LEVELS_BOOT = 0        # optional larger scale on the CoeffToSlot levels (top_levels=3 buys only 1.5x precision)
 FRESH_LEVEL_BOOT = 14      # fresh encryptions of the bootstrapping set: SubBytes needs 13 levels
 
 
@@ -141,10 +143,12 @@ class Engine:
         fresh = overrides.get("fresh_level", -1)
         if fresh < 0 and use_bootstrap and max_level is None and cfg["levels"] > FRESH_LEVEL_BOOT:
             fresh = FRESH_LEVEL_BOOT
+        if use_bootstrap and "top_levels" not in overrides:
+            cfg["top_levels"] = TOP_LEVELS_BOOT
         out = C.c_void_p()
         _capi.check(self._lib.ckks_engine_create_default(
             cfg["logn"], cfg["levels"], cfg["scale_bits"], cfg["q0_bits"], cfg["p_bits"], cfg["dnum"],
-            cfg["hamming_weight"], fresh, seed, device_id, C.byref(out)))
+            cfg["hamming_weight"], fresh, cfg["top_levels"], cfg["top_bits"], seed, device_id, C.byref(out)))
         self._ptr = out.value
         self.slot_count = self._lib.ckks_slot_count(self._ptr)
         if overrides.get("keys_external"):

@@ -52,7 +52,7 @@ def load():
         "ckks_last_error": (C.c_char_p, []),
         "ckks_backend": (C.c_char_p, []),
         "ckks_launch_count": (lng, []),
-        "ckks_engine_create_default": (i32, [i32] * 8 + [u64, i32, pp]),
+        "ckks_engine_create_default": (i32, [i32] * 10 + [u64, i32, pp]),
         "ckks_engine_create": (i32, [i32, u64p, i32, u64p, i32, i32, i32, i32, i32, u64, i32, pp]),
         "ckks_engine_destroy": (None, [vp]),
         "ckks_sync": (i32, [vp]),

@@ -38,10 +38,11 @@ const char* ckks_backend(void);          /* "cuda-sm_100a" for the product libra
 long ckks_launch_count(void);            /* kernels launched by this library so far (bench.py gpu_launches) */
 
 /* ---- engine construction: replaces desilofhe.Engine(...) (engine_context.py:17-42).
- * `_default` derives the deterministic prime chain of DESIGN.md spec S1 (q0 | L scale primes | K special). */
+ * `_default` derives the deterministic prime chain of DESIGN.md spec S1 (q0 | L scale primes | K special); with
+ * top_levels > 0 the highest levels carry the larger scale 2^top_bits (bootstrapping precision). */
 int ckks_engine_create_default(int logn, int levels, int scale_bits, int q0_bits, int p_bits, int dnum,
-                               int hamming_weight, int fresh_level, uint64_t seed, int device_id,
-                               ckks_engine** out);
+                               int hamming_weight, int fresh_level, int top_levels, int top_bits, uint64_t seed,
+                               int device_id, ckks_engine** out);
 int ckks_engine_create(int logn, const uint64_t* q, int nq, const uint64_t* p, int np, int scale_bits, int alpha,
                        int hamming_weight, int fresh_level, uint64_t seed, int device_id, ckks_engine** out);
 void ckks_engine_destroy(ckks_engine* e);

@@ -53,6 +53,7 @@ def lib() -> C.CDLL:
         "ref_mul_const_batch": (None, [u64p, u64p, u64p, u64p, i32, sz, u64p]),
         "ref_permute_batch": (None, [u64p, u64p, u32p, i32, sz]),
         "ref_baseconv": (None, [u64p, u64p, sz, i32, u64p, u64p, i32, u64p, u64p]),
+        "ref_baseconv_exact": (None, [u64p, u64p, sz, i32, u64p, u64p, i32, u64p, u64p, f64p, u64p]),
         "ref_reduce_i64_batch": (None, [u64p, i64p, i32, sz, u64p]),
         "ref_rand64": (u64, [u64, u64, u64]),
         "ref_sample_uniform": (None, [u64p, sz, u64, u64, u64, u64]),
@@ -310,13 +311,19 @@ class OracleCKKS:
         return self.decode_limb0(coef, ct.scale)
 
     # ------------------------------------------------------------------ key switching (spec S5/S6)
-    def _baseconv(self, x: np.ndarray, src: List[int], tgt: List[int]) -> np.ndarray:
+    def _baseconv(self, x: np.ndarray, src: List[int], tgt: List[int], exact: bool = False) -> np.ndarray:
         D = 1
         for i in src:
             D *= self.moduli[i]
         hatinv = np.array([pow(D // self.moduli[i] % self.moduli[i], -1, self.moduli[i]) for i in src], dtype=np.uint64)
         hat = np.array([[D // self.moduli[i] % self.moduli[t] for t in tgt] for i in src], dtype=np.uint64)
         out = np.empty((len(tgt), self.N), dtype=np.uint64)
+        if exact:      # spec S5': centred residue modulo D (ModDown)
+            inv_src = np.array([1.0 / float(self.moduli[i]) for i in src], dtype=np.float64)
+            negD = np.array([(self.moduli[t] - D % self.moduli[t]) % self.moduli[t] for t in tgt], dtype=np.uint64)
+            self.lib.ref_baseconv_exact(out, np.ascontiguousarray(x), self.N, len(src), self._mods(src), hatinv,
+                                        len(tgt), self._mods(tgt), np.ascontiguousarray(hat), inv_src, negD)
+            return out
         self.lib.ref_baseconv(out, np.ascontiguousarray(x), self.N, len(src), self._mods(src), hatinv, len(tgt),
                               self._mods(tgt), np.ascontiguousarray(hat))
         return out
@@ -345,7 +352,7 @@ class OracleCKKS:
         src_mods = list(range(level - drop + 1, level + 1)) + list(range(self.L + 1, self.L + 1 + self.K))
         src_rows = list(range(level - drop + 1, level + 1)) + list(range(nq, nq + self.K))
         coef = self.intt(acc[src_rows], src_mods)
-        conv = self.ntt(self._baseconv(coef, src_mods, keep), keep)
+        conv = self.ntt(self._baseconv(coef, src_mods, keep, exact=True), keep)
         D = 1
         for i in src_mods:
             D *= self.moduli[i]

@@ -175,6 +175,30 @@ void ref_baseconv(u64 *out, const u64 *in, size_t N, int ns, const u64 *sq, cons
     }
 }
 
+/* spec S5' (exact, centred conversion used by ModDown): as ref_baseconv, then the overflow count
+ * u = round(sum_i y_i / s_i) (fp64, sequential, separately rounded products) times D = prod s_i is taken out:
+ * out[t] = sum_i y_i hat[i][t] - u D  (mod tq[t]);  negD[t] = tq[t] - (D mod tq[t]) */
+void ref_baseconv_exact(u64 *out, const u64 *in, size_t N, int ns, const u64 *sq, const u64 *hatinv, int nt,
+                        const u64 *tq, const u64 *hat /* [ns][nt] */, const double *inv_src, const u64 *negD) {
+#pragma omp parallel for schedule(static)
+    for (size_t k = 0; k < N; k++) {
+        u64 y[64];
+        double v = 0.0;
+        for (int i = 0; i < ns; i++) {
+            y[i] = mulmod(in[i * N + k], hatinv[i], sq[i]);
+            volatile double p = (double)y[i] * inv_src[i];
+            v = v + p;
+        }
+        u64 u = (u64)(i64)nearbyint(v);
+        for (int t = 0; t < nt; t++) {
+            u64 acc = 0, q = tq[t];
+            for (int i = 0; i < ns; i++) acc = addmod(acc, mulmod(y[i] % q, hat[i * nt + t], q), q);
+            acc = addmod(acc, mulmod(u % q, negD[t], q), q);
+            out[t * N + k] = acc;
+        }
+    }
+}
+
 /* signed small coefficients -> residues, [nl][N] */
 void ref_reduce_i64_batch(u64 *out, const i64 *v, int nl, size_t N, const u64 *qs) {
 #pragma omp parallel for schedule(static)

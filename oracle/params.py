@@ -14,6 +14,7 @@ canonical scale S_{l-1} = S_l^2 / q_l stays re-centred on 2^scale_bits (DESIGN.m
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 from typing import List
 
@@ -104,27 +105,35 @@ class CKKSParams:
 
 
 def make_params(logn: int = 16, levels: int = 20, scale_bits: int = 50, q0_bits: int = 60, p_bits: int = 61,
-                alpha: int = 0, dnum: int = 3, hamming_weight: int = 192, fresh_level: int = -1) -> CKKSParams:
-    """Deterministic parameter construction.  `levels` = L (number of scale primes)."""
+                alpha: int = 0, dnum: int = 3, hamming_weight: int = 192, fresh_level: int = -1,
+                top_levels: int = 0, top_bits: int = 58) -> CKKSParams:
+    """Deterministic parameter construction.  `levels` = L (number of scale primes).  With top_levels > 0 the highest
+    levels carry the scale 2^top_bits and the chain descends to 2^scale_bits as fast as primes below 2^60.5 allow."""
     step = 2 << logn
     used: set = set()
     nq = levels + 1
     if alpha <= 0:
         alpha = -(-nq // dnum)
-    # special primes: P must dominate the largest digit product (digit 0 holds q_0)
-    digit_bits = q0_bits + (alpha - 1) * scale_bits
-    K = -(-(digit_bits + 1) // (p_bits - 1))
-    p = _primes_below(1 << p_bits, step, K, used)
+    # special primes = the largest primes below 2^p_bits; reserve 16 so `used` protects them, cut to K below
+    reserve = _primes_below(1 << p_bits, step, 16, used)
     q0 = _primes_below(1 << q0_bits, step, 1, used)[0]
     delta = float(1 << scale_bits)
+    hi = float(1 << top_bits)
+    cap = math.pow(2.0, 60.5)
     scales = [0.0] * nq
-    scales[levels] = delta
+    scales[levels] = hi if top_levels > 0 else delta
     q = [0] * nq
     q[0] = q0
     for l in range(levels, 0, -1):
-        target = scales[l] * scales[l] / delta
+        want = hi if (top_levels > 0 and l - 1 > levels - top_levels) else delta       # desired S_{l-1}
+        nxt = max(want, scales[l] * scales[l] / cap)
+        target = scales[l] * scales[l] / nxt
         q[l] = _prime_nearest(target, step, used)
         scales[l - 1] = scales[l] * scales[l] / float(q[l])
+    # P must dominate the widest key-switch digit (alpha consecutive limbs): sum of the limbs' bit lengths
+    digit_bits = max(sum(x.bit_length() for x in q[j:j + alpha]) for j in range(0, nq, alpha))
+    K = -(-(digit_bits + 1) // (p_bits - 1))
+    p = reserve[:K]
     return CKKSParams(logn=logn, q=q, p=p, scale_bits=scale_bits, alpha=alpha, hamming_weight=hamming_weight,
                       scales=scales, fresh_level=levels if fresh_level < 0 else min(fresh_level, levels))
 
