@@ -51,12 +51,12 @@ def test_bootstrap_precision_and_levels(boot_ctx):
     out = ctx.bootstrap(ctx.to_intt(ctx.encrypt(z)))
     assert out.level == eng._lib.ckks_bootstrap_out_level(eng._ptr) >= 5         # >= 5 after bootstrap
     err = np.abs(ctx.decrypt(out) - z).max()
-    assert err < 2e-3, err                  # stated tolerance: 9 bits worst case at N = 2^16
+    assert err < 1e-3, err                  # stated tolerance: 10 bits; measured 5.7e-4 at N = 2^16
     # the state encoding: ones everywhere, codewords on the stride grid
     v = np.ones(n, dtype=np.complex128)
     v[:: n // 16] = np.exp(-2j * np.pi * np.arange(16) / 16)
     err2 = np.abs(ctx.decrypt(ctx.bootstrap(ctx.encrypt(v))) - v).max()
-    assert err2 < 2e-3, err2
+    assert err2 < 1e-3, err2
     assert ctx.bootstrap_stats()["count"] == 2
 
 
