@@ -179,6 +179,7 @@ Engine::Engine(const Params& P) : prm(P) {
     const int nm = nmod();
     std::vector<ModConst> mc(nm);
     std::vector<u64> fwd((size_t)nm * n), fwd_s((size_t)nm * n), inv((size_t)nm * n), inv_s((size_t)nm * n);
+    std::vector<double> fwd_d((size_t)nm * n), fwd_q((size_t)nm * n), inv_d((size_t)nm * n), inv_q((size_t)nm * n);
     psi.resize(nm);
     Jroot.resize(nm);
     for (int i = 0; i < nm; i++) {
@@ -194,6 +195,8 @@ Engine::Engine(const Params& P) : prm(P) {
             const size_t k = bitrev_h(e, prm.logn);
             F[k] = pw; Fs[k] = shoup_h(pw, q);
             I[k] = ipw; Is[k] = shoup_h(ipw, q);
+            fwd_d[(size_t)i * n + k] = (double)pw;  fwd_q[(size_t)i * n + k] = (double)pw / (double)q;
+            inv_d[(size_t)i * n + k] = (double)ipw; inv_q[(size_t)i * n + k] = (double)ipw / (double)q;
             pw = mulmod_h(pw, psi[i], q);
             ipw = mulmod_h(ipw, ipsi, q);
         }
@@ -213,7 +216,8 @@ Engine::Engine(const Params& P) : prm(P) {
     d_inv = upload(this, inv, owned);
     d_inv_s = upload(this, inv_s, owned);
     d_mc = upload(this, mc, owned);
-    tabs = NttTables{d_fwd, d_fwd_s, d_inv, d_inv_s, d_mc, prm.logn};
+    tabs = NttTables{d_fwd, d_fwd_s, d_inv, d_inv_s, upload(this, fwd_d, owned), upload(this, fwd_q, owned),
+                     upload(this, inv_d, owned), upload(this, inv_q, owned), d_mc, prm.logn};
     ks = KShape{d_mc, prm.logn};
     // canonical-embedding tables (spec S9)
     const size_t M = 2 * n, ns = n / 2;

@@ -8,6 +8,11 @@ struct NttTables {
     const u64* fwd_s;
     const u64* inv;
     const u64* inv_s;
+    // FP64 path (scale primes): the same twiddles as doubles and their quotients by q
+    const double* fwd_d;
+    const double* fwd_q;
+    const double* inv_d;
+    const double* inv_q;
     const ModConst* mc;
     int logn;
 };

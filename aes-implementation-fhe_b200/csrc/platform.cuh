@@ -139,6 +139,8 @@ __device__ __forceinline__ double fmul_rn(double a, double b) { return __dmul_rn
 __device__ __forceinline__ double fadd_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double fsub_rn(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double fdiv_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double ffma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ double frint(double a) { return rint(a); }
 __device__ __forceinline__ u32 brev32(u32 x) { return __brev(x); }
 __device__ __forceinline__ int popc64(u64 x) { return __popcll(x); }
 __device__ __forceinline__ i64 d2ll_rn(double x) { return __double2ll_rn(x); }
@@ -224,6 +226,8 @@ static inline double fmul_rn(double a, double b) { return a * b; }   // built wi
 static inline double fadd_rn(double a, double b) { return a + b; }
 static inline double fsub_rn(double a, double b) { return a - b; }
 static inline double fdiv_rn(double a, double b) { return a / b; }
+static inline double ffma_rn(double a, double b, double c) { return fma(a, b, c); }     // exact single rounding (libm)
+static inline double frint(double a) { return nearbyint(a); }
 static inline u32 brev32(u32 x) {
     x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
     x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
