@@ -10,10 +10,14 @@
 // No transposition and no extra inter-pass twiddle multiply is needed in this formulation:
 // the bit-reversed table is self-similar, a radix-16 sub-transform rooted at table index X
 // uses entries (X << s) + g, s = 0..3 (forward) -- for N = 2^16: X = 1, 16+rh, 256+R, 4096+16R+jh
-// for the four register rounds.  Each thread keeps 16 coefficients in registers for 4 stages,
-// with ONE shared-memory exchange per pass.  Global accesses are 128-byte coalesced in both
-// passes; pass B stages its stores through shared memory (padded 1-in-16 so the 64-bit accesses
-// are bank-conflict free).
+// for the four register rounds.  Each thread keeps 16 coefficients in registers for 4 stages.
+//
+// Memory staging.  Pass A needs table entries 1..255 only (the same for every CTA of a limb): its data tile and those
+// twiddles are copied with cp.async (LDGSTS) in the first instructions of the kernel and the arithmetic runs from shared
+// memory (no global latency inside the butterfly stages; 39 -> 34.5 us on 126 limbs).  Pass B needs 15 twiddle pairs
+// per sixteen-element group, 61 KB per tile: staging them too was measured (100 KB of shared memory per CTA, two CTAs
+// per SM: 54 -> 57 us on 126 limbs, and slower inside the AES step where other lanes' kernels share the SMs), so pass
+// B reads its twiddles from the global tables, a pair per 128-bit load (profiles/README.md, NTT v2).
 //
 // Two arithmetic paths, chosen per limb (a CTA works on one limb, so the choice is uniform):
 //   * integer path (the 60/61-bit moduli q_0 and the special primes): Harvey lazy butterflies with Shoup
@@ -22,40 +26,95 @@
 //   * FP64 path (the ~2^50 scale primes, q < 1.4 * 2^50): coefficients are held as exact integers in doubles and
 //     multiplied with two DMUL, two DFMA, one rounding and one add (error-free product + quotient estimate):
 //     measured 7.70 modmul/clk/SM, on the FP64 pipe, which the integer path leaves idle.  Values stay two-sided
-//     lazy (|x| < 2^53) and are folded to |x| <= q/2 every two stages.  Every operation is exact, so the
+//     lazy (|x| < 2^53) and are folded to |x| <= q/2 once per radix-16 block.  Every operation is exact, so the
 //     canonical output is bit-identical to the integer path and to the oracle.
 //
-// Algorithmic bytes: 2*N*8 = 1 MiB per limb-NTT at N = 2^16; measured DRAM traffic is 1.63x that
-// (the twiddle tables are as large as the data).
+// Algorithmic bytes: 2*N*8 = 1 MiB per limb-NTT at N = 2^16.
 #include "ntt.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-#ifndef NTT_MIN_BLOCKS
-#define NTT_MIN_BLOCKS 3      // register cap 80, no spills; measured best of {2,3,4,5} (profiles/r1_ntt_occupancy_sweep.txt)
+#ifndef NTT_MIN_BLOCKS_A
+#define NTT_MIN_BLOCKS_A 3    // pass A: 37 KB static shared memory, register cap 80
+#endif
+#ifndef NTT_MIN_BLOCKS_B
+#define NTT_MIN_BLOCKS_B 3    // pass B: 35 KB static shared memory, register cap 80
 #endif
 #ifndef NTT_FP64
 #define NTT_FP64 1            // 0: every limb takes the integer path (A/B measurement)
 #endif
-// FP64 path bound: |x| < 4.6 q must stay below 2^53
+// FP64 path bound: |x| < 5.1 q must stay below 2^53
 #define NTT_FP_LIMIT 1576258512130867ull     /* 1.4 * 2^50 */
 
 __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
 __device__ __forceinline__ bool use_fp(u64 q) { return NTT_FP64 && q < NTT_FP_LIMIT; }
+// lazy doubles travel between the two passes (and through shared memory) in u64 words as raw bits
+__device__ __forceinline__ u64 d2bits(double x) { union { double d; u64 u; } c; c.d = x; return c.u; }
+__device__ __forceinline__ double bits2d(u64 x) { union { double d; u64 u; } c; c.u = x; return c.d; }
+
+struct alignas(16) u64x2 { u64 a, b; };
+
+// ============================================================================================ twiddle accessors
+// A radix-16 block rooted at table index X needs, for r = 0..3, the 2^r entries (X << r) + g.  get(r, g) returns the
+// twiddle and its companion (Shoup word / quotient by q) as raw 64-bit words; get2 returns the pair g = 2 gh, 2 gh + 1.
+//
+// TwLin: a linear shared-memory copy.  MODE 0: entries 1..255 stored at [e - 1], block X = 1;  MODE 1: the same copy,
+// blocks X = 16 + xl;  MODE 2: the four ranges of 16 consecutive blocks stored back to back (16, 32, 64, 128 entries).
+template <int MODE>
+__device__ __forceinline__ int tw_base(int r) {
+    return MODE == 0 ? (1 << r) - 1 : MODE == 1 ? (16 << r) - 1 : (16 << r) - 16;
+}
+template <int MODE>
+struct TwLin {
+    const u64* W;
+    const u64* C;
+    u32 xl;
+    DEV_MEMBER void get(int r, int g, u64& w, u64& c) const {
+        const int i = tw_base<MODE>(r) + (int)(xl << r) + g;
+        w = W[i];
+        c = C[i];
+    }
+    DEV_MEMBER void get2(int r, int gh, u64& w0, u64& c0, u64& w1, u64& c1) const {
+        get(r, 2 * gh, w0, c0);
+        get(r, 2 * gh + 1, w1, c1);
+    }
+};
+// TwGlobal: straight from the global table (read-only path), pairs as one 128-bit load.  Used by pass B, whose
+// per-thread twiddles (61 KB per tile) would cost a third of the resident CTAs if they were staged.
+struct TwGlobal {
+    const u64* W;
+    const u64* C;
+    u32 X;
+    DEV_MEMBER void get(int r, int g, u64& w, u64& c) const {
+        w = ldg(W + (X << r) + g);
+        c = ldg(C + (X << r) + g);
+    }
+    DEV_MEMBER void get2(int r, int gh, u64& w0, u64& c0, u64& w1, u64& c1) const {
+        ldg_pair(W + (X << r) + 2 * gh, w0, w1);
+        ldg_pair(C + (X << r) + 2 * gh, c0, c1);
+    }
+};
+template <typename TW>
+__device__ __forceinline__ void tw_stage(const TW& tw, int r, u64 (&w)[8], u64 (&c)[8]) {
+    if (r == 0) tw.get(0, 0, w[0], c[0]);
+#pragma unroll
+    for (int gh = 0; gh < 4; gh++)
+        if (r > 0 && 2 * gh < (1 << r)) tw.get2(r, gh, w[2 * gh], c[2 * gh], w[2 * gh + 1], c[2 * gh + 1]);
+}
+
+constexpr int kPassBData = 16 * 256 + 16 * 16;                   // pass B tile in the pad16 layout
 
 // ============================================================================================ integer path
-// Forward radix-16 block rooted at table index X: 4 CT stages on x[0..15], lazy in [0,4q).
-__device__ __forceinline__ void fwd16(u64 (&x)[16], u32 X, const u64* __restrict__ W, const u64* __restrict__ Ws,
-                                      u64 q) {
+// Forward radix-16 block: 4 CT stages on x[0..15], lazy in [0,4q).
+template <typename TW>
+__device__ __forceinline__ void fwd16(u64 (&x)[16], const TW& tw, u64 q) {
     const u64 q2 = 2 * q;
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         const int span = 8 >> s;
         u64 w[8], ws[8];
-#pragma unroll
-        for (int g = 0; g < 8; g++)
-            if (g < (1 << s)) { w[g] = ldg(W + (X << s) + g); ws[g] = ldg(Ws + (X << s) + g); }
+        tw_stage(tw, s, w, ws);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int g = i / span, k0 = g * 2 * span + (i % span), k1 = k0 + span;
@@ -68,22 +127,17 @@ __device__ __forceinline__ void fwd16(u64 (&x)[16], u32 X, const u64* __restrict
     }
 }
 
-// Inverse radix-16 block rooted at X: 4 GS stages, values kept in [0,2q).
+// Inverse radix-16 block: 4 GS stages, values kept in [0,2q).
 // If FINAL, the last stage folds in N^-1 (scaling the sum by ninv and the twiddle by ninv).
-template <bool FINAL>
-__device__ __forceinline__ void inv16(u64 (&x)[16], u32 X, const u64* __restrict__ W, const u64* __restrict__ Ws,
-                                      u64 q, u64 ninv, u64 ninv_s, u64 w1n, u64 w1n_s) {
+template <bool FINAL, typename TW>
+__device__ __forceinline__ void inv16(u64 (&x)[16], const TW& tw, u64 q, u64 ninv, u64 ninv_s, u64 w1n, u64 w1n_s) {
     const u64 q2 = 2 * q;
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         const int span = 1 << s;
         u64 w[8], ws[8];
-#pragma unroll
-        for (int g = 0; g < 8; g++)
-            if (g < (8 >> s)) {
-                if (FINAL && s == 3) { w[g] = w1n; ws[g] = w1n_s; }
-                else { w[g] = ldg(W + (X << (3 - s)) + g); ws[g] = ldg(Ws + (X << (3 - s)) + g); }
-            }
+        if (FINAL && s == 3) { w[0] = w1n; ws[0] = w1n_s; }
+        else tw_stage(tw, 3 - s, w, ws);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int g = i / span, k0 = g * 2 * span + (i % span), k1 = k0 + span;
@@ -128,49 +182,42 @@ struct FpMod {
     double q, qinv, ninv, ninvq, w1n, w1nq;
 };
 
-// Forward radix-16 block, 4 CT stages.  In: |x| <= 0.51 q.  Out: |x| < 4.6 q after two stages, folded, then again:
-// the caller receives |x| < 4.6 q (lazy) -- two folds per block keep everything below 2^53.
-__device__ __forceinline__ void fwd16_fp(double (&x)[16], u32 X, const double* __restrict__ W,
-                                         const double* __restrict__ Wq, const FpMod& m) {
+// Forward radix-16 block, 4 CT stages.  In: |x| <= 0.51 q.  A product of an input |a| = m q comes back with
+// |r| <= (0.5 + m q 2^-52) q (the quotient estimate is off by |a| 2^-52 at most), so the lazy values grow as
+// 0.51 -> 1.2 -> 2.2 -> 3.4 -> 5.02 q at q = 1.4 * 2^50 (tools/ntt_fp_bounds.py): below 2^53 = 5.71 q without any fold
+// inside the block.  The caller folds once per block.
+template <typename TW>
+__device__ __forceinline__ void fwd16_fp(double (&x)[16], const TW& tw, const FpMod& m) {
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         const int span = 8 >> s;
-        if (s == 2) {
-#pragma unroll
-            for (int k = 0; k < 16; k++) x[k] = fold_fp(x[k], m.q, m.qinv);
-        }
-        double w[8], wq[8];
-#pragma unroll
-        for (int g = 0; g < 8; g++)
-            if (g < (1 << s)) { w[g] = ldg(W + (X << s) + g); wq[g] = ldg(Wq + (X << s) + g); }
+        u64 w[8], wq[8];
+        tw_stage(tw, s, w, wq);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int g = i / span, k0 = g * 2 * span + (i % span), k1 = k0 + span;
             const double u = x[k0];
-            const double v = modmul_fp(x[k1], w[g], wq[g], m.q);
+            const double v = modmul_fp(x[k1], bits2d(w[g]), bits2d(wq[g]), m.q);
             x[k0] = fadd_rn(u, v);
             x[k1] = fsub_rn(u, v);
         }
     }
 }
-// Inverse radix-16 block, 4 GS stages.  In: |x| <= 0.51 q; sums double per stage, so fold after two stages.
-template <bool FINAL>
-__device__ __forceinline__ void inv16_fp(double (&x)[16], u32 X, const double* __restrict__ W,
-                                         const double* __restrict__ Wq, const FpMod& m) {
+// Inverse radix-16 block, 4 GS stages.  In: |x| <= 0.51 q.  Only the pure-sum paths double per stage: before the last
+// stage x[0], x[8] hold up to 4.08 q and x[1], x[9] up to 3.5 q, everything else is a product or a sum of products.
+// Folding those four keeps every intermediate below 4.9 q < 2^53 at q = 1.4 * 2^50 (tools/ntt_fp_bounds.py).
+template <bool FINAL, typename TW>
+__device__ __forceinline__ void inv16_fp(double (&x)[16], const TW& tw, const FpMod& m) {
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         const int span = 1 << s;
-        if (s == 2) {
-#pragma unroll
-            for (int k = 0; k < 16; k++) x[k] = fold_fp(x[k], m.q, m.qinv);
+        if (s == 3) {
+            x[0] = fold_fp(x[0], m.q, m.qinv); x[8] = fold_fp(x[8], m.q, m.qinv);
+            x[1] = fold_fp(x[1], m.q, m.qinv); x[9] = fold_fp(x[9], m.q, m.qinv);
         }
-        double w[8], wq[8];
-#pragma unroll
-        for (int g = 0; g < 8; g++)
-            if (g < (8 >> s)) {
-                if (FINAL && s == 3) { w[g] = m.w1n; wq[g] = m.w1nq; }
-                else { w[g] = ldg(W + (X << (3 - s)) + g); wq[g] = ldg(Wq + (X << (3 - s)) + g); }
-            }
+        u64 w[8], wq[8];
+        if (FINAL && s == 3) { w[0] = d2bits(m.w1n); wq[0] = d2bits(m.w1nq); }
+        else tw_stage(tw, 3 - s, w, wq);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int g = i / span, k0 = g * 2 * span + (i % span), k1 = k0 + span;
@@ -178,7 +225,7 @@ __device__ __forceinline__ void inv16_fp(double (&x)[16], u32 X, const double* _
             double sum = fadd_rn(u, v);
             if (FINAL && s == 3) sum = modmul_fp(sum, m.ninv, m.ninvq, m.q);
             x[k0] = sum;
-            x[k1] = modmul_fp(fsub_rn(u, v), w[g], wq[g], m.q);
+            x[k1] = modmul_fp(fsub_rn(u, v), bits2d(w[g]), bits2d(wq[g]), m.q);
         }
     }
 }
@@ -193,91 +240,110 @@ __device__ __forceinline__ FpMod fp_mod(const ModConst& mc) {
     m.w1nq = fdiv_rn(m.w1n, m.q);
     return m;
 }
-// lazy doubles travel between the two passes in the u64 buffer as raw bits
-__device__ __forceinline__ u64 d2bits(double x) { union { double d; u64 u; } c; c.d = x; return c.u; }
-__device__ __forceinline__ double bits2d(u64 x) { union { double d; u64 u; } c; c.u = x; return c.d; }
 
 // ============================================================================================ forward, pass A
 // LOGR = 8: R = 256 rows, tile = 16 columns x 256 rows, two radix-16 rounds (X = 1, then 16 + rr).
 // LOGR = 4: R = 16 rows,  tile = 256 columns x 16 rows, one radix-16 round (X = 1).
+// Shared memory: 4096 data words ([row][16 columns] / [k][256 columns]) + table entries 1..255 and their companions.
+constexpr int kPassAWords = 4096 + 2 * 256;
 template <int LOGR, bool FP>
 __device__ __forceinline__ void fwd_passA_body(const u64* __restrict__ src, u64* __restrict__ dst, u64* sm, int limb,
                                                int slimb, int tile, size_t N, const ModConst& mc, const NttTables& T,
                                                int mod) {
     constexpr int RG = (1 << LOGR) / 16;          // row groups per column: 16 or 1
     constexpr int TC = kThreads / RG;             // columns per CTA: 16 or 256
+    constexpr int NTW = LOGR == 8 ? 255 : 15;
     const u64 q = mc.q;
-    const u64* W = T.fwd + (size_t)mod * N;
-    const u64* Ws = T.fwd_s + (size_t)mod * N;
-    const double* Wd = T.fwd_d + (size_t)mod * N;
-    const double* Wq = T.fwd_q + (size_t)mod * N;
+    const u64* W = (FP ? reinterpret_cast<const u64*>(T.fwd_d) : T.fwd) + (size_t)mod * N;
+    const u64* C = (FP ? reinterpret_cast<const u64*>(T.fwd_q) : T.fwd_s) + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
-    double* smd = reinterpret_cast<double*>(sm);
+    u64* sd = sm;
+    u64* tw = sm + 4096;
+    u64* tc = tw + 256;
+    FOR_THREADS {
+        const int tid = threadIdx.x;
+        if (tid < NTW) { cp_async8(tw + tid, W + 1 + tid); cp_async8(tc + tid, C + 1 + tid); }
+        if (LOGR == 8) {
+            const int c = tid % TC, rr = tid / TC;
+            const u64* s0 = src + (size_t)slimb * N + tile * TC + c;
+#pragma unroll
+            for (int k = 0; k < 16; k++) cp_async8(sd + (rr + 16 * k) * TC + c, s0 + (size_t)(rr + 16 * k) * 256);
+        } else {
+            const u64* s0 = src + (size_t)slimb * N + tid;
+#pragma unroll
+            for (int k = 0; k < 16; k++) cp_async8(sd + k * 256 + tid, s0 + (size_t)k * 256);
+        }
+        cp_async_wait_all();
+    }
+    BLOCK_SYNC;
     if (LOGR == 8) {
         FOR_THREADS {
             const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
-            const size_t sbase = (size_t)slimb * N + tile * TC + c;
+            const TwLin<0> t1{tw, tc, 0u};
             if (FP) {
                 double x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = ull2d_rn(src[sbase + (size_t)(rr + 16 * k) * 256]);
-                fwd16_fp(x, 1u, Wd, Wq, fm);
+                for (int k = 0; k < 16; k++) x[k] = ull2d_rn(sd[(rr + 16 * k) * TC + c]);
+                fwd16_fp(x, t1, fm);
 #pragma unroll
-                for (int k = 0; k < 16; k++) smd[(rr + 16 * k) * TC + c] = fold_fp(x[k], fm.q, fm.qinv);
+                for (int k = 0; k < 16; k++) sd[(rr + 16 * k) * TC + c] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
             } else {
                 u64 x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = src[sbase + (size_t)(rr + 16 * k) * 256];
-                fwd16(x, 1u, W, Ws, q);
+                for (int k = 0; k < 16; k++) x[k] = sd[(rr + 16 * k) * TC + c];
+                fwd16(x, t1, q);
 #pragma unroll
-                for (int k = 0; k < 16; k++) sm[(rr + 16 * k) * TC + c] = x[k];
+                for (int k = 0; k < 16; k++) sd[(rr + 16 * k) * TC + c] = x[k];
             }
         }
         BLOCK_SYNC;
         FOR_THREADS {
             const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
-            const size_t base = (size_t)limb * N + tile * TC + c;
+            const TwLin<1> t2{tw, tc, (u32)rr};
+            u64* d0 = dst + (size_t)limb * N + tile * TC + c;
             if (FP) {
                 double x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = smd[(16 * rr + k) * TC + c];
-                fwd16_fp(x, 16u + rr, Wd, Wq, fm);
+                for (int k = 0; k < 16; k++) x[k] = bits2d(sd[(16 * rr + k) * TC + c]);
+                fwd16_fp(x, t2, fm);
 #pragma unroll
-                for (int k = 0; k < 16; k++) dst[base + (size_t)(16 * rr + k) * 256] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+                for (int k = 0; k < 16; k++) d0[(size_t)(16 * rr + k) * 256] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
             } else {
                 u64 x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = sm[(16 * rr + k) * TC + c];
-                fwd16(x, 16u + rr, W, Ws, q);
+                for (int k = 0; k < 16; k++) x[k] = sd[(16 * rr + k) * TC + c];
+                fwd16(x, t2, q);
 #pragma unroll
-                for (int k = 0; k < 16; k++) dst[base + (size_t)(16 * rr + k) * 256] = x[k];   // lazy [0,4q)
+                for (int k = 0; k < 16; k++) d0[(size_t)(16 * rr + k) * 256] = x[k];   // lazy [0,4q)
             }
         }
     } else {
         FOR_THREADS {
-            const size_t base = (size_t)limb * N + threadIdx.x, sbase = (size_t)slimb * N + threadIdx.x;
+            const int tid = threadIdx.x;
+            const TwLin<0> t1{tw, tc, 0u};
+            u64* d0 = dst + (size_t)limb * N + tid;
             if (FP) {
                 double x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = ull2d_rn(src[sbase + (size_t)k * 256]);
-                fwd16_fp(x, 1u, Wd, Wq, fm);
+                for (int k = 0; k < 16; k++) x[k] = ull2d_rn(sd[k * 256 + tid]);
+                fwd16_fp(x, t1, fm);
 #pragma unroll
-                for (int k = 0; k < 16; k++) dst[base + (size_t)k * 256] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+                for (int k = 0; k < 16; k++) d0[(size_t)k * 256] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
             } else {
                 u64 x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = src[sbase + (size_t)k * 256];
-                fwd16(x, 1u, W, Ws, q);
+                for (int k = 0; k < 16; k++) x[k] = sd[k * 256 + tid];
+                fwd16(x, t1, q);
 #pragma unroll
-                for (int k = 0; k < 16; k++) dst[base + (size_t)k * 256] = x[k];
+                for (int k = 0; k < 16; k++) d0[(size_t)k * 256] = x[k];
             }
         }
     }
 }
 template <int LOGR>
-__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_A)
 ntt_fwd_passA(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
-    CKKS_SHARED u64 sm[LOGR == 8 ? 256 * 16 : 1];
+    CKKS_SHARED __align__(16) u64 sm[kPassAWords];
     if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
     const int limb = J.rows[blockIdx.z][blockIdx.y], slimb = J.srows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
     const int mod = J.mods[blockIdx.z][blockIdx.y];
@@ -290,32 +356,31 @@ ntt_fwd_passA(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CON
 }
 
 // ============================================================================================ forward, pass B
-// 16 rows of 256 per CTA; row with global index Rg is rooted at table index R + Rg.
+// 16 rows of 256 per CTA; row with global index Rg is rooted at table index R_n + Rg.  Data goes global -> registers,
+// the twiddles come from the global tables (128-bit pair loads); one shared-memory exchange between the two rounds and
+// one to make the final store coalesced.
 template <bool FP>
 __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int tile, u32 Rn, const ModConst& mc,
                                                const NttTables& T, int mod, size_t N) {
     const u64 q = mc.q;
-    const u64* W = T.fwd + (size_t)mod * N;
-    const u64* Ws = T.fwd_s + (size_t)mod * N;
-    const double* Wd = T.fwd_d + (size_t)mod * N;
-    const double* Wq = T.fwd_q + (size_t)mod * N;
+    const u64* W = (FP ? reinterpret_cast<const u64*>(T.fwd_d) : T.fwd) + (size_t)mod * N;
+    const u64* C = (FP ? reinterpret_cast<const u64*>(T.fwd_q) : T.fwd_s) + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
-    double* smd = reinterpret_cast<double*>(sm);
     FOR_THREADS {
         const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
-        const u32 R = tile * 16 + row;
+        const TwGlobal t1{W, C, Rn + (u32)(tile * 16 + row)};
         if (FP) {
             double x[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) x[k] = bits2d(g[row * 256 + jj + 16 * k]);
-            fwd16_fp(x, Rn + R, Wd, Wq, fm);
+            fwd16_fp(x, t1, fm);
 #pragma unroll
-            for (int k = 0; k < 16; k++) smd[pad16(row * 256 + jj + 16 * k)] = fold_fp(x[k], fm.q, fm.qinv);
+            for (int k = 0; k < 16; k++) sm[pad16(row * 256 + jj + 16 * k)] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
         } else {
             u64 x[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) x[k] = g[row * 256 + jj + 16 * k];
-            fwd16(x, Rn + R, W, Ws, q);
+            fwd16(x, t1, q);
 #pragma unroll
             for (int k = 0; k < 16; k++) sm[pad16(row * 256 + jj + 16 * k)] = x[k];
         }
@@ -323,20 +388,20 @@ __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int
     BLOCK_SYNC;
     FOR_THREADS {
         const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
-        const u32 R = tile * 16 + row;
+        const TwGlobal t2{W, C, 16u * (Rn + (u32)(tile * 16 + row)) + (u32)jj};
         // each thread rewrites exactly the 16 slots it just read, so no barrier is needed before this store
         if (FP) {
             double x[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) x[k] = smd[pad16(row * 256 + 16 * jj + k)];
-            fwd16_fp(x, 16u * (Rn + R) + jj, Wd, Wq, fm);
+            for (int k = 0; k < 16; k++) x[k] = bits2d(sm[pad16(row * 256 + 16 * jj + k)]);
+            fwd16_fp(x, t2, fm);
 #pragma unroll
             for (int k = 0; k < 16; k++) sm[pad16(row * 256 + 16 * jj + k)] = canon_fp(x[k], fm.q, fm.qinv);
         } else {
             u64 x[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) x[k] = sm[pad16(row * 256 + 16 * jj + k)];
-            fwd16(x, 16u * (Rn + R) + jj, W, Ws, q);
+            fwd16(x, t2, q);
 #pragma unroll
             for (int k = 0; k < 16; k++) sm[pad16(row * 256 + 16 * jj + k)] = canon4(x[k], q);
         }
@@ -347,9 +412,9 @@ __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int
         for (int k = 0; k < 16; k++) g[k * 256 + threadIdx.x] = sm[pad16(k * 256 + threadIdx.x)];
     }
 }
-__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_B)
 ntt_fwd_passB(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
-    CKKS_SHARED u64 sm[16 * 256 + 16 * 16];
+    CKKS_SHARED u64 sm[kPassBData];
     if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
     const int limb = J.rows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
     const int mod = J.mods[blockIdx.z][blockIdx.y];
@@ -367,32 +432,30 @@ template <bool FP>
 __device__ __forceinline__ void inv_passB_body(const u64* __restrict__ s_in, u64* __restrict__ d_out, u64* sm, int tile,
                                                u32 Rn, const ModConst& mc, const NttTables& T, int mod, size_t N) {
     const u64 q = mc.q;
-    const u64* W = T.inv + (size_t)mod * N;
-    const u64* Ws = T.inv_s + (size_t)mod * N;
-    const double* Wd = T.inv_d + (size_t)mod * N;
-    const double* Wq = T.inv_q + (size_t)mod * N;
+    const u64* W = (FP ? reinterpret_cast<const u64*>(T.inv_d) : T.inv) + (size_t)mod * N;
+    const u64* C = (FP ? reinterpret_cast<const u64*>(T.inv_q) : T.inv_s) + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
-    double* smd = reinterpret_cast<double*>(sm);
     FOR_THREADS {
 #pragma unroll
-        for (int k = 0; k < 16; k++) sm[pad16(k * 256 + threadIdx.x)] = s_in[k * 256 + threadIdx.x];
+        for (int k = 0; k < 16; k++) cp_async8(sm + pad16(k * 256 + threadIdx.x), s_in + k * 256 + threadIdx.x);
+        cp_async_wait_all();
     }
     BLOCK_SYNC;
     FOR_THREADS {
         const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
-        const u32 R = tile * 16 + row;
+        const TwGlobal t2{W, C, 16u * (Rn + (u32)(tile * 16 + row)) + (u32)jj};
         if (FP) {
             double x[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) x[k] = ull2d_rn(sm[pad16(row * 256 + 16 * jj + k)]);
-            inv16_fp<false>(x, 16u * (Rn + R) + jj, Wd, Wq, fm);
+            inv16_fp<false>(x, t2, fm);
 #pragma unroll
-            for (int k = 0; k < 16; k++) smd[pad16(row * 256 + 16 * jj + k)] = fold_fp(x[k], fm.q, fm.qinv);
+            for (int k = 0; k < 16; k++) sm[pad16(row * 256 + 16 * jj + k)] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
         } else {
             u64 x[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) x[k] = sm[pad16(row * 256 + 16 * jj + k)];
-            inv16<false>(x, 16u * (Rn + R) + jj, W, Ws, q, 0, 0, 0, 0);
+            inv16<false>(x, t2, q, 0, 0, 0, 0);
 #pragma unroll
             for (int k = 0; k < 16; k++) sm[pad16(row * 256 + 16 * jj + k)] = x[k];
         }
@@ -400,27 +463,27 @@ __device__ __forceinline__ void inv_passB_body(const u64* __restrict__ s_in, u64
     BLOCK_SYNC;
     FOR_THREADS {
         const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
-        const u32 R = tile * 16 + row;
+        const TwGlobal t1{W, C, Rn + (u32)(tile * 16 + row)};
         if (FP) {
             double x[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) x[k] = smd[pad16(row * 256 + jj + 16 * k)];
-            inv16_fp<false>(x, Rn + R, Wd, Wq, fm);
+            for (int k = 0; k < 16; k++) x[k] = bits2d(sm[pad16(row * 256 + jj + 16 * k)]);
+            inv16_fp<false>(x, t1, fm);
 #pragma unroll
             for (int k = 0; k < 16; k++) d_out[row * 256 + jj + 16 * k] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
         } else {
             u64 x[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) x[k] = sm[pad16(row * 256 + jj + 16 * k)];
-            inv16<false>(x, Rn + R, W, Ws, q, 0, 0, 0, 0);
+            inv16<false>(x, t1, q, 0, 0, 0, 0);
 #pragma unroll
             for (int k = 0; k < 16; k++) d_out[row * 256 + jj + 16 * k] = x[k];       // lazy [0,2q)
         }
     }
 }
-__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_B)
 ntt_inv_passB(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
-    CKKS_SHARED u64 sm[16 * 256 + 16 * 16];
+    CKKS_SHARED u64 sm[kPassBData];
     if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
     const int limb = J.rows[blockIdx.z][blockIdx.y], slimb = J.srows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
     const int mod = J.mods[blockIdx.z][blockIdx.y];
@@ -441,78 +504,98 @@ __device__ __forceinline__ void inv_passA_body(u64* __restrict__ data, u64* sm, 
                                                const ModConst& mc, const NttTables& T, int mod) {
     constexpr int RG = (1 << LOGR) / 16;
     constexpr int TC = kThreads / RG;
+    constexpr int NTW = LOGR == 8 ? 255 : 15;
     const u64 q = mc.q;
-    const u64* W = T.inv + (size_t)mod * N;
-    const u64* Ws = T.inv_s + (size_t)mod * N;
-    const double* Wd = T.inv_d + (size_t)mod * N;
-    const double* Wq = T.inv_q + (size_t)mod * N;
+    const u64* W = (FP ? reinterpret_cast<const u64*>(T.inv_d) : T.inv) + (size_t)mod * N;
+    const u64* C = (FP ? reinterpret_cast<const u64*>(T.inv_q) : T.inv_s) + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
-    double* smd = reinterpret_cast<double*>(sm);
+    u64* sd = sm;
+    u64* tw = sm + 4096;
+    u64* tc = tw + 256;
+    FOR_THREADS {
+        const int tid = threadIdx.x;
+        if (tid < NTW) { cp_async8(tw + tid, W + 1 + tid); cp_async8(tc + tid, C + 1 + tid); }
+        if (LOGR == 8) {
+            const int c = tid % TC, rr = tid / TC;
+            const u64* s0 = data + (size_t)limb * N + tile * TC + c;
+#pragma unroll
+            for (int k = 0; k < 16; k++) cp_async8(sd + (16 * rr + k) * TC + c, s0 + (size_t)(16 * rr + k) * 256);
+        } else {
+            const u64* s0 = data + (size_t)limb * N + tid;
+#pragma unroll
+            for (int k = 0; k < 16; k++) cp_async8(sd + k * 256 + tid, s0 + (size_t)k * 256);
+        }
+        cp_async_wait_all();
+    }
+    BLOCK_SYNC;
     if (LOGR == 8) {
         FOR_THREADS {
             const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
-            const size_t base = (size_t)limb * N + tile * TC + c;
+            const TwLin<1> t2{tw, tc, (u32)rr};
             if (FP) {
                 double x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = bits2d(data[base + (size_t)(16 * rr + k) * 256]);
-                inv16_fp<false>(x, 16u + rr, Wd, Wq, fm);
+                for (int k = 0; k < 16; k++) x[k] = bits2d(sd[(16 * rr + k) * TC + c]);
+                inv16_fp<false>(x, t2, fm);
 #pragma unroll
-                for (int k = 0; k < 16; k++) smd[(16 * rr + k) * TC + c] = fold_fp(x[k], fm.q, fm.qinv);
+                for (int k = 0; k < 16; k++) sd[(16 * rr + k) * TC + c] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
             } else {
                 u64 x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = data[base + (size_t)(16 * rr + k) * 256];
-                inv16<false>(x, 16u + rr, W, Ws, q, 0, 0, 0, 0);
+                for (int k = 0; k < 16; k++) x[k] = sd[(16 * rr + k) * TC + c];
+                inv16<false>(x, t2, q, 0, 0, 0, 0);
 #pragma unroll
-                for (int k = 0; k < 16; k++) sm[(16 * rr + k) * TC + c] = x[k];
+                for (int k = 0; k < 16; k++) sd[(16 * rr + k) * TC + c] = x[k];
             }
         }
         BLOCK_SYNC;
         FOR_THREADS {
             const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
-            const size_t base = (size_t)limb * N + tile * TC + c;
+            const TwLin<0> t1{tw, tc, 0u};
+            u64* d0 = data + (size_t)limb * N + tile * TC + c;
             if (FP) {
                 double x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = smd[(rr + 16 * k) * TC + c];
-                inv16_fp<true>(x, 1u, Wd, Wq, fm);
+                for (int k = 0; k < 16; k++) x[k] = bits2d(sd[(rr + 16 * k) * TC + c]);
+                inv16_fp<true>(x, t1, fm);
 #pragma unroll
-                for (int k = 0; k < 16; k++) data[base + (size_t)(rr + 16 * k) * 256] = canon_fp(x[k], fm.q, fm.qinv);
+                for (int k = 0; k < 16; k++) d0[(size_t)(rr + 16 * k) * 256] = canon_fp(x[k], fm.q, fm.qinv);
             } else {
                 u64 x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = sm[(rr + 16 * k) * TC + c];
-                inv16<true>(x, 1u, W, Ws, q, mc.ninv, mc.ninv_s, mc.w1n, mc.w1n_s);
+                for (int k = 0; k < 16; k++) x[k] = sd[(rr + 16 * k) * TC + c];
+                inv16<true>(x, t1, q, mc.ninv, mc.ninv_s, mc.w1n, mc.w1n_s);
 #pragma unroll
-                for (int k = 0; k < 16; k++) data[base + (size_t)(rr + 16 * k) * 256] = canon2(x[k], q);
+                for (int k = 0; k < 16; k++) d0[(size_t)(rr + 16 * k) * 256] = canon2(x[k], q);
             }
         }
     } else {
         FOR_THREADS {
-            const size_t base = (size_t)limb * N + threadIdx.x;
+            const int tid = threadIdx.x;
+            const TwLin<0> t1{tw, tc, 0u};
+            u64* d0 = data + (size_t)limb * N + tid;
             if (FP) {
                 double x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = bits2d(data[base + (size_t)k * 256]);
-                inv16_fp<true>(x, 1u, Wd, Wq, fm);
+                for (int k = 0; k < 16; k++) x[k] = bits2d(sd[k * 256 + tid]);
+                inv16_fp<true>(x, t1, fm);
 #pragma unroll
-                for (int k = 0; k < 16; k++) data[base + (size_t)k * 256] = canon_fp(x[k], fm.q, fm.qinv);
+                for (int k = 0; k < 16; k++) d0[(size_t)k * 256] = canon_fp(x[k], fm.q, fm.qinv);
             } else {
                 u64 x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = data[base + (size_t)k * 256];
-                inv16<true>(x, 1u, W, Ws, q, mc.ninv, mc.ninv_s, mc.w1n, mc.w1n_s);
+                for (int k = 0; k < 16; k++) x[k] = sd[k * 256 + tid];
+                inv16<true>(x, t1, q, mc.ninv, mc.ninv_s, mc.w1n, mc.w1n_s);
 #pragma unroll
-                for (int k = 0; k < 16; k++) data[base + (size_t)k * 256] = canon2(x[k], q);
+                for (int k = 0; k < 16; k++) d0[(size_t)k * 256] = canon2(x[k], q);
             }
         }
     }
 }
 template <int LOGR>
-__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_A)
 ntt_inv_passA(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
-    CKKS_SHARED u64 sm[LOGR == 8 ? 256 * 16 : 1];
+    CKKS_SHARED __align__(16) u64 sm[kPassAWords];
     if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
     const int limb = J.rows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
     const int mod = J.mods[blockIdx.z][blockIdx.y];

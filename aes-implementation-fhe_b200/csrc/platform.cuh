@@ -48,6 +48,32 @@ struct LaunchTimer {
 #endif
 #define CKKS_SHARED __shared__
 #define GRID_CONST __grid_constant__
+#define DEV_MEMBER __device__ __forceinline__      // member functions of device-side helper structs
+// dynamic shared memory (kernels that need more than the 48 KB static limit): one 16-byte aligned array per kernel
+#define DYN_SHARED_U64(name, words) extern __shared__ __align__(16) u64 name[]
+template <typename K>
+inline void dyn_smem_optin(K kern, size_t bytes) {
+    // once per (kernel, device)
+    static thread_local struct { const void* k; int dev; } done[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (auto& d : done) {
+        if (d.k == (const void*)kern && d.dev == dev) return;
+        if (!d.k) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+                throw std::runtime_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+            d.k = (const void*)kern;
+            d.dev = dev;
+            return;
+        }
+    }
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+#ifdef CKKS_TIME_LAUNCHES
+#define LAUNCH_DYN(kern, grid, block, smem, stream, ...) do { LaunchTimer _lt; dyn_smem_optin(kern, smem); ++g_launch_count; kern<<<grid, block, smem, stream>>>(__VA_ARGS__); } while (0)
+#else
+#define LAUNCH_DYN(kern, grid, block, smem, stream, ...) (dyn_smem_optin(kern, smem), ++g_launch_count, kern<<<grid, block, smem, stream>>>(__VA_ARGS__))
+#endif
 
 #define CUDA_CHECK(expr)                                                                          \
     do {                                                                                          \
@@ -147,6 +173,20 @@ __device__ __forceinline__ i64 d2ll_rn(double x) { return __double2ll_rn(x); }
 __device__ __forceinline__ double ull2d_rn(u64 x) { return __ull2double_rn(x); }
 template <typename T>
 __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+// two consecutive 64-bit words (16-byte aligned) through the read-only path as one 128-bit load
+__device__ __forceinline__ void ldg_pair(const u64* p, u64& a, u64& b) {
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
+    a = v.x;
+    b = v.y;
+}
+// asynchronous global -> shared copies (LDGSTS): issued up front, no registers held while the data is in flight
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(__cvta_generic_to_global(gmem_src)) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(__cvta_generic_to_global(gmem_src)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 #else
 // =================================================================================== emulation (tests only)
@@ -165,8 +205,11 @@ extern thread_local dim3 blockDim, gridDim;
 #define __device__ static
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 #define CKKS_SHARED static thread_local
 #define GRID_CONST
+#define DEV_MEMBER inline
+#define DYN_SHARED_U64(name, words) static thread_local u64 name[words]
 #define FOR_THREADS for (threadIdx.x = 0; threadIdx.x < blockDim.x; ++threadIdx.x)
 #define BLOCK_SYNC ((void)0)
 
@@ -189,6 +232,7 @@ inline void launch(dim3 grid, dim3 block, F body) {
 }
 }  // namespace emu
 #define LAUNCH(kern, grid, block, stream, ...) (++g_launch_count, emu::launch(grid, block, [=]() { kern(__VA_ARGS__); }))
+#define LAUNCH_DYN(kern, grid, block, smem, stream, ...) LAUNCH(kern, grid, block, stream, __VA_ARGS__)
 
 namespace dev {
 inline const char* backend_name() { return "emulation (tests only)"; }
@@ -240,4 +284,8 @@ static inline i64 d2ll_rn(double x) { return (i64)nearbyint(x); }
 static inline double ull2d_rn(u64 x) { return (double)x; }
 template <typename T>
 static inline T ldg(const T* p) { return *p; }
+static inline void ldg_pair(const u64* p, u64& a, u64& b) { a = p[0]; b = p[1]; }
+static inline void cp_async8(void* d, const void* s) { memcpy(d, s, 8); }
+static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
+static inline void cp_async_wait_all() {}
 #endif

@@ -172,6 +172,8 @@ def run_ours(args) -> None:
         LOGN, HW = 12, 64
         torch = None
     else:
+        if args.host_floor:
+            LOGN, HW = 12, 64
         import torch
         assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
         torch.cuda.set_device(local)
@@ -266,7 +268,14 @@ def run_ours(args) -> None:
     clocks.start()
     l0 = lib.ckks_launch_count()
     c0 = eng.counters()
+    # BENCH_NCU_WINDOW=1 (with `ncu --profile-from-start off`): only the timed steps are profiled, so the launch list
+    # under profiles/ is the list of exactly this region (a value printed under ncu is never a bench number)
+    window = torch is not None and os.environ.get("BENCH_NCU_WINDOW") == "1"
+    if window:
+        torch.cuda.cudart().cudaProfilerStart()
     ms, out = timed(step_resident, args.steps)
+    if window:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = (lib.ckks_launch_count() - l0) // args.steps
     c1 = eng.counters()
     clk = clocks.stop()
@@ -341,6 +350,8 @@ def run_ours(args) -> None:
                 "cpu_baseline": cpu}
         if dry:
             line["invalid"] = "dry run on the test-only emulation build (N=2^12): not a measurement"
+        if args.host_floor:
+            line["invalid"] = "host-floor diagnostic at N=2^12: not the benchmark workload"
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -356,6 +367,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--dry-run-emulation", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--host-floor", action="store_true",
+                    help="diagnostic: the same call sequence at N=2^12 (kernels 16x smaller), i.e. the host enqueue "
+                         "floor of one step; the line is marked invalid")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -16,6 +16,7 @@ from oracle.params import make_params
 
 CASES = [
     pytest.param(("emu", 12, 6), id="emu-n12"),
+    pytest.param(("emu", 16, 5), id="emu-n16"),      # the two-round pass A (LOGR = 8) only exists at N = 2^16
     pytest.param(("cuda", 12, 6), id="cuda-n12", marks=pytest.mark.gpu),
     pytest.param(("cuda", 16, 5), id="cuda-n16", marks=pytest.mark.gpu),
 ]
@@ -87,6 +88,24 @@ def test_raw_ntt_roundtrip_and_parity(pair):
     f = e.copy()
     pair.lib.ckks_test_ntt(pair.eng._ptr, f, len(mods), marr, 0)
     assert np.array_equal(f, pair.orc.ntt(e, mods))
+    # largest magnitudes for the lazy (unreduced) intermediate values of both arithmetic paths (tools/ntt_fp_bounds.py)
+    for pat in range(3):
+        e = np.zeros_like(a)
+        for i, m in enumerate(pair.orc.moduli):
+            if pat == 0:
+                e[i, :] = m - 1
+            elif pat == 1:
+                e[i, ::2] = m - 1
+            else:
+                e[i, :] = m // 2
+        f = e.copy()
+        pair.lib.ckks_test_ntt(pair.eng._ptr, f, len(mods), marr, 0)
+        assert np.array_equal(f, pair.orc.ntt(e, mods))
+        pair.lib.ckks_test_ntt(pair.eng._ptr, f, len(mods), marr, 1)
+        assert np.array_equal(f, e)
+        pair.lib.ckks_test_ntt(pair.eng._ptr, f, len(mods), marr, 1)      # inverse first, then forward
+        pair.lib.ckks_test_ntt(pair.eng._ptr, f, len(mods), marr, 0)
+        assert np.array_equal(f, e)
 
 
 def test_raw_automorphism(pair):
