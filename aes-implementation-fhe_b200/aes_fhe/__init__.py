@@ -1,6 +1,6 @@
 """Host-side mirror of the reference's AES-on-CKKS caller stack."""
 from .context import EngineContext
-from .pipeline import (AESPipeline, BatchedStateEncoder, FipsDriver, RowMajorShiftRows, decrypt_readme_order)
+from .pipeline import (AESPipeline, BatchedStateEncoder, CapturedRound, FipsDriver, RowMajorShiftRows, decrypt_readme_order)
 from .steps import (AddRoundKey, InvMixColumnsFHE, InvShiftRows, MixColFinal, ShiftRows, StateEncoder, SubBytesLUT,
                     XOR4LUT, from_zeta, to_zeta)
 from .tables import expand_aes128_key, load_all_coeffs

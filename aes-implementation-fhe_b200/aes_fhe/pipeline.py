@@ -273,6 +273,31 @@ class BatchedStateEncoder:
         return ((hi.astype(np.uint8) << 4) | lo).astype(np.uint8)
 
 
+class CapturedRound:
+    """One middle round (`AESPipeline.encrypt_round`, reference pipeline.py:143-151) recorded as a CUDA graph.
+
+    The round's ~3 300 engine calls / 13 000 kernel launches are data-oblivious, so they are captured once (state pair and
+    round-key pair are the graph's static inputs) and replayed with one driver call per round; rounds of independent
+    ciphertext pairs replay concurrently on separate replay streams.  Needs the device-side hard renorm (no host round
+    trip inside the round) and an engine with `capture` (the B200 engine); there is no fallback."""
+
+    def __init__(self, pipe: AESPipeline, state: Pair, round_key: Pair):
+        if not getattr(pipe.ctx, "device_renorm", False) and pipe.use_hard_renorm_between_steps:
+            raise RuntimeError("a captured round needs the device-side renorm (fused engine)")
+        self.pipe = pipe
+        self.call = pipe.ctx.engine.capture(pipe.encrypt_round, [*state, *round_key])
+
+    def __call__(self, ct_hi, ct_lo, key_hi, key_lo, stream: int = 0) -> Pair:
+        out = self.call(ct_hi, ct_lo, key_hi, key_lo, stream=stream)
+        return out[0], out[1]
+
+    def info(self) -> dict:
+        return self.call.info()
+
+    def close(self):
+        self.call.close()
+
+
 class FipsDriver:
     """R2 (+R3 when batched=True): FIPS-197-exact AES-128 on an unchanged `AESPipeline`.
 

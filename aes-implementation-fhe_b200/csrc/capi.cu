@@ -226,7 +226,8 @@ int ckks_arena_stats(const ckks_engine* e, long* driver_allocs, size_t* arena_by
     *driver_allocs = e->E->n_driver_allocs;
     *arena_bytes = e->E->driver_bytes;
     *cached_bytes = 0;
-    for (int i = 0; i < Engine::kMaxLanes; i++) *cached_bytes += e->E->pools[i].cached;
+    for (auto& kv : e->E->arenas)
+        for (int i = 0; i < Engine::kMaxLanes; i++) *cached_bytes += kv.second->pools[i].cached;
     return CKKS_OK;
 }
 
@@ -326,6 +327,30 @@ int ckks_test_key_switch(ckks_engine* e, const uint64_t* poly, int level, uint64
 uint64_t ckks_galois_for_rotation(const ckks_engine* e, long steps) { return e->E->galois_for_rotation(steps); }
 
 // ---------------------------------------------------------------- timing
+// ---------------------------------------------------------------- captured graphs
+int ckks_graph_create(ckks_engine* e, int* id) { return guard([&] { *id = e->E->graph_create(); }); }
+int ckks_graph_enter(ckks_engine* e, int id) { return guard([&] { e->E->graph_enter(id); }); }
+int ckks_graph_leave(ckks_engine* e) { return guard([&] { e->E->graph_leave(); }); }
+int ckks_graph_capture_begin(ckks_engine* e, int id) { return guard([&] { e->E->graph_capture_begin(id); }); }
+int ckks_graph_capture_end(ckks_engine* e, int id) { return guard([&] { e->E->graph_capture_end(id); }); }
+int ckks_graph_capture_abort(ckks_engine* e) { return guard([&] { e->E->graph_capture_abort(); }); }
+int ckks_graph_launch(ckks_engine* e, int id, int replay_stream) { return guard([&] { e->E->graph_launch(id, replay_stream); }); }
+int ckks_graph_wait(ckks_engine* e, int replay_stream) { return guard([&] { e->E->graph_wait(replay_stream); }); }
+int ckks_graph_destroy(ckks_engine* e, int id) { return guard([&] { e->E->graph_destroy(id); }); }
+int ckks_graph_info(ckks_engine* e, int id, long* nodes, long* launches, size_t* arena_bytes, long* capture_misses) {
+    return guard([&] {
+        Engine::GraphRec* G = e->E->graph_rec(id);
+        if (nodes) *nodes = G->g ? (long)G->g->nodes : 0;
+        if (launches) *launches = G->launches;
+        if (arena_bytes) *arena_bytes = G->arena.bytes;
+        if (capture_misses) *capture_misses = G->arena.capture_misses;
+    });
+}
+int ckks_ct_assign(ckks_engine* e, ckks_ct* dst, const ckks_ct* src, int replay_stream) {
+    return guard([&] { e->E->ct_assign(C(dst), C(src), replay_stream); });
+}
+int ckks_ct_clear_memo(ckks_engine* e, ckks_ct* ct) { return guard([&] { e->E->ct_clear_memo(C(ct)); }); }
+
 int ckks_timer_start(ckks_engine* e) { return guard([&] { e->timer.start(e->E->st); }); }
 int ckks_timer_stop_ms(ckks_engine* e, float* ms) { return guard([&] { *ms = e->timer.stop_ms(e->E->st); }); }
 

@@ -16,7 +16,9 @@ double g_launch_host_ns = 0;
 #ifdef CKKS_EMU
 thread_local emu_uint3 blockIdx, threadIdx;
 thread_local dim3 blockDim, gridDim;
+namespace emu { std::vector<std::function<void()>>* g_record = nullptr; }
 #endif
+namespace dev { int g_capturing = 0; }
 
 namespace ckks {
 
@@ -168,6 +170,7 @@ Engine::Engine(const Params& P) : prm(P) {
     dev::pool_setup(prm.device);
     st = streams[0] = dev::stream_create();
     lane_made[0] = lane_busy[0] = true;
+    arenas[0] = &main_arena;
     mod = prm.q;
     mod.insert(mod.end(), prm.p.begin(), prm.p.end());
     if ((int)mod.size() > CKKS_MAX_MODULI) throw std::runtime_error("engine: too many moduli");
@@ -270,7 +273,13 @@ Engine::Engine(const Params& P) : prm(P) {
 }
 
 Engine::~Engine() {
-    try { while (in_fork()) join(); sync(); } catch (...) {}
+    try {
+        if (dev::capturing()) graph_capture_abort();
+        while (in_fork()) join();
+        sync();
+        arena = &main_arena;
+        while (!graphs.empty()) graph_destroy(graphs.begin()->first);
+    } catch (...) {}
     bootstrap_teardown();
     for (auto& kv : gkeys) dev::free(kv.second.d, st);
     for (auto& kv : perms) dev::free(kv.second, st);
@@ -288,6 +297,8 @@ Engine::~Engine() {
     try { sync(); } catch (...) {}
     for (int i = 0; i < kMaxLanes; i++)
         if (lane_made[i]) dev::stream_destroy(streams[i]);
+    for (int i = 1; i < kMaxReplay; i++)
+        if (replay[i]) dev::stream_destroy(replay[i]);
 }
 
 // ------------------------------------------------------------------ lanes
@@ -334,6 +345,7 @@ void Engine::join() {
     Frame F = std::move(frames.back());
     frames.pop_back();
     // the parent is ordered after every lane: their cached buffers return to the parent's pool
+    LanePool* pools = arena->pools;
     LanePool& PP = pools[F.parent];
     if (F.serial) F.lanes.clear();
     for (int l : F.lanes) {
@@ -369,6 +381,7 @@ u64* Engine::alloc(size_t words) {
     const size_t limbs = (words + N() - 1) / N();
     const size_t bytes = size_class_limbs(limbs ? limbs : 1) * N() * sizeof(u64);
     // own pool first, then the pools of the enclosing frames' parent streams (idle and ordered before this lane)
+    LanePool* pools = arena->pools;
     int lane = cur_lane;
     for (int depth = (int)frames.size(); depth >= 0; depth--) {
         LanePool& P = pools[lane];
@@ -382,30 +395,170 @@ u64* Engine::alloc(size_t words) {
         if (depth == 0) break;
         lane = frames[depth - 1].parent;
     }
+    // miss: stream-ordered driver memory, or -- while a graph is being captured -- plain device memory owned by the
+    // graph's arena (dev::alloc switches by itself)
     void* p = dev::alloc(bytes, st);
-    alloc_bytes[p] = bytes;
+    alloc_bytes[p] = Buf{bytes, arena->id};
+    if (dev::capturing()) { arena->plain.push_back(p); arena->capture_misses++; }
     n_driver_allocs++;
     driver_bytes += bytes;
+    arena->bytes += bytes;
     return (u64*)p;
 }
+// a buffer always returns to the arena it was born in: the scratch a captured graph replays into never becomes the
+// memory of an eager operation, and the other way round
 void Engine::release(void* p) {
     if (!p) return;
     auto it = alloc_bytes.find(p);
     if (it == alloc_bytes.end()) { dev::free(p, st); return; }
-    LanePool& P = pools[cur_lane];
-    P.free[it->second].push_back(p);
-    P.cached += it->second;
-    if (P.cached > ((size_t)48 << 30)) trim_pools();
+    const Buf b = it->second;
+    if (b.arena != arena->id) {
+        auto ia = arenas.find(b.arena);
+        if (ia == arenas.end()) {                 // its arena is gone (graph destroyed): back to the driver
+            alloc_bytes.erase(it);
+            driver_bytes -= b.bytes;
+            if (!dev::capturing()) dev::free(p, st);
+            return;
+        }
+        LanePool& P = ia->second->pools[0];
+        P.free[b.bytes].push_back(p);
+        P.cached += b.bytes;
+        return;
+    }
+    LanePool& P = arena->pools[cur_lane];
+    P.free[b.bytes].push_back(p);
+    P.cached += b.bytes;
+    if (P.cached > ((size_t)48 << 30) && !dev::capturing()) trim_pools();
 }
-// give everything cached back to the driver pool (only when a lane hoards more than 48 GiB, and at teardown)
+// give everything cached in the current arena back to the driver pool (only when a lane hoards more than 48 GiB, and at
+// teardown); plain allocations made during a capture stay with their arena until it is destroyed
 void Engine::trim_pools() {
     sync();
-    for (LanePool& P : pools) {
-        for (auto& kv : P.free)
-            for (void* p : kv.second) { alloc_bytes.erase(p); dev::free(p, streams[0]); driver_bytes -= kv.first; }
-        P.free.clear();
-        P.cached = 0;
+    std::set<void*> plain(arena->plain.begin(), arena->plain.end());
+    for (LanePool& P : arena->pools) {
+        for (auto& kv : P.free) {
+            std::vector<void*> keep;
+            for (void* p : kv.second) {
+                if (plain.count(p)) { keep.push_back(p); continue; }
+                alloc_bytes.erase(p);
+                dev::free(p, streams[0]);
+                driver_bytes -= kv.first;
+                arena->bytes -= kv.first;
+                P.cached -= kv.first;
+            }
+            kv.second.swap(keep);
+        }
     }
+}
+
+// ------------------------------------------------------------------ captured graphs
+// A Graph owns a private arena.  Life cycle (driven through the C ABI by desilofhe.Engine.capture):
+//   graph_create -> graph_enter (the arena becomes current) -> [static inputs are copied, one eager warm-up run fills the
+//   arena and creates every lazily built table] -> graph_capture_begin -> the same calls again, now recorded ->
+//   graph_capture_end (instantiate) -> graph_leave.  graph_launch replays it on a replay stream; graph_wait orders the
+//   engine's main stream after that replay.
+int Engine::graph_create() {
+    if (in_fork()) throw std::runtime_error("graph_create inside a fork");
+    GraphRec* G = new GraphRec();
+    G->id = ++graph_counter;
+    G->arena.id = G->id;
+    graphs[G->id] = G;
+    arenas[G->id] = &G->arena;
+    return G->id;
+}
+Engine::GraphRec* Engine::graph_rec(int id) {
+    auto it = graphs.find(id);
+    if (it == graphs.end()) throw std::runtime_error("no such graph");
+    return it->second;
+}
+void Engine::graph_enter(int id) {
+    if (in_fork()) throw std::runtime_error("graph_enter inside a fork");
+    if (arena != &main_arena) throw std::runtime_error("another graph arena is already current");
+    arena = &graph_rec(id)->arena;
+}
+void Engine::graph_leave() {
+    if (in_fork()) throw std::runtime_error("graph_leave inside a fork");
+    if (dev::capturing()) throw std::runtime_error("graph_leave during a capture");
+    arena = &main_arena;
+}
+void Engine::graph_capture_begin(int id) {
+    GraphRec* G = graph_rec(id);
+    if (arena != &G->arena) throw std::runtime_error("graph_capture_begin: enter the graph's arena first");
+    if (in_fork()) throw std::runtime_error("graph_capture_begin inside a fork");
+    if (G->g) throw std::runtime_error("graph already captured");
+    sync();                                          // everything the capture reads has been produced
+    G->launches0 = g_launch_count;
+    G->cnt0[0] = n_keyswitch; G->cnt0[1] = n_ntt_limbs; G->cnt0[2] = n_rescale; G->cnt0[3] = n_mul_cc; G->cnt0[4] = n_boot;
+    capture_id = G->id;
+    dev::capture_begin(streams[0]);
+}
+void Engine::graph_capture_end(int id) {
+    GraphRec* G = graph_rec(id);
+    if (!dev::capturing() || capture_id != id) throw std::runtime_error("graph_capture_end without a matching begin");
+    if (in_fork()) { dev::capture_abort(streams[0]); capture_id = 0; throw std::runtime_error("graph_capture_end inside a fork"); }
+    capture_id = 0;
+    G->g = dev::capture_end(streams[0]);
+    G->launches = g_launch_count - G->launches0;
+    const long now[5] = {n_keyswitch, n_ntt_limbs, n_rescale, n_mul_cc, n_boot};
+    for (int i = 0; i < 5; i++) G->cnt[i] = now[i] - G->cnt0[i];
+}
+void Engine::graph_capture_abort() {
+    while (in_fork()) { try { join(); } catch (...) { break; } }
+    dev::capture_abort(streams[0]);
+    capture_id = 0;
+}
+dev_stream Engine::replay_stream(int slot) {
+    if (slot < 0 || slot >= kMaxReplay) throw std::runtime_error("replay stream index out of range");
+    if (slot == 0) return streams[0];
+    if (!replay[slot]) replay[slot] = dev::stream_create();
+    return replay[slot];
+}
+void Engine::graph_launch(int id, int slot) {
+    GraphRec* G = graph_rec(id);
+    if (!G->g) throw std::runtime_error("graph has not been captured");
+    if (in_fork() || dev::capturing()) throw std::runtime_error("graph_launch inside a fork or capture");
+    dev_stream s = replay_stream(slot);
+    if (slot) dev::stream_wait(s, streams[0]);      // its inputs were produced on the main stream
+    dev::graph_launch(G->g, s);
+    g_launch_count += G->launches;
+    n_keyswitch += G->cnt[0]; n_ntt_limbs += G->cnt[1]; n_rescale += G->cnt[2]; n_mul_cc += G->cnt[3]; n_boot += G->cnt[4];
+    G->replays++;
+}
+void Engine::graph_wait(int slot) {
+    if (slot) dev::stream_wait(streams[0], replay_stream(slot));
+}
+// overwrite the contents of a static input of a graph (same shape) on the replay stream the graph will be launched on
+void Engine::ct_assign(Ct* dst, const Ct* src, int slot) {
+    if (dst->npoly != src->npoly || dst->level != src->level) throw std::runtime_error("ct_assign: shape mismatch");
+    dev_stream s = replay_stream(slot);
+    if (slot) dev::stream_wait(s, streams[0]);
+    dev::d2d(dst->d, src->d, (size_t)src->npoly * (src->level + 1) * N() * sizeof(u64), s);
+    if (slot) dev::stream_wait(streams[0], s);      // src may be released (and rewritten) by the main stream afterwards
+}
+void Engine::ct_clear_memo(Ct* c) {
+    for (auto& kv : c->lowered) free_ct(kv.second);
+    c->lowered.clear();
+}
+void Engine::graph_destroy(int id) {
+    GraphRec* G = graph_rec(id);
+    if (arena == &G->arena) throw std::runtime_error("graph_destroy: leave the graph's arena first");
+    sync();
+    for (int i = 1; i < kMaxReplay; i++)
+        if (replay[i]) dev::sync(replay[i]);
+    dev::graph_destroy(G->g);
+    std::set<void*> plain(G->arena.plain.begin(), G->arena.plain.end());
+    for (LanePool& P : G->arena.pools)
+        for (auto& kv : P.free)
+            for (void* p : kv.second) {
+                alloc_bytes.erase(p);
+                driver_bytes -= kv.first;
+                if (plain.count(p)) { dev::free_plain(p); plain.erase(p); }
+                else dev::free(p, streams[0]);
+            }
+    // plain buffers still held by live ciphertexts are left to the process teardown (they are few: the graph's outputs)
+    arenas.erase(id);
+    graphs.erase(id);
+    delete G;
 }
 Ct* Engine::new_ct(int npoly, int level) {
     Ct* c = new Ct();
@@ -413,6 +566,7 @@ Ct* Engine::new_ct(int npoly, int level) {
     c->level = level;
     c->lane = cur_lane;
     c->epoch = cur_epoch();
+    c->cap = capture_id;
     c->d = alloc((size_t)npoly * (level + 1) * N());
     return c;
 }
@@ -1082,8 +1236,11 @@ Ct* Engine::level_down(Ct* c, int target) {
     if (target > c->level || target < 0) throw std::runtime_error("level_down: bad target");
     for (auto& kv : c->lowered)
         if (kv.first == target) {
-            // a copy memoised by the other lane has not necessarily been computed yet on the device
-            if (in_fork() && kv.second->lane != cur_lane && lane_made[kv.second->lane]) dev::sync(streams[kv.second->lane]);
+            // a copy memoised by another lane has not necessarily been computed yet on the device: order this lane
+            // after that lane's stream (an event, no host synchronisation).  A copy made before the open capture began
+            // is complete (graph_capture_begin synchronises) and its stream may not belong to the capture: no wait.
+            if (in_fork() && kv.second->lane != cur_lane && lane_made[kv.second->lane] && kv.second->cap == capture_id)
+                dev::stream_wait(st, streams[kv.second->lane]);
             return kv.second;
         }
     const size_t n = N();

@@ -37,6 +37,7 @@ struct Ct {
     u64* d = nullptr;                               // [npoly][level+1][N], NTT domain
     int lane = 0;                                   // stream lane that produced it (0: the main stream)
     long epoch = 0;                                 // fork region it was produced in
+    int cap = 0;                                    // graph capture it was recorded in (0: produced eagerly)
     std::vector<std::pair<int, Ct*>> lowered;       // memoised level_down() results (owned)
 };
 struct Pt {
@@ -136,9 +137,48 @@ class Engine {
     // stream-ordered caching arena: a released buffer goes to the free list of the lane it is released on and is handed
     // out again to later work on the SAME stream (stream order makes that safe), so the hot path makes no
     // cudaMallocAsync / cudaFreeAsync calls at all; fork deals the parent's cached buffers to the lanes, join returns them
-    LanePool pools[kMaxLanes];
-    std::map<void*, size_t> alloc_bytes;
+    struct MemArena {
+        int id = 0;                        // 0: the engine's own arena; otherwise the graph that owns it
+        LanePool pools[kMaxLanes];
+        std::vector<void*> plain;          // cudaMalloc'ed during a capture (an arena miss must not become a graph node)
+        long capture_misses = 0;
+        size_t bytes = 0;
+    };
+    struct Buf { size_t bytes; int arena; };
+    MemArena main_arena;
+    MemArena* arena = &main_arena;
+    std::map<int, MemArena*> arenas;          // live arenas by id (the main arena is looked up by pointer)
+    std::map<void*, Buf> alloc_bytes;
     void trim_pools();
+
+    // ---- captured graphs (CUDA graphs): a whole sequence of engine calls -- e.g. one AES round, 13 000 launches over
+    // nested stream lanes -- is recorded once into a private arena and replayed with one driver call; several graphs
+    // replay concurrently on separate replay streams (one ciphertext pair each)
+    static const int kMaxReplay = 16;
+    struct GraphRec {
+        int id = 0;
+        MemArena arena;
+        dev::Graph* g = nullptr;
+        long launches0 = 0, launches = 0, replays = 0;
+        long cnt0[5] = {}, cnt[5] = {};
+    };
+    std::map<int, GraphRec*> graphs;
+    int graph_counter = 0;
+    int capture_id = 0;                    // graph whose capture is open (0: none)
+    dev_stream replay[kMaxReplay] = {};
+    int graph_create();
+    GraphRec* graph_rec(int id);
+    void graph_enter(int id);
+    void graph_leave();
+    void graph_capture_begin(int id);
+    void graph_capture_end(int id);
+    void graph_capture_abort();
+    void graph_launch(int id, int slot);
+    void graph_wait(int slot);
+    void graph_destroy(int id);
+    dev_stream replay_stream(int slot);
+    void ct_assign(Ct* dst, const Ct* src, int slot);
+    void ct_clear_memo(Ct* c);
     long n_driver_allocs = 0;
     size_t driver_bytes = 0;
 

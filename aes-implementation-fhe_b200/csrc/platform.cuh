@@ -86,6 +86,13 @@ inline void dyn_smem_optin(K kern, size_t bytes) {
 typedef cudaStream_t dev_stream;
 
 namespace dev {
+// stream capture (CUDA graphs): while a capture is open nothing may synchronise or touch host memory; the guards below
+// turn such a call into an exception BEFORE the driver sees it (an illegal call would silently invalidate the capture)
+extern int g_capturing;
+inline bool capturing() { return g_capturing != 0; }
+inline void no_capture(const char* what) {
+    if (g_capturing) throw std::runtime_error(std::string(what) + " is not allowed while a graph is being captured");
+}
 inline const char* backend_name() { return "cuda-sm_100a"; }
 inline void set_device(int id) { CUDA_CHECK(cudaSetDevice(id)); }
 inline dev_stream stream_create() {
@@ -102,23 +109,33 @@ inline void pool_setup(int device) {
 }
 inline void* alloc(size_t bytes, dev_stream s) {
     void* p = nullptr;
+    if (g_capturing) {      // a stream-ordered allocation would become a node of the graph: take plain device memory
+        CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 8));
+        return p;
+    }
     CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 8, s));
     return p;
 }
 inline void free(void* p, dev_stream s) {
+    no_capture("freeing device memory");
     if (p) cudaFreeAsync(p, s);
 }
 inline void h2d(void* d, const void* h, size_t bytes, dev_stream s) {
+    no_capture("a host-to-device copy");
     CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
 }
 inline void d2h(void* h, const void* d, size_t bytes, dev_stream s) {
+    no_capture("a device-to-host copy");
     CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
 }
 inline void d2d(void* o, const void* i, size_t bytes, dev_stream s) {
     CUDA_CHECK(cudaMemcpyAsync(o, i, bytes, cudaMemcpyDeviceToDevice, s));
 }
 inline void zero(void* d, size_t bytes, dev_stream s) { CUDA_CHECK(cudaMemsetAsync(d, 0, bytes, s)); }
-inline void sync(dev_stream s) { CUDA_CHECK(cudaStreamSynchronize(s)); }
+inline void sync(dev_stream s) {
+    no_capture("a stream synchronisation");
+    CUDA_CHECK(cudaStreamSynchronize(s));
+}
 inline void check_last(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA launch error in ") + what + ": " + cudaGetErrorString(e));
@@ -137,6 +154,53 @@ inline void* host_alloc_pinned(size_t bytes) {
     return p;
 }
 inline void host_free_pinned(void* p) { cudaFreeHost(p); }
+// a captured sequence of launches / copies (every stream that was forked from `s` during the capture included),
+// instantiated once and replayed with one call
+struct Graph {
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    size_t nodes = 0;
+};
+inline void capture_begin(dev_stream s) {
+    if (g_capturing) throw std::runtime_error("a graph capture is already open");
+    // relaxed mode: cudaMalloc (arena misses) and event creation stay legal on this thread during the capture
+    CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+    g_capturing = 1;
+}
+inline Graph* capture_end(dev_stream s) {
+    g_capturing = 0;
+    Graph* G = new Graph();
+    cudaError_t e = cudaStreamEndCapture(s, &G->g);
+    if (e != cudaSuccess || !G->g) {
+        delete G;
+        cudaGetLastError();
+        throw std::runtime_error(std::string("graph capture failed: ") + cudaGetErrorString(e));
+    }
+    cudaGraphGetNodes(G->g, nullptr, &G->nodes);
+    e = cudaGraphInstantiate(&G->exec, G->g, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(G->g);
+        delete G;
+        throw std::runtime_error(std::string("graph instantiation failed: ") + cudaGetErrorString(e));
+    }
+    return G;
+}
+inline void capture_abort(dev_stream s) {
+    if (!g_capturing) return;
+    g_capturing = 0;
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(s, &g);
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+}
+inline void graph_launch(Graph* G, dev_stream s) { CUDA_CHECK(cudaGraphLaunch(G->exec, s)); }
+inline void graph_destroy(Graph* G) {
+    if (!G) return;
+    if (G->exec) cudaGraphExecDestroy(G->exec);
+    if (G->g) cudaGraphDestroy(G->g);
+    delete G;
+}
+inline void free_plain(void* p) { if (p) cudaFree(p); }      // memory taken by alloc() during a capture
 struct Timer {
     cudaEvent_t a = nullptr, b = nullptr;
     void start(dev_stream s) {
@@ -215,9 +279,22 @@ extern thread_local dim3 blockDim, gridDim;
 
 typedef int dev_stream;
 
+#include <functional>
+#include <vector>
 namespace emu {
+// graph capture under emulation: launches and device copies are RECORDED (not run) while a capture is open, exactly as
+// CUDA does, and replayed in order by graph_launch -- so the host-side capture logic (static buffers, private arena,
+// memoised level alignments) is testable without a GPU
+extern std::vector<std::function<void()>>* g_record;
+template <typename F>
+inline void run_grid(dim3 grid, dim3 block, F body);
 template <typename F>
 inline void launch(dim3 grid, dim3 block, F body) {
+    if (g_record) { g_record->push_back([=]() { run_grid(grid, block, body); }); return; }
+    run_grid(grid, block, body);
+}
+template <typename F>
+inline void run_grid(dim3 grid, dim3 block, F body) {
     const long total = (long)grid.x * grid.y * grid.z;
 #pragma omp parallel for schedule(static)
     for (long b = 0; b < total; b++) {
@@ -235,6 +312,11 @@ inline void launch(dim3 grid, dim3 block, F body) {
 #define LAUNCH_DYN(kern, grid, block, smem, stream, ...) LAUNCH(kern, grid, block, stream, __VA_ARGS__)
 
 namespace dev {
+extern int g_capturing;
+inline bool capturing() { return g_capturing != 0; }
+inline void no_capture(const char* what) {
+    if (g_capturing) throw std::runtime_error(std::string(what) + " is not allowed while a graph is being captured");
+}
 inline const char* backend_name() { return "emulation (tests only)"; }
 inline void set_device(int) {}
 inline dev_stream stream_create() { return 0; }
@@ -245,12 +327,44 @@ inline void* alloc(size_t bytes, dev_stream) {
     if (!p) throw std::runtime_error("emulation: out of memory");
     return p;
 }
-inline void free(void* p, dev_stream) { ::free(p); }
-inline void h2d(void* d, const void* h, size_t bytes, dev_stream) { memcpy(d, h, bytes); }
-inline void d2h(void* h, const void* d, size_t bytes, dev_stream) { memcpy(h, d, bytes); }
-inline void d2d(void* o, const void* i, size_t bytes, dev_stream) { memmove(o, i, bytes); }
-inline void zero(void* d, size_t bytes, dev_stream) { memset(d, 0, bytes); }
-inline void sync(dev_stream) {}
+inline void free(void* p, dev_stream) { no_capture("freeing device memory"); ::free(p); }
+inline void h2d(void* d, const void* h, size_t bytes, dev_stream) { no_capture("a host-to-device copy"); memcpy(d, h, bytes); }
+inline void d2h(void* h, const void* d, size_t bytes, dev_stream) { no_capture("a device-to-host copy"); memcpy(h, d, bytes); }
+inline void d2d(void* o, const void* i, size_t bytes, dev_stream) {
+    if (emu::g_record) { emu::g_record->push_back([=]() { memmove(o, i, bytes); }); return; }
+    memmove(o, i, bytes);
+}
+inline void zero(void* d, size_t bytes, dev_stream) {
+    if (emu::g_record) { emu::g_record->push_back([=]() { memset(d, 0, bytes); }); return; }
+    memset(d, 0, bytes);
+}
+inline void sync(dev_stream) { no_capture("a stream synchronisation"); }
+struct Graph {
+    std::vector<std::function<void()>> ops;
+    size_t nodes = 0;
+};
+inline void capture_begin(dev_stream) {
+    if (g_capturing) throw std::runtime_error("a graph capture is already open");
+    g_capturing = 1;
+    emu::g_record = new std::vector<std::function<void()>>();
+}
+inline Graph* capture_end(dev_stream) {
+    Graph* G = new Graph();
+    G->ops.swap(*emu::g_record);
+    G->nodes = G->ops.size();
+    delete emu::g_record;
+    emu::g_record = nullptr;
+    g_capturing = 0;
+    return G;
+}
+inline void capture_abort(dev_stream) {
+    delete emu::g_record;
+    emu::g_record = nullptr;
+    g_capturing = 0;
+}
+inline void graph_launch(Graph* G, dev_stream) { for (auto& f : G->ops) f(); }
+inline void graph_destroy(Graph* G) { delete G; }
+inline void free_plain(void* p) { ::free(p); }
 inline void check_last(const char*) {}
 inline void stream_wait(dev_stream, dev_stream) {}
 inline void* host_alloc_pinned(size_t bytes) { return ::malloc(bytes); }

@@ -30,7 +30,7 @@ import numpy as np
 
 from . import _capi
 
-__all__ = ["Engine", "Ciphertext", "Plaintext", "SecretKey", "PublicKey", "RelinearizationKey", "ConjugationKey",
+__all__ = ["Engine", "CapturedCall", "Ciphertext", "Plaintext", "SecretKey", "PublicKey", "RelinearizationKey", "ConjugationKey",
            "RotationKey", "BootstrapKey"]
 
 # parameter sets (DESIGN.md "Parameters"): N = 2^16, q0 ~ 2^60, scale primes ~ 2^50, special primes ~ 2^61
@@ -108,6 +108,76 @@ class Plaintext:
             for h in self._enc.values():
                 eng._lib.ckks_pt_free(eng._ptr, h)
         self._enc = {}
+
+
+class CapturedCall:
+    """`fn(*inputs)` recorded once as a CUDA graph and replayed with one driver call.
+
+    CKKS evaluation is data-oblivious: the ~13 000 kernel launches of an AES round (over nested stream lanes) are the
+    same for every input, so they are captured into a graph with a private arena.  `inputs` are copied into static
+    ciphertexts; `__call__(*cts, stream=k)` overwrites them, replays the graph on replay stream k and returns the static
+    output ciphertexts (valid until the next replay of this object).  Graphs launched on different replay streams run
+    concurrently; `engine.graph_wait(k)` orders the main stream (decrypt, further eager calls) after replay k.
+    `fn` may take further arguments by closure as long as those ciphertexts/plaintexts stay alive and unchanged."""
+
+    def __init__(self, eng: "Engine", fn, inputs: Sequence[Ciphertext]):
+        self._eng, lib, ptr = eng, eng._lib, eng._ptr
+        gid = C.c_int()
+        _capi.check(lib.ckks_graph_create(ptr, C.byref(gid)))
+        self.id = gid.value
+        self.outputs = None
+        _capi.check(lib.ckks_graph_enter(ptr, self.id))
+        try:
+            self.inputs = [eng.level_down_copy(c) for c in inputs]
+            warm = fn(*self.inputs)          # eager: fills the private arena, builds every lazily created table / key
+            eng.sync()
+            del warm
+            for c in self.inputs:
+                _capi.check(lib.ckks_ct_clear_memo(ptr, c._h))
+            _capi.check(lib.ckks_graph_capture_begin(ptr, self.id))
+            try:
+                out = fn(*self.inputs)
+                _capi.check(lib.ckks_graph_capture_end(ptr, self.id))
+            except BaseException:
+                lib.ckks_graph_capture_abort(ptr)
+                raise
+            self.outputs = out
+        finally:
+            _capi.check(lib.ckks_graph_leave(ptr))
+
+    def info(self) -> dict:
+        n, l, b, m = C.c_long(), C.c_long(), C.c_size_t(), C.c_long()
+        _capi.check(self._eng._lib.ckks_graph_info(self._eng._ptr, self.id, C.byref(n), C.byref(l), C.byref(b), C.byref(m)))
+        return {"nodes": n.value, "launches": l.value, "arena_bytes": b.value, "capture_misses": m.value}
+
+    def assign(self, cts: Sequence[Ciphertext], stream: int = 0):
+        lib, ptr = self._eng._lib, self._eng._ptr
+        if len(cts) != len(self.inputs):
+            raise ValueError("wrong number of inputs for this captured call")
+        for dst, src in zip(self.inputs, cts):
+            _capi.check(lib.ckks_ct_assign(ptr, dst._h, src._h, stream))
+
+    def launch(self, stream: int = 0):
+        _capi.check(self._eng._lib.ckks_graph_launch(self._eng._ptr, self.id, stream))
+        return self.outputs
+
+    def __call__(self, *cts: Ciphertext, stream: int = 0):
+        self.assign(cts, stream)
+        return self.launch(stream)
+
+    def close(self):
+        eng = self._eng
+        if self.id and eng is not None and eng._ptr:
+            self.outputs = None
+            self.inputs = []
+            eng._lib.ckks_graph_destroy(eng._ptr, self.id)
+        self.id = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Engine:
@@ -220,6 +290,10 @@ class Engine:
         finally:
             _capi.check(self._lib.ckks_join(self._ptr))
         return out
+
+    def capture(self, fn, inputs: Sequence["Ciphertext"]) -> "CapturedCall":
+        """Record `fn(*inputs)` -- any sequence of engine calls without host round trips -- into a CUDA graph."""
+        return CapturedCall(self, fn, inputs)
 
     def pair_map(self, fn, first, second):
         a, b = self.lane_map(fn, [first, second])
@@ -387,6 +461,14 @@ class Engine:
 
     def level_down(self, ct: Ciphertext, level: int) -> Ciphertext:
         return self._new(self._lib.ckks_level_down, ct._h, int(level))
+
+    def level_down_copy(self, ct: Ciphertext) -> Ciphertext:
+        """A fresh copy of `ct` (own buffer in the current arena)."""
+        return self._new(self._lib.ckks_level_down, ct._h, ct.level)
+
+    def graph_wait(self, stream: int = 0):
+        """Order the engine's main stream after everything enqueued on replay stream `stream`."""
+        _capi.check(self._lib.ckks_graph_wait(self._ptr, int(stream)))
 
     # ------------------------------------------------------------------ fused entry points (beyond the reference surface)
     def rotate_many(self, ct: Ciphertext, key: Optional[RotationKey], steps: Sequence[int]) -> List[Ciphertext]:

@@ -100,6 +100,15 @@ def load():
         "ckks_test_automorph": (i32, [vp, u64p, i32, u64]),
         "ckks_test_key_switch": (i32, [vp, u64p, i32, u64, u64p]),
         "ckks_galois_for_rotation": (u64, [vp, lng]),
+        "ckks_graph_create": (i32, [vp, C.POINTER(i32)]),
+        "ckks_graph_enter": (i32, [vp, i32]), "ckks_graph_leave": (i32, [vp]),
+        "ckks_graph_capture_begin": (i32, [vp, i32]), "ckks_graph_capture_end": (i32, [vp, i32]),
+        "ckks_graph_capture_abort": (i32, [vp]),
+        "ckks_graph_launch": (i32, [vp, i32, i32]), "ckks_graph_wait": (i32, [vp, i32]),
+        "ckks_graph_destroy": (i32, [vp, i32]),
+        "ckks_graph_info": (i32, [vp, i32, C.POINTER(lng), C.POINTER(lng), C.POINTER(C.c_size_t), C.POINTER(lng)]),
+        "ckks_ct_assign": (i32, [vp, vp, vp, i32]),
+        "ckks_ct_clear_memo": (i32, [vp, vp]),
         "ckks_timer_start": (i32, [vp]),
         "ckks_timer_stop_ms": (i32, [vp, C.POINTER(C.c_float)]),
         "ckks_profile_ntt_begin": (i32, [vp]),

@@ -7,11 +7,14 @@ renorm, two bootstraps), AddRoundKey (two XOR4 LUTs), hard renorm -- on one ciph
 every one of the 2048 stride positions carrying an independent block (batched encoder), i.e.
 the reference's `pipeline.py:143-151` flow issued through the host mirror `aes_fhe` onto the `desilofhe` drop-in.
 
-  value  : blocks/s = gpus * 2048 blocks / (10 rounds * seconds per round); state, round-key ciphertexts and all
-           evaluation keys resident in HBM when the timed region starts (the renorm's decrypt/re-encrypt host
-           round trips are part of the reference algorithm, SURVEY.md H4, and stay inside).
+  value  : blocks/s = gpus * pairs * 2048 blocks / (10 rounds * seconds per step); a step is the round on `--pairs`
+           independent ciphertext pairs per GPU (BASELINE.json configs[4]: "many ciphertexts"), each pair's round
+           recorded once as a CUDA graph (13 000 launches over nested stream lanes) and replayed on its own stream, so
+           the device overlaps the small kernels of different pairs; states, round-key ciphertexts and all evaluation
+           keys resident in HBM when the timed region starts.  `--no-graph` issues the round eagerly (one pair).
   e2e    : same metric with the step starting from HOST bytes (encode + encrypt: H2D) and ending with decrypted
            bytes on the host (D2H), through the reference-facing API.
+  s_per_round: latency of ONE pair's round (a single graph replay, nothing else on the device).
   roofline: the NTT kernels (dominant), algorithmic bytes 2*N*8 per limb transform / CUDA-event time per call.
   cpu_baseline: the oracle port of the same CKKS arithmetic on the host cores, bounded sample.
 
@@ -218,20 +221,13 @@ def run_ours(args) -> None:
     ctx.encrypt, ctx.decrypt = enc, dec
 
     rng = np.random.default_rng(1000 + rank)
-    blocks = rng.integers(0, 256, (stride, 16), dtype=np.uint8)
     key = np.frombuffer(bytes.fromhex("000102030405060708090a0b0c0d0e0f"), dtype=np.uint8)
     rks = aes_fhe.expand_aes128_key(key)
     rk_ct = pipe._prepare_round_keys([drv._perm(rk) for rk in rks])        # resident round-key ciphertexts
-    state = pipe.encoder.encode(drv._perm(blocks))                          # resident state
-    expect = plain_round(blocks, rks[1])
-
-    def step_resident():
-        return pipe.encrypt_round(*state, *rk_ct[1])
-
-    def step_e2e():
-        ct = pipe.encoder.encode(drv._perm(blocks))
-        out = pipe.encrypt_round(*ct, *rk_ct[1])
-        return drv.decode(*out)
+    npairs = 1 if args.no_graph else max(1, args.pairs)
+    blocks = [rng.integers(0, 256, (stride, 16), dtype=np.uint8) for _ in range(npairs)]
+    states = [pipe.encoder.encode(drv._perm(b)) for b in blocks]           # resident states
+    expect = [plain_round(b, rks[1]) for b in blocks]
 
     def barrier():
         eng.sync()
@@ -240,29 +236,71 @@ def run_ours(args) -> None:
         if dist is not None:
             dist.barrier()
 
+    def _check(rc):
+        desilofhe._capi.check(rc)
+
     def timed(fn, n):
         barrier()
         _check(lib.ckks_timer_start(ptr))
         res = None
         for _ in range(n):
             res = fn()
-        eng.sync()
-        ms = C.c_float()
-        _check(lib.ckks_timer_stop_ms(ptr, C.byref(ms)))
+        _check(lib.ckks_timer_stop_ms(ptr, C.byref(ms_box)))      # event on the main stream, which waits on every replay
         barrier()
         if dist is not None:
-            t = torch.tensor([ms.value], device="cuda", dtype=torch.float64)
+            t = torch.tensor([ms_box.value], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item()), res
-        return float(ms.value), res
+        return float(ms_box.value), res
 
-    def _check(rc):
-        desilofhe._capi.check(rc)
+    ms_box = C.c_float()
+    graph_info = None
+    t_capture = time.perf_counter()
+    if args.no_graph:
+        rounds = None
+
+        def step_resident():
+            return [pipe.encrypt_round(*states[0], *rk_ct[1])]
+
+        def step_e2e():
+            ct = pipe.encoder.encode(drv._perm(blocks[0]))
+            return [drv.decode(*pipe.encrypt_round(*ct, *rk_ct[1]))]
+
+        def step_latency():
+            return step_resident()
+    else:
+        # one captured round per resident pair: private arena, static inputs = the pair's state and the round key
+        rounds = [aes_fhe.CapturedRound(pipe, states[j], rk_ct[1]) for j in range(npairs)]
+        graph_info = rounds[0].info()
+
+        def step_resident():
+            outs = [rounds[j].call.launch(stream=j + 1) for j in range(npairs)]
+            for j in range(npairs):
+                eng.graph_wait(j + 1)
+            return outs
+
+        def step_e2e():
+            outs = []
+            for j in range(npairs):
+                ct = pipe.encoder.encode(drv._perm(blocks[j]))          # host bytes -> H2D -> encrypt
+                outs.append(rounds[j](*ct, *rk_ct[1], stream=j + 1))
+            for j in range(npairs):
+                eng.graph_wait(j + 1)
+            return [drv.decode(*o) for o in outs]                        # decrypt -> D2H -> bytes
+
+        def step_latency():
+            return [rounds[0].call.launch(stream=0)]
+    t_capture = time.perf_counter() - t_capture
+
+    def decode_all(outs):
+        return [drv.decode(*o) for o in outs]
+
+    def all_equal(got):
+        return all(bool(np.array_equal(g, e)) for g, e in zip(got, expect))
 
     for _ in range(args.warmup):
         out = step_resident()
-    got = drv.decode(*out)
-    ok = bool(np.array_equal(got, expect))
+    ok = all_equal(decode_all(out))
 
     clocks = Clocks(local)
     clocks.start()
@@ -279,27 +317,33 @@ def run_ours(args) -> None:
     launches = (lib.ckks_launch_count() - l0) // args.steps
     c1 = eng.counters()
     clk = clocks.stop()
-    ok = ok and bool(np.array_equal(drv.decode(*out), expect))
-    s_round = ms * 1e-3 / args.steps
-    value = world * stride / (ROUNDS_PER_BLOCK * s_round)
+    ok = ok and all_equal(decode_all(out))
+    s_step = ms * 1e-3 / args.steps
+    value = world * npairs * stride / (ROUNDS_PER_BLOCK * s_step)
+
+    ms_l, _ = timed(step_latency, args.steps)
+    s_round = ms_l * 1e-3 / args.steps
 
     io["h2d"] = io["d2h"] = 0
     ms_e, got = timed(step_e2e, args.steps)
-    ok = ok and bool(np.array_equal(got, expect))
-    s_round_e = ms_e * 1e-3 / args.steps
-    e2e = {"value": world * stride / (ROUNDS_PER_BLOCK * s_round_e), "unit": UNIT,
+    ok = ok and all_equal(got)
+    s_step_e = ms_e * 1e-3 / args.steps
+    e2e = {"value": world * npairs * stride / (ROUNDS_PER_BLOCK * s_step_e), "unit": UNIT,
            "h2d_bytes_per_step": io["h2d"] // args.steps, "d2h_bytes_per_step": io["d2h"] // args.steps,
-           "ms_per_step": s_round_e * 1e3}
+           "ms_per_step": s_step_e * 1e3}
+
+    def step_eager():
+        return pipe.encrypt_round(*states[0], *rk_ct[1])
 
     # roofline leg: one more resident step with a CUDA-event pair around every NTT call.  The stream lanes are switched
     # off for this step so that an event pair brackets the NTT kernels alone (with lanes on, kernels of other streams
     # run inside the bracket and the per-call time is not a kernel time).
     eng.set_lanes_enabled(False)
-    step_resident()
+    step_eager()
     eng.sync()
     _check(lib.ckks_profile_ntt_begin(ptr))
     t0 = time.perf_counter()
-    step_resident()
+    step_eager()
     eng.sync()
     prof_wall = time.perf_counter() - t0
     pms, pcalls, plimbs = C.c_double(), C.c_long(), C.c_long()
@@ -338,14 +382,15 @@ def run_ours(args) -> None:
                              f"{KS_PER_ROUND} key switches of one round issued call for call as the reference does",
                    "s_per_round": s_cpu}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": s_round * 1e3, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": s_step * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "logn": LOGN, "levels": LEVELS, "fresh_level": FRESH, "dnum": DNUM,
-                           "pairs_per_gpu": 1, "evk_broadcast_bytes": key_bytes, "setup_s": round(t_keys, 2), "l2": "working set (evaluation keys 87 MiB each, ~60 live ciphertexts) "
+                           "pairs_per_gpu": npairs, "cuda_graph": graph_info, "capture_s": round(t_capture, 2),
+                           "evk_broadcast_bytes": key_bytes, "setup_s": round(t_keys, 2), "l2": "working set (evaluation keys 87 MiB each, ~60 live ciphertexts) "
                            "exceeds the 126 MB L2; no explicit flush"},
                 "s_per_round": s_round, "bytes_exact_vs_fips197_round": ok,
                 "key_switches_per_step": ks_round, "bootstraps_per_step": (c1["bootstrap"] - c0["bootstrap"]) // args.steps,
-                "rotations_per_s_equiv": ks_round / s_round, "arena": eng.arena_stats(),
+                "rotations_per_s_equiv": ks_round / s_step, "arena": eng.arena_stats(),
                 "e2e": e2e, "gpu_launches": int(launches) * args.steps, "clocks": clk, "roofline": roofline,
                 "cpu_baseline": cpu}
         if dry:
@@ -366,6 +411,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pairs", type=int, default=4, help="independent ciphertext pairs per GPU, one captured round each")
+    ap.add_argument("--no-graph", action="store_true", help="issue the round eagerly, call by call (one pair; A/B)")
     ap.add_argument("--dry-run-emulation", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--host-floor", action="store_true",
                     help="diagnostic: the same call sequence at N=2^12 (kernels 16x smaller), i.e. the host enqueue "

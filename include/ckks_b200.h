@@ -151,6 +151,28 @@ int ckks_test_key_switch(ckks_engine* e, const uint64_t* poly /* [level+1][N] */
                          uint64_t galois_or_0_for_relin, uint64_t* out /* [2][level+1][N] */);
 uint64_t ckks_galois_for_rotation(const ckks_engine* e, long steps);
 
+/* ---- captured graphs (CUDA graphs).  The reference issues one backend call per homomorphic operation
+ * (engine_context.py:65-162); one AES round is about 3 300 such calls and 13 000 kernel launches.  Because CKKS
+ * evaluation is data-oblivious, the whole sequence can be recorded once and replayed with one driver call:
+ *   create -> enter (a private arena becomes current) -> copy the inputs into static ciphertexts, run the calls once
+ *   eagerly (fills the arena, builds every lazily created table), ckks_ct_clear_memo the static inputs ->
+ *   capture_begin -> the same calls again (recorded, not executed; host<->device copies and synchronisation raise) ->
+ *   capture_end -> leave.
+ * ckks_ct_assign overwrites a static input, ckks_graph_launch replays on replay stream `replay_stream` (0 = the engine's
+ * main stream; graphs on different replay streams run concurrently), ckks_graph_wait orders the main stream after it. */
+int ckks_graph_create(ckks_engine* e, int* id_out);
+int ckks_graph_enter(ckks_engine* e, int id);
+int ckks_graph_leave(ckks_engine* e);
+int ckks_graph_capture_begin(ckks_engine* e, int id);
+int ckks_graph_capture_end(ckks_engine* e, int id);
+int ckks_graph_capture_abort(ckks_engine* e);
+int ckks_graph_launch(ckks_engine* e, int id, int replay_stream);
+int ckks_graph_wait(ckks_engine* e, int replay_stream);
+int ckks_graph_destroy(ckks_engine* e, int id);
+int ckks_graph_info(ckks_engine* e, int id, long* nodes, long* launches, size_t* arena_bytes, long* capture_misses);
+int ckks_ct_assign(ckks_engine* e, ckks_ct* dst, const ckks_ct* src, int replay_stream);
+int ckks_ct_clear_memo(ckks_engine* e, ckks_ct* ct);
+
 /* ---- timing helpers for bench.py: device-side timing on the engine's own stream (torch.cuda.Event only
  * sees torch's current stream) */
 int ckks_timer_start(ckks_engine* e);

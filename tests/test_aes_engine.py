@@ -128,6 +128,43 @@ def test_config5_batched_fips_round(boot_ctx):
     assert np.array_equal(drv.decode(*out), plain_round(blocks, rks[1]))
 
 
+def test_captured_round_replays_on_new_inputs(boot_ctx):
+    """The batched FIPS round recorded as one graph (CUDA graph on the device, recorded closures under emulation): replays
+    with OTHER blocks and ANOTHER round key must give the plain round of those inputs; the recording run itself executes
+    nothing, so a wrong static buffer, a stale memoised level alignment or scratch shared with eager work shows here."""
+    which, ctx = boot_ctx
+    pipe = make_pipe(ctx)
+    drv = aes_fhe.FipsDriver(pipe, batched=True)
+    eng = ctx.engine
+    stride = eng.slot_count // 16
+    rng = np.random.default_rng(21)
+    key = np.frombuffer(bytes.fromhex("000102030405060708090a0b0c0d0e0f"), dtype=np.uint8)
+    rks = aes_fhe.expand_aes128_key(key)
+    rk_ct = pipe._prepare_round_keys([drv._perm(rk) for rk in rks])
+    a = rng.integers(0, 256, (stride, 16), dtype=np.uint8)
+    b = rng.integers(0, 256, (stride, 16), dtype=np.uint8)
+    ct_a = pipe.encoder.encode(drv._perm(a))
+    l0 = eng.counters()
+    rnd = aes_fhe.CapturedRound(pipe, ct_a, rk_ct[1])
+    info = rnd.info()
+    assert info["nodes"] > 1000 and info["launches"] > 1000
+    k0 = eng.counters()
+    out = rnd(*pipe.encoder.encode(drv._perm(b)), *rk_ct[2], stream=1)
+    eng.graph_wait(1)
+    assert np.array_equal(drv.decode(*out), plain_round(b, rks[2]))
+    k1 = eng.counters()
+    assert k1["launches"] - k0["launches"] >= info["launches"]          # replays are counted as the launches they are
+    assert k1["bootstrap"] - k0["bootstrap"] == 2
+    # eager work between replays must not disturb the graph's private arena, nor the other way round
+    eager = pipe.add_round_key(*pipe.encoder.encode(drv._perm(a)), *rk_ct[0])
+    out = rnd(*ct_a, *rk_ct[1])
+    assert np.array_equal(drv.decode(*out), plain_round(a, rks[1]))
+    assert np.array_equal(drv.decode(*eager), a ^ rks[0][None, :])
+    rnd.close()
+    out2 = pipe.encrypt_round(*ct_a, *rk_ct[3])                        # the engine still works eagerly afterwards
+    assert np.array_equal(drv.decode(*out2), plain_round(a, rks[3]))
+
+
 @pytest.mark.gpu
 def test_config3_full_fips_encryption_gpu():
     """configs[2]: full AES-128 encryption of 2048 packed blocks with 18 bootstraps, bit-exact with FIPS-197."""
