@@ -102,6 +102,12 @@ class EngineContext:
     def make_power_basis(self, ct, degree: int):
         return self.engine.make_power_basis(ct, degree, self.relinearization_key)
 
+    def make_power_basis_sparse(self, ct, degree: int, exponents):
+        """Fused mode: only the powers in `exponents` (+ intermediates); a list with None for the skipped ones."""
+        if self.fused and hasattr(self.engine, "make_power_basis_sparse"):
+            return self.engine.make_power_basis_sparse(ct, degree, exponents, self.relinearization_key)
+        return self.engine.make_power_basis(ct, degree, self.relinearization_key)
+
     def conjugate(self, ct):
         return self.engine.conjugate(ct, self.conjugation_key)
 

@@ -26,6 +26,7 @@ import os as _os
 # tuning switches for the stream-lane granularity (measured choices recorded in profiles/README.md)
 LANES_CONJ = _os.environ.get("AESFHE_LANES_CONJ", "1") == "1"
 LANES_AB = _os.environ.get("AESFHE_LANES_AB", "1") == "1"
+PRUNE_BASIS = _os.environ.get("AESFHE_PRUNE_BASIS", "1") == "1"   # fused mode: build only the powers a LUT uses
 
 # multiplicative depths of the steps, used for the encryption-level hints of the fused mode
 XOR4_DEPTH = 5          # power basis 3 + product 1 + constant 1
@@ -82,6 +83,27 @@ def _const_pt(ctx: EngineContext, sc: int, c: complex):
     return ctx.encode(np.full(sc, c, dtype=np.complex128))
 
 
+def _zeta16_basis_pruned(eng, ct, exps) -> Dict[int, Any]:
+    """Fused mode: the zeta16 basis {k: ct^k} restricted to the exponents a LUT really uses.  Powers 9..15 are
+    conjugates of 7..1 (unit-modulus slots); only the needed positive powers and only the needed conjugations are
+    computed -- XOR4 has odd exponents only: 5 products + 4 conjugations per base instead of 7 + 7."""
+    exps = sorted(set(int(k) for k in exps))
+    pos_need = sorted({k for k in exps if 1 <= k <= 8} | {16 - k for k in exps if k > 8})
+    pos = eng.make_power_basis_sparse(ct, 8, pos_need) if pos_need else []
+    basis: Dict[int, Any] = {}
+    if 0 in exps:
+        basis[0] = eng.add_plain(eng.multiply(ct, 0.0), 1.0)
+    basis.update({k: pos[k - 1] for k in exps if 1 <= k <= 8})
+    hi = [k for k in exps if k > 8]
+    if hi:
+        if LANES_CONJ:
+            conj = eng.lane_map(eng.conjugate, [(pos[15 - k],) for k in hi])
+        else:
+            conj = [eng.conjugate(pos[15 - k]) for k in hi]
+        basis.update(dict(zip(hi, conj)))
+    return basis
+
+
 class XOR4LUT:
     """a xor b on nibbles as sum_{p,q} c[p,q] A^p B^q over the zeta16 power bases."""
 
@@ -94,9 +116,13 @@ class XOR4LUT:
             for p in range(16) for q in range(16) if abs(coeffs[p, q]) > 1e-12
         }
         self.terms = [(p, q, complex(coeffs[p, q])) for (p, q) in self.pt]
+        self.exps_a = sorted({p for p, _, _ in self.terms})
+        self.exps_b = sorted({q for _, q, _ in self.terms})
 
-    def _build_power_basis_16(self, ct) -> Dict[int, Any]:
+    def _build_power_basis_16(self, ct, exps=None) -> Dict[int, Any]:
         eng = self.ctx
+        if exps is not None and getattr(eng, "fused", False) and PRUNE_BASIS:
+            return _zeta16_basis_pruned(eng, ct, exps)
 
         def quiet_intt(x):
             try:
@@ -131,10 +157,11 @@ class XOR4LUT:
             lvl = min(a_ct.level, b_ct.level)
             a_ct, b_ct = eng.level_down(a_ct, lvl), eng.level_down(b_ct, lvl)
         if getattr(eng, "fused", False) and LANES_AB:
-            A, B = eng.pair_map(self._build_power_basis_16, (a_ct,), (b_ct,))     # independent: two stream lanes
+            A, B = eng.pair_map(self._build_power_basis_16, (a_ct, self.exps_a), (b_ct, self.exps_b))   # two stream lanes
         else:
-            A = self._build_power_basis_16(a_ct)
-            B = self._build_power_basis_16(b_ct)
+            fused = getattr(eng, "fused", False)
+            A = self._build_power_basis_16(a_ct, self.exps_a if fused else None)
+            B = self._build_power_basis_16(b_ct, self.exps_b if fused else None)
         if getattr(eng, "fused", False):
             # same polynomial, one tensor accumulation and ONE relinearisation (csrc/lut.cu) instead of 64
             return eng.lut2([A.get(k) for k in range(16)], [B.get(k) for k in range(16)], self.terms)
@@ -290,8 +317,10 @@ class _MixBase:
         self.sc = ctx.engine.slot_count
         self._coeffs = _GFTables()
 
-    def _basis16(self, ct) -> Dict[int, Any]:
+    def _basis16(self, ct, exps=None) -> Dict[int, Any]:
         eng = self.ctx
+        if exps is not None and getattr(eng, "fused", False) and PRUNE_BASIS:
+            return _zeta16_basis_pruned(eng, ct, exps)
         try:
             pos = eng.make_power_basis(ct, 8)
         except RuntimeError:
@@ -327,7 +356,8 @@ class _MixBase:
         if getattr(self.ctx, "fused", False):
             # the reference rebuilds both 16-power bases for the hi and the lo table (mixcol_final.py:82-83);
             # they are identical, so the fused path builds them once
-            bases = self.ctx.pair_map(self._basis16, (ct_hi,), (ct_lo,))
+            ents = [e for which in ("hi", "lo") for e in tables.gf_mult_entries(mult, which)]
+            bases = self.ctx.pair_map(self._basis16, (ct_hi, {p for p, _, _ in ents}), (ct_lo, {q for _, q, _ in ents}))
             return self.ctx.pair_map(self._eval2, (ct_hi, ct_lo, mult, "hi", bases), (ct_hi, ct_lo, mult, "lo", bases))
         return self._eval2(ct_hi, ct_lo, mult, "hi"), self._eval2(ct_hi, ct_lo, mult, "lo")
 

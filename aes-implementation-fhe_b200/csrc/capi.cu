@@ -189,6 +189,17 @@ int ckks_power_basis(ckks_engine* e, ckks_ct* a, int degree, ckks_ct** out) {
         for (int i = 0; i < degree; i++) out[i] = H(v[i]);
     });
 }
+int ckks_power_basis_sparse(ckks_engine* e, ckks_ct* a, int degree, const int* exponents, int n, ckks_ct** out) {
+    return guard([&] {
+        std::vector<unsigned char> need(degree > 0 ? degree : 1, 0);
+        for (int i = 0; i < n; i++) {
+            if (exponents[i] < 1 || exponents[i] > degree) throw std::runtime_error("make_power_basis: exponent out of range");
+            need[exponents[i] - 1] = 1;
+        }
+        std::vector<Ct*> v = e->E->power_basis(C(a), degree, need.data());
+        for (int i = 0; i < degree; i++) out[i] = v[i] ? H(v[i]) : nullptr;
+    });
+}
 int ckks_conjugate(ckks_engine* e, const ckks_ct* a, ckks_ct** out) { return guard([&] { *out = H(e->E->conjugate(C(a))); }); }
 int ckks_rotate(ckks_engine* e, const ckks_ct* a, long steps, ckks_ct** out) {
     return guard([&] { *out = H(e->E->rotate(C(a), steps)); });

@@ -1477,11 +1477,22 @@ std::vector<Ct*> Engine::rotate_hoisted(const Ct* a, const std::vector<long>& st
 }
 
 // [a^1 .. a^degree], a^k = a^(k//2) * a^((k+1)//2)  (depth ceil(log2 k))
-std::vector<Ct*> Engine::power_basis(Ct* a, int degree) {
+// `need` (optional, degree flags): only the flagged powers and the intermediates their products use are computed, with
+// the same decomposition k = floor(k/2) + ceil(k/2) as the full basis -- so every power that is computed is bit-identical
+// to the one the full basis holds; the others come back as null.  (XOR4 only uses odd exponents: 5 products, not 7.)
+std::vector<Ct*> Engine::power_basis(Ct* a, int degree, const unsigned char* need) {
     if (degree < 1) throw std::runtime_error("make_power_basis: degree must be positive");
     int depth = 0;
     while ((1 << depth) < degree) depth++;
     need_levels(a->level, depth, "make_power_basis");
+    std::vector<unsigned char> want(degree + 1, need ? 0 : 1);
+    if (need) {
+        for (int k = degree; k >= 1; k--) {
+            if (need[k - 1]) want[k] = 1;
+            if (want[k] && k > 1) want[k / 2] = want[(k + 1) / 2] = 1;
+        }
+        want[1] = 1;
+    }
     std::vector<Ct*> out(degree, nullptr);
     out[0] = copy(a);
     bool forked = false;
@@ -1489,11 +1500,15 @@ std::vector<Ct*> Engine::power_basis(Ct* a, int degree) {
         // generation g holds the powers 2^(g-1) < k <= 2^g; they only need powers of earlier generations, so the
         // products of one generation are independent: up to 8 of them run on separate stream lanes
         for (int lo = 1; lo < degree; lo *= 2) {
-            const int hi = std::min(2 * lo, degree), cnt = hi - lo;
+            const int hi = std::min(2 * lo, degree);
+            int cnt = 0;
+            for (int k = lo + 1; k <= hi; k++) cnt += want[k];
             const int lanes = std::min(cnt, 8);
             if (lanes > 1) { fork(lanes); forked = true; }
+            int slot = 0;
             for (int k = lo + 1; k <= hi; k++) {
-                if (lanes > 1) set_lane((k - lo - 1) % lanes);
+                if (!want[k]) continue;
+                if (lanes > 1) set_lane(slot++ % lanes);
                 out[k - 1] = mul(out[k / 2 - 1], out[(k + 1) / 2 - 1]);
             }
             if (lanes > 1) { join(); forked = false; }

@@ -220,7 +220,7 @@ class Engine {
     Ct* conjugate(const Ct* a);
     Ct* apply_galois(const Ct* a, u64 g);
     std::vector<Ct*> rotate_hoisted(const Ct* a, const std::vector<long>& steps);
-    std::vector<Ct*> power_basis(Ct* a, int degree);
+    std::vector<Ct*> power_basis(Ct* a, int degree, const unsigned char* need = nullptr);
     Ct* copy(const Ct* a);
     Ct* lut2(const std::vector<Ct*>& A, const std::vector<Ct*>& B, const int* p, const int* q, const double* coef,
              int nterms);

@@ -439,6 +439,15 @@ class Engine:
         _capi.check(self._lib.ckks_power_basis(self._ptr, ct._h, int(degree), arr))
         return [Ciphertext(self, arr[i]) for i in range(int(degree))]
 
+    def make_power_basis_sparse(self, ct: Ciphertext, degree: int, exponents: Iterable[int],
+                                relin: Optional[RelinearizationKey] = None) -> List[Optional[Ciphertext]]:
+        """`make_power_basis` restricted to `exponents` (and the intermediates their products need): element k-1 is
+        ct^k, bit-identical to the full basis, or None when that power was not needed."""
+        ex = np.asarray(sorted(set(int(k) for k in exponents)), dtype=np.int32)
+        arr = (C.c_void_p * int(degree))()
+        _capi.check(self._lib.ckks_power_basis_sparse(self._ptr, ct._h, int(degree), ex, len(ex), arr))
+        return [Ciphertext(self, arr[i]) if arr[i] else None for i in range(int(degree))]
+
     def conjugate(self, ct: Ciphertext, key: Optional[ConjugationKey] = None) -> Ciphertext:
         return self._new(self._lib.ckks_conjugate, ct._h)
 

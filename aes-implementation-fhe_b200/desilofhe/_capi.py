@@ -81,6 +81,7 @@ def load():
         "ckks_mul_i": (i32, [vp, vp, i32, pp]),
         "ckks_level_down": (i32, [vp, vp, i32, pp]),
         "ckks_power_basis": (i32, [vp, vp, i32, pp]),
+        "ckks_power_basis_sparse": (i32, [vp, vp, i32, i32p, i32, pp]),
         "ckks_conjugate": (i32, [vp, vp, pp]),
         "ckks_rotate": (i32, [vp, vp, lng, pp]),
         "ckks_rotate_hoisted": (i32, [vp, vp, lngp, i32, pp]),

@@ -112,6 +112,10 @@ int ckks_level_down(ckks_engine* e, ckks_ct* a, int level, ckks_ct** out);
 
 /* make_power_basis(ct, degree, relin_key) -> [ct^1 .. ct^degree] (engine_context.py:100-101) */
 int ckks_power_basis(ckks_engine* e, ckks_ct* a, int degree, ckks_ct** out /* degree handles */);
+/* the same basis restricted to the listed exponents and the intermediates their products need (same products, so the
+ * powers that are computed are bit-identical to ckks_power_basis'); handles of powers that were not computed are NULL.
+ * The XOR4 table (xor4_lut.py:10-77) only has odd exponents: 5 products and 4 conjugations per base instead of 7 + 7. */
+int ckks_power_basis_sparse(ckks_engine* e, ckks_ct* a, int degree, const int* exponents, int n, ckks_ct** out);
 /* conjugate(ct, conj_key) (engine_context.py:103-104) */
 int ckks_conjugate(ckks_engine* e, const ckks_ct* a, ckks_ct** out);
 /* rotate(ct, rot_key, steps): out = np.roll(slots, steps) (engine_context.py:127-132, shift_rows.py:35-37) */

@@ -184,6 +184,15 @@ def test_power_basis_and_level_errors(pair):
         assert np.array_equal(pair.export(x), y.c)
     assert [x.level for x in pb] == [c.level - d for d in (0, 1, 2, 2, 3, 3, 3, 3)]
     assert np.abs(eng.decrypt(pb[7]) - z ** 8).max() < 1e-6
+    # pruned basis (XOR4's odd exponents): same products, so bit-identical to the oracle's full basis; 6 and 8 are skipped
+    c0 = eng.counters()
+    sp = eng.make_power_basis_sparse(c, 8, [1, 3, 5, 7], pair.rk)
+    assert eng.counters()["mul_cc"] - c0["mul_cc"] == 5
+    assert [x is not None for x in sp] == [True, True, True, True, True, False, True, False]
+    for k in (1, 2, 3, 4, 5, 7):
+        assert np.array_equal(pair.export(sp[k - 1]), opb[k - 1].c)
+    with pytest.raises(RuntimeError, match="out of range"):
+        eng.make_power_basis_sparse(c, 8, [9], pair.rk)
     low = eng.level_down(c, 1)
     with pytest.raises(RuntimeError) as ei:
         eng.make_power_basis(low, 8, pair.rk)
