@@ -44,7 +44,7 @@ ROUNDS_PER_BLOCK = 10
 METRIC = "aes128_fhe_blocks_per_s"
 UNIT = "blocks/s (2048 blocks per ciphertext pair, 10 round-equivalents per block)"
 WORKLOAD = ("configs[1]: one AES-128 encryption round (SubBytes, ShiftRows, MixColumns + 2 bootstraps, AddRoundKey, "
-            "5 hard renorms) on one ciphertext pair per GPU, N=2^16, 2048 packed blocks per pair")
+            "5 hard renorms) on `pairs_per_gpu` independent ciphertext pairs per GPU, N=2^16, 2048 packed blocks per pair")
 
 
 # ------------------------------------------------------------------------------------------ plain AES round (checker)
