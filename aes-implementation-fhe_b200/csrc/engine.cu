@@ -171,6 +171,7 @@ Engine::Engine(const Params& P) : prm(P) {
     st = streams[0] = dev::stream_create();
     lane_made[0] = lane_busy[0] = true;
     arenas[0] = &main_arena;
+    if (const char* v = getenv("CKKS_NTT_FUSE")) fuse_ntt = atoi(v) != 0;
     mod = prm.q;
     mod.insert(mod.end(), prm.p.begin(), prm.p.end());
     if ((int)mod.size() > CKKS_MAX_MODULI) throw std::runtime_error("engine: too many moduli");
@@ -668,6 +669,18 @@ void Engine::run_ntt(const u64* src, u64* dst, const NttJob& J, bool inverse, lo
     if (t) { t->mark_stop(st); prof_limbs += limbs; prof_calls++; }
     n_ntt_limbs += limbs;
 }
+// forward transform with the rescale-lift prologue and / or the (a - NTT(x)) * s epilogue fused in (ntt.cuh: NttFuse)
+void Engine::run_ntt_fused(const u64* src, u64* dst, const NttJob& J, const NttFuse& F, long limbs) {
+    dev::Timer* t = nullptr;
+    if (prof_on) {
+        if (prof_used == prof_timers.size()) prof_timers.emplace_back();
+        t = &prof_timers[prof_used++];
+        t->start(st);
+    }
+    ntt_forward_fused(src, dst, J, tabs, F, st);
+    if (t) { t->mark_stop(st); prof_limbs += limbs; prof_calls++; }
+    n_ntt_limbs += limbs;
+}
 void Engine::profile_begin() {
     prof_on = true;
     prof_used = 0;
@@ -1154,9 +1167,25 @@ void Engine::ks_moddown(u64* acc, int level, int drop, u64* out) {
     launch_base_convert(ks, conv, acc, moddown_table_dev(level, drop), 0, K() + drop, nout, 2, (size_t)rows * n,
                         (size_t)nout * n, st);
     std::vector<int> qi = mods_q(level - drop);
-    ntt_rows(conv, qi, qi, false, 2, (size_t)nout * n);
-    launch_sub_mul_scalar(ks, out, acc, conv, limb_list(qi), moddown_inv(level, drop), 2,
-                          PolyStride{(size_t)nout * n, (size_t)rows * n, (size_t)nout * n}, st);
+    if (fuse_ntt) {
+        // out = (acc - NTT(conv)) * (P q_dropped)^-1 as the epilogue of the transform's second pass
+        NttJob J;
+        memset(&J, 0, sizeof(J));
+        J.n = nout; J.nz = 2;
+        J.szs = J.dzs = (size_t)nout * n;
+        for (int z = 0; z < 2; z++)
+            for (int i = 0; i < nout; i++) { J.rows[z][i] = J.srows[z][i] = (unsigned char)i; J.mods[z][i] = (unsigned char)i; }
+        NttFuse F;
+        F.pro_mod = -1;
+        F.ep_a = acc; F.ep_azs = (size_t)rows * n;
+        F.ep_out = out; F.ep_ozs = (size_t)nout * n;
+        F.s = moddown_inv(level, drop);
+        run_ntt_fused(conv, conv, J, F, 2L * nout);
+    } else {
+        ntt_rows(conv, qi, qi, false, 2, (size_t)nout * n);
+        launch_sub_mul_scalar(ks, out, acc, conv, limb_list(qi), moddown_inv(level, drop), 2,
+                              PolyStride{(size_t)nout * n, (size_t)rows * n, (size_t)nout * n}, st);
+    }
     release(conv);
     if (drop) n_rescale++;
 }
@@ -1202,10 +1231,28 @@ void Engine::rescale_into(u64* out, const u64* in, int npoly, int level) {
     std::vector<int> lo = mods_q(level - 1);
     LimbList ll = limb_list(lo);
     u64* delta = alloc((size_t)npoly * level * n);
-    launch_rescale_delta(ks, delta, last, ll, level, npoly, PolyStride{(size_t)level * n, n, 0}, st);
-    ntt_rows(delta, lo, lo, false, npoly, (size_t)level * n);
-    launch_sub_mul_scalar(ks, out, in, delta, ll, sl_qinv[level], npoly,
-                          PolyStride{(size_t)level * n, (size_t)nl * n, (size_t)level * n}, st);
+    if (fuse_ntt) {
+        // the centred lift of the dropped limb is the prologue of the transform's first pass, (in - NTT(delta)) q_l^-1
+        // the epilogue of its second: four launches per rescale instead of six, delta never goes to HBM in full
+        NttJob J;
+        memset(&J, 0, sizeof(J));
+        J.n = level; J.nz = npoly;
+        J.szs = n;
+        J.dzs = (size_t)level * n;
+        for (int z = 0; z < npoly; z++)
+            for (int i = 0; i < level; i++) { J.srows[z][i] = 0; J.rows[z][i] = (unsigned char)i; J.mods[z][i] = (unsigned char)i; }
+        NttFuse F;
+        F.pro_mod = level;
+        F.ep_a = in; F.ep_azs = (size_t)nl * n;
+        F.ep_out = out; F.ep_ozs = (size_t)level * n;
+        F.s = sl_qinv[level];
+        run_ntt_fused(last, delta, J, F, (long)npoly * level);
+    } else {
+        launch_rescale_delta(ks, delta, last, ll, level, npoly, PolyStride{(size_t)level * n, n, 0}, st);
+        ntt_rows(delta, lo, lo, false, npoly, (size_t)level * n);
+        launch_sub_mul_scalar(ks, out, in, delta, ll, sl_qinv[level], npoly,
+                              PolyStride{(size_t)level * n, (size_t)nl * n, (size_t)level * n}, st);
+    }
     release(last);
     release(delta);
     n_rescale++;

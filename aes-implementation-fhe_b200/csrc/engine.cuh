@@ -241,6 +241,8 @@ class Engine {
     void ntt_rows(u64* data, const std::vector<int>& rows, const std::vector<int>& mods, bool inverse, int nz = 1,
                   size_t zstride = 0);
     void run_ntt(const u64* src, u64* dst, const NttJob& J, bool inverse, long limbs);
+    void run_ntt_fused(const u64* src, u64* dst, const NttJob& J, const NttFuse& F, long limbs);
+    bool fuse_ntt = true;                  // CKKS_NTT_FUSE=0: stand-alone lift / subtract-scale kernels (A/B timing)
     void profile_begin();
     void profile_end(double* ms, long* calls, long* limbs);
     Decomp decompose(const u64* d, int level);

@@ -246,10 +246,17 @@ __device__ __forceinline__ FpMod fp_mod(const ModConst& mc) {
 // LOGR = 4: R = 16 rows,  tile = 256 columns x 16 rows, one radix-16 round (X = 1).
 // Shared memory: 4096 data words ([row][16 columns] / [k][256 columns]) + table entries 1..255 and their companions.
 constexpr int kPassAWords = 4096 + 2 * 256;
-template <int LOGR, bool FP>
+// rescale lift of one coefficient x mod q_l into the row modulus (spec S6), see NttFuse
+__device__ __forceinline__ u64 pro_lift(u64 x, u64 ql, const ModConst& mc) {
+    const u64 h = ql >> 1;
+    u64 t = x + h;
+    t = t >= ql ? t - ql : t;
+    return sub_mod(barrett_reduce64(t, mc), barrett_reduce64(h, mc), mc.q);
+}
+template <int LOGR, bool FP, bool PRO>
 __device__ __forceinline__ void fwd_passA_body(const u64* __restrict__ src, u64* __restrict__ dst, u64* sm, int limb,
                                                int slimb, int tile, size_t N, const ModConst& mc, const NttTables& T,
-                                               int mod) {
+                                               int mod, u64 ql) {
     constexpr int RG = (1 << LOGR) / 16;          // row groups per column: 16 or 1
     constexpr int TC = kThreads / RG;             // columns per CTA: 16 or 256
     constexpr int NTW = LOGR == 8 ? 255 : 15;
@@ -283,14 +290,20 @@ __device__ __forceinline__ void fwd_passA_body(const u64* __restrict__ src, u64*
             if (FP) {
                 double x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = ull2d_rn(sd[(rr + 16 * k) * TC + c]);
+                for (int k = 0; k < 16; k++) {
+                    const u64 v = sd[(rr + 16 * k) * TC + c];
+                    x[k] = ull2d_rn(PRO ? pro_lift(v, ql, mc) : v);
+                }
                 fwd16_fp(x, t1, fm);
 #pragma unroll
                 for (int k = 0; k < 16; k++) sd[(rr + 16 * k) * TC + c] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
             } else {
                 u64 x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = sd[(rr + 16 * k) * TC + c];
+                for (int k = 0; k < 16; k++) {
+                    const u64 v = sd[(rr + 16 * k) * TC + c];
+                    x[k] = PRO ? pro_lift(v, ql, mc) : v;
+                }
                 fwd16(x, t1, q);
 #pragma unroll
                 for (int k = 0; k < 16; k++) sd[(rr + 16 * k) * TC + c] = x[k];
@@ -325,14 +338,20 @@ __device__ __forceinline__ void fwd_passA_body(const u64* __restrict__ src, u64*
             if (FP) {
                 double x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = ull2d_rn(sd[k * 256 + tid]);
+                for (int k = 0; k < 16; k++) {
+                    const u64 v = sd[k * 256 + tid];
+                    x[k] = ull2d_rn(PRO ? pro_lift(v, ql, mc) : v);
+                }
                 fwd16_fp(x, t1, fm);
 #pragma unroll
                 for (int k = 0; k < 16; k++) d0[(size_t)k * 256] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
             } else {
                 u64 x[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = sd[k * 256 + tid];
+                for (int k = 0; k < 16; k++) {
+                    const u64 v = sd[k * 256 + tid];
+                    x[k] = PRO ? pro_lift(v, ql, mc) : v;
+                }
                 fwd16(x, t1, q);
 #pragma unroll
                 for (int k = 0; k < 16; k++) d0[(size_t)k * 256] = x[k];
@@ -351,17 +370,34 @@ ntt_fwd_passA(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CON
     src += blockIdx.z * J.szs;
     dst += blockIdx.z * J.dzs;
     const ModConst mc = T.mc[mod];
-    if (use_fp(mc.q)) fwd_passA_body<LOGR, true>(src, dst, sm, limb, slimb, tile, N, mc, T, mod);
-    else fwd_passA_body<LOGR, false>(src, dst, sm, limb, slimb, tile, N, mc, T, mod);
+    if (use_fp(mc.q)) fwd_passA_body<LOGR, true, false>(src, dst, sm, limb, slimb, tile, N, mc, T, mod, 0);
+    else fwd_passA_body<LOGR, false, false>(src, dst, sm, limb, slimb, tile, N, mc, T, mod, 0);
+}
+// pass A with the rescale-lift prologue (NttFuse::pro_mod)
+template <int LOGR>
+__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_A)
+ntt_fwd_passA_lift(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T, int pro_mod) {
+    CKKS_SHARED __align__(16) u64 sm[kPassAWords];
+    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
+    const int limb = J.rows[blockIdx.z][blockIdx.y], slimb = J.srows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const size_t N = (size_t)1 << T.logn;
+    src += blockIdx.z * J.szs;
+    dst += blockIdx.z * J.dzs;
+    const ModConst mc = T.mc[mod];
+    const u64 ql = T.mc[pro_mod].q;
+    if (use_fp(mc.q)) fwd_passA_body<LOGR, true, true>(src, dst, sm, limb, slimb, tile, N, mc, T, mod, ql);
+    else fwd_passA_body<LOGR, false, true>(src, dst, sm, limb, slimb, tile, N, mc, T, mod, ql);
 }
 
 // ============================================================================================ forward, pass B
 // 16 rows of 256 per CTA; row with global index Rg is rooted at table index R_n + Rg.  Data goes global -> registers,
 // the twiddles come from the global tables (128-bit pair loads); one shared-memory exchange between the two rounds and
 // one to make the final store coalesced.
-template <bool FP>
+template <bool FP, bool EP>
 __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int tile, u32 Rn, const ModConst& mc,
-                                               const NttTables& T, int mod, size_t N) {
+                                               const NttTables& T, int mod, size_t N, const u64* __restrict__ ep_a,
+                                               u64* __restrict__ ep_out, u64 sv, u64 svs) {
     const u64 q = mc.q;
     const u64* W = (FP ? reinterpret_cast<const u64*>(T.fwd_d) : T.fwd) + (size_t)mod * N;
     const u64* C = (FP ? reinterpret_cast<const u64*>(T.fwd_q) : T.fwd_s) + (size_t)mod * N;
@@ -408,8 +444,18 @@ __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int
     }
     BLOCK_SYNC;
     FOR_THREADS {
+        if (EP) {
+            // fused tail of ModDown / rescale: (a - NTT(x)) * s, the transform itself is never stored
+            u64 a[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) g[k * 256 + threadIdx.x] = sm[pad16(k * 256 + threadIdx.x)];
+            for (int k = 0; k < 16; k++) a[k] = ep_a[k * 256 + threadIdx.x];
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                ep_out[k * 256 + threadIdx.x] = shoup_mul(sub_mod(a[k], sm[pad16(k * 256 + threadIdx.x)], q), sv, svs, q);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) g[k * 256 + threadIdx.x] = sm[pad16(k * 256 + threadIdx.x)];
+        }
     }
 }
 __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_B)
@@ -423,8 +469,27 @@ ntt_fwd_passB(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
     data += blockIdx.z * J.dzs;
     const ModConst mc = T.mc[mod];
     u64* g = data + (size_t)limb * N + (size_t)tile * 16 * 256;
-    if (use_fp(mc.q)) fwd_passB_body<true>(g, sm, tile, Rn, mc, T, mod, N);
-    else fwd_passB_body<false>(g, sm, tile, Rn, mc, T, mod, N);
+    if (use_fp(mc.q)) fwd_passB_body<true, false>(g, sm, tile, Rn, mc, T, mod, N, nullptr, nullptr, 0, 0);
+    else fwd_passB_body<false, false>(g, sm, tile, Rn, mc, T, mod, N, nullptr, nullptr, 0, 0);
+}
+// pass B with the (a - NTT(x)) * s epilogue (NttFuse::ep_*)
+__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_B)
+ntt_fwd_passB_ep(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T, const GRID_CONST NttFuse F) {
+    CKKS_SHARED u64 sm[kPassBData];
+    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
+    const int limb = J.rows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const size_t N = (size_t)1 << T.logn;
+    const u32 Rn = (u32)(N >> 8);
+    data += blockIdx.z * J.dzs;
+    const ModConst mc = T.mc[mod];
+    const size_t off = (size_t)limb * N + (size_t)tile * 16 * 256;
+    u64* g = data + off;
+    const u64* ep_a = F.ep_a + blockIdx.z * F.ep_azs + off;
+    u64* ep_out = F.ep_out + blockIdx.z * F.ep_ozs + off;
+    const u64 sv = F.s.v[blockIdx.y], svs = F.s.vs[blockIdx.y];
+    if (use_fp(mc.q)) fwd_passB_body<true, true>(g, sm, tile, Rn, mc, T, mod, N, ep_a, ep_out, sv, svs);
+    else fwd_passB_body<false, true>(g, sm, tile, Rn, mc, T, mod, N, ep_a, ep_out, sv, svs);
 }
 
 // ============================================================================================ inverse, pass B^-1
@@ -622,6 +687,23 @@ void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, 
         throw std::runtime_error("ntt: only N = 2^16 and N = 2^12 are built");
     }
     LAUNCH(ntt_fwd_passB, gridB, dim3(kThreads), st, dst, J, T);
+}
+
+void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J, const NttTables& T, const NttFuse& F, dev_stream st) {
+    if (J.n == 0 || J.nz == 0) return;
+    const unsigned R = 1u << (T.logn - 8);
+    dim3 gridB(R / 16, J.n, J.nz);
+    if (T.logn != 16 && T.logn != 12) throw std::runtime_error("ntt: only N = 2^16 and N = 2^12 are built");
+    dim3 gridA(T.logn == 16 ? 16 : 1, J.n, J.nz);
+    if (F.pro_mod >= 0) {
+        if (T.logn == 16) LAUNCH(ntt_fwd_passA_lift<8>, gridA, dim3(kThreads), st, src, dst, J, T, F.pro_mod);
+        else LAUNCH(ntt_fwd_passA_lift<4>, gridA, dim3(kThreads), st, src, dst, J, T, F.pro_mod);
+    } else {
+        if (T.logn == 16) LAUNCH(ntt_fwd_passA<8>, gridA, dim3(kThreads), st, src, dst, J, T);
+        else LAUNCH(ntt_fwd_passA<4>, gridA, dim3(kThreads), st, src, dst, J, T);
+    }
+    if (F.ep_out) LAUNCH(ntt_fwd_passB_ep, gridB, dim3(kThreads), st, dst, J, T, F);
+    else LAUNCH(ntt_fwd_passB, gridB, dim3(kThreads), st, dst, J, T);
 }
 
 void ntt_inverse(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st) {

@@ -31,5 +31,21 @@ struct NttJob {
     unsigned char cnt[NTT_MAX_Z];     // items of slice z (0 = all n); CTAs beyond it exit at once
 };
 
+// Work fused into the forward transform (one launch less each, and the intermediate never goes to HBM):
+//   prologue (pass A, pro_mod >= 0): every source row holds the SAME kind of data, one coefficient-domain limb modulo
+//     q_l = mc[pro_mod]; item i transforms the centred rescale lift ((x + h) mod q_l) mod q_i - (h mod q_i), h = q_l >> 1
+//     (spec S6; the stand-alone kernel is k_rescale_delta);
+//   epilogue (pass B, ep_out != null): instead of storing NTT(x), item i of slice z stores (a - NTT(x)) * s[i] into row
+//     rows[z][i] of ep_out + z*ep_ozs, a = the same row of ep_a + z*ep_azs (the tail of ModDown and of a rescale; the
+//     stand-alone kernel is k_sub_mul_scalar).
+struct NttFuse {
+    int pro_mod;
+    const u64* ep_a;
+    u64* ep_out;
+    size_t ep_azs, ep_ozs;
+    ScalarList s;
+};
+
 void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st);
+void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J, const NttTables& T, const NttFuse& F, dev_stream st);
 void ntt_inverse(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st);
