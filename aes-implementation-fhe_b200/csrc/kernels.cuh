@@ -4,7 +4,9 @@
 
 #define BC_MAX_SRC 16
 #define BC_MAX_TGT 48
-#define BC_CHUNK 6
+#ifndef BC_CHUNK
+#define BC_CHUNK 24
+#endif
 
 // element strides between consecutive polynomials (blockIdx.z) for each pointer of a kernel
 struct PolyStride {

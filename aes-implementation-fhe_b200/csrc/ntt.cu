@@ -36,10 +36,10 @@ namespace {
 
 constexpr int kThreads = 256;
 #ifndef NTT_MIN_BLOCKS_A
-#define NTT_MIN_BLOCKS_A 3    // pass A: 37 KB static shared memory, register cap 80
+#define NTT_MIN_BLOCKS_A 4    // pass A: 37 KB static shared memory, register cap 64 (A/B in graph mode: profiles/README.md)
 #endif
 #ifndef NTT_MIN_BLOCKS_B
-#define NTT_MIN_BLOCKS_B 3    // pass B: 35 KB static shared memory, register cap 80
+#define NTT_MIN_BLOCKS_B 4    // pass B: 35 KB static shared memory, register cap 64
 #endif
 #ifndef NTT_FP64
 #define NTT_FP64 1            // 0: every limb takes the integer path (A/B measurement)

@@ -270,7 +270,11 @@ def run_ours(args) -> None:
             return step_resident()
     else:
         # one captured round per resident pair: private arena, static inputs = the pair's state and the round key
+        if args.serial_graphs:                 # A/B: no stream lanes inside a graph, concurrency only across pairs
+            eng.set_lanes_enabled(False)
         rounds = [aes_fhe.CapturedRound(pipe, states[j], rk_ct[1]) for j in range(npairs)]
+        if args.serial_graphs:
+            eng.set_lanes_enabled(True)
         graph_info = rounds[0].info()
 
         def step_resident():
@@ -412,6 +416,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--pairs", type=int, default=4, help="independent ciphertext pairs per GPU, one captured round each")
+    ap.add_argument("--serial-graphs", action="store_true", help="A/B: capture each round without stream lanes")
     ap.add_argument("--no-graph", action="store_true", help="issue the round eagerly, call by call (one pair; A/B)")
     ap.add_argument("--dry-run-emulation", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--host-floor", action="store_true",
