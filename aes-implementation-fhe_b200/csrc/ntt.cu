@@ -95,6 +95,17 @@ struct TwGlobal {
         ldg_pair(C + (X << r) + 2 * gh, c0, c1);
     }
 };
+#ifndef NTT_PREFETCH
+#define NTT_PREFETCH 0        // 0: off (default), 1: towards L1, 2: towards L2 -- measured slower on the B200 (profiles/r1_ab_prefetch.txt)
+#endif
+// the 1 + 2 + 4 + 8 entries (and companions) of the radix-16 block rooted at X: asked for while the first round computes
+__device__ __forceinline__ void tw_prefetch(const u64* W, const u64* C, u32 X) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        if (NTT_PREFETCH == 1) { prefetch_l1(W + (X << r)); prefetch_l1(C + (X << r)); }
+        if (NTT_PREFETCH == 2) { prefetch_l2(W + (X << r)); prefetch_l2(C + (X << r)); }
+    }
+}
 template <typename TW>
 __device__ __forceinline__ void tw_stage(const TW& tw, int r, u64 (&w)[8], u64 (&c)[8]) {
     if (r == 0) tw.get(0, 0, w[0], c[0]);
@@ -405,6 +416,7 @@ __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int
     FOR_THREADS {
         const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
         const TwGlobal t1{W, C, Rn + (u32)(tile * 16 + row)};
+        if (NTT_PREFETCH) tw_prefetch(W, C, 16u * (Rn + (u32)(tile * 16 + row)) + (u32)jj);
         if (FP) {
             double x[16];
 #pragma unroll
@@ -503,6 +515,7 @@ __device__ __forceinline__ void inv_passB_body(const u64* __restrict__ s_in, u64
     FOR_THREADS {
 #pragma unroll
         for (int k = 0; k < 16; k++) cp_async8(sm + pad16(k * 256 + threadIdx.x), s_in + k * 256 + threadIdx.x);
+        if (NTT_PREFETCH) tw_prefetch(W, C, 16u * (Rn + (u32)(tile * 16 + threadIdx.x / 16)) + (u32)(threadIdx.x % 16));
         cp_async_wait_all();
     }
     BLOCK_SYNC;

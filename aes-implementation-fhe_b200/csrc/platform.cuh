@@ -251,6 +251,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(__cvta_generic_to_global(gmem_src)) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// pull a line towards the SM ahead of its use (no register, no shared memory held meanwhile)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p))); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(p))); }
 
 #else
 // =================================================================================== emulation (tests only)
@@ -402,4 +405,6 @@ static inline void ldg_pair(const u64* p, u64& a, u64& b) { a = p[0]; b = p[1]; 
 static inline void cp_async8(void* d, const void* s) { memcpy(d, s, 8); }
 static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
 static inline void cp_async_wait_all() {}
+static inline void prefetch_l1(const void*) {}
+static inline void prefetch_l2(const void*) {}
 #endif
