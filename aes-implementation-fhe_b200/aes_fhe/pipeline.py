@@ -105,8 +105,48 @@ class AESPipeline:
         ct_hi, ct_lo = self.add_round_key(ct_hi, ct_lo, key_hi, key_lo)
         return self._renorm_pair(ct_hi, ct_lo, depth=SUBBYTES_DEPTH)
 
+    # ---- one middle round of the README-order decryption (README.md:85-95; driver R1 below) ----
+    def decrypt_round(self, ct_hi, ct_lo, key_hi, key_lo) -> Pair:
+        need = SHIFTROWS_DEPTH + SUBBYTES_DEPTH           # levels the next round's InvShiftRows + InvSubBytes consume
+        ct = self.inv_shift_rows(ct_hi, ct_lo)
+        ct = self.inv_sub_bytes(*ct)
+        ct = self._renorm_pair(*ct, depth=XOR4_DEPTH)
+        ct = self.add_round_key(*ct, key_hi, key_lo)
+        ct = self._renorm_pair(*ct, depth=GF_DEPTH + XOR4_DEPTH)
+        ct = self.inv_mix_columns(*ct)
+        # InvMixColumns ends with a bootstrap; an engine whose bootstrap returns fewer than 14 levels re-encrypts here
+        # ("post-bootstrap level >= 14, or >= 5 if the decrypt driver renorms instead")
+        lvl = getattr(ct[0], "level", None)
+        if self.use_hard_renorm_between_steps and lvl is not None and lvl < need:
+            ct = self._renorm_pair(*ct, depth=need)
+        return ct
+
+    def _captured(self, which: str, state: Pair, key: Pair) -> "CapturedRound":
+        """The middle round of one direction recorded as a CUDA graph on first use (same shapes afterwards)."""
+        cache = self.__dict__.setdefault("_round_graphs", {})
+        sig = (which, state[0].level, state[1].level, key[0].level, key[1].level)
+        if sig not in cache:
+            cache[sig] = CapturedRound(self, state, key, inverse=(which == "dec"))
+        return cache[sig]
+
+    def release_graphs(self) -> None:
+        for g in self.__dict__.pop("_round_graphs", {}).values():
+            g.close()
+
     # ---- full flows ----
-    def encrypt(self, state, round_keys, debug: Optional[Dict[str, Any]] = None) -> Pair:
+    def encrypt(self, state, round_keys, debug: Optional[Dict[str, Any]] = None, captured: bool = False) -> Pair:
+        """`captured=True` (B200 engine): rounds 1..9 are nine replays of ONE recorded round graph (the round key is a
+        graph input); the result is bit-identical to the eager flow up to the encryption randomness of the renorms."""
+        if captured and debug is None:
+            ct = self.encoder.encode(np.asarray(state, dtype=np.uint8))
+            rk = self._prepare_round_keys(round_keys)
+            ct = self._renorm_pair(*self.add_round_key(*ct, *rk[0]), depth=SUBBYTES_DEPTH)
+            for r in range(1, 10):
+                # the graph's static outputs feed its static inputs: the copy is enqueued before the next replay
+                ct = self._captured("enc", ct, rk[r])(*ct, *rk[r])
+            ct = self._renorm_pair(*self.sub_bytes(*ct), depth=SHIFTROWS_DEPTH + XOR4_DEPTH)
+            ct = self.add_round_key(*self.shift_rows(*ct), *rk[10])
+            return self._renorm_pair(*ct)
         if debug is not None:
             debug.clear()
         ct = self.encoder.encode(np.asarray(state, dtype=np.uint8))
@@ -161,29 +201,19 @@ class AESPipeline:
 
 
 # ------------------------------------------------------------------------------ drivers
-def decrypt_readme_order(pipe, ct_hi, ct_lo, round_keys) -> Pair:
+def decrypt_readme_order(pipe, ct_hi, ct_lo, round_keys, captured: bool = False) -> Pair:
     """R1: inverse of the as-shipped `encrypt`, in the order the reference README lists
-    (README.md:85-95), using only the pipeline's own primitives."""
+    (README.md:85-95), using only the pipeline's own primitives.  `captured=True`: the nine middle rounds are replays
+    of one recorded round graph."""
     rk = pipe._prepare_round_keys(round_keys)
     need = SHIFTROWS_DEPTH + SUBBYTES_DEPTH           # levels InvShiftRows + InvSubBytes consume
-
-    def refill(ct):
-        # InvMixColumns ends with a bootstrap; an engine whose bootstrap returns fewer than 14 levels re-encrypts here
-        # (SURVEY.md App. B: "post-bootstrap level >= 14, or >= 5 if the decrypt driver renorms instead")
-        lvl = getattr(ct[0], "level", None)
-        if pipe.use_hard_renorm_between_steps and lvl is not None and lvl < need:
-            return pipe._renorm_pair(*ct, depth=need)
-        return ct
-
     ct = pipe.add_round_key(ct_hi, ct_lo, *rk[10])
     ct = pipe._renorm_pair(*ct, depth=need)
     for r in range(9, 0, -1):
-        ct = pipe.inv_shift_rows(*ct)
-        ct = pipe.inv_sub_bytes(*ct)
-        ct = pipe._renorm_pair(*ct, depth=XOR4_DEPTH)
-        ct = pipe.add_round_key(*ct, *rk[r])
-        ct = pipe._renorm_pair(*ct, depth=GF_DEPTH + XOR4_DEPTH)
-        ct = refill(pipe.inv_mix_columns(*ct))
+        if captured:
+            ct = pipe._captured("dec", ct, rk[r])(*ct, *rk[r])
+        else:
+            ct = pipe.decrypt_round(*ct, *rk[r])
     ct = pipe.inv_shift_rows(*ct)
     ct = pipe.inv_sub_bytes(*ct)
     ct = pipe._renorm_pair(*ct, depth=XOR4_DEPTH)
@@ -281,11 +311,13 @@ class CapturedRound:
     ciphertext pairs replay concurrently on separate replay streams.  Needs the device-side hard renorm (no host round
     trip inside the round) and an engine with `capture` (the B200 engine); there is no fallback."""
 
-    def __init__(self, pipe: AESPipeline, state: Pair, round_key: Pair):
+    def __init__(self, pipe: AESPipeline, state: Pair, round_key: Pair, inverse: bool = False):
         if not getattr(pipe.ctx, "device_renorm", False) and pipe.use_hard_renorm_between_steps:
             raise RuntimeError("a captured round needs the device-side renorm (fused engine)")
         self.pipe = pipe
-        self.call = pipe.ctx.engine.capture(pipe.encrypt_round, [*state, *round_key])
+        self.inverse = inverse       # True: the README-order decryption round (`AESPipeline.decrypt_round`)
+        fn = pipe.decrypt_round if inverse else pipe.encrypt_round
+        self.call = pipe.ctx.engine.capture(fn, [*state, *round_key])
 
     def __call__(self, ct_hi, ct_lo, key_hi, key_lo, stream: int = 0) -> Pair:
         out = self.call(ct_hi, ct_lo, key_hi, key_lo, stream=stream)
@@ -320,13 +352,13 @@ class FipsDriver:
     def _perm(x: np.ndarray) -> np.ndarray:
         return np.asarray(x, dtype=np.uint8)[..., ROWMAJOR]
 
-    def encrypt(self, blocks: np.ndarray, round_keys) -> Pair:
+    def encrypt(self, blocks: np.ndarray, round_keys, captured: bool = False) -> Pair:
         rks = [self._perm(rk) for rk in round_keys]
-        return self.pipe.encrypt(self._perm(blocks), rks)
+        return self.pipe.encrypt(self._perm(blocks), rks, captured=captured)
 
-    def decrypt(self, ct_hi, ct_lo, round_keys) -> Pair:
+    def decrypt(self, ct_hi, ct_lo, round_keys, captured: bool = False) -> Pair:
         rks = [self._perm(rk) for rk in round_keys]
-        return decrypt_readme_order(self.pipe, ct_hi, ct_lo, rks)
+        return decrypt_readme_order(self.pipe, ct_hi, ct_lo, rks, captured=captured)
 
     def decode(self, ct_hi, ct_lo) -> np.ndarray:
         out = self.pipe.encoder.decode(ct_hi, ct_lo)

@@ -67,6 +67,24 @@ def plain_round(blocks: np.ndarray, rk: np.ndarray) -> np.ndarray:
     return out ^ rk[None, :]
 
 
+def plain_inv_round(blocks: np.ndarray, rk: np.ndarray) -> np.ndarray:
+    """FIPS-197 middle round of the inverse cipher on (B,16) column-first states: InvShiftRows, InvSubBytes,
+    AddRoundKey, InvMixColumns (the order of the reference README, README.md:85-95)."""
+    from aes_fhe import tables
+    _, isbox = tables.sbox_tables()
+    idx = np.array([(i - 4 * (i % 4)) % 16 for i in range(16)])
+    s = isbox[blocks[:, idx]] ^ rk[None, :]
+    m = {k: np.array([tables.gf_mul(x, k) for x in range(256)], dtype=np.uint8) for k in (9, 11, 13, 14)}
+    out = np.zeros_like(s)
+    for c in range(4):
+        a = [s[:, 4 * c + r] for r in range(4)]
+        out[:, 4 * c + 0] = m[14][a[0]] ^ m[11][a[1]] ^ m[13][a[2]] ^ m[9][a[3]]
+        out[:, 4 * c + 1] = m[9][a[0]] ^ m[14][a[1]] ^ m[11][a[2]] ^ m[13][a[3]]
+        out[:, 4 * c + 2] = m[13][a[0]] ^ m[9][a[1]] ^ m[14][a[2]] ^ m[11][a[3]]
+        out[:, 4 * c + 3] = m[11][a[0]] ^ m[13][a[1]] ^ m[9][a[2]] ^ m[14][a[3]]
+    return out
+
+
 # ------------------------------------------------------------------------------------------ clocks sampler
 class Clocks:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -339,6 +357,26 @@ def run_ours(args) -> None:
     def step_eager():
         return pipe.encrypt_round(*states[0], *rk_ct[1])
 
+    # the other half of BASELINE.json's "s/round (enc+dec)": one middle round of the README-order decryption
+    # (InvShiftRows, InvSubBytes, AddRoundKey, InvMixColumns with the GF 9/11/13/14 LUTs + 2 bootstraps), one pair,
+    # latency of one replay of its captured graph (eager with --no-graph)
+    dec = None
+    if not args.no_dec:
+        dstate = pipe.encoder.encode(drv._perm(blocks[0]), level=FRESH)
+        dwant = plain_inv_round(blocks[0], rks[5])
+        if args.no_graph:
+            dec_step = lambda: pipe.decrypt_round(*dstate, *rk_ct[5])
+            dinfo = None
+        else:
+            drnd = aes_fhe.CapturedRound(pipe, dstate, rk_ct[5], inverse=True)
+            dec_step = lambda: drnd.call.launch(stream=0)
+            dinfo = drnd.info()
+        dec_step()
+        ms_d, dout = timed(dec_step, args.steps)
+        dok = bool(np.array_equal(drv.decode(*dout), dwant))
+        ok = ok and dok
+        dec = {"s_per_round": ms_d * 1e-3 / args.steps, "bytes_exact_vs_fips197_inverse_round": dok, "cuda_graph": dinfo}
+
     # roofline leg: one more resident step with a CUDA-event pair around every NTT call.  The stream lanes are switched
     # off for this step so that an event pair brackets the NTT kernels alone (with lanes on, kernels of other streams
     # run inside the bracket and the per-call time is not a kernel time).
@@ -404,7 +442,9 @@ def run_ours(args) -> None:
                            "pairs_per_gpu": npairs, "cuda_graph": graph_info, "capture_s": round(t_capture, 2),
                            "evk_broadcast_bytes": key_bytes, "setup_s": round(t_keys, 2), "l2": "working set (evaluation keys 87 MiB each, ~60 live ciphertexts) "
                            "exceeds the 126 MB L2; no explicit flush"},
-                "s_per_round": s_round, "bytes_exact_vs_fips197_round": ok,
+                "s_per_round": s_round, "dec_round": dec,
+                "s_per_round_enc_plus_dec": (s_round + dec["s_per_round"]) if dec else None,
+                "bytes_exact_vs_fips197_round": ok,
                 "key_switches_per_step": ks_round, "bootstraps_per_step": (c1["bootstrap"] - c0["bootstrap"]) // args.steps,
                 "rotations_per_s_equiv": ks_round / s_step, "arena": eng.arena_stats(),
                 "e2e": e2e, "gpu_launches": int(launches) * args.steps, "clocks": clk, "roofline": roofline,
@@ -428,6 +468,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--pairs", type=int, default=4, help="independent ciphertext pairs per GPU, one captured round each")
+    ap.add_argument("--no-dec", action="store_true", help="skip the decryption-round latency leg")
     ap.add_argument("--serial-graphs", action="store_true", help="A/B: capture each round without stream lanes")
     ap.add_argument("--no-graph", action="store_true", help="issue the round eagerly, call by call (one pair; A/B)")
     ap.add_argument("--dry-run-emulation", action="store_true", help=argparse.SUPPRESS)

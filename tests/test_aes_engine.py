@@ -167,6 +167,33 @@ def test_captured_round_replays_on_new_inputs(boot_ctx):
 
 
 @pytest.mark.gpu
+def test_config3_config4_with_captured_rounds_gpu():
+    """configs[2] and [3] with the nine middle rounds of each direction replayed from ONE recorded round graph
+    (`captured=True`): FIPS-197 ciphertext, then the round trip back to the plaintext."""
+    mod = backend.use_cuda()
+    ctx = aes_fhe.EngineContext(1, mode="gpu", thread_count=1, backend=mod, logn=16, levels=21, fresh_level=14)
+    pipe = make_pipe(ctx)
+    drv = aes_fhe.FipsDriver(pipe, batched=True)
+    stride = ctx.engine.slot_count // 16
+    rng = np.random.default_rng(17)
+    blocks = rng.integers(0, 256, (stride, 16), dtype=np.uint8)
+    blocks[0] = np.frombuffer(bytes.fromhex("00112233445566778899aabbccddeeff"), dtype=np.uint8)
+    key = bytes.fromhex("000102030405060708090a0b0c0d0e0f")
+    rks = aes_fhe.expand_aes128_key(np.frombuffer(key, dtype=np.uint8))
+    l0 = ctx.engine.counters()
+    ct = drv.encrypt(blocks, rks, captured=True)
+    got = drv.decode(*ct)
+    assert bytes(got[0]).hex() == "69c4e0d86a7b0430d8cdb78070b4c55a"                     # FIPS-197 C.1
+    want = np.frombuffer(ecb(key, blocks.tobytes()), dtype=np.uint8).reshape(stride, 16)
+    assert np.array_equal(got, want)
+    assert ctx.engine.counters()["bootstrap"] - l0["bootstrap"] == 2 + 2 + 18            # warm-up, recording, 9 replays
+    back = drv.decode(*drv.decrypt(*ct, rks, captured=True))
+    assert np.array_equal(back, blocks)
+    assert len(pipe._round_graphs) == 2                                                  # one graph per direction
+    pipe.release_graphs()
+
+
+@pytest.mark.gpu
 def test_config3_full_fips_encryption_gpu():
     """configs[2]: full AES-128 encryption of 2048 packed blocks with 18 bootstraps, bit-exact with FIPS-197."""
     mod = backend.use_cuda()
