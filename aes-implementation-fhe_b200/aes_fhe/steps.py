@@ -31,7 +31,10 @@ PRUNE_BASIS = _os.environ.get("AESFHE_PRUNE_BASIS", "1") == "1"   # fused mode: 
 # multiplicative depths of the steps, used for the encryption-level hints of the fused mode
 XOR4_DEPTH = 5          # power basis 3 + product 1 + constant 1
 GF_DEPTH = 5
-SUBBYTES_DEPTH = 13
+# fused mode evaluates the two degree-255 S-box polynomials baby-step/giant-step (b^k = b^i (b^16)^j, one fused bivariate
+# LUT per half: 39 key switches instead of 138) at the price of one more level than the reference's 13 (3+1+1+7+1)
+PS_SUBBYTES = _os.environ.get("AESFHE_PS_SUBBYTES", "1") == "1"
+SUBBYTES_DEPTH = 14 if PS_SUBBYTES else 13
 SHIFTROWS_DEPTH = 1
 
 
@@ -214,6 +217,14 @@ class SubBytesLUT:
         self._lift = lift
         self.ks_hi_nz = [k for k in self.ks_hi if k != 0]
         self.ks_lo_nz = [k for k in self.ks_lo if k != 0]
+        # baby-step/giant-step term lists (fused mode): b^k = b^i G^j, k = 16 j + i; powers above 128 are conjugates of
+        # b^(256-k), so each polynomial is a "direct" bivariate LUT plus the conjugate of a "mirror" one
+        def split(coeffs, ks):
+            direct = [(k % 16, k // 16, complex(coeffs[k])) for k in ks if 1 <= k <= 128]
+            mirror = [((256 - k) % 16, (256 - k) // 16, complex(np.conj(coeffs[k]))) for k in ks if k > 128]
+            return direct, mirror
+        self._ps_hi = split(self.hi, self.ks_hi_nz)
+        self._ps_lo = split(self.lo, self.ks_lo_nz)
 
     def _poly_fused(self, pos: List[Any], period: int, coeffs, ks, c0):
         """c0 + sum_k c_k X^k with X^(period-k) = conj(X^k):  sum_{k<=len(pos)} c_k X^k + conj(sum conj(c_k) X^(period-k)).
@@ -227,6 +238,27 @@ class SubBytesLUT:
             acc = m if acc is None else eng.add(acc, m)
         return eng.add_plain(acc, c0)
 
+    def _apply_bsgs(self, ct_b) -> Pair:
+        """Both S-box polynomials from 15 baby powers b^1..b^16 and 7 giant powers (b^16)^1..8: every monomial
+        c_k b^(16j+i) is a term (i, j, c_k) of a bivariate LUT over the two bases, evaluated by the engine's fused
+        `lut2` with ONE relinearisation -- 22 products + 4 LUTs + 2 conjugations instead of 127 products."""
+        eng = self.ctx
+        babies = eng.make_power_basis(ct_b, 16)
+        giants = eng.make_power_basis(babies[15], 8)
+        one = eng.add_plain(eng.multiply(ct_b, 0.0), 1.0)
+        A = [one] + list(babies[:15])
+        B = [one] + list(giants) + [None] * 7
+        jobs = [t for t in (self._ps_hi[0], self._ps_hi[1], self._ps_lo[0], self._ps_lo[1])]
+        outs = eng.lane_map(lambda terms: eng.lut2(A, B, terms) if terms else None, [(t,) for t in jobs])
+        mir = [o for o in (outs[1], outs[3]) if o is not None]
+        conj = iter(eng.lane_map(eng.conjugate, [(o,) for o in mir]))
+        res = []
+        for direct, mirror, c0 in ((outs[0], outs[1], self.c0_hi), (outs[2], outs[3], self.c0_lo)):
+            m = next(conj) if mirror is not None else None
+            acc = direct if m is None else (m if direct is None else eng.add(direct, m))
+            res.append(eng.add_plain(acc, c0))
+        return res[0], res[1]
+
     def apply(self, ct_hi, ct_lo) -> Pair:
         eng = self.ctx
         if getattr(eng, "fused", False):
@@ -234,6 +266,8 @@ class SubBytesLUT:
             lift = self._lift
             lifted = self._poly_fused(pos16, 16, lift, self.ks_lift, self.c0_lift)
             ct_b = eng.multiply(ct_hi, lifted)
+            if PS_SUBBYTES and self.deg256 == 128:
+                return self._apply_bsgs(ct_b)
             pos256 = eng.make_power_basis(ct_b, self.deg256)
             return eng.pair_map(self._poly_fused, (pos256, 256, self.hi, self.ks_hi_nz, self.c0_hi),
                                 (pos256, 256, self.lo, self.ks_lo_nz, self.c0_lo))

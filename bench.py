@@ -362,7 +362,8 @@ def run_ours(args) -> None:
     # latency of one replay of its captured graph (eager with --no-graph)
     dec = None
     if not args.no_dec:
-        dstate = pipe.encoder.encode(drv._perm(blocks[0]), level=FRESH)
+        from aes_fhe.steps import SHIFTROWS_DEPTH, SUBBYTES_DEPTH
+        dstate = pipe.encoder.encode(drv._perm(blocks[0]), level=SHIFTROWS_DEPTH + SUBBYTES_DEPTH)
         dwant = plain_inv_round(blocks[0], rks[5])
         if args.no_graph:
             dec_step = lambda: pipe.decrypt_round(*dstate, *rk_ct[5])
