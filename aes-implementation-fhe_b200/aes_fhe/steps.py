@@ -26,6 +26,7 @@ import os as _os
 # tuning switches for the stream-lane granularity (measured choices recorded in profiles/README.md)
 LANES_CONJ = _os.environ.get("AESFHE_LANES_CONJ", "1") == "1"
 LANES_AB = _os.environ.get("AESFHE_LANES_AB", "1") == "1"
+SHARE_GF_BASES = _os.environ.get("AESFHE_SHARE_GF_BASES", "1") == "1"   # fused mode: M_k(rot_k x) = rot_k(M_k x)
 PRUNE_BASIS = _os.environ.get("AESFHE_PRUNE_BASIS", "1") == "1"   # fused mode: build only the powers a LUT uses
 
 # multiplicative depths of the steps, used for the encryption-level hints of the fused mode
@@ -395,6 +396,21 @@ class _MixBase:
             return self.ctx.pair_map(self._eval2, (ct_hi, ct_lo, mult, "hi", bases), (ct_hi, ct_lo, mult, "lo", bases))
         return self._eval2(ct_hi, ct_lo, mult, "hi"), self._eval2(ct_hi, ct_lo, mult, "lo")
 
+    def _gf_shared(self, mults, ct_hi, ct_lo) -> List[Pair]:
+        """Fused mode: several GF(2^8) constant multiplications of the SAME state from ONE pair of zeta16 bases.
+        The LUTs act slot by slot, so M(rot_k(x)) = rot_k(M(x)): the reference's M_k(rot_k(x)) (mixcol_final.py:124-131,
+        invmixcolumns_fhe.py:140-147) is evaluated as rot_k(M_k(x)) -- one basis pair per MixColumns instead of one per
+        multiplier, and the rotations act on the (lower-level) LUT outputs."""
+        ents = [e for m in mults for which in ("hi", "lo") for e in tables.gf_mult_entries(m, which)]
+        bases = self.ctx.pair_map(self._basis16, (ct_hi, {p for p, _, _ in ents}), (ct_lo, {q for _, q, _ in ents}))
+        jobs = [(ct_hi, ct_lo, m, which, bases) for m in mults for which in ("hi", "lo")]
+        outs = self.ctx.lane_map(self._eval2, jobs)
+        return [(outs[2 * i], outs[2 * i + 1]) for i in range(len(mults))]
+
+    def _rot_pair(self, pair: Pair, k_up: int) -> Pair:
+        step = -4 * k_up * self.stride
+        return self.ctx.pair_map(self.ctx.rotate, (pair[0], step), (pair[1], step))
+
     def _col_shift_rowmajor(self, ct, k_up: int):
         return self.ctx.rotate(ct, -4 * k_up * self.stride)
 
@@ -436,10 +452,17 @@ class MixColFinal(_MixBase):
     def __call__(self, ct_hi, ct_lo, do_final_bootstrap: bool = True,
                  debug: Optional[Dict[str, Any]] = None) -> Pair:
         log = debug.__setitem__ if isinstance(debug, dict) else (lambda k, v: None)
-        r1, r2, r3 = self._shifts(ct_hi, ct_lo)
-        log("rotc1", r1), log("rotc2", r2), log("rotc3", r3), log("in", (ct_hi, ct_lo))
-        two = self.gf_mult_2(ct_hi, ct_lo)
-        thr = self.gf_mult_3(*r1)
+        if getattr(self.ctx, "fused", False) and SHARE_GF_BASES and not isinstance(debug, dict):
+            # 2x and 3x from one basis pair of x; 3*rot1(x) = rot1(3x); rot2, rot3 of x share one ModUp
+            two, thr0 = self._gf_shared([2, 3], ct_hi, ct_lo)
+            thr = self._rot_pair(thr0, 1)
+            steps = [-4 * k * self.stride for k in (2, 3)]
+            r2, r3 = zip(self.ctx.rotate_many(ct_hi, steps), self.ctx.rotate_many(ct_lo, steps))
+        else:
+            r1, r2, r3 = self._shifts(ct_hi, ct_lo)
+            log("rotc1", r1), log("rotc2", r2), log("rotc3", r3), log("in", (ct_hi, ct_lo))
+            two = self.gf_mult_2(ct_hi, ct_lo)
+            thr = self.gf_mult_3(*r1)
         log("two", two), log("thr", thr)
         acc = self._xor_pair(two, thr)
         log("acc1", acc)
@@ -505,12 +528,17 @@ class InvMixColumnsFHE(_MixBase):
     def __call__(self, ct_hi, ct_lo, do_final_bootstrap: bool = True,
                  debug: Optional[Dict[str, Any]] = None) -> Pair:
         log = debug.__setitem__ if debug is not None else (lambda k, v: None)
-        r1, r2, r3 = self._shifts(ct_hi, ct_lo)
-        log("rotc1", r1), log("rotc2", r2), log("rotc3", r3)
-        e14 = self.gf_mult_14(ct_hi, ct_lo); log("mul14", e14)
-        e11 = self.gf_mult_11(*r1); log("mul11", e11)
-        e13 = self.gf_mult_13(*r2); log("mul13", e13)
-        e9 = self.gf_mult_9(*r3); log("mul9", e9)
+        if getattr(self.ctx, "fused", False) and SHARE_GF_BASES and debug is None:
+            # all four multipliers from one basis pair of x; M_k(rot_k(x)) = rot_k(M_k(x))
+            e14, m11, m13, m9 = self._gf_shared([14, 11, 13, 9], ct_hi, ct_lo)
+            e11, e13, e9 = self.ctx.lane_map(self._rot_pair, [(m11, 1), (m13, 2), (m9, 3)])
+        else:
+            r1, r2, r3 = self._shifts(ct_hi, ct_lo)
+            log("rotc1", r1), log("rotc2", r2), log("rotc3", r3)
+            e14 = self.gf_mult_14(ct_hi, ct_lo); log("mul14", e14)
+            e11 = self.gf_mult_11(*r1); log("mul11", e11)
+            e13 = self.gf_mult_13(*r2); log("mul13", e13)
+            e9 = self.gf_mult_9(*r3); log("mul9", e9)
         acc = self._xor_pair(e14, e11)
         log("acc1", acc)
         acc = self._renorm_pair(*acc, depth=XOR4_DEPTH)
