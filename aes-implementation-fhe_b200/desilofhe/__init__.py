@@ -383,6 +383,43 @@ class Engine:
         _capi.check(self._lib.ckks_decrypt(self._ptr, ct._h, out))
         return out.view(np.complex128)
 
+    # ------------------------------------------------------------------ wire format (transciphering clients)
+    _MAGIC = b"CKB2"
+
+    def _chain_id(self) -> int:
+        """64-bit fingerprint of the modulus chain: a ciphertext only makes sense to an engine with the same primes."""
+        P = self.params()
+        h = 1469598103934665603
+        for v in [P["logn"]] + P["q"] + P["p"]:
+            h = ((h ^ int(v)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    def serialize_ciphertext(self, ct: Ciphertext) -> bytes:
+        """Header (magic, logN, polynomial count, level, chain fingerprint) + the residues [npoly][level+1][N] as
+        little-endian uint64 in the engine's own layout (NTT domain, bit-reversed order)."""
+        npoly, level, n = ct.polynomial_count, ct.level, 2 * self.slot_count
+        body = np.zeros((npoly, level + 1, n), dtype=np.uint64)
+        _capi.check(self._lib.ckks_ct_export(self._ptr, ct._h, body))
+        head = self._MAGIC + np.array([self.config["logn"], npoly, level, 0], dtype="<u4").tobytes() + \
+            np.array([self._chain_id()], dtype="<u8").tobytes()
+        return head + body.astype("<u8", copy=False).tobytes()
+
+    def deserialize_ciphertext(self, blob: bytes) -> Ciphertext:
+        if len(blob) < 28 or blob[:4] != self._MAGIC:
+            raise ValueError("not a serialized ciphertext of this engine")
+        logn, npoly, level, _ = (int(x) for x in np.frombuffer(blob, dtype="<u4", count=4, offset=4))
+        chain = int(np.frombuffer(blob, dtype="<u8", count=1, offset=20)[0])
+        if logn != self.config["logn"] or chain != self._chain_id():
+            raise ValueError("ciphertext was produced under a different ring or modulus chain")
+        n = 2 * self.slot_count
+        if npoly not in (2, 3) or not 0 <= level <= self.max_level or len(blob) != 28 + npoly * (level + 1) * n * 8:
+            raise ValueError("corrupt ciphertext header or length")
+        body = np.ascontiguousarray(np.frombuffer(blob, dtype="<u8", offset=28).astype(np.uint64))
+        q = np.array(self.params()["q"][:level + 1], dtype=np.uint64)
+        if np.any(body.reshape(npoly, level + 1, n) >= q[None, :, None]):
+            raise ValueError("residue out of range")
+        return self._new(self._lib.ckks_ct_import, npoly, level, body)
+
     # ------------------------------------------------------------------ arithmetic (engine_context.py:65-98)
     @staticmethod
     def _is_scalar(x) -> bool:

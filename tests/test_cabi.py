@@ -77,3 +77,30 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "aes128_fhe_blocks_per_s" and line["higher_is_better"]
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] > 0
+
+
+def test_ciphertext_wire_format_roundtrip():
+    """serialize -> deserialize gives a ciphertext that decrypts identically and multiplies bit-identically; a blob from
+    another modulus chain, a truncated blob and an out-of-range residue are rejected."""
+    import numpy as np
+    import backend
+    mod = backend.use_emulation()
+    eng = mod.Engine(logn=12, levels=4, dnum=2, hamming_weight=32, seed=9)
+    sk = eng.create_secret_key(); eng.create_public_key(sk); rk = eng.create_relinearization_key(sk)
+    rng = np.random.default_rng(1)
+    z = np.exp(2j * np.pi * rng.random(eng.slot_count))
+    ct = eng.multiply(eng.encrypt(z), eng.encrypt(z), rk)
+    blob = eng.serialize_ciphertext(ct)
+    assert len(blob) == 28 + 2 * (ct.level + 1) * 4096 * 8
+    back = eng.deserialize_ciphertext(blob)
+    assert back.level == ct.level and back.polynomial_count == 2
+    assert np.array_equal(eng.decrypt(back), eng.decrypt(ct))
+    assert eng.serialize_ciphertext(eng.multiply(back, back, rk)) == eng.serialize_ciphertext(eng.multiply(ct, ct, rk))
+    other = mod.Engine(logn=12, levels=3, dnum=2, hamming_weight=32, seed=9)
+    with pytest.raises(ValueError, match="different ring or modulus chain"):
+        other.deserialize_ciphertext(blob)
+    with pytest.raises(ValueError, match="corrupt"):
+        eng.deserialize_ciphertext(blob[:-8])
+    bad = bytearray(blob); bad[28:36] = (2 ** 64 - 1).to_bytes(8, "little")
+    with pytest.raises(ValueError, match="out of range"):
+        eng.deserialize_ciphertext(bytes(bad))
