@@ -50,9 +50,10 @@ def main(reps: int = 3):
         ct = phase("sub_bytes", lambda: pipe.sub_bytes(*state))
         ct = phase("renorm", lambda: pipe._renorm_pair(*ct))
         ct = phase("shift_rows", lambda: pipe.shift_rows(*ct))
-        r1, r2, r3 = phase("mix.rotations", lambda: mix._shifts(*ct))
-        two = phase("mix.gf2", lambda: mix.gf_mult_2(*ct))
-        thr = phase("mix.gf3", lambda: mix.gf_mult_3(*r1))
+        two, thr0 = phase("mix.gf2+gf3", lambda: mix._gf_shared([2, 3], *ct))       # one basis pair for both LUTs
+        thr = phase("mix.rotations", lambda: mix._rot_pair(thr0, 1))
+        steps = [-4 * k * mix.stride for k in (2, 3)]
+        r2, r3 = phase("mix.rotations", lambda: list(zip(ctx.rotate_many(ct[0], steps), ctx.rotate_many(ct[1], steps))))
         a = phase("mix.xor", lambda: mix._xor_pair(two, thr))
         a = phase("renorm", lambda: mix._renorm_pair(*a))
         a = phase("mix.xor", lambda: mix._xor_pair(a, r2))
