@@ -1,0 +1,116 @@
+"""Homomorphic snap / noise-reduction classes (reference `zeta16_noise_reducter.py`,
+`noise_reduction.py`, `snapper_1d_z16.py`) -- the host mirror `aes_fhe/snap.py`.
+
+(i) On the slot stand-in the mirror must issue the SAME engine-call trace and return the same slots as the unchanged
+reference classes (fixtures: tests/golden/snap_reference_golden.json, made by tests/golden/make_snap_golden.py).
+(ii) On the engine (emulation build here, CUDA on the GPU box) the maps must contract the error of noisy zeta16
+codewords quadratically and keep the codeword: |f(t(1+e)) - t| = O(|e|^2).
+"""
+from __future__ import annotations
+
+import json
+from collections import Counter
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import backend
+import aes_fhe
+from aes_fhe import snap
+from oracle import slot_standin as ss
+
+GOLD = json.load(open(Path(__file__).parent / "golden" / "snap_reference_golden.json"))
+
+
+def noisy_codewords(n, seed=3, sigma=0.02):
+    rng = np.random.default_rng(seed)
+    t = np.exp(-2j * np.pi * rng.integers(0, 16, n) / 16)
+    return t, t * (1 + sigma * (rng.standard_normal(n) + 1j * rng.standard_normal(n)))
+
+
+def lut1d_coeffs():
+    w = np.exp(-2j * np.pi / 16)
+    return np.fft.ifft(np.array([w ** ((5 * v + 3) % 16) for v in range(16)]))
+
+
+MAKERS = {
+    "Zeta16NoiseReducer": lambda ctx: snap.Zeta16NoiseReducer(ctx),
+    "Zeta16SnapNoMul": lambda ctx: snap.Zeta16SnapNoMul(ctx),
+    "Zeta16Snap": lambda ctx: snap.Zeta16Snap(ctx),
+    "NoiseReducer": lambda ctx: snap.NoiseReducer(ctx),
+    "Zeta16Snap1D": lambda ctx: snap.Zeta16Snap1D(ctx, lut1d_coeffs()),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MAKERS))
+def test_mirror_trace_and_slots_equal_the_reference_classes(name):
+    g = GOLD["classes"][name]
+    ctx = aes_fhe.EngineContext(1, mode="cpu", thread_count=4, backend=ss, slot_count=GOLD["slots"])
+    ctx.engine.trace_enabled = True
+    obj = MAKERS[name](ctx)
+    _, z = noisy_codewords(GOLD["slots"])
+    ct = ctx.encrypt(z)
+    ctx.engine.reset_trace()
+    y = ctx.decrypt(obj.apply(ct))
+    ops = Counter()
+    for (_, op), n in ctx.engine.counters.items():
+        ops[op] += n
+    assert dict(sorted(ops.items())) == g["ops"]
+    assert ctx.engine.trace_digest() == g["digest"]
+    assert np.array_equal(y, np.array(g["re"]) + 1j * np.array(g["im"]))
+
+
+CASES = [
+    pytest.param(("emu", 12, 64), id="emu-n12"),
+    pytest.param(("cuda", 16, 192), id="cuda-n16", marks=pytest.mark.gpu),
+]
+
+
+@pytest.fixture(scope="module", params=CASES)
+def eng_ctx(request):
+    which, logn, hw = request.param
+    mod = backend.use_emulation() if which == "emu" else backend.use_cuda()
+    return aes_fhe.EngineContext(2, max_level=8, mode="gpu", thread_count=1, backend=mod, logn=logn, hamming_weight=hw)
+
+
+CLOSED_FORM = {
+    "Zeta16NoiseReducer": lambda z: (17 / 16) * z - (1 / 16) * z ** 17,
+    "NoiseReducer": lambda z: (17 / 16) * z - (1 / 16) * z ** 17,
+    # x^17 taken as conj(x^7) x^8 (zeta16_noise_reducter.py:108-112): equal to x^17 only on the unit circle, so this
+    # variant damps the radial error (x 1/8) but passes the phase error through unchanged -- reference behaviour
+    "Zeta16Snap": lambda z: (17 / 16) * z - (1 / 16) * np.conj(z ** 7) * z ** 8,
+    "Zeta16SnapNoMul": lambda z: (9 / 8) * z + (1 / 8) * np.conj(z ** 7),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CLOSED_FORM))
+@pytest.mark.parametrize("fused", [False, True], ids=["call-for-call", "fused"])
+def test_snap_maps_on_the_engine(eng_ctx, name, fused):
+    ctx = eng_ctx
+    ctx.fused = fused
+    t, z = noisy_codewords(ctx.engine.slot_count, seed=8, sigma=0.005)
+    y = ctx.decrypt(MAKERS[name](ctx).apply(ctx.encrypt(z)))
+    assert np.abs(y - CLOSED_FORM[name](z)).max() < 1e-6            # stated tolerance: engine noise after <= 6 levels
+    if name in ("Zeta16NoiseReducer", "NoiseReducer"):
+        e_in, e_out = np.abs(z - t).max(), np.abs(y - t).max()
+        # f(t(1+e)) = t(1 - (17/2) e^2 + ..): the error is squared
+        assert e_out < 12 * e_in ** 2 + 1e-6 and e_out < 0.5 * e_in, (e_in, e_out)
+    if name == "Zeta16Snap":
+        assert np.abs(np.abs(y) - 1).max() < 0.2 * np.abs(np.abs(z) - 1).max() + 1e-6      # radial error only
+    ctx.fused = True
+
+
+def test_snap1d_evaluates_the_lut_on_the_engine(eng_ctx):
+    """Zeta16Snap1D with the LUT v -> (5 v + 3) mod 16, call for call and through the fused linear combination."""
+    ctx = eng_ctx
+    n = ctx.engine.slot_count
+    rng = np.random.default_rng(2)
+    v = rng.integers(0, 16, n)
+    w = np.exp(-2j * np.pi / 16)
+    want = w ** ((5 * v + 3) % 16)
+    for fused in (False, True):
+        ctx.fused = fused
+        y = ctx.decrypt(snap.Zeta16Snap1D(ctx, lut1d_coeffs()).apply(ctx.encrypt(w ** v)))
+        assert np.abs(y - want).max() < 1e-5, fused
+    ctx.fused = True
