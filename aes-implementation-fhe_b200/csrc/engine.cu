@@ -172,6 +172,7 @@ Engine::Engine(const Params& P) : prm(P) {
     lane_made[0] = lane_busy[0] = true;
     arenas[0] = &main_arena;
     if (const char* v = getenv("CKKS_NTT_FUSE")) fuse_ntt = atoi(v) != 0;
+    if (const char* v = getenv("CKKS_CHEB_DEGREE")) prm.boot.cheb_degree = atoi(v);      // tuning / A-B runs only
     mod = prm.q;
     mod.insert(mod.end(), prm.p.begin(), prm.p.end());
     if ((int)mod.size() > CKKS_MAX_MODULI) throw std::runtime_error("engine: too many moduli");

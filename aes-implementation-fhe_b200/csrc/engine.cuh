@@ -58,7 +58,7 @@ struct BootParams {
     int enabled = 0;
     int cts_groups = 3, stc_groups = 3;             // matrices the (i)DFT is factored into
     int K = 25;                                     // bound on |I| in t = m + q0 I
-    int cheb_degree = 63;
+    int cheb_degree = 47;                           // 63 gives the same measured precision (5.6e-4) for 4 more products
     int double_angle = 3;
 };
 

@@ -124,7 +124,7 @@ def bsgs_split(diags: Diags, n: int) -> Tuple[int, int, Dict[int, Dict[int, np.n
 
 # ---------------------------------------------------------------------------------------- oracle-side evaluation
 class BootstrapOracle:
-    def __init__(self, orc: OracleCKKS, K: int = 25, degree: int = 63, double_angle: int = 2, cts_groups: int = 3,
+    def __init__(self, orc: OracleCKKS, K: int = 25, degree: int = 47, double_angle: int = 2, cts_groups: int = 3,
                  stc_groups: int = 3):
         self.o = orc
         self.K, self.degree, self.r = K, degree, double_angle

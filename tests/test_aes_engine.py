@@ -112,7 +112,7 @@ def test_config2_one_round_as_shipped_matches_standin(boot_ctx):
     want = sp.encoder.decode(*sp.encrypt_round(*sp.encoder.encode(state), *sp.encoder.encode(key)))
     assert bytes(pipe.encoder.decode(*out)) == bytes(want)
     assert c1["bootstrap"] - c0["bootstrap"] == 2
-    assert c1["mul_cc"] - c0["mul_cc"] == 1034 + 2 * 38      # SURVEY App. B round count + EvalMod multiplications
+    assert c1["mul_cc"] - c0["mul_cc"] == 1034 + 2 * 34      # SURVEY App. B round count + EvalMod multiplications
 
 
 def test_config5_batched_fips_round(boot_ctx):
