@@ -405,6 +405,29 @@ int ckks_bench_rotate(ckks_engine* e, int level, int iters, float* ms_out) {
         E.free_ct(c);
     });
 }
+// the same with `lanes` independent ciphertexts rotated concurrently on stream lanes (throughput rather than latency)
+int ckks_bench_rotate_lanes(ckks_engine* e, int level, int lanes, int iters, float* ms_per_rotation) {
+    return guard([&] {
+        Engine& E = *e->E;
+        if (lanes < 1 || lanes > 16) throw std::runtime_error("bench_rotate_lanes: 1..16 lanes");
+        std::vector<Ct*> cts;
+        for (int l = 0; l < lanes; l++) cts.push_back(random_ct(E, level, 40 + 2 * l));
+        const long step = (long)E.slots() / 4;
+        auto round = [&](int reps) {
+            if (lanes > 1) E.fork(lanes);
+            for (int l = 0; l < lanes; l++) {
+                if (lanes > 1) E.set_lane(l);
+                for (int it = 0; it < reps; it++) E.free_ct(E.rotate(cts[l], step));
+            }
+            if (lanes > 1) E.join();
+        };
+        round(3);
+        e->timer.start(E.st);
+        round(iters);
+        *ms_per_rotation = e->timer.stop_ms(E.st) / (iters * lanes);
+        for (Ct* c : cts) E.free_ct(c);
+    });
+}
 int ckks_bench_mul(ckks_engine* e, int level, int iters, float* ms_out) {
     return guard([&] {
         Engine& E = *e->E;

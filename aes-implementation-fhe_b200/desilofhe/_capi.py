@@ -116,6 +116,7 @@ def load():
         "ckks_profile_ntt_end": (i32, [vp, C.POINTER(dbl), C.POINTER(lng), C.POINTER(lng)]),
         "ckks_bench_ntt": (i32, [vp, i32, i32, i32, i32, C.POINTER(C.c_float)]),
         "ckks_bench_rotate": (i32, [vp, i32, i32, C.POINTER(C.c_float)]),
+        "ckks_bench_rotate_lanes": (i32, [vp, i32, i32, i32, C.POINTER(C.c_float)]),
         "ckks_bench_mul": (i32, [vp, i32, i32, C.POINTER(C.c_float)]),
     }
     for name, (res, args) in sig.items():

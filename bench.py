@@ -401,6 +401,17 @@ def run_ours(args) -> None:
         _check(lib.ckks_bench_ntt(ptr, nl, 6, 0, 20, C.byref(lb)))
         large_batch = {"limbs_per_call": nl * 6, "us_per_call": lb.value * 1e3,
                        "achieved": nl * 6 * 2 * (1 << LOGN) * 8 / (lb.value * 1e-3) / 1e9}
+    # BASELINE.json's third figure: rotations/s at N = 2^16 (one hybrid key switch + Galois gather, resident operands),
+    # back to back on the engine's stream, at the top, the fresh and the post-bootstrap level
+    rotations = None
+    if not dry and LOGN == 16:
+        rotations = {}
+        rms = C.c_float()
+        for lvl in (LEVELS, FRESH, 5):
+            _check(lib.ckks_bench_rotate(ptr, lvl, 20, C.byref(rms)))
+            rotations[f"level_{lvl}"] = 1e3 / rms.value
+            _check(lib.ckks_bench_rotate_lanes(ptr, lvl, 8, 10, C.byref(rms)))
+            rotations[f"level_{lvl}_8_lanes"] = 1e3 / rms.value
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -449,7 +460,7 @@ def run_ours(args) -> None:
                 "s_per_round_enc_plus_dec": (s_round + dec["s_per_round"]) if dec else None,
                 "bytes_exact_vs_fips197_round": ok,
                 "key_switches_per_step": ks_round, "bootstraps_per_step": (c1["bootstrap"] - c0["bootstrap"]) // args.steps,
-                "rotations_per_s_equiv": ks_round / s_step, "arena": eng.arena_stats(),
+                "rotations_per_s_equiv": ks_round / s_step, "rotations_per_s_n16": rotations, "arena": eng.arena_stats(),
                 "e2e": e2e, "gpu_launches": int(launches) * args.steps, "clocks": clk, "roofline": roofline,
                 "cpu_baseline": cpu}
         if dry:

@@ -188,6 +188,8 @@ int ckks_profile_ntt_end(ckks_engine* e, double* ms_out, long* calls_out, long* 
 /* micro-benchmarks on resident random data: returns average milliseconds per call over `iters` calls */
 int ckks_bench_ntt(ckks_engine* e, int nlimbs, int batches, int inverse, int iters, float* ms_out);
 int ckks_bench_rotate(ckks_engine* e, int level, int iters, float* ms_out);
+/* `lanes` independent ciphertexts rotated concurrently on stream lanes: milliseconds per rotation (throughput) */
+int ckks_bench_rotate_lanes(ckks_engine* e, int level, int lanes, int iters, float* ms_per_rotation);
 int ckks_bench_mul(ckks_engine* e, int level, int iters, float* ms_out);
 
 #ifdef __cplusplus

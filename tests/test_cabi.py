@@ -104,3 +104,42 @@ def test_ciphertext_wire_format_roundtrip():
     bad = bytearray(blob); bad[28:36] = (2 ** 64 - 1).to_bytes(8, "little")
     with pytest.raises(ValueError, match="out of range"):
         eng.deserialize_ciphertext(bytes(bad))
+
+
+def test_capture_rejects_host_round_trips_and_recovers():
+    """A function with a hidden host round trip (decrypt) cannot be captured: the call raises before the driver sees it,
+    the capture is abandoned, and the engine keeps working eagerly and can capture again; replays are bit-identical to
+    the eager result on new inputs."""
+    import numpy as np
+    import backend
+    mod = backend.use_emulation()
+    eng = mod.Engine(logn=12, levels=4, dnum=2, hamming_weight=32, seed=4)
+    sk = eng.create_secret_key(); eng.create_public_key(sk); rk = eng.create_relinearization_key(sk)
+    rng = np.random.default_rng(0)
+    z1, z2 = (np.exp(2j * np.pi * rng.random(eng.slot_count)) for _ in range(2))
+    a, b = eng.encrypt(z1), eng.encrypt(z2)
+
+    def bad(x, y):
+        p = eng.multiply(x, y, rk)
+        eng.decrypt(p)                       # device-to-host copy + synchronisation
+        return [p]
+
+    with pytest.raises(RuntimeError, match="not allowed while a graph is being captured"):
+        eng.capture(bad, [a, b])
+    assert np.abs(eng.decrypt(eng.multiply(a, b, rk)) - z1 * z2).max() < 1e-7        # eager path intact
+
+    def good(x, y):
+        return [eng.add(eng.multiply(x, y, rk), eng.rotate(x, None, 5))]
+
+    call = eng.capture(good, [a, b])
+    assert call.info()["capture_misses"] == 0 and call.info()["launches"] > 10
+    out = call(b, a)[0]                                                                 # swapped inputs
+    want = good(b, a)[0]
+    assert eng.serialize_ciphertext(out) == eng.serialize_ciphertext(want)
+    assert np.abs(eng.decrypt(out) - (z1 * z2 + np.roll(z2, 5))).max() < 1e-7
+    with pytest.raises(ValueError):
+        call(a)                                                                         # wrong number of inputs
+    with pytest.raises(RuntimeError, match="shape mismatch"):
+        call(eng.level_down(a, 2), b)                                                   # wrong level
+    call.close()
+    assert np.abs(eng.decrypt(eng.multiply(a, b, rk)) - z1 * z2).max() < 1e-7
