@@ -26,148 +26,126 @@ import numpy as np
 from .context import EngineContext
 
 
-class Zeta16NoiseReducer:
+def _with_bootstrap_retry(ctx, ct, fn):
+    """The recovery ladder every reference class repeats: run `fn(ct)`; on a level / form `RuntimeError` bootstrap the
+    ciphertext once and run it again.  Returns (ciphertext actually used, result)."""
+    try:
+        return ct, fn(ct)
+    except RuntimeError:
+        ct = ctx.bootstrap(ct)
+        return ct, fn(ct)
+
+
+class _PolySnap:
+    """Shared shape of the three zeta16 maps: optional bootstrap before / after, positive powers x^1..x^8 first."""
+
     def __init__(self, ctx: EngineContext, bootstrap_before: bool = False, bootstrap_after: bool = False):
         self.ctx = ctx
-        self.alpha = 17.0 / 16.0
-        self.beta = -1.0 / 16.0
         self.bootstrap_before = bootstrap_before
         self.bootstrap_after = bootstrap_after
 
-    def _ensure_power_basis(self, ct: Any):
-        eng = self.ctx
-        try:
-            return ct, eng.make_power_basis(ct, 8)
-        except RuntimeError:                      # level / form trouble: one bootstrap, then retry (:24-29)
-            ct = eng.bootstrap(ct)
-            return ct, eng.make_power_basis(ct, 8)
+    def _powers8(self, ct: Any):
+        return _with_bootstrap_retry(self.ctx, ct, lambda c: self.ctx.make_power_basis(c, 8))
+
+    def _combine(self, x: Any, pos) -> Any:
+        raise NotImplementedError
 
     def apply(self, ct: Any) -> Any:
-        eng = self.ctx
-        x = eng.bootstrap(ct) if self.bootstrap_before else ct
-        x, pos = self._ensure_power_basis(x)
-        x1, x8 = pos[0], pos[7]
-        x16 = eng.multiply(x8, x8)
-        x17 = eng.multiply(x16, x1)
-        y = eng.add(eng.multiply_plain(x1, self.alpha), eng.multiply_plain(x17, self.beta))
-        return eng.bootstrap(y) if self.bootstrap_after else y
+        x = self.ctx.bootstrap(ct) if self.bootstrap_before else ct
+        x, pos = self._powers8(x)
+        y = self._combine(x, pos)
+        return self.ctx.bootstrap(y) if self.bootstrap_after else y
 
     def apply_pair(self, ct_hi: Any, ct_lo: Any) -> Tuple[Any, Any]:
         return self.apply(ct_hi), self.apply(ct_lo)
 
 
-class Zeta16SnapNoMul:
+class Zeta16NoiseReducer(_PolySnap):
+    """f(x) = (17/16) x - (1/16) x^17 with x^16 = (x^8)^2, x^17 = x^16 x   (zeta16_noise_reducter.py:31-52)."""
+
     def __init__(self, ctx: EngineContext, bootstrap_before: bool = False, bootstrap_after: bool = False):
-        self.ctx = ctx
-        self.a = 9.0 / 8.0
-        self.b = 1.0 / 8.0
-        self.bootstrap_before = bootstrap_before
-        self.bootstrap_after = bootstrap_after
+        super().__init__(ctx, bootstrap_before, bootstrap_after)
+        self.alpha, self.beta = 17.0 / 16.0, -1.0 / 16.0
 
-    def _pb1_8(self, ct: Any):
+    _ensure_power_basis = _PolySnap._powers8
+
+    def _combine(self, x, pos):
         eng = self.ctx
-        try:
-            return eng.make_power_basis(ct, 8)
-        except RuntimeError:
-            return eng.make_power_basis(eng.bootstrap(ct), 8)
+        x17 = eng.multiply(eng.multiply(pos[7], pos[7]), pos[0])
+        return eng.add(eng.multiply_plain(pos[0], self.alpha), eng.multiply_plain(x17, self.beta))
 
-    def apply(self, ct: Any) -> Any:
+
+class Zeta16SnapNoMul(_PolySnap):
+    """f(x) = (9/8) x + (1/8) x^9 with x^9 = conj(x^7): no product beyond the basis   (zeta16_noise_reducter.py:84-101)."""
+
+    def __init__(self, ctx: EngineContext, bootstrap_before: bool = False, bootstrap_after: bool = False):
+        super().__init__(ctx, bootstrap_before, bootstrap_after)
+        self.a, self.b = 9.0 / 8.0, 1.0 / 8.0
+
+    def _powers8(self, ct: Any):
+        # the reference keeps the un-bootstrapped handle here (:76-82); only the basis matters afterwards
+        return ct, _with_bootstrap_retry(self.ctx, ct, lambda c: self.ctx.make_power_basis(c, 8))[1]
+
+    def _combine(self, x, pos):
         eng = self.ctx
-        x = eng.bootstrap(ct) if self.bootstrap_before else ct
-        pos = self._pb1_8(x)
-        x1, x9 = pos[0], eng.conjugate(pos[6])
-        y = eng.add(eng.multiply_plain(x1, self.a), eng.multiply_plain(x9, self.b))
-        return eng.bootstrap(y) if self.bootstrap_after else y
-
-    def apply_pair(self, hi: Any, lo: Any) -> Tuple[Any, Any]:
-        return self.apply(hi), self.apply(lo)
+        x9 = eng.conjugate(pos[6])
+        return eng.add(eng.multiply_plain(pos[0], self.a), eng.multiply_plain(x9, self.b))
 
 
-class Zeta16Snap:
+class Zeta16Snap(_PolySnap):
+    """f(x) = (17/16) x - (1/16) x^17 with x^17 taken as conj(x^7) x^8 (one product; equal to x^17 on the unit circle
+    only), every product guarded by its own bootstrap retry   (zeta16_noise_reducter.py:108-166)."""
+
     def __init__(self, ctx: EngineContext, *, always_bs: bool = False):
-        self.ctx = ctx
+        super().__init__(ctx)
         self.always_bs = always_bs
 
-    def _to_coeff(self, ct: Any) -> Any:
-        try:
-            return self.ctx.to_intt(ct)
-        except Exception:
-            return ct
-
-    def _pb_1_8(self, ct: Any):
+    def _powers8(self, ct: Any):
         eng = self.ctx
-        ct = self._to_coeff(ct)
+        try:                                   # bootstrap wants coefficient form (:118-122)
+            ct = eng.to_intt(ct)
+        except Exception:
+            pass
         if self.always_bs:
             ct = eng.bootstrap(ct)
-        try:
-            pos = eng.make_power_basis(ct, 8)
-        except RuntimeError:
-            ct = eng.bootstrap(ct)
-            pos = eng.make_power_basis(ct, 8)
-        return ct, pos
+        return _with_bootstrap_retry(eng, ct, lambda c: eng.make_power_basis(c, 8))
 
-    def _mul_safe(self, a: Any, b: Any) -> Any:
-        eng = self.ctx
-        try:
-            return eng.multiply(a, b)
-        except RuntimeError:
-            return eng.multiply(eng.bootstrap(a), b)
+    def _guarded(self, a: Any, b) -> Any:
+        return _with_bootstrap_retry(self.ctx, a, lambda c: self.ctx.multiply(c, b))[1]
 
-    def _scale_safe(self, ct: Any, s: float) -> Any:
+    def _combine(self, x, pos):
         eng = self.ctx
-        try:
-            return eng.multiply(ct, float(s))
-        except RuntimeError:
-            return eng.multiply(eng.bootstrap(ct), float(s))
-
-    def apply(self, ct: Any) -> Any:
-        eng = self.ctx
-        ct, pos = self._pb_1_8(ct)
-        x1, x8 = pos[0], pos[7]
-        x9 = eng.conjugate(pos[6])
-        x17 = self._mul_safe(x9, x8)
-        t1 = self._scale_safe(x1, 17.0 / 16.0)
-        t2 = self._scale_safe(x17, 1.0 / 16.0)
-        try:
+        x17 = self._guarded(eng.conjugate(pos[6]), pos[7])
+        t1 = self._guarded(pos[0], 17.0 / 16.0)
+        t2 = self._guarded(x17, 1.0 / 16.0)
+        if hasattr(eng, "sub"):
             return eng.sub(t1, t2)
-        except AttributeError:
-            return eng.add(t1, eng.multiply(t2, -1.0))
-
-    def apply_pair(self, hi: Any, lo: Any) -> Tuple[Any, Any]:
-        return self.apply(hi), self.apply(lo)
+        return eng.add(t1, eng.multiply(t2, -1.0))
 
 
 class NoiseReducer:
+    """f(x) = (1 + 1/n) x - (1/n) x^(n+1), n = 16, through make_power_basis(x, 16)   (noise_reduction.py:14-79)."""
+
     def __init__(self, ctx: EngineContext, n: int = 16, profile: bool = False):
-        assert n >= 2
-        self.ctx = ctx
-        self.n = n
-        self.alpha = 1.0 + 1.0 / n
-        self.beta = -1.0 / n
-        self.profile = profile
+        if n < 2:
+            raise AssertionError("n must be at least 2")
+        self.ctx, self.n, self.profile = ctx, n, profile
+        self.alpha, self.beta = 1.0 + 1.0 / n, -1.0 / n
         self._last_stats: Optional[dict] = None
 
     def _ensure_read(self, ct: Any, deg: int = 1) -> Any:
-        try:
-            self.ctx.make_power_basis(ct, deg)
-            return ct
-        except RuntimeError:
-            return self.ctx.bootstrap(ct)
+        return _with_bootstrap_retry(self.ctx, ct, lambda c: self.ctx.make_power_basis(c, deg))[0]
 
     def _x_pow_nplus1(self, x: Any) -> Any:
+        if self.n != 16:                        # the reference implements the nibble case only (:41-52)
+            return None
         eng = self.ctx
-        if self.n == 16:                              # the only branch the reference implements (:43-52)
-            try:
-                pos = eng.make_power_basis(x, 16)
-            except RuntimeError:
-                x = eng.bootstrap(x)
-                pos = eng.make_power_basis(x, 16)
-            return eng.relinearize(eng.multiply(pos[15], x))
-        return None
+        x, pos = _with_bootstrap_retry(eng, x, lambda c: eng.make_power_basis(c, 16))
+        return eng.relinearize(eng.multiply(pos[15], x))
 
     def apply(self, ct: Any) -> Any:
         eng = self.ctx
-        t0 = time.perf_counter() if self.profile else None
+        t0 = time.perf_counter()
         x = self._ensure_read(ct, 1)
         xn1 = self._x_pow_nplus1(x)
         y = eng.add(eng.multiply_plain(x, self.alpha), eng.multiply_plain(xn1, self.beta))
