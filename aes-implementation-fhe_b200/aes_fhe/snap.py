@@ -161,73 +161,70 @@ class NoiseReducer:
 
 
 def load_coeff1d(json_path: Path) -> np.ndarray:
-    obj = json.loads(Path(json_path).read_text(encoding="utf-8"))
-    max_k = max(int(k) for k, _, _ in obj["entries"])
-    coeff = np.zeros(max_k + 1, dtype=np.complex128)
-    for k, re, im in obj["entries"]:
-        coeff[int(k)] = complex(re, im)
+    """Dense coefficient vector from the generator's sparse JSON ({"entries": [[k, re, im], ...]})."""
+    entries = json.loads(Path(json_path).read_text(encoding="utf-8"))["entries"]
+    coeff = np.zeros(1 + max(int(e[0]) for e in entries), dtype=np.complex128)
+    for k, re, im in entries:
+        coeff[int(k)] = re + 1j * im
     return coeff
 
 
 class Zeta16Snap1D:
+    """A 1-D LUT on one nibble ciphertext: sum_k c_k x^k over the zeta16 basis {1, x..x^8, conj(x^7)..conj(x)}
+    (snapper_1d_z16.py:17-84); exponents above 15 fold with x^16 = 1."""
+
     def __init__(self, ctx: EngineContext, coeff_1d: np.ndarray, bootstrap_before: bool = False):
-        self.ctx = ctx
-        self.sc = ctx.engine.slot_count
+        self.ctx, self.sc, self.bootstrap_before = ctx, ctx.engine.slot_count, bootstrap_before
         self.coeff = np.asarray(coeff_1d, dtype=np.complex128)
         self.K = len(self.coeff) - 1
-        self.bootstrap_before = bootstrap_before
-        self.pt: Dict[int, Any] = {k: ctx.encode(np.full(self.sc, c, dtype=np.complex128))
-                                   for k, c in enumerate(self.coeff) if abs(c) > 1e-12}
+        nz = [k for k, c in enumerate(self.coeff) if abs(c) > 1e-12]
+        self.pt: Dict[int, Any] = {k: ctx.encode(np.full(self.sc, self.coeff[k], dtype=np.complex128)) for k in nz}
 
     def _power_basis_16(self, ct: Any) -> Dict[int, Any]:
         eng = self.ctx
+        ct, pos = _with_bootstrap_retry(eng, ct, lambda c: eng.make_power_basis(c, 8))
+        zero = eng.multiply(ct, 0.0)
         try:
-            pos = eng.make_power_basis(ct, 8)
+            one = eng.add_plain(zero, 1.0)
         except RuntimeError:
-            ct = eng.bootstrap(ct)
-            pos = eng.make_power_basis(ct, 8)
-        zero_like = eng.multiply(ct, 0.0)
-        try:
-            basis0 = eng.add_plain(zero_like, 1.0)
-        except RuntimeError:
-            ct = eng.bootstrap(ct)
-            basis0 = eng.add_plain(eng.multiply(ct, 0.0), 1.0)
-        basis = {0: basis0}
-        basis.update({k: pos[k - 1] for k in range(1, 9)})
+            one = eng.add_plain(eng.multiply(eng.bootstrap(ct), 0.0), 1.0)
+        basis = dict(enumerate([one] + list(pos)))
         for k in range(9, 16):
-            basis[k] = eng.conjugate(pos[(16 - k) - 1])
+            basis[k] = eng.conjugate(pos[15 - k])
         return basis
+
+    def _apply_fused(self, ct: Any) -> Any:
+        """The same polynomial through the engine's fused linear combination: one rescale, one conjugation."""
+        eng = self.ctx
+        pos = eng.make_power_basis(ct, 8)
+        lo = [k for k in self.pt if 1 <= k % 16 <= 8]
+        hi = [k for k in self.pt if k % 16 > 8]
+        acc = eng.lincomb([pos[k % 16 - 1] for k in lo], [self.coeff[k] for k in lo]) if lo else None
+        if hi:
+            m = eng.conjugate(eng.lincomb([pos[15 - k % 16] for k in hi], [np.conj(self.coeff[k]) for k in hi]))
+            acc = m if acc is None else eng.add(acc, m)
+        return eng.add_plain(acc, sum(self.coeff[k] for k in self.pt if k % 16 == 0))
 
     def apply(self, ct: Any) -> Any:
         eng = self.ctx
         if self.bootstrap_before:
             ct = eng.bootstrap(ct)
         if getattr(eng, "fused", False):
-            # the same polynomial through the engine's fused linear combination: conj(x^k) = x^(16-k), one rescale
-            pos = eng.make_power_basis(ct, 8)
-            ks = [k for k in self.pt if k % 16 != 0]
-            direct = [k for k in ks if k % 16 <= 8]
-            mirror = [k for k in ks if k % 16 > 8]
-            acc = eng.lincomb([pos[k % 16 - 1] for k in direct], [self.coeff[k] for k in direct]) if direct else None
-            if mirror:
-                m = eng.conjugate(eng.lincomb([pos[16 - k % 16 - 1] for k in mirror],
-                                              [np.conj(self.coeff[k]) for k in mirror]))
-                acc = m if acc is None else eng.add(acc, m)
-            c0 = sum(self.coeff[k] for k in self.pt if k % 16 == 0)
-            return eng.add_plain(acc, c0)
+            return self._apply_fused(ct)
         basis = self._power_basis_16(ct)
         try:
             res = eng.multiply(ct, 0.0)
         except RuntimeError:
             ct = eng.bootstrap(ct)
-            basis = self._power_basis_16(ct)
-            res = eng.multiply(ct, 0.0)
+            basis, res = self._power_basis_16(ct), eng.multiply(ct, 0.0)
         for k, pt in self.pt.items():
-            res = eng.add(res, eng.multiply(basis[k % 16], pt))      # k > 15 folds with x^16 = 1 (:78-81)
+            res = eng.add(res, eng.multiply(basis[k % 16], pt))
         return res
 
 
 class Zeta16SnapPair:
+    """The same 1-D snap on the hi and the lo nibble ciphertext (snapper_1d_z16.py:86-91)."""
+
     def __init__(self, snap1d: Zeta16Snap1D):
         self.snap = snap1d
 
