@@ -100,10 +100,15 @@ def _zeta16_basis_pruned(eng, ct, exps) -> Dict[int, Any]:
     basis.update({k: pos[k - 1] for k in exps if 1 <= k <= 8})
     hi = [k for k in exps if k > 8]
     if hi:
+        # conjugate at the level the LUT will run at (the deepest needed power): the alignment is memoised on the
+        # positive power, so the LUT reuses it, the conjugation key-switches fewer limbs, and conj(x^k) needs no
+        # alignment of its own
+        deep = min(pos[k - 1].level for k in pos_need)
+        src = [eng.level_down(pos[15 - k], deep) for k in hi]
         if LANES_CONJ:
-            conj = eng.lane_map(eng.conjugate, [(pos[15 - k],) for k in hi])
+            conj = eng.lane_map(eng.conjugate, [(c,) for c in src])
         else:
-            conj = [eng.conjugate(pos[15 - k]) for k in hi]
+            conj = [eng.conjugate(c) for c in src]
         basis.update(dict(zip(hi, conj)))
     return basis
 
