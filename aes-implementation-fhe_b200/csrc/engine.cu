@@ -172,6 +172,7 @@ Engine::Engine(const Params& P) : prm(P) {
     lane_made[0] = lane_busy[0] = true;
     arenas[0] = &main_arena;
     if (const char* v = getenv("CKKS_NTT_FUSE")) fuse_ntt = atoi(v) != 0;
+    if (const char* v = getenv("CKKS_TENSOR_FUSE")) fuse_tensor = atoi(v) != 0;
     if (const char* v = getenv("CKKS_CHEB_DEGREE")) prm.boot.cheb_degree = atoi(v);      // tuning / A-B runs only
     mod = prm.q;
     mod.insert(mod.end(), prm.p.begin(), prm.p.end());
@@ -658,14 +659,14 @@ void Engine::ntt_rows(u64* data, const std::vector<int>& rows, const std::vector
 
 // every NTT launch goes through here: limb accounting and, when profiling, a CUDA-event pair per call on the
 // engine's stream (bench.py's roofline leg: average duration and algorithmic bytes of the NTT kernels)
-void Engine::run_ntt(const u64* src, u64* dst, const NttJob& J, bool inverse, long limbs) {
+void Engine::run_ntt(const u64* src, u64* dst, const NttJob& J, bool inverse, long limbs, const u64* src2) {
     dev::Timer* t = nullptr;
     if (prof_on) {
         if (prof_used == prof_timers.size()) prof_timers.emplace_back();
         t = &prof_timers[prof_used++];
         t->start(st);
     }
-    if (inverse) ntt_inverse(src, dst, J, tabs, st);
+    if (inverse) ntt_inverse(src, dst, J, tabs, st, src2);
     else ntt_forward(src, dst, J, tabs, st);
     if (t) { t->mark_stop(st); prof_limbs += limbs; prof_calls++; }
     n_ntt_limbs += limbs;
@@ -1091,7 +1092,7 @@ const BaseConvTable* Engine::moddown_table_dev(int level, int drop) {
 }
 
 // ------------------------------------------------------------------ hybrid key switching (spec S5, S6)
-Decomp Engine::decompose(const u64* d, int level) {
+Decomp Engine::decompose(const u64* d, int level, const u64* times) {
     const size_t n = N();
     const int nq = level + 1, rows = nq + K();
     const int beta = (nq + prm.alpha - 1) / prm.alpha;
@@ -1107,7 +1108,7 @@ Decomp Engine::decompose(const u64* d, int level) {
         memset(&J, 0, sizeof(J));
         J.n = nq; J.nz = 1;
         for (int i = 0; i < nq; i++) { J.rows[0][i] = J.srows[0][i] = (unsigned char)i; J.mods[0][i] = (unsigned char)i; }
-        run_ntt(d, coef, J, true, nq);
+        run_ntt(d, coef, J, true, nq, times);      // times != null: the polynomial is d * times, formed inside the transform
     }
     // fast basis conversion of every digit to the other moduli of Q_level u P: one launch, z = digit.  The digit's own
     // limbs are never copied: the inner product reads them from the NTT-domain input (Decomp::own).
@@ -1144,13 +1145,14 @@ Decomp Engine::decompose(const u64* d, int level) {
 
 // <digits, evk> (+ P * addend) into acc = [2][level+1+K][N] over Q_level u P; with accumulate the result is added to
 // what acc already holds (several key switches sharing ONE ModDown)
-void Engine::ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64* acc, const u64* addend, bool accumulate) {
+void Engine::ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64* acc, const u64* addend, bool accumulate,
+                      bool tensor) {
     const int level = D.level, nq = level + 1;
     std::vector<int> qp = mods_qp(level);
     LimbList ll = limb_list(qp);
     LimbList er = limb_list(qp);                 // evk rows are indexed by global modulus index
     launch_ks_inner(ks, acc, D.ext, D.own, evk->d, perm, ll, er, D.beta, nmod(), nq, prm.alpha, addend, sl_pmodq,
-                    accumulate ? 1 : 0, st);
+                    accumulate ? 1 : 0, st, tensor);
     n_keyswitch++;
 }
 
@@ -1193,10 +1195,11 @@ void Engine::ks_moddown(u64* acc, int level, int drop, u64* out) {
 
 // inner product with the key, then ONE division by P * q_{level-drop+1..level}: out is [2][level+1-drop][N].
 // addend ([2][level+1][N], e.g. the (d0, d1) of a tensor product) is folded in as P * addend before the division.
-void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out, const u64* addend, int drop) {
+void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out, const u64* addend, int drop,
+                      bool tensor) {
     const int rows = D.level + 1 + K();
     u64* acc = alloc((size_t)2 * rows * N());
-    ks_inner(D, evk, perm, acc, addend, false);
+    ks_inner(D, evk, perm, acc, addend, false, tensor);
     ks_moddown(acc, D.level, drop, out);
     release(acc);
 }
@@ -1381,6 +1384,17 @@ Ct* Engine::mul(Ct* a, Ct* b) {
     b = level_down(b, l);
     const size_t n = N(), ps = (size_t)(l + 1) * n;
     LimbList ll = limb_list(mods_q(l));
+    if (fuse_tensor) {
+        // the tensor product is never written: d2 = a1 b1 is formed inside the inverse transform of the decomposition
+        // and (as the digits' own rows) inside the inner product, which also adds P (a0 b0, a0 b1 + a1 b0)
+        Decomp D = decompose(a->d + ps, l, b->d + ps);
+        D.own = a->d;
+        Ct* r = new_ct(2, l - 1);
+        ks_apply(D, &relin, nullptr, r->d, b->d, 1, true);
+        release(D.ext);
+        n_mul_cc++;
+        return r;
+    }
     u64* t = alloc(3 * ps);
     launch_tensor(ks, t, a->d, b->d, ll, st);
     // relinearisation and rescale in one division: (<digits(d2), rlk> + P (d0, d1)) / (P q_l)   (spec S6b)

@@ -240,16 +240,18 @@ class Engine {
     // ---- low-level pieces (exposed through the C ABI for parity tests against the oracle)
     void ntt_rows(u64* data, const std::vector<int>& rows, const std::vector<int>& mods, bool inverse, int nz = 1,
                   size_t zstride = 0);
-    void run_ntt(const u64* src, u64* dst, const NttJob& J, bool inverse, long limbs);
+    void run_ntt(const u64* src, u64* dst, const NttJob& J, bool inverse, long limbs, const u64* src2 = nullptr);
     void run_ntt_fused(const u64* src, u64* dst, const NttJob& J, const NttFuse& F, long limbs);
+    bool fuse_tensor = true;               // CKKS_TENSOR_FUSE=0: ct x ct writes its tensor product (k_tensor) first
     bool fuse_ntt = true;                  // CKKS_NTT_FUSE=0: stand-alone lift / subtract-scale kernels (A/B timing)
     void profile_begin();
     void profile_end(double* ms, long* calls, long* limbs);
-    Decomp decompose(const u64* d, int level);
+    Decomp decompose(const u64* d, int level, const u64* times = nullptr);
     void ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out /* [2][level+1-drop][N] */,
-                  const u64* addend = nullptr, int drop = 0);
+                  const u64* addend = nullptr, int drop = 0, bool tensor = false);
     void key_switch(const u64* d, int level, const EvalKey* evk, u64* out);
-    void ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64* acc, const u64* addend, bool accumulate);
+    void ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64* acc, const u64* addend, bool accumulate,
+                  bool tensor = false);
     void ks_moddown(u64* acc, int level, int drop, u64* out);
     void automorph(u64* out, const u64* in, int rows, int npoly, u64 g);
     const u32* galois_perm(u64 g);

@@ -119,6 +119,10 @@ __global__ void k_permute(KShape S, u64* __restrict__ out, const u64* __restrict
 // the decomposition).
 // If addend != null ([2][nq][N], NTT domain) the q rows also receive P * addend (merged relinearisation:
 // acc = <digits, evk> + P (d0, d1), so that one ModDown by P q_l .. also performs the rescale, spec S6b).
+// TENSOR: the switched polynomial is the d2 of a ct x ct product that was never written out -- the digit's own rows are
+// a1*b1 computed here, and the addend is P*(a0 b0, a0 b1 + a1 b0) from the operands (`own` = a, `addend` = b, both
+// [2][nq][N]; same formulas as k_tensor, so the result is bit-identical to tensor + inner product).
+template <bool TENSOR>
 __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restrict__ ext, const u64* __restrict__ own,
                            const u64* __restrict__ evk, const u32* __restrict__ perm, const GRID_CONST LimbList L,
                            const GRID_CONST LimbList ERow, int beta, int rows, int evk_rows, int nq, int alpha,
@@ -132,8 +136,14 @@ __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restric
         const u32 k = blockIdx.x * TPB + threadIdx.x;
         const u32 ks = perm ? ldg(perm + k) : k;
         u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+        u64 a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+        if (TENSOR && row < nq) {
+            a0 = own[(size_t)row * N + k];    a1 = own[((size_t)nq + row) * N + k];
+            b0 = addend[(size_t)row * N + k]; b1 = addend[((size_t)nq + row) * N + k];
+        }
         for (int j = 0; j < beta; j++) {
-            const u64 x = j == jown ? own[(size_t)row * N + ks] : ext[((size_t)j * rows + row) * N + ks];
+            const u64 x = j == jown ? (TENSOR ? barrett_mul(a1, b1, m) : own[(size_t)row * N + ks])
+                                    : ext[((size_t)j * rows + row) * N + ks];
             const u64* e = evk + ((size_t)j * 2 * evk_rows + er) * N + k;
             mac128(h0, l0, x, ldg(e));
             mac128(h1, l1, x, ldg(e + (size_t)evk_rows * N));
@@ -143,7 +153,15 @@ __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restric
             }
         }
         u64 r0 = barrett_reduce128(h0, l0, m), r1 = barrett_reduce128(h1, l1, m);
-        if (addend != nullptr && row < nq) {
+        if (TENSOR) {
+            if (row < nq) {
+                u64 hi = 0, lo = 0;
+                mac128(hi, lo, a0, b1);
+                mac128(hi, lo, a1, b0);
+                r0 = add_mod(r0, shoup_mul(barrett_mul(a0, b0, m), PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+                r1 = add_mod(r1, shoup_mul(barrett_reduce128(hi, lo, m), PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+            }
+        } else if (addend != nullptr && row < nq) {
             r0 = add_mod(r0, shoup_mul(addend[(size_t)row * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
             r1 = add_mod(r1, shoup_mul(addend[((size_t)nq + row) * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
         }
@@ -417,10 +435,14 @@ void launch_permute(KShape S, u64* out, const u64* a, const u32* perm, int rows,
 }
 void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u64* evk, const u32* perm,
                      const LimbList& L, const LimbList& ERow, int beta, int evk_rows, int nq, int alpha,
-                     const u64* addend, const ScalarList& PmodQ, int accumulate, dev_stream st) {
-    if (L.n)
-        LAUNCH(k_ks_inner, grid3(S, L.n), dim3(TPB), st, S, acc, ext, own, evk, perm, L, ERow, beta, L.n, evk_rows, nq,
-               alpha, addend, PmodQ, accumulate);
+                     const u64* addend, const ScalarList& PmodQ, int accumulate, dev_stream st, bool tensor) {
+    if (!L.n) return;
+    if (tensor)
+        LAUNCH(k_ks_inner<true>, grid3(S, L.n), dim3(TPB), st, S, acc, ext, own, evk, perm, L, ERow, beta, L.n, evk_rows,
+               nq, alpha, addend, PmodQ, accumulate);
+    else
+        LAUNCH(k_ks_inner<false>, grid3(S, L.n), dim3(TPB), st, S, acc, ext, own, evk, perm, L, ERow, beta, L.n, evk_rows,
+               nq, alpha, addend, PmodQ, accumulate);
 }
 void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns,
                          int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st) {

@@ -46,7 +46,7 @@ void launch_add_const(KShape S, u64* out, const u64* a, const LimbList& L, const
 void launch_tensor(KShape S, u64* d, const u64* a, const u64* b, const LimbList& L, dev_stream st);
 void launch_permute(KShape S, u64* out, const u64* a, const u32* perm, int rows, int npoly, PolyStride ps, dev_stream st);
 // acc[2][rows][N] = sum_j ext[j][rows][N] * evk[j][2][evk_rows][N]; ERow maps working row -> evk row
-void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u64* evk, const u32* perm, const LimbList& L, const LimbList& ERow, int beta, int evk_rows, int nq, int alpha, const u64* addend, const ScalarList& PmodQ, int accumulate, dev_stream st);
+void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u64* evk, const u32* perm, const LimbList& L, const LimbList& ERow, int beta, int evk_rows, int nq, int alpha, const u64* addend, const ScalarList& PmodQ, int accumulate, dev_stream st, bool tensor = false);
 // nz independent conversions: slice z reads in + z*in_zs, writes out + z*out_zs, with table tabs_dev[z*tab_zstride]
 // (device memory); every table of the launch has exactly `ns` sources and at most `max_nt` targets
 void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns, int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st);

@@ -505,18 +505,28 @@ ntt_fwd_passB_ep(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T,
 }
 
 // ============================================================================================ inverse, pass B^-1
-template <bool FP>
+template <bool FP, bool MUL>
 __device__ __forceinline__ void inv_passB_body(const u64* __restrict__ s_in, u64* __restrict__ d_out, u64* sm, int tile,
-                                               u32 Rn, const ModConst& mc, const NttTables& T, int mod, size_t N) {
+                                               u32 Rn, const ModConst& mc, const NttTables& T, int mod, size_t N,
+                                               const u64* __restrict__ s_in2) {
     const u64 q = mc.q;
     const u64* W = (FP ? reinterpret_cast<const u64*>(T.inv_d) : T.inv) + (size_t)mod * N;
     const u64* C = (FP ? reinterpret_cast<const u64*>(T.inv_q) : T.inv_s) + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
     FOR_THREADS {
+        if (MUL) {
+            // the transformed polynomial is the product of two NTT-domain rows (d2 = a1 * b1 of a ct x ct) formed on the fly
+            u64 x[16], y[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) cp_async8(sm + pad16(k * 256 + threadIdx.x), s_in + k * 256 + threadIdx.x);
-        if (NTT_PREFETCH) tw_prefetch(W, C, 16u * (Rn + (u32)(tile * 16 + threadIdx.x / 16)) + (u32)(threadIdx.x % 16));
-        cp_async_wait_all();
+            for (int k = 0; k < 16; k++) { x[k] = s_in[k * 256 + threadIdx.x]; y[k] = s_in2[k * 256 + threadIdx.x]; }
+#pragma unroll
+            for (int k = 0; k < 16; k++) sm[pad16(k * 256 + threadIdx.x)] = barrett_mul(x[k], y[k], mc);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) cp_async8(sm + pad16(k * 256 + threadIdx.x), s_in + k * 256 + threadIdx.x);
+            if (NTT_PREFETCH) tw_prefetch(W, C, 16u * (Rn + (u32)(tile * 16 + threadIdx.x / 16)) + (u32)(threadIdx.x % 16));
+            cp_async_wait_all();
+        }
     }
     BLOCK_SYNC;
     FOR_THREADS {
@@ -572,8 +582,27 @@ ntt_inv_passB(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CON
     const ModConst mc = T.mc[mod];
     const u64* s_in = src + (size_t)slimb * N + (size_t)tile * 16 * 256;
     u64* d_out = dst + (size_t)limb * N + (size_t)tile * 16 * 256;
-    if (use_fp(mc.q)) inv_passB_body<true>(s_in, d_out, sm, tile, Rn, mc, T, mod, N);
-    else inv_passB_body<false>(s_in, d_out, sm, tile, Rn, mc, T, mod, N);
+    if (use_fp(mc.q)) inv_passB_body<true, false>(s_in, d_out, sm, tile, Rn, mc, T, mod, N, nullptr);
+    else inv_passB_body<false, false>(s_in, d_out, sm, tile, Rn, mc, T, mod, N, nullptr);
+}
+// inverse pass B of the product of two polynomials (rows srows[z][i] of src and of src2)
+__global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_B)
+ntt_inv_passB_mul(const u64* __restrict__ src, const u64* __restrict__ src2, u64* __restrict__ dst, const GRID_CONST NttJob J,
+                  NttTables T) {
+    CKKS_SHARED u64 sm[kPassBData];
+    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
+    const int limb = J.rows[blockIdx.z][blockIdx.y], slimb = J.srows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const size_t N = (size_t)1 << T.logn;
+    const u32 Rn = (u32)(N >> 8);
+    src += blockIdx.z * J.szs;
+    src2 += blockIdx.z * J.szs;
+    dst += blockIdx.z * J.dzs;
+    const ModConst mc = T.mc[mod];
+    const size_t off = (size_t)slimb * N + (size_t)tile * 16 * 256;
+    u64* d_out = dst + (size_t)limb * N + (size_t)tile * 16 * 256;
+    if (use_fp(mc.q)) inv_passB_body<true, true>(src + off, d_out, sm, tile, Rn, mc, T, mod, N, src2 + off);
+    else inv_passB_body<false, true>(src + off, d_out, sm, tile, Rn, mc, T, mod, N, src2 + off);
 }
 
 // ============================================================================================ inverse, pass A^-1
@@ -719,11 +748,12 @@ void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J, const NttTable
     else LAUNCH(ntt_fwd_passB, gridB, dim3(kThreads), st, dst, J, T);
 }
 
-void ntt_inverse(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st) {
+void ntt_inverse(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st, const u64* src2) {
     if (J.n == 0 || J.nz == 0) return;
     const unsigned R = 1u << (T.logn - 8);
     dim3 gridB(R / 16, J.n, J.nz);
-    LAUNCH(ntt_inv_passB, gridB, dim3(kThreads), st, src, dst, J, T);
+    if (src2) LAUNCH(ntt_inv_passB_mul, gridB, dim3(kThreads), st, src, src2, dst, J, T);
+    else LAUNCH(ntt_inv_passB, gridB, dim3(kThreads), st, src, dst, J, T);
     if (T.logn == 16) {
         dim3 gridA(16, J.n, J.nz);
         LAUNCH(ntt_inv_passA<8>, gridA, dim3(kThreads), st, dst, J, T);
