@@ -173,6 +173,7 @@ Engine::Engine(const Params& P) : prm(P) {
     arenas[0] = &main_arena;
     if (const char* v = getenv("CKKS_NTT_FUSE")) fuse_ntt = atoi(v) != 0;
     if (const char* v = getenv("CKKS_TENSOR_FUSE")) fuse_tensor = atoi(v) != 0;
+    if (const char* v = getenv("CKKS_BC_MMA")) bc_mma = atoi(v) != 0;
     if (const char* v = getenv("CKKS_CHEB_DEGREE")) prm.boot.cheb_degree = atoi(v);      // tuning / A-B runs only
     mod = prm.q;
     mod.insert(mod.end(), prm.p.begin(), prm.p.end());
@@ -1017,6 +1018,38 @@ BaseConvTable Engine::make_bc_table(const std::vector<int>& src, const std::vect
     dev::sync(st);
     T.hat = dh;
     T.hat_s = dhs;
+    if (T.ns <= BC_MMA_MAX_SRC) {
+        // tensor-core path (kernels.cu: k_base_convert_mma): the hat matrix cut into bytes, Toeplitz-expanded over the
+        // 16 diagonals and stored in mma.m16n8k32 A-fragment order; 2^(8d) mod q_t for the recombination
+        const int ntg = (T.nt + 7) / 8;
+        std::vector<u32> af((size_t)ntg * 8 * 2 * 32 * 4, 0);
+        auto entry = [&](int t, int d, int k) -> u32 {          // row (t, d), column k = (i, a)
+            const int i = k / 8, a = k % 8, b = d - a;
+            if (t >= T.nt || i >= T.ns || b < 0 || b > 7) return 0;
+            return (u32)((hat[(size_t)i * T.nt + t] >> (8 * b)) & 0xff);
+        };
+        for (int tg = 0; tg < ntg; tg++)
+            for (int j = 0; j < 8; j++)
+                for (int ks = 0; ks < 2; ks++)
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int g = lane >> 2, q4 = lane & 3, t = tg * 8 + g, k0 = ks * 32 + q4 * 4;
+                        u32* r = &af[((((size_t)tg * 8 + j) * 2 + ks) * 32 + lane) * 4];
+                        for (int e = 0; e < 4; e++) {
+                            r[0] |= entry(t, 2 * j, k0 + e) << (8 * e);
+                            r[1] |= entry(t, 2 * j + 1, k0 + e) << (8 * e);
+                            r[2] |= entry(t, 2 * j, k0 + 16 + e) << (8 * e);
+                            r[3] |= entry(t, 2 * j + 1, k0 + 16 + e) << (8 * e);
+                        }
+                    }
+        std::vector<u64> p8((size_t)T.nt * 16, 0);
+        for (int t = 0; t < T.nt; t++) {
+            const u64 qt = mod[tgt[t]];
+            u64 pw = 1 % qt;
+            for (int d = 0; d < 16; d++) { p8[(size_t)t * 16 + d] = pw; pw = mulmod_h(pw, 256 % qt, qt); }
+        }
+        T.afrag = upload(this, af, owned);
+        T.pow8 = upload(this, p8, owned);
+    }
     return T;
 }
 
@@ -1132,10 +1165,10 @@ Decomp Engine::decompose(const u64* d, int level, const u64* times) {
         const BaseConvTable* tabs = modup_tables_dev(level);
         const int ns_last = nq - (beta - 1) * prm.alpha;
         const int nfull = ns_last == prm.alpha ? beta : beta - 1;
-        if (nfull) launch_base_convert(ks, D.ext, coef, tabs, 1, prm.alpha, rows, nfull, 0, (size_t)rows * n, st);
+        if (nfull) launch_base_convert(ks, D.ext, coef, tabs, 1, prm.alpha, rows, nfull, 0, (size_t)rows * n, st, bc_mma);
         if (nfull < beta)
             launch_base_convert(ks, D.ext + (size_t)nfull * rows * n, coef, tabs + nfull, 1, ns_last, rows, 1, 0,
-                                (size_t)rows * n, st);
+                                (size_t)rows * n, st, bc_mma);
     }
     // one batched forward NTT over the converted rows of all digits (z = digit)
     run_ntt(D.ext, D.ext, J, false, modup_limbs);
@@ -1168,7 +1201,7 @@ void Engine::ks_moddown(u64* acc, int level, int drop, u64* out) {
     ntt_rows(acc, prow, pmod, true, 2, (size_t)rows * n);
     u64* conv = alloc((size_t)2 * nout * n);
     launch_base_convert(ks, conv, acc, moddown_table_dev(level, drop), 0, K() + drop, nout, 2, (size_t)rows * n,
-                        (size_t)nout * n, st);
+                        (size_t)nout * n, st, bc_mma);
     std::vector<int> qi = mods_q(level - drop);
     if (fuse_ntt) {
         // out = (acc - NTT(conv)) * (P q_dropped)^-1 as the epilogue of the transform's second pass

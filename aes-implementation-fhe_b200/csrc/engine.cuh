@@ -242,6 +242,7 @@ class Engine {
                   size_t zstride = 0);
     void run_ntt(const u64* src, u64* dst, const NttJob& J, bool inverse, long limbs, const u64* src2 = nullptr);
     void run_ntt_fused(const u64* src, u64* dst, const NttJob& J, const NttFuse& F, long limbs);
+    bool bc_mma = false;                   // CKKS_BC_MMA=1: basis conversion as a byte-sliced u8 tensor-core GEMM (measured slower: profiles/README.md)
     bool fuse_tensor = true;               // CKKS_TENSOR_FUSE=0: ct x ct writes its tensor product (k_tensor) first
     bool fuse_ntt = true;                  // CKKS_NTT_FUSE=0: stand-alone lift / subtract-scale kernels (A/B timing)
     void profile_begin();

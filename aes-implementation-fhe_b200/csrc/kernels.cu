@@ -233,6 +233,118 @@ k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in, cons
     }
 }
 
+#ifndef CKKS_EMU
+// ------------------------------------------------------------------ basis conversion on the tensor cores
+// The same sum  out[n][t] = sum_i y_i[n] * hat[i][t]  (mod q_t), as an 8-bit integer GEMM.  y_i and hat are cut into
+// bytes, y_i = sum_a ya 2^(8a), hat = sum_b hb 2^(8b); the products with a + b = d form diagonal d:
+//     S_d[n][t] = sum_{i, a} ya[n][(i,a)] * hb[(i,a)][(t,d)],   hb[(i,a)][(t,d)] = byte (d - a) of hat[i][t]  (or 0)
+// i.e. ONE [16 d x 8 t] x [64] x [n] integer GEMM per group of 8 targets (mma.sync.m16n8k32.u8.u8.s32; |S_d| < 2^22).
+// The M rows of tile j are ordered (d = 2j, t = 0..7), (d = 2j + 1, t = 0..7), so the thread with groupID g ends up holding
+// ALL 16 diagonals of target g for its two coefficients and finishes them alone:
+//     out = sum_d S_d * (2^(8d) mod q_t)  (< 2^88: two 32 x 32 + 64 multiply-adds per diagonal)  -> ONE Barrett reduction.
+// About 70 CUDA-core instructions per output instead of ~195 (8 x 128-bit multiply-accumulate + three-step reduction).
+__device__ __forceinline__ void mma_u8(int (&c)[4], const uint4& a, u32 b0, u32 b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+constexpr int BCM_TILE = 128;          // coefficients per CTA: 4 warps x 4 steps x 8
+constexpr int BCM_YSTRIDE = 9;         // u64 per coefficient row of ys (8 sources + 1 pad: conflict-free 32-bit reads)
+#ifndef BCM_MIN_BLOCKS
+#define BCM_MIN_BLOCKS 6
+#endif
+#ifndef BCM_TG_PER_CTA
+#define BCM_TG_PER_CTA 8      // all target groups in one CTA (1 or 2 per CTA measured slower: y_i recomputed, more CTAs than SM slots)
+#endif
+template <int NS>
+__global__ void __launch_bounds__(BCM_TILE, BCM_MIN_BLOCKS)
+k_base_convert_mma(KShape S, u64* __restrict__ out, const u64* __restrict__ in, const BaseConvTable* __restrict__ tabs,
+                   int tab_zstride, size_t in_zs, size_t out_zs) {
+    __shared__ __align__(16) u64 ys[BCM_TILE * BCM_YSTRIDE];
+    __shared__ u64 s_pow8[BC_MAX_TGT * 16];
+    __shared__ u64 s_q[BC_MAX_TGT], s_mu[BC_MAX_TGT], s_negD[BC_MAX_TGT];
+    __shared__ u32 s_k1[BC_MAX_TGT], s_orow[BC_MAX_TGT];
+    __shared__ unsigned char s_u[BCM_TILE];
+    const size_t N = (size_t)1 << S.logn;
+    const BaseConvTable& T = tabs[blockIdx.z * tab_zstride];
+    const int nt = T.nt, tid = threadIdx.x;
+    // blockIdx.y picks BCM_TG_PER_CTA target groups: more CTAs in flight for the small launches of a key switch (the y_i
+    // are recomputed per CTA: NS multiplications against 8 x 16 diagonals of recombination)
+    const int tg_beg = blockIdx.y * BCM_TG_PER_CTA;
+    if (tg_beg * 8 >= nt) return;
+    const u64* src = in + blockIdx.z * in_zs;
+    u64* dst = out + blockIdx.z * out_zs + (size_t)blockIdx.x * BCM_TILE;
+    {
+        // y_i = x_i * (D/s_i)^-1 mod s_i and the overflow count of the exact variant (same arithmetic as k_base_convert)
+        const size_t k = (size_t)blockIdx.x * BCM_TILE + tid;
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            u64 y = 0;
+            if (i < NS) {
+                y = shoup_mul(src[(size_t)T.srow[i] * N + k], T.hatinv[i], T.hatinv_s[i], S.mc[T.src[i]].q);
+                v = fadd_rn(v, fmul_rn(ull2d_rn(y), T.inv_src[i]));
+            }
+            ys[tid * BCM_YSTRIDE + i] = y;
+        }
+        s_u[tid] = T.exact ? (unsigned char)d2ll_rn(v) : 0;
+        for (int e = tid; e < nt * 16; e += BCM_TILE) s_pow8[e] = ldg(T.pow8 + e);
+        if (tid < nt) {
+            const ModConst m = S.mc[T.tgt[tid]];
+            s_q[tid] = m.q; s_mu[tid] = m.mu; s_k1[tid] = m.k1;
+            s_negD[tid] = T.negD[tid];
+            s_orow[tid] = T.orow[tid];
+        }
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
+    const uint4* AF = reinterpret_cast<const uint4*>(T.afrag) + lane;
+    const u32* yw = reinterpret_cast<const u32*>(ys);
+    const int exact = T.exact;
+#pragma unroll 1
+    for (int step = 0; step < 4; step++) {
+        const int n0 = warp * 32 + step * 8;
+        // B fragment: bytes k = (i, a) of coefficient n0 + g; this lane owns the 32-bit half q4 & 1 of sources
+        // q4/2, 2 + q4/2 (k-step 0) and 4 + q4/2, 6 + q4/2 (k-step 1)
+        const u32* row = yw + (size_t)(n0 + g) * (2 * BCM_YSTRIDE) + (q4 & 1);
+        const u32 b00 = row[2 * (q4 >> 1)], b01 = row[2 * (2 + (q4 >> 1))];
+        const u32 b10 = row[2 * (4 + (q4 >> 1))], b11 = row[2 * (6 + (q4 >> 1))];
+        const u64 u0 = s_u[n0 + 2 * q4], u1 = s_u[n0 + 2 * q4 + 1];
+#pragma unroll 1
+        for (int tg = tg_beg; tg < tg_beg + BCM_TG_PER_CTA && tg * 8 < nt; tg++) {
+            // the hat fragments of this target group come straight from the (L1-resident, 8 KB per group) table: holding
+            // them in registers across the steps costs 64 registers and half the resident CTAs
+            int acc[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0;
+                mma_u8(acc[j], __ldg(AF + ((size_t)(tg * 8 + j) * 2) * 32), b00, b01);
+                if (NS > 4) mma_u8(acc[j], __ldg(AF + ((size_t)(tg * 8 + j) * 2 + 1) * 32), b10, b11);
+            }
+            const int t = tg * 8 + g;
+            if (t < nt) {
+                ModConst m;
+                m.q = s_q[t]; m.mu = s_mu[t]; m.k1 = s_k1[t];
+                const u64* pw = s_pow8 + t * 16;
+                u64 a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+#pragma unroll
+                for (int d = 0; d < 15; d++) {
+                    const u64 p = pw[d], pl = p & 0xffffffffull, ph = p >> 32;
+                    const u64 s0 = (u64)(u32)acc[d >> 1][(d & 1) * 2], s1 = (u64)(u32)acc[d >> 1][(d & 1) * 2 + 1];
+                    a00 += s0 * pl; a01 += s0 * ph;
+                    a10 += s1 * pl; a11 += s1 * ph;
+                }
+                u64 lo0 = a00 + (a01 << 32), hi0 = (a01 >> 32) + (lo0 < a00);
+                u64 lo1 = a10 + (a11 << 32), hi1 = (a11 >> 32) + (lo1 < a10);
+                if (exact) { mac128(hi0, lo0, u0, s_negD[t]); mac128(hi1, lo1, u1, s_negD[t]); }
+                *reinterpret_cast<ulonglong2*>(dst + (size_t)s_orow[t] * N + n0 + 2 * q4) =
+                    make_ulonglong2(barrett_reduce128(hi0, lo0, m), barrett_reduce128(hi1, lo1, m));
+            }
+        }
+    }
+}
+#endif
+
 // ------------------------------------------------------------------ rescale helpers (spec S6)
 // t = (last + h) mod q_l (coefficient domain, single limb) -> delta[i] = (t mod q_i) - (h mod q_i)
 __global__ void k_rescale_delta(KShape S, u64* __restrict__ delta, const u64* __restrict__ last, const GRID_CONST LimbList L,
@@ -445,8 +557,16 @@ void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u
                nq, alpha, addend, PmodQ, accumulate);
 }
 void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns,
-                         int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st) {
+                         int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st, bool mma) {
     if (!nz || !max_nt) return;
+#ifndef CKKS_EMU
+    if (mma && ns <= BC_MMA_MAX_SRC) {
+        dim3 gm((1u << S.logn) / BCM_TILE, ((max_nt + 7) / 8 + BCM_TG_PER_CTA - 1) / BCM_TG_PER_CTA, nz);
+#define BCM_CASE(n) case n: LAUNCH(k_base_convert_mma<n>, gm, dim3(BCM_TILE), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs); return;
+        switch (ns) { BCM_CASE(1) BCM_CASE(2) BCM_CASE(3) BCM_CASE(4) BCM_CASE(5) BCM_CASE(6) BCM_CASE(7) BCM_CASE(8) }
+#undef BCM_CASE
+    }
+#endif
     dim3 g((1u << S.logn) / TPB, (max_nt + BC_CHUNK - 1) / BC_CHUNK, nz);
 #define BC_CASE(n) case n: LAUNCH(k_base_convert<n>, g, dim3(TPB), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs); break;
     switch (ns) {

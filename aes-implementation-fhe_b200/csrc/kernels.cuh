@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #define BC_MAX_SRC 16
+#define BC_MMA_MAX_SRC 8
 #define BC_MAX_TGT 48
 #ifndef BC_CHUNK
 #define BC_CHUNK 24
@@ -27,6 +28,10 @@ struct BaseConvTable {
     int exact;
     double inv_src[BC_MAX_SRC];        // 1 / s_i
     u64 negD[BC_MAX_TGT];              // q_t - (D mod q_t)
+    // tensor-core path (ns <= 8, k_base_convert_mma): the hat matrix byte-sliced and laid out in mma.m16n8k32 A-fragment
+    // order, [target group of 8][diagonal pair j][k-step][lane] x 16 bytes, and 2^(8 d) mod q_t, [nt][16]
+    const void* afrag;
+    const u64* pow8;
 };
 // shape shared by all kernels: N coefficients per row, modulus table
 struct KShape {
@@ -49,7 +54,7 @@ void launch_permute(KShape S, u64* out, const u64* a, const u32* perm, int rows,
 void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u64* evk, const u32* perm, const LimbList& L, const LimbList& ERow, int beta, int evk_rows, int nq, int alpha, const u64* addend, const ScalarList& PmodQ, int accumulate, dev_stream st, bool tensor = false);
 // nz independent conversions: slice z reads in + z*in_zs, writes out + z*out_zs, with table tabs_dev[z*tab_zstride]
 // (device memory); every table of the launch has exactly `ns` sources and at most `max_nt` targets
-void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns, int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st);
+void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns, int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st, bool mma = false);
 void launch_rescale_delta(KShape S, u64* delta, const u64* last, const LimbList& L, int last_mod, int npoly, PolyStride ps, dev_stream st);
 void launch_center_lift(KShape S, u64* out, const u64* in, const LimbList& L, int src_mod, int npoly, PolyStride ps, dev_stream st);
 void launch_sample_uniform(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, dev_stream st);
