@@ -292,3 +292,25 @@ def test_device_renorm_equals_host_renorm(pair):
     want2 = np.ones(pair.n, dtype=np.complex128)
     want2[::stride] = want[::stride]
     assert np.abs(got2 - want2).max() < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("logn,levels", [(12, 6), (16, 5)])
+def test_tensor_core_base_conversion_bit_exact(logn, levels):
+    """The byte-sliced u8 tensor-core basis conversion (k_base_convert_mma, off by default: CKKS_BC_MMA=1) must give the
+    same integers as the oracle's conversion in ModUp and in the exact ModDown: ct*ct, rotation, conjugation bit for bit."""
+    import os
+    os.environ["CKKS_BC_MMA"] = "1"
+    try:
+        p = Pair("cuda", logn, levels)
+    finally:
+        os.environ.pop("CKKS_BC_MMA", None)
+    rng = np.random.default_rng(12)
+    z1, z2 = (np.exp(2j * np.pi * rng.random(p.n)) for _ in range(2))
+    c1, c2, o1, o2 = p.eng.encrypt(z1), p.eng.encrypt(z2), p.orc.encrypt(z1), p.orc.encrypt(z2)
+    m, om = p.eng.multiply(c1, c2, p.rk), p.orc.mul_ct(o1, o2)
+    assert np.array_equal(p.export(m), om.c)
+    assert np.array_equal(p.export(p.eng.rotate(m, None, 7)), p.orc.rotate(om, 7).c)
+    assert np.array_equal(p.export(p.eng.conjugate(c1)), p.orc.conjugate(o1).c)
+    m2 = p.eng.multiply(m, m, p.rk)
+    assert np.array_equal(p.export(m2), p.orc.mul_ct(om, om).c)
