@@ -143,3 +143,28 @@ def test_capture_rejects_host_round_trips_and_recovers():
         call(eng.level_down(a, 2), b)                                                   # wrong level
     call.close()
     assert np.abs(eng.decrypt(eng.multiply(a, b, rk)) - z1 * z2).max() < 1e-7
+
+
+def test_bench_line_contract_on_the_emulation_build():
+    """bench.py's own arm, run end to end on the test-only emulation build (N = 2^12, marked invalid as a measurement):
+    the JSON line must carry every key the driver and the judge read, the captured-graph path must be the one that ran,
+    and the decrypted bytes must equal the plain FIPS-197 round."""
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--dry-run-emulation", "--pairs", "1", "--steps", "1",
+                          "--warmup", "1", "--no-dec"], capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == "aes128_fhe_blocks_per_s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["vs_baseline"] is None and d["dtype"] == "u64" and d["data"] == "synthetic"
+    assert "workload" in d["config"] and d["config"]["pairs_per_gpu"] == 1
+    assert d["config"]["cuda_graph"]["launches"] > 1000 and d["config"]["cuda_graph"]["capture_misses"] == 0
+    assert d["gpu_launches"] >= d["config"]["cuda_graph"]["launches"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in d["roofline"], k
+    assert d["bytes_exact_vs_fips197_round"] is True
+    assert "invalid" in d                                   # a dry run never passes for a measurement
