@@ -134,6 +134,17 @@ class EngineContext:
         return self.engine.snap_zeta16(ct, -1 if level is None else int(level), stride)
 
     @property
+    def device_codec(self) -> bool:
+        """The backend encrypts / decrypts zeta16 nibbles itself (no complex slot vectors over PCIe, no host loops)."""
+        return self.fused and hasattr(self.engine, "encrypt_zeta16") and hasattr(self.engine, "decrypt_zeta16")
+
+    def encrypt_nibbles(self, nibbles, level=None):
+        return self.engine.encrypt_zeta16(nibbles, -1 if level is None else int(level))
+
+    def decrypt_nibbles(self, ct) -> np.ndarray:
+        return self.engine.decrypt_zeta16(ct)
+
+    @property
     def device_renorm(self) -> bool:
         return self.fused and hasattr(self.engine, "snap_zeta16")
 

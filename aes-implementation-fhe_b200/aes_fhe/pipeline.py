@@ -284,6 +284,9 @@ class BatchedStateEncoder:
         full = np.zeros((self.stride, 16), dtype=np.uint8)
         full[:st.shape[0]] = st
         # slot i*stride + b  <-  byte i of block b
+        if getattr(self.ctx, "device_codec", False):          # nibbles over PCIe, codeword lookup on the device
+            return (self.ctx.encrypt_nibbles(((full >> 4) & 0xF).T.reshape(-1), level=level),
+                    self.ctx.encrypt_nibbles((full & 0xF).T.reshape(-1), level=level))
         hi = to_zeta((full >> 4) & 0xF, 16).T.reshape(-1)
         lo = to_zeta(full & 0xF, 16).T.reshape(-1)
         if level is None:
@@ -298,8 +301,12 @@ class BatchedStateEncoder:
         return self.encode(self.decode(ct_hi, ct_lo), level=level)
 
     def decode(self, ct_hi, ct_lo) -> np.ndarray:
-        hi = from_zeta(self.ctx.decrypt(ct_hi), 16).reshape(16, self.stride).T
-        lo = from_zeta(self.ctx.decrypt(ct_lo), 16).reshape(16, self.stride).T
+        if getattr(self.ctx, "device_codec", False):
+            hi = self.ctx.decrypt_nibbles(ct_hi).reshape(16, self.stride).T
+            lo = self.ctx.decrypt_nibbles(ct_lo).reshape(16, self.stride).T
+        else:
+            hi = from_zeta(self.ctx.decrypt(ct_hi), 16).reshape(16, self.stride).T
+            lo = from_zeta(self.ctx.decrypt(ct_lo), 16).reshape(16, self.stride).T
         return ((hi.astype(np.uint8) << 4) | lo).astype(np.uint8)
 
 

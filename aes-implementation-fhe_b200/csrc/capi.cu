@@ -150,6 +150,12 @@ int ckks_encrypt(ckks_engine* e, const double* z, int level, ckks_ct** out) {
     return guard([&] { *out = H(e->E->encrypt(z, level)); });
 }
 int ckks_decrypt(ckks_engine* e, const ckks_ct* ct, double* z) { return guard([&] { e->E->decrypt(C(ct), z); }); }
+int ckks_encrypt_zeta16(ckks_engine* e, const uint8_t* nibbles, int level, ckks_ct** out) {
+    return guard([&] { *out = H(e->E->encrypt_zeta16(nibbles, level)); });
+}
+int ckks_decrypt_zeta16(ckks_engine* e, const ckks_ct* ct, uint8_t* nibbles_out) {
+    return guard([&] { e->E->decrypt_zeta16(C(ct), nibbles_out); });
+}
 int ckks_snap_zeta16(ckks_engine* e, const ckks_ct* ct, int level, int stride, ckks_ct** out) {
     return guard([&] { *out = H(e->E->snap_zeta16(C(ct), level, stride)); });
 }

@@ -969,6 +969,36 @@ Ct* Engine::snap_zeta16(const Ct* a, int level, int stride) {
     return c;
 }
 
+// zeta_16 codec on the device: the caller ships one nibble per slot (n bytes instead of 16 n), the codeword lookup,
+// the embedding and the encryption run here; decryption returns the nearest-codeword index per slot (the host side of
+// reference state_encoder.py:14-38 / utils.py:9-19 moved next to the data)
+Ct* Engine::encrypt_zeta16(const unsigned char* nib_host, int level) {
+    if (!has_pk) throw std::runtime_error("encrypt needs a public key");
+    if (level < 0) level = prm.fresh_level;
+    if (level > L()) throw std::runtime_error("encrypt: bad level");
+    const size_t ns = slots();
+    unsigned char* nib = (unsigned char*)alloc((ns + 7) / 8);
+    double* z = (double*)alloc(2 * ns);
+    i64* coef = (i64*)alloc(N());
+    dev::h2d(nib, nib_host, ns, st);
+    launch_zeta16_from_nibbles(ks, z, nib, d_zeta16, st);
+    encode_coeffs_from_dev(coef, z, scales[level], false);           // unit-modulus slots cannot overflow
+    Ct* c = encrypt_coeffs(coef, level);
+    dev::sync(st);                                                    // nib_host may be reused by the caller
+    release(coef); release(z); release(nib);
+    return c;
+}
+void Engine::decrypt_zeta16(const Ct* c, unsigned char* nib_out_host) {
+    const size_t ns = slots();
+    double* zz = decrypt_to_dev(c);
+    unsigned char* nib = (unsigned char*)alloc((ns + 7) / 8);
+    launch_nibbles_from_zeta16(ks, nib, zz, st);
+    dev::d2h(nib_out_host, nib, ns, st);
+    dev::sync(st);
+    release(nib);
+    release(zz);
+}
+
 void Engine::decrypt(const Ct* c, double* z_out) {
     double* zz = decrypt_to_dev(c);
     dev::d2h(z_out, zz, 2 * slots() * sizeof(double), st);

@@ -200,6 +200,8 @@ class Engine {
     void decrypt(const Ct* c, double* z_out);
     double* decrypt_to_dev(const Ct* c);
     Ct* encrypt_coeffs(const i64* coef_dev, int level);
+    Ct* encrypt_zeta16(const unsigned char* nib_host, int level);   // one nibble per slot in, zeta_16 codewords encrypted
+    void decrypt_zeta16(const Ct* c, unsigned char* nib_out_host);  // nearest zeta_16 codeword index per slot out
     Ct* snap_zeta16(const Ct* a, int level, int stride);   // decrypt, snap to zeta_16 codewords, re-encrypt: all on device
 
     // ---- homomorphic ops (all out of place)

@@ -502,6 +502,25 @@ __global__ void k_snap_zeta16(KShape S, double* __restrict__ z, const double* __
     }
 }
 
+// zeta_16 codec on the device (the host side of reference utils.py:9-19 / state_encoder.py): nibble k <-> exp(-2 pi i k/16)
+__global__ void k_zeta16_from_nibbles(KShape S, double* __restrict__ z, const unsigned char* __restrict__ nib,
+                                      const double* __restrict__ table) {
+    FOR_THREADS {
+        const u32 j = blockIdx.x * TPB + threadIdx.x;
+        const int k = nib[j] & 15;
+        z[2 * j] = table[2 * k];
+        z[2 * j + 1] = table[2 * k + 1];
+    }
+}
+__global__ void k_nibbles_from_zeta16(KShape S, unsigned char* __restrict__ nib, const double* __restrict__ z) {
+    FOR_THREADS {
+        const u32 j = blockIdx.x * TPB + threadIdx.x;
+        const double ang = atan2(z[2 * j + 1], z[2 * j]);
+        int k = (int)rint(-ang * (16.0 / (2.0 * 3.14159265358979323846)));
+        nib[j] = (unsigned char)(((k % 16) + 16) % 16);
+    }
+}
+
 inline dim3 grid3(KShape S, int rows, int npoly = 1) { return dim3((1u << S.logn) / TPB, rows, npoly); }
 
 }  // namespace
@@ -609,6 +628,12 @@ void launch_special_ifft(KShape S, double* out, double* z, const u32* rot, const
 }
 void launch_snap_zeta16(KShape S, double* z, const double* table, int stride, dev_stream st) {
     LAUNCH(k_snap_zeta16, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, z, table, stride);
+}
+void launch_zeta16_from_nibbles(KShape S, double* z, const unsigned char* nib, const double* table, dev_stream st) {
+    LAUNCH(k_zeta16_from_nibbles, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, z, nib, table);
+}
+void launch_nibbles_from_zeta16(KShape S, unsigned char* nib, const double* z, dev_stream st) {
+    LAUNCH(k_nibbles_from_zeta16, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, nib, z);
 }
 void launch_round_coeffs(KShape S, i64* out, const double* w, double scale, int* flag, dev_stream st) {
     LAUNCH(k_round_coeffs, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, out, w, scale, flag);

@@ -65,3 +65,5 @@ void launch_special_ifft(KShape S, double* out, double* z, const u32* rot, const
 void launch_snap_zeta16(KShape S, double* z, const double* table, int stride, dev_stream st);
 void launch_round_coeffs(KShape S, i64* out, const double* w, double scale, int* flag, dev_stream st);
 void launch_center_to_w(KShape S, double* w, const u64* coef, int mod, double scale, dev_stream st);
+void launch_zeta16_from_nibbles(KShape S, double* z, const unsigned char* nib, const double* table, dev_stream st);
+void launch_nibbles_from_zeta16(KShape S, unsigned char* nib, const double* z, dev_stream st);

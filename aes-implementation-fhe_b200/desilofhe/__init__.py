@@ -539,6 +539,19 @@ class Engine:
         """Hard renorm on the device: decrypt, snap each slot to the nearest zeta_16 codeword, re-encrypt at `level`."""
         return self._new(self._lib.ckks_snap_zeta16, ct._h, int(level), int(stride))
 
+    def encrypt_zeta16(self, nibbles, level: int = -1) -> Ciphertext:
+        """Encrypt the codewords exp(-2 pi i k / 16) of one nibble k per slot; the lookup runs on the device."""
+        nib = np.ascontiguousarray(np.asarray(nibbles, dtype=np.uint8).reshape(-1))
+        if nib.size != self.slot_count:
+            raise ValueError(f"expected {self.slot_count} nibbles")
+        return self._new(self._lib.ckks_encrypt_zeta16, nib, int(level))
+
+    def decrypt_zeta16(self, ct: Ciphertext) -> np.ndarray:
+        """Index of the nearest zeta_16 codeword of every slot (uint8[slot_count])."""
+        out = np.empty(self.slot_count, dtype=np.uint8)
+        _capi.check(self._lib.ckks_decrypt_zeta16(self._ptr, ct._h, out))
+        return out
+
     def lincomb(self, cts: Sequence[Ciphertext], coeffs) -> Ciphertext:
         """sum_k coeffs[k] * cts[k]: one fused multiply-accumulate + one rescale per distinct input level."""
         n = len(cts)

@@ -70,6 +70,8 @@ def load():
         "ckks_encrypt": (i32, [vp, dp, i32, pp]),
         "ckks_decrypt": (i32, [vp, vp, dp]),
         "ckks_snap_zeta16": (i32, [vp, vp, i32, i32, pp]),
+        "ckks_encrypt_zeta16": (i32, [vp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"), i32, pp]),
+        "ckks_decrypt_zeta16": (i32, [vp, vp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")]),
         "ckks_ct_free": (None, [vp, vp]), "ckks_pt_free": (None, [vp, vp]),
         "ckks_ct_level": (i32, [vp]), "ckks_ct_npoly": (i32, [vp]), "ckks_pt_level": (i32, [vp]),
         "ckks_add": (i32, [vp, vp, vp, pp]), "ckks_sub": (i32, [vp, vp, vp, pp]),

@@ -88,6 +88,11 @@ int ckks_decrypt(ckks_engine* e, const ckks_ct* ct, double* slots_re_im_out);
  * without leaving the device: no D2H/H2D of the 512 KiB slot vector.  stride > 1 reproduces StateEncoder's layout
  * (data on slots 0 mod stride, 1.0 elsewhere, state_encoder.py:23-27); level < 0 means the fresh level. */
 int ckks_snap_zeta16(ckks_engine* e, const ckks_ct* ct, int level, int stride, ckks_ct** out);
+/* zeta_16 codec next to the data (the host loops of state_encoder.py:14-38 / utils.py:9-19): `nibbles` holds one value
+ * 0..15 per slot (slot_count bytes); encryption looks the codewords exp(-2 pi i k / 16) up on the device, decryption
+ * returns the index of the nearest codeword of every slot.  16 x fewer bytes over PCIe than complex128 slots. */
+int ckks_encrypt_zeta16(ckks_engine* e, const uint8_t* nibbles, int level, ckks_ct** out);
+int ckks_decrypt_zeta16(ckks_engine* e, const ckks_ct* ct, uint8_t* nibbles_out);
 void ckks_ct_free(ckks_engine* e, ckks_ct* ct);
 void ckks_pt_free(ckks_engine* e, ckks_pt* pt);
 int ckks_ct_level(const ckks_ct* ct);

@@ -130,6 +130,28 @@ def test_config5_batched_fips_round(boot_ctx):
     assert np.array_equal(drv.decode(*out), plain_round(blocks, rks[1]))
 
 
+def test_device_zeta16_codec_equals_the_host_codec(boot_ctx):
+    """encrypt_zeta16 / decrypt_zeta16 (nibbles over PCIe, codeword lookup and nearest-codeword search on the device)
+    against the host codec of the reference (utils.py:9-19): same slots within encryption noise, same nibbles exactly,
+    also for slots pushed a third of the way to the neighbouring codeword."""
+    which, ctx = boot_ctx
+    eng = ctx.engine
+    n = eng.slot_count
+    rng = np.random.default_rng(4)
+    nib = rng.integers(0, 16, n).astype(np.uint8)
+    ct = eng.encrypt_zeta16(nib)
+    assert ct.level == eng.params()["fresh_level"]
+    z = eng.decrypt(ct)
+    assert np.abs(z - aes_fhe.to_zeta(nib, 16)).max() < 1e-7
+    assert np.array_equal(eng.decrypt_zeta16(ct), nib)
+    assert np.array_equal(aes_fhe.from_zeta(z, 16), nib)
+    off = aes_fhe.to_zeta(nib, 16) * np.exp(1j * (2 * np.pi / 16) * rng.uniform(-0.33, 0.33, n)) * rng.uniform(0.7, 1.3, n)
+    assert np.array_equal(eng.decrypt_zeta16(eng.encrypt(off)), nib)
+    assert eng.encrypt_zeta16(nib, level=5).level == 5
+    with pytest.raises(ValueError):
+        eng.encrypt_zeta16(nib[:-1])
+
+
 def test_captured_round_replays_on_new_inputs(boot_ctx):
     """The batched FIPS round recorded as one graph (CUDA graph on the device, recorded closures under emulation): replays
     with OTHER blocks and ANOTHER round key must give the plain round of those inputs; the recording run itself executes
