@@ -248,12 +248,21 @@ class RowMajorShiftRows:
                         m[s * self.stride:(s + 1) * self.stride] = 1.0
                     else:
                         m[s * self.stride] = 1.0
-                self.parts.append((ctx.encode(m), step))
+                # fused mode rotates first (all steps share one ModUp) and masks afterwards: rot(ct * m) = rot(ct) * rot(m)
+                self.parts.append((ctx.encode(m), step, ctx.encode(np.roll(m, step)) if step else None))
 
     def _apply_one(self, ct):
         eng = self.ctx
+        if getattr(eng, "fused", False):
+            steps = [step for _, step, _ in self.parts if step]
+            rots = dict(zip(steps, eng.rotate_many(ct, steps)))
+            out = None
+            for mask, step, rolled in self.parts:
+                part = eng.multiply(rots[step], rolled) if step else eng.multiply(ct, mask)
+                out = part if out is None else eng.add(out, part)
+            return out
         out = eng.multiply(ct, 0.0)
-        for mask, step in self.parts:
+        for mask, step, _ in self.parts:
             part = eng.multiply(ct, mask)
             if step:
                 part = eng.rotate(part, step)

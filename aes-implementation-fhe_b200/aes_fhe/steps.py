@@ -462,7 +462,9 @@ class MixColFinal(_MixBase):
             two, thr0 = self._gf_shared([2, 3], ct_hi, ct_lo)
             thr = self._rot_pair(thr0, 1)
             steps = [-4 * k * self.stride for k in (2, 3)]
-            r2, r3 = zip(self.ctx.rotate_many(ct_hi, steps), self.ctx.rotate_many(ct_lo, steps))
+            # rot2 / rot3 only feed XOR4s that run at XOR4_DEPTH: rotate the state there, not at its own level
+            lo_hi, lo_lo = self.ctx.level_down(ct_hi, XOR4_DEPTH), self.ctx.level_down(ct_lo, XOR4_DEPTH)
+            r2, r3 = zip(self.ctx.rotate_many(lo_hi, steps), self.ctx.rotate_many(lo_lo, steps))
         else:
             r1, r2, r3 = self._shifts(ct_hi, ct_lo)
             log("rotc1", r1), log("rotc2", r2), log("rotc3", r3), log("in", (ct_hi, ct_lo))
