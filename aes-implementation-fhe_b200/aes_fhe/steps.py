@@ -27,6 +27,7 @@ import os as _os
 LANES_CONJ = _os.environ.get("AESFHE_LANES_CONJ", "1") == "1"
 LANES_AB = _os.environ.get("AESFHE_LANES_AB", "1") == "1"
 SHARE_GF_BASES = _os.environ.get("AESFHE_SHARE_GF_BASES", "1") == "1"   # fused mode: M_k(rot_k x) = rot_k(M_k x)
+XOR_MIRROR = _os.environ.get("AESFHE_XOR_MIRROR", "1") == "1"   # fused XOR4: no conjugations on the A side
 PRUNE_BASIS = _os.environ.get("AESFHE_PRUNE_BASIS", "1") == "1"   # fused mode: build only the powers a LUT uses
 
 # multiplicative depths of the steps, used for the encryption-level hints of the fused mode
@@ -127,6 +128,13 @@ class XOR4LUT:
         self.terms = [(p, q, complex(coeffs[p, q])) for (p, q) in self.pt]
         self.exps_a = sorted({p for p, _, _ in self.terms})
         self.exps_b = sorted({q for _, q, _ in self.terms})
+        # mirror split (fused mode): terms with p <= 8 as they are, terms with p > 8 conjugated onto A^(16-p) B^(16-q)
+        self._terms_direct = [(p, q, c) for p, q, c in self.terms if 1 <= p <= 8]
+        self._terms_mirror = [(16 - p, 16 - q, complex(np.conj(c))) for p, q, c in self.terms if p > 8]
+        self._exps_a_pos = sorted({p for p, _, _ in self._terms_direct} | {p for p, _, _ in self._terms_mirror})
+        need_b = {q for _, q, _ in self._terms_direct} | {q for _, q, _ in self._terms_mirror}
+        self._mirror_ok = (bool(self._terms_direct) and bool(self._terms_mirror) and need_b <= set(self.exps_b)
+                           and all(1 <= q <= 15 for q in need_b) and all(p != 0 for p, _, _ in self.terms))
 
     def _build_power_basis_16(self, ct, exps=None) -> Dict[int, Any]:
         eng = self.ctx
@@ -165,6 +173,14 @@ class XOR4LUT:
             # build both power bases at the common level (a cached round-key ciphertext may sit far above the state)
             lvl = min(a_ct.level, b_ct.level)
             a_ct, b_ct = eng.level_down(a_ct, lvl), eng.level_down(b_ct, lvl)
+        if getattr(eng, "fused", False) and XOR_MIRROR and PRUNE_BASIS and LANES_AB and self._mirror_ok:
+            # A^p for p > 8 is conj(A^(16-p)):  sum_{p>8} c A^p B^q = conj( sum conj(c) A^(16-p) B^(16-q) ), so only the
+            # positive powers of A are needed (no conjugations on the A side): two fused LUTs over the same bases and ONE
+            # conjugation instead of four
+            A, B = eng.pair_map(self._build_power_basis_16, (a_ct, self._exps_a_pos), (b_ct, self.exps_b))
+            la, lb = [A.get(k) for k in range(16)], [B.get(k) for k in range(16)]
+            direct, mirror = eng.pair_map(eng.lut2, (la, lb, self._terms_direct), (la, lb, self._terms_mirror))
+            return eng.add(direct, eng.conjugate(mirror))
         if getattr(eng, "fused", False) and LANES_AB:
             A, B = eng.pair_map(self._build_power_basis_16, (a_ct, self.exps_a), (b_ct, self.exps_b))   # two stream lanes
         else:

@@ -84,8 +84,9 @@ def test_config1_ark_subbytes_fips_vector(boot_ctx, fused):
     else:
         # XOR4 has odd exponents only: 5 products (2, 3, 4, 5, 7) and 4 conjugations per pruned power base
         # SubBytes baby-step/giant-step: 7 (zeta16 basis) + 1 (b = hi * lift) + 15 babies + 7 giants + 4 bivariate LUTs
-        assert c1["mul_cc"] - c0["mul_cc"] == 4 * 5 + 2 + 34      # 4 power bases + 2 fused XOR4 + SubBytes
-        assert c1["keyswitch"] - c0["keyswitch"] == 56 + 4 * 4 + 3    # + basis conjugations + 3 in SubBytes
+        # XOR4 mirror split: two fused LUTs per XOR4, conjugations only on the B side (4) plus one on the mirror half
+        assert c1["mul_cc"] - c0["mul_cc"] == 4 * 5 + 2 * 2 + 34   # 4 power bases + 2 XOR4 x 2 LUTs + SubBytes
+        assert c1["keyswitch"] - c0["keyswitch"] == 58 + 2 * (4 + 1) + 3   # + conjugations + 3 in SubBytes
     # per-stage slots against the reference-semantics stand-in: stated tolerance 1e-4 on unit-modulus slots
     sctx = aes_fhe.EngineContext(1, mode="cpu", thread_count=1, backend=ss, slot_count=ctx.engine.slot_count)
     sp = make_pipe(sctx)
