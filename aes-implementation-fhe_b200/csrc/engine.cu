@@ -534,6 +534,7 @@ void Engine::graph_wait(int slot) {
 // overwrite the contents of a static input of a graph (same shape) on the replay stream the graph will be launched on
 void Engine::ct_assign(Ct* dst, const Ct* src, int slot) {
     if (dst->npoly != src->npoly || dst->level != src->level) throw std::runtime_error("ct_assign: shape mismatch");
+    if (dst->d == src->d) return;                  // the static input itself: nothing to copy
     dev_stream s = replay_stream(slot);
     if (slot) dev::stream_wait(s, streams[0]);
     dev::d2d(dst->d, src->d, (size_t)src->npoly * (src->level + 1) * N() * sizeof(u64), s);
