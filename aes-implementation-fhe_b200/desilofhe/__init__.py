@@ -83,8 +83,11 @@ class Plaintext:
 
     def __init__(self, eng: "Engine", vec: np.ndarray):
         self._eng = eng
+        self._enc: Dict[int, int] = {}
         v = np.asarray(vec)
-        first = v.flat[0]
+        if v.ndim != 1 or v.size > eng.slot_count:
+            raise ValueError(f"expected a vector of at most {eng.slot_count} slots")
+        first = v.flat[0] if v.size else 0.0
         if v.size == eng.slot_count and np.all(v == first):
             self.const: Optional[complex] = complex(first)
             self.vec = None

@@ -314,3 +314,39 @@ def test_tensor_core_base_conversion_bit_exact(logn, levels):
     assert np.array_equal(p.export(p.eng.conjugate(c1)), p.orc.conjugate(o1).c)
     m2 = p.eng.multiply(m, m, p.rk)
     assert np.array_equal(p.export(m2), p.orc.mul_ct(om, om).c)
+
+
+def test_edge_cases_of_the_reference_surface(pair):
+    """The corners the reference's callers actually touch: short ("ragged") vectors are zero-padded,
+    over-long ones rejected; rotations by 0 / slot_count / negative multiples are identities; a degree-1 power basis;
+    operands many levels apart are aligned; constants as large as the XOR table's 95.5; the zero ciphertext; real input."""
+    eng = pair.eng
+    n = pair.n
+    rng = np.random.default_rng(9)
+    short = np.exp(2j * np.pi * rng.random(5))
+    got = eng.decrypt(eng.encrypt(short))
+    assert np.abs(got[:5] - short).max() < 1e-8 and np.abs(got[5:]).max() < 1e-8            # padded with zeros
+    with pytest.raises(ValueError):
+        eng.encrypt(np.ones(n + 1))
+    with pytest.raises(ValueError):
+        eng.encode(np.ones((2, n // 2)))
+    z = np.exp(2j * np.pi * rng.random(n))
+    c = eng.encrypt(z)
+    for steps in (0, n, -n, 3 * n):
+        assert np.abs(eng.decrypt(eng.rotate(c, None, steps)) - z).max() < 1e-8
+    assert np.abs(eng.decrypt(eng.rotate(c, None, n + 2)) - np.roll(z, 2)).max() < 1e-7
+    pb = eng.make_power_basis(c, 1, pair.rk)
+    assert len(pb) == 1 and np.array_equal(pair.export(pb[0]), pair.export(c))
+    deep = c
+    for _ in range(c.level - 1):
+        deep = eng.multiply(deep, 1.0)                                                       # one level per call
+    assert deep.level == 1
+    s = eng.add(c, deep)                                                                     # levels L and 1
+    assert s.level == 1 and np.abs(eng.decrypt(s) - 2 * z).max() < 1e-6
+    big = eng.multiply(c, 95.5)
+    assert np.abs(eng.decrypt(big) - 95.5 * z).max() < 1e-5
+    zero = eng.subtract(c, c)
+    assert zero.level == c.level and np.abs(eng.decrypt(zero)).max() < 1e-9
+    real = eng.decrypt(eng.encrypt(np.linspace(-1.0, 1.0, n)))                               # float64 input
+    assert np.abs(real - np.linspace(-1.0, 1.0, n)).max() < 1e-8
+    assert eng.decrypt(eng.encrypt(np.zeros(0))).shape == (n,)                                # empty input = all zeros
