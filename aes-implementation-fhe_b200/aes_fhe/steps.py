@@ -27,6 +27,7 @@ import os as _os
 LANES_CONJ = _os.environ.get("AESFHE_LANES_CONJ", "1") == "1"
 LANES_AB = _os.environ.get("AESFHE_LANES_AB", "1") == "1"
 SHARE_GF_BASES = _os.environ.get("AESFHE_SHARE_GF_BASES", "1") == "1"   # fused mode: M_k(rot_k x) = rot_k(M_k x)
+XOR_TREE = _os.environ.get("AESFHE_XOR_TREE", "0") == "1"       # fused MixColumns: (a ^ b) ^ (c ^ d) on two lanes; measured: no gain
 XOR_MIRROR = _os.environ.get("AESFHE_XOR_MIRROR", "1") == "1"   # fused XOR4: no conjugations on the A side
 PRUNE_BASIS = _os.environ.get("AESFHE_PRUNE_BASIS", "1") == "1"   # fused mode: build only the powers a LUT uses
 
@@ -486,6 +487,22 @@ class MixColFinal(_MixBase):
             log("rotc1", r1), log("rotc2", r2), log("rotc3", r3), log("in", (ct_hi, ct_lo))
             two = self.gf_mult_2(ct_hi, ct_lo)
             thr = self.gf_mult_3(*r1)
+        if getattr(self.ctx, "fused", False) and XOR_TREE and not isinstance(debug, dict):
+            # XOR is associative: (2x ^ 3 rot1) and (rot2 ^ rot3) are independent, so they (and their renorms) run on two
+            # lanes and only ONE XOR4 + renorm is left on the critical path after them (same three XOR4 pairs in total)
+            def left():
+                return self._renorm_pair(*self._xor_pair(two, thr), depth=XOR4_DEPTH)
+
+            def right():
+                return self._renorm_pair(*self._xor_pair(r2, r3), depth=XOR4_DEPTH)
+
+            u, w = self.ctx.lane_map(lambda f: f(), [(left,), (right,)])
+            acc = self._renorm_pair(*self._xor_pair(u, w), depth=0 if do_final_bootstrap else None)
+            out_hi, out_lo = acc
+            if do_final_bootstrap:
+                boot = lambda c: self.ctx.bootstrap(self.ctx.to_intt(c))
+                out_hi, out_lo = self.ctx.pair_map(boot, (out_hi,), (out_lo,))
+            return out_hi, out_lo
         log("two", two), log("thr", thr)
         acc = self._xor_pair(two, thr)
         log("acc1", acc)
@@ -562,6 +579,18 @@ class InvMixColumnsFHE(_MixBase):
             e11 = self.gf_mult_11(*r1); log("mul11", e11)
             e13 = self.gf_mult_13(*r2); log("mul13", e13)
             e9 = self.gf_mult_9(*r3); log("mul9", e9)
+        if getattr(self.ctx, "fused", False) and XOR_TREE and debug is None:
+            def left():
+                return self._renorm_pair(*self._xor_pair(e14, e11), depth=XOR4_DEPTH)
+
+            def right():
+                return self._renorm_pair(*self._xor_pair(e13, e9), depth=XOR4_DEPTH)
+
+            u, w = self.ctx.lane_map(lambda f: f(), [(left,), (right,)])
+            out_h, out_l = self._renorm_pair(*self._xor_pair(u, w), depth=0 if do_final_bootstrap else None)
+            if do_final_bootstrap:
+                out_h, out_l = self.ctx.pair_map(self.ctx.bootstrap, (out_h,), (out_l,))
+            return out_h, out_l
         acc = self._xor_pair(e14, e11)
         log("acc1", acc)
         acc = self._renorm_pair(*acc, depth=XOR4_DEPTH)
