@@ -171,3 +171,20 @@ def test_product_rotation_and_conjugation_semantics(orc):
     assert np.abs(orc.decrypt(orc.rotate(c1, 3)) - np.roll(z1, 3)).max() < 1e-6      # positive = right (shift_rows.py:35-37)
     assert np.abs(orc.decrypt(orc.rotate(c1, -5)) - np.roll(z1, -5)).max() < 1e-6
     assert np.abs(orc.decrypt(orc.conjugate(c1)) - np.conj(z1)).max() < 1e-6
+
+
+def test_bootstrap_oracle_refreshes_levels_within_tolerance():
+    """oracle/bootstrap_oracle.py (ModRaise, CoeffToSlot, EvalMod, SlotToCoeff) on rings of 2^8 and 2^12
+    coefficients: the refreshed ciphertext decrypts to the input within the stated tolerance (1e-3; the error grows
+    with the ring: 5e-7 and 2e-5 here, 5.6e-4 measured on the engine at 2^16) and has at least 5 levels left."""
+    from oracle.bootstrap_oracle import BootstrapOracle
+    for logn, hw in ((8, 16), (12, 64)):
+        o = OracleCKKS(make_params(logn=logn, levels=21, dnum=3, hamming_weight=hw, fresh_level=14), seed=2)
+        o.keygen_secret(); o.keygen_public(); o.keygen_relin()
+        B = BootstrapOracle(o, K=25, degree=47, double_angle=3)
+        rng = np.random.default_rng(0)
+        z = np.exp(2j * np.pi * rng.random(o.n))
+        spent = o.level_down(o.encrypt(z), 1)                       # a ciphertext that has run out of levels
+        out = B.bootstrap(spent)
+        assert out.level >= 5 and out.level >= B.out_level
+        assert np.abs(o.decrypt(out) - z).max() < 1e-3
