@@ -129,6 +129,7 @@ class CapturedCall:
         _capi.check(lib.ckks_graph_create(ptr, C.byref(gid)))
         self.id = gid.value
         self.outputs = None
+        self._last_stream: Optional[int] = None
         _capi.check(lib.ckks_graph_enter(ptr, self.id))
         try:
             self.inputs = [eng.level_down_copy(c) for c in inputs]
@@ -153,14 +154,22 @@ class CapturedCall:
         _capi.check(self._eng._lib.ckks_graph_info(self._eng._ptr, self.id, C.byref(n), C.byref(l), C.byref(b), C.byref(m)))
         return {"nodes": n.value, "launches": l.value, "arena_bytes": b.value, "capture_misses": m.value}
 
+    def _order_after_previous(self, stream: int):
+        # a replay owns the graph's static buffers and scratch: the next use on ANOTHER stream must come after it
+        if self._last_stream is not None and self._last_stream != stream:
+            self._eng.graph_wait(self._last_stream)        # main stream after the old replay; `stream` waits on main
+        self._last_stream = stream
+
     def assign(self, cts: Sequence[Ciphertext], stream: int = 0):
         lib, ptr = self._eng._lib, self._eng._ptr
         if len(cts) != len(self.inputs):
             raise ValueError("wrong number of inputs for this captured call")
+        self._order_after_previous(stream)
         for dst, src in zip(self.inputs, cts):
             _capi.check(lib.ckks_ct_assign(ptr, dst._h, src._h, stream))
 
     def launch(self, stream: int = 0):
+        self._order_after_previous(stream)
         _capi.check(self._eng._lib.ckks_graph_launch(self._eng._ptr, self.id, stream))
         return self.outputs
 
