@@ -42,6 +42,23 @@ def run(levels: int = 20, dnum: int = 3, iters: int = 20) -> dict:
                                    "frac_of_measured_hbm": alg / (ms.value * 1e-3) / 1e9 / peak}
         desilofhe._capi.check(lib.ckks_bench_mul(ptr, level, iters, C.byref(ms)))
         out[f"mul_l{level}"] = {"ms": ms.value, "per_s": 1e3 / ms.value}
+    # element-wise: ct + ct at the top level (reads 2, writes 1 ciphertext of 2 x (levels+1) limbs), enqueued back to back
+    import numpy as np
+    rng = np.random.default_rng(0)
+    a = eng.encrypt(np.exp(2j * np.pi * rng.random(eng.slot_count)), level=levels)
+    b = eng.encrypt(np.exp(2j * np.pi * rng.random(eng.slot_count)), level=levels)
+    for _ in range(5):
+        eng.add(a, b)
+    eng.sync()
+    desilofhe._capi.check(lib.ckks_timer_start(ptr))
+    reps = 200
+    for _ in range(reps):
+        eng.add(a, b)
+    desilofhe._capi.check(lib.ckks_timer_stop_ms(ptr, C.byref(ms)))
+    byts = 3 * 2 * nq * N * 8
+    out["add_ct_ct_top"] = {"ms": ms.value / reps, "alg_MiB": byts / 2 ** 20, "alg_GBps": byts / (ms.value / reps * 1e-3) / 1e9,
+                            "frac_of_measured_hbm": byts / (ms.value / reps * 1e-3) / 1e9 / peak,
+                            "note": "includes the Python/ctypes enqueue of every call"}
     out["launches"] = eng.counters()["launches"]
     return out
 
