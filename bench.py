@@ -3,18 +3,20 @@
 
 Workload (BASELINE.json configs[1]): ONE AES-128 encryption round -- SubBytes (two degree-255 LUT polynomials),
 hard renorm, ShiftRows (masked rotates), MixColumns (GF*2/GF*3 bivariate LUTs, rotations, three XOR4 LUTs with
-renorm, two bootstraps), AddRoundKey (two XOR4 LUTs), hard renorm -- on one ciphertext pair per GPU at N = 2^16,
-every one of the 2048 stride positions carrying an independent block (batched encoder), i.e.
+renorm, two bootstraps), AddRoundKey (two XOR4 LUTs), hard renorm -- on `--pairs` ciphertext pairs per GPU at N = 2^16,
+every one of the 2048 stride positions of a pair carrying an independent block (batched encoder), i.e.
 the reference's `pipeline.py:143-151` flow issued through the host mirror `aes_fhe` onto the `desilofhe` drop-in.
 
   value  : blocks/s = gpus * pairs * 2048 blocks / (10 rounds * seconds per step); a step is the round on `--pairs`
            independent ciphertext pairs per GPU (BASELINE.json configs[4]: "many ciphertexts"), each pair's round
-           recorded once as a CUDA graph (13 000 launches over nested stream lanes) and replayed on its own stream, so
+           recorded once as a CUDA graph (about 8 000 launches over nested stream lanes) and replayed on its own stream, so
            the device overlaps the small kernels of different pairs; states, round-key ciphertexts and all evaluation
            keys resident in HBM when the timed region starts.  `--no-graph` issues the round eagerly (one pair).
-  e2e    : same metric with the step starting from HOST bytes (encode + encrypt: H2D) and ending with decrypted
-           bytes on the host (D2H), through the reference-facing API.
-  s_per_round: latency of ONE pair's round (a single graph replay, nothing else on the device).
+  e2e    : same metric with the step starting from HOST bytes (batched encoder: nibbles H2D, zeta16 lookup + encrypt
+           on the device) and ending with decrypted bytes on the host (nearest-codeword nibbles D2H), through the
+           public API (`BatchedStateEncoder.encode` -> `CapturedRound` -> `FipsDriver.decode`).
+  s_per_round: latency of ONE pair's round (a single graph replay, nothing else on the device); dec_round: the same
+           for one README-order decryption round; rotations_per_s_n16: key-switch micro-benchmark at N = 2^16.
   roofline: the NTT kernels (dominant), algorithmic bytes 2*N*8 per limb transform / CUDA-event time per call.
   cpu_baseline: the oracle port of the same CKKS arithmetic on the host cores, bounded sample.
 
