@@ -213,6 +213,31 @@ def test_captured_round_replays_on_new_inputs(boot_ctx):
     assert np.array_equal(drv.decode(*out2), plain_round(a, rks[3]))
 
 
+def test_captured_decrypt_round_replays_on_new_inputs(boot_ctx):
+    """The README-order decryption round (InvShiftRows, InvSubBytes, AddRoundKey, InvMixColumns with the GF 9/11/13/14 LUTs
+    and two bootstraps) recorded as one graph and replayed with other ciphertext bytes and another round key."""
+    from bench import plain_inv_round
+    from aes_fhe.steps import SHIFTROWS_DEPTH, SUBBYTES_DEPTH
+    which, ctx = boot_ctx
+    pipe = make_pipe(ctx)
+    drv = aes_fhe.FipsDriver(pipe, batched=True)
+    stride = ctx.engine.slot_count // 16
+    rng = np.random.default_rng(23)
+    rks = aes_fhe.expand_aes128_key(np.frombuffer(bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c"), dtype=np.uint8))
+    rk_ct = pipe._prepare_round_keys([drv._perm(rk) for rk in rks])
+    a = rng.integers(0, 256, (stride, 16), dtype=np.uint8)
+    b = rng.integers(0, 256, (stride, 16), dtype=np.uint8)
+    lvl = SHIFTROWS_DEPTH + SUBBYTES_DEPTH
+    ct_a = pipe.encoder.encode(drv._perm(a), level=lvl)
+    rnd = aes_fhe.CapturedRound(pipe, ct_a, rk_ct[9], inverse=True)
+    out = rnd(*pipe.encoder.encode(drv._perm(b), level=lvl), *rk_ct[4])
+    assert np.array_equal(drv.decode(*out), plain_inv_round(b, rks[4]))
+    out = rnd(*ct_a, *rk_ct[9])
+    assert np.array_equal(drv.decode(*out), plain_inv_round(a, rks[9]))
+    assert out[0].level >= lvl                                   # ready for the next round's InvShiftRows + InvSubBytes
+    rnd.close()
+
+
 @pytest.mark.gpu
 def test_config3_config4_with_captured_rounds_gpu():
     """configs[2] and [3] with the nine middle rounds of each direction replayed from ONE recorded round graph
