@@ -287,8 +287,6 @@ Engine::~Engine() {
     bootstrap_teardown();
     for (auto& kv : gkeys) dev::free(kv.second.d, st);
     for (auto& kv : perms) dev::free(kv.second, st);
-    for (auto& kv : modup_tabs) { dev::free((void*)kv.second.hat, st); dev::free((void*)kv.second.hat_s, st); }
-    for (auto& kv : moddown_tabs) { dev::free((void*)kv.second.hat, st); dev::free((void*)kv.second.hat_s, st); }
     for (auto& kv : const_tabs) dev::free(kv.second, st);
     for (auto& kv : modup_dev) dev::free(kv.second, st);
     for (auto& kv : moddown_dev) dev::free(kv.second, st);
@@ -1022,7 +1020,7 @@ BaseConvTable Engine::make_bc_table(const std::vector<int>& src, const std::vect
     }
     T.ns = (int)src.size();
     T.nt = (int)tgt.size();
-    std::vector<u64> hat((size_t)T.ns * T.nt), hat_s((size_t)T.ns * T.nt);
+    std::vector<u64> hat((size_t)T.ns * T.nt);
     for (int i = 0; i < T.ns; i++) {
         T.src[i] = (unsigned char)src[i];
         T.srow[i] = (unsigned char)srow[i];
@@ -1038,17 +1036,10 @@ BaseConvTable Engine::make_bc_table(const std::vector<int>& src, const std::vect
             for (int j = 0; j < T.ns; j++)
                 if (j != i) pr = mulmod_h(pr, mod[src[j]] % qt, qt);
             hat[(size_t)i * T.nt + t] = pr;
-            hat_s[(size_t)i * T.nt + t] = shoup_h(pr, qt);
         }
     }
     for (int t = 0; t < T.nt; t++) { T.tgt[t] = (unsigned char)tgt[t]; T.orow[t] = (unsigned char)orow[t]; }
-    u64* dh = alloc(hat.size());
-    u64* dhs = alloc(hat.size());
-    dev::h2d(dh, hat.data(), hat.size() * sizeof(u64), st);
-    dev::h2d(dhs, hat_s.data(), hat.size() * sizeof(u64), st);
-    dev::sync(st);
-    T.hat = dh;
-    T.hat_s = dhs;
+    T.hat = upload(this, hat, owned);           // exact size, freed with the engine
     if (T.ns <= BC_MMA_MAX_SRC) {
         // tensor-core path (kernels.cu: k_base_convert_mma): the hat matrix cut into bytes, Toeplitz-expanded over the
         // 16 diagonals and stored in mma.m16n8k32 A-fragment order; 2^(8d) mod q_t for the recombination

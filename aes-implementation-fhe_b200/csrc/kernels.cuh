@@ -13,7 +13,7 @@
 struct PolyStride {
     size_t out, a, b;
 };
-// fast basis conversion {src} -> {tgt}; hat/hat_s are device arrays [ns][nt]
+// fast basis conversion {src} -> {tgt}; hat is a device array [ns][nt]
 struct BaseConvTable {
     int ns, nt;
     unsigned char src[BC_MAX_SRC];     // modulus index of source row i
@@ -22,7 +22,6 @@ struct BaseConvTable {
     unsigned char orow[BC_MAX_TGT];    // output row of target t
     u64 hatinv[BC_MAX_SRC], hatinv_s[BC_MAX_SRC];
     const u64* hat;
-    const u64* hat_s;
     // exact mode (ModDown): the overflow count u = round(sum_i y_i / s_i) is computed in fp64 and u * D is taken out,
     // so the conversion returns the CENTRED residue of the input modulo D = prod s_i (spec S5')
     int exact;
