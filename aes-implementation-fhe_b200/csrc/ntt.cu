@@ -31,6 +31,9 @@
 //
 // Algorithmic bytes: 2*N*8 = 1 MiB per limb-NTT at N = 2^16.
 #include "ntt.cuh"
+#ifndef CKKS_EMU
+#include <cooperative_groups.h>
+#endif
 
 namespace {
 
@@ -713,10 +716,145 @@ ntt_inv_passA(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
     else inv_passA_body<LOGR, false>(data, sm, limb, tile, N, mc, T, mod);
 }
 
+#ifndef CKKS_EMU
+// ============================================================================================ forward, ONE kernel per transform
+// EXPERIMENTAL (CKKS_NTT_CLUSTER=1, off by default): both passes in one launch, the limb never leaves the
+// chip between them.  Bit-exact on the B200 against the oracle (keys, raw NTT, homomorphic operations of the GPU parity
+// suite at N = 2^16); NOT yet timed -- the round's GPU budget ended with the run that validated it.  One thread-block cluster of 8 CTAs per limb, 512 threads per CTA.  Pass A: CTA c
+// owns columns 32c..32c+31 of all 256 rows (two radix-16 rounds in shared memory, as fwd_passA_body with 32 columns).
+// Exchange: the thread (column c, row group rr) then holds rows 16rr..16rr+15 of its column in registers; they all belong
+// to CTA rr/2, and go to that CTA's shared memory over the cluster (st.shared::cluster through map_shared_rank), a warp
+// writing 32 consecutive words per row.  Pass B: CTA r owns rows 32r..32r+31 and runs fwd_passB_body's two rounds from
+// shared memory.  The same 68 KB buffer serves both passes: a cluster barrier separates the last pass-A read from the
+// first remote write, a second one the last remote write from the first pass-B read.
+constexpr int kClThreads = 512;
+constexpr int kClData = 32 * 256 + 32 * 16;                     // pass-B tile of 32 rows in the pad16 layout (>= 8192)
+constexpr int kClWords = kClData + 2 * 256;                     // + table entries 1..255 and companions for pass A
+template <bool FP>
+__device__ __forceinline__ void fwd_cluster_body(const u64* __restrict__ src, u64* __restrict__ dst, u64* sm, int limb,
+                                                 int slimb, int tile, size_t N, const ModConst& mc, const NttTables& T,
+                                                 int mod) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const u64 q = mc.q;
+    const u64* W = (FP ? reinterpret_cast<const u64*>(T.fwd_d) : T.fwd) + (size_t)mod * N;
+    const u64* C = (FP ? reinterpret_cast<const u64*>(T.fwd_q) : T.fwd_s) + (size_t)mod * N;
+    const FpMod fm = fp_mod(mc);
+    u64* sd = sm;
+    u64* tw = sm + kClData;
+    u64* tc = tw + 256;
+    const int tid = threadIdx.x;
+    // ---- pass A: 32 columns x 256 rows
+    {
+        const int c = tid % 32, rr = tid / 32;                  // rr = 0..15
+        if (tid < 255) { cp_async8(tw + tid, W + 1 + tid); cp_async8(tc + tid, C + 1 + tid); }
+        const u64* s0 = src + (size_t)slimb * N + tile * 32 + c;
+#pragma unroll
+        for (int k = 0; k < 16; k++) cp_async8(sd + (rr + 16 * k) * 32 + c, s0 + (size_t)(rr + 16 * k) * 256);
+        cp_async_wait_all();
+        __syncthreads();
+        const TwLin<0> t1{tw, tc, 0u};
+        const TwLin<1> t2{tw, tc, (u32)rr};
+        u64 y[16];
+        if (FP) {
+            double x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = ull2d_rn(sd[(rr + 16 * k) * 32 + c]);
+            fwd16_fp(x, t1, fm);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sd[(rr + 16 * k) * 32 + c] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = bits2d(sd[(16 * rr + k) * 32 + c]);
+            fwd16_fp(x, t2, fm);
+#pragma unroll
+            for (int k = 0; k < 16; k++) y[k] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) y[k] = sd[(rr + 16 * k) * 32 + c];
+            fwd16(y, t1, q);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sd[(rr + 16 * k) * 32 + c] = y[k];
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 16; k++) y[k] = sd[(16 * rr + k) * 32 + c];
+            fwd16(y, t2, q);                                    // lazy [0,4q), as between today's two passes
+        }
+        // ---- exchange: rows 16rr..16rr+15 of column tile*32 + c belong to CTA rr/2
+        cluster.sync();                                         // every CTA has finished reading its pass-A tile
+        u64* remote = cluster.map_shared_rank(sd, (unsigned)(rr >> 1));
+        const int col = tile * 32 + c, lrow0 = 16 * (rr & 1);
+#pragma unroll
+        for (int k = 0; k < 16; k++) remote[pad16((lrow0 + k) * 256 + col)] = y[k];
+        cluster.sync();                                         // every remote write has landed
+    }
+    // ---- pass B: 32 rows x 256 columns, from shared memory
+    {
+        const int jj = tid % 16, row = tid / 16;                // row = 0..31
+        const u32 Rn = (u32)(N >> 8);
+        const TwGlobal t1{W, C, Rn + (u32)(tile * 32 + row)};
+        const TwGlobal t2{W, C, 16u * (Rn + (u32)(tile * 32 + row)) + (u32)jj};
+        if (FP) {
+            double x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = bits2d(sd[pad16(row * 256 + jj + 16 * k)]);
+            fwd16_fp(x, t1, fm);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sd[pad16(row * 256 + jj + 16 * k)] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = bits2d(sd[pad16(row * 256 + 16 * jj + k)]);
+            fwd16_fp(x, t2, fm);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sd[pad16(row * 256 + 16 * jj + k)] = canon_fp(x[k], fm.q, fm.qinv);
+        } else {
+            u64 x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = sd[pad16(row * 256 + jj + 16 * k)];
+            fwd16(x, t1, q);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sd[pad16(row * 256 + jj + 16 * k)] = x[k];
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = sd[pad16(row * 256 + 16 * jj + k)];
+            fwd16(x, t2, q);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sd[pad16(row * 256 + 16 * jj + k)] = canon4(x[k], q);
+        }
+        __syncthreads();
+        u64* g = dst + (size_t)limb * N + (size_t)tile * 32 * 256;
+#pragma unroll
+        for (int k = 0; k < 16; k++) g[k * 512 + tid] = sd[pad16(k * 512 + tid)];
+    }
+}
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kClThreads, 2)
+ntt_fwd_cluster(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
+    extern __shared__ __align__(16) u64 sm_cl[];
+    // NOTE: no early exit -- every CTA of a cluster must reach the cluster barriers; a z-slice with fewer items than the
+    // launch's y extent works on a clamped (repeated) item instead, writing the same values twice
+    const int y = (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) ? J.cnt[blockIdx.z] - 1 : blockIdx.y;
+    const int limb = J.rows[blockIdx.z][y], slimb = J.srows[blockIdx.z][y], tile = blockIdx.x;
+    const int mod = J.mods[blockIdx.z][y];
+    const size_t N = (size_t)1 << T.logn;
+    src += blockIdx.z * J.szs;
+    dst += blockIdx.z * J.dzs;
+    const ModConst mc = T.mc[mod];
+    if (use_fp(mc.q)) fwd_cluster_body<true>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod);
+    else fwd_cluster_body<false>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod);
+}
+#endif
+
 }  // namespace
 
+bool g_ntt_cluster = false;       // CKKS_NTT_CLUSTER=1 (engine constructor): forward transforms at N = 2^16 in one kernel
 void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st) {
     if (J.n == 0 || J.nz == 0) return;
+#ifndef CKKS_EMU
+    if (g_ntt_cluster && T.logn == 16) {
+        LAUNCH_DYN(ntt_fwd_cluster, dim3(8, J.n, J.nz), dim3(kClThreads), kClWords * sizeof(u64), st, src, dst, J, T);
+        return;
+    }
+#endif
     const unsigned R = 1u << (T.logn - 8);
     dim3 gridB(R / 16, J.n, J.nz);
     if (T.logn == 16) {
