@@ -730,10 +730,11 @@ ntt_inv_passA(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
 constexpr int kClThreads = 512;
 constexpr int kClData = 32 * 256 + 32 * 16;                     // pass-B tile of 32 rows in the pad16 layout (>= 8192)
 constexpr int kClWords = kClData + 2 * 256;                     // + table entries 1..255 and companions for pass A
-template <bool FP>
+template <bool FP, bool PRO, bool EP>
 __device__ __forceinline__ void fwd_cluster_body(const u64* __restrict__ src, u64* __restrict__ dst, u64* sm, int limb,
                                                  int slimb, int tile, size_t N, const ModConst& mc, const NttTables& T,
-                                                 int mod) {
+                                                 int mod, u64 ql, const u64* __restrict__ ep_a, u64* __restrict__ ep_out,
+                                                 u64 sv, u64 svs) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const u64 q = mc.q;
@@ -759,7 +760,10 @@ __device__ __forceinline__ void fwd_cluster_body(const u64* __restrict__ src, u6
         if (FP) {
             double x[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) x[k] = ull2d_rn(sd[(rr + 16 * k) * 32 + c]);
+            for (int k = 0; k < 16; k++) {
+                const u64 v = sd[(rr + 16 * k) * 32 + c];
+                x[k] = ull2d_rn(PRO ? pro_lift(v, ql, mc) : v);
+            }
             fwd16_fp(x, t1, fm);
 #pragma unroll
             for (int k = 0; k < 16; k++) sd[(rr + 16 * k) * 32 + c] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
@@ -771,7 +775,10 @@ __device__ __forceinline__ void fwd_cluster_body(const u64* __restrict__ src, u6
             for (int k = 0; k < 16; k++) y[k] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
         } else {
 #pragma unroll
-            for (int k = 0; k < 16; k++) y[k] = sd[(rr + 16 * k) * 32 + c];
+            for (int k = 0; k < 16; k++) {
+                const u64 v = sd[(rr + 16 * k) * 32 + c];
+                y[k] = PRO ? pro_lift(v, ql, mc) : v;
+            }
             fwd16(y, t1, q);
 #pragma unroll
             for (int k = 0; k < 16; k++) sd[(rr + 16 * k) * 32 + c] = y[k];
@@ -822,31 +829,187 @@ __device__ __forceinline__ void fwd_cluster_body(const u64* __restrict__ src, u6
             for (int k = 0; k < 16; k++) sd[pad16(row * 256 + 16 * jj + k)] = canon4(x[k], q);
         }
         __syncthreads();
-        u64* g = dst + (size_t)limb * N + (size_t)tile * 32 * 256;
+        const size_t off = (size_t)limb * N + (size_t)tile * 32 * 256;
+        if (EP) {                                               // (a - NTT(x)) * s, as ntt_fwd_passB_ep
 #pragma unroll
-        for (int k = 0; k < 16; k++) g[k * 512 + tid] = sd[pad16(k * 512 + tid)];
+            for (int k = 0; k < 16; k++)
+                ep_out[off + k * 512 + tid] =
+                    shoup_mul(sub_mod(ep_a[off + k * 512 + tid], sd[pad16(k * 512 + tid)], q), sv, svs, q);
+        } else {
+            u64* g = dst + off;
+#pragma unroll
+            for (int k = 0; k < 16; k++) g[k * 512 + tid] = sd[pad16(k * 512 + tid)];
+        }
     }
 }
+// y index of a CTA: no early exit -- every CTA of a cluster must reach the cluster barriers; a z-slice with fewer items than
+// the launch's y extent works on a clamped (repeated) item instead, writing the same values twice
+__device__ __forceinline__ int cluster_item(const NttJob& J) {
+    return (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) ? J.cnt[blockIdx.z] - 1 : (int)blockIdx.y;
+}
+// forward transform with the rescale-lift prologue and / or the (a - NTT(x)) * s epilogue (NttFuse), one kernel
+template <bool PRO, bool EP>
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kClThreads, 2)
-ntt_fwd_cluster(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
+ntt_fwd_cluster_fused(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T,
+                      const GRID_CONST NttFuse F) {
     extern __shared__ __align__(16) u64 sm_cl[];
-    // NOTE: no early exit -- every CTA of a cluster must reach the cluster barriers; a z-slice with fewer items than the
-    // launch's y extent works on a clamped (repeated) item instead, writing the same values twice
-    const int y = (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) ? J.cnt[blockIdx.z] - 1 : blockIdx.y;
+    const int y = cluster_item(J);
     const int limb = J.rows[blockIdx.z][y], slimb = J.srows[blockIdx.z][y], tile = blockIdx.x;
     const int mod = J.mods[blockIdx.z][y];
     const size_t N = (size_t)1 << T.logn;
     src += blockIdx.z * J.szs;
     dst += blockIdx.z * J.dzs;
     const ModConst mc = T.mc[mod];
-    if (use_fp(mc.q)) fwd_cluster_body<true>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod);
-    else fwd_cluster_body<false>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod);
+    const u64 ql = PRO ? T.mc[F.pro_mod].q : 0;
+    const u64* ep_a = EP ? F.ep_a + blockIdx.z * F.ep_azs : nullptr;
+    u64* ep_out = EP ? F.ep_out + blockIdx.z * F.ep_ozs : nullptr;
+    const u64 sv = EP ? F.s.v[y] : 0, svs = EP ? F.s.vs[y] : 0;
+    if (use_fp(mc.q)) fwd_cluster_body<true, PRO, EP>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, ql, ep_a, ep_out, sv, svs);
+    else fwd_cluster_body<false, PRO, EP>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, ql, ep_a, ep_out, sv, svs);
+}
+
+// ============================================================================================ inverse, ONE kernel per transform
+// (NOT yet run on hardware.)  The forward structure backwards: CTA r transforms rows 32r..32r+31 (pass B^-1, two radix-16
+// rounds from shared memory), the thread (row, jj) then holds columns jj + 16k of its row, which belong to CTA k/2; they
+// cross the cluster into that CTA's [256 rows][32 columns] tile, and pass A^-1 finishes with the 1/N scaling.
+template <bool FP, bool MUL>
+__device__ __forceinline__ void inv_cluster_body(const u64* __restrict__ src, const u64* __restrict__ src2,
+                                                 u64* __restrict__ dst, u64* sm, int limb, int slimb, int tile, size_t N,
+                                                 const ModConst& mc, const NttTables& T, int mod) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const u64 q = mc.q;
+    const u64* W = (FP ? reinterpret_cast<const u64*>(T.inv_d) : T.inv) + (size_t)mod * N;
+    const u64* C = (FP ? reinterpret_cast<const u64*>(T.inv_q) : T.inv_s) + (size_t)mod * N;
+    const FpMod fm = fp_mod(mc);
+    u64* sd = sm;
+    u64* tw = sm + kClData;
+    u64* tc = tw + 256;
+    const int tid = threadIdx.x;
+    u64 y[16];
+    {
+        // ---- pass B^-1: 32 rows x 256 columns
+        const size_t off = (size_t)slimb * N + (size_t)tile * 32 * 256;
+        if (tid < 255) { cp_async8(tw + tid, W + 1 + tid); cp_async8(tc + tid, C + 1 + tid); }
+        if (MUL) {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                sd[pad16(k * 512 + tid)] = barrett_mul(src[off + k * 512 + tid], src2[off + k * 512 + tid], mc);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) cp_async8(sd + pad16(k * 512 + tid), src + off + k * 512 + tid);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        const int jj = tid % 16, row = tid / 16;
+        const u32 Rn = (u32)(N >> 8);
+        const TwGlobal t2{W, C, 16u * (Rn + (u32)(tile * 32 + row)) + (u32)jj};
+        const TwGlobal t1{W, C, Rn + (u32)(tile * 32 + row)};
+        if (FP) {
+            double x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = ull2d_rn(sd[pad16(row * 256 + 16 * jj + k)]);
+            inv16_fp<false>(x, t2, fm);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sd[pad16(row * 256 + 16 * jj + k)] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = bits2d(sd[pad16(row * 256 + jj + 16 * k)]);
+            inv16_fp<false>(x, t1, fm);
+#pragma unroll
+            for (int k = 0; k < 16; k++) y[k] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) y[k] = sd[pad16(row * 256 + 16 * jj + k)];
+            inv16<false>(y, t2, q, 0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sd[pad16(row * 256 + 16 * jj + k)] = y[k];
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 16; k++) y[k] = sd[pad16(row * 256 + jj + 16 * k)];
+            inv16<false>(y, t1, q, 0, 0, 0, 0);                 // lazy [0,2q), as between today's two passes
+        }
+        // ---- exchange: column jj + 16k of global row 32 tile + row belongs to CTA k/2, local column jj + 16 (k & 1)
+        cluster.sync();                                         // every CTA has finished reading its pass-B tile
+        const int grow = tile * 32 + row;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            u64* remote = cluster.map_shared_rank(sd, (unsigned)(k >> 1));
+            remote[grow * 32 + jj + 16 * (k & 1)] = y[k];
+        }
+        cluster.sync();                                         // every remote write has landed
+    }
+    {
+        // ---- pass A^-1: 32 columns x 256 rows, 1/N folded into the last stage
+        const int c = tid % 32, rr = tid / 32;
+        const TwLin<1> t2{tw, tc, (u32)rr};
+        const TwLin<0> t1{tw, tc, 0u};
+        u64* d0 = dst + (size_t)limb * N + tile * 32 + c;
+        if (FP) {
+            double x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = bits2d(sd[(16 * rr + k) * 32 + c]);
+            inv16_fp<false>(x, t2, fm);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sd[(16 * rr + k) * 32 + c] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = bits2d(sd[(rr + 16 * k) * 32 + c]);
+            inv16_fp<true>(x, t1, fm);
+#pragma unroll
+            for (int k = 0; k < 16; k++) d0[(size_t)(rr + 16 * k) * 256] = canon_fp(x[k], fm.q, fm.qinv);
+        } else {
+            u64 x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = sd[(16 * rr + k) * 32 + c];
+            inv16<false>(x, t2, q, 0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sd[(16 * rr + k) * 32 + c] = x[k];
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = sd[(rr + 16 * k) * 32 + c];
+            inv16<true>(x, t1, q, mc.ninv, mc.ninv_s, mc.w1n, mc.w1n_s);
+#pragma unroll
+            for (int k = 0; k < 16; k++) d0[(size_t)(rr + 16 * k) * 256] = canon2(x[k], q);
+        }
+    }
+}
+template <bool MUL>
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kClThreads, 2)
+ntt_inv_cluster(const u64* __restrict__ src, const u64* __restrict__ src2, u64* __restrict__ dst, const GRID_CONST NttJob J,
+                NttTables T) {
+    extern __shared__ __align__(16) u64 sm_cl[];
+    const int y = cluster_item(J);
+    const int limb = J.rows[blockIdx.z][y], slimb = J.srows[blockIdx.z][y], tile = blockIdx.x;
+    const int mod = J.mods[blockIdx.z][y];
+    const size_t N = (size_t)1 << T.logn;
+    src += blockIdx.z * J.szs;
+    if (MUL) src2 += blockIdx.z * J.szs;
+    dst += blockIdx.z * J.dzs;
+    const ModConst mc = T.mc[mod];
+    if (use_fp(mc.q)) inv_cluster_body<true, MUL>(src, src2, dst, sm_cl, limb, slimb, tile, N, mc, T, mod);
+    else inv_cluster_body<false, MUL>(src, src2, dst, sm_cl, limb, slimb, tile, N, mc, T, mod);
+}
+
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kClThreads, 2)
+ntt_fwd_cluster(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
+    extern __shared__ __align__(16) u64 sm_cl[];
+    const int y = cluster_item(J);
+    const int limb = J.rows[blockIdx.z][y], slimb = J.srows[blockIdx.z][y], tile = blockIdx.x;
+    const int mod = J.mods[blockIdx.z][y];
+    const size_t N = (size_t)1 << T.logn;
+    src += blockIdx.z * J.szs;
+    dst += blockIdx.z * J.dzs;
+    const ModConst mc = T.mc[mod];
+    if (use_fp(mc.q)) fwd_cluster_body<true, false, false>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, 0, nullptr, nullptr, 0, 0);
+    else fwd_cluster_body<false, false, false>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, 0, nullptr, nullptr, 0, 0);
 }
 #endif
 
 }  // namespace
 
 bool g_ntt_cluster = false;       // CKKS_NTT_CLUSTER=1 (engine constructor): forward transforms at N = 2^16 in one kernel
+bool g_ntt_cluster_all = false;   // CKKS_NTT_CLUSTER=2: also the fused forward variants and the inverse (not yet run on hardware)
 void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st) {
     if (J.n == 0 || J.nz == 0) return;
 #ifndef CKKS_EMU
@@ -871,6 +1034,18 @@ void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, 
 
 void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J, const NttTables& T, const NttFuse& F, dev_stream st) {
     if (J.n == 0 || J.nz == 0) return;
+#ifndef CKKS_EMU
+    if (g_ntt_cluster_all && T.logn == 16) {
+        const dim3 g(8, J.n, J.nz), b(kClThreads);
+        const size_t smem = kClWords * sizeof(u64);
+        const bool pro = F.pro_mod >= 0, ep = F.ep_out != nullptr;
+        if (pro && ep) LAUNCH_DYN((ntt_fwd_cluster_fused<true, true>), g, b, smem, st, src, dst, J, T, F);
+        else if (pro) LAUNCH_DYN((ntt_fwd_cluster_fused<true, false>), g, b, smem, st, src, dst, J, T, F);
+        else if (ep) LAUNCH_DYN((ntt_fwd_cluster_fused<false, true>), g, b, smem, st, src, dst, J, T, F);
+        else LAUNCH_DYN(ntt_fwd_cluster, g, b, smem, st, src, dst, J, T);
+        return;
+    }
+#endif
     const unsigned R = 1u << (T.logn - 8);
     dim3 gridB(R / 16, J.n, J.nz);
     if (T.logn != 16 && T.logn != 12) throw std::runtime_error("ntt: only N = 2^16 and N = 2^12 are built");
@@ -888,6 +1063,15 @@ void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J, const NttTable
 
 void ntt_inverse(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st, const u64* src2) {
     if (J.n == 0 || J.nz == 0) return;
+#ifndef CKKS_EMU
+    if (g_ntt_cluster_all && T.logn == 16) {
+        const dim3 g(8, J.n, J.nz), b(kClThreads);
+        const size_t smem = kClWords * sizeof(u64);
+        if (src2) LAUNCH_DYN(ntt_inv_cluster<true>, g, b, smem, st, src, src2, dst, J, T);
+        else LAUNCH_DYN(ntt_inv_cluster<false>, g, b, smem, st, src, src2, dst, J, T);
+        return;
+    }
+#endif
     const unsigned R = 1u << (T.logn - 8);
     dim3 gridB(R / 16, J.n, J.nz);
     if (src2) LAUNCH(ntt_inv_passB_mul, gridB, dim3(kThreads), st, src, src2, dst, J, T);

@@ -50,4 +50,5 @@ void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, 
 void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J, const NttTables& T, const NttFuse& F, dev_stream st);
 // src2 != null: the inverse transform of the row-wise product src * src2 (the d2 of a ct x ct, never stored)
 void ntt_inverse(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st, const u64* src2 = nullptr);
-extern bool g_ntt_cluster;   // experimental single-kernel forward transform (ntt.cu)
+extern bool g_ntt_cluster;       // experimental single-kernel forward transform (ntt.cu)
+extern bool g_ntt_cluster_all;   // ... plus its fused variants and the inverse (not yet run on hardware)
