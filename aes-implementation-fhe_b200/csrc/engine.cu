@@ -174,9 +174,10 @@ Engine::Engine(const Params& P) : prm(P) {
     if (const char* v = getenv("CKKS_NTT_FUSE")) fuse_ntt = atoi(v) != 0;
     if (const char* v = getenv("CKKS_TENSOR_FUSE")) fuse_tensor = atoi(v) != 0;
     if (const char* v = getenv("CKKS_BC_MMA")) bc_mma = atoi(v) != 0;
-    if (const char* v = getenv("CKKS_NTT_CLUSTER")) {                                    // experimental
-        g_ntt_cluster = atoi(v) >= 1;
-        g_ntt_cluster_all = atoi(v) >= 2;
+    {                                                                                    // experimental
+        const char* v = getenv("CKKS_NTT_CLUSTER");        // process-wide switch, re-read by every engine (unset = off)
+        g_ntt_cluster = v && atoi(v) >= 1;
+        g_ntt_cluster_all = v && atoi(v) >= 2;
     }
     if (const char* v = getenv("CKKS_CHEB_DEGREE")) prm.boot.cheb_degree = atoi(v);      // tuning / A-B runs only
     mod = prm.q;

@@ -350,3 +350,19 @@ def test_edge_cases_of_the_reference_surface(pair):
     real = eng.decrypt(eng.encrypt(np.linspace(-1.0, 1.0, n)))                               # float64 input
     assert np.abs(real - np.linspace(-1.0, 1.0, n)).max() < 1e-8
     assert eng.decrypt(eng.encrypt(np.zeros(0))).shape == (n,)                                # empty input = all zeros
+
+
+@pytest.mark.gpu
+def test_cluster_forward_ntt_bit_exact():
+    """The experimental single-kernel forward NTT (8-CTA cluster, DSMEM exchange; CKKS_NTT_CLUSTER=1, off by default):
+    keys, raw transforms and homomorphic operations at N = 2^16 must stay bit-identical to the oracle with it switched on."""
+    import os
+    os.environ["CKKS_NTT_CLUSTER"] = "1"
+    try:
+        p = Pair("cuda", 16, 5)
+        test_keys_bit_exact(p)
+        test_raw_ntt_roundtrip_and_parity(p)
+        test_homomorphic_ops_bit_exact(p)
+    finally:
+        os.environ.pop("CKKS_NTT_CLUSTER", None)
+        Pair("cuda", 12, 6)                 # a new engine re-reads the (now unset) switch: off again for later tests
