@@ -278,7 +278,12 @@ class BatchedStateEncoder:
 
     encode((B,16)) places byte i of block b in slot i*stride+b (B <= stride, the rest is
     padded with the zero byte codeword); a (16,) input (a round key) is broadcast to every b;
-    decode returns (stride,16)."""
+    decode returns (stride,16).
+
+    A 3-D input (P,B,16) -- P independent ciphertext pairs (BASELINE.json configs[4]: "many ciphertexts") -- becomes ONE
+    batched pair of handles on the B200 engine (`Ciphertext.batch` = P): every step of the pipeline then runs all P
+    pairs through one set of kernel launches, and decode returns (P,stride,16).  Round keys stay unbatched and are
+    broadcast by the engine."""
 
     def __init__(self, ctx: EngineContext):
         self.ctx = ctx
@@ -287,6 +292,19 @@ class BatchedStateEncoder:
 
     def encode(self, state: np.ndarray, level=None) -> Pair:
         st = np.asarray(state, dtype=np.uint8)
+        if st.ndim == 3:                                       # (P, B, 16): P pairs in one batched handle pair
+            assert st.shape[2] == 16 and st.shape[1] <= self.stride
+            full = np.zeros((st.shape[0], self.stride, 16), dtype=np.uint8)
+            full[:, :st.shape[1]] = st
+            flat = lambda a: np.ascontiguousarray(a.transpose(0, 2, 1)).reshape(st.shape[0], -1)
+            if getattr(self.ctx, "device_codec", False):
+                return (self.ctx.encrypt_nibbles(flat((full >> 4) & 0xF), level=level),
+                        self.ctx.encrypt_nibbles(flat(full & 0xF), level=level))
+            hi, lo = to_zeta(flat((full >> 4) & 0xF), 16), to_zeta(flat(full & 0xF), 16)
+            if level is None:
+                return self.ctx.encrypt(hi.astype(np.complex128)), self.ctx.encrypt(lo.astype(np.complex128))
+            return (self.ctx.encrypt(hi.astype(np.complex128), level=level),
+                    self.ctx.encrypt(lo.astype(np.complex128), level=level))
         if st.ndim == 1:
             st = np.broadcast_to(st, (self.stride, 16))
         assert st.shape[1] == 16 and st.shape[0] <= self.stride
@@ -311,12 +329,14 @@ class BatchedStateEncoder:
 
     def decode(self, ct_hi, ct_lo) -> np.ndarray:
         if getattr(self.ctx, "device_codec", False):
-            hi = self.ctx.decrypt_nibbles(ct_hi).reshape(16, self.stride).T
-            lo = self.ctx.decrypt_nibbles(ct_lo).reshape(16, self.stride).T
+            hi, lo = self.ctx.decrypt_nibbles(ct_hi), self.ctx.decrypt_nibbles(ct_lo)
         else:
-            hi = from_zeta(self.ctx.decrypt(ct_hi), 16).reshape(16, self.stride).T
-            lo = from_zeta(self.ctx.decrypt(ct_lo), 16).reshape(16, self.stride).T
-        return ((hi.astype(np.uint8) << 4) | lo).astype(np.uint8)
+            hi, lo = from_zeta(self.ctx.decrypt(ct_hi), 16), from_zeta(self.ctx.decrypt(ct_lo), 16)
+        if hi.ndim == 2:                                       # batched handles: (P, slots) -> (P, stride, 16)
+            shape = lambda a: a.reshape(a.shape[0], 16, self.stride).transpose(0, 2, 1)
+        else:
+            shape = lambda a: a.reshape(16, self.stride).T
+        return ((shape(hi).astype(np.uint8) << 4) | shape(lo)).astype(np.uint8)
 
 
 class CapturedRound:

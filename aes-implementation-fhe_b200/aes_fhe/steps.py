@@ -2,7 +2,7 @@
 
 Host-side mirror of the reference's L2 step classes.  Each class keeps the reference's
 name, constructor and call signature and issues the *same sequence of engine calls*
-through `EngineContext` (verified op-for-op by `tests/test_trace_equivalence.py` against
+through `EngineContext` (verified op-for-op by `tests/test_aes_mirror.py` against
 the reference's own files on a tracing backend), so that the workload measured on the
 B200 engine is the reference's workload:
 

@@ -201,8 +201,12 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
     std::vector<Ct*> rot = E.rotate_hoisted(a, steps);
     std::map<int, Ct*> baby;
     for (size_t t = 0; t < rot.size(); t++) baby[P.babies[t]] = A.keep(rot[t]);
+    const int nb = a->nb;                              // batch items: every buffer below is [nb][2][..], uniform strides
     const size_t ps = (size_t)(P.level + 1) * E.N();
     LimbList ll = E.limb_list(E.mods_q(P.level));
+    const PolyStride U{ps, ps, ps};                    // whole ciphertext buffers: the batch folds into 2 * nb polynomials
+    PolyStride U0{0, 0, 0};                            // polynomial 0 of every batch item
+    U0.nb = nb; U0.bout = U0.ba = U0.bb = 2 * ps;
     // Giant steps with ONE ModDown for the whole matrix ("double hoisting"): every rotated inner sum contributes
     //   sigma_g(c0) in Q_l   and   <ModUp(sigma_g(c1)), rtk_g> in Q_l u P,
     // the Q_l u P parts are accumulated and divided by P once; the un-rotated row (giant 0) is added as it is.
@@ -226,7 +230,7 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
             if (nl > 1) E.set_lane((int)(ri % nl));
             // inner = sum_i diag_i (.) baby_i in one fused multiply-accumulate, un-rescaled (scale S_l^2): one rescale
             // per matrix at the end
-            u64* inner = E.alloc(2 * ps);
+            u64* inner = E.alloc((size_t)nb * 2 * ps);
             for (size_t off = 0; off < R.terms.size(); off += 16) {
                 std::vector<const Ct*> xs;
                 std::vector<const Pt*> ps_;
@@ -234,32 +238,32 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
                     xs.push_back(baby[R.terms[t].i]);
                     ps_.push_back(R.terms[t].pt);
                 }
-                if (off == 0) E.diag_mac(inner, xs, ps_, P.level);
+                if (off == 0) E.diag_mac(inner, xs, ps_, P.level, nb);
                 else {
-                    if (!S.tmp) S.tmp = E.alloc(2 * ps);
-                    E.diag_mac(S.tmp, xs, ps_, P.level);
-                    launch_add(E.ks, inner, inner, S.tmp, ll, 2, PolyStride{ps, ps, ps}, E.st);
+                    if (!S.tmp) S.tmp = E.alloc((size_t)nb * 2 * ps);
+                    E.diag_mac(S.tmp, xs, ps_, P.level, nb);
+                    launch_add(E.ks, inner, inner, S.tmp, ll, 2 * nb, U, E.st);
                 }
             }
             if (R.giant % (long)E.slots() == 0) {
                 if (!S.sum) { S.sum = inner; inner = nullptr; }
-                else launch_add(E.ks, S.sum, S.sum, inner, ll, 2, PolyStride{ps, ps, ps}, E.st);
+                else launch_add(E.ks, S.sum, S.sum, inner, ll, 2 * nb, U, E.st);
             } else {
                 const u64 g = E.galois_for_rotation(-R.giant);
                 EvalKey* key = E.galois_key(g);
-                if (!S.rbuf) S.rbuf = E.alloc(2 * ps);
-                E.automorph(S.rbuf, inner, P.level + 1, 2, g);                  // (sigma(c0), sigma(c1))
-                Decomp D = E.decompose(S.rbuf + ps, P.level);
+                if (!S.rbuf) S.rbuf = E.alloc((size_t)nb * 2 * ps);
+                E.automorph(S.rbuf, inner, P.level + 1, 2 * nb, g);             // (sigma(c0), sigma(c1))
+                Decomp D = E.decompose(S.rbuf + ps, P.level, nullptr, nb, 2 * ps, 0);
                 if (!S.accqp) {
-                    S.accqp = E.alloc((size_t)2 * rows * n);
+                    S.accqp = E.alloc((size_t)nb * 2 * rows * n);
                     E.ks_inner(D, key, nullptr, S.accqp, nullptr, false);
                 } else E.ks_inner(D, key, nullptr, S.accqp, nullptr, true);
                 E.release(D.ext);
                 if (!S.sum) {
-                    S.sum = E.alloc(2 * ps);
-                    dev::d2d(S.sum, S.rbuf, ps * sizeof(u64), E.st);
-                    dev::zero(S.sum + ps, ps * sizeof(u64), E.st);
-                } else launch_add(E.ks, S.sum, S.sum, S.rbuf, ll, 1, PolyStride{0, 0, 0}, E.st);
+                    S.sum = E.alloc((size_t)nb * 2 * ps);
+                    dev::zero(S.sum, (size_t)nb * 2 * ps * sizeof(u64), E.st);
+                }
+                launch_add(E.ks, S.sum, S.sum, S.rbuf, ll, 1, U0, E.st);
             }
             if (inner) E.release(inner);
         }
@@ -272,7 +276,7 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
     if (nl > 1) E.join();
     // combine the lanes' accumulators on the parent stream
     u64* accqp = nullptr;
-    Ct* sum = A.keep(E.new_ct(2, P.level));
+    Ct* sum = A.keep(E.new_ct(2, P.level, nb));
     bool sum_init = false;
     LimbList llqp = E.limb_list(E.mods_qp(P.level));
     const size_t psqp = (size_t)rows * n;
@@ -280,21 +284,21 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
         if (LA[l].accqp) {
             if (!accqp) accqp = LA[l].accqp;
             else {
-                launch_add(E.ks, accqp, accqp, LA[l].accqp, llqp, 2, PolyStride{psqp, psqp, psqp}, E.st);
+                launch_add(E.ks, accqp, accqp, LA[l].accqp, llqp, 2 * nb, PolyStride{psqp, psqp, psqp}, E.st);
                 E.release(LA[l].accqp);
             }
         }
         if (LA[l].sum) {
-            if (!sum_init) { dev::d2d(sum->d, LA[l].sum, 2 * ps * sizeof(u64), E.st); sum_init = true; }
-            else launch_add(E.ks, sum->d, sum->d, LA[l].sum, ll, 2, PolyStride{ps, ps, ps}, E.st);
+            if (!sum_init) { dev::d2d(sum->d, LA[l].sum, (size_t)nb * 2 * ps * sizeof(u64), E.st); sum_init = true; }
+            else launch_add(E.ks, sum->d, sum->d, LA[l].sum, ll, 2 * nb, U, E.st);
             E.release(LA[l].sum);
         }
     }
     if (accqp) {
-        u64* down = E.alloc(2 * ps);
-        E.ks_moddown(accqp, P.level, 0, down);
-        if (sum_init) launch_add(E.ks, sum->d, sum->d, down, ll, 2, PolyStride{ps, ps, ps}, E.st);
-        else dev::d2d(sum->d, down, 2 * ps * sizeof(u64), E.st);
+        u64* down = E.alloc((size_t)nb * 2 * ps);
+        E.ks_moddown(accqp, P.level, 0, down, nb);
+        if (sum_init) launch_add(E.ks, sum->d, sum->d, down, ll, 2 * nb, U, E.st);
+        else dev::d2d(sum->d, down, (size_t)nb * 2 * ps * sizeof(u64), E.st);
         E.release(down);
         E.release(accqp);
     }
@@ -434,19 +438,20 @@ Ct* Engine::mod_raise(Ct* a) {
     if (a->npoly != 2) throw PolyCountError("bootstrap: ciphertext should have 2 polynomials");
     Ct* low = level_down(a, 0);
     const size_t n = N();
-    const int top = L();
-    u64* coef = alloc(2 * n);
+    const int top = L(), nb = a->nb;
+    u64* coef = alloc((size_t)nb * 2 * n);
     {
         NttJob J;
         memset(&J, 0, sizeof(J));
         J.n = 1; J.nz = 2;
         J.szs = n; J.dzs = n;
-        run_ntt(low->d, coef, J, true, 2);
+        J.nb = nb; J.sbs = J.dbs = 2 * n;
+        run_ntt(low->d, coef, J, true, 2L * nb);
     }
-    Ct* r = new_ct(2, top);
+    Ct* r = new_ct(2, top, nb);
     std::vector<int> idx = mods_q(top);
-    launch_center_lift(ks, r->d, coef, limb_list(idx), 0, 2, PolyStride{(size_t)(top + 1) * n, n, 0}, st);
-    ntt_rows(r->d, idx, idx, false, 2, (size_t)(top + 1) * n);
+    launch_center_lift(ks, r->d, coef, limb_list(idx), 0, 2 * nb, PolyStride{(size_t)(top + 1) * n, n, 0}, st);
+    ntt_rows(r->d, idx, idx, false, 2, (size_t)(top + 1) * n, nb, (size_t)2 * (top + 1) * n);
     release(coef);
     return r;
 }
@@ -474,7 +479,7 @@ Ct* Engine::bootstrap(Ct* a) {
     if (t->level > B.stc[0].level) t = level_down(t, B.stc[0].level);     // memoised on (and owned by) its parent
     for (const LinearPlan& P : B.stc) t = apply_linear(*this, A, t, P);
     Ct* out = copy(t);
-    n_boot++;
+    n_boot += a->nb;
     return out;
 }
 

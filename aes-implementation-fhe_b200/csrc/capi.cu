@@ -159,6 +159,23 @@ int ckks_decrypt_zeta16(ckks_engine* e, const ckks_ct* ct, uint8_t* nibbles_out)
 int ckks_snap_zeta16(ckks_engine* e, const ckks_ct* ct, int level, int stride, ckks_ct** out) {
     return guard([&] { *out = H(e->E->snap_zeta16(C(ct), level, stride)); });
 }
+int ckks_ct_batch(const ckks_ct* ct) { return C(ct)->nb; }
+int ckks_encrypt_batch(ckks_engine* e, const double* z, int nb, int level, ckks_ct** out) {
+    return guard([&] { *out = H(e->E->encrypt(z, level, nb)); });
+}
+int ckks_encrypt_zeta16_batch(ckks_engine* e, const uint8_t* nibbles, int nb, int level, ckks_ct** out) {
+    return guard([&] { *out = H(e->E->encrypt_zeta16(nibbles, level, nb)); });
+}
+int ckks_ct_stack(ckks_engine* e, ckks_ct* const* items, int n, ckks_ct** out) {
+    return guard([&] {
+        std::vector<Ct*> v(n);
+        for (int i = 0; i < n; i++) v[i] = C(items[i]);
+        *out = H(e->E->stack(v));
+    });
+}
+int ckks_ct_item(ckks_engine* e, const ckks_ct* ct, int index, ckks_ct** out) {
+    return guard([&] { *out = H(e->E->item(C(ct), index)); });
+}
 void ckks_ct_free(ckks_engine* e, ckks_ct* ct) { e->E->free_ct(C(ct)); }
 void ckks_pt_free(ckks_engine* e, ckks_pt* pt) { e->E->free_pt(reinterpret_cast<Pt*>(pt)); }
 int ckks_ct_level(const ckks_ct* ct) { return C(ct)->level; }
@@ -252,7 +269,7 @@ int ckks_arena_stats(const ckks_engine* e, long* driver_allocs, size_t* arena_by
 int ckks_ct_export(ckks_engine* e, const ckks_ct* ct, uint64_t* out) {
     return guard([&] {
         const Ct* c = C(ct);
-        dev::d2h(out, c->d, (size_t)c->npoly * (c->level + 1) * e->E->N() * sizeof(u64), e->E->st);
+        dev::d2h(out, c->d, (size_t)c->nb * c->npoly * (c->level + 1) * e->E->N() * sizeof(u64), e->E->st);
         e->E->sync();
     });
 }
@@ -260,6 +277,14 @@ int ckks_ct_import(ckks_engine* e, int npoly, int level, const uint64_t* data, c
     return guard([&] {
         Ct* c = e->E->new_ct(npoly, level);
         dev::h2d(c->d, data, (size_t)npoly * (level + 1) * e->E->N() * sizeof(u64), e->E->st);
+        e->E->sync();
+        *out = H(c);
+    });
+}
+int ckks_ct_import_batch(ckks_engine* e, int nb, int npoly, int level, const uint64_t* data, ckks_ct** out) {
+    return guard([&] {
+        Ct* c = e->E->new_ct(npoly, level, nb);
+        dev::h2d(c->d, data, (size_t)nb * npoly * (level + 1) * e->E->N() * sizeof(u64), e->E->st);
         e->E->sync();
         *out = H(c);
     });
@@ -392,12 +417,37 @@ int ckks_bench_ntt(ckks_engine* e, int nlimbs, int batches, int inverse, int ite
         E.release(d);
     });
 }
-static Ct* random_ct(Engine& E, int level, u64 tag) {
-    Ct* c = E.new_ct(2, level);
+static Ct* random_ct(Engine& E, int level, u64 tag, int nb = 1) {
+    Ct* c = E.new_ct(2, level, nb);
     LimbList ll = E.limb_list(E.mods_q(level));
-    launch_sample_uniform(E.ks, c->d, ll, 99, tag, E.st);
-    launch_sample_uniform(E.ks, c->d + (size_t)(level + 1) * E.N(), ll, 99, tag + 1, E.st);
+    const size_t ps = (size_t)(level + 1) * E.N();
+    for (int k = 0; k < 2 * nb; k++) launch_sample_uniform(E.ks, c->d + k * ps, ll, 99, tag + k, E.st);
     return c;
+}
+int ckks_bench_rotate_batch(ckks_engine* e, int level, int nb, int iters, float* ms_out) {
+    return guard([&] {
+        Engine& E = *e->E;
+        Ct* c = random_ct(E, level, 10, nb);
+        const long step = (long)E.slots() / 4;
+        for (int w = 0; w < 3; w++) E.free_ct(E.rotate(c, step));
+        e->timer.start(E.st);
+        for (int it = 0; it < iters; it++) E.free_ct(E.rotate(c, step));
+        *ms_out = e->timer.stop_ms(E.st) / iters;
+        E.free_ct(c);
+    });
+}
+int ckks_bench_mul_batch(ckks_engine* e, int level, int nb, int iters, float* ms_out) {
+    return guard([&] {
+        Engine& E = *e->E;
+        Ct* a = random_ct(E, level, 20, nb);
+        Ct* b = random_ct(E, level, 300, nb);
+        for (int w = 0; w < 3; w++) E.free_ct(E.mul(a, b));
+        e->timer.start(E.st);
+        for (int it = 0; it < iters; it++) E.free_ct(E.mul(a, b));
+        *ms_out = e->timer.stop_ms(E.st) / iters;
+        E.free_ct(a);
+        E.free_ct(b);
+    });
 }
 int ckks_bench_rotate(ckks_engine* e, int level, int iters, float* ms_out) {
     return guard([&] {

@@ -174,11 +174,8 @@ Engine::Engine(const Params& P) : prm(P) {
     if (const char* v = getenv("CKKS_NTT_FUSE")) fuse_ntt = atoi(v) != 0;
     if (const char* v = getenv("CKKS_TENSOR_FUSE")) fuse_tensor = atoi(v) != 0;
     if (const char* v = getenv("CKKS_BC_MMA")) bc_mma = atoi(v) != 0;
-    {                                                                                    // experimental
-        const char* v = getenv("CKKS_NTT_CLUSTER");        // process-wide switch, re-read by every engine (unset = off)
-        g_ntt_cluster = v && atoi(v) >= 1;
-        g_ntt_cluster_all = v && atoi(v) >= 2;
-    }
+    int ntt_cluster = 0;                                                                 // DESIGN.md 8.1; a field of THIS engine's tables
+    if (const char* v = getenv("CKKS_NTT_CLUSTER")) ntt_cluster = atoi(v);
     if (const char* v = getenv("CKKS_CHEB_DEGREE")) prm.boot.cheb_degree = atoi(v);      // tuning / A-B runs only
     mod = prm.q;
     mod.insert(mod.end(), prm.p.begin(), prm.p.end());
@@ -229,7 +226,7 @@ Engine::Engine(const Params& P) : prm(P) {
     d_inv_s = upload(this, inv_s, owned);
     d_mc = upload(this, mc, owned);
     tabs = NttTables{d_fwd, d_fwd_s, d_inv, d_inv_s, upload(this, fwd_d, owned), upload(this, fwd_q, owned),
-                     upload(this, inv_d, owned), upload(this, inv_q, owned), d_mc, prm.logn};
+                     upload(this, inv_d, owned), upload(this, inv_q, owned), d_mc, prm.logn, ntt_cluster};
     ks = KShape{d_mc, prm.logn};
     // canonical-embedding tables (spec S9)
     const size_t M = 2 * n, ns = n / 2;
@@ -279,6 +276,8 @@ Engine::Engine(const Params& P) : prm(P) {
     d_ksi = upload(this, ksi, owned);
     std::vector<int> flag(1, 0);
     d_flag = upload(this, flag, owned);
+    std::vector<u64> epoch(1, 0);
+    d_epoch = upload(this, epoch, owned);
 }
 
 Engine::~Engine() {
@@ -498,6 +497,9 @@ void Engine::graph_capture_begin(int id) {
     G->cnt0[0] = n_keyswitch; G->cnt0[1] = n_ntt_limbs; G->cnt0[2] = n_rescale; G->cnt0[3] = n_mul_cc; G->cnt0[4] = n_boot;
     capture_id = G->id;
     dev::capture_begin(streams[0]);
+    // first node of every graph: advance the replay epoch, so the encryptions recorded in the graph (device-side hard
+    // renorm) draw fresh randomness on every replay instead of the values frozen at capture time
+    launch_bump(d_epoch, streams[0]);
 }
 void Engine::graph_capture_end(int id) {
     GraphRec* G = graph_rec(id);
@@ -536,11 +538,12 @@ void Engine::graph_wait(int slot) {
 }
 // overwrite the contents of a static input of a graph (same shape) on the replay stream the graph will be launched on
 void Engine::ct_assign(Ct* dst, const Ct* src, int slot) {
-    if (dst->npoly != src->npoly || dst->level != src->level) throw std::runtime_error("ct_assign: shape mismatch");
+    if (dst->npoly != src->npoly || dst->level != src->level || dst->nb != src->nb)
+        throw std::runtime_error("ct_assign: shape mismatch");
     if (dst->d == src->d) return;                  // the static input itself: nothing to copy
     dev_stream s = replay_stream(slot);
     if (slot) dev::stream_wait(s, streams[0]);
-    dev::d2d(dst->d, src->d, (size_t)src->npoly * (src->level + 1) * N() * sizeof(u64), s);
+    dev::d2d(dst->d, src->d, (size_t)src->nb * src->npoly * (src->level + 1) * N() * sizeof(u64), s);
     if (slot) dev::stream_wait(streams[0], s);      // src may be released (and rewritten) by the main stream afterwards
 }
 void Engine::ct_clear_memo(Ct* c) {
@@ -568,15 +571,41 @@ void Engine::graph_destroy(int id) {
     graphs.erase(id);
     delete G;
 }
-Ct* Engine::new_ct(int npoly, int level) {
+Ct* Engine::new_ct(int npoly, int level, int nb) {
+    if (nb < 1) throw std::runtime_error("new_ct: batch size must be positive");
     Ct* c = new Ct();
     c->npoly = npoly;
     c->level = level;
+    c->nb = nb;
     c->lane = cur_lane;
     c->epoch = cur_epoch();
     c->cap = capture_id;
-    c->d = alloc((size_t)npoly * (level + 1) * N());
+    c->d = alloc((size_t)nb * npoly * (level + 1) * N());
     return c;
+}
+int Engine::batch_of(const Ct* a, const Ct* b) const {
+    if (a->nb != b->nb && a->nb != 1 && b->nb != 1)
+        throw std::runtime_error("operands hold different batch sizes (" + std::to_string(a->nb) + " and " +
+                                 std::to_string(b->nb) + ")");
+    return std::max(a->nb, b->nb);
+}
+Ct* Engine::stack(const std::vector<Ct*>& items) {
+    if (items.empty()) throw std::runtime_error("stack: no ciphertexts");
+    const Ct* f = items[0];
+    for (const Ct* c : items)
+        if (!c || c->nb != 1 || c->npoly != f->npoly || c->level != f->level)
+            throw std::runtime_error("stack: items must be unbatched ciphertexts of one shape");
+    Ct* r = new_ct(f->npoly, f->level, (int)items.size());
+    const size_t per = (size_t)f->npoly * (f->level + 1) * N();
+    for (size_t i = 0; i < items.size(); i++) dev::d2d(r->d + i * per, items[i]->d, per * sizeof(u64), st);
+    return r;
+}
+Ct* Engine::item(const Ct* c, int i) {
+    if (i < 0 || i >= c->nb) throw std::runtime_error("item: batch index out of range");
+    Ct* r = new_ct(c->npoly, c->level, 1);
+    const size_t per = (size_t)c->npoly * (c->level + 1) * N();
+    dev::d2d(r->d, c->d + (size_t)i * per, per * sizeof(u64), st);
+    return r;
 }
 void Engine::free_ct(Ct* c) {
     if (!c) return;
@@ -642,24 +671,26 @@ void Engine::const_residues(double re, double im, double scale, const std::vecto
 }
 
 void Engine::ntt_rows(u64* data, const std::vector<int>& rows, const std::vector<int>& mods, bool inverse, int nz,
-                      size_t zstride) {
+                      size_t zstride, int nb, size_t bstride) {
     if (rows.empty() || nz == 0) return;
     if (nz > NTT_MAX_Z) {   // split long batches
         for (int z0 = 0; z0 < nz; z0 += NTT_MAX_Z)
-            ntt_rows(data + z0 * zstride, rows, mods, inverse, std::min(NTT_MAX_Z, nz - z0), zstride);
+            ntt_rows(data + z0 * zstride, rows, mods, inverse, std::min(NTT_MAX_Z, nz - z0), zstride, nb, bstride);
         return;
     }
     NttJob J;
     memset(&J, 0, sizeof(J));
     J.n = (int)rows.size();
     J.nz = nz;
+    J.nb = nb;
+    J.sbs = J.dbs = bstride;
     J.szs = J.dzs = zstride;
     for (int z = 0; z < nz; z++)
         for (int i = 0; i < J.n; i++) {
             J.rows[z][i] = J.srows[z][i] = (unsigned char)rows[i];
             J.mods[z][i] = (unsigned char)mods[i];
         }
-    run_ntt(data, data, J, inverse, (long)J.n * nz);
+    run_ntt(data, data, J, inverse, (long)J.n * nz * nb);
 }
 
 // every NTT launch goes through here: limb accounting and, when profiling, a CUDA-event pair per call on the
@@ -728,6 +759,9 @@ const u32* Engine::galois_perm(u64 g) {
 void Engine::automorph(u64* out, const u64* in, int rows, int npoly, u64 g) {
     const size_t stride = (size_t)rows * N();
     launch_permute(ks, out, in, galois_perm(g), rows, npoly, PolyStride{stride, stride, 0}, st);
+}
+void Engine::automorph(u64* out, const u64* in, int rows, int npoly, u64 g, PolyStride ps) {
+    launch_permute(ks, out, in, galois_perm(g), rows, npoly, ps, st);
 }
 
 // ------------------------------------------------------------------ keys (spec S8)
@@ -850,12 +884,18 @@ EvalKey* Engine::galois_key(u64 g) {
 }
 
 // ------------------------------------------------------------------ encode / encrypt / decrypt (spec S9, S10)
-// z_dev: 2n doubles on the device (overwritten as scratch) -> N signed coefficients
-void Engine::encode_coeffs_from_dev(i64* out_dev, double* z_dev, double scale, bool check) {
+// polynomial strides + batch strides of a launch (kernels.cuh: PolyStride)
+static PolyStride psb(size_t o, size_t a, size_t b, int nb, size_t bo, size_t ba, size_t bb) {
+    PolyStride p{o, a, b};
+    p.nb = nb; p.bout = bo; p.ba = ba; p.bb = bb;
+    return p;
+}
+// z_dev: nb x 2n doubles on the device (overwritten as scratch) -> nb x N signed coefficients
+void Engine::encode_coeffs_from_dev(i64* out_dev, double* z_dev, double scale, bool check, int nb) {
     const size_t ns = slots();
-    double* w = (double*)alloc(2 * ns);
-    launch_special_ifft(ks, w, z_dev, d_rot, d_ksi, st);
-    launch_round_coeffs(ks, out_dev, w, scale, d_flag, st);
+    double* w = (double*)alloc((size_t)nb * 2 * ns);
+    launch_special_ifft(ks, w, z_dev, d_rot, d_ksi, st, nb);
+    launch_round_coeffs(ks, out_dev, w, scale, d_flag, st, nb);
     release(w);
     if (!check) return;
     int flag = 0;
@@ -868,91 +908,100 @@ void Engine::encode_coeffs_from_dev(i64* out_dev, double* z_dev, double scale, b
         throw std::runtime_error("plaintext coefficient does not fit 62 bits");
     }
 }
-void Engine::encode_coeffs_dev(i64* out_dev, const double* z_host, double scale) {
+void Engine::encode_coeffs_dev(i64* out_dev, const double* z_host, double scale, int nb) {
     const size_t ns = slots();
-    double* z = (double*)alloc(2 * ns);
-    dev::h2d(z, z_host, 2 * ns * sizeof(double), st);
-    try { encode_coeffs_from_dev(out_dev, z, scale, true); } catch (...) { release(z); throw; }
+    double* z = (double*)alloc((size_t)nb * 2 * ns);
+    dev::h2d(z, z_host, (size_t)nb * 2 * ns * sizeof(double), st);
+    try { encode_coeffs_from_dev(out_dev, z, scale, true, nb); } catch (...) { release(z); throw; }
     release(z);
 }
 
 Pt* Engine::encode(const double* z, int level) {
     if (level < 0 || level > L()) throw std::runtime_error("encode: bad level");
     const size_t n = N();
-    i64* coef = (i64*)dev::alloc(n * sizeof(i64), st);
-    encode_coeffs_dev(coef, z, scales[level]);
+    i64* coef = (i64*)alloc(n);
+    try { encode_coeffs_dev(coef, z, scales[level]); } catch (...) { release(coef); throw; }
     Pt* p = new Pt();
     p->level = level;
     p->d = alloc((size_t)(level + 1) * n);
     std::vector<int> idx = mods_q(level);
     launch_reduce_i64(ks, p->d, coef, limb_list(idx), st);
     ntt_rows(p->d, idx, idx, false);
-    dev::free(coef, st);
+    release(coef);
     return p;
 }
 
-Ct* Engine::encrypt(const double* z, int level) {
+Ct* Engine::encrypt(const double* z, int level, int nb) {
     if (!has_pk) throw std::runtime_error("encrypt needs a public key");
     if (level < 0) level = prm.fresh_level;
     if (level > L()) throw std::runtime_error("encrypt: bad level");
-    i64* coef = (i64*)alloc(N());
-    try { encode_coeffs_dev(coef, z, scales[level]); } catch (...) { release(coef); throw; }
-    Ct* c = encrypt_coeffs(coef, level);
+    if (nb < 1) throw std::runtime_error("encrypt: batch size must be positive");
+    i64* coef = (i64*)alloc((size_t)nb * N());
+    try { encode_coeffs_dev(coef, z, scales[level], nb); } catch (...) { release(coef); throw; }
+    Ct* c = encrypt_coeffs(coef, level, nb);
     release(coef);
     return c;
 }
 
-// public-key encryption of N signed message coefficients already on the device (spec S8, S10)
-Ct* Engine::encrypt_coeffs(const i64* coef, int level) {
+// public-key encryption of nb x N signed message coefficients already on the device (spec S8, S10).  Item i of a batch
+// draws the streams an unbatched encryption number (counter + i) would draw: a batched encryption is bit-identical to
+// nb consecutive single ones.
+Ct* Engine::encrypt_coeffs(const i64* coef, int level, int nb) {
     const size_t n = N();
     const int nl = level + 1, nq = L() + 1;
     std::vector<int> idx = mods_q(level);
     LimbList ll = limb_list(idx);
-    const u64 k = enc_counter++;
-    // t[0] = v, t[1] = e0 + m, t[2] = e1  (coefficient domain), one batched NTT for all three
-    u64* t = alloc((size_t)3 * nl * n);
-    const size_t ps = (size_t)nl * n;
-    launch_sample_small(ks, t, ll, prm.seed, stream_id(ST_ENC_V, k), 1, st);
-    launch_sample_small(ks, t + ps, ll, prm.seed, stream_id(ST_ENC_E0, k), 0, st);
-    launch_sample_small(ks, t + 2 * ps, ll, prm.seed, stream_id(ST_ENC_E1, k), 0, st);
-    u64* m = alloc(ps);
-    launch_reduce_i64(ks, m, coef, ll, st);
-    PolyStride z0{0, 0, 0};
-    launch_add(ks, t + ps, t + ps, m, ll, 1, z0, st);
-    ntt_rows(t, idx, idx, false, 3, ps);
-    Ct* c = new_ct(2, level);
+    const u64 k = enc_counter;
+    enc_counter += (u64)nb;
+    // per item: t[0] = v, t[1] = e0 + m, t[2] = e1  (coefficient domain), one batched NTT for all of them
+    const size_t ps = (size_t)nl * n, tb = 3 * ps;
+    u64* t = alloc((size_t)nb * tb);
+    launch_sample_small(ks, t, ll, prm.seed, stream_id(ST_ENC_V, k), 1, st, nb, tb, d_epoch);
+    launch_sample_small(ks, t + ps, ll, prm.seed, stream_id(ST_ENC_E0, k), 0, st, nb, tb, d_epoch);
+    launch_sample_small(ks, t + 2 * ps, ll, prm.seed, stream_id(ST_ENC_E1, k), 0, st, nb, tb, d_epoch);
+    u64* m = alloc((size_t)nb * ps);
+    launch_reduce_i64(ks, m, coef, ll, st, nb, ps);
+    launch_add(ks, t + ps, t + ps, m, ll, 1, psb(0, 0, 0, nb, tb, tb, ps), st);
+    ntt_rows(t, idx, idx, false, 3, ps, nb, tb);
+    Ct* c = new_ct(2, level, nb);
     // c_k = v * pk_k + t[k+1]
-    launch_mul(ks, c->d, t, pk, ll, 2, PolyStride{ps, 0, (size_t)nq * n}, st);
-    launch_add(ks, c->d, c->d, t + ps, ll, 2, PolyStride{ps, ps, ps}, st);
+    launch_mul(ks, c->d, t, pk, ll, 2, psb(ps, 0, (size_t)nq * n, nb, 2 * ps, tb, 0), st);
+    launch_add(ks, c->d, c->d, t + ps, ll, 2, psb(ps, ps, ps, nb, 2 * ps, 2 * ps, tb), st);
     release(t);
     release(m);
     return c;
 }
 
-// secret-key decryption to slot values left ON THE DEVICE (2n doubles, caller releases)
+// secret-key decryption to slot values left ON THE DEVICE (nb x 2n doubles, caller releases)
 double* Engine::decrypt_to_dev(const Ct* c) {
     if (!has_sk) throw std::runtime_error("decrypt needs a secret key");
     const size_t n = N(), ns = slots();
-    const size_t ps = (size_t)(c->level + 1) * n;
+    const int nb = c->nb;
+    const size_t ps = (size_t)(c->level + 1) * n, cb = (size_t)c->npoly * ps;    // polynomial / batch strides of c
     std::vector<int> idx{0};
     LimbList ll = limb_list(idx);
     PolyStride z0{0, 0, 0};
-    u64* t = alloc(n);
-    u64* sp = alloc(n);
-    u64* tmp = alloc(n);
-    dev::d2d(t, c->d, n * sizeof(u64), st);
-    dev::d2d(sp, sk_ntt, n * sizeof(u64), st);
+    // t = c0 + c1 s (+ c2 s^2) on limb 0 (spec S10)
+    u64* t = alloc((size_t)nb * n);
+    u64* tmp = alloc((size_t)nb * n);
+    u64* sp = nullptr;
     for (int k = 1; k < c->npoly; k++) {
-        launch_mul(ks, tmp, c->d + k * ps, sp, ll, 1, z0, st);
-        launch_add(ks, t, t, tmp, ll, 1, z0, st);
-        if (k + 1 < c->npoly) launch_mul(ks, sp, sp, sk_ntt, ll, 1, z0, st);
+        const u64* spow = sk_ntt;
+        if (k > 1) {
+            if (!sp) { sp = alloc(n); launch_mul(ks, sp, sk_ntt, sk_ntt, ll, 1, z0, st); }
+            else launch_mul(ks, sp, sp, sk_ntt, ll, 1, z0, st);
+            spow = sp;
+        }
+        launch_mul(ks, tmp, c->d + k * ps, spow, ll, 1, psb(0, 0, 0, nb, n, cb, 0), st);
+        launch_add(ks, t, k == 1 ? c->d : t, tmp, ll, 1, psb(0, 0, 0, nb, n, k == 1 ? cb : n, n), st);
     }
-    ntt_rows(t, idx, idx, true);
-    double* w = (double*)alloc(2 * ns);
-    double* zz = (double*)alloc(2 * ns);
-    launch_center_to_w(ks, w, t, 0, scales[c->level], st);
-    launch_special_fft(ks, zz, w, d_rot, d_ksi, st);
-    release(t); release(sp); release(tmp);
+    ntt_rows(t, idx, idx, true, 1, 0, nb, n);
+    double* w = (double*)alloc((size_t)nb * 2 * ns);
+    double* zz = (double*)alloc((size_t)nb * 2 * ns);
+    launch_center_to_w(ks, w, t, 0, scales[c->level], st, nb);
+    launch_special_fft(ks, zz, w, d_rot, d_ksi, st, nb);
+    release(t); release(tmp);
+    if (sp) release(sp);
     release(w);
     return zz;
 }
@@ -964,10 +1013,10 @@ Ct* Engine::snap_zeta16(const Ct* a, int level, int stride) {
     if (level < 0) level = prm.fresh_level;
     if (level > L()) throw std::runtime_error("renorm: bad level");
     double* zz = decrypt_to_dev(a);
-    launch_snap_zeta16(ks, zz, d_zeta16, stride < 1 ? 1 : stride, st);
-    i64* coef = (i64*)alloc(N());
-    encode_coeffs_from_dev(coef, zz, scales[level], false);       // unit-modulus slots cannot overflow
-    Ct* c = encrypt_coeffs(coef, level);
+    launch_snap_zeta16(ks, zz, d_zeta16, stride < 1 ? 1 : stride, st, a->nb);
+    i64* coef = (i64*)alloc((size_t)a->nb * N());
+    encode_coeffs_from_dev(coef, zz, scales[level], false, a->nb);       // unit-modulus slots cannot overflow
+    Ct* c = encrypt_coeffs(coef, level, a->nb);
     release(coef);
     release(zz);
     return c;
@@ -976,18 +1025,19 @@ Ct* Engine::snap_zeta16(const Ct* a, int level, int stride) {
 // zeta_16 codec on the device: the caller ships one nibble per slot (n bytes instead of 16 n), the codeword lookup,
 // the embedding and the encryption run here; decryption returns the nearest-codeword index per slot (the host side of
 // reference state_encoder.py:14-38 / utils.py:9-19 moved next to the data)
-Ct* Engine::encrypt_zeta16(const unsigned char* nib_host, int level) {
+Ct* Engine::encrypt_zeta16(const unsigned char* nib_host, int level, int nb) {
     if (!has_pk) throw std::runtime_error("encrypt needs a public key");
     if (level < 0) level = prm.fresh_level;
     if (level > L()) throw std::runtime_error("encrypt: bad level");
+    if (nb < 1) throw std::runtime_error("encrypt: batch size must be positive");
     const size_t ns = slots();
-    unsigned char* nib = (unsigned char*)alloc((ns + 7) / 8);
-    double* z = (double*)alloc(2 * ns);
-    i64* coef = (i64*)alloc(N());
-    dev::h2d(nib, nib_host, ns, st);
-    launch_zeta16_from_nibbles(ks, z, nib, d_zeta16, st);
-    encode_coeffs_from_dev(coef, z, scales[level], false);           // unit-modulus slots cannot overflow
-    Ct* c = encrypt_coeffs(coef, level);
+    unsigned char* nib = (unsigned char*)alloc(((size_t)nb * ns + 7) / 8);
+    double* z = (double*)alloc((size_t)nb * 2 * ns);
+    i64* coef = (i64*)alloc((size_t)nb * N());
+    dev::h2d(nib, nib_host, (size_t)nb * ns, st);
+    launch_zeta16_from_nibbles(ks, z, nib, d_zeta16, st, nb);
+    encode_coeffs_from_dev(coef, z, scales[level], false, nb);        // unit-modulus slots cannot overflow
+    Ct* c = encrypt_coeffs(coef, level, nb);
     dev::sync(st);                                                    // nib_host may be reused by the caller
     release(coef); release(z); release(nib);
     return c;
@@ -995,9 +1045,9 @@ Ct* Engine::encrypt_zeta16(const unsigned char* nib_host, int level) {
 void Engine::decrypt_zeta16(const Ct* c, unsigned char* nib_out_host) {
     const size_t ns = slots();
     double* zz = decrypt_to_dev(c);
-    unsigned char* nib = (unsigned char*)alloc((ns + 7) / 8);
-    launch_nibbles_from_zeta16(ks, nib, zz, st);
-    dev::d2h(nib_out_host, nib, ns, st);
+    unsigned char* nib = (unsigned char*)alloc(((size_t)c->nb * ns + 7) / 8);
+    launch_nibbles_from_zeta16(ks, nib, zz, st, c->nb);
+    dev::d2h(nib_out_host, nib, (size_t)c->nb * ns, st);
     dev::sync(st);
     release(nib);
     release(zz);
@@ -1005,7 +1055,7 @@ void Engine::decrypt_zeta16(const Ct* c, unsigned char* nib_out_host) {
 
 void Engine::decrypt(const Ct* c, double* z_out) {
     double* zz = decrypt_to_dev(c);
-    dev::d2h(z_out, zz, 2 * slots() * sizeof(double), st);
+    dev::d2h(z_out, zz, (size_t)c->nb * 2 * slots() * sizeof(double), st);
     dev::sync(st);
     release(zz);
 }
@@ -1152,23 +1202,27 @@ const BaseConvTable* Engine::moddown_table_dev(int level, int drop) {
 }
 
 // ------------------------------------------------------------------ hybrid key switching (spec S5, S6)
-Decomp Engine::decompose(const u64* d, int level, const u64* times) {
+Decomp Engine::decompose(const u64* d, int level, const u64* times, int nb, size_t d_bs, size_t times_bs) {
     const size_t n = N();
     const int nq = level + 1, rows = nq + K();
     const int beta = (nq + prm.alpha - 1) / prm.alpha;
+    const size_t eb = (size_t)beta * rows * n;             // batch stride of ext
     Decomp D;
     D.level = level;
     D.beta = beta;
-    D.ext = alloc((size_t)beta * rows * n);
+    D.nb = nb;
+    D.ext = alloc((size_t)nb * eb);
     D.own = d;
+    D.own_bs = d_bs;
     // coefficient form of all q-limbs
-    u64* coef = alloc((size_t)nq * n);
+    u64* coef = alloc((size_t)nb * nq * n);
     {
         NttJob J;
         memset(&J, 0, sizeof(J));
         J.n = nq; J.nz = 1;
+        J.nb = nb; J.sbs = d_bs; J.dbs = (size_t)nq * n; J.s2bs = times_bs;
         for (int i = 0; i < nq; i++) { J.rows[0][i] = J.srows[0][i] = (unsigned char)i; J.mods[0][i] = (unsigned char)i; }
-        run_ntt(d, coef, J, true, nq, times);      // times != null: the polynomial is d * times, formed inside the transform
+        run_ntt(d, coef, J, true, (long)nq * nb, times);      // times != null: the polynomial is d * times, formed inside the transform
     }
     // fast basis conversion of every digit to the other moduli of Q_level u P: one launch, z = digit.  The digit's own
     // limbs are never copied: the inner product reads them from the NTT-domain input (Decomp::own).
@@ -1176,6 +1230,8 @@ Decomp Engine::decompose(const u64* d, int level, const u64* times) {
     memset(&J, 0, sizeof(J));
     J.nz = beta;
     J.szs = J.dzs = (size_t)rows * n;
+    J.nb = nb;
+    J.sbs = J.dbs = eb;
     long modup_limbs = 0;
     for (int j = 0; j < beta; j++) {
         const BaseConvTable& T = modup_table(level, j);
@@ -1192,32 +1248,40 @@ Decomp Engine::decompose(const u64* d, int level, const u64* times) {
         const BaseConvTable* tabs = modup_tables_dev(level);
         const int ns_last = nq - (beta - 1) * prm.alpha;
         const int nfull = ns_last == prm.alpha ? beta : beta - 1;
-        if (nfull) launch_base_convert(ks, D.ext, coef, tabs, 1, prm.alpha, rows, nfull, 0, (size_t)rows * n, st, bc_mma);
+        if (nfull)
+            launch_base_convert(ks, D.ext, coef, tabs, 1, prm.alpha, rows, nfull, 0, (size_t)rows * n, st, bc_mma, nb,
+                                (size_t)nq * n, eb);
         if (nfull < beta)
             launch_base_convert(ks, D.ext + (size_t)nfull * rows * n, coef, tabs + nfull, 1, ns_last, rows, 1, 0,
-                                (size_t)rows * n, st, bc_mma);
+                                (size_t)rows * n, st, bc_mma, nb, (size_t)nq * n, eb);
     }
-    // one batched forward NTT over the converted rows of all digits (z = digit)
-    run_ntt(D.ext, D.ext, J, false, modup_limbs);
+    // one batched forward NTT over the converted rows of all digits (z = digit) of all batch items
+    run_ntt(D.ext, D.ext, J, false, modup_limbs * nb);
     release(coef);
     return D;
 }
 
-// <digits, evk> (+ P * addend) into acc = [2][level+1+K][N] over Q_level u P; with accumulate the result is added to
+// <digits, evk> (+ P * addend) into acc = [nb][2][level+1+K][N] over Q_level u P; with accumulate the result is added to
 // what acc already holds (several key switches sharing ONE ModDown)
 void Engine::ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64* acc, const u64* addend, bool accumulate,
-                      bool tensor) {
-    const int level = D.level, nq = level + 1;
+                      bool tensor, size_t addend_bs) {
+    const int level = D.level, nq = level + 1, rows = nq + K();
     std::vector<int> qp = mods_qp(level);
     LimbList ll = limb_list(qp);
     LimbList er = limb_list(qp);                 // evk rows are indexed by global modulus index
+    KsBatch kb;
+    kb.nb = D.nb;
+    kb.acc = (size_t)2 * rows * N();
+    kb.ext = (size_t)D.beta * rows * N();
+    kb.own = D.own_bs;
+    kb.addend = addend_bs;
     launch_ks_inner(ks, acc, D.ext, D.own, evk->d, perm, ll, er, D.beta, nmod(), nq, prm.alpha, addend, sl_pmodq,
-                    accumulate ? 1 : 0, st, tensor);
-    n_keyswitch++;
+                    accumulate ? 1 : 0, st, tensor, kb);
+    n_keyswitch += D.nb;
 }
 
-// ONE division of acc by P * q_{level-drop+1..level}: out is [2][level+1-drop][N] (acc is used as scratch)
-void Engine::ks_moddown(u64* acc, int level, int drop, u64* out) {
+// ONE division of acc by P * q_{level-drop+1..level}: out is [nb][2][level+1-drop][N] (acc is used as scratch)
+void Engine::ks_moddown(u64* acc, int level, int drop, u64* out, int nb) {
     const size_t n = N();
     const int nq = level + 1, rows = nq + K(), nout = nq - drop;
     if (nout < 1) throw LevelError("key switch: ciphertext level should be positive for this rescale");
@@ -1225,9 +1289,10 @@ void Engine::ks_moddown(u64* acc, int level, int drop, u64* out) {
     std::vector<int> prow, pmod;
     for (int i = level - drop + 1; i <= level; i++) { prow.push_back(i); pmod.push_back(i); }
     for (int k = 0; k < K(); k++) { prow.push_back(nq + k); pmod.push_back(L() + 1 + k); }
-    ntt_rows(acc, prow, pmod, true, 2, (size_t)rows * n);
-    u64* conv = alloc((size_t)2 * nout * n);
-    launch_base_convert(ks, conv, acc, moddown_table_dev(level, drop), 0, K() + drop, nout, 2, (size_t)rows * n,
+    ntt_rows(acc, prow, pmod, true, 2, (size_t)rows * n, nb, (size_t)2 * rows * n);
+    u64* conv = alloc((size_t)nb * 2 * nout * n);
+    // [nb][2] slices with uniform strides: the batch folds into the slice count
+    launch_base_convert(ks, conv, acc, moddown_table_dev(level, drop), 0, K() + drop, nout, 2 * nb, (size_t)rows * n,
                         (size_t)nout * n, st, bc_mma);
     std::vector<int> qi = mods_q(level - drop);
     if (fuse_ntt) {
@@ -1236,36 +1301,38 @@ void Engine::ks_moddown(u64* acc, int level, int drop, u64* out) {
         memset(&J, 0, sizeof(J));
         J.n = nout; J.nz = 2;
         J.szs = J.dzs = (size_t)nout * n;
+        J.nb = nb;
+        J.sbs = J.dbs = (size_t)2 * nout * n;
         for (int z = 0; z < 2; z++)
             for (int i = 0; i < nout; i++) { J.rows[z][i] = J.srows[z][i] = (unsigned char)i; J.mods[z][i] = (unsigned char)i; }
         NttFuse F;
         F.pro_mod = -1;
-        F.ep_a = acc; F.ep_azs = (size_t)rows * n;
-        F.ep_out = out; F.ep_ozs = (size_t)nout * n;
+        F.ep_a = acc; F.ep_azs = (size_t)rows * n; F.ep_abs = (size_t)2 * rows * n;
+        F.ep_out = out; F.ep_ozs = (size_t)nout * n; F.ep_obs = (size_t)2 * nout * n;
         F.s = moddown_inv(level, drop);
-        run_ntt_fused(conv, conv, J, F, 2L * nout);
+        run_ntt_fused(conv, conv, J, F, 2L * nout * nb);
     } else {
-        ntt_rows(conv, qi, qi, false, 2, (size_t)nout * n);
-        launch_sub_mul_scalar(ks, out, acc, conv, limb_list(qi), moddown_inv(level, drop), 2,
+        ntt_rows(conv, qi, qi, false, 2, (size_t)nout * n, nb, (size_t)2 * nout * n);
+        launch_sub_mul_scalar(ks, out, acc, conv, limb_list(qi), moddown_inv(level, drop), 2 * nb,
                               PolyStride{(size_t)nout * n, (size_t)rows * n, (size_t)nout * n}, st);
     }
     release(conv);
-    if (drop) n_rescale++;
+    if (drop) n_rescale += nb;
 }
 
-// inner product with the key, then ONE division by P * q_{level-drop+1..level}: out is [2][level+1-drop][N].
-// addend ([2][level+1][N], e.g. the (d0, d1) of a tensor product) is folded in as P * addend before the division.
+// inner product with the key, then ONE division by P * q_{level-drop+1..level}: out is [nb][2][level+1-drop][N].
+// addend ([2][level+1][N] per item, e.g. the (d0, d1) of a tensor product) is folded in as P * addend before the division.
 void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out, const u64* addend, int drop,
-                      bool tensor) {
+                      bool tensor, size_t addend_bs) {
     const int rows = D.level + 1 + K();
-    u64* acc = alloc((size_t)2 * rows * N());
-    ks_inner(D, evk, perm, acc, addend, false, tensor);
-    ks_moddown(acc, D.level, drop, out);
+    u64* acc = alloc((size_t)D.nb * 2 * rows * N());
+    ks_inner(D, evk, perm, acc, addend, false, tensor, addend_bs);
+    ks_moddown(acc, D.level, drop, out, D.nb);
     release(acc);
 }
 
-void Engine::key_switch(const u64* d, int level, const EvalKey* evk, u64* out) {
-    Decomp D = decompose(d, level);
+void Engine::key_switch(const u64* d, int level, const EvalKey* evk, u64* out, int nb, size_t d_bs) {
+    Decomp D = decompose(d, level, nullptr, nb, d_bs, 0);
     ks_apply(D, evk, nullptr, out);
     release(D.ext);
 }
@@ -1277,24 +1344,27 @@ void Engine::need_levels(int level, int need, const char* what) const {
                          std::to_string(level) + ", need " + std::to_string(need) + ")");
 }
 
-// in: [npoly][level+1][N] -> out: [npoly][level][N]
-void Engine::rescale_into(u64* out, const u64* in, int npoly, int level) {
+// in: [nb][npoly][level+1][N] -> out: [nb][npoly][level][N]
+void Engine::rescale_into(u64* out, const u64* in, int npoly, int level, int nb) {
     const size_t n = N();
     const int nl = level + 1;
-    u64* last = alloc((size_t)npoly * n);
+    if (npoly > NTT_MAX_Z) throw std::runtime_error("rescale: too many polynomials");
+    u64* last = alloc((size_t)nb * npoly * n);
     {
         NttJob J;
         memset(&J, 0, sizeof(J));
         J.n = 1; J.nz = npoly;
         J.szs = (size_t)nl * n;
         J.dzs = n;
+        J.nb = nb;
+        J.sbs = (size_t)npoly * nl * n;
+        J.dbs = (size_t)npoly * n;
         for (int z = 0; z < npoly; z++) { J.srows[z][0] = (unsigned char)level; J.rows[z][0] = 0; J.mods[z][0] = (unsigned char)level; }
-        if (npoly > NTT_MAX_Z) throw std::runtime_error("rescale: too many polynomials");
-        run_ntt(in, last, J, true, npoly);
+        run_ntt(in, last, J, true, (long)npoly * nb);
     }
     std::vector<int> lo = mods_q(level - 1);
     LimbList ll = limb_list(lo);
-    u64* delta = alloc((size_t)npoly * level * n);
+    u64* delta = alloc((size_t)nb * npoly * level * n);
     if (fuse_ntt) {
         // the centred lift of the dropped limb is the prologue of the transform's first pass, (in - NTT(delta)) q_l^-1
         // the epilogue of its second: four launches per rescale instead of six, delta never goes to HBM in full
@@ -1303,39 +1373,45 @@ void Engine::rescale_into(u64* out, const u64* in, int npoly, int level) {
         J.n = level; J.nz = npoly;
         J.szs = n;
         J.dzs = (size_t)level * n;
+        J.nb = nb;
+        J.sbs = (size_t)npoly * n;
+        J.dbs = (size_t)npoly * level * n;
         for (int z = 0; z < npoly; z++)
             for (int i = 0; i < level; i++) { J.srows[z][i] = 0; J.rows[z][i] = (unsigned char)i; J.mods[z][i] = (unsigned char)i; }
         NttFuse F;
         F.pro_mod = level;
-        F.ep_a = in; F.ep_azs = (size_t)nl * n;
-        F.ep_out = out; F.ep_ozs = (size_t)level * n;
+        F.ep_a = in; F.ep_azs = (size_t)nl * n; F.ep_abs = (size_t)npoly * nl * n;
+        F.ep_out = out; F.ep_ozs = (size_t)level * n; F.ep_obs = (size_t)npoly * level * n;
         F.s = sl_qinv[level];
-        run_ntt_fused(last, delta, J, F, (long)npoly * level);
+        run_ntt_fused(last, delta, J, F, (long)npoly * level * nb);
     } else {
-        launch_rescale_delta(ks, delta, last, ll, level, npoly, PolyStride{(size_t)level * n, n, 0}, st);
-        ntt_rows(delta, lo, lo, false, npoly, (size_t)level * n);
-        launch_sub_mul_scalar(ks, out, in, delta, ll, sl_qinv[level], npoly,
+        // [nb][npoly] slices with uniform strides: the batch folds into the polynomial count
+        launch_rescale_delta(ks, delta, last, ll, level, npoly * nb, PolyStride{(size_t)level * n, n, 0}, st);
+        ntt_rows(delta, lo, lo, false, npoly, (size_t)level * n, nb, (size_t)npoly * level * n);
+        launch_sub_mul_scalar(ks, out, in, delta, ll, sl_qinv[level], npoly * nb,
                               PolyStride{(size_t)level * n, (size_t)nl * n, (size_t)level * n}, st);
     }
     release(last);
     release(delta);
-    n_rescale++;
+    n_rescale += nb;
 }
 
 Ct* Engine::rescale(const Ct* c) {
     need_levels(c->level, 1, "rescale");
-    Ct* r = new_ct(c->npoly, c->level - 1);
-    rescale_into(r->d, c->d, c->npoly, c->level);
+    Ct* r = new_ct(c->npoly, c->level - 1, c->nb);
+    rescale_into(r->d, c->d, c->npoly, c->level, c->nb);
     return r;
 }
 
 Ct* Engine::drop_to(const Ct* a, int level) {
     if (level > a->level) throw std::runtime_error("drop_to: cannot raise a level");
     const size_t n = N();
-    Ct* r = new_ct(a->npoly, level);
-    for (int k = 0; k < a->npoly; k++)
-        dev::d2d(r->d + (size_t)k * (level + 1) * n, a->d + (size_t)k * (a->level + 1) * n,
-                 (size_t)(level + 1) * n * sizeof(u64), st);
+    Ct* r = new_ct(a->npoly, level, a->nb);
+    if (level == a->level)
+        dev::d2d(r->d, a->d, (size_t)a->nb * a->npoly * (level + 1) * n * sizeof(u64), st);
+    else
+        launch_copy(ks, r->d, a->d, level + 1, a->npoly * a->nb,
+                    PolyStride{(size_t)(level + 1) * n, (size_t)(a->level + 1) * n, 0}, st);
     return r;
 }
 
@@ -1362,50 +1438,54 @@ Ct* Engine::level_down(Ct* c, int target) {
     std::vector<u64> kv(idx.size(), k);
     ScalarList sc;
     scalar_list(kv, idx, sc);
-    u64* tmp = alloc((size_t)c->npoly * (t1 + 1) * n);
-    launch_mul_scalar(ks, tmp, c->d, limb_list(idx), sc, c->npoly,
+    const int np = c->npoly * c->nb;                        // uniform strides: the batch folds into the polynomial count
+    u64* tmp = alloc((size_t)np * (t1 + 1) * n);
+    launch_mul_scalar(ks, tmp, c->d, limb_list(idx), sc, np,
                       PolyStride{(size_t)(t1 + 1) * n, (size_t)(c->level + 1) * n, 0}, st);
-    Ct* r = new_ct(c->npoly, target);
-    rescale_into(r->d, tmp, c->npoly, t1);
+    Ct* r = new_ct(c->npoly, target, c->nb);
+    rescale_into(r->d, tmp, c->npoly, t1, c->nb);
     release(tmp);
     c->lowered.push_back(std::make_pair(target, r));
     return r;
 }
 
 // ------------------------------------------------------------------ homomorphic ops
+// r = a (+/-) b on the common polynomials; the surplus polynomials of the longer operand are copied (negated for b in a - b)
+static void addsub(Engine& E, bool subtract, Ct* r, const Ct* a, const Ct* b) {
+    const int l = r->level, nb = r->nb;
+    const size_t ps = (size_t)(l + 1) * E.N();
+    const int np = r->npoly, nmin = std::min(a->npoly, b->npoly);
+    LimbList ll = E.limb_list(E.mods_q(l));
+    const PolyStride S = psb(ps, ps, ps, nb, np * ps, Engine::bstride(a, a->npoly * ps), Engine::bstride(b, b->npoly * ps));
+    if (subtract) launch_sub(E.ks, r->d, a->d, b->d, ll, nmin, S, E.st);
+    else launch_add(E.ks, r->d, a->d, b->d, ll, nmin, S, E.st);
+    if (np > nmin) {
+        const Ct* big = a->npoly > b->npoly ? a : b;
+        const PolyStride T = psb(ps, ps, 0, nb, np * ps, Engine::bstride(big, big->npoly * ps), 0);
+        if (subtract && big == b) launch_neg(E.ks, r->d + nmin * ps, b->d + nmin * ps, ll, np - nmin, T, E.st);
+        else launch_copy(E.ks, r->d + nmin * ps, big->d + nmin * ps, l + 1, np - nmin, T, E.st);
+    }
+}
 Ct* Engine::add(Ct* a, Ct* b) {
     const int l = std::min(a->level, b->level);
     a = level_down(a, l);
     b = level_down(b, l);
-    const size_t ps = (size_t)(l + 1) * N();
-    const int np = std::max(a->npoly, b->npoly), nmin = std::min(a->npoly, b->npoly);
-    Ct* r = new_ct(np, l);
-    launch_add(ks, r->d, a->d, b->d, limb_list(mods_q(l)), nmin, PolyStride{ps, ps, ps}, st);
-    if (np > nmin) {
-        const Ct* big = a->npoly > b->npoly ? a : b;
-        dev::d2d(r->d + nmin * ps, big->d + nmin * ps, (np - nmin) * ps * sizeof(u64), st);
-    }
+    Ct* r = new_ct(std::max(a->npoly, b->npoly), l, batch_of(a, b));
+    addsub(*this, false, r, a, b);
     return r;
 }
 Ct* Engine::sub(Ct* a, Ct* b) {
     const int l = std::min(a->level, b->level);
     a = level_down(a, l);
     b = level_down(b, l);
-    const size_t ps = (size_t)(l + 1) * N();
-    const int np = std::max(a->npoly, b->npoly), nmin = std::min(a->npoly, b->npoly);
-    Ct* r = new_ct(np, l);
-    LimbList ll = limb_list(mods_q(l));
-    launch_sub(ks, r->d, a->d, b->d, ll, nmin, PolyStride{ps, ps, ps}, st);
-    if (np > nmin) {
-        if (a->npoly > b->npoly) dev::d2d(r->d + nmin * ps, a->d + nmin * ps, (np - nmin) * ps * sizeof(u64), st);
-        else launch_neg(ks, r->d + nmin * ps, b->d + nmin * ps, ll, np - nmin, PolyStride{ps, ps, 0}, st);
-    }
+    Ct* r = new_ct(std::max(a->npoly, b->npoly), l, batch_of(a, b));
+    addsub(*this, true, r, a, b);
     return r;
 }
 Ct* Engine::negate(const Ct* a) {
     const size_t ps = (size_t)(a->level + 1) * N();
-    Ct* r = new_ct(a->npoly, a->level);
-    launch_neg(ks, r->d, a->d, limb_list(mods_q(a->level)), a->npoly, PolyStride{ps, ps, 0}, st);
+    Ct* r = new_ct(a->npoly, a->level, a->nb);
+    launch_neg(ks, r->d, a->d, limb_list(mods_q(a->level)), a->npoly * a->nb, PolyStride{ps, ps, 0}, st);
     return r;
 }
 
@@ -1415,11 +1495,12 @@ Ct* Engine::mul_norelin(Ct* a, Ct* b) {
     need_levels(l, 1, "multiply");
     a = level_down(a, l);
     b = level_down(b, l);
-    const size_t n = N();
-    u64* t = alloc((size_t)3 * (l + 1) * n);
-    launch_tensor(ks, t, a->d, b->d, limb_list(mods_q(l)), st);
-    Ct* r = new_ct(3, l - 1);
-    rescale_into(r->d, t, 3, l);
+    const int nb = batch_of(a, b);
+    const size_t n = N(), ps = (size_t)(l + 1) * n;
+    u64* t = alloc((size_t)nb * 3 * ps);
+    launch_tensor(ks, t, a->d, b->d, limb_list(mods_q(l)), psb(0, 0, 0, nb, 3 * ps, bstride(a, 2 * ps), bstride(b, 2 * ps)), st);
+    Ct* r = new_ct(3, l - 1, nb);
+    rescale_into(r->d, t, 3, l, nb);
     release(t);
     return r;
 }
@@ -1427,11 +1508,11 @@ Ct* Engine::mul_norelin(Ct* a, Ct* b) {
 Ct* Engine::relinearize(const Ct* t) {
     if (t->npoly != 3) throw PolyCountError("relinearize: ciphertext should have 3 polynomials");
     if (!has_relin) throw std::runtime_error("relinearize needs a relinearisation key");
-    const int l = t->level;
+    const int l = t->level, nb = t->nb;
     const size_t ps = (size_t)(l + 1) * N();
-    Ct* r = new_ct(2, l);
-    key_switch(t->d + 2 * ps, l, &relin, r->d);
-    launch_add(ks, r->d, r->d, t->d, limb_list(mods_q(l)), 2, PolyStride{ps, ps, ps}, st);
+    Ct* r = new_ct(2, l, nb);
+    key_switch(t->d + 2 * ps, l, &relin, r->d, nb, 3 * ps);
+    launch_add(ks, r->d, r->d, t->d, limb_list(mods_q(l)), 2, psb(ps, ps, ps, nb, 2 * ps, 2 * ps, 3 * ps), st);
     return r;
 }
 
@@ -1442,42 +1523,44 @@ Ct* Engine::mul(Ct* a, Ct* b) {
     need_levels(l, 1, "multiply");
     a = level_down(a, l);
     b = level_down(b, l);
+    const int nb = batch_of(a, b);
     const size_t n = N(), ps = (size_t)(l + 1) * n;
+    const size_t abs_ = bstride(a, 2 * ps), bbs = bstride(b, 2 * ps);
     LimbList ll = limb_list(mods_q(l));
     if (fuse_tensor) {
         // the tensor product is never written: d2 = a1 b1 is formed inside the inverse transform of the decomposition
         // and (as the digits' own rows) inside the inner product, which also adds P (a0 b0, a0 b1 + a1 b0)
-        Decomp D = decompose(a->d + ps, l, b->d + ps);
+        Decomp D = decompose(a->d + ps, l, b->d + ps, nb, abs_, bbs);
         D.own = a->d;
-        Ct* r = new_ct(2, l - 1);
-        ks_apply(D, &relin, nullptr, r->d, b->d, 1, true);
+        Ct* r = new_ct(2, l - 1, nb);
+        ks_apply(D, &relin, nullptr, r->d, b->d, 1, true, bbs);
         release(D.ext);
-        n_mul_cc++;
+        n_mul_cc += nb;
         return r;
     }
-    u64* t = alloc(3 * ps);
-    launch_tensor(ks, t, a->d, b->d, ll, st);
+    u64* t = alloc((size_t)nb * 3 * ps);
+    launch_tensor(ks, t, a->d, b->d, ll, psb(0, 0, 0, nb, 3 * ps, abs_, bbs), st);
     // relinearisation and rescale in one division: (<digits(d2), rlk> + P (d0, d1)) / (P q_l)   (spec S6b)
-    Decomp D = decompose(t + 2 * ps, l);
-    Ct* r = new_ct(2, l - 1);
-    ks_apply(D, &relin, nullptr, r->d, t, 1);
+    Decomp D = decompose(t + 2 * ps, l, nullptr, nb, 3 * ps, 0);
+    Ct* r = new_ct(2, l - 1, nb);
+    ks_apply(D, &relin, nullptr, r->d, t, 1, false, 3 * ps);
     release(D.ext);
     release(t);
-    n_mul_cc++;
+    n_mul_cc += nb;
     return r;
 }
 
 Ct* Engine::mul_const(const Ct* a, double re, double im) {
     need_levels(a->level, 1, "multiply");
-    const int l = a->level;
+    const int l = a->level, np = a->npoly * a->nb;          // uniform strides: the batch folds into the polynomial count
     const size_t ps = (size_t)(l + 1) * N();
     std::vector<int> idx = mods_q(l);
     ScalarList cp, cm;
     const_residues(re, im, scales[l], idx, cp, cm);
-    u64* t = alloc((size_t)a->npoly * ps);
-    launch_mul_const(ks, t, a->d, limb_list(idx), cp, cm, a->npoly, PolyStride{ps, ps, 0}, st);
-    Ct* r = new_ct(a->npoly, l - 1);
-    rescale_into(r->d, t, a->npoly, l);
+    u64* t = alloc((size_t)np * ps);
+    launch_mul_const(ks, t, a->d, limb_list(idx), cp, cm, np, PolyStride{ps, ps, 0}, st);
+    Ct* r = new_ct(a->npoly, l - 1, a->nb);
+    rescale_into(r->d, t, a->npoly, l, a->nb);
     release(t);
     return r;
 }
@@ -1485,12 +1568,12 @@ Ct* Engine::mul_const(const Ct* a, double re, double im) {
 Ct* Engine::mul_plain(const Ct* a, const Pt* p) {
     need_levels(a->level, 1, "multiply");
     if (p->level != a->level) throw std::runtime_error("mul_plain: plaintext must be encoded at the ciphertext level");
-    const int l = a->level;
+    const int l = a->level, np = a->npoly * a->nb;
     const size_t ps = (size_t)(l + 1) * N();
-    u64* t = alloc((size_t)a->npoly * ps);
-    launch_mul(ks, t, a->d, p->d, limb_list(mods_q(l)), a->npoly, PolyStride{ps, ps, 0}, st);
-    Ct* r = new_ct(a->npoly, l - 1);
-    rescale_into(r->d, t, a->npoly, l);
+    u64* t = alloc((size_t)np * ps);
+    launch_mul(ks, t, a->d, p->d, limb_list(mods_q(l)), np, PolyStride{ps, ps, 0}, st);
+    Ct* r = new_ct(a->npoly, l - 1, a->nb);
+    rescale_into(r->d, t, a->npoly, l, a->nb);
     release(t);
     return r;
 }
@@ -1508,8 +1591,8 @@ Ct* Engine::mul_i(const Ct* a, int sign) {
     ScalarList cp, cm;
     scalar_list(vp, idx, cp);
     scalar_list(vm, idx, cm);
-    Ct* r = new_ct(a->npoly, l);
-    launch_mul_const(ks, r->d, a->d, limb_list(idx), cp, cm, a->npoly, PolyStride{ps, ps, 0}, st);
+    Ct* r = new_ct(a->npoly, l, a->nb);
+    launch_mul_const(ks, r->d, a->d, limb_list(idx), cp, cm, a->npoly * a->nb, PolyStride{ps, ps, 0}, st);
     return r;
 }
 
@@ -1519,32 +1602,33 @@ Ct* Engine::add_const(const Ct* a, double re, double im) {
     std::vector<int> idx = mods_q(l);
     ScalarList cp, cm;
     const_residues(re, im, scales[l], idx, cp, cm);
-    Ct* r = new_ct(a->npoly, l);
-    launch_add_const(ks, r->d, a->d, limb_list(idx), cp, cm, st);
-    dev::d2d(r->d + ps, a->d + ps, (size_t)(a->npoly - 1) * ps * sizeof(u64), st);
+    Ct* r = new_ct(a->npoly, l, a->nb);
+    // one launch: polynomial 0 of every item receives the constant, the others are copied
+    launch_add_const(ks, r->d, a->d, limb_list(idx), cp, cm, a->npoly,
+                     psb(ps, ps, 0, a->nb, a->npoly * ps, a->npoly * ps, 0), st);
     return r;
 }
 
 Ct* Engine::add_plain(const Ct* a, const Pt* p) {
     if (p->level != a->level) throw std::runtime_error("add_plain: plaintext must be encoded at the ciphertext level");
     const int l = a->level;
-    const size_t ps = (size_t)(l + 1) * N();
-    Ct* r = new_ct(a->npoly, l);
-    launch_add(ks, r->d, a->d, p->d, limb_list(mods_q(l)), 1, PolyStride{0, 0, 0}, st);
-    dev::d2d(r->d + ps, a->d + ps, (size_t)(a->npoly - 1) * ps * sizeof(u64), st);
+    const size_t ps = (size_t)(l + 1) * N(), ab = (size_t)a->npoly * ps;
+    Ct* r = new_ct(a->npoly, l, a->nb);
+    launch_add(ks, r->d, a->d, p->d, limb_list(mods_q(l)), 1, psb(0, 0, 0, a->nb, ab, ab, 0), st);
+    launch_copy(ks, r->d + ps, a->d + ps, l + 1, a->npoly - 1, psb(ps, ps, 0, a->nb, ab, ab, 0), st);
     return r;
 }
 
 Ct* Engine::apply_galois(const Ct* a, u64 g) {
     if (a->npoly != 2) throw PolyCountError("rotate/conjugate: ciphertext should have 2 polynomials");
-    const int l = a->level;
+    const int l = a->level, nb = a->nb;
     const size_t ps = (size_t)(l + 1) * N();
     EvalKey* key = galois_key(g);
-    u64* t = alloc(2 * ps);
-    automorph(t, a->d, l + 1, 2, g);
-    Ct* r = new_ct(2, l);
-    key_switch(t + ps, l, key, r->d);
-    launch_add(ks, r->d, r->d, t, limb_list(mods_q(l)), 1, PolyStride{0, 0, 0}, st);
+    u64* t = alloc((size_t)nb * 2 * ps);
+    automorph(t, a->d, l + 1, 2 * nb, g);
+    Ct* r = new_ct(2, l, nb);
+    key_switch(t + ps, l, key, r->d, nb, 2 * ps);
+    launch_add(ks, r->d, r->d, t, limb_list(mods_q(l)), 1, psb(0, 0, 0, nb, 2 * ps, 2 * ps, 2 * ps), st);
     release(t);
     return r;
 }
@@ -1558,7 +1642,7 @@ Ct* Engine::conjugate(const Ct* a) { return apply_galois(a, galois_conj()); }
 // hoisted rotations: one ModUp of c1, then per step the Galois gather is fused into the inner product
 std::vector<Ct*> Engine::rotate_hoisted(const Ct* a, const std::vector<long>& steps) {
     if (a->npoly != 2) throw PolyCountError("rotate: ciphertext should have 2 polynomials");
-    const int l = a->level;
+    const int l = a->level, nb = a->nb;
     const size_t ps = (size_t)(l + 1) * N();
     const long n = (long)slots();
     std::vector<Ct*> out(steps.size(), nullptr);
@@ -1569,7 +1653,7 @@ std::vector<Ct*> Engine::rotate_hoisted(const Ct* a, const std::vector<long>& st
     }
     if (work.empty()) return out;
     LimbList ll = limb_list(mods_q(l));
-    Decomp D = decompose(a->d + ps, l);
+    Decomp D = decompose(a->d + ps, l, nullptr, nb, 2 * ps, 0);
     for (size_t i : work) { galois_key(galois_for_rotation(steps[i])); galois_perm(galois_for_rotation(steps[i])); }
     // the rotations only read the shared decomposition: one stream lane each (up to 8)
     const int lanes = (int)std::min<size_t>(work.size(), 8);
@@ -1579,11 +1663,11 @@ std::vector<Ct*> Engine::rotate_hoisted(const Ct* a, const std::vector<long>& st
             if (lanes > 1) set_lane((int)(w % lanes));
             const size_t i = work[w];
             const u64 g = galois_for_rotation(steps[i]);
-            Ct* r = new_ct(2, l);
+            Ct* r = new_ct(2, l, nb);
             ks_apply(D, galois_key(g), galois_perm(g), r->d);
-            u64* t = alloc(ps);
-            automorph(t, a->d, l + 1, 1, g);
-            launch_add(ks, r->d, r->d, t, ll, 1, PolyStride{0, 0, 0}, st);
+            u64* t = alloc((size_t)nb * ps);
+            automorph(t, a->d, l + 1, 1, g, psb(0, 0, 0, nb, ps, 2 * ps, 0));
+            launch_add(ks, r->d, r->d, t, ll, 1, psb(0, 0, 0, nb, 2 * ps, 2 * ps, ps), st);
             release(t);
             out[i] = r;
         }

@@ -10,6 +10,12 @@
 // S[l-1] = S[l]^2 / q_l.  Every ciphertext at level l has exactly scale S[l]; plaintext operands
 // of a multiplication are encoded at S[l] so the rescaled product lands on S[l-1]; operands of
 // different levels are aligned by level_down() (limb drop + one integer multiply + one rescale).
+//
+// Batch dimension.  A Ct may hold nb INDEPENDENT ciphertexts of one shape, [nb][npoly][level+1][N] contiguous (the AES
+// path: one item per packed ciphertext pair, BASELINE.json configs[4]).  Every operation acts on all items in ONE set of
+// kernel launches -- an NTT call carries nb x the limbs, the key of a key switch is read once for the whole batch -- and
+// item i of the result is bit-identical to the operation applied to item i alone.  An nb = 1 operand of a binary
+// operation is broadcast to the batch (round-key ciphertexts are shared by all pairs).
 #pragma once
 #include <map>
 #include <unordered_map>
@@ -34,7 +40,8 @@ struct PolyCountError : std::runtime_error { using std::runtime_error::runtime_e
 struct Ct {
     int npoly = 2;
     int level = 0;
-    u64* d = nullptr;                               // [npoly][level+1][N], NTT domain
+    int nb = 1;                                     // batch items (independent ciphertexts of this shape)
+    u64* d = nullptr;                               // [nb][npoly][level+1][N], NTT domain
     int lane = 0;                                   // stream lane that produced it (0: the main stream)
     long epoch = 0;                                 // fork region it was produced in
     int cap = 0;                                    // graph capture it was recorded in (0: produced eagerly)
@@ -50,8 +57,10 @@ struct EvalKey {
 // ModUp result: every digit of a polynomial extended to Q_level u P, NTT domain
 struct Decomp {
     int level = 0, beta = 0;
-    u64* ext = nullptr;                             // [beta][level+1+K][N]; a digit's own rows are not filled
+    int nb = 1;
+    u64* ext = nullptr;                             // [nb][beta][level+1+K][N]; a digit's own rows are not filled
     const u64* own = nullptr;                       // the NTT-domain input [level+1][N] (read for own rows)
+    size_t own_bs = 0;                              // element stride of `own` between batch items (0: shared)
 };
 
 struct BootParams {
@@ -102,7 +111,11 @@ class Engine {
     // ---- memory
     u64* alloc(size_t words);
     void release(void* p);
-    Ct* new_ct(int npoly, int level);
+    Ct* new_ct(int npoly, int level, int nb = 1);
+    static size_t bstride(const Ct* c, size_t per_item) { return c->nb > 1 ? per_item : 0; }   // 0 broadcasts an nb = 1 operand
+    int batch_of(const Ct* a, const Ct* b) const;   // common batch size of a binary operation (nb = 1 broadcasts)
+    Ct* stack(const std::vector<Ct*>& items);       // nb = 1 ciphertexts of one shape -> one batched ciphertext (copies)
+    Ct* item(const Ct* c, int i);                   // copy of batch item i as an nb = 1 ciphertext
     void free_ct(Ct* c);
     void free_pt(Pt* p);
     void sync();
@@ -195,12 +208,13 @@ class Engine {
     u64* switch_key_buffer(u64 id, size_t* words);
 
     // ---- encode / encrypt / decrypt (host pointers: interleaved re,im doubles, n = N/2 slots)
+    // batched forms: z / nib hold nb consecutive slot vectors; decrypt writes c->nb of them
     Pt* encode(const double* z, int level);
-    Ct* encrypt(const double* z, int level);
+    Ct* encrypt(const double* z, int level, int nb = 1);
     void decrypt(const Ct* c, double* z_out);
     double* decrypt_to_dev(const Ct* c);
-    Ct* encrypt_coeffs(const i64* coef_dev, int level);
-    Ct* encrypt_zeta16(const unsigned char* nib_host, int level);   // one nibble per slot in, zeta_16 codewords encrypted
+    Ct* encrypt_coeffs(const i64* coef_dev, int level, int nb = 1);
+    Ct* encrypt_zeta16(const unsigned char* nib_host, int level, int nb = 1);   // one nibble per slot in, zeta_16 codewords encrypted
     void decrypt_zeta16(const Ct* c, unsigned char* nib_out_host);  // nearest zeta_16 codeword index per slot out
     Ct* snap_zeta16(const Ct* a, int level, int stride);   // decrypt, snap to zeta_16 codewords, re-encrypt: all on device
 
@@ -227,7 +241,7 @@ class Engine {
     Ct* lut2(const std::vector<Ct*>& A, const std::vector<Ct*>& B, const int* p, const int* q, const double* coef,
              int nterms);
     Ct* lincomb(const std::vector<Ct*>& X, const double* coef, int n);
-    void diag_mac(u64* out, const std::vector<const Ct*>& x, const std::vector<const Pt*>& p, int level);
+    void diag_mac(u64* out, const std::vector<const Ct*>& x, const std::vector<const Pt*>& p, int level, int nb = 1);
     const u64* const_table(const double* coef_re_im, int n, int scale_level, int level);
     Ct* drop_to(const Ct* a, int level);         // plain limb drop (scale unchanged): internal/bootstrap use
 
@@ -241,7 +255,7 @@ class Engine {
 
     // ---- low-level pieces (exposed through the C ABI for parity tests against the oracle)
     void ntt_rows(u64* data, const std::vector<int>& rows, const std::vector<int>& mods, bool inverse, int nz = 1,
-                  size_t zstride = 0);
+                  size_t zstride = 0, int nb = 1, size_t bstride = 0);
     void run_ntt(const u64* src, u64* dst, const NttJob& J, bool inverse, long limbs, const u64* src2 = nullptr);
     void run_ntt_fused(const u64* src, u64* dst, const NttJob& J, const NttFuse& F, long limbs);
     bool bc_mma = false;                   // CKKS_BC_MMA=1: basis conversion as a byte-sliced u8 tensor-core GEMM (measured slower: profiles/README.md)
@@ -249,14 +263,17 @@ class Engine {
     bool fuse_ntt = true;                  // CKKS_NTT_FUSE=0: stand-alone lift / subtract-scale kernels (A/B timing)
     void profile_begin();
     void profile_end(double* ms, long* calls, long* limbs);
-    Decomp decompose(const u64* d, int level, const u64* times = nullptr);
-    void ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out /* [2][level+1-drop][N] */,
-                  const u64* addend = nullptr, int drop = 0, bool tensor = false);
-    void key_switch(const u64* d, int level, const EvalKey* evk, u64* out);
+    // batched forms: nb items, d / times / addend advance by their batch stride per item (0 = shared by all items);
+    // ext, acc and out are [nb][...] contiguous
+    Decomp decompose(const u64* d, int level, const u64* times = nullptr, int nb = 1, size_t d_bs = 0, size_t times_bs = 0);
+    void ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out /* [nb][2][level+1-drop][N] */,
+                  const u64* addend = nullptr, int drop = 0, bool tensor = false, size_t addend_bs = 0);
+    void key_switch(const u64* d, int level, const EvalKey* evk, u64* out, int nb = 1, size_t d_bs = 0);
     void ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64* acc, const u64* addend, bool accumulate,
-                  bool tensor = false);
-    void ks_moddown(u64* acc, int level, int drop, u64* out);
+                  bool tensor = false, size_t addend_bs = 0);
+    void ks_moddown(u64* acc, int level, int drop, u64* out, int nb = 1);
     void automorph(u64* out, const u64* in, int rows, int npoly, u64 g);
+    void automorph(u64* out, const u64* in, int rows, int npoly, u64 g, PolyStride ps);
     const u32* galois_perm(u64 g);
     std::vector<int> mods_q(int level) const;
     std::vector<int> mods_qp(int level) const;
@@ -301,6 +318,7 @@ class Engine {
     double* d_zeta16 = nullptr;
     int* d_flag = nullptr;
     u64 enc_counter = 0;
+    u64* d_epoch = nullptr;                // replay epoch of captured graphs (mixed into the encryption randomness)
     bool prof_on = false;
     std::vector<dev::Timer> prof_timers;
     size_t prof_used = 0;
@@ -314,9 +332,9 @@ class Engine {
     EvalKey make_switch_key(u64 key_id, const u64* s_from_ntt);
     BaseConvTable make_bc_table(const std::vector<int>& src, const std::vector<int>& srow,
                                 const std::vector<int>& tgt, const std::vector<int>& orow, bool exact = false);
-    void encode_coeffs_dev(i64* out_dev, const double* z_host, double scale);
-    void encode_coeffs_from_dev(i64* out_dev, double* z_dev, double scale, bool check);
-    void rescale_into(u64* out, const u64* in, int npoly, int level);
+    void encode_coeffs_dev(i64* out_dev, const double* z_host, double scale, int nb = 1);
+    void encode_coeffs_from_dev(i64* out_dev, double* z_dev, double scale, bool check, int nb = 1);
+    void rescale_into(u64* out, const u64* in, int npoly, int level, int nb = 1);
     void need_levels(int level, int need, const char* what) const;
 };
 

@@ -13,25 +13,45 @@ constexpr int TPB = 256;
 
 // ------------------------------------------------------------------ element-wise
 enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2 };
-// blockIdx.z selects the polynomial; each pointer has its own polynomial stride (elements)
+// blockIdx.z selects the polynomial (and the batch item, batch-major, when ps.npoly is set); each pointer has its own
+// polynomial and batch strides (elements)
+struct ZOff { size_t out, a, b; };
+__device__ __forceinline__ ZOff zoff(const PolyStride& ps) {
+    const unsigned z = blockIdx.z;
+    const unsigned bi = ps.npoly ? z / (unsigned)ps.npoly : 0u, k = ps.npoly ? z - bi * (unsigned)ps.npoly : z;
+    ZOff o;
+    o.out = k * ps.out + bi * ps.bout;
+    o.a = k * ps.a + bi * ps.ba;
+    o.b = k * ps.b + bi * ps.bb;
+    return o;
+}
 template <int OP>
 __global__ void k_binop(KShape S, u64* __restrict__ out, const u64* __restrict__ a, const u64* __restrict__ b,
                         const GRID_CONST LimbList L, PolyStride ps) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
+    const ZOff o = zoff(ps);
     FOR_THREADS {
         const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
-        const u64 x = a[i + blockIdx.z * ps.a], y = b[i + blockIdx.z * ps.b];
-        out[i + blockIdx.z * ps.out] =
-            OP == OP_ADD ? add_mod(x, y, m.q) : OP == OP_SUB ? sub_mod(x, y, m.q) : barrett_mul(x, y, m);
+        const u64 x = a[i + o.a], y = b[i + o.b];
+        out[i + o.out] = OP == OP_ADD ? add_mod(x, y, m.q) : OP == OP_SUB ? sub_mod(x, y, m.q) : barrett_mul(x, y, m);
     }
 }
 __global__ void k_neg(KShape S, u64* __restrict__ out, const u64* __restrict__ a, const GRID_CONST LimbList L, PolyStride ps) {
     const int row = blockIdx.y;
     const u64 q = S.mc[L.idx[row]].q;
+    const ZOff o = zoff(ps);
     FOR_THREADS {
         const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
-        out[i + blockIdx.z * ps.out] = neg_mod(a[i + blockIdx.z * ps.a], q);
+        out[i + o.out] = neg_mod(a[i + o.a], q);
+    }
+}
+// plain copy of rows (limb drop of a batched ciphertext: one launch instead of one copy per polynomial)
+__global__ void k_copy(KShape S, u64* __restrict__ out, const u64* __restrict__ a, PolyStride ps) {
+    const ZOff o = zoff(ps);
+    FOR_THREADS {
+        const size_t i = ((size_t)blockIdx.y << S.logn) + blockIdx.x * TPB + threadIdx.x;
+        out[i + o.out] = a[i + o.a];
     }
 }
 
@@ -40,9 +60,10 @@ __global__ void k_mul_scalar(KShape S, u64* __restrict__ out, const u64* __restr
                              PolyStride ps) {
     const int row = blockIdx.y;
     const u64 q = S.mc[L.idx[row]].q;
+    const ZOff o = zoff(ps);
     FOR_THREADS {
         const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
-        out[i + blockIdx.z * ps.out] = shoup_mul(a[i + blockIdx.z * ps.a], Sc.v[row], Sc.vs[row], q);
+        out[i + o.out] = shoup_mul(a[i + o.a], Sc.v[row], Sc.vs[row], q);
     }
 }
 
@@ -51,10 +72,10 @@ __global__ void k_sub_mul_scalar(KShape S, u64* __restrict__ out, const u64* __r
                                  const u64* __restrict__ b, const GRID_CONST LimbList L, const GRID_CONST ScalarList Sc, PolyStride ps) {
     const int row = blockIdx.y;
     const u64 q = S.mc[L.idx[row]].q;
+    const ZOff o = zoff(ps);
     FOR_THREADS {
         const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
-        out[i + blockIdx.z * ps.out] =
-            shoup_mul(sub_mod(a[i + blockIdx.z * ps.a], b[i + blockIdx.z * ps.b], q), Sc.v[row], Sc.vs[row], q);
+        out[i + o.out] = shoup_mul(sub_mod(a[i + o.a], b[i + o.b], q), Sc.v[row], Sc.vs[row], q);
     }
 }
 
@@ -66,30 +87,35 @@ __global__ void k_mul_const(KShape S, u64* __restrict__ out, const u64* __restri
     const u64 q = S.mc[L.idx[row]].q;
     const bool lo = blockIdx.x < (gridDim.x >> 1);
     const u64 c = lo ? CP.v[row] : CM.v[row], cs = lo ? CP.vs[row] : CM.vs[row];
+    const ZOff zo = zoff(ps);
     FOR_THREADS {
         const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
-        const u64 t = shoup_mul(a[i + blockIdx.z * ps.a], c, cs, q);
-        u64* o = out + i + blockIdx.z * ps.out;
+        const u64 t = shoup_mul(a[i + zo.a], c, cs, q);
+        u64* o = out + i + zo.out;
         *o = ACC ? add_mod(*o, t, q) : t;
     }
 }
+// polynomial 0 of every batch item receives the constant, the other polynomials are copied (one launch per ciphertext)
 __global__ void k_add_const(KShape S, u64* __restrict__ out, const u64* __restrict__ a, const GRID_CONST LimbList L, const GRID_CONST ScalarList CP,
-                            const GRID_CONST ScalarList CM) {
+                            const GRID_CONST ScalarList CM, PolyStride ps, int npoly) {
     const int row = blockIdx.y;
     const u64 q = S.mc[L.idx[row]].q;
-    const u64 c = blockIdx.x < (gridDim.x >> 1) ? CP.v[row] : CM.v[row];
+    const bool first = (blockIdx.z % (unsigned)npoly) == 0;
+    const u64 c = !first ? 0 : blockIdx.x < (gridDim.x >> 1) ? CP.v[row] : CM.v[row];
+    const ZOff o = zoff(ps);
     FOR_THREADS {
         const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
-        out[i] = add_mod(a[i], c, q);
+        out[i + o.out] = add_mod(a[i + o.a], c, q);
     }
 }
 
 // tensor product of two 2-polynomial ciphertexts, nl limbs each: d0=a0 b0, d1=a0 b1+a1 b0, d2=a1 b1
 __global__ void k_tensor(KShape S, u64* __restrict__ d, const u64* __restrict__ a, const u64* __restrict__ b,
-                         const GRID_CONST LimbList L, int nl) {
+                         const GRID_CONST LimbList L, int nl, PolyStride ps) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
     const size_t P = (size_t)nl << S.logn;
+    d += blockIdx.z * ps.bout; a += blockIdx.z * ps.ba; b += blockIdx.z * ps.bb;      // blockIdx.z: batch item
     FOR_THREADS {
         const size_t i = ((size_t)row << S.logn) + blockIdx.x * TPB + threadIdx.x;
         const u64 a0 = a[i], a1 = a[i + P], b0 = b[i], b1 = b[i + P];
@@ -105,10 +131,11 @@ __global__ void k_tensor(KShape S, u64* __restrict__ d, const u64* __restrict__ 
 // out[r][k] = a[r][perm[k]]
 __global__ void k_permute(KShape S, u64* __restrict__ out, const u64* __restrict__ a, const u32* __restrict__ perm,
                           PolyStride ps) {
+    const ZOff o = zoff(ps);
     FOR_THREADS {
         const u32 k = blockIdx.x * TPB + threadIdx.x;
         const size_t base = (size_t)blockIdx.y << S.logn;
-        out[base + blockIdx.z * ps.out + k] = a[base + blockIdx.z * ps.a + ldg(perm + k)];
+        out[base + o.out + k] = a[base + o.a + ldg(perm + k)];
     }
 }
 
@@ -122,11 +149,13 @@ __global__ void k_permute(KShape S, u64* __restrict__ out, const u64* __restrict
 // TENSOR: the switched polynomial is the d2 of a ct x ct product that was never written out -- the digit's own rows are
 // a1*b1 computed here, and the addend is P*(a0 b0, a0 b1 + a1 b0) from the operands (`own` = a, `addend` = b, both
 // [2][nq][N]; same formulas as k_tensor, so the result is bit-identical to tensor + inner product).
+#define KS_MAX_BETA 6      /* == NTT_MAX_Z: the engine refuses parameter sets with more digits */
 template <bool TENSOR>
 __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restrict__ ext, const u64* __restrict__ own,
                            const u64* __restrict__ evk, const u32* __restrict__ perm, const GRID_CONST LimbList L,
                            const GRID_CONST LimbList ERow, int beta, int rows, int evk_rows, int nq, int alpha,
-                           const u64* __restrict__ addend, const GRID_CONST ScalarList PmodQ, int accumulate) {
+                           const u64* __restrict__ addend, const GRID_CONST ScalarList PmodQ, int accumulate,
+                           const GRID_CONST KsBatch kb) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
     const size_t er = ERow.idx[row];
@@ -135,42 +164,61 @@ __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restric
     FOR_THREADS {
         const u32 k = blockIdx.x * TPB + threadIdx.x;
         const u32 ks = perm ? ldg(perm + k) : k;
-        u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
-        u64 a0 = 0, a1 = 0, b0 = 0, b1 = 0;
-        if (TENSOR && row < nq) {
-            a0 = own[(size_t)row * N + k];    a1 = own[((size_t)nq + row) * N + k];
-            b0 = addend[(size_t)row * N + k]; b1 = addend[((size_t)nq + row) * N + k];
-        }
-        for (int j = 0; j < beta; j++) {
-            const u64 x = j == jown ? (TENSOR ? barrett_mul(a1, b1, m) : own[(size_t)row * N + ks])
-                                    : ext[((size_t)j * rows + row) * N + ks];
-            const u64* e = evk + ((size_t)j * 2 * evk_rows + er) * N + k;
-            mac128(h0, l0, x, ldg(e));
-            mac128(h1, l1, x, ldg(e + (size_t)evk_rows * N));
-            if ((j & 3) == 3 && j + 1 < beta) {      // keep the 128-bit sums below 4 q^2 (61-bit moduli)
-                l0 = barrett_reduce128(h0, l0, m); h0 = 0;
-                l1 = barrett_reduce128(h1, l1, m); h1 = 0;
+        // the key words of this coefficient: loaded once, applied to every batch item
+        u64 e0[KS_MAX_BETA], e1[KS_MAX_BETA];
+#pragma unroll
+        for (int j = 0; j < KS_MAX_BETA; j++) {
+            e0[j] = e1[j] = 0;
+            if (j < beta) {
+                const u64* e = evk + ((size_t)j * 2 * evk_rows + er) * N + k;
+                e0[j] = ldg(e);
+                e1[j] = ldg(e + (size_t)evk_rows * N);
             }
         }
-        u64 r0 = barrett_reduce128(h0, l0, m), r1 = barrett_reduce128(h1, l1, m);
-        if (TENSOR) {
-            if (row < nq) {
-                u64 hi = 0, lo = 0;
-                mac128(hi, lo, a0, b1);
-                mac128(hi, lo, a1, b0);
-                r0 = add_mod(r0, shoup_mul(barrett_mul(a0, b0, m), PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
-                r1 = add_mod(r1, shoup_mul(barrett_reduce128(hi, lo, m), PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+        for (int bi = 0; bi < kb.nb; bi++) {
+            const u64* xext = ext + bi * kb.ext;
+            const u64* xown = own + bi * kb.own;
+            const u64* xadd = addend ? addend + bi * kb.addend : nullptr;
+            u64* xacc = acc + bi * kb.acc;
+            u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+            u64 a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+            if (TENSOR && row < nq) {
+                a0 = xown[(size_t)row * N + k];  a1 = xown[((size_t)nq + row) * N + k];
+                b0 = xadd[(size_t)row * N + k];  b1 = xadd[((size_t)nq + row) * N + k];
             }
-        } else if (addend != nullptr && row < nq) {
-            r0 = add_mod(r0, shoup_mul(addend[(size_t)row * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
-            r1 = add_mod(r1, shoup_mul(addend[((size_t)nq + row) * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+#pragma unroll
+            for (int j = 0; j < KS_MAX_BETA; j++) {
+                if (j < beta) {
+                    const u64 x = j == jown ? (TENSOR ? barrett_mul(a1, b1, m) : xown[(size_t)row * N + ks])
+                                            : xext[((size_t)j * rows + row) * N + ks];
+                    mac128(h0, l0, x, e0[j]);
+                    mac128(h1, l1, x, e1[j]);
+                    if ((j & 3) == 3 && j + 1 < beta) {      // keep the 128-bit sums below 4 q^2 (61-bit moduli)
+                        l0 = barrett_reduce128(h0, l0, m); h0 = 0;
+                        l1 = barrett_reduce128(h1, l1, m); h1 = 0;
+                    }
+                }
+            }
+            u64 r0 = barrett_reduce128(h0, l0, m), r1 = barrett_reduce128(h1, l1, m);
+            if (TENSOR) {
+                if (row < nq) {
+                    u64 hi = 0, lo = 0;
+                    mac128(hi, lo, a0, b1);
+                    mac128(hi, lo, a1, b0);
+                    r0 = add_mod(r0, shoup_mul(barrett_mul(a0, b0, m), PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+                    r1 = add_mod(r1, shoup_mul(barrett_reduce128(hi, lo, m), PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+                }
+            } else if (xadd != nullptr && row < nq) {
+                r0 = add_mod(r0, shoup_mul(xadd[(size_t)row * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+                r1 = add_mod(r1, shoup_mul(xadd[((size_t)nq + row) * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+            }
+            if (accumulate) {          // several key switches summed before ONE ModDown (giant steps of a linear transform)
+                r0 = add_mod(r0, xacc[(size_t)row * N + k], m.q);
+                r1 = add_mod(r1, xacc[((size_t)rows + row) * N + k], m.q);
+            }
+            xacc[(size_t)row * N + k] = r0;
+            xacc[((size_t)rows + row) * N + k] = r1;
         }
-        if (accumulate) {          // several key switches summed before ONE ModDown (giant steps of a linear transform)
-            r0 = add_mod(r0, acc[(size_t)row * N + k], m.q);
-            r1 = add_mod(r1, acc[((size_t)rows + row) * N + k], m.q);
-        }
-        acc[(size_t)row * N + k] = r0;
-        acc[((size_t)rows + row) * N + k] = r1;
     }
 }
 
@@ -183,11 +231,12 @@ __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restric
 template <int NS>
 __global__ void __launch_bounds__(TPB)
 k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in, const BaseConvTable* __restrict__ tabs,
-               int tab_zstride, size_t in_zs, size_t out_zs) {
+               int tab_zstride, size_t in_zs, size_t out_zs, int nz, size_t in_bs, size_t out_bs) {
     CKKS_SHARED u64 s_hat[BC_MAX_TGT * NS];
     CKKS_SHARED u64 s_r64[BC_MAX_TGT];
     const size_t N = (size_t)1 << S.logn;
-    const BaseConvTable& T = tabs[blockIdx.z * tab_zstride];      // slice z uses its own table (digit) or a shared one
+    const unsigned zb = blockIdx.z / (unsigned)nz, zz = blockIdx.z - zb * (unsigned)nz;     // batch item, slice
+    const BaseConvTable& T = tabs[zz * tab_zstride];              // slice z uses its own table (digit) or a shared one
     const int nt = T.nt;
     // blockIdx.y picks a chunk of BC_CHUNK targets: more CTAs in flight for the small launches of a key switch; the
     // NS multiplications for y are repeated per chunk (NS of NS*(BC_CHUNK+1))
@@ -206,8 +255,8 @@ k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in, cons
     BLOCK_SYNC;
     FOR_THREADS {
         const u32 k = blockIdx.x * TPB + threadIdx.x;
-        const u64* src = in + blockIdx.z * in_zs;
-        u64* dst = out + blockIdx.z * out_zs;
+        const u64* src = in + zz * in_zs + zb * in_bs;
+        u64* dst = out + zz * out_zs + zb * out_bs;
         u64 y[NS];
         double v = 0.0;
 #pragma unroll
@@ -259,21 +308,22 @@ constexpr int BCM_YSTRIDE = 9;         // u64 per coefficient row of ys (8 sourc
 template <int NS>
 __global__ void __launch_bounds__(BCM_TILE, BCM_MIN_BLOCKS)
 k_base_convert_mma(KShape S, u64* __restrict__ out, const u64* __restrict__ in, const BaseConvTable* __restrict__ tabs,
-                   int tab_zstride, size_t in_zs, size_t out_zs) {
+                   int tab_zstride, size_t in_zs, size_t out_zs, int nz, size_t in_bs, size_t out_bs) {
     __shared__ __align__(16) u64 ys[BCM_TILE * BCM_YSTRIDE];
     __shared__ u64 s_pow8[BC_MAX_TGT * 16];
     __shared__ u64 s_q[BC_MAX_TGT], s_mu[BC_MAX_TGT], s_negD[BC_MAX_TGT];
     __shared__ u32 s_k1[BC_MAX_TGT], s_orow[BC_MAX_TGT];
     __shared__ unsigned char s_u[BCM_TILE];
     const size_t N = (size_t)1 << S.logn;
-    const BaseConvTable& T = tabs[blockIdx.z * tab_zstride];
+    const unsigned zb = blockIdx.z / (unsigned)nz, zz = blockIdx.z - zb * (unsigned)nz;
+    const BaseConvTable& T = tabs[zz * tab_zstride];
     const int nt = T.nt, tid = threadIdx.x;
     // blockIdx.y picks BCM_TG_PER_CTA target groups: more CTAs in flight for the small launches of a key switch (the y_i
     // are recomputed per CTA: NS multiplications against 8 x 16 diagonals of recombination)
     const int tg_beg = blockIdx.y * BCM_TG_PER_CTA;
     if (tg_beg * 8 >= nt) return;
-    const u64* src = in + blockIdx.z * in_zs;
-    u64* dst = out + blockIdx.z * out_zs + (size_t)blockIdx.x * BCM_TILE;
+    const u64* src = in + zz * in_zs + zb * in_bs;
+    u64* dst = out + zz * out_zs + zb * out_bs + (size_t)blockIdx.x * BCM_TILE;
     {
         // y_i = x_i * (D/s_i)^-1 mod s_i and the overflow count of the exact variant (same arithmetic as k_base_convert)
         const size_t k = (size_t)blockIdx.x * BCM_TILE + tid;
@@ -353,12 +403,13 @@ __global__ void k_rescale_delta(KShape S, u64* __restrict__ delta, const u64* __
     const ModConst m = S.mc[L.idx[row]];
     const u64 ql = S.mc[last_mod].q;
     const u64 h = ql >> 1;
+    const ZOff o = zoff(ps);
     FOR_THREADS {
         const u32 k = blockIdx.x * TPB + threadIdx.x;
-        u64 t = last[k + blockIdx.z * ps.a] + h;
+        u64 t = last[k + o.a] + h;
         t = t >= ql ? t - ql : t;
         const u64 r = barrett_reduce64(t, m), hm = barrett_reduce64(h, m);
-        delta[((size_t)row << S.logn) + k + blockIdx.z * ps.out] = sub_mod(r, hm, m.q);
+        delta[((size_t)row << S.logn) + k + o.out] = sub_mod(r, hm, m.q);
     }
 }
 
@@ -368,13 +419,14 @@ __global__ void k_center_lift(KShape S, u64* __restrict__ out, const u64* __rest
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
     const u64 qs = S.mc[src_mod].q;
+    const ZOff o = zoff(ps);
     FOR_THREADS {
         const u32 k = blockIdx.x * TPB + threadIdx.x;
-        const u64 v = in[k + blockIdx.z * ps.a];
+        const u64 v = in[k + o.a];
         u64 r;
         if (v > (qs >> 1)) r = neg_mod(barrett_reduce64(qs - v, m), m.q);
         else r = barrett_reduce64(v, m);
-        out[((size_t)row << S.logn) + k + blockIdx.z * ps.out] = r;
+        out[((size_t)row << S.logn) + k + o.out] = r;
     }
 }
 
@@ -404,20 +456,31 @@ __global__ void k_sample_uniform(KShape S, u64* __restrict__ out, const GRID_CON
     }
 }
 // kind 0: centred binomial (21+21 bits); kind 1: ternary {-1,0,1} w.p. 1/4,1/2,1/4.  Same value in every row.
-__global__ void k_sample_small(KShape S, u64* __restrict__ out, const GRID_CONST LimbList L, u64 seed, u64 stream, int kind) {
+// blockIdx.z = batch item: its own stream (the "a" field of the stream id advances by one per item) and output slice.
+// epoch != null: the seed is offset by the replay epoch of captured graphs (see launch_sample_small).
+__global__ void k_sample_small(KShape S, u64* __restrict__ out, const GRID_CONST LimbList L, u64 seed, u64 stream, int kind,
+                               size_t out_bs, const u64* __restrict__ epoch) {
     const int row = blockIdx.y;
     const u64 q = S.mc[L.idx[row]].q;
+    const u64 sd = seed + (epoch ? *epoch : 0) * 0xA24BAED4963EE407ull;
+    const u64 str = stream + ((u64)blockIdx.z << 16);
+    out += blockIdx.z * out_bs;
     FOR_THREADS {
         const u64 k = blockIdx.x * TPB + threadIdx.x;
-        const u64 r = rand64(seed, stream, k);
+        const u64 r = rand64(sd, str, k);
         int v = kind == 0 ? popc64(r & 0x1FFFFF) - popc64((r >> 21) & 0x1FFFFF) : (int)(r & 1) - (int)((r >> 1) & 1);
         out[((size_t)row << S.logn) + k] = v < 0 ? q - (u64)(-v) : (u64)v;
     }
 }
+__global__ void k_bump(u64* __restrict__ word) {
+    FOR_THREADS { if (threadIdx.x == 0) *word += 1; }
+}
 // signed 64-bit coefficients -> residues in every row
-__global__ void k_reduce_i64(KShape S, u64* __restrict__ out, const i64* __restrict__ v, const GRID_CONST LimbList L) {
+__global__ void k_reduce_i64(KShape S, u64* __restrict__ out, const i64* __restrict__ v, const GRID_CONST LimbList L, size_t out_bs) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
+    out += blockIdx.z * out_bs;                       // blockIdx.z = batch item (N coefficients each in v)
+    v += (size_t)blockIdx.z << S.logn;
     FOR_THREADS {
         const u32 k = blockIdx.x * TPB + threadIdx.x;
         const i64 x = v[k];
@@ -430,6 +493,7 @@ __global__ void k_reduce_i64(KShape S, u64* __restrict__ out, const i64* __restr
 // one butterfly stage of the "special FFT" on n = N/2 complex values (v: interleaved re,im)
 __global__ void k_fft_stage(KShape S, double* __restrict__ v, const u32* __restrict__ rot,
                             const double* __restrict__ ksi, int len, int inverse) {
+    v += (size_t)blockIdx.y << S.logn;                // blockIdx.y = batch item (n complex = N doubles each)
     FOR_THREADS {
         const int b = blockIdx.x * TPB + threadIdx.x;     // butterfly index in [0, n/2)
         const int lenh = len >> 1, lenq = len << 2, gap = (2 << S.logn) / lenq;
@@ -453,6 +517,8 @@ __global__ void k_fft_stage(KShape S, double* __restrict__ v, const u32* __restr
     }
 }
 __global__ void k_bitrev_copy(KShape S, double* __restrict__ out, const double* __restrict__ in, double mul) {
+    out += (size_t)blockIdx.y << S.logn;
+    in += (size_t)blockIdx.y << S.logn;
     FOR_THREADS {
         const u32 i = blockIdx.x * TPB + threadIdx.x;      // n = N/2 complex values
         const u32 j = brev32(i) >> (32 - (S.logn - 1));
@@ -464,6 +530,8 @@ __global__ void k_bitrev_copy(KShape S, double* __restrict__ out, const double* 
 __global__ void k_round_coeffs(KShape S, i64* __restrict__ out, const double* __restrict__ w, double scale,
                                int* __restrict__ flag) {
     const u32 n = 1u << (S.logn - 1);
+    out += (size_t)blockIdx.y << S.logn;
+    w += (size_t)blockIdx.y << S.logn;
     FOR_THREADS {
         const u32 k = blockIdx.x * TPB + threadIdx.x;      // k < n
         const double a = fmul_rn(w[2 * k], scale), b = fmul_rn(w[2 * k + 1], scale);
@@ -475,6 +543,8 @@ __global__ void k_round_coeffs(KShape S, i64* __restrict__ out, const double* __
 __global__ void k_center_to_w(KShape S, double* __restrict__ w, const u64* __restrict__ coef, int mod, double scale) {
     const u32 n = 1u << (S.logn - 1);
     const u64 q = S.mc[mod].q, half = q >> 1;
+    w += (size_t)blockIdx.y << S.logn;
+    coef += (size_t)blockIdx.y << S.logn;
     FOR_THREADS {
         const u32 k = blockIdx.x * TPB + threadIdx.x;      // k < n
         const u64 a = coef[k], b = coef[k + n];
@@ -489,6 +559,7 @@ __global__ void k_center_to_w(KShape S, double* __restrict__ w, const u64* __res
 // reference utils.py:15-19); with stride > 1 only slots j = 0 mod stride carry data and the others are set to 1.0
 // (reference state_encoder.py:23-27)
 __global__ void k_snap_zeta16(KShape S, double* __restrict__ z, const double* __restrict__ table, int stride) {
+    z += (size_t)blockIdx.y << S.logn;
     FOR_THREADS {
         const u32 j = blockIdx.x * TPB + threadIdx.x;
         if (stride > 1 && (j % (u32)stride) != 0) { z[2 * j] = 1.0; z[2 * j + 1] = 0.0; }
@@ -505,6 +576,8 @@ __global__ void k_snap_zeta16(KShape S, double* __restrict__ z, const double* __
 // zeta_16 codec on the device (the host side of reference utils.py:9-19 / state_encoder.py): nibble k <-> exp(-2 pi i k/16)
 __global__ void k_zeta16_from_nibbles(KShape S, double* __restrict__ z, const unsigned char* __restrict__ nib,
                                       const double* __restrict__ table) {
+    z += (size_t)blockIdx.y << S.logn;
+    nib += (size_t)blockIdx.y << (S.logn - 1);
     FOR_THREADS {
         const u32 j = blockIdx.x * TPB + threadIdx.x;
         const int k = nib[j] & 15;
@@ -513,6 +586,8 @@ __global__ void k_zeta16_from_nibbles(KShape S, double* __restrict__ z, const un
     }
 }
 __global__ void k_nibbles_from_zeta16(KShape S, unsigned char* __restrict__ nib, const double* __restrict__ z) {
+    z += (size_t)blockIdx.y << S.logn;
+    nib += (size_t)blockIdx.y << (S.logn - 1);
     FOR_THREADS {
         const u32 j = blockIdx.x * TPB + threadIdx.x;
         const double ang = atan2(z[2 * j + 1], z[2 * j]);
@@ -522,72 +597,84 @@ __global__ void k_nibbles_from_zeta16(KShape S, unsigned char* __restrict__ nib,
 }
 
 inline dim3 grid3(KShape S, int rows, int npoly = 1) { return dim3((1u << S.logn) / TPB, rows, npoly); }
+// grid z = batch items x polynomials (batch-major); the kernels split blockIdx.z with ps.npoly
+inline dim3 grid3b(KShape S, int rows, int npoly, PolyStride& ps) {
+    ps.npoly = ps.nb > 1 ? npoly : 0;
+    return dim3((1u << S.logn) / TPB, rows, npoly * (ps.nb > 1 ? ps.nb : 1));
+}
 
 }  // namespace
 
 // ============================================================================ host wrappers
 void launch_add(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, int npoly, PolyStride ps, dev_stream st) {
-    if (L.n) LAUNCH(k_binop<OP_ADD>, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, b, L, ps);
+    if (L.n) { const dim3 g = grid3b(S, L.n, npoly, ps); LAUNCH(k_binop<OP_ADD>, g, dim3(TPB), st, S, out, a, b, L, ps); }
 }
 void launch_sub(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, int npoly, PolyStride ps, dev_stream st) {
-    if (L.n) LAUNCH(k_binop<OP_SUB>, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, b, L, ps);
+    if (L.n) { const dim3 g = grid3b(S, L.n, npoly, ps); LAUNCH(k_binop<OP_SUB>, g, dim3(TPB), st, S, out, a, b, L, ps); }
 }
 void launch_mul(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, int npoly, PolyStride ps, dev_stream st) {
-    if (L.n) LAUNCH(k_binop<OP_MUL>, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, b, L, ps);
+    if (L.n) { const dim3 g = grid3b(S, L.n, npoly, ps); LAUNCH(k_binop<OP_MUL>, g, dim3(TPB), st, S, out, a, b, L, ps); }
 }
 void launch_neg(KShape S, u64* out, const u64* a, const LimbList& L, int npoly, PolyStride ps, dev_stream st) {
-    if (L.n) LAUNCH(k_neg, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, L, ps);
+    if (L.n) { const dim3 g = grid3b(S, L.n, npoly, ps); LAUNCH(k_neg, g, dim3(TPB), st, S, out, a, L, ps); }
+}
+void launch_copy(KShape S, u64* out, const u64* a, int rows, int npoly, PolyStride ps, dev_stream st) {
+    if (rows) { const dim3 g = grid3b(S, rows, npoly, ps); LAUNCH(k_copy, g, dim3(TPB), st, S, out, a, ps); }
 }
 void launch_mul_scalar(KShape S, u64* out, const u64* a, const LimbList& L, const ScalarList& Sc, int npoly, PolyStride ps,
                        dev_stream st) {
-    if (L.n) LAUNCH(k_mul_scalar, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, L, Sc, ps);
+    if (L.n) { const dim3 g = grid3b(S, L.n, npoly, ps); LAUNCH(k_mul_scalar, g, dim3(TPB), st, S, out, a, L, Sc, ps); }
 }
 void launch_sub_mul_scalar(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, const ScalarList& Sc,
                            int npoly, PolyStride ps, dev_stream st) {
-    if (L.n) LAUNCH(k_sub_mul_scalar, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, b, L, Sc, ps);
+    if (L.n) { const dim3 g = grid3b(S, L.n, npoly, ps); LAUNCH(k_sub_mul_scalar, g, dim3(TPB), st, S, out, a, b, L, Sc, ps); }
 }
 void launch_mul_const(KShape S, u64* out, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM,
                       int npoly, PolyStride ps, dev_stream st) {
-    if (L.n) LAUNCH(k_mul_const<0>, grid3(S, L.n, npoly), dim3(TPB), st, S, out, a, L, CP, CM, ps);
+    if (L.n) { const dim3 g = grid3b(S, L.n, npoly, ps); LAUNCH(k_mul_const<0>, g, dim3(TPB), st, S, out, a, L, CP, CM, ps); }
 }
 void launch_mac_const(KShape S, u64* acc, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM,
                       int npoly, PolyStride ps, dev_stream st) {
-    if (L.n) LAUNCH(k_mul_const<1>, grid3(S, L.n, npoly), dim3(TPB), st, S, acc, a, L, CP, CM, ps);
+    if (L.n) { const dim3 g = grid3b(S, L.n, npoly, ps); LAUNCH(k_mul_const<1>, g, dim3(TPB), st, S, acc, a, L, CP, CM, ps); }
 }
 void launch_add_const(KShape S, u64* out, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM,
-                      dev_stream st) {
-    if (L.n) LAUNCH(k_add_const, grid3(S, L.n), dim3(TPB), st, S, out, a, L, CP, CM);
+                      int npoly, PolyStride ps, dev_stream st) {
+    if (L.n) { const dim3 g = grid3b(S, L.n, npoly, ps); LAUNCH(k_add_const, g, dim3(TPB), st, S, out, a, L, CP, CM, ps, npoly); }
 }
-void launch_tensor(KShape S, u64* d, const u64* a, const u64* b, const LimbList& L, dev_stream st) {
-    if (L.n) LAUNCH(k_tensor, grid3(S, L.n), dim3(TPB), st, S, d, a, b, L, L.n);
+void launch_tensor(KShape S, u64* d, const u64* a, const u64* b, const LimbList& L, PolyStride ps, dev_stream st) {
+    if (L.n) LAUNCH(k_tensor, grid3(S, L.n, ps.nb > 1 ? ps.nb : 1), dim3(TPB), st, S, d, a, b, L, L.n, ps);
 }
 void launch_permute(KShape S, u64* out, const u64* a, const u32* perm, int rows, int npoly, PolyStride ps, dev_stream st) {
-    if (rows) LAUNCH(k_permute, grid3(S, rows, npoly), dim3(TPB), st, S, out, a, perm, ps);
+    if (rows) { const dim3 g = grid3b(S, rows, npoly, ps); LAUNCH(k_permute, g, dim3(TPB), st, S, out, a, perm, ps); }
 }
 void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u64* evk, const u32* perm,
                      const LimbList& L, const LimbList& ERow, int beta, int evk_rows, int nq, int alpha,
-                     const u64* addend, const ScalarList& PmodQ, int accumulate, dev_stream st, bool tensor) {
+                     const u64* addend, const ScalarList& PmodQ, int accumulate, dev_stream st, bool tensor, KsBatch kb) {
     if (!L.n) return;
+    if (beta > KS_MAX_BETA) throw std::runtime_error("ks_inner: too many digits");
+    if (kb.nb < 1) kb.nb = 1;
     if (tensor)
         LAUNCH(k_ks_inner<true>, grid3(S, L.n), dim3(TPB), st, S, acc, ext, own, evk, perm, L, ERow, beta, L.n, evk_rows,
-               nq, alpha, addend, PmodQ, accumulate);
+               nq, alpha, addend, PmodQ, accumulate, kb);
     else
         LAUNCH(k_ks_inner<false>, grid3(S, L.n), dim3(TPB), st, S, acc, ext, own, evk, perm, L, ERow, beta, L.n, evk_rows,
-               nq, alpha, addend, PmodQ, accumulate);
+               nq, alpha, addend, PmodQ, accumulate, kb);
 }
 void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns,
-                         int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st, bool mma) {
+                         int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st, bool mma, int nb, size_t in_bs,
+                         size_t out_bs) {
     if (!nz || !max_nt) return;
+    if (nb < 1) nb = 1;
 #ifndef CKKS_EMU
     if (mma && ns <= BC_MMA_MAX_SRC) {
-        dim3 gm((1u << S.logn) / BCM_TILE, ((max_nt + 7) / 8 + BCM_TG_PER_CTA - 1) / BCM_TG_PER_CTA, nz);
-#define BCM_CASE(n) case n: LAUNCH(k_base_convert_mma<n>, gm, dim3(BCM_TILE), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs); return;
+        dim3 gm((1u << S.logn) / BCM_TILE, ((max_nt + 7) / 8 + BCM_TG_PER_CTA - 1) / BCM_TG_PER_CTA, nz * nb);
+#define BCM_CASE(n) case n: LAUNCH(k_base_convert_mma<n>, gm, dim3(BCM_TILE), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs, nz, in_bs, out_bs); return;
         switch (ns) { BCM_CASE(1) BCM_CASE(2) BCM_CASE(3) BCM_CASE(4) BCM_CASE(5) BCM_CASE(6) BCM_CASE(7) BCM_CASE(8) }
 #undef BCM_CASE
     }
 #endif
-    dim3 g((1u << S.logn) / TPB, (max_nt + BC_CHUNK - 1) / BC_CHUNK, nz);
-#define BC_CASE(n) case n: LAUNCH(k_base_convert<n>, g, dim3(TPB), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs); break;
+    dim3 g((1u << S.logn) / TPB, (max_nt + BC_CHUNK - 1) / BC_CHUNK, nz * nb);
+#define BC_CASE(n) case n: LAUNCH(k_base_convert<n>, g, dim3(TPB), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs, nz, in_bs, out_bs); break;
     switch (ns) {
         BC_CASE(1) BC_CASE(2) BC_CASE(3) BC_CASE(4) BC_CASE(5) BC_CASE(6) BC_CASE(7) BC_CASE(8) BC_CASE(9) BC_CASE(10)
         BC_CASE(11) BC_CASE(12) BC_CASE(13) BC_CASE(14) BC_CASE(15) BC_CASE(16)
@@ -597,47 +684,49 @@ void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable*
 }
 void launch_rescale_delta(KShape S, u64* delta, const u64* last, const LimbList& L, int last_mod, int npoly, PolyStride ps,
                           dev_stream st) {
-    if (L.n) LAUNCH(k_rescale_delta, grid3(S, L.n, npoly), dim3(TPB), st, S, delta, last, L, last_mod, ps);
+    if (L.n) { const dim3 g = grid3b(S, L.n, npoly, ps); LAUNCH(k_rescale_delta, g, dim3(TPB), st, S, delta, last, L, last_mod, ps); }
 }
 void launch_center_lift(KShape S, u64* out, const u64* in, const LimbList& L, int src_mod, int npoly, PolyStride ps,
                         dev_stream st) {
-    if (L.n) LAUNCH(k_center_lift, grid3(S, L.n, npoly), dim3(TPB), st, S, out, in, L, src_mod, ps);
+    if (L.n) { const dim3 g = grid3b(S, L.n, npoly, ps); LAUNCH(k_center_lift, g, dim3(TPB), st, S, out, in, L, src_mod, ps); }
 }
 void launch_sample_uniform(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, dev_stream st) {
     if (L.n) LAUNCH(k_sample_uniform, grid3(S, L.n), dim3(TPB), st, S, out, L, seed, stream);
 }
-void launch_sample_small(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, int kind, dev_stream st) {
-    if (L.n) LAUNCH(k_sample_small, grid3(S, L.n), dim3(TPB), st, S, out, L, seed, stream, kind);
+void launch_sample_small(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, int kind, dev_stream st, int nb,
+                         size_t out_bs, const u64* epoch) {
+    if (L.n) LAUNCH(k_sample_small, grid3(S, L.n, nb < 1 ? 1 : nb), dim3(TPB), st, S, out, L, seed, stream, kind, out_bs, epoch);
 }
-void launch_reduce_i64(KShape S, u64* out, const i64* v, const LimbList& L, dev_stream st) {
-    if (L.n) LAUNCH(k_reduce_i64, grid3(S, L.n), dim3(TPB), st, S, out, v, L);
+void launch_bump(u64* word, dev_stream st) { LAUNCH(k_bump, dim3(1), dim3(32), st, word); }
+void launch_reduce_i64(KShape S, u64* out, const i64* v, const LimbList& L, dev_stream st, int nb, size_t out_bs) {
+    if (L.n) LAUNCH(k_reduce_i64, grid3(S, L.n, nb < 1 ? 1 : nb), dim3(TPB), st, S, out, v, L, out_bs);
 }
 // decode direction: w (n complex, natural order) -> z in `out`
-void launch_special_fft(KShape S, double* out, const double* w, const u32* rot, const double* ksi, dev_stream st) {
+void launch_special_fft(KShape S, double* out, const double* w, const u32* rot, const double* ksi, dev_stream st, int nb) {
     const int n = 1 << (S.logn - 1);
-    LAUNCH(k_bitrev_copy, dim3(n / TPB), dim3(TPB), st, S, out, w, 1.0);
+    LAUNCH(k_bitrev_copy, dim3(n / TPB, nb), dim3(TPB), st, S, out, w, 1.0);
     for (int len = 2; len <= n; len <<= 1)
-        LAUNCH(k_fft_stage, dim3(n / 2 / TPB), dim3(TPB), st, S, out, rot, ksi, len, 0);
+        LAUNCH(k_fft_stage, dim3(n / 2 / TPB, nb), dim3(TPB), st, S, out, rot, ksi, len, 0);
 }
 // encode direction: z -> w (includes 1/n); `z` is overwritten as scratch
-void launch_special_ifft(KShape S, double* out, double* z, const u32* rot, const double* ksi, dev_stream st) {
+void launch_special_ifft(KShape S, double* out, double* z, const u32* rot, const double* ksi, dev_stream st, int nb) {
     const int n = 1 << (S.logn - 1);
     for (int len = n; len >= 2; len >>= 1)
-        LAUNCH(k_fft_stage, dim3(n / 2 / TPB), dim3(TPB), st, S, z, rot, ksi, len, 1);
-    LAUNCH(k_bitrev_copy, dim3(n / TPB), dim3(TPB), st, S, out, z, 1.0 / (double)n);
+        LAUNCH(k_fft_stage, dim3(n / 2 / TPB, nb), dim3(TPB), st, S, z, rot, ksi, len, 1);
+    LAUNCH(k_bitrev_copy, dim3(n / TPB, nb), dim3(TPB), st, S, out, z, 1.0 / (double)n);
 }
-void launch_snap_zeta16(KShape S, double* z, const double* table, int stride, dev_stream st) {
-    LAUNCH(k_snap_zeta16, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, z, table, stride);
+void launch_snap_zeta16(KShape S, double* z, const double* table, int stride, dev_stream st, int nb) {
+    LAUNCH(k_snap_zeta16, dim3((1u << (S.logn - 1)) / TPB, nb), dim3(TPB), st, S, z, table, stride);
 }
-void launch_zeta16_from_nibbles(KShape S, double* z, const unsigned char* nib, const double* table, dev_stream st) {
-    LAUNCH(k_zeta16_from_nibbles, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, z, nib, table);
+void launch_zeta16_from_nibbles(KShape S, double* z, const unsigned char* nib, const double* table, dev_stream st, int nb) {
+    LAUNCH(k_zeta16_from_nibbles, dim3((1u << (S.logn - 1)) / TPB, nb), dim3(TPB), st, S, z, nib, table);
 }
-void launch_nibbles_from_zeta16(KShape S, unsigned char* nib, const double* z, dev_stream st) {
-    LAUNCH(k_nibbles_from_zeta16, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, nib, z);
+void launch_nibbles_from_zeta16(KShape S, unsigned char* nib, const double* z, dev_stream st, int nb) {
+    LAUNCH(k_nibbles_from_zeta16, dim3((1u << (S.logn - 1)) / TPB, nb), dim3(TPB), st, S, nib, z);
 }
-void launch_round_coeffs(KShape S, i64* out, const double* w, double scale, int* flag, dev_stream st) {
-    LAUNCH(k_round_coeffs, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, out, w, scale, flag);
+void launch_round_coeffs(KShape S, i64* out, const double* w, double scale, int* flag, dev_stream st, int nb) {
+    LAUNCH(k_round_coeffs, dim3((1u << (S.logn - 1)) / TPB, nb), dim3(TPB), st, S, out, w, scale, flag);
 }
-void launch_center_to_w(KShape S, double* w, const u64* coef, int mod, double scale, dev_stream st) {
-    LAUNCH(k_center_to_w, dim3((1u << (S.logn - 1)) / TPB), dim3(TPB), st, S, w, coef, mod, scale);
+void launch_center_to_w(KShape S, double* w, const u64* coef, int mod, double scale, dev_stream st, int nb) {
+    LAUNCH(k_center_to_w, dim3((1u << (S.logn - 1)) / TPB, nb), dim3(TPB), st, S, w, coef, mod, scale);
 }

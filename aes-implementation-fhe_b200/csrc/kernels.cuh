@@ -9,9 +9,15 @@
 #define BC_CHUNK 24
 #endif
 
-// element strides between consecutive polynomials (blockIdx.z) for each pointer of a kernel
+// element strides between consecutive polynomials for each pointer of a kernel.  Batched ciphertexts (engine.cuh: Ct::nb
+// independent ciphertexts of one shape in one buffer, [nb][npoly][rows][N]) add a second set of strides between
+// consecutive batch items; blockIdx.z then runs over nb * npoly (batch-major).  A stride of 0 broadcasts an operand
+// (a plaintext, a key, an nb = 1 ciphertext) to every polynomial / batch item.
 struct PolyStride {
     size_t out, a, b;
+    int nb = 1;                       // batch items
+    size_t bout = 0, ba = 0, bb = 0;  // element strides between consecutive batch items
+    int npoly = 0;                    // set by the launch wrapper: polynomials per batch item (0: blockIdx.z is the polynomial)
 };
 // fast basis conversion {src} -> {tgt}; hat is a device array [ns][nt]
 struct BaseConvTable {
@@ -46,23 +52,38 @@ void launch_mul_scalar(KShape S, u64* out, const u64* a, const LimbList& L, cons
 void launch_sub_mul_scalar(KShape S, u64* out, const u64* a, const u64* b, const LimbList& L, const ScalarList& Sc, int npoly, PolyStride ps, dev_stream st);
 void launch_mul_const(KShape S, u64* out, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM, int npoly, PolyStride ps, dev_stream st);
 void launch_mac_const(KShape S, u64* acc, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM, int npoly, PolyStride ps, dev_stream st);
-void launch_add_const(KShape S, u64* out, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM, dev_stream st);
-void launch_tensor(KShape S, u64* d, const u64* a, const u64* b, const LimbList& L, dev_stream st);
+// out = a with the constant added to polynomial 0 of every batch item; the other polynomials are copied
+void launch_add_const(KShape S, u64* out, const u64* a, const LimbList& L, const ScalarList& CP, const ScalarList& CM, int npoly, PolyStride ps, dev_stream st);
+// d[nb][3][nl][N] from a[nb|1][2][nl][N], b[nb|1][2][nl][N]; ps.nb / bout / ba / bb give the batch layout (poly strides unused)
+void launch_tensor(KShape S, u64* d, const u64* a, const u64* b, const LimbList& L, PolyStride ps, dev_stream st);
+void launch_copy(KShape S, u64* out, const u64* a, int rows, int npoly, PolyStride ps, dev_stream st);
 void launch_permute(KShape S, u64* out, const u64* a, const u32* perm, int rows, int npoly, PolyStride ps, dev_stream st);
-// acc[2][rows][N] = sum_j ext[j][rows][N] * evk[j][2][evk_rows][N]; ERow maps working row -> evk row
-void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u64* evk, const u32* perm, const LimbList& L, const LimbList& ERow, int beta, int evk_rows, int nq, int alpha, const u64* addend, const ScalarList& PmodQ, int accumulate, dev_stream st, bool tensor = false);
+// batch layout of a key-switch inner product: element strides between consecutive batch items (0 = shared operand)
+struct KsBatch {
+    int nb = 1;
+    size_t acc = 0, ext = 0, own = 0, addend = 0;
+};
+// acc[2][rows][N] = sum_j ext[j][rows][N] * evk[j][2][evk_rows][N]; ERow maps working row -> evk row.  The key is read
+// ONCE per coefficient and applied to every batch item (its HBM traffic is amortised over the batch).
+void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u64* evk, const u32* perm, const LimbList& L, const LimbList& ERow, int beta, int evk_rows, int nq, int alpha, const u64* addend, const ScalarList& PmodQ, int accumulate, dev_stream st, bool tensor = false, KsBatch kb = KsBatch());
 // nz independent conversions: slice z reads in + z*in_zs, writes out + z*out_zs, with table tabs_dev[z*tab_zstride]
-// (device memory); every table of the launch has exactly `ns` sources and at most `max_nt` targets
-void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns, int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st, bool mma = false);
+// (device memory); every table of the launch has exactly `ns` sources and at most `max_nt` targets.  nb batch items
+// repeat the nz slices at in + b*in_bs / out + b*out_bs.
+void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns, int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st, bool mma = false, int nb = 1, size_t in_bs = 0, size_t out_bs = 0);
 void launch_rescale_delta(KShape S, u64* delta, const u64* last, const LimbList& L, int last_mod, int npoly, PolyStride ps, dev_stream st);
 void launch_center_lift(KShape S, u64* out, const u64* in, const LimbList& L, int src_mod, int npoly, PolyStride ps, dev_stream st);
 void launch_sample_uniform(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, dev_stream st);
-void launch_sample_small(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, int kind, dev_stream st);
-void launch_reduce_i64(KShape S, u64* out, const i64* v, const LimbList& L, dev_stream st);
-void launch_special_fft(KShape S, double* out, const double* w, const u32* rot, const double* ksi, dev_stream st);
-void launch_special_ifft(KShape S, double* out, double* z, const u32* rot, const double* ksi, dev_stream st);
-void launch_snap_zeta16(KShape S, double* z, const double* table, int stride, dev_stream st);
-void launch_round_coeffs(KShape S, i64* out, const double* w, double scale, int* flag, dev_stream st);
-void launch_center_to_w(KShape S, double* w, const u64* coef, int mod, double scale, dev_stream st);
-void launch_zeta16_from_nibbles(KShape S, double* z, const unsigned char* nib, const double* table, dev_stream st);
-void launch_nibbles_from_zeta16(KShape S, unsigned char* nib, const double* z, dev_stream st);
+// nb batch items: item b writes out + b*out_bs and draws from stream + (b << 16) (the "a" field of the stream id).  epoch
+// (device word, may be null): the seed is offset by *epoch * const, so that a captured graph draws fresh randomness on
+// every replay (the engine bumps the word at the head of each captured graph; 0 outside graphs: oracle parity).
+void launch_sample_small(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, int kind, dev_stream st, int nb = 1, size_t out_bs = 0, const u64* epoch = nullptr);
+void launch_bump(u64* word, dev_stream st);
+void launch_reduce_i64(KShape S, u64* out, const i64* v, const LimbList& L, dev_stream st, int nb = 1, size_t out_bs = 0);
+// embedding kernels: nb independent vectors, consecutive in memory (n complex slots / N coefficients each)
+void launch_special_fft(KShape S, double* out, const double* w, const u32* rot, const double* ksi, dev_stream st, int nb = 1);
+void launch_special_ifft(KShape S, double* out, double* z, const u32* rot, const double* ksi, dev_stream st, int nb = 1);
+void launch_snap_zeta16(KShape S, double* z, const double* table, int stride, dev_stream st, int nb = 1);
+void launch_round_coeffs(KShape S, i64* out, const double* w, double scale, int* flag, dev_stream st, int nb = 1);
+void launch_center_to_w(KShape S, double* w, const u64* coef, int mod, double scale, dev_stream st, int nb = 1);
+void launch_zeta16_from_nibbles(KShape S, double* z, const unsigned char* nib, const double* table, dev_stream st, int nb = 1);
+void launch_nibbles_from_zeta16(KShape S, unsigned char* nib, const double* z, dev_stream st, int nb = 1);

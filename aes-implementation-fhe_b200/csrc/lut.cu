@@ -23,16 +23,19 @@ struct Lut2Args {
     const unsigned char* tq;           // [nterms]
     const u64* consts;                 // [rows][2 halves][nterms][2] = {c, shoup(c)}
     int nterms, rows;
+    unsigned abm, bbm;                 // bit p set: basis element p is batched (advances by 2 rows N per batch item = blockIdx.z)
 };
 struct LinCombArgs {
     const u64* x[LINCOMB_MAX];         // [npoly][rows][N] each (same level)
     const u64* consts;                 // [rows][2][nterms][2]
     int nterms, rows;
+    int npoly;                         // blockIdx.z = batch item * npoly + polynomial
+    u64 xbm[LINCOMB_MAX / 64];         // bit t set: x[t] is batched
 };
 
 struct DiagMacArgs {
-    const u64* x[16];                  // ciphertexts [2][rows][N]
-    const u64* p[16];                  // plaintext polynomials [rows][N]
+    const u64* x[16];                  // ciphertexts [nb][2][rows][N] (blockIdx.z = batch item * 2 + polynomial)
+    const u64* p[16];                  // plaintext polynomials [rows][N], shared by the batch
     int nterms, rows;
 };
 
@@ -63,6 +66,8 @@ k_lut2(KShape S, u64* __restrict__ d, const GRID_CONST Lut2Args G, const GRID_CO
     const size_t N = (size_t)1 << S.logn, P = (size_t)G.rows << S.logn;
     const int half = blockIdx.x < (gridDim.x >> 1) ? 0 : 1;
     const u64* cst = G.consts + ((size_t)(row * 2 + half) * G.nterms) * 2;
+    const size_t zb = (size_t)blockIdx.z * 2 * P;       // offset of this batch item inside a batched basis element
+    d += (size_t)blockIdx.z * 3 * P;
     FOR_THREADS {
         const size_t i = (size_t)row * N + blockIdx.x * 256 + threadIdx.x;
         u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0, h2 = 0, l2 = 0;
@@ -72,7 +77,8 @@ k_lut2(KShape S, u64* __restrict__ d, const GRID_CONST Lut2Args G, const GRID_CO
             u64 u0 = 0, u1 = 0;
             int cnt = 0;
             for (; t < G.nterms && ldg(G.tp + t) == p; t++) {
-                const u64* bq = G.b[ldg(G.tq + t)];
+                const int q = ldg(G.tq + t);
+                const u64* bq = G.b[q] + (((G.bbm >> q) & 1u) ? zb : 0);
                 const u64 c = ldg(cst + 2 * t), cs = ldg(cst + 2 * t + 1);
                 u0 += shoup_mul(ldg(bq + i), c, cs, m.q);
                 u1 += shoup_mul(ldg(bq + i + P), c, cs, m.q);
@@ -80,7 +86,8 @@ k_lut2(KShape S, u64* __restrict__ d, const GRID_CONST Lut2Args G, const GRID_CO
             }
             u0 = barrett_reduce64(u0, m);
             u1 = barrett_reduce64(u1, m);
-            const u64 a0 = ldg(G.a[p] + i), a1 = ldg(G.a[p] + i + P);
+            const u64* ap = G.a[p] + (((G.abm >> p) & 1u) ? zb : 0);
+            const u64 a0 = ldg(ap + i), a1 = ldg(ap + i + P);
             mac128(h0, l0, a0, u0);
             mac128(h1, l1, a0, u1);
             mac128(h1, l1, a1, u0);
@@ -105,14 +112,17 @@ k_lincomb(KShape S, u64* __restrict__ out, const GRID_CONST LinCombArgs G, const
     const size_t N = (size_t)1 << S.logn, P = (size_t)G.rows << S.logn;
     const int half = blockIdx.x < (gridDim.x >> 1) ? 0 : 1;
     const u64* cst = G.consts + ((size_t)(row * 2 + half) * G.nterms) * 2;
+    const unsigned bi = blockIdx.z / (unsigned)G.npoly, kp = blockIdx.z - bi * (unsigned)G.npoly;
+    const size_t zb = (size_t)bi * G.npoly * P;          // offset of this batch item inside a batched operand
     FOR_THREADS {
-        const size_t i = blockIdx.z * P + (size_t)row * N + blockIdx.x * 256 + threadIdx.x;
+        const size_t i = kp * P + (size_t)row * N + blockIdx.x * 256 + threadIdx.x;
         u64 acc = 0;
         for (int t = 0; t < G.nterms; t++) {
-            acc += shoup_mul(ldg(G.x[t] + i), ldg(cst + 2 * t), ldg(cst + 2 * t + 1), m.q);
+            const u64* xt = G.x[t] + (((G.xbm[t >> 6] >> (t & 63)) & 1ull) ? zb : 0);
+            acc += shoup_mul(ldg(xt + i), ldg(cst + 2 * t), ldg(cst + 2 * t + 1), m.q);
             if ((t & 7) == 7) acc = barrett_reduce64(acc, m);
         }
-        out[i] = barrett_reduce64(acc, m);
+        out[zb + i] = barrett_reduce64(acc, m);
     }
 }
 
@@ -170,6 +180,7 @@ Ct* Engine::lut2(const std::vector<Ct*>& A, const std::vector<Ct*>& B, const int
     memset(&G, 0, sizeof(G));
     std::vector<unsigned char> tp(nterms), tq(nterms);
     std::vector<double> cs(2 * (size_t)nterms);
+    int nb = 1;
     for (int t = 0; t < nterms; t++) {
         const int s = order[t];
         tp[t] = (unsigned char)p[s];
@@ -178,6 +189,13 @@ Ct* Engine::lut2(const std::vector<Ct*>& A, const std::vector<Ct*>& B, const int
         cs[2 * t + 1] = coef[2 * s + 1];
         G.a[p[s]] = level_down(A[p[s]], level)->d;
         G.b[q[s]] = level_down(B[q[s]], level)->d;
+        // an nb = 1 basis (a round key's) is broadcast to the batch of the other one
+        for (const Ct* c : {A[p[s]], B[q[s]]}) {
+            if (c->nb != 1 && nb != 1 && c->nb != nb) throw std::runtime_error("lut2: basis elements hold different batch sizes");
+            nb = std::max(nb, c->nb);
+        }
+        if (A[p[s]]->nb > 1) G.abm |= 1u << p[s];
+        if (B[q[s]]->nb > 1) G.bbm |= 1u << q[s];
     }
     // constants at scale S[level-1]: S_l^2 * S_{l-1} / (q_l q_{l-1}) = S_{l-2}
     G.consts = const_table(cs.data(), nterms, level - 1, level);
@@ -200,31 +218,33 @@ Ct* Engine::lut2(const std::vector<Ct*>& A, const std::vector<Ct*>& B, const int
     G.rows = level + 1;
     const size_t n = N(), ps = (size_t)(level + 1) * n;
     LimbList ll = limb_list(mods_q(level));
-    u64* d = alloc(3 * ps);
-    LAUNCH(k_lut2, dim3((unsigned)(n / 256), level + 1), dim3(256), st, ks, d, G, ll);
+    u64* d = alloc((size_t)nb * 3 * ps);
+    LAUNCH(k_lut2, dim3((unsigned)(n / 256), level + 1, nb), dim3(256), st, ks, d, G, ll);
     // ONE relinearisation merged with BOTH rescales: (<digits(d2), rlk> + P (d0, d1)) / (P q_l q_{l-1})   (spec S6b)
-    Decomp D = decompose(d + 2 * ps, level);
-    Ct* out = new_ct(2, level - 2);
-    ks_apply(D, &relin, nullptr, out->d, d, 2);
+    Decomp D = decompose(d + 2 * ps, level, nullptr, nb, 3 * ps, 0);
+    Ct* out = new_ct(2, level - 2, nb);
+    ks_apply(D, &relin, nullptr, out->d, d, 2, false, 3 * ps);
     release(D.ext);
     release(d);
-    n_mul_cc++;
+    n_mul_cc += nb;
     return out;
 }
 
 // out = sum_t x_t (.) p_t for up to 16 (ciphertext, plaintext) pairs at the same level, no rescale
-void Engine::diag_mac(u64* out, const std::vector<const Ct*>& x, const std::vector<const Pt*>& p, int level) {
+void Engine::diag_mac(u64* out, const std::vector<const Ct*>& x, const std::vector<const Pt*>& p, int level, int nb) {
     if (x.empty() || x.size() != p.size() || x.size() > 16) throw std::runtime_error("diag_mac: 1..16 terms");
     DiagMacArgs G;
     memset(&G, 0, sizeof(G));
     for (size_t t = 0; t < x.size(); t++) {
-        if (x[t]->level != level || p[t]->level != level || x[t]->npoly != 2) throw std::runtime_error("diag_mac: level mismatch");
+        if (x[t]->level != level || p[t]->level != level || x[t]->npoly != 2 || x[t]->nb != nb)
+            throw std::runtime_error("diag_mac: level mismatch");
         G.x[t] = x[t]->d;
         G.p[t] = p[t]->d;
     }
     G.nterms = (int)x.size();
     G.rows = level + 1;
-    LAUNCH(k_diag_mac, dim3((unsigned)(N() / 256), level + 1, 2), dim3(256), st, ks, out, G, limb_list(mods_q(level)));
+    // [nb][2] slices with uniform strides: blockIdx.z = batch item * 2 + polynomial
+    LAUNCH(k_diag_mac, dim3((unsigned)(N() / 256), level + 1, 2 * nb), dim3(256), st, ks, out, G, limb_list(mods_q(level)));
 }
 
 // sum_k c_k X_k: one fused multiply-accumulate and one rescale per distinct input level, partial sums added
@@ -232,10 +252,13 @@ void Engine::diag_mac(u64* out, const std::vector<const Ct*>& x, const std::vect
 Ct* Engine::lincomb(const std::vector<Ct*>& X, const double* coef, int n) {
     if (n < 1) throw std::runtime_error("lincomb: empty");
     std::map<int, std::vector<int>, std::greater<int>> by_level;
-    int npoly = X[0]->npoly;
+    if (!X[0]) throw std::runtime_error("lincomb: missing ciphertext");
+    int npoly = X[0]->npoly, nb = 1;
     for (int k = 0; k < n; k++) {
         if (!X[k]) throw std::runtime_error("lincomb: missing ciphertext");
         if (X[k]->npoly != npoly) throw PolyCountError("lincomb: mixed polynomial counts");
+        if (X[k]->nb != 1 && nb != 1 && X[k]->nb != nb) throw std::runtime_error("lincomb: operands hold different batch sizes");
+        nb = std::max(nb, X[k]->nb);
         need_levels(X[k]->level, 1, "lincomb");
         by_level[X[k]->level].push_back(k);
     }
@@ -253,22 +276,24 @@ Ct* Engine::lincomb(const std::vector<Ct*>& X, const double* coef, int n) {
             for (int t = 0; t < cnt; t++) {
                 const int k = kv.second[off + t];
                 G.x[t] = X[k]->d;
+                if (X[k]->nb > 1) G.xbm[t >> 6] |= 1ull << (t & 63);
                 cs[2 * t] = coef[2 * k];
                 cs[2 * t + 1] = coef[2 * k + 1];
             }
             G.consts = const_table(cs.data(), cnt, level, level);
             G.nterms = cnt;
             G.rows = level + 1;
-            u64* part = alloc((size_t)npoly * ps);
-            LAUNCH(k_lincomb, dim3((unsigned)(nn / 256), level + 1, npoly), dim3(256), st, ks, part, G, ll);
+            G.npoly = npoly;
+            u64* part = alloc((size_t)nb * npoly * ps);
+            LAUNCH(k_lincomb, dim3((unsigned)(nn / 256), level + 1, npoly * nb), dim3(256), st, ks, part, G, ll);
             if (!sum) sum = part;
             else {
-                launch_add(ks, sum, sum, part, ll, npoly, PolyStride{ps, ps, ps}, st);
+                launch_add(ks, sum, sum, part, ll, npoly * nb, PolyStride{ps, ps, ps}, st);
                 release(part);
             }
         }
-        Ct* r = new_ct(npoly, level - 1);
-        rescale_into(r->d, sum, npoly, level);
+        Ct* r = new_ct(npoly, level - 1, nb);
+        rescale_into(r->d, sum, npoly, level, nb);
         release(sum);
         if (!acc) acc = r;
         else {

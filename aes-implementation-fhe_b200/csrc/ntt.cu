@@ -58,6 +58,15 @@ __device__ __forceinline__ double bits2d(u64 x) { union { double d; u64 u; } c; 
 
 struct alignas(16) u64x2 { u64 a, b; };
 
+// blockIdx.z = batch item * nz + slice
+struct ZB { unsigned z, b; };
+__device__ __forceinline__ ZB zb_split(const NttJob& J) {
+    ZB r;
+    r.b = blockIdx.z / (unsigned)J.nz;
+    r.z = blockIdx.z - r.b * (unsigned)J.nz;
+    return r;
+}
+
 // ============================================================================================ twiddle accessors
 // A radix-16 block rooted at table index X needs, for r = 0..3, the 2^r entries (X << r) + g.  get(r, g) returns the
 // twiddle and its companion (Shoup word / quotient by q) as raw 64-bit words; get2 returns the pair g = 2 gh, 2 gh + 1.
@@ -377,12 +386,13 @@ template <int LOGR>
 __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_A)
 ntt_fwd_passA(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
     CKKS_SHARED __align__(16) u64 sm[kPassAWords];
-    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
-    const int limb = J.rows[blockIdx.z][blockIdx.y], slimb = J.srows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const ZB zb = zb_split(J);
+    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][blockIdx.y], slimb = J.srows[zb.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][blockIdx.y];
     const size_t N = (size_t)1 << T.logn;
-    src += blockIdx.z * J.szs;
-    dst += blockIdx.z * J.dzs;
+    src += zb.z * J.szs + zb.b * J.sbs;
+    dst += zb.z * J.dzs + zb.b * J.dbs;
     const ModConst mc = T.mc[mod];
     if (use_fp(mc.q)) fwd_passA_body<LOGR, true, false>(src, dst, sm, limb, slimb, tile, N, mc, T, mod, 0);
     else fwd_passA_body<LOGR, false, false>(src, dst, sm, limb, slimb, tile, N, mc, T, mod, 0);
@@ -392,12 +402,13 @@ template <int LOGR>
 __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_A)
 ntt_fwd_passA_lift(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T, int pro_mod) {
     CKKS_SHARED __align__(16) u64 sm[kPassAWords];
-    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
-    const int limb = J.rows[blockIdx.z][blockIdx.y], slimb = J.srows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const ZB zb = zb_split(J);
+    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][blockIdx.y], slimb = J.srows[zb.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][blockIdx.y];
     const size_t N = (size_t)1 << T.logn;
-    src += blockIdx.z * J.szs;
-    dst += blockIdx.z * J.dzs;
+    src += zb.z * J.szs + zb.b * J.sbs;
+    dst += zb.z * J.dzs + zb.b * J.dbs;
     const ModConst mc = T.mc[mod];
     const u64 ql = T.mc[pro_mod].q;
     if (use_fp(mc.q)) fwd_passA_body<LOGR, true, true>(src, dst, sm, limb, slimb, tile, N, mc, T, mod, ql);
@@ -476,12 +487,13 @@ __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int
 __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_B)
 ntt_fwd_passB(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
     CKKS_SHARED u64 sm[kPassBData];
-    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
-    const int limb = J.rows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const ZB zb = zb_split(J);
+    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][blockIdx.y];
     const size_t N = (size_t)1 << T.logn;
     const u32 Rn = (u32)(N >> 8);
-    data += blockIdx.z * J.dzs;
+    data += zb.z * J.dzs + zb.b * J.dbs;
     const ModConst mc = T.mc[mod];
     u64* g = data + (size_t)limb * N + (size_t)tile * 16 * 256;
     if (use_fp(mc.q)) fwd_passB_body<true, false>(g, sm, tile, Rn, mc, T, mod, N, nullptr, nullptr, 0, 0);
@@ -491,17 +503,18 @@ ntt_fwd_passB(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
 __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_B)
 ntt_fwd_passB_ep(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T, const GRID_CONST NttFuse F) {
     CKKS_SHARED u64 sm[kPassBData];
-    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
-    const int limb = J.rows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const ZB zb = zb_split(J);
+    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][blockIdx.y];
     const size_t N = (size_t)1 << T.logn;
     const u32 Rn = (u32)(N >> 8);
-    data += blockIdx.z * J.dzs;
+    data += zb.z * J.dzs + zb.b * J.dbs;
     const ModConst mc = T.mc[mod];
     const size_t off = (size_t)limb * N + (size_t)tile * 16 * 256;
     u64* g = data + off;
-    const u64* ep_a = F.ep_a + blockIdx.z * F.ep_azs + off;
-    u64* ep_out = F.ep_out + blockIdx.z * F.ep_ozs + off;
+    const u64* ep_a = F.ep_a + zb.z * F.ep_azs + zb.b * F.ep_abs + off;
+    u64* ep_out = F.ep_out + zb.z * F.ep_ozs + zb.b * F.ep_obs + off;
     const u64 sv = F.s.v[blockIdx.y], svs = F.s.vs[blockIdx.y];
     if (use_fp(mc.q)) fwd_passB_body<true, true>(g, sm, tile, Rn, mc, T, mod, N, ep_a, ep_out, sv, svs);
     else fwd_passB_body<false, true>(g, sm, tile, Rn, mc, T, mod, N, ep_a, ep_out, sv, svs);
@@ -575,13 +588,14 @@ __device__ __forceinline__ void inv_passB_body(const u64* __restrict__ s_in, u64
 __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_B)
 ntt_inv_passB(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
     CKKS_SHARED u64 sm[kPassBData];
-    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
-    const int limb = J.rows[blockIdx.z][blockIdx.y], slimb = J.srows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const ZB zb = zb_split(J);
+    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][blockIdx.y], slimb = J.srows[zb.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][blockIdx.y];
     const size_t N = (size_t)1 << T.logn;
     const u32 Rn = (u32)(N >> 8);
-    src += blockIdx.z * J.szs;
-    dst += blockIdx.z * J.dzs;
+    src += zb.z * J.szs + zb.b * J.sbs;
+    dst += zb.z * J.dzs + zb.b * J.dbs;
     const ModConst mc = T.mc[mod];
     const u64* s_in = src + (size_t)slimb * N + (size_t)tile * 16 * 256;
     u64* d_out = dst + (size_t)limb * N + (size_t)tile * 16 * 256;
@@ -593,14 +607,15 @@ __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_B)
 ntt_inv_passB_mul(const u64* __restrict__ src, const u64* __restrict__ src2, u64* __restrict__ dst, const GRID_CONST NttJob J,
                   NttTables T) {
     CKKS_SHARED u64 sm[kPassBData];
-    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
-    const int limb = J.rows[blockIdx.z][blockIdx.y], slimb = J.srows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const ZB zb = zb_split(J);
+    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][blockIdx.y], slimb = J.srows[zb.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][blockIdx.y];
     const size_t N = (size_t)1 << T.logn;
     const u32 Rn = (u32)(N >> 8);
-    src += blockIdx.z * J.szs;
-    src2 += blockIdx.z * J.szs;
-    dst += blockIdx.z * J.dzs;
+    src += zb.z * J.szs + zb.b * J.sbs;
+    src2 += zb.z * J.szs + zb.b * J.s2bs;
+    dst += zb.z * J.dzs + zb.b * J.dbs;
     const ModConst mc = T.mc[mod];
     const size_t off = (size_t)slimb * N + (size_t)tile * 16 * 256;
     u64* d_out = dst + (size_t)limb * N + (size_t)tile * 16 * 256;
@@ -706,11 +721,12 @@ template <int LOGR>
 __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_A)
 ntt_inv_passA(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
     CKKS_SHARED __align__(16) u64 sm[kPassAWords];
-    if (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) return;
-    const int limb = J.rows[blockIdx.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[blockIdx.z][blockIdx.y];
+    const ZB zb = zb_split(J);
+    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][blockIdx.y], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][blockIdx.y];
     const size_t N = (size_t)1 << T.logn;
-    data += blockIdx.z * J.dzs;
+    data += zb.z * J.dzs + zb.b * J.dbs;
     const ModConst mc = T.mc[mod];
     if (use_fp(mc.q)) inv_passA_body<LOGR, true>(data, sm, limb, tile, N, mc, T, mod);
     else inv_passA_body<LOGR, false>(data, sm, limb, tile, N, mc, T, mod);
@@ -734,7 +750,7 @@ template <bool FP, bool PRO, bool EP>
 __device__ __forceinline__ void fwd_cluster_body(const u64* __restrict__ src, u64* __restrict__ dst, u64* sm, int limb,
                                                  int slimb, int tile, size_t N, const ModConst& mc, const NttTables& T,
                                                  int mod, u64 ql, const u64* __restrict__ ep_a, u64* __restrict__ ep_out,
-                                                 u64 sv, u64 svs) {
+                                                 u64 sv, u64 svs, bool active) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const u64 q = mc.q;
@@ -830,6 +846,7 @@ __device__ __forceinline__ void fwd_cluster_body(const u64* __restrict__ src, u6
         }
         __syncthreads();
         const size_t off = (size_t)limb * N + (size_t)tile * 32 * 256;
+        if (!active) return;                                    // surplus cluster of a ragged batch: no global store
         if (EP) {                                               // (a - NTT(x)) * s, as ntt_fwd_passB_ep
 #pragma unroll
             for (int k = 0; k < 16; k++)
@@ -842,10 +859,12 @@ __device__ __forceinline__ void fwd_cluster_body(const u64* __restrict__ src, u6
         }
     }
 }
-// y index of a CTA: no early exit -- every CTA of a cluster must reach the cluster barriers; a z-slice with fewer items than
-// the launch's y extent works on a clamped (repeated) item instead, writing the same values twice
-__device__ __forceinline__ int cluster_item(const NttJob& J) {
-    return (J.cnt[blockIdx.z] && blockIdx.y >= J.cnt[blockIdx.z]) ? J.cnt[blockIdx.z] - 1 : (int)blockIdx.y;
+// y index of a CTA: no early exit -- every CTA of a cluster must reach the cluster barriers.  A z-slice with fewer items than
+// the launch's y extent gives its surplus clusters a clamped (repeated) item to READ and sets active = false: they run the
+// barriers but store nothing (an in-place transform of a ragged batch would otherwise be transformed twice).
+__device__ __forceinline__ int cluster_item(const NttJob& J, const ZB& zb, bool& active) {
+    active = !(J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]);
+    return active ? (int)blockIdx.y : J.cnt[zb.z] - 1;
 }
 // forward transform with the rescale-lift prologue and / or the (a - NTT(x)) * s epilogue (NttFuse), one kernel
 template <bool PRO, bool EP>
@@ -853,19 +872,21 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kClThreads, 2)
 ntt_fwd_cluster_fused(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T,
                       const GRID_CONST NttFuse F) {
     extern __shared__ __align__(16) u64 sm_cl[];
-    const int y = cluster_item(J);
-    const int limb = J.rows[blockIdx.z][y], slimb = J.srows[blockIdx.z][y], tile = blockIdx.x;
-    const int mod = J.mods[blockIdx.z][y];
+    const ZB zb = zb_split(J);
+    bool active;
+    const int y = cluster_item(J, zb, active);
+    const int limb = J.rows[zb.z][y], slimb = J.srows[zb.z][y], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][y];
     const size_t N = (size_t)1 << T.logn;
-    src += blockIdx.z * J.szs;
-    dst += blockIdx.z * J.dzs;
+    src += zb.z * J.szs + zb.b * J.sbs;
+    dst += zb.z * J.dzs + zb.b * J.dbs;
     const ModConst mc = T.mc[mod];
     const u64 ql = PRO ? T.mc[F.pro_mod].q : 0;
-    const u64* ep_a = EP ? F.ep_a + blockIdx.z * F.ep_azs : nullptr;
-    u64* ep_out = EP ? F.ep_out + blockIdx.z * F.ep_ozs : nullptr;
+    const u64* ep_a = EP ? F.ep_a + zb.z * F.ep_azs + zb.b * F.ep_abs : nullptr;
+    u64* ep_out = EP ? F.ep_out + zb.z * F.ep_ozs + zb.b * F.ep_obs : nullptr;
     const u64 sv = EP ? F.s.v[y] : 0, svs = EP ? F.s.vs[y] : 0;
-    if (use_fp(mc.q)) fwd_cluster_body<true, PRO, EP>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, ql, ep_a, ep_out, sv, svs);
-    else fwd_cluster_body<false, PRO, EP>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, ql, ep_a, ep_out, sv, svs);
+    if (use_fp(mc.q)) fwd_cluster_body<true, PRO, EP>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, ql, ep_a, ep_out, sv, svs, active);
+    else fwd_cluster_body<false, PRO, EP>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, ql, ep_a, ep_out, sv, svs, active);
 }
 
 // ============================================================================================ inverse, ONE kernel per transform
@@ -875,7 +896,7 @@ ntt_fwd_cluster_fused(const u64* __restrict__ src, u64* __restrict__ dst, const 
 template <bool FP, bool MUL>
 __device__ __forceinline__ void inv_cluster_body(const u64* __restrict__ src, const u64* __restrict__ src2,
                                                  u64* __restrict__ dst, u64* sm, int limb, int slimb, int tile, size_t N,
-                                                 const ModConst& mc, const NttTables& T, int mod) {
+                                                 const ModConst& mc, const NttTables& T, int mod, bool active) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const u64 q = mc.q;
@@ -941,6 +962,7 @@ __device__ __forceinline__ void inv_cluster_body(const u64* __restrict__ src, co
     }
     {
         // ---- pass A^-1: 32 columns x 256 rows, 1/N folded into the last stage
+        if (!active) return;                                    // surplus cluster of a ragged batch: no global store
         const int c = tid % 32, rr = tid / 32;
         const TwLin<1> t2{tw, tc, (u32)rr};
         const TwLin<0> t1{tw, tc, 0u};
@@ -979,52 +1001,58 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kClThreads, 2)
 ntt_inv_cluster(const u64* __restrict__ src, const u64* __restrict__ src2, u64* __restrict__ dst, const GRID_CONST NttJob J,
                 NttTables T) {
     extern __shared__ __align__(16) u64 sm_cl[];
-    const int y = cluster_item(J);
-    const int limb = J.rows[blockIdx.z][y], slimb = J.srows[blockIdx.z][y], tile = blockIdx.x;
-    const int mod = J.mods[blockIdx.z][y];
+    const ZB zb = zb_split(J);
+    bool active;
+    const int y = cluster_item(J, zb, active);
+    const int limb = J.rows[zb.z][y], slimb = J.srows[zb.z][y], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][y];
     const size_t N = (size_t)1 << T.logn;
-    src += blockIdx.z * J.szs;
-    if (MUL) src2 += blockIdx.z * J.szs;
-    dst += blockIdx.z * J.dzs;
+    src += zb.z * J.szs + zb.b * J.sbs;
+    if (MUL) src2 += zb.z * J.szs + zb.b * J.s2bs;
+    dst += zb.z * J.dzs + zb.b * J.dbs;
     const ModConst mc = T.mc[mod];
-    if (use_fp(mc.q)) inv_cluster_body<true, MUL>(src, src2, dst, sm_cl, limb, slimb, tile, N, mc, T, mod);
-    else inv_cluster_body<false, MUL>(src, src2, dst, sm_cl, limb, slimb, tile, N, mc, T, mod);
+    if (use_fp(mc.q)) inv_cluster_body<true, MUL>(src, src2, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, active);
+    else inv_cluster_body<false, MUL>(src, src2, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, active);
 }
 
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kClThreads, 2)
 ntt_fwd_cluster(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
     extern __shared__ __align__(16) u64 sm_cl[];
-    const int y = cluster_item(J);
-    const int limb = J.rows[blockIdx.z][y], slimb = J.srows[blockIdx.z][y], tile = blockIdx.x;
-    const int mod = J.mods[blockIdx.z][y];
+    const ZB zb = zb_split(J);
+    bool active;
+    const int y = cluster_item(J, zb, active);
+    const int limb = J.rows[zb.z][y], slimb = J.srows[zb.z][y], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][y];
     const size_t N = (size_t)1 << T.logn;
-    src += blockIdx.z * J.szs;
-    dst += blockIdx.z * J.dzs;
+    src += zb.z * J.szs + zb.b * J.sbs;
+    dst += zb.z * J.dzs + zb.b * J.dbs;
     const ModConst mc = T.mc[mod];
-    if (use_fp(mc.q)) fwd_cluster_body<true, false, false>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, 0, nullptr, nullptr, 0, 0);
-    else fwd_cluster_body<false, false, false>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, 0, nullptr, nullptr, 0, 0);
+    if (use_fp(mc.q)) fwd_cluster_body<true, false, false>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, 0, nullptr, nullptr, 0, 0, active);
+    else fwd_cluster_body<false, false, false>(src, dst, sm_cl, limb, slimb, tile, N, mc, T, mod, 0, nullptr, nullptr, 0, 0, active);
 }
 #endif
 
 }  // namespace
 
-bool g_ntt_cluster = false;       // CKKS_NTT_CLUSTER=1 (engine constructor): forward transforms at N = 2^16 in one kernel
-bool g_ntt_cluster_all = false;   // CKKS_NTT_CLUSTER=2: also the fused forward variants and the inverse (not yet run on hardware)
-void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st) {
-    if (J.n == 0 || J.nz == 0) return;
+static inline int nbz(const NttJob& J) { return J.nz * (J.nb > 1 ? J.nb : 1); }
+static NttJob norm(const NttJob& J) { NttJob K = J; if (K.nb < 1) K.nb = 1; return K; }
+
+void ntt_forward(const u64* src, u64* dst, const NttJob& J0, const NttTables& T, dev_stream st) {
+    if (J0.n == 0 || J0.nz == 0) return;
+    const NttJob J = norm(J0);
 #ifndef CKKS_EMU
-    if (g_ntt_cluster && T.logn == 16) {
-        LAUNCH_DYN(ntt_fwd_cluster, dim3(8, J.n, J.nz), dim3(kClThreads), kClWords * sizeof(u64), st, src, dst, J, T);
+    if (T.cluster >= 1 && T.logn == 16) {
+        LAUNCH_DYN(ntt_fwd_cluster, dim3(8, J.n, nbz(J)), dim3(kClThreads), kClWords * sizeof(u64), st, src, dst, J, T);
         return;
     }
 #endif
     const unsigned R = 1u << (T.logn - 8);
-    dim3 gridB(R / 16, J.n, J.nz);
+    dim3 gridB(R / 16, J.n, nbz(J));
     if (T.logn == 16) {
-        dim3 gridA(16, J.n, J.nz);
+        dim3 gridA(16, J.n, nbz(J));
         LAUNCH(ntt_fwd_passA<8>, gridA, dim3(kThreads), st, src, dst, J, T);
     } else if (T.logn == 12) {
-        dim3 gridA(1, J.n, J.nz);
+        dim3 gridA(1, J.n, nbz(J));
         LAUNCH(ntt_fwd_passA<4>, gridA, dim3(kThreads), st, src, dst, J, T);
     } else {
         throw std::runtime_error("ntt: only N = 2^16 and N = 2^12 are built");
@@ -1032,11 +1060,12 @@ void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, 
     LAUNCH(ntt_fwd_passB, gridB, dim3(kThreads), st, dst, J, T);
 }
 
-void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J, const NttTables& T, const NttFuse& F, dev_stream st) {
-    if (J.n == 0 || J.nz == 0) return;
+void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J0, const NttTables& T, const NttFuse& F, dev_stream st) {
+    if (J0.n == 0 || J0.nz == 0) return;
+    const NttJob J = norm(J0);
 #ifndef CKKS_EMU
-    if (g_ntt_cluster_all && T.logn == 16) {
-        const dim3 g(8, J.n, J.nz), b(kClThreads);
+    if (T.cluster >= 2 && T.logn == 16) {
+        const dim3 g(8, J.n, nbz(J)), b(kClThreads);
         const size_t smem = kClWords * sizeof(u64);
         const bool pro = F.pro_mod >= 0, ep = F.ep_out != nullptr;
         if (pro && ep) LAUNCH_DYN((ntt_fwd_cluster_fused<true, true>), g, b, smem, st, src, dst, J, T, F);
@@ -1047,9 +1076,9 @@ void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J, const NttTable
     }
 #endif
     const unsigned R = 1u << (T.logn - 8);
-    dim3 gridB(R / 16, J.n, J.nz);
+    dim3 gridB(R / 16, J.n, nbz(J));
     if (T.logn != 16 && T.logn != 12) throw std::runtime_error("ntt: only N = 2^16 and N = 2^12 are built");
-    dim3 gridA(T.logn == 16 ? 16 : 1, J.n, J.nz);
+    dim3 gridA(T.logn == 16 ? 16 : 1, J.n, nbz(J));
     if (F.pro_mod >= 0) {
         if (T.logn == 16) LAUNCH(ntt_fwd_passA_lift<8>, gridA, dim3(kThreads), st, src, dst, J, T, F.pro_mod);
         else LAUNCH(ntt_fwd_passA_lift<4>, gridA, dim3(kThreads), st, src, dst, J, T, F.pro_mod);
@@ -1061,11 +1090,12 @@ void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J, const NttTable
     else LAUNCH(ntt_fwd_passB, gridB, dim3(kThreads), st, dst, J, T);
 }
 
-void ntt_inverse(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st, const u64* src2) {
-    if (J.n == 0 || J.nz == 0) return;
+void ntt_inverse(const u64* src, u64* dst, const NttJob& J0, const NttTables& T, dev_stream st, const u64* src2) {
+    if (J0.n == 0 || J0.nz == 0) return;
+    const NttJob J = norm(J0);
 #ifndef CKKS_EMU
-    if (g_ntt_cluster_all && T.logn == 16) {
-        const dim3 g(8, J.n, J.nz), b(kClThreads);
+    if (T.cluster >= 2 && T.logn == 16) {
+        const dim3 g(8, J.n, nbz(J)), b(kClThreads);
         const size_t smem = kClWords * sizeof(u64);
         if (src2) LAUNCH_DYN(ntt_inv_cluster<true>, g, b, smem, st, src, src2, dst, J, T);
         else LAUNCH_DYN(ntt_inv_cluster<false>, g, b, smem, st, src, src2, dst, J, T);
@@ -1073,14 +1103,14 @@ void ntt_inverse(const u64* src, u64* dst, const NttJob& J, const NttTables& T, 
     }
 #endif
     const unsigned R = 1u << (T.logn - 8);
-    dim3 gridB(R / 16, J.n, J.nz);
+    dim3 gridB(R / 16, J.n, nbz(J));
     if (src2) LAUNCH(ntt_inv_passB_mul, gridB, dim3(kThreads), st, src, src2, dst, J, T);
     else LAUNCH(ntt_inv_passB, gridB, dim3(kThreads), st, src, dst, J, T);
     if (T.logn == 16) {
-        dim3 gridA(16, J.n, J.nz);
+        dim3 gridA(16, J.n, nbz(J));
         LAUNCH(ntt_inv_passA<8>, gridA, dim3(kThreads), st, dst, J, T);
     } else if (T.logn == 12) {
-        dim3 gridA(1, J.n, J.nz);
+        dim3 gridA(1, J.n, nbz(J));
         LAUNCH(ntt_inv_passA<4>, gridA, dim3(kThreads), st, dst, J, T);
     } else {
         throw std::runtime_error("ntt: only N = 2^16 and N = 2^12 are built");

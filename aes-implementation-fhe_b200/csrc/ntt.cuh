@@ -15,6 +15,8 @@ struct NttTables {
     const double* inv_q;
     const ModConst* mc;
     int logn;
+    int cluster;     // 0: two-pass kernels; 1: single-kernel (8-CTA cluster) forward transform at N = 2^16; 2: also the fused
+                     // forward variants and the inverse.  Per engine (CKKS_NTT_CLUSTER is read by the Engine constructor).
 };
 
 // One batched transform: for z-slice z, item i reads source row srows[z][i] of src + z*szs and
@@ -22,9 +24,13 @@ struct NttTables {
 // mc[mods[z][i]].  The first pass goes src -> dst, the second runs in place on dst; src may equal dst
 // when srows == rows.
 #define NTT_MAX_Z 6
+// Batched ciphertexts: the whole job is repeated for nb batch items at src + b*sbs / dst + b*dbs (the grid's z extent is
+// nz * nb, batch-major); nb = 0 means 1.
 struct NttJob {
     int n, nz;
+    int nb;
     size_t szs, dzs;
+    size_t sbs, dbs, s2bs;            // batch strides (elements) of src, dst and the second source of ntt_inverse
     unsigned char mods[NTT_MAX_Z][CKKS_MAX_MODULI];
     unsigned char rows[NTT_MAX_Z][CKKS_MAX_MODULI];
     unsigned char srows[NTT_MAX_Z][CKKS_MAX_MODULI];
@@ -43,6 +49,7 @@ struct NttFuse {
     const u64* ep_a;
     u64* ep_out;
     size_t ep_azs, ep_ozs;
+    size_t ep_abs = 0, ep_obs = 0;    // batch strides of ep_a / ep_out
     ScalarList s;
 };
 
@@ -50,5 +57,3 @@ void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, 
 void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J, const NttTables& T, const NttFuse& F, dev_stream st);
 // src2 != null: the inverse transform of the row-wise product src * src2 (the d2 of a ct x ct, never stored)
 void ntt_inverse(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st, const u64* src2 = nullptr);
-extern bool g_ntt_cluster;       // experimental single-kernel forward transform (ntt.cu)
-extern bool g_ntt_cluster_all;   // ... plus its fused variants and the inverse (not yet run on hardware)

@@ -70,6 +70,11 @@ class Ciphertext:
     def polynomial_count(self) -> int:
         return self._eng._lib.ckks_ct_npoly(self._h)
 
+    @property
+    def batch(self) -> int:
+        """Independent ciphertexts of this shape held by the handle (1 unless created by a batched entry point)."""
+        return self._eng._lib.ckks_ct_batch(self._h)
+
     def __del__(self):
         eng, h = self._eng, self._h
         if h and eng is not None and eng._ptr:
@@ -195,7 +200,7 @@ class CapturedCall:
 class Engine:
     def __init__(self, *, mode: str = "gpu", use_bootstrap: bool = False, use_multiparty: bool = False,
                  thread_count: Optional[int] = None, device_id: int = 0, max_level: Optional[int] = None,
-                 seed: int = 1, **overrides):
+                 seed: Optional[int] = None, **overrides):
         if use_multiparty:
             raise NotImplementedError("multiparty keys are outside the AES path (SURVEY.md 8)")
         if mode not in ("gpu", "cpu", "parallel"):
@@ -205,6 +210,13 @@ class Engine:
                           "cuda:%d" % (mode, device_id), stacklevel=2)
         self._lib = _capi.load()
         self._ptr = None
+        # key material and encryption randomness derive from `seed`: OS entropy unless the caller fixes it (the parity
+        # tests and the oracle comparison do, to reproduce keys bit for bit; a multi-GPU job shares one seed so every
+        # rank derives the same secret key).  The stream generator itself is a counter-based SplitMix64:
+        # statistically sound, NOT a cryptographic generator -- `ckks_export_secret` and fixed seeds are test-only.
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little") >> 1
+        self.seed = int(seed)
         cfg = dict(DEFAULTS)
         if max_level is not None:
             cfg["levels"] = int(max_level)
@@ -387,13 +399,29 @@ class Engine:
         return Plaintext(self, vec)
 
     def encrypt(self, data, pk: Optional[PublicKey] = None, level: int = -1) -> Ciphertext:
+        """A 2-D `data` (nb, slots) gives ONE batched ciphertext of nb independent items (see `Ciphertext.batch`)."""
+        if np.ndim(data) == 2:
+            z = np.ascontiguousarray(np.stack([self._as_slots(row) for row in np.asarray(data)]))
+            return self._new(self._lib.ckks_encrypt_batch, z.view(np.float64).reshape(-1), z.shape[0], level)
         z = self._as_slots(data)
         return self._new(self._lib.ckks_encrypt, z.view(np.float64), level)
 
     def decrypt(self, ct: Ciphertext, sk: Optional[SecretKey] = None) -> np.ndarray:
-        out = np.empty(2 * self.slot_count, dtype=np.float64)
+        """complex128[slot_count]; (batch, slot_count) for a batched ciphertext."""
+        nb = ct.batch
+        out = np.empty(nb * 2 * self.slot_count, dtype=np.float64)
         _capi.check(self._lib.ckks_decrypt(self._ptr, ct._h, out))
-        return out.view(np.complex128)
+        z = out.view(np.complex128)
+        return z if nb == 1 else z.reshape(nb, self.slot_count)
+
+    def stack(self, cts: Sequence[Ciphertext]) -> Ciphertext:
+        """Unbatched ciphertexts of one shape -> one batched ciphertext (copies); every later operation on it runs
+        all items through one set of kernel launches."""
+        arr = (C.c_void_p * len(cts))(*[c._h for c in cts])
+        return self._new(self._lib.ckks_ct_stack, arr, len(cts))
+
+    def unstack(self, ct: Ciphertext) -> List[Ciphertext]:
+        return [self._new(self._lib.ckks_ct_item, ct._h, i) for i in range(ct.batch)]
 
     # ------------------------------------------------------------------ wire format (SURVEY.md 8f-4: transciphering clients)
     _MAGIC = b"CKB2"
@@ -409,6 +437,8 @@ class Engine:
     def serialize_ciphertext(self, ct: Ciphertext) -> bytes:
         """Header (magic, logN, polynomial count, level, chain fingerprint) + the residues [npoly][level+1][N] as
         little-endian uint64 in the engine's own layout (NTT domain, bit-reversed order)."""
+        if ct.batch != 1:
+            raise ValueError("serialize one item at a time (Engine.unstack)")
         npoly, level, n = ct.polynomial_count, ct.level, 2 * self.slot_count
         body = np.zeros((npoly, level + 1, n), dtype=np.uint64)
         _capi.check(self._lib.ckks_ct_export(self._ptr, ct._h, body))
@@ -553,16 +583,22 @@ class Engine:
 
     def encrypt_zeta16(self, nibbles, level: int = -1) -> Ciphertext:
         """Encrypt the codewords exp(-2 pi i k / 16) of one nibble k per slot; the lookup runs on the device."""
-        nib = np.ascontiguousarray(np.asarray(nibbles, dtype=np.uint8).reshape(-1))
+        nib = np.asarray(nibbles, dtype=np.uint8)
+        if nib.ndim == 2:          # (nb, slots): one batched ciphertext
+            if nib.shape[1] != self.slot_count:
+                raise ValueError(f"expected {self.slot_count} nibbles per item")
+            return self._new(self._lib.ckks_encrypt_zeta16_batch, np.ascontiguousarray(nib).reshape(-1), nib.shape[0], int(level))
+        nib = np.ascontiguousarray(nib.reshape(-1))
         if nib.size != self.slot_count:
             raise ValueError(f"expected {self.slot_count} nibbles")
         return self._new(self._lib.ckks_encrypt_zeta16, nib, int(level))
 
     def decrypt_zeta16(self, ct: Ciphertext) -> np.ndarray:
-        """Index of the nearest zeta_16 codeword of every slot (uint8[slot_count])."""
-        out = np.empty(self.slot_count, dtype=np.uint8)
+        """Index of the nearest zeta_16 codeword of every slot: uint8[slot_count], (batch, slot_count) when batched."""
+        nb = ct.batch
+        out = np.empty(nb * self.slot_count, dtype=np.uint8)
         _capi.check(self._lib.ckks_decrypt_zeta16(self._ptr, ct._h, out))
-        return out
+        return out if nb == 1 else out.reshape(nb, self.slot_count)
 
     def lincomb(self, cts: Sequence[Ciphertext], coeffs) -> Ciphertext:
         """sum_k coeffs[k] * cts[k]: one fused multiply-accumulate + one rescale per distinct input level."""

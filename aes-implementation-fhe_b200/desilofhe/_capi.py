@@ -72,6 +72,11 @@ def load():
         "ckks_snap_zeta16": (i32, [vp, vp, i32, i32, pp]),
         "ckks_encrypt_zeta16": (i32, [vp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"), i32, pp]),
         "ckks_decrypt_zeta16": (i32, [vp, vp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")]),
+        "ckks_ct_batch": (i32, [vp]),
+        "ckks_encrypt_batch": (i32, [vp, dp, i32, i32, pp]),
+        "ckks_encrypt_zeta16_batch": (i32, [vp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"), i32, i32, pp]),
+        "ckks_ct_stack": (i32, [vp, pp, i32, pp]),
+        "ckks_ct_item": (i32, [vp, vp, i32, pp]),
         "ckks_ct_free": (None, [vp, vp]), "ckks_pt_free": (None, [vp, vp]),
         "ckks_ct_level": (i32, [vp]), "ckks_ct_npoly": (i32, [vp]), "ckks_pt_level": (i32, [vp]),
         "ckks_add": (i32, [vp, vp, vp, pp]), "ckks_sub": (i32, [vp, vp, vp, pp]),
@@ -95,6 +100,7 @@ def load():
         "ckks_arena_stats": (i32, [vp, C.POINTER(lng), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
         "ckks_ct_export": (i32, [vp, vp, u64p]),
         "ckks_ct_import": (i32, [vp, i32, i32, u64p, pp]),
+        "ckks_ct_import_batch": (i32, [vp, i32, i32, i32, u64p, pp]),
         "ckks_pt_export": (i32, [vp, vp, u64p]),
         "ckks_export_secret": (i32, [vp, i64p]),
         "ckks_export_public": (i32, [vp, u64p]),
@@ -120,6 +126,8 @@ def load():
         "ckks_bench_rotate": (i32, [vp, i32, i32, C.POINTER(C.c_float)]),
         "ckks_bench_rotate_lanes": (i32, [vp, i32, i32, i32, C.POINTER(C.c_float)]),
         "ckks_bench_mul": (i32, [vp, i32, i32, C.POINTER(C.c_float)]),
+        "ckks_bench_rotate_batch": (i32, [vp, i32, i32, i32, C.POINTER(C.c_float)]),
+        "ckks_bench_mul_batch": (i32, [vp, i32, i32, i32, C.POINTER(C.c_float)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)        # AttributeError here = the library does not export the ABI

@@ -93,6 +93,17 @@ int ckks_snap_zeta16(ckks_engine* e, const ckks_ct* ct, int level, int stride, c
  * returns the index of the nearest codeword of every slot.  16 x fewer bytes over PCIe than complex128 slots. */
 int ckks_encrypt_zeta16(ckks_engine* e, const uint8_t* nibbles, int level, ckks_ct** out);
 int ckks_decrypt_zeta16(ckks_engine* e, const ckks_ct* ct, uint8_t* nibbles_out);
+/* ---- batched ciphertexts (BASELINE.json configs[4]: "many ciphertexts"; reference test/test_aes_pipeline_roundtrip.py
+ * processes ONE ciphertext pair).  A handle may hold nb INDEPENDENT ciphertexts of one shape; every operation below
+ * (arithmetic, key switches, LUTs, bootstrap, snap) then acts on all items with one set of kernel launches, item i of the
+ * result being bit-identical to the operation on item i alone; an nb = 1 operand of a binary operation is broadcast
+ * (a round-key ciphertext shared by all pairs).  The *_batch encryptions take nb consecutive slot / nibble vectors;
+ * ckks_decrypt, ckks_decrypt_zeta16 and ckks_ct_export write ckks_ct_batch(ct) consecutive vectors. */
+int ckks_ct_batch(const ckks_ct* ct);
+int ckks_encrypt_batch(ckks_engine* e, const double* slots_re_im /* [nb][2 slot_count] */, int nb, int level, ckks_ct** out);
+int ckks_encrypt_zeta16_batch(ckks_engine* e, const uint8_t* nibbles /* [nb][slot_count] */, int nb, int level, ckks_ct** out);
+int ckks_ct_stack(ckks_engine* e, ckks_ct* const* items /* n unbatched ciphertexts of one shape */, int n, ckks_ct** out);
+int ckks_ct_item(ckks_engine* e, const ckks_ct* ct, int index, ckks_ct** out /* copy of one item, nb = 1 */);
 void ckks_ct_free(ckks_engine* e, ckks_ct* ct);
 void ckks_pt_free(ckks_engine* e, ckks_pt* pt);
 int ckks_ct_level(const ckks_ct* ct);
@@ -148,8 +159,9 @@ int ckks_counters(const ckks_engine* e, long* out5);
 int ckks_arena_stats(const ckks_engine* e, long* driver_allocs, size_t* arena_bytes, size_t* cached_bytes);
 
 /* ---- raw access for the bit-exact parity tests against oracle/ (tests/ only; not used by the shim's hot path) */
-int ckks_ct_export(ckks_engine* e, const ckks_ct* ct, uint64_t* out /* [npoly][level+1][N] */);
+int ckks_ct_export(ckks_engine* e, const ckks_ct* ct, uint64_t* out /* [nb][npoly][level+1][N] */);
 int ckks_ct_import(ckks_engine* e, int npoly, int level, const uint64_t* data, ckks_ct** out);
+int ckks_ct_import_batch(ckks_engine* e, int nb, int npoly, int level, const uint64_t* data, ckks_ct** out);
 int ckks_pt_export(ckks_engine* e, const ckks_pt* pt, uint64_t* out /* [level+1][N] */);
 int ckks_export_secret(ckks_engine* e, int64_t* coef_out /* [N] */);
 int ckks_export_public(ckks_engine* e, uint64_t* out /* [2][L+1][N] */);
@@ -196,6 +208,9 @@ int ckks_bench_rotate(ckks_engine* e, int level, int iters, float* ms_out);
 /* `lanes` independent ciphertexts rotated concurrently on stream lanes: milliseconds per rotation (throughput) */
 int ckks_bench_rotate_lanes(ckks_engine* e, int level, int lanes, int iters, float* ms_per_rotation);
 int ckks_bench_mul(ckks_engine* e, int level, int iters, float* ms_out);
+/* one rotation / one ct*ct multiplication of a batched ciphertext of nb items: milliseconds per CALL (nb items each) */
+int ckks_bench_rotate_batch(ckks_engine* e, int level, int nb, int iters, float* ms_out);
+int ckks_bench_mul_batch(ckks_engine* e, int level, int nb, int iters, float* ms_out);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,7 @@ def boot_ctx(request):
     which, logn, hw = request.param
     mod = backend.use_emulation() if which == "emu" else backend.use_cuda()
     ctx = aes_fhe.EngineContext(1, mode="gpu", thread_count=1, backend=mod, logn=logn, levels=21, fresh_level=14,
-                                hamming_weight=hw)
+                                hamming_weight=hw, seed=1)
     return which, ctx
 
 
@@ -152,6 +152,40 @@ def test_config5_batched_fips_round(boot_ctx):
     rk_ct = pipe._prepare_round_keys([drv._perm(rk) for rk in rks])
     out = pipe.encrypt_round(*pipe.encoder.encode(drv._perm(blocks)), *rk_ct[1])
     assert np.array_equal(drv.decode(*out), plain_round(blocks, rks[1]))
+
+
+def test_config5_many_pairs_in_one_batched_handle(boot_ctx):
+    """configs[4]: "many ciphertexts" -- P ciphertext pairs travel as ONE batched handle pair (Ciphertext.batch = P), so every
+    step of the round (LUTs, key switches, renorms, both bootstraps) runs all pairs through one set of kernel launches;
+    the round keys stay unbatched and are broadcast.  Every block of every pair equals the plain FIPS-197 round, eagerly
+    and as a captured graph replayed on other inputs."""
+    which, ctx = boot_ctx
+    pipe = make_pipe(ctx)
+    drv = aes_fhe.FipsDriver(pipe, batched=True)
+    eng = ctx.engine
+    stride = eng.slot_count // 16
+    P = 2
+    rng = np.random.default_rng(55)
+    blocks = rng.integers(0, 256, (P, stride, 16), dtype=np.uint8)
+    other = rng.integers(0, 256, (P, stride, 16), dtype=np.uint8)
+    key = np.frombuffer(bytes.fromhex("000102030405060708090a0b0c0d0e0f"), dtype=np.uint8)
+    rks = aes_fhe.expand_aes128_key(key)
+    rk_ct = pipe._prepare_round_keys([drv._perm(rk) for rk in rks])
+    ct = pipe.encoder.encode(drv._perm(blocks))
+    assert ct[0].batch == P and rk_ct[1][0].batch == 1
+    k0 = eng.counters()
+    out = pipe.encrypt_round(*ct, *rk_ct[1])
+    k1 = eng.counters()
+    assert out[0].batch == P and k1["bootstrap"] - k0["bootstrap"] == 2 * P
+    got = drv.decode(*out)
+    assert got.shape == (P, stride, 16)
+    for j in range(P):
+        assert np.array_equal(got[j], plain_round(blocks[j], rks[1]))
+    rnd = aes_fhe.CapturedRound(pipe, ct, rk_ct[1])
+    got = drv.decode(*rnd(*pipe.encoder.encode(drv._perm(other)), *rk_ct[2]))
+    for j in range(P):
+        assert np.array_equal(got[j], plain_round(other[j], rks[2]))
+    rnd.close()
 
 
 def test_device_zeta16_codec_equals_the_host_codec(boot_ctx):
