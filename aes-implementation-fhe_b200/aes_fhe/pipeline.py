@@ -121,12 +121,29 @@ class AESPipeline:
             ct = self._renorm_pair(*ct, depth=need)
         return ct
 
+    # ---- the first and the last round of both directions (pipeline.py:135-138,174-187 / README.md:85-95) ----
+    def encrypt_first(self, ct_hi, ct_lo, key_hi, key_lo) -> Pair:
+        return self._renorm_pair(*self.add_round_key(ct_hi, ct_lo, key_hi, key_lo), depth=SUBBYTES_DEPTH)
+
+    def encrypt_last(self, ct_hi, ct_lo, key_hi, key_lo) -> Pair:
+        ct = self._renorm_pair(*self.sub_bytes(ct_hi, ct_lo), depth=SHIFTROWS_DEPTH + XOR4_DEPTH)
+        return self._renorm_pair(*self.add_round_key(*self.shift_rows(*ct), key_hi, key_lo))
+
+    def decrypt_first(self, ct_hi, ct_lo, key_hi, key_lo) -> Pair:
+        return self._renorm_pair(*self.add_round_key(ct_hi, ct_lo, key_hi, key_lo), depth=SHIFTROWS_DEPTH + SUBBYTES_DEPTH)
+
+    def decrypt_last(self, ct_hi, ct_lo, key_hi, key_lo) -> Pair:
+        ct = self.inv_sub_bytes(*self.inv_shift_rows(ct_hi, ct_lo))
+        ct = self._renorm_pair(*ct, depth=XOR4_DEPTH)
+        return self._renorm_pair(*self.add_round_key(*ct, key_hi, key_lo))
+
     def _captured(self, which: str, state: Pair, key: Pair) -> "CapturedRound":
-        """The middle round of one direction recorded as a CUDA graph on first use (same shapes afterwards)."""
+        """One round of one direction ("enc" / "dec": the middle round; "enc_first", "enc_last", "dec_first",
+        "dec_last") recorded as a CUDA graph on first use (same shapes and batch size afterwards)."""
         cache = self.__dict__.setdefault("_round_graphs", {})
-        sig = (which, state[0].level, state[1].level, key[0].level, key[1].level)
+        sig = (which, state[0].level, state[1].level, key[0].level, key[1].level, getattr(state[0], "batch", 1))
         if sig not in cache:
-            cache[sig] = CapturedRound(self, state, key, inverse=(which == "dec"))
+            cache[sig] = CapturedRound(self, state, key, which=which)
         return cache[sig]
 
     def release_graphs(self) -> None:
@@ -139,14 +156,7 @@ class AESPipeline:
         graph input); the result is bit-identical to the eager flow up to the encryption randomness of the renorms."""
         if captured and debug is None:
             ct = self.encoder.encode(np.asarray(state, dtype=np.uint8))
-            rk = self._prepare_round_keys(round_keys)
-            ct = self._renorm_pair(*self.add_round_key(*ct, *rk[0]), depth=SUBBYTES_DEPTH)
-            for r in range(1, 10):
-                # the graph's static outputs feed its static inputs: the copy is enqueued before the next replay
-                ct = self._captured("enc", ct, rk[r])(*ct, *rk[r])
-            ct = self._renorm_pair(*self.sub_bytes(*ct), depth=SHIFTROWS_DEPTH + XOR4_DEPTH)
-            ct = self.add_round_key(*self.shift_rows(*ct), *rk[10])
-            return self._renorm_pair(*ct)
+            return self.encrypt_resident(ct, self._prepare_round_keys(round_keys))
         if debug is not None:
             debug.clear()
         ct = self.encoder.encode(np.asarray(state, dtype=np.uint8))
@@ -169,6 +179,16 @@ class AESPipeline:
         ct = self._renorm_pair(*ct)
         self._log_pair(debug, "enc.output", *ct)
         return ct
+
+    def encrypt_resident(self, ct: Pair, rk: List[Pair]) -> Pair:
+        """The ten rounds of `encrypt` on a state pair that is already encrypted, as eleven graph replays: the first
+        round, nine replays of ONE recorded middle round (the round key is a graph input), the last round.  Bit-identical
+        to the eager flow up to the encryption randomness of the renorms."""
+        ct = self._captured("enc_first", ct, rk[0])(*ct, *rk[0])
+        for r in range(1, 10):
+            # the graph's static outputs feed its static inputs: the copy is enqueued before the next replay
+            ct = self._captured("enc", ct, rk[r])(*ct, *rk[r])
+        return self._captured("enc_last", ct, rk[10])(*ct, *rk[10])
 
     def decrypt(self, ct_hi, ct_lo, round_keys, debug: Optional[Dict[str, Any]] = None) -> Pair:
         """As shipped (pipeline.py:193-254): no InvMixColumns in the round loop."""
@@ -206,14 +226,16 @@ def decrypt_readme_order(pipe, ct_hi, ct_lo, round_keys, captured: bool = False)
     (README.md:85-95), using only the pipeline's own primitives.  `captured=True`: the nine middle rounds are replays
     of one recorded round graph."""
     rk = pipe._prepare_round_keys(round_keys)
+    if captured:
+        ct = pipe._captured("dec_first", (ct_hi, ct_lo), rk[10])(ct_hi, ct_lo, *rk[10])
+        for r in range(9, 0, -1):
+            ct = pipe._captured("dec", ct, rk[r])(*ct, *rk[r])
+        return pipe._captured("dec_last", ct, rk[0])(*ct, *rk[0])
     need = SHIFTROWS_DEPTH + SUBBYTES_DEPTH           # levels InvShiftRows + InvSubBytes consume
     ct = pipe.add_round_key(ct_hi, ct_lo, *rk[10])
     ct = pipe._renorm_pair(*ct, depth=need)
     for r in range(9, 0, -1):
-        if captured:
-            ct = pipe._captured("dec", ct, rk[r])(*ct, *rk[r])
-        else:
-            ct = pipe.decrypt_round(*ct, *rk[r])
+        ct = pipe.decrypt_round(*ct, *rk[r])
     ct = pipe.inv_shift_rows(*ct)
     ct = pipe.inv_sub_bytes(*ct)
     ct = pipe._renorm_pair(*ct, depth=XOR4_DEPTH)
@@ -347,12 +369,16 @@ class CapturedRound:
     ciphertext pairs replay concurrently on separate replay streams.  Needs the device-side hard renorm (no host round
     trip inside the round) and an engine with `capture` (the B200 engine); there is no fallback."""
 
-    def __init__(self, pipe: AESPipeline, state: Pair, round_key: Pair, inverse: bool = False):
+    ROUNDS = {"enc": "encrypt_round", "dec": "decrypt_round", "enc_first": "encrypt_first", "enc_last": "encrypt_last",
+              "dec_first": "decrypt_first", "dec_last": "decrypt_last"}
+
+    def __init__(self, pipe: AESPipeline, state: Pair, round_key: Pair, inverse: bool = False, which: Optional[str] = None):
         if not getattr(pipe.ctx, "device_renorm", False) and pipe.use_hard_renorm_between_steps:
             raise RuntimeError("a captured round needs the device-side renorm (fused engine)")
         self.pipe = pipe
-        self.inverse = inverse       # True: the README-order decryption round (`AESPipeline.decrypt_round`)
-        fn = pipe.decrypt_round if inverse else pipe.encrypt_round
+        self.which = which or ("dec" if inverse else "enc")     # "dec": the README-order decryption round
+        self.inverse = self.which.startswith("dec")
+        fn = getattr(pipe, self.ROUNDS[self.which])
         self.call = pipe.ctx.engine.capture(fn, [*state, *round_key])
 
     def __call__(self, ct_hi, ct_lo, key_hi, key_lo, stream: int = 0) -> Pair:

@@ -1,27 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- AES-128-over-CKKS throughput on the B200-native engine (driver contract in the task statement).
 
-Workload (BASELINE.json configs[1]): ONE AES-128 encryption round -- SubBytes (two degree-255 LUT polynomials),
-hard renorm, ShiftRows (masked rotates), MixColumns (GF*2/GF*3 bivariate LUTs, rotations, three XOR4 LUTs with
-renorm, two bootstraps), AddRoundKey (two XOR4 LUTs), hard renorm -- on `--pairs` ciphertext pairs per GPU at N = 2^16,
-every one of the 2048 stride positions of a pair carrying an independent block (batched encoder), i.e.
-the reference's `pipeline.py:143-151` flow issued through the host mirror `aes_fhe` onto the `desilofhe` drop-in.
+Workload (BASELINE.json configs[4], the configuration the blocks/s metric is quoted on): FULL 10-round AES-128
+encryption, FIPS-197-exact, of `--pairs` ciphertext pairs per GPU at N = 2^16, every one of the 2048 stride positions of
+a pair carrying an independent block (batched encoder): the reference's `pipeline.py:123-188` flow
+(initial AddRoundKey, nine middle rounds -- SubBytes, ShiftRows, MixColumns with two bootstraps, AddRoundKey, five hard
+renorms -- and the final round) issued through the host mirror `aes_fhe` onto the `desilofhe` drop-in.  The pairs travel
+as ONE batched handle pair (`Ciphertext.batch` = pairs): every kernel launch carries all of them.
 
-  value  : blocks/s = gpus * pairs * 2048 blocks / (10 rounds * seconds per step); a step is the round on `--pairs`
-           independent ciphertext pairs per GPU (BASELINE.json configs[4]: "many ciphertexts"), each pair's round
-           recorded once as a CUDA graph (about 8 000 launches over nested stream lanes) and replayed on its own stream, so
-           the device overlaps the small kernels of different pairs; states, round-key ciphertexts and all evaluation
-           keys resident in HBM when the timed region starts.  `--no-graph` issues the round eagerly (one pair).
-  e2e    : same metric with the step starting from HOST bytes (batched encoder: nibbles H2D, zeta16 lookup + encrypt
-           on the device) and ending with decrypted bytes on the host (nearest-codeword nibbles D2H), through the
-           public API (`BatchedStateEncoder.encode` -> `CapturedRound` -> `FipsDriver.decode`).
-  s_per_round: latency of ONE pair's round (a single graph replay, nothing else on the device); dec_round: the same
-           for one README-order decryption round; rotations_per_s_n16: key-switch micro-benchmark at N = 2^16.
-  roofline: the NTT kernels (dominant), algorithmic bytes 2*N*8 per limb transform / CUDA-event time per call.
-  cpu_baseline: the oracle port of the same CKKS arithmetic on the host cores, bounded sample.
-
-`--impl reference` times the oracle port (the reference's own backend is the closed `desilofhe` wheel: not in
-/root/reference, not installable) on the host cores for the same metric.
+  value  : blocks/s = gpus * pairs * 2048 / seconds per step; a step is one whole AES-128 encryption of all pairs (eleven
+           CUDA-graph replays: first round, 9 x the recorded middle round, last round), states, round-key ciphertexts
+           and all evaluation keys resident in HBM when the timed region starts.  `--no-graph` issues it eagerly.
+  e2e    : the same with the step starting from HOST plaintext bytes (nibbles H2D, zeta16 lookup + encrypt on the
+           device) and ending with the AES ciphertext bytes decrypted back to the host, through the public API
+           (`FipsDriver.encrypt(captured=True)` -> `FipsDriver.decode`); checked against `cryptography` AES-ECB.
+  s_per_round / dec: latency of ONE replay of the middle round of each direction (all pairs); `dec` also times the full
+           10-round README-order decryption; rotations_per_s_n16: key-switch micro-benchmark at N = 2^16.
+  roofline: the NTT kernels (dominant), algorithmic bytes 2*N*8 per limb transform / CUDA-event time per call, taken on
+           the middle round at the bench's batch size; roofline_keyswitch: one batched rotation against SURVEY 8d's bytes.
+  cpu_baseline / --impl reference: the reference's call sequence EXECUTED on the oracle port (oracle/desilofhe_cpu.py)
+           on the host cores -- a bounded slice per step, scaled to a full encryption by its key-switch count.
 """
 from __future__ import annotations
 
@@ -44,9 +42,14 @@ import numpy as np
 LOGN, LEVELS, FRESH, DNUM, HW = 16, 21, 14, 3, 192
 ROUNDS_PER_BLOCK = 10
 METRIC = "aes128_fhe_blocks_per_s"
-UNIT = "blocks/s (2048 blocks per ciphertext pair, 10 round-equivalents per block)"
-WORKLOAD = ("configs[1]: one AES-128 encryption round (SubBytes, ShiftRows, MixColumns + 2 bootstraps, AddRoundKey, "
-            "5 hard renorms) on `pairs_per_gpu` independent ciphertext pairs per GPU, N=2^16, 2048 packed blocks per pair")
+UNIT = "blocks/s (full AES-128 encryptions of 16-byte blocks, 2048 blocks per ciphertext pair)"
+WORKLOAD = ("configs[4]: batched AES-128 transciphering -- full 10-round FIPS-197 AES-128 encryption (18 bootstraps, 48 hard "
+            "renorms per pair) of `pairs_per_gpu` ciphertext pairs per GPU carried by one batched handle pair, N=2^16, "
+            "2048 packed blocks per pair")
+# the reference's own call sequence for one AES-128 encryption (measured on the unchanged modules):
+# ct*ct (+relin+rescale), conjugations, rotations -- each one hybrid key switch -- and ct*plaintext products
+REF_KS_PER_ENCRYPTION = 9753 + 2908 + 114
+REF_PT_PER_ENCRYPTION = 12165
 
 
 # ------------------------------------------------------------------------------------------ plain AES round (checker)
@@ -125,60 +128,104 @@ class Clocks:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm (oracle port)
-def cpu_sample(n_mul: int = 24, n_conj: int = 8, threads: int = 0) -> dict:
-    """Seconds per key-switch-equivalent of the oracle port at the benchmark's parameters and fresh level."""
-    if threads:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
-    from oracle.ckks_oracle import OracleCKKS
-    from oracle.params import make_params
-    prm = make_params(logn=LOGN, levels=LEVELS, dnum=DNUM, hamming_weight=HW, fresh_level=FRESH)
-    orc = OracleCKKS(prm, seed=1)
-    orc.keygen_secret(); orc.keygen_public(); orc.keygen_relin()
-    orc.keygen_galois(orc.galois_conj())
-    rng = np.random.default_rng(0)
-    z = np.exp(2j * np.pi * rng.random(orc.n))
-    a, b = orc.encrypt(z), orc.encrypt(z)
-    orc.mul_ct(a, b)                                   # warm
-    t0 = time.perf_counter()
-    for _ in range(n_mul):
-        orc.mul_ct(a, b)
-    for _ in range(n_conj):
-        orc.conjugate(a)
-    dt = time.perf_counter() - t0
-    return {"s_per_ks": dt / (n_mul + n_conj), "seconds": dt, "n_mul": n_mul, "n_conj": n_conj,
-            "cores": os.cpu_count() if not threads else threads}
+class CpuArm:
+    """The reference's call sequence executed on the oracle port (oracle/desilofhe_cpu.py) on the host cores.
 
+    One step = a bounded slice of `XOR4LUT.apply` exactly as the reference issues it (xor4_lut.py:27-74 through the
+    host mirror with fused=False): make_power_basis(ct, 8) + 7 conjugations for ONE operand, then 16 LUT terms, each
+    multiply(A^p, B^q) + multiply(term, constant) + add -- 23 ct*ct, 7 conjugations, 16 ct*const at N = 2^16 from fresh
+    level-14 ciphertexts.  XOR4 evaluations are 61 % of the ct*ct of an encryption.  The slice is
+    scaled to one full AES-128 encryption by key-switch count: REF_KS_PER_ENCRYPTION / 30."""
+    KS_PER_STEP = 23 + 7
 
-# key switches of one round when the reference's engine calls are issued one for one (no fusion), incl. the two
-# bootstraps: engine counter of the unfused FIPS batched round (profiles/r1_bench_v1_unfused.json)
-KS_PER_ROUND = 1588
+    def __init__(self, threads: int = 0):
+        os.environ["OMP_NUM_THREADS"] = str(threads or os.cpu_count())     # torchrun exports OMP_NUM_THREADS=1
+        import aes_fhe
+        from oracle import desilofhe_cpu as be
+        self.be = be
+        self.cores = threads or os.cpu_count()
+        self.ctx = aes_fhe.EngineContext(1, mode="cpu", thread_count=self.cores, backend=be, fused=False, logn=LOGN,
+                                         levels=LEVELS, fresh_level=FRESH, dnum=DNUM, hamming_weight=HW, seed=1,
+                                         use_bootstrap=False)
+        co = aes_fhe.load_all_coeffs()
+        self.x4 = aes_fhe.XOR4LUT(self.ctx, co["xor4"])
+        self.enc = aes_fhe.StateEncoder(self.ctx)
+        rng = np.random.default_rng(3)
+        self.a = self.enc.encode(rng.integers(0, 256, 16, dtype=np.uint8))[0]
+        self.b = self.enc.encode(rng.integers(0, 256, 16, dtype=np.uint8))[0]
+        self.B = self.x4._build_power_basis_16(self.b)           # the other operand's basis: built once, outside the steps
+
+    def step(self) -> float:
+        ctx = self.ctx
+        t0 = time.perf_counter()
+        A = self.x4._build_power_basis_16(self.a)
+        acc = ctx.sub(A[0], A[0])
+        for (p, q), pt in list(self.x4.pt.items())[:16]:
+            acc = ctx.add(acc, ctx.multiply(ctx.multiply(A[p], self.B[q]), pt))
+        return time.perf_counter() - t0
+
+    def blocks_per_s(self, s_step: float) -> float:
+        return 2048.0 / (s_step * REF_KS_PER_ENCRYPTION / self.KS_PER_STEP)
+
+    def describe(self, s_step: float) -> str:
+        return (f"oracle port of the CKKS arithmetic (numpy + OpenMP C, Barrett reduction, {self.cores} threads) driven through "
+                f"the reference's call sequence: one step = make_power_basis(ct,8) + 7 conjugations + 16 XOR4 LUT terms "
+                f"(23 ct*ct, 7 conjugations, 16 ct*const) at N=2^16, level {FRESH}: {s_step:.2f} s; scaled to one AES-128 "
+                f"encryption of 2048 packed blocks by key-switch count ({REF_KS_PER_ENCRYPTION} / {self.KS_PER_STEP}; the "
+                f"18 bootstraps and 96 renorm decrypt/encrypts are left out, in the baseline's favour)")
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    arm = CpuArm()
+    config0 = None
+    if args.config0:
+        # BASELINE.json configs[0] executed for real on the CPU arm: AddRoundKey + hard renorm + SubBytes, FIPS C.1 vector
+        import aes_fhe
+        key = np.frombuffer(bytes.fromhex("000102030405060708090a0b0c0d0e0f"), dtype=np.uint8)
+        pt = np.frombuffer(bytes.fromhex("00112233445566778899aabbccddeeff"), dtype=np.uint8)
+        co = aes_fhe.load_all_coeffs()
+        sub = aes_fhe.SubBytesLUT(arm.ctx, co["sub_hi"], co["sub_lo"])
+        c0 = dict(arm.be.COUNTS)
+        t0 = time.perf_counter()
+        st = aes_fhe.AddRoundKey(arm.x4)(*arm.enc.encode(pt), *arm.enc.encode(key))
+        st = arm.enc.encode(arm.enc.decode(*st))
+        out = arm.enc.decode(*sub.apply(*st))
+        dt = time.perf_counter() - t0
+        sbox, _ = aes_fhe.tables.sbox_tables()
+        ops = {k: arm.be.COUNTS[k] - c0[k] for k in c0}
+        config0 = {"seconds": dt, "bytes_ok": bool(np.array_equal(out, sbox[pt ^ key])), "ops": ops,
+                   "s_per_key_switch": dt / max(ops["mul_cc"] + ops["conj"] + ops["rot"], 1)}
     vals = []
-    smp = None
     for i in range(args.warmup + args.steps):
-        smp = cpu_sample(n_mul=6, n_conj=2)
+        dt = arm.step()
         if i >= args.warmup:
-            vals.append(smp["s_per_ks"])
-    s_round = float(np.mean(vals)) * KS_PER_ROUND
-    value = 2048 / (ROUNDS_PER_BLOCK * s_round)
-    sample = (f"oracle port (numpy + OpenMP C, all host cores): each step = 6 ct*ct multiplications + 2 conjugations at "
-              f"N=2^16 level {FRESH}; scaled by the {KS_PER_ROUND} key switches of one round")
+            vals.append(dt)
+    s_step = float(np.mean(vals))
+    value = arm.blocks_per_s(s_step)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": s_round * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": s_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "the reference backend (closed desilofhe wheel) cannot run here; "
-                       "this is the oracle port of the same CKKS arithmetic on the host CPU"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": smp["cores"], "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "logn": LOGN, "levels": LEVELS, "fresh_level": FRESH, "dnum": DNUM},
+            "note": "the reference backend (closed desilofhe wheel) cannot run here; this is the oracle port of the same "
+                    "CKKS arithmetic executing the reference's call sequence on the host CPU",
+            "scaling_to_one_encryption": {"key_switches_per_step": arm.KS_PER_STEP, "key_switches_per_encryption": REF_KS_PER_ENCRYPTION,
+                                          "s_per_encryption_of_2048_blocks": s_step * REF_KS_PER_ENCRYPTION / arm.KS_PER_STEP},
+            "config0_real_run": config0,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": arm.describe(s_step)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def ecb_encrypt(key: bytes, data: bytes) -> bytes:
+    from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+    e = Cipher(algorithms.AES(key), modes.ECB()).encryptor()
+    return e.update(data) + e.finalize()
+
+
 def run_ours(args) -> None:
     import ctypes as C
 
@@ -208,9 +255,10 @@ def run_ours(args) -> None:
     import desilofhe
     assert dry or "cuda" in desilofhe._capi.backend(), "bench.py must run the CUDA library"
     # rank 0 samples the evaluation keys; the other ranks only allocate them and receive them in ONE broadcast pass over
-    # NCCL/NVLink.  Secret/public keys and later, lazily derived rotation keys come from the shared seed.
+    # NCCL/NVLink.  Secret/public keys and later, lazily derived rotation keys come from the shared seed
+    # (synthetic benchmark keys: a fixed seed, so that every rank derives the same secret key).
     t_keys = time.perf_counter()
-    ctx = aes_fhe.EngineContext(1, mode="gpu", device_id=local, thread_count=1, logn=LOGN, levels=LEVELS,
+    ctx = aes_fhe.EngineContext(1, mode="gpu", device_id=local, thread_count=1, logn=LOGN, levels=LEVELS, seed=20261019,
                                 fresh_level=FRESH, dnum=DNUM, hamming_weight=HW, keys_external=(world > 1 and rank != 0))
     eng = ctx.engine
     key_bytes = 0
@@ -225,41 +273,33 @@ def run_ours(args) -> None:
                                inv_mixcolumns=aes_fhe.InvMixColumnsFHE(ctx, x4), use_hard_renorm_between_steps=True)
     drv = aes_fhe.FipsDriver(pipe, batched=True)
     stride = eng.slot_count // 16
+    npairs = max(1, args.pairs)
 
-    # byte accounting of the host<->device traffic of encrypt / decrypt
+    # byte accounting of the host<->device traffic of encrypt / decrypt (the batched encoder ships nibbles, one byte per
+    # slot, when the engine has the device-side zeta16 codec)
     io = {"h2d": 0, "d2h": 0}
-    enc0, dec0 = ctx.encrypt, ctx.decrypt
-
-    def enc(v, level=None):
-        io["h2d"] += eng.slot_count * 16
-        return enc0(v, level=level)
-
-    def dec(c):
-        io["d2h"] += eng.slot_count * 16
-        return dec0(c)
-
-    ctx.encrypt, ctx.decrypt = enc, dec
-    # the batched encoder ships nibbles (one byte per slot) when the engine has the device-side zeta16 codec
     encn0, decn0 = ctx.encrypt_nibbles, ctx.decrypt_nibbles
 
     def encn(nib, level=None):
-        io["h2d"] += eng.slot_count
+        io["h2d"] += int(np.asarray(nib).size)
         return encn0(nib, level=level)
 
     def decn(c):
-        io["d2h"] += eng.slot_count
-        return decn0(c)
+        out = decn0(c)
+        io["d2h"] += int(out.size)
+        return out
 
     ctx.encrypt_nibbles, ctx.decrypt_nibbles = encn, decn
 
     rng = np.random.default_rng(1000 + rank)
-    key = np.frombuffer(bytes.fromhex("000102030405060708090a0b0c0d0e0f"), dtype=np.uint8)
-    rks = aes_fhe.expand_aes128_key(key)
-    rk_ct = pipe._prepare_round_keys([drv._perm(rk) for rk in rks])        # resident round-key ciphertexts
-    npairs = 1 if args.no_graph else max(1, args.pairs)
-    blocks = [rng.integers(0, 256, (stride, 16), dtype=np.uint8) for _ in range(npairs)]
-    states = [pipe.encoder.encode(drv._perm(b)) for b in blocks]           # resident states
-    expect = [plain_round(b, rks[1]) for b in blocks]
+    key = bytes.fromhex("000102030405060708090a0b0c0d0e0f")
+    rks = aes_fhe.expand_aes128_key(np.frombuffer(key, dtype=np.uint8))
+    rk_perm = [drv._perm(rk) for rk in rks]
+    rk_ct = pipe._prepare_round_keys(rk_perm)                              # resident round-key ciphertexts (unbatched)
+    blocks = rng.integers(0, 256, (npairs, stride, 16), dtype=np.uint8)
+    blocks[0, 0] = np.frombuffer(bytes.fromhex("00112233445566778899aabbccddeeff"), dtype=np.uint8)   # FIPS-197 C.1
+    state = pipe.encoder.encode(drv._perm(blocks))                         # resident state: ONE batched handle pair
+    want = np.frombuffer(ecb_encrypt(key, blocks.tobytes()), dtype=np.uint8).reshape(blocks.shape)
 
     def barrier():
         eng.sync()
@@ -271,13 +311,15 @@ def run_ours(args) -> None:
     def _check(rc):
         desilofhe._capi.check(rc)
 
+    ms_box = C.c_float()
+
     def timed(fn, n):
         barrier()
         _check(lib.ckks_timer_start(ptr))
         res = None
         for _ in range(n):
             res = fn()
-        _check(lib.ckks_timer_stop_ms(ptr, C.byref(ms_box)))      # event on the main stream, which waits on every replay
+        _check(lib.ckks_timer_stop_ms(ptr, C.byref(ms_box)))      # event pair on the engine's main stream (the graphs replay on it)
         barrier()
         if dist is not None:
             t = torch.tensor([ms_box.value], device="cuda", dtype=torch.float64)
@@ -285,58 +327,45 @@ def run_ours(args) -> None:
             return float(t.item()), res
         return float(ms_box.value), res
 
-    ms_box = C.c_float()
-    graph_info = None
+    def encrypt_eager(ct):
+        ct = pipe.encrypt_first(*ct, *rk_ct[0])
+        for r in range(1, 10):
+            ct = pipe.encrypt_round(*ct, *rk_ct[r])
+        return pipe.encrypt_last(*ct, *rk_ct[10])
+
     t_capture = time.perf_counter()
     if args.no_graph:
-        rounds = None
-
-        def step_resident():
-            return [pipe.encrypt_round(*states[0], *rk_ct[1])]
-
-        def step_e2e():
-            ct = pipe.encoder.encode(drv._perm(blocks[0]))
-            return [drv.decode(*pipe.encrypt_round(*ct, *rk_ct[1]))]
-
-        def step_latency():
-            return step_resident()
+        step_resident = lambda: encrypt_eager(state)
     else:
-        # one captured round per resident pair: private arena, static inputs = the pair's state and the round key
-        if args.serial_graphs:                 # A/B: no stream lanes inside a graph, concurrency only across pairs
+        if args.serial_graphs:                 # A/B: no stream lanes inside a graph
             eng.set_lanes_enabled(False)
-        rounds = [aes_fhe.CapturedRound(pipe, states[j], rk_ct[1]) for j in range(npairs)]
+        pipe.encrypt_resident(state, rk_ct)    # records the three round graphs (first / middle / last) on first use
         if args.serial_graphs:
             eng.set_lanes_enabled(True)
-        graph_info = rounds[0].info()
-
-        def step_resident():
-            outs = [rounds[j].call.launch(stream=j + 1) for j in range(npairs)]
-            for j in range(npairs):
-                eng.graph_wait(j + 1)
-            return outs
-
-        def step_e2e():
-            outs = []
-            for j in range(npairs):
-                ct = pipe.encoder.encode(drv._perm(blocks[j]))          # host bytes -> H2D -> encrypt
-                outs.append(rounds[j](*ct, *rk_ct[1], stream=j + 1))
-            for j in range(npairs):
-                eng.graph_wait(j + 1)
-            return [drv.decode(*o) for o in outs]                        # decrypt -> D2H -> bytes
-
-        def step_latency():
-            return [rounds[0].call.launch(stream=0)]
+        step_resident = lambda: pipe.encrypt_resident(state, rk_ct)
     t_capture = time.perf_counter() - t_capture
+    graphs = {k[0]: g.info() for k, g in pipe.__dict__.get("_round_graphs", {}).items()}
 
-    def decode_all(outs):
-        return [drv.decode(*o) for o in outs]
-
-    def all_equal(got):
-        return all(bool(np.array_equal(g, e)) for g, e in zip(got, expect))
+    def step_e2e():
+        ct = pipe.encoder.encode(drv._perm(blocks))                      # host bytes -> H2D -> encrypt
+        out = encrypt_eager(ct) if args.no_graph else pipe.encrypt_resident(ct, rk_ct)
+        return drv.decode(*out)                                          # decrypt -> D2H -> bytes
 
     for _ in range(args.warmup):
         out = step_resident()
-    ok = all_equal(decode_all(out))
+    ok = bool(np.array_equal(np.asarray(drv.decode(*out)).reshape(want.shape), want))
+
+    if os.environ.get("BENCH_NCU_ROUND") == "1" and torch is not None and not args.no_graph:
+        # profiling aid (`ncu --graph-profiling node --profile-from-start off`): ONE replay of the recorded middle round
+        # inside the profiler window, then exit -- the per-kernel launch list of exactly the unit the bench replays 9 x
+        mid = next(g for k, g in pipe._round_graphs.items() if k[0] == "enc")
+        barrier()
+        torch.cuda.cudart().cudaProfilerStart()
+        mid.call.launch(stream=0)
+        barrier()
+        torch.cuda.cudart().cudaProfilerStop()
+        print(json.dumps({"profiled": "one replay of the middle-round graph", "pairs": npairs, "bytes_ok": ok}))
+        return
 
     clocks = Clocks(local)
     clocks.start()
@@ -353,130 +382,144 @@ def run_ours(args) -> None:
     launches = (lib.ckks_launch_count() - l0) // args.steps
     c1 = eng.counters()
     clk = clocks.stop()
-    ok = ok and all_equal(decode_all(out))
+    ok = ok and bool(np.array_equal(np.asarray(drv.decode(*out)).reshape(want.shape), want))
     s_step = ms * 1e-3 / args.steps
-    value = world * npairs * stride / (ROUNDS_PER_BLOCK * s_step)
+    value = world * npairs * stride / s_step
 
-    ms_l, _ = timed(step_latency, args.steps)
-    s_round = ms_l * 1e-3 / args.steps
+    # latency of one replay of the middle round (all pairs)
+    s_round = None
+    mid = None
+    if not args.no_graph:
+        mid = next(g for k, g in pipe._round_graphs.items() if k[0] == "enc")
+        ms_l, _ = timed(lambda: mid.call.launch(stream=0), max(args.steps, 3))
+        s_round = ms_l * 1e-3 / max(args.steps, 3)
 
     for _ in range(min(args.warmup, 2)):          # the host path has its own first-use costs (arena, pinned staging)
         step_e2e()
     io["h2d"] = io["d2h"] = 0
     ms_e, got = timed(step_e2e, args.steps)
-    ok = ok and all_equal(got)
+    ok = ok and bool(np.array_equal(np.asarray(got).reshape(want.shape), want))
     s_step_e = ms_e * 1e-3 / args.steps
-    e2e = {"value": world * npairs * stride / (ROUNDS_PER_BLOCK * s_step_e), "unit": UNIT,
+    e2e = {"value": world * npairs * stride / s_step_e, "unit": UNIT,
            "h2d_bytes_per_step": io["h2d"] // args.steps, "d2h_bytes_per_step": io["d2h"] // args.steps,
            "ms_per_step": s_step_e * 1e3}
 
-    def step_eager():
-        return pipe.encrypt_round(*states[0], *rk_ct[1])
-
-    # the other half of BASELINE.json's "s/round (enc+dec)": one middle round of the README-order decryption
-    # (InvShiftRows, InvSubBytes, AddRoundKey, InvMixColumns with the GF 9/11/13/14 LUTs + 2 bootstraps), one pair,
-    # latency of one replay of its captured graph (eager with --no-graph)
-    dec = None
-    if not args.no_dec:
-        from aes_fhe.steps import SHIFTROWS_DEPTH, SUBBYTES_DEPTH
-        dstate = pipe.encoder.encode(drv._perm(blocks[0]), level=SHIFTROWS_DEPTH + SUBBYTES_DEPTH)
-        dwant = plain_inv_round(blocks[0], rks[5])
-        if args.no_graph:
-            dec_step = lambda: pipe.decrypt_round(*dstate, *rk_ct[5])
-            dinfo = None
-        else:
-            drnd = aes_fhe.CapturedRound(pipe, dstate, rk_ct[5], inverse=True)
-            dec_step = lambda: drnd.call.launch(stream=0)
-            dinfo = drnd.info()
-        dec_step()
-        ms_d, dout = timed(dec_step, args.steps)
-        dok = bool(np.array_equal(drv.decode(*dout), dwant))
-        ok = ok and dok
-        dec = {"s_per_round": ms_d * 1e-3 / args.steps, "bytes_exact_vs_fips197_inverse_round": dok, "cuda_graph": dinfo}
-
-    # roofline leg: one more resident step with a CUDA-event pair around every NTT call.  The stream lanes are switched
-    # off for this step so that an event pair brackets the NTT kernels alone (with lanes on, kernels of other streams
-    # run inside the bracket and the per-call time is not a kernel time).
+    # roofline leg: one more middle round, eagerly, with a CUDA-event pair around every NTT call.  The stream lanes are
+    # switched off so that an event pair brackets the NTT kernels alone (with lanes on, kernels of other streams run
+    # inside the bracket and the per-call time is not a kernel time).  Same batch size as the timed step.
+    mid_in = pipe.encrypt_first(*state, *rk_ct[0])
     eng.set_lanes_enabled(False)
-    step_eager()
+    pipe.encrypt_round(*mid_in, *rk_ct[1])
     eng.sync()
     _check(lib.ckks_profile_ntt_begin(ptr))
     t0 = time.perf_counter()
-    step_eager()
+    pipe.encrypt_round(*mid_in, *rk_ct[1])
     eng.sync()
     prof_wall = time.perf_counter() - t0
     pms, pcalls, plimbs = C.c_double(), C.c_long(), C.c_long()
     _check(lib.ckks_profile_ntt_end(ptr, C.byref(pms), C.byref(pcalls), C.byref(plimbs)))
     eng.set_lanes_enabled(True)
-    large_batch = None
-    if not dry and LOGN == 16:
-        lb = C.c_float()
-        nl = LEVELS + 1 + 7
-        _check(lib.ckks_bench_ntt(ptr, nl, 6, 0, 20, C.byref(lb)))
-        large_batch = {"limbs_per_call": nl * 6, "us_per_call": lb.value * 1e3,
-                       "achieved": nl * 6 * 2 * (1 << LOGN) * 8 / (lb.value * 1e-3) / 1e9}
-    # BASELINE.json's third figure: rotations/s at N = 2^16 (one hybrid key switch + Galois gather, resident operands),
-    # back to back on the engine's stream, at the top, the fresh and the post-bootstrap level
-    rotations = None
-    if not dry and LOGN == 16:
-        rotations = {}
-        rms = C.c_float()
-        for lvl in (LEVELS, FRESH, 5):
-            _check(lib.ckks_bench_rotate(ptr, lvl, 20, C.byref(rms)))
-            rotations[f"level_{lvl}"] = 1e3 / rms.value
-            _check(lib.ckks_bench_rotate_lanes(ptr, lvl, 8, 10, C.byref(rms)))
-            rotations[f"level_{lvl}_8_lanes"] = 1e3 / rms.value
+    del mid_in
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    large_batch = None
+    rotations = None
+    roofline_ks = None
+    if not dry and LOGN == 16:
+        lb = C.c_float()
+        nl = LEVELS + 1 + 7
+        _check(lib.ckks_bench_ntt(ptr, nl, 6, 0, 20, C.byref(lb)))
+        large_batch = {"limbs_per_call": nl * 6, "us_per_call": lb.value * 1e3,
+                       "achieved": nl * 6 * 2 * (1 << LOGN) * 8 / (lb.value * 1e-3) / 1e9}
+        large_batch["frac"] = large_batch["achieved"] / peak
+        # BASELINE.json's third figure: rotations/s at N = 2^16 (one hybrid key switch + Galois gather, resident
+        # operands), back to back on the engine's stream, at the top, the fresh and the post-bootstrap level, for an
+        # unbatched handle and for a handle of `pairs` items
+        rotations = {}
+        rms = C.c_float()
+        P_ = eng.params()
+        K_ = len(P_["p"])
+        for lvl in (LEVELS, FRESH, 5):
+            for nb in sorted({1, npairs}):
+                _check(lib.ckks_bench_rotate_batch(ptr, lvl, nb, 20, C.byref(rms)))
+                rotations[f"level_{lvl}_batch_{nb}"] = nb * 1e3 / rms.value
+                if lvl == FRESH and nb == npairs:
+                    beta = -(-(lvl + 1) // P_["alpha"])
+                    per_item = (1 << LOGN) * 8 * ((lvl + 1) + 2 * beta * (lvl + 1 + K_) + 2 * (lvl + 1))
+                    ach = nb * per_item / (rms.value * 1e-3) / 1e9
+                    roofline_ks = {"bound": "hbm", "kernel": "hybrid key switch (rotation) = iNTT, ModUp conversion, NTT, inner "
+                                   "product with the key, iNTT, ModDown conversion, NTT + epilogue", "level": lvl, "batch": nb,
+                                   "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                                   "alg_bytes_per_key_switch": per_item, "ms_per_call": rms.value, "traffic": None,
+                                   "note": "algorithmic bytes per SURVEY.md 8d (input polynomial, the key, the output "
+                                           "ciphertext), counted per item although the batched kernel reads the key once"}
     alg_bytes = plimbs.value * 2 * (1 << LOGN) * 8
     achieved = alg_bytes / (pms.value * 1e-3) / 1e9 if pms.value else 0.0
     roofline = {"bound": "hbm", "kernel": "ntt_fwd_passA/B + ntt_inv_passB/A (negacyclic NTT, N=2^16)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 # dram__bytes_read+write of the two NTT passes from the `ncu --set full` capture committed as
                 # profiles/r1_ncu_full_ntt_v3_126limbs.csv: 181 MB for 132.1 MB algorithmic (twiddle tables re-read)
                 "traffic": alg_bytes / max(pcalls.value, 1) * 1.37,
                 "traffic_source": "ncu --set full, profiles/r1_ncu_full_ntt_v3_126limbs.csv (ratio 1.37 x algorithmic)",
-                "bound_note": "HBM roofline as the contract asks; achieved/frac are the NTT calls of the AES step itself "
-                              "(14 limbs per call on average: a pass is latency-bound below ~27 limbs); large_batch is "
-                              "the same kernels on 168 limbs per call, timed live in this run; ncu: FP64 pipe 41-51 %, "
-                              "long-scoreboard (per-thread twiddle loads) is the top stall of pass B",
-                "large_batch": large_batch,
-                "serial_step_ms": prof_wall * 1e3, "ntt_calls_per_step": pcalls.value, "limb_ntts_per_step": plimbs.value,
-                "alg_bytes_per_call": alg_bytes / max(pcalls.value, 1), "avg_call_us": pms.value * 1e3 / max(pcalls.value, 1),
-                "ntt_share_of_step": pms.value * 1e-3 / prof_wall}
+                "bound_note": "HBM roofline as the contract asks; achieved/frac are ALL NTT calls of one middle round at the "
+                              "bench's batch size, each bracketed by a CUDA-event pair (lanes off for that leg); ncu: FP64 "
+                              "pipe 41-51 %, the kernel is bound by the 64-bit modular multiply rate, not by HBM",
+                "large_batch": large_batch, "profiled_round_wall_ms": prof_wall * 1e3, "ntt_ms_per_round": pms.value,
+                "graph_round_ms": s_round * 1e3 if s_round else None,
+                "ntt_share_of_graph_round": (pms.value * 1e-3 / s_round) if s_round else None,
+                "ntt_calls_per_round": pcalls.value, "limb_ntts_per_round": plimbs.value,
+                "limbs_per_call": plimbs.value / max(pcalls.value, 1),
+                "alg_bytes_per_call": alg_bytes / max(pcalls.value, 1), "avg_call_us": pms.value * 1e3 / max(pcalls.value, 1)}
 
-    if large_batch:
-        large_batch["frac"] = large_batch["achieved"] / peak
+    # the other half of BASELINE.json's "s/round (enc+dec)": README-order decryption (InvShiftRows, InvSubBytes,
+    # AddRoundKey, InvMixColumns with the GF 9/11/13/14 LUTs + 2 bootstraps per middle round) of the ciphertexts
+    dec = None
+    if not args.no_dec and not args.no_graph:
+        pipe.release_graphs()                      # the encryption graphs' arenas go back to the pool first
+        cts = pipe.encoder.encode(drv._perm(want))
+        dstep = lambda: drv.decrypt(*cts, rks, captured=True)
+        dout = dstep()
+        dstep()
+        ms_d, dout = timed(dstep, args.steps)
+        dok = bool(np.array_equal(np.asarray(drv.decode(*dout)).reshape(blocks.shape), blocks))
+        ok = ok and dok
+        dmid = next(g for k, g in pipe._round_graphs.items() if k[0] == "dec")
+        ms_dr, _ = timed(lambda: dmid.call.launch(stream=0), max(args.steps, 3))
+        dec = {"blocks_per_s": world * npairs * stride / (ms_d * 1e-3 / args.steps), "ms_per_step": ms_d / args.steps,
+               "s_per_round": ms_dr * 1e-3 / max(args.steps, 3), "roundtrip_equals_plaintext": dok,
+               "cuda_graphs": {k[0]: g.info() for k, g in pipe._round_graphs.items()}}
+        pipe.release_graphs()
+
     if rank == 0:
-        ks_round = (c1["keyswitch"] - c0["keyswitch"]) // args.steps
+        ks_step = (c1["keyswitch"] - c0["keyswitch"]) // args.steps
         cpu = None
         if world == 1 and not args.no_cpu and not dry:
-            smp = cpu_sample()
-            s_cpu = smp["s_per_ks"] * KS_PER_ROUND
-            cpu = {"value": stride / (ROUNDS_PER_BLOCK * s_cpu), "unit": UNIT, "cores": smp["cores"], "kind": "port",
-                   "sample": f"oracle port (numpy + OpenMP C): {smp['n_mul']} ct*ct multiplications + {smp['n_conj']} "
-                             f"conjugations at N=2^16 level {FRESH} in {smp['seconds']:.1f} s, scaled by the "
-                             f"{KS_PER_ROUND} key switches of one round issued call for call as the reference does",
-                   "s_per_round": s_cpu}
+            arm = CpuArm()
+            arm.step()
+            dts = [arm.step() for _ in range(2)]
+            s_cpu = float(np.mean(dts))
+            cpu = {"value": arm.blocks_per_s(s_cpu), "unit": UNIT, "cores": arm.cores, "kind": "port",
+                   "sample": arm.describe(s_cpu)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": s_step * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "logn": LOGN, "levels": LEVELS, "fresh_level": FRESH, "dnum": DNUM,
-                           "pairs_per_gpu": npairs, "cuda_graph": graph_info, "capture_s": round(t_capture, 2),
-                           "evk_broadcast_bytes": key_bytes, "setup_s": round(t_keys, 2), "l2": "working set (evaluation keys 87 MiB each, ~60 live ciphertexts) "
-                           "exceeds the 126 MB L2; no explicit flush"},
-                "s_per_round": s_round, "dec_round": dec,
-                "s_per_round_enc_plus_dec": (s_round + dec["s_per_round"]) if dec else None,
-                "bytes_exact_vs_fips197_round": ok,
-                "key_switches_per_step": ks_round, "bootstraps_per_step": (c1["bootstrap"] - c0["bootstrap"]) // args.steps,
-                "rotations_per_s_equiv": ks_round / s_step, "rotations_per_s_n16": rotations, "arena": eng.arena_stats(),
+                           "pairs_per_gpu": npairs, "blocks_per_step_per_gpu": npairs * stride, "cuda_graphs": graphs,
+                           "capture_s": round(t_capture, 2), "evk_broadcast_bytes": key_bytes, "setup_s": round(t_keys, 2),
+                           "l2": "working set (evaluation keys 87 MiB each, hundreds of live ciphertexts) exceeds the 126 MB L2; "
+                                 "no explicit flush"},
+                "s_per_round": s_round, "s_per_round_per_pair": (s_round / npairs) if s_round else None, "dec": dec,
+                "s_per_round_enc_plus_dec": (s_round + dec["s_per_round"]) if (dec and s_round) else None,
+                "bytes_exact_vs_fips197": ok,
+                "key_switches_per_step": ks_step, "bootstraps_per_step": (c1["bootstrap"] - c0["bootstrap"]) // args.steps,
+                "key_switches_per_s": ks_step / s_step, "rotations_per_s_n16": rotations, "arena": eng.arena_stats(),
                 "e2e": e2e, "gpu_launches": int(launches) * args.steps, "clocks": clk, "roofline": roofline,
-                "cpu_baseline": cpu}
+                "roofline_keyswitch": roofline_ks, "cpu_baseline": cpu}
         if dry:
             line["invalid"] = "dry run on the test-only emulation build (N=2^12): not a measurement"
         if args.host_floor:
@@ -495,10 +538,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--pairs", type=int, default=4, help="independent ciphertext pairs per GPU, one captured round each")
-    ap.add_argument("--no-dec", action="store_true", help="skip the decryption-round latency leg")
-    ap.add_argument("--serial-graphs", action="store_true", help="A/B: capture each round without stream lanes")
-    ap.add_argument("--no-graph", action="store_true", help="issue the round eagerly, call by call (one pair; A/B)")
+    ap.add_argument("--pairs", type=int, default=4, help="ciphertext pairs per GPU, carried by one batched handle pair")
+    ap.add_argument("--no-dec", action="store_true", help="skip the decryption legs")
+    ap.add_argument("--serial-graphs", action="store_true", help="A/B: capture the rounds without stream lanes")
+    ap.add_argument("--no-graph", action="store_true", help="issue the encryption eagerly, call by call (A/B)")
+    ap.add_argument("--config0", action="store_true",
+                    help="--impl reference: also execute BASELINE.json configs[0] (AddRoundKey + SubBytes) for real, once")
     ap.add_argument("--dry-run-emulation", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--host-floor", action="store_true",
                     help="diagnostic: the same call sequence at N=2^12 (kernels 16x smaller), i.e. the host enqueue "

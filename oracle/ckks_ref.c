@@ -28,6 +28,24 @@ static inline u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - 
 
 u64 ref_mulmod(u64 a, u64 b, u64 q) { return mulmod(a, b, q); }
 
+/* Barrett reduction of a 128-bit product for the hot loops (q < 2^62): the same canonical residue as `% q` -- every result
+ * of this file is unchanged -- at a few cycles instead of a 128-bit division (so that the CPU baseline timed by bench.py is
+ * not a strawman).  mu = floor(2^(k+63) / q), k = bitlen(q); the quotient estimate is low by at most 3. */
+typedef struct { u64 q, mu; int k1; } bar_t;
+static inline bar_t bar_init(u64 q) {
+    int k = 64 - __builtin_clzll(q);
+    bar_t b = {q, (u64)((((u128)1) << (k + 63)) / q), k - 1};
+    return b;
+}
+static inline u64 bar_reduce(u128 z, bar_t b) {
+    u64 x = (u64)(z >> b.k1);
+    u64 qh = (u64)(((u128)x * b.mu) >> 64);
+    u64 r = (u64)z - qh * b.q;
+    while (r >= b.q) r -= b.q;
+    return r;
+}
+static inline u64 bmul(u64 a, u64 b, bar_t m) { return bar_reduce((u128)a * b, m); }
+
 u64 ref_powmod(u64 a, u64 e, u64 q) {
     u64 r = 1 % q;
     a %= q;
@@ -71,12 +89,13 @@ void ref_ntt_tables(int logn, u64 q, u64 psi, u64 *tab, u64 *itab) {
 /* negacyclic forward NTT, natural order in, bit-reversed order out: A[k] = a(psi^(2 bitrev(k)+1)) */
 void ref_ntt_fwd(u64 *a, int logn, u64 q, const u64 *tab) {
     u64 N = 1ull << logn, t = N;
+    const bar_t B = bar_init(q);
     for (u64 m = 1; m < N; m <<= 1) {
         t >>= 1;
         for (u64 i = 0; i < m; i++) {
             u64 W = tab[m + i], j1 = 2 * i * t;
             for (u64 j = j1; j < j1 + t; j++) {
-                u64 U = a[j], V = mulmod(a[j + t], W, q);
+                u64 U = a[j], V = bmul(a[j + t], W, B);
                 a[j] = addmod(U, V, q);
                 a[j + t] = submod(U, V, q);
             }
@@ -86,6 +105,7 @@ void ref_ntt_fwd(u64 *a, int logn, u64 q, const u64 *tab) {
 
 void ref_ntt_inv(u64 *a, int logn, u64 q, const u64 *itab) {
     u64 N = 1ull << logn, t = 1;
+    const bar_t B = bar_init(q);
     for (u64 m = N; m > 1; m >>= 1) {
         u64 h = m >> 1, j1 = 0;
         for (u64 i = 0; i < h; i++) {
@@ -93,14 +113,14 @@ void ref_ntt_inv(u64 *a, int logn, u64 q, const u64 *itab) {
             for (u64 j = j1; j < j1 + t; j++) {
                 u64 U = a[j], V = a[j + t];
                 a[j] = addmod(U, V, q);
-                a[j + t] = mulmod(submod(U, V, q), W, q);
+                a[j + t] = bmul(submod(U, V, q), W, B);
             }
             j1 += 2 * t;
         }
         t <<= 1;
     }
     u64 ninv = ref_powmod(N % q, q - 2, q);
-    for (u64 j = 0; j < N; j++) a[j] = mulmod(a[j], ninv, q);
+    for (u64 j = 0; j < N; j++) a[j] = bmul(a[j], ninv, B);
 }
 
 /* batches: a is [nl][N]; qs[nl]; tabs is [nl][N] */
@@ -119,14 +139,18 @@ void ref_ntt_inv_batch(u64 *a, int nl, int logn, const u64 *qs, const u64 *itabs
 /* out[l][k] = a[l][k] * b[l][k]  (+ acc) */
 void ref_mul_batch(u64 *out, const u64 *a, const u64 *b, int nl, size_t N, const u64 *qs) {
 #pragma omp parallel for schedule(static)
-    for (int l = 0; l < nl; l++)
-        for (size_t k = 0; k < N; k++) out[l * N + k] = mulmod(a[l * N + k], b[l * N + k], qs[l]);
+    for (int l = 0; l < nl; l++) {
+        const bar_t B = bar_init(qs[l]);
+        for (size_t k = 0; k < N; k++) out[l * N + k] = bmul(a[l * N + k], b[l * N + k], B);
+    }
 }
 void ref_muladd_batch(u64 *acc, const u64 *a, const u64 *b, int nl, size_t N, const u64 *qs) {
 #pragma omp parallel for schedule(static)
-    for (int l = 0; l < nl; l++)
+    for (int l = 0; l < nl; l++) {
+        const bar_t B = bar_init(qs[l]);
         for (size_t k = 0; k < N; k++)
-            acc[l * N + k] = addmod(acc[l * N + k], mulmod(a[l * N + k], b[l * N + k], qs[l]), qs[l]);
+            acc[l * N + k] = addmod(acc[l * N + k], bmul(a[l * N + k], b[l * N + k], B), qs[l]);
+    }
 }
 void ref_add_batch(u64 *out, const u64 *a, const u64 *b, int nl, size_t N, const u64 *qs) {
 #pragma omp parallel for schedule(static)
@@ -141,16 +165,20 @@ void ref_sub_batch(u64 *out, const u64 *a, const u64 *b, int nl, size_t N, const
 /* out[l][k] = a[l][k] * s[l] */
 void ref_mul_scalar_batch(u64 *out, const u64 *a, const u64 *s, int nl, size_t N, const u64 *qs) {
 #pragma omp parallel for schedule(static)
-    for (int l = 0; l < nl; l++)
-        for (size_t k = 0; k < N; k++) out[l * N + k] = mulmod(a[l * N + k], s[l], qs[l]);
+    for (int l = 0; l < nl; l++) {
+        const bar_t B = bar_init(qs[l]);
+        for (size_t k = 0; k < N; k++) out[l * N + k] = bmul(a[l * N + k], s[l], B);
+    }
 }
 /* NTT-domain multiply by the 2-term polynomial R + I*X^(N/2): first half of the bit-reversed array sees
  * cp[l] = R + I*J, second half cm[l] = R - I*J  (J = psi^(N/2)); DESIGN.md spec S7 */
 void ref_mul_const_batch(u64 *out, const u64 *a, const u64 *cp, const u64 *cm, int nl, size_t N, const u64 *qs) {
 #pragma omp parallel for schedule(static)
-    for (int l = 0; l < nl; l++)
+    for (int l = 0; l < nl; l++) {
+        const bar_t B = bar_init(qs[l]);
         for (size_t k = 0; k < N; k++)
-            out[l * N + k] = mulmod(a[l * N + k], k < N / 2 ? cp[l] : cm[l], qs[l]);
+            out[l * N + k] = bmul(a[l * N + k], k < N / 2 ? cp[l] : cm[l], B);
+    }
 }
 /* gather: out[l][k] = a[l][perm[k]] */
 void ref_permute_batch(u64 *out, const u64 *a, const uint32_t *perm, int nl, size_t N) {
@@ -163,13 +191,17 @@ void ref_permute_batch(u64 *out, const u64 *a, const uint32_t *perm, int nl, siz
  * out[t][k] = sum_i ((in[i][k] * hatinv[i]) mod sq[i]) * hat[i][t]   mod tq[t] */
 void ref_baseconv(u64 *out, const u64 *in, size_t N, int ns, const u64 *sq, const u64 *hatinv, int nt,
                   const u64 *tq, const u64 *hat /* [ns][nt] */) {
+    bar_t BS[64], BT[64];
+    for (int i = 0; i < ns; i++) BS[i] = bar_init(sq[i]);
+    for (int t = 0; t < nt; t++) BT[t] = bar_init(tq[t]);
 #pragma omp parallel for schedule(static)
     for (size_t k = 0; k < N; k++) {
         u64 y[64];
-        for (int i = 0; i < ns; i++) y[i] = mulmod(in[i * N + k], hatinv[i], sq[i]);
+        for (int i = 0; i < ns; i++) y[i] = bmul(in[i * N + k], hatinv[i], BS[i]);
         for (int t = 0; t < nt; t++) {
             u64 acc = 0, q = tq[t];
-            for (int i = 0; i < ns; i++) acc = addmod(acc, mulmod(y[i] % q, hat[i * nt + t], q), q);
+            /* (y mod q) * hat mod q == y * hat mod q; y * hat < 2^124 fits the Barrett input range */
+            for (int i = 0; i < ns; i++) acc = addmod(acc, bmul(y[i] % q, hat[i * nt + t], BT[t]), q);
             out[t * N + k] = acc;
         }
     }
@@ -180,20 +212,23 @@ void ref_baseconv(u64 *out, const u64 *in, size_t N, int ns, const u64 *sq, cons
  * out[t] = sum_i y_i hat[i][t] - u D  (mod tq[t]);  negD[t] = tq[t] - (D mod tq[t]) */
 void ref_baseconv_exact(u64 *out, const u64 *in, size_t N, int ns, const u64 *sq, const u64 *hatinv, int nt,
                         const u64 *tq, const u64 *hat /* [ns][nt] */, const double *inv_src, const u64 *negD) {
+    bar_t BS[64], BT[64];
+    for (int i = 0; i < ns; i++) BS[i] = bar_init(sq[i]);
+    for (int t = 0; t < nt; t++) BT[t] = bar_init(tq[t]);
 #pragma omp parallel for schedule(static)
     for (size_t k = 0; k < N; k++) {
         u64 y[64];
         double v = 0.0;
         for (int i = 0; i < ns; i++) {
-            y[i] = mulmod(in[i * N + k], hatinv[i], sq[i]);
+            y[i] = bmul(in[i * N + k], hatinv[i], BS[i]);
             volatile double p = (double)y[i] * inv_src[i];
             v = v + p;
         }
         u64 u = (u64)(i64)nearbyint(v);
         for (int t = 0; t < nt; t++) {
             u64 acc = 0, q = tq[t];
-            for (int i = 0; i < ns; i++) acc = addmod(acc, mulmod(y[i] % q, hat[i * nt + t], q), q);
-            acc = addmod(acc, mulmod(u % q, negD[t], q), q);
+            for (int i = 0; i < ns; i++) acc = addmod(acc, bmul(y[i] % q, hat[i * nt + t], BT[t]), q);
+            acc = addmod(acc, bmul(u % q, negD[t], BT[t]), q);
             out[t * N + k] = acc;
         }
     }
