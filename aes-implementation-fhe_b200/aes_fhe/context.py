@@ -28,6 +28,10 @@ class EngineContext:
                  thread_count: int, backend=None, fused: bool = True, **engine_kwargs):
         be = _load_backend(backend)
         self._ct_type = be.Ciphertext
+        if getattr(be, "SUPPORTS_LAZY", False):
+            # this mirror issues either the reference's exact call sequence (fused=False) or the fused entry points
+            # itself (fused=True): in both cases the engine must execute call for call, not defer (desilofhe/lazy.py)
+            engine_kwargs.setdefault("lazy", False)
         common = dict(mode=mode, use_multiparty=use_multiparty, thread_count=thread_count,
                       device_id=device_id, **engine_kwargs)
         # the three constructor "signatures" of engine_context.py:17-42

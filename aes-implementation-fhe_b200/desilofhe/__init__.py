@@ -29,9 +29,12 @@ from typing import Dict, Iterable, List, Optional, Sequence
 import numpy as np
 
 from . import _capi
+from .lazy import LazyOps, LConj, LPow, LProd, LSum
 
 __all__ = ["Engine", "CapturedCall", "Ciphertext", "Plaintext", "SecretKey", "PublicKey", "RelinearizationKey", "ConjugationKey",
            "RotationKey", "BootstrapKey"]
+
+SUPPORTS_LAZY = True       # Engine(lazy=...) exists (the host mirror asks for lazy=False: it fuses by itself)
 
 # parameter sets (DESIGN.md "Parameters"): N = 2^16, q0 ~ 2^60, scale primes ~ 2^50, special primes ~ 2^61
 DEFAULTS = dict(logn=16, levels=21, scale_bits=50, q0_bits=60, p_bits=61, dnum=3, hamming_weight=192,
@@ -54,17 +57,32 @@ class BootstrapKey(_Key): pass
 
 
 class Ciphertext:
-    """Opaque handle to a ciphertext resident in HBM.  Immutable; freed with the Python object."""
-    __slots__ = ("_eng", "_h", "ntt_form", "__weakref__")
+    """Opaque handle to a ciphertext resident in HBM.  Immutable; freed with the Python object.
 
-    def __init__(self, eng: "Engine", handle: int):
+    On an `Engine(lazy=True)` a handle may stand for a deferred expression (`desilofhe/lazy.py`): level and batch size are
+    known at once, the value is computed when `_h` is first needed."""
+    __slots__ = ("_eng", "_hraw", "ntt_form", "_lz", "_lvl", "_nb", "_memo", "__weakref__")
+
+    def __init__(self, eng: "Engine", handle: int, lazy=None, level: int = -1, batch: int = 1):
         self._eng = eng
-        self._h = handle
+        self._hraw = handle
         self.ntt_form = True
+        self._lz = lazy
+        self._lvl = level
+        self._nb = batch
+        self._memo: Dict = {}
+
+    @property
+    def _h(self) -> int:
+        if self._lz is not None:
+            self._eng._force(self)
+        return self._hraw
 
     @property
     def level(self) -> int:
-        return self._eng._lib.ckks_ct_level(self._h)
+        if self._lz is not None:
+            return self._lvl
+        return self._eng._lib.ckks_ct_level(self._hraw)
 
     @property
     def polynomial_count(self) -> int:
@@ -73,13 +91,15 @@ class Ciphertext:
     @property
     def batch(self) -> int:
         """Independent ciphertexts of this shape held by the handle (1 unless created by a batched entry point)."""
-        return self._eng._lib.ckks_ct_batch(self._h)
+        if self._lz is not None:
+            return self._nb
+        return self._eng._lib.ckks_ct_batch(self._hraw)
 
     def __del__(self):
-        eng, h = self._eng, self._h
+        eng, h = self._eng, self._hraw
         if h and eng is not None and eng._ptr:
             eng._lib.ckks_ct_free(eng._ptr, h)
-        self._h = 0
+        self._hraw = 0
 
 
 class Plaintext:
@@ -197,10 +217,10 @@ class CapturedCall:
             pass
 
 
-class Engine:
+class Engine(LazyOps):
     def __init__(self, *, mode: str = "gpu", use_bootstrap: bool = False, use_multiparty: bool = False,
                  thread_count: Optional[int] = None, device_id: int = 0, max_level: Optional[int] = None,
-                 seed: Optional[int] = None, **overrides):
+                 seed: Optional[int] = None, lazy: Optional[bool] = None, **overrides):
         if use_multiparty:
             raise NotImplementedError("multiparty keys are outside the AES path (SURVEY.md 8)")
         if mode not in ("gpu", "cpu", "parallel"):
@@ -210,6 +230,9 @@ class Engine:
                           "cuda:%d" % (mode, device_id), stacklevel=2)
         self._lib = _capi.load()
         self._ptr = None
+        # deferred evaluation of the callers' term-by-term LUT loops (desilofhe/lazy.py): on unless CKKS_B200_LAZY=0 or
+        # lazy=False (the host mirror `aes_fhe` fuses by itself and asks for the call-for-call engine)
+        self.lazy = (os.environ.get("CKKS_B200_LAZY", "1") != "0") if lazy is None else bool(lazy)
         # key material and encryption randomness derive from `seed`: OS entropy unless the caller fixes it (the parity
         # tests and the oracle comparison do, to reproduce keys bit for bit; a multi-GPU job shares one seed so every
         # rank derives the same secret key).  The stream generator itself is a counter-based SplitMix64:
@@ -225,6 +248,8 @@ class Engine:
         env = os.environ.get("CKKS_B200_ENGINE_OVERRIDES")
         if env:
             overrides = {**json.loads(env), **overrides}
+        if "lazy" in overrides:
+            self.lazy = bool(overrides.pop("lazy"))
         unknown = set(overrides) - set(cfg) - {"fresh_level", "boot", "keys_external"}
         if unknown:
             raise TypeError(f"unknown Engine arguments: {sorted(unknown)}")
@@ -268,6 +293,45 @@ class Engine:
         out = C.c_void_p()
         _capi.check(fn(self._ptr, *args, C.byref(out)))
         return Ciphertext(self, out.value)
+
+    # ---- deferred evaluation (desilofhe/lazy.py): constructors and the eager primitives it bottoms out in
+    def _wrap(self, lazy, level: int, batch: int) -> Ciphertext:
+        return Ciphertext(self, 0, lazy=lazy, level=level, batch=batch)
+
+    def _eager_copy(self, a: Ciphertext) -> Ciphertext:
+        return self._new(self._lib.ckks_level_down, a._h, a.level)
+
+    def _eager_level_down(self, a: Ciphertext, level: int) -> Ciphertext:
+        return self._new(self._lib.ckks_level_down, a._h, int(level))
+
+    def _eager_multiply_cc(self, a: Ciphertext, b: Ciphertext) -> Ciphertext:
+        return self._new(self._lib.ckks_mul, a._h, b._h)
+
+    def _eager_conjugate(self, a: Ciphertext) -> Ciphertext:
+        return self._new(self._lib.ckks_conjugate, a._h)
+
+    def _eager_add(self, a: Ciphertext, b: Ciphertext) -> Ciphertext:
+        return self._new(self._lib.ckks_add, a._h, b._h)
+
+    def _eager_add_const(self, a: Ciphertext, c: complex) -> Ciphertext:
+        return self._new(self._lib.ckks_add_const, a._h, c.real, c.imag)
+
+    def _eager_zero(self, src: Ciphertext, levels_below: int) -> Ciphertext:
+        if levels_below:
+            return self._new(self._lib.ckks_mul_const, src._h, 0.0, 0.0)
+        return self._new(self._lib.ckks_sub, src._h, src._h)
+
+    def _eager_power_basis_sparse(self, ct: Ciphertext, degree: int, exponents) -> List[Optional[Ciphertext]]:
+        ex = np.asarray(sorted(set(int(k) for k in exponents)), dtype=np.int32)
+        arr = (C.c_void_p * int(degree))()
+        _capi.check(self._lib.ckks_power_basis_sparse(self._ptr, ct._h, int(degree), ex, len(ex), arr))
+        return [Ciphertext(self, arr[i]) if arr[i] else None for i in range(int(degree))]
+
+    def _eager_lut2(self, A, B, terms) -> Ciphertext:
+        return Engine.lut2(self, A, B, terms)
+
+    def _eager_lincomb(self, cts, coeffs) -> Ciphertext:
+        return Engine.lincomb(self, cts, coeffs)
 
     def params(self) -> dict:
         i = [C.c_int() for _ in range(5)]
@@ -473,13 +537,23 @@ class Engine:
         if not isinstance(a, Ciphertext):
             raise TypeError("multiply needs at least one ciphertext")
         if isinstance(b, Ciphertext):
+            if self.lazy and relin is not None:
+                return self._lazy_multiply_cc(a, b)
             return self._new(self._lib.ckks_mul if relin is not None else self._lib.ckks_mul_norelin, a._h, b._h)
         if isinstance(b, Plaintext):
             if b.const is not None:
+                if self.lazy:
+                    r = self._lazy_multiply_const(a, b.const)
+                    if r is not None:
+                        return r
                 return self._new(self._lib.ckks_mul_const, a._h, b.const.real, b.const.imag)
             return self._new(self._lib.ckks_mul_plain, a._h, b._at(a.level))
         if self._is_scalar(b):
             c = complex(b)
+            if self.lazy:
+                r = self._lazy_multiply_const(a, c)
+                if r is not None:
+                    return r
             return self._new(self._lib.ckks_mul_const, a._h, c.real, c.imag)
         return self.multiply(a, self.encode(b))
 
@@ -487,18 +561,32 @@ class Engine:
         if isinstance(b, Ciphertext) and not isinstance(a, Ciphertext):
             a, b = b, a
         if isinstance(b, Ciphertext):
+            if self.lazy:
+                r = self._lazy_add(a, b)
+                if r is not None:
+                    return r
             return self._new(self._lib.ckks_add, a._h, b._h)
         if isinstance(b, Plaintext):
             if b.const is not None:
+                if self.lazy:
+                    r = self._lazy_add_const(a, b.const)
+                    if r is not None:
+                        return r
                 return self._new(self._lib.ckks_add_const, a._h, b.const.real, b.const.imag)
             return self._new(self._lib.ckks_add_plain, a._h, b._at(a.level))
         if self._is_scalar(b):
             c = complex(b)
+            if self.lazy:
+                r = self._lazy_add_const(a, c)
+                if r is not None:
+                    return r
             return self._new(self._lib.ckks_add_const, a._h, c.real, c.imag)
         return self.add(a, self.encode(b))
 
     def subtract(self, a, b) -> Ciphertext:
         if isinstance(a, Ciphertext) and isinstance(b, Ciphertext):
+            if self.lazy and a is b:                 # "a zero ciphertext at this level" (xor4_lut.py:54,67)
+                return self._lazy_sub_self(a)
             return self._new(self._lib.ckks_sub, a._h, b._h)
         if isinstance(a, Ciphertext):
             if isinstance(b, Plaintext):
@@ -514,6 +602,8 @@ class Engine:
         return self._new(self._lib.ckks_negate, ct._h)
 
     def make_power_basis(self, ct: Ciphertext, degree: int, relin: Optional[RelinearizationKey] = None) -> List[Ciphertext]:
+        if self.lazy:
+            return self._lazy_power_basis(ct, int(degree))
         arr = (C.c_void_p * int(degree))()
         _capi.check(self._lib.ckks_power_basis(self._ptr, ct._h, int(degree), arr))
         return [Ciphertext(self, arr[i]) for i in range(int(degree))]
@@ -528,6 +618,8 @@ class Engine:
         return [Ciphertext(self, arr[i]) if arr[i] else None for i in range(int(degree))]
 
     def conjugate(self, ct: Ciphertext, key: Optional[ConjugationKey] = None) -> Ciphertext:
+        if self.lazy:
+            return self._lazy_conjugate(ct)
         return self._new(self._lib.ckks_conjugate, ct._h)
 
     def rotate(self, ct: Ciphertext, key: Optional[RotationKey], steps: int) -> Ciphertext:

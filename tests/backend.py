@@ -10,6 +10,10 @@ import os
 import sys
 from pathlib import Path
 
+# the engine-level tests check operations call for call against the oracle: deferred evaluation (desilofhe/lazy.py) is
+# switched on explicitly by the tests that cover it
+os.environ.setdefault("CKKS_B200_LAZY", "0")
+
 ROOT = Path(__file__).resolve().parent.parent
 for p in (str(ROOT), str(ROOT / "aes-implementation-fhe_b200"), str(ROOT / "tests")):
     if p not in sys.path:

@@ -20,10 +20,13 @@ import refload
 pytestmark = pytest.mark.skipif(not refload.available(), reason="needs /root/reference")
 
 
-@pytest.fixture(scope="module")
-def ref():
+@pytest.fixture(scope="module", params=["call-for-call", "deferred"])
+def ref(request):
+    """Both engine modes: every call executed at once, and the deferred evaluation of desilofhe/lazy.py (the default
+    outside the tests) that turns the reference's term-by-term LUT loops into fused kernel calls."""
     mod = backend.use_emulation()
-    os.environ["CKKS_B200_ENGINE_OVERRIDES"] = json.dumps({"logn": 12, "hamming_weight": 64})
+    os.environ["CKKS_B200_ENGINE_OVERRIDES"] = json.dumps({"logn": 12, "hamming_weight": 64,
+                                                           "lazy": request.param == "deferred"})
     try:
         ns = refload.load(mod)
         with warnings.catch_warnings():
@@ -61,8 +64,11 @@ def test_reference_ark_subbytes_shiftrows_bytes(ref):
     key = np.frombuffer(bytes.fromhex("000102030405060708090a0b0c0d0e0f"), dtype=np.uint8)
     pt = np.frombuffer(bytes.fromhex("00112233445566778899aabbccddeeff"), dtype=np.uint8)
     ark = ref.add_round_key.AddRoundKey(x4)
+    k0 = ctx.engine.counters()["keyswitch"]
     out = ark(*enc.encode(pt), *enc.encode(key))
     assert bytes(enc.decode(*out)).hex() == "00102030405060708090a0b0c0d0e0f0"          # golden enc.r0.ark
+    ks = ctx.engine.counters()["keyswitch"] - k0
+    assert ks == (2 * 19 if ctx.engine.lazy else 2 * 92), ks       # the unchanged XOR4 loop: 92 key switches, 19 when deferred
     sr = ref.shift_rows.ShiftRows(ctx)
     got = enc.decode(*sr.apply(*enc.encode(pt)))
     want = pt.reshape(4, 4).T.copy()                     # column-first packing: row r = bytes r + 4c (shift_rows.py:15-17)
