@@ -236,6 +236,65 @@ class LazyOps:
         elif inners:
             inners[0]._memo["conj"] = self._eager_conjugate(inners[0])
 
+    BSGS_MIN_DEGREE = 32           # below this the plain power basis is as cheap
+
+    def _single_base(self, terms):
+        """The common base if every term is c * base^k (distinct k) and the degree is high enough for baby-step/giant-step."""
+        base, ks = None, set()
+        for _, x in terms:
+            z = x._lz
+            if not isinstance(z, LPow) or (base is not None and z.base is not base) or z.k in ks:
+                return None
+            base = z.base
+            ks.add(z.k)
+        if base is None or max(ks) <= self.BSGS_MIN_DEGREE or len(ks) < self.BSGS_MIN_DEGREE or max(ks) > 256:
+            return None
+        return base
+
+    def _poly_bsgs(self, base, coef: Dict[int, complex]):
+        """sum_k coef[k] base^k (k >= 1) as sum_j (sum_i coef[16 j + i] base^i) * (base^16)^j: the inner sums are fused
+        linear combinations of the 15 baby powers (no key switch), the outer products are accumulated as 3-polynomial
+        ciphertexts and relinearised ONCE.  The inner sums sit one level below the babies, i.e. above every giant power
+        from (base^16)^2 on, so the result is at the level the call-for-call evaluation reports (depth(max k) + 1)."""
+        bval = self._atom_value(base)
+        kmax = max(coef)
+        J = kmax // 16
+        self._materialize_powers(bval, list(range(2, 17)))
+        memo = bval._memo
+        baby = {1: bval}
+        baby.update({i: memo[("pow", i)] for i in range(2, 16)})
+        G = memo[("pow", 16)]
+        if J > 1:
+            need = [j for j in range(2, J + 1) if any((16 * j + i) in coef for i in range(16))]
+            self._materialize_powers(G, need)
+        giant = {1: G}
+        giant.update({j: G._memo[("pow", j)] for j in range(2, J + 1) if ("pow", j) in G._memo})
+        acc3, acc2 = None, None
+        for j in range(0, J + 1):
+            idx = [i for i in range(1, 16) if (16 * j + i) in coef]
+            c0 = coef.get(16 * j, 0j) if j else 0j
+            if not idx and c0 == 0:
+                continue
+            if idx:
+                u = self._eager_lincomb([baby[i] for i in idx], [coef[16 * j + i] for i in idx])
+                if c0 != 0:
+                    u = self._eager_add_const(u, c0)
+            if j == 0:
+                acc2 = u
+                continue
+            if idx:
+                t = self._new(self._lib.ckks_mul_norelin, u._h, giant[j]._h)
+                acc3 = t if acc3 is None else self._eager_add(acc3, t)
+            else:                                        # only the pure giant power: c * (base^16)^j
+                t = self._new(self._lib.ckks_mul_const, giant[j]._h, c0.real, c0.imag)
+                acc2 = t if acc2 is None else self._eager_add(acc2, t)
+        out = None
+        if acc3 is not None:
+            out = self._new(self._lib.ckks_relinearize, acc3._h)
+        if acc2 is not None:
+            out = acc2 if out is None else self._eager_add(out, acc2)
+        return out
+
     def _sum_value(self, S: LSum, level: int):
         parts = []
         # ---- bilinear terms: fused LUT(s), at most 16 distinct left and 16 distinct right operands each
@@ -263,12 +322,23 @@ class LazyOps:
         if S.t1:
             direct = [(c, x) for c, x in S.t1 if not isinstance(x._lz, LConj)]
             mirror = [(c.conjugate(), x._lz.x) for c, x in S.t1 if isinstance(x._lz, LConj)]
-            self._prepare_atoms([x for _, x in direct] + [x for _, x in mirror])
-            if direct:
-                parts.append(self._eager_lincomb([self._atom_value(x) for _, x in direct], [c for c, _ in direct]))
-            if mirror:
-                parts.append(self._eager_conjugate(self._eager_lincomb([self._atom_value(x) for _, x in mirror],
-                                                                       [c for c, _ in mirror])))
+            bd = self._single_base(direct) if direct else None
+            bm = self._single_base(mirror) if mirror else None
+            base = bd if bd is not None else bm
+            if base is not None and (not direct or bd is base) and (not mirror or bm is base):
+                # a polynomial of high degree in ONE base (the S-box polynomials of sub_bytes_lut.py:63-71): baby-step /
+                # giant-step instead of the full power basis -- 22 products for degree 128 instead of 127
+                if direct:
+                    parts.append(self._poly_bsgs(base, {x._lz.k: c for c, x in direct}))
+                if mirror:
+                    parts.append(self._eager_conjugate(self._poly_bsgs(base, {x._lz.k: c for c, x in mirror})))
+            else:
+                self._prepare_atoms([x for _, x in direct] + [x for _, x in mirror])
+                if direct:
+                    parts.append(self._eager_lincomb([self._atom_value(x) for _, x in direct], [c for c, _ in direct]))
+                if mirror:
+                    parts.append(self._eager_conjugate(self._eager_lincomb([self._atom_value(x) for _, x in mirror],
+                                                                           [c for c, _ in mirror])))
         shared = set()
         for y in S.plain:
             v = self._atom_value(y)

@@ -79,12 +79,14 @@ def test_reference_arm_prints_the_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] > 0
 
 
-def test_ciphertext_wire_format_roundtrip():
+@pytest.mark.parametrize("which", [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)])
+def test_ciphertext_wire_format_roundtrip(which):
     """serialize -> deserialize gives a ciphertext that decrypts identically and multiplies bit-identically; a blob from
-    another modulus chain, a truncated blob and an out-of-range residue are rejected."""
+    another modulus chain, a truncated blob and an out-of-range residue are rejected (on the emulation
+    build and on the B200)."""
     import numpy as np
     import backend
-    mod = backend.use_emulation()
+    mod = backend.use_emulation() if which == "emu" else backend.use_cuda()
     eng = mod.Engine(logn=12, levels=4, dnum=2, hamming_weight=32, seed=9)
     sk = eng.create_secret_key(); eng.create_public_key(sk); rk = eng.create_relinearization_key(sk)
     rng = np.random.default_rng(1)

@@ -19,14 +19,19 @@ CASES = [
     pytest.param(("emu", 16, 5), id="emu-n16"),      # the two-round pass A (LOGR = 8) only exists at N = 2^16
     pytest.param(("cuda", 12, 6), id="cuda-n12", marks=pytest.mark.gpu),
     pytest.param(("cuda", 16, 5), id="cuda-n16", marks=pytest.mark.gpu),
+    # the benchmark's own parameter set (bench.py): 22 ciphertext primes, 7 special primes, dnum 3 (digits of 8 limbs, the
+    # last one ragged at the fresh level 14), Hamming weight 192 -- k_base_convert<7/8>, the 7-prime ModDown and the ragged
+    # ModUp are compared bit for bit here, not only through decoded bytes
+    pytest.param(("cuda", 16, 21, 192, 14), id="cuda-n16-bench", marks=pytest.mark.gpu),
 ]
 
 
 class Pair:
-    def __init__(self, which, logn, levels, seed=5):
+    def __init__(self, which, logn, levels, hw=64, fresh=-1, seed=5):
         mod = backend.use_emulation() if which == "emu" else backend.use_cuda()
-        self.eng = mod.Engine(logn=logn, levels=levels, dnum=3, hamming_weight=64, seed=seed)
-        self.params = make_params(logn=logn, levels=levels, dnum=3, hamming_weight=64)
+        kw = dict(fresh_level=fresh) if fresh >= 0 else {}
+        self.eng = mod.Engine(logn=logn, levels=levels, dnum=3, hamming_weight=hw, seed=seed, **kw)
+        self.params = make_params(logn=logn, levels=levels, dnum=3, hamming_weight=hw, **kw)
         self.orc = OracleCKKS(self.params, seed=seed)
         self.N = 1 << logn
         self.n = self.N // 2
@@ -46,8 +51,7 @@ class Pair:
 
 @pytest.fixture(scope="module", params=CASES)
 def pair(request):
-    which, logn, levels = request.param
-    return Pair(which, logn, levels)
+    return Pair(*request.param)
 
 
 def test_parameters_agree(pair):
@@ -62,7 +66,7 @@ def test_keys_bit_exact(pair):
     s = np.zeros(pair.N, dtype=np.int64)
     pair.lib.ckks_export_secret(pair.eng._ptr, s)
     assert np.array_equal(s, pair.orc.sk_coef)
-    assert int(np.abs(s).sum()) == 64
+    assert int(np.abs(s).sum()) == pair.eng.config["hamming_weight"]
     pk = np.zeros((2, pair.params.L + 1, pair.N), dtype=np.uint64)
     pair.lib.ckks_export_public(pair.eng._ptr, pk)
     assert np.array_equal(pk, pair.orc.pk)
@@ -353,16 +357,28 @@ def test_edge_cases_of_the_reference_surface(pair):
 
 
 @pytest.mark.gpu
-def test_cluster_forward_ntt_bit_exact():
-    """The experimental single-kernel forward NTT (8-CTA cluster, DSMEM exchange; CKKS_NTT_CLUSTER=1, off by default):
-    keys, raw transforms and homomorphic operations at N = 2^16 must stay bit-identical to the oracle with it switched on."""
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_cluster_ntt_bit_exact(mode):
+    """The single-kernel NTT (8-CTA cluster, DSMEM exchange; CKKS_NTT_CLUSTER=1: forward, =2: also the inverse and the fused
+    forward variants; off by default -- measured slower than the two-pass kernels, profiles/README.md): keys, raw transforms,
+    homomorphic operations and key switches with a RAGGED last digit (in-place transform of a batch whose slices have
+    different item counts: ADVICE r1 -- surplus clusters must not store), repeated, stay bit-identical to the oracle."""
     import os
-    os.environ["CKKS_NTT_CLUSTER"] = "1"
+    os.environ["CKKS_NTT_CLUSTER"] = mode
     try:
-        p = Pair("cuda", 16, 5)
-        test_keys_bit_exact(p)
-        test_raw_ntt_roundtrip_and_parity(p)
-        test_homomorphic_ops_bit_exact(p)
+        p = Pair("cuda", 16, 5)              # alpha = 2: levels 4, 2 have a ragged last digit
     finally:
         os.environ.pop("CKKS_NTT_CLUSTER", None)
-        Pair("cuda", 12, 6)                 # a new engine re-reads the (now unset) switch: off again for later tests
+    q = Pair("cuda", 12, 6)                  # the switch is per engine: an engine made afterwards is unaffected
+    test_keys_bit_exact(p)
+    test_raw_ntt_roundtrip_and_parity(p)
+    test_homomorphic_ops_bit_exact(p)
+    test_homomorphic_ops_bit_exact(q)
+    rng = np.random.default_rng(3)
+    for level in (4, 2):
+        poly = np.stack([rng.integers(0, p.params.q[i], p.N, dtype=np.uint64) for i in range(level + 1)])
+        k0, k1 = p.orc.key_switch(poly, level, 0)
+        for _ in range(25):
+            out = np.zeros((2, level + 1, p.N), dtype=np.uint64)
+            assert p.lib.ckks_test_key_switch(p.eng._ptr, poly, level, 0, out) == 0
+            assert np.array_equal(out[0], k0) and np.array_equal(out[1], k1)

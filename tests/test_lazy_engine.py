@@ -114,3 +114,32 @@ def test_errors_surface_at_the_call_and_values_are_shared(engines):
     # a deferred handle used by an operation outside the fused patterns is simply evaluated
     r = lazy.rotate(lazy.multiply(pb[1], pb[2], lazy._rk), None, 3)
     assert np.abs(lazy.decrypt(r) - np.roll(z ** 5, 3)).max() < 1e-4
+
+
+def test_high_degree_polynomial_is_evaluated_baby_step_giant_step(engines):
+    """sub_bytes_lut.py:60-71 shape: make_power_basis(b, 128) and sum_k c_k b^k, c_k conj(b^(256-k)) term by term.  Deferred:
+    15 baby + 7 giant products, ONE relinearisation per partial sum and ONE conjugation, at the level the call-for-call
+    evaluation reports."""
+    eager, lazy = engines
+    rng = np.random.default_rng(5)
+    n = eager.slot_count
+    byte = rng.integers(0, 256, n)
+    z = np.exp(-2j * np.pi * byte / 256)
+    table = rng.integers(0, 16, 256)                                          # some nibble-valued function of the byte
+    coeffs = np.fft.ifft(np.exp(-2j * np.pi * table / 16))                     # f(z) = sum_k c_k z^k on the 256th roots
+    outs, ks = [], []
+    for eng in (eager, lazy):
+        ct = eng.encrypt(z)
+        k0 = eng.counters()["keyswitch"]
+        pos = eng.make_power_basis(ct, 128, eng._rk)
+        res = eng.add_plain(eng.multiply(ct, 0.0), complex(coeffs[0]))
+        for k in range(1, 256):
+            bk = pos[k - 1] if k <= 128 else eng.conjugate(pos[256 - k - 1], eng._cj)
+            res = eng.add(res, eng.multiply(bk, eng.encode(np.full(n, coeffs[k], dtype=np.complex128))))
+        assert res.level == ct.level - 8
+        outs.append(eng.decrypt(res))
+        assert res.level == ct.level - 8                                       # still true once it has a value
+        ks.append(eng.counters()["keyswitch"] - k0)
+    want = np.exp(-2j * np.pi * table[byte] / 16)
+    assert np.abs(outs[0] - want).max() < 2e-3 and np.abs(outs[1] - want).max() < 2e-3
+    assert ks[0] == 127 + 127 and ks[1] == 15 + 7 + 2 + 1, ks

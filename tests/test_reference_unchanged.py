@@ -75,3 +75,15 @@ def test_reference_ark_subbytes_shiftrows_bytes(ref):
     for r in range(4):
         want[r] = np.roll(want[r], -r)
     assert bytes(got) == bytes(want.T.reshape(-1))
+    if ctx.engine.lazy:
+        # the reference's SubBytes (sub_bytes_lut.py:46-73: 135 ct x ct, 134 conjugations call for call) through the deferred
+        # engine: baby-step/giant-step polynomial evaluation, bytes against the S-box table embedded in the reference
+        coeffs = refload.load_test_driver(ref).load_all_coeffs(coeff_dir)
+        sb = ref.sub_bytes_lut.SubBytesLUT(ctx, coeffs["sub_hi"], coeffs["sub_lo"])
+        k0 = ctx.engine.counters()["keyswitch"]
+        got = enc.decode(*sb.apply(*enc.encode(pt)))
+        ks = ctx.engine.counters()["keyswitch"] - k0
+        sbox = np.array(ref.sub_bytes_lut.SBOX, dtype=np.uint8)            # the table embedded in the reference (sub_bytes_lut.py:86-103)
+        assert bytes(got) == bytes(sbox[pt]), bytes(got).hex()
+        assert ks < 60, ks
+
