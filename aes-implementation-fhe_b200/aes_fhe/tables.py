@@ -78,15 +78,20 @@ def expand_aes128_key(master: np.ndarray) -> List[np.ndarray]:
 
 # ---------------------------------------------------------------- coefficient tables
 @lru_cache(maxsize=None)
-def xor4_coeffs() -> np.ndarray:
+def xor4_coeffs(normalized: bool = False) -> np.ndarray:
     """16x16 complex table c[p,q] with sum_pq c[p,q] z^(p a) z^(q b) = 256 * z^(a xor b).
 
     The factor 256 is the reference's (`gen/generate_xor4_coeffs.py:13-17` multiplies
-    ifft2 by n^2); entries below 1e-8 are dropped there and below 1e-12 by the consumer."""
+    ifft2 by n^2); entries below 1e-8 are dropped there and below 1e-12 by the consumer.
+
+    `normalized=True` is the corrected table: the plain inverse DFT, whose outputs are unit-modulus
+    codewords z^(a xor b).  With it an XOR output can feed the next LUT (or a bootstrap) directly, without the
+    decrypt / re-encrypt "hard renorm" the reference needs after every XOR (pipeline.py:65-69) -- the precondition of
+    the keyless flow built on `aes_fhe.snap` (tests/test_snap.py::test_normalized_xor_chain_needs_no_renorm)."""
     a = np.arange(16)
     F = ZETA16 ** (a[:, None] ^ a[None, :])
-    C = np.fft.ifft2(F) * 256.0
-    C[np.abs(C) <= 1e-8] = 0
+    C = np.fft.ifft2(F) * (1.0 if normalized else 256.0)
+    C[np.abs(C) <= (1e-8 / 256.0 if normalized else 1e-8)] = 0
     return C
 
 

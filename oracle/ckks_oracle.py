@@ -435,8 +435,12 @@ class OracleCKKS:
         return Ct(np.stack([self.sub(a.c[k], b.c[k], idx) for k in range(2)]), a.level, a.scale)
 
     def pt_scale(self, level: int) -> float:
-        """Scale at which a plaintext meets a level-`level` ciphertext so the product lands on S[level-1]."""
-        return float(self.q[level]) * self.scales[level - 1] / self.scales[level]
+        """Scale at which a plaintext meets a level-`level` ciphertext so the product lands on S[level-1]: the canonical
+        scale S[level] itself (DESIGN.md spec S1/S7: S[l-1] = S[l]^2 / q_l).  The algebraically equal expression
+        q_l * S[l-1] / S[l] differs from S[l] by one ulp at levels 5, 8, 11, 14, 16 of the benchmark's 22-prime chain --
+        enough to change round(c * scale) for a large constant; found by the bench-chain parity case
+        (tests/test_engine_parity.py, cuda-n16-bench) and resolved in favour of the written spec."""
+        return self.scales[level]
 
     def mul_const(self, a: Ct, c: complex) -> Ct:
         if a.level < 1:

@@ -115,3 +115,28 @@ def test_snap1d_evaluates_the_lut_on_the_engine(eng_ctx):
         y = ctx.decrypt(snap.Zeta16Snap1D(ctx, lut1d_coeffs()).apply(ctx.encrypt(w ** v)))
         assert np.abs(y - want).max() < 1e-5, fused
     ctx.fused = True
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_normalized_xor_chain_needs_no_renorm(case):
+    """with the corrected XOR table (aes_fhe.tables.xor4_coeffs(normalized=True): outputs are unit-modulus
+    codewords instead of the reference's 256 x, H3) an XOR output feeds a homomorphic snap (zeta16_noise_reducter.py:
+    f(x) = (17/16) x - (1/16) x^17) and then the NEXT XOR directly: (a ^ b) ^ c evaluated entirely on ciphertexts, the secret
+    key is only used by the test to check the result.  (The reference's flow decrypts and re-encrypts after every XOR.)"""
+    which, logn, hw = case
+    mod = backend.use_emulation() if which == "emu" else backend.use_cuda()
+    ctx = aes_fhe.EngineContext(2, max_level=16, mode="gpu", thread_count=1, backend=mod, logn=logn, hamming_weight=hw)
+    x4 = aes_fhe.XOR4LUT(ctx, aes_fhe.tables.xor4_coeffs(normalized=True))
+    n = ctx.engine.slot_count
+    rng = np.random.default_rng(6)
+    a, b, c = (rng.integers(0, 16, n) for _ in range(3))
+    w = np.exp(-2j * np.pi / 16)
+    enc = lambda v: ctx.encrypt(w ** v)
+    ab = x4.apply(enc(a), enc(b))
+    z = ctx.decrypt(ab)
+    assert np.abs(np.abs(z) - 1).max() < 1e-3 and np.abs(z - w ** (a ^ b)).max() < 1e-3       # unit modulus, not 256
+    snapped = snap.Zeta16NoiseReducer(ctx).apply(ab)
+    assert np.abs(ctx.decrypt(snapped) - w ** (a ^ b)).max() < np.abs(z - w ** (a ^ b)).max() + 1e-7
+    out = x4.apply(snapped, enc(c))
+    got = aes_fhe.from_zeta(ctx.decrypt(out), 16)
+    assert np.array_equal(got, (a ^ b ^ c).astype(np.uint8))
