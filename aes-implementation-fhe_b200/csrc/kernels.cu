@@ -516,6 +516,95 @@ __global__ void k_fft_stage(KShape S, double* __restrict__ v, const u32* __restr
         }
     }
 }
+// The same transform in two launches instead of one per stage (butterflies of one stage are independent, so the values
+// are bit-identical to the stage-by-stage kernels and to the oracle).  n = N/2 complex points are split as hi * FFT_LOW + lo:
+//   k_fft_low : the stages len <= FFT_LOW stay inside one contiguous block of FFT_LOW points -> one CTA, shared memory;
+//               forward: bit-reversal gather on load, stages len = 2 .. FFT_LOW; inverse: stages FFT_LOW .. 2, bit-reversal
+//               scatter and the 1/n scaling on store;
+//   k_fft_high: the stages len > FFT_LOW couple points FFT_LOW apart -> one thread per lo holds the n / FFT_LOW values in
+//               registers (16 at N = 2^16; no such stage at N = 2^12).
+constexpr int FFT_LOW = 2048;
+constexpr int FFT_HI_MAX = 16;
+__device__ __forceinline__ void fft_butterfly(double& ar, double& ai, double& br, double& bi, double wr, double wi, int inverse) {
+    if (!inverse) {
+        const double tr = fsub_rn(fmul_rn(br, wr), fmul_rn(bi, wi));
+        const double ti = fadd_rn(fmul_rn(br, wi), fmul_rn(bi, wr));
+        const double xr = ar, xi = ai;
+        ar = fadd_rn(xr, tr); ai = fadd_rn(xi, ti);
+        br = fsub_rn(xr, tr); bi = fsub_rn(xi, ti);
+    } else {
+        const double dr = fsub_rn(ar, br), di = fsub_rn(ai, bi);
+        ar = fadd_rn(ar, br); ai = fadd_rn(ai, bi);
+        br = fsub_rn(fmul_rn(dr, wr), fmul_rn(di, wi));
+        bi = fadd_rn(fmul_rn(dr, wi), fmul_rn(di, wr));
+    }
+}
+__global__ void __launch_bounds__(FFT_LOW / 2)
+k_fft_low(KShape S, double* __restrict__ out, const double* __restrict__ in, const u32* __restrict__ rot,
+          const double* __restrict__ ksi, int inverse, double mul) {
+    CKKS_SHARED double sm[2 * FFT_LOW];
+    const int n = 1 << (S.logn - 1), bits = S.logn - 1;
+    const int blk = n < FFT_LOW ? n : FFT_LOW;                // points of this CTA (n >= 2048 for both built rings)
+    const size_t vec = (size_t)blockIdx.y << S.logn;          // batch item
+    const int base = blockIdx.x * blk;
+    FOR_THREADS {
+        for (int e = threadIdx.x; e < blk; e += blockDim.x) {
+            const int p = base + e;
+            const int src = inverse ? p : (int)(brev32((u32)p) >> (32 - bits));
+            sm[2 * e] = in[vec + 2 * (size_t)src];
+            sm[2 * e + 1] = in[vec + 2 * (size_t)src + 1];
+        }
+    }
+    BLOCK_SYNC;
+    for (int st = 0; (2 << st) <= blk; st++) {
+        const int len = inverse ? (blk >> st) : (2 << st);
+        const int lenh = len >> 1, lenq = len << 2, gap = (2 << S.logn) / lenq;
+        FOR_THREADS {
+            for (int b = threadIdx.x; b < blk / 2; b += blockDim.x) {
+                const int j = b % lenh, p0 = (b / lenh) * len + j, p1 = p0 + lenh;
+                const int rj = rot[j] % lenq;
+                const int idx = (inverse ? (lenq - rj) : rj) * gap;
+                fft_butterfly(sm[2 * p0], sm[2 * p0 + 1], sm[2 * p1], sm[2 * p1 + 1], ksi[2 * idx], ksi[2 * idx + 1], inverse);
+            }
+        }
+        BLOCK_SYNC;
+    }
+    FOR_THREADS {
+        for (int e = threadIdx.x; e < blk; e += blockDim.x) {
+            const int p = base + e;
+            const int dst = inverse ? (int)(brev32((u32)p) >> (32 - bits)) : p;
+            out[vec + 2 * (size_t)dst] = inverse ? fmul_rn(sm[2 * e], mul) : sm[2 * e];
+            out[vec + 2 * (size_t)dst + 1] = inverse ? fmul_rn(sm[2 * e + 1], mul) : sm[2 * e + 1];
+        }
+    }
+}
+// NH = n / FFT_LOW values per thread, INV: direction -- both compile-time so the register arrays are indexed statically
+template <int NH, int INV>
+__global__ void k_fft_high(KShape S, double* __restrict__ v, const u32* __restrict__ rot, const double* __restrict__ ksi) {
+    v += (size_t)blockIdx.y << S.logn;
+    FOR_THREADS {
+        const int lo = blockIdx.x * TPB + threadIdx.x;        // lo < FFT_LOW
+        double xr[NH], xi[NH];
+#pragma unroll
+        for (int h = 0; h < NH; h++) { xr[h] = v[2 * ((size_t)h * FFT_LOW + lo)]; xi[h] = v[2 * ((size_t)h * FFT_LOW + lo) + 1]; }
+#pragma unroll
+        for (int st = 0; (2 << st) <= NH; st++) {
+            const int hl = INV ? (NH >> st) : (2 << st);      // stage length in units of FFT_LOW
+            const int hh = hl >> 1;
+            const int len = hl * FFT_LOW, lenq = len << 2, gap = (2 << S.logn) / lenq;
+#pragma unroll
+            for (int b = 0; b < NH / 2; b++) {
+                const int jh = b % hh, h0 = (b / hh) * hl + jh, h1 = h0 + hh;
+                const int j = jh * FFT_LOW + lo;
+                const int rj = rot[j] % lenq;
+                const int idx = (INV ? (lenq - rj) : rj) * gap;
+                fft_butterfly(xr[h0], xi[h0], xr[h1], xi[h1], ksi[2 * idx], ksi[2 * idx + 1], INV);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < NH; h++) { v[2 * ((size_t)h * FFT_LOW + lo)] = xr[h]; v[2 * ((size_t)h * FFT_LOW + lo) + 1] = xi[h]; }
+    }
+}
 __global__ void k_bitrev_copy(KShape S, double* __restrict__ out, const double* __restrict__ in, double mul) {
     out += (size_t)blockIdx.y << S.logn;
     in += (size_t)blockIdx.y << S.logn;
@@ -702,8 +791,16 @@ void launch_reduce_i64(KShape S, u64* out, const i64* v, const LimbList& L, dev_
     if (L.n) LAUNCH(k_reduce_i64, grid3(S, L.n, nb < 1 ? 1 : nb), dim3(TPB), st, S, out, v, L, out_bs);
 }
 // decode direction: w (n complex, natural order) -> z in `out`
+#ifndef FFT_FUSED
+#define FFT_FUSED 1            // 0: one launch per butterfly stage (round-1 form, kept for A/B and as the reference form)
+#endif
 void launch_special_fft(KShape S, double* out, const double* w, const u32* rot, const double* ksi, dev_stream st, int nb) {
     const int n = 1 << (S.logn - 1);
+    if (FFT_FUSED && (n == FFT_LOW || n == FFT_LOW * FFT_HI_MAX)) {
+        LAUNCH(k_fft_low, dim3(n / FFT_LOW, nb), dim3(FFT_LOW / 2), st, S, out, w, rot, ksi, 0, 1.0);
+        if (n > FFT_LOW) LAUNCH((k_fft_high<FFT_HI_MAX, 0>), dim3(FFT_LOW / TPB, nb), dim3(TPB), st, S, out, rot, ksi);
+        return;
+    }
     LAUNCH(k_bitrev_copy, dim3(n / TPB, nb), dim3(TPB), st, S, out, w, 1.0);
     for (int len = 2; len <= n; len <<= 1)
         LAUNCH(k_fft_stage, dim3(n / 2 / TPB, nb), dim3(TPB), st, S, out, rot, ksi, len, 0);
@@ -711,6 +808,11 @@ void launch_special_fft(KShape S, double* out, const double* w, const u32* rot, 
 // encode direction: z -> w (includes 1/n); `z` is overwritten as scratch
 void launch_special_ifft(KShape S, double* out, double* z, const u32* rot, const double* ksi, dev_stream st, int nb) {
     const int n = 1 << (S.logn - 1);
+    if (FFT_FUSED && (n == FFT_LOW || n == FFT_LOW * FFT_HI_MAX)) {
+        if (n > FFT_LOW) LAUNCH((k_fft_high<FFT_HI_MAX, 1>), dim3(FFT_LOW / TPB, nb), dim3(TPB), st, S, z, rot, ksi);
+        LAUNCH(k_fft_low, dim3(n / FFT_LOW, nb), dim3(FFT_LOW / 2), st, S, out, z, rot, ksi, 1, 1.0 / (double)n);
+        return;
+    }
     for (int len = n; len >= 2; len >>= 1)
         LAUNCH(k_fft_stage, dim3(n / 2 / TPB, nb), dim3(TPB), st, S, z, rot, ksi, len, 1);
     LAUNCH(k_bitrev_copy, dim3(n / TPB, nb), dim3(TPB), st, S, out, z, 1.0 / (double)n);
