@@ -14,3 +14,9 @@ for p in (str(ROOT), str(PKG), str(ROOT / "tests")):
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "slow: long-running")
+
+
+# tests/_refscratch/ is the staged byte-for-byte copy of the reference's modules (tests/refload.py); it carries the
+# reference's own test/ directory, which must not be collected as part of this suite.
+collect_ignore_glob = ["_refscratch/*", "_refscratch/**/*"]
+collect_ignore = ["_refscratch"]
