@@ -77,3 +77,29 @@ __device__ __forceinline__ void mac128(u64& hi, u64& lo, u64 a, u64 b) {
     lo += pl;
     hi += ph + (lo < pl);
 }
+
+// ------------------------------------------------------------------ FP64-pipe modular arithmetic (moduli below CKKS_FP_LIMIT)
+// The B200's full-rate FP64 pipe multiplies modulo a ~2^50 prime about three times as fast as the 64-bit integer
+// multiplier (profiles/r1_pipe_peaks.txt, profiles/r2_fp64_round.txt): the NTT butterflies of the scale primes (ntt.cu) and
+// the basis conversion towards them (kernels.cu: k_base_convert_fp) hold residues as exact integers in doubles.
+#define CKKS_FP_LIMIT 1576258512130867ull     /* 1.4 * 2^50: lazy values up to 5.1 q stay below 2^53 */
+// a * w mod q as an exact integer in (-2q, 2q): a any integer with |a| < 2^53, w < q < 2^51, wq = fl(w / q).
+//   h = fl(a w), l = a w - h (exact, FMA), c = rint(a wq) (quotient, off by at most 2), r = (h - c q) + l (both exact)
+//   |r| <= (0.5 + |a| 2^-52) q
+__device__ __forceinline__ double modmul_fp(double a, double w, double wq, double q) {
+    const double h = fmul_rn(a, w);
+    const double l = ffma_rn(a, w, -h);
+    const double c = frint(fmul_rn(a, wq));
+    return fadd_rn(ffma_rn(-c, q, h), l);
+}
+// fold a lazy value (|x| < 2^53) to |x| <= q/2 (+ one q when the quotient estimate is off by one)
+__device__ __forceinline__ double fold_fp(double x, double q, double qinv) {
+    return ffma_rn(-frint(fmul_rn(x, qinv)), q, x);
+}
+// exact canonical residue in [0,q) as an integer
+__device__ __forceinline__ u64 canon_fp(double x, double q, double qinv) {
+    x = fold_fp(x, q, qinv);
+    x = x < 0.0 ? fadd_rn(x, q) : x;
+    x = x >= q ? fsub_rn(x, q) : x;
+    return (u64)d2ll_rn(x);
+}

@@ -173,7 +173,9 @@ Engine::Engine(const Params& P) : prm(P) {
     arenas[0] = &main_arena;
     if (const char* v = getenv("CKKS_NTT_FUSE")) fuse_ntt = atoi(v) != 0;
     if (const char* v = getenv("CKKS_TENSOR_FUSE")) fuse_tensor = atoi(v) != 0;
-    if (const char* v = getenv("CKKS_BC_MMA")) bc_mma = atoi(v) != 0;
+    if (const char* v = getenv("CKKS_BC_MMA")) bc_mode = atoi(v) != 0 ? BC_MMA : bc_mode;
+    if (const char* v = getenv("CKKS_BC_FP")) bc_mode = atoi(v) != 0 ? BC_FP : (bc_mode == BC_FP ? BC_INT : bc_mode);
+    if (const char* v = getenv("CKKS_BC_FP_INT_EVERY")) bc_fp_int_every = atoi(v);
     int ntt_cluster = 0;                                                                 // DESIGN.md 8.1; a field of THIS engine's tables
     if (const char* v = getenv("CKKS_NTT_CLUSTER")) ntt_cluster = atoi(v);
     if (const char* v = getenv("CKKS_CHEB_DEGREE")) prm.boot.cheb_degree = atoi(v);      // tuning / A-B runs only
@@ -1095,6 +1097,32 @@ BaseConvTable Engine::make_bc_table(const std::vector<int>& src, const std::vect
     }
     for (int t = 0; t < T.nt; t++) { T.tgt[t] = (unsigned char)tgt[t]; T.orow[t] = (unsigned char)orow[t]; }
     T.hat = upload(this, hat, owned);           // exact size, freed with the engine
+    {
+        // FP64 path (kernels.cu: k_base_convert_fp): which targets take it, which sources are split, the constants as doubles
+        std::vector<double> hf((size_t)T.nt * T.ns * 4, 0.0);
+        T.swide = 0;
+        for (int i = 0; i < T.ns; i++)
+            if (mod[src[i]] >> 52) T.swide |= 1u << i;
+        int eligible = 0;
+        for (int t = 0; t < T.nt; t++) {
+            const u64 qt = mod[tgt[t]];
+            bool fp = qt < CKKS_FP_LIMIT;
+            // CKKS_BC_FP_INT_EVERY=k: every k-th FP64-capable target stays on the integer pipe (pipe balance, A/B)
+            if (fp && bc_fp_int_every > 0 && (++eligible % bc_fp_int_every) == 0) fp = false;
+            T.tfp[t] = fp ? 1 : 0;
+            T.tqinv[t] = 1.0 / (double)qt;
+            T.negDd[t] = (double)T.negD[t];
+            T.negDq[t] = (double)T.negD[t] / (double)qt;
+            if (!fp) continue;
+            for (int i = 0; i < T.ns; i++) {
+                const u64 h = hat[(size_t)i * T.nt + t], h32 = mulmod_h(h, (1ull << 32) % qt, qt);
+                double* e = &hf[((size_t)t * T.ns + i) * 4];
+                e[0] = (double)h;   e[1] = (double)h / (double)qt;
+                e[2] = (double)h32; e[3] = (double)h32 / (double)qt;
+            }
+        }
+        T.hatf = upload(this, hf, owned);
+    }
     if (T.ns <= BC_MMA_MAX_SRC) {
         // tensor-core path (kernels.cu: k_base_convert_mma): the hat matrix cut into bytes, Toeplitz-expanded over the
         // 16 diagonals and stored in mma.m16n8k32 A-fragment order; 2^(8d) mod q_t for the recombination
@@ -1248,12 +1276,17 @@ Decomp Engine::decompose(const u64* d, int level, const u64* times, int nb, size
         const BaseConvTable* tabs = modup_tables_dev(level);
         const int ns_last = nq - (beta - 1) * prm.alpha;
         const int nfull = ns_last == prm.alpha ? beta : beta - 1;
+        // FP64 path: its branch-free form allows a wide (60/61-bit) source only in position 0 of a table
+        int mode = bc_mode;
+        if (mode == BC_FP)
+            for (int j = 0; j < beta; j++)
+                if (modup_table(level, j).swide & ~1u) mode = BC_FP_GENERIC;
         if (nfull)
-            launch_base_convert(ks, D.ext, coef, tabs, 1, prm.alpha, rows, nfull, 0, (size_t)rows * n, st, bc_mma, nb,
+            launch_base_convert(ks, D.ext, coef, tabs, 1, prm.alpha, rows, nfull, 0, (size_t)rows * n, st, mode, nb,
                                 (size_t)nq * n, eb);
         if (nfull < beta)
             launch_base_convert(ks, D.ext + (size_t)nfull * rows * n, coef, tabs + nfull, 1, ns_last, rows, 1, 0,
-                                (size_t)rows * n, st, bc_mma, nb, (size_t)nq * n, eb);
+                                (size_t)rows * n, st, mode, nb, (size_t)nq * n, eb);
     }
     // one batched forward NTT over the converted rows of all digits (z = digit) of all batch items
     run_ntt(D.ext, D.ext, J, false, modup_limbs * nb);
@@ -1292,8 +1325,9 @@ void Engine::ks_moddown(u64* acc, int level, int drop, u64* out, int nb) {
     ntt_rows(acc, prow, pmod, true, 2, (size_t)rows * n, nb, (size_t)2 * rows * n);
     u64* conv = alloc((size_t)nb * 2 * nout * n);
     // [nb][2] slices with uniform strides: the batch folds into the slice count
+    const int bcm = (bc_mode == BC_FP && (moddown_table(level, drop).swide & ~1u)) ? BC_FP_GENERIC : bc_mode;
     launch_base_convert(ks, conv, acc, moddown_table_dev(level, drop), 0, K() + drop, nout, 2 * nb, (size_t)rows * n,
-                        (size_t)nout * n, st, bc_mma);
+                        (size_t)nout * n, st, bcm);
     std::vector<int> qi = mods_q(level - drop);
     if (fuse_ntt) {
         // out = (acc - NTT(conv)) * (P q_dropped)^-1 as the epilogue of the transform's second pass

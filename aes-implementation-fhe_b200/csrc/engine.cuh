@@ -258,7 +258,10 @@ class Engine {
                   size_t zstride = 0, int nb = 1, size_t bstride = 0);
     void run_ntt(const u64* src, u64* dst, const NttJob& J, bool inverse, long limbs, const u64* src2 = nullptr);
     void run_ntt_fused(const u64* src, u64* dst, const NttJob& J, const NttFuse& F, long limbs);
-    bool bc_mma = false;                   // CKKS_BC_MMA=1: basis conversion as a byte-sliced u8 tensor-core GEMM (measured slower: profiles/README.md)
+    // basis conversion: BC_FP (default) = scale-prime targets on the FP64 pipe, 60/61-bit targets on the integer pipe;
+    // CKKS_BC_FP=0: every target on the integer pipe; CKKS_BC_MMA=1: byte-sliced u8 tensor-core GEMM (measured slower: profiles/README.md)
+    int bc_mode = BC_FP;
+    int bc_fp_int_every = 0;               // CKKS_BC_FP_INT_EVERY=k: every k-th FP64-capable target stays on the integer pipe
     bool fuse_tensor = true;               // CKKS_TENSOR_FUSE=0: ct x ct writes its tensor product (k_tensor) first
     bool fuse_ntt = true;                  // CKKS_NTT_FUSE=0: stand-alone lift / subtract-scale kernels (A/B timing)
     void profile_begin();

@@ -282,6 +282,167 @@ k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in, cons
     }
 }
 
+// ------------------------------------------------------------------ basis conversion on the FP64 pipe (+ the integer pipe)
+// The same sums as k_base_convert, evaluated per target on the pipe that suits its modulus.  A target below
+// CKKS_FP_LIMIT (the ~2^50 scale primes, and the special primes of the default chain) is a sum of exact FP64 modular
+// products (common.cuh: modmul_fp, 5 FP64-pipe instructions + 1 rounding each, measured 11.1 per clock and SM against 4.8
+// 128-bit integer multiply-accumulates):
+//     out_t = canon( sum_i y_i * hat[i][t] mod q_t ),   residues of the products kept as exact integers in doubles.
+// A source modulus of 60/61 bits (q_0; 61-bit special primes if a chain has them) gives y_i that a double cannot hold: it
+// enters as y_i = yh 2^32 + yl with a second constant hat 2^32 mod q_t.  Two accumulators (even / odd sources) are folded
+// every four sources: |acc| <= 0.51 q + 4 * 0.85 q stays far below 2^53.  Targets of 60/61 bits keep the 128-bit integer
+// multiply-accumulate of k_base_convert; warps working on them run beside FP64 warps on the same SM.  Results are
+// canonical residues, identical to k_base_convert's bit for bit (the arithmetic is exact on both paths).
+// GENERIC = 0: only source 0 may be wide (q_0 in the first digit; warp-uniform, decided once per CTA): the source loop
+// is branch-free.  GENERIC = 1: any source may be wide (run-time mask; the compiler predicates both forms).
+#ifndef BC_FP_MIN_BLOCKS
+#define BC_FP_MIN_BLOCKS 4
+#endif
+struct BcFpTarget { double q, qinv, negD, negDq; };
+// sum_i y_i * hat_i mod q_t as a lazy double: products in groups of five (tree of exact additions), one fold between
+// groups.  Bounds in units of q_t <= 1.4 * 2^50 (2^53 = 5.71 q): a product of a narrow source is at most 0.85, of a half
+// of a wide source 0.5; first group (+ the high half of source 0) <= 4.75, later: 0.51 + 4.25 = 4.76; the caller may add
+// one more product of a small operand (0.5).
+template <int NS, bool W0>
+__device__ __forceinline__ double bc_fp_sum(const double (&yl)[NS], double yh0, const double* hf, const double* hw, double q,
+                                            double qinv) {
+    double s = 0.0;
+#pragma unroll
+    for (int g0 = 0; g0 < NS; g0 += 5) {
+        double r[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++)
+            r[j] = g0 + j < NS ? modmul_fp(yl[g0 + j], hf[2 * (g0 + j)], hf[2 * (g0 + j) + 1], q) : 0.0;
+        double p = fadd_rn(r[0], r[1]);
+        if (g0 + 2 < NS) p = fadd_rn(p, g0 + 3 < NS ? fadd_rn(r[2], r[3]) : r[2]);
+        if (g0 + 4 < NS) p = fadd_rn(p, r[4]);
+        if (g0 == 0) s = W0 ? fadd_rn(p, modmul_fp(yh0, hw[0], hw[1], q)) : p;
+        else s = fadd_rn(fold_fp(s, q, qinv), p);
+    }
+    return s;
+}
+template <int NS, int GENERIC>
+__global__ void __launch_bounds__(TPB, BC_FP_MIN_BLOCKS)
+k_base_convert_fp(KShape S, u64* __restrict__ out, const u64* __restrict__ in, const BaseConvTable* __restrict__ tabs,
+                  int tab_zstride, size_t in_zs, size_t out_zs, int nz, size_t in_bs, size_t out_bs) {
+    constexpr int HW = GENERIC ? 4 : 2;                 // doubles per (target, source)
+    CKKS_SHARED u64 s_hat[BC_CHUNK * NS];
+    CKKS_SHARED u64 s_r64[BC_CHUNK];
+    CKKS_SHARED __align__(16) double s_hf[BC_CHUNK * NS * HW];
+    CKKS_SHARED __align__(16) double s_hw[BC_CHUNK * 2];             // source 0's second constant pair (GENERIC = 0)
+    CKKS_SHARED BcFpTarget s_tg[BC_CHUNK];
+    CKKS_SHARED int s_nint;                                          // integer-pipe targets in this chunk
+    const size_t N = (size_t)1 << S.logn;
+    const unsigned zb = blockIdx.z / (unsigned)nz, zz = blockIdx.z - zb * (unsigned)nz;     // batch item, slice
+    const BaseConvTable& T = tabs[zz * tab_zstride];
+    const int nt = T.nt;
+    const int tbeg = blockIdx.y * BC_CHUNK, tend = tbeg + BC_CHUNK < nt ? tbeg + BC_CHUNK : nt;
+    if (tbeg >= nt) return;
+    FOR_THREADS {
+        const int cnt = (tend - tbeg) * NS;
+        for (int e = threadIdx.x; e < cnt; e += TPB) {
+            const int t = tbeg + e / NS, i = e % NS;
+            s_hat[e] = ldg(T.hat + i * nt + t);
+            const double* h = T.hatf + ((size_t)t * NS + i) * 4;
+#pragma unroll
+            for (int c = 0; c < HW; c++) s_hf[e * HW + c] = ldg(h + c);
+            if (!GENERIC && i == 0) { s_hw[(t - tbeg) * 2] = ldg(h + 2); s_hw[(t - tbeg) * 2 + 1] = ldg(h + 3); }
+        }
+        for (int t = tbeg + threadIdx.x; t < tend; t += TPB) {
+            const ModConst m = S.mc[T.tgt[t]];
+            s_r64[t - tbeg] = barrett_reduce128(1, 0, m);         // 2^64 mod q_t
+            BcFpTarget g;
+            g.q = ull2d_rn(m.q); g.qinv = T.tqinv[t]; g.negD = T.negDd[t]; g.negDq = T.negDq[t];
+            s_tg[t - tbeg] = g;
+        }
+        if (threadIdx.x == 0) {
+            int c = 0;
+            for (int t = tbeg; t < tend; t++) c += T.tfp[t] ? 0 : 1;
+            s_nint = c;
+        }
+    }
+    BLOCK_SYNC;
+    FOR_THREADS {
+        const u32 k = blockIdx.x * TPB + threadIdx.x;
+        const u64* src = in + zz * in_zs + zb * in_bs;
+        u64* dst = out + zz * out_zs + zb * out_bs;
+        const u32 wide = T.swide;
+        const int exact = T.exact;
+        // the FP64 targets read the y_i as doubles only (low / high halves for a wide source); the integer residues are
+        // rebuilt from them for the (few) integer-pipe targets, so the main loop does not carry both forms in registers
+        double yl[NS], yh[GENERIC ? NS : 1];
+        double v = 0.0;
+        yh[0] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            const u64 y = shoup_mul(src[(size_t)T.srow[i] * N + k], T.hatinv[i], T.hatinv_s[i], S.mc[T.src[i]].q);
+            const double yd = ull2d_rn(y);
+            v = fadd_rn(v, fmul_rn(yd, T.inv_src[i]));
+            if ((GENERIC || i == 0) && (wide >> i & 1)) {
+                yl[i] = ull2d_rn(y & 0xffffffffull);
+                yh[GENERIC ? i : 0] = ull2d_rn(y >> 32);
+            } else {
+                yl[i] = yd;
+                if (GENERIC) yh[i] = 0.0;
+            }
+        }
+        const double ud = exact ? frint(v) : 0.0;        // overflow count of the fast conversion (0..NS)
+        for (int t = tbeg; t < tend; t++) {
+            if (!T.tfp[t]) continue;
+            const BcFpTarget g = s_tg[t - tbeg];
+            const double* hf = s_hf + (t - tbeg) * NS * HW;
+            double s;
+            if (GENERIC) {
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < NS; i++) {
+                    if (wide >> i & 1) {
+                        a0 = fadd_rn(a0, modmul_fp(yl[i], hf[4 * i], hf[4 * i + 1], g.q));
+                        a1 = fadd_rn(a1, modmul_fp(yh[GENERIC ? i : 0], hf[4 * i + 2], hf[4 * i + 3], g.q));
+                    } else if (i & 1) {
+                        a1 = fadd_rn(a1, modmul_fp(yl[i], hf[4 * i], hf[4 * i + 1], g.q));
+                    } else {
+                        a0 = fadd_rn(a0, modmul_fp(yl[i], hf[4 * i], hf[4 * i + 1], g.q));
+                    }
+                    if ((i & 3) == 3 && i + 1 < NS) { a0 = fold_fp(a0, g.q, g.qinv); a1 = fold_fp(a1, g.q, g.qinv); }
+                }
+                s = fadd_rn(fold_fp(a0, g.q, g.qinv), fold_fp(a1, g.q, g.qinv));
+            } else if (wide & 1) {
+                s = bc_fp_sum<NS, true>(yl, yh[0], hf, s_hw + (t - tbeg) * 2, g.q, g.qinv);
+            } else {
+                s = bc_fp_sum<NS, false>(yl, 0.0, hf, nullptr, g.q, g.qinv);
+            }
+            if (exact) s = fadd_rn(s, modmul_fp(ud, g.negD, g.negDq, g.q));             // - u * D  (mod q_t)
+            dst[(size_t)T.orow[t] * N + k] = canon_fp(s, g.q, g.qinv);
+        }
+        if (s_nint) {
+            u64 y[NS];
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                y[i] = (u64)d2ll_rn(yl[i]);
+                if ((GENERIC || i == 0) && (wide >> i & 1)) y[i] |= (u64)d2ll_rn(yh[GENERIC ? i : 0]) << 32;
+            }
+            const u64 u = (u64)d2ll_rn(ud);
+            for (int t = tbeg; t < tend; t++) {
+                if (T.tfp[t]) continue;
+                const ModConst m = S.mc[T.tgt[t]];
+                const u64* hat = s_hat + (t - tbeg) * NS;
+                u64 hi = 0, lo = 0;
+#pragma unroll
+                for (int i = 0; i < NS; i++) mac128(hi, lo, y[i], hat[i]);
+                if (exact) mac128(hi, lo, u, T.negD[t]);
+                const u64 r64 = s_r64[t - tbeg];
+                const u64 h1 = barrett_reduce64(hi, m);
+                u64 h2 = 0, l2 = lo;
+                const u64 pl = h1 * r64;
+                l2 += pl;
+                h2 = mulhi64(h1, r64) + (l2 < pl);
+                dst[(size_t)T.orow[t] * N + k] = barrett_reduce128(h2, l2, m);
+            }
+        }
+    }
+}
+
 #ifndef CKKS_EMU
 // ------------------------------------------------------------------ basis conversion on the tensor cores
 // The same sum  out[n][t] = sum_i y_i[n] * hat[i][t]  (mod q_t), as an 8-bit integer GEMM.  y_i and hat are cut into
@@ -750,12 +911,25 @@ void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u
                nq, alpha, addend, PmodQ, accumulate, kb);
 }
 void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns,
-                         int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st, bool mma, int nb, size_t in_bs,
+                         int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st, int mode, int nb, size_t in_bs,
                          size_t out_bs) {
     if (!nz || !max_nt) return;
     if (nb < 1) nb = 1;
+    if (mode == BC_FP || mode == BC_FP_GENERIC) {
+        dim3 g((1u << S.logn) / TPB, (max_nt + BC_CHUNK - 1) / BC_CHUNK, nz * nb);
+#define BCF_CASE(n) case n: \
+        if (mode == BC_FP) LAUNCH((k_base_convert_fp<n, 0>), g, dim3(TPB), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs, nz, in_bs, out_bs); \
+        else LAUNCH((k_base_convert_fp<n, 1>), g, dim3(TPB), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs, nz, in_bs, out_bs); \
+        return;
+        switch (ns) {
+            BCF_CASE(1) BCF_CASE(2) BCF_CASE(3) BCF_CASE(4) BCF_CASE(5) BCF_CASE(6) BCF_CASE(7) BCF_CASE(8) BCF_CASE(9) BCF_CASE(10)
+            BCF_CASE(11) BCF_CASE(12) BCF_CASE(13) BCF_CASE(14) BCF_CASE(15) BCF_CASE(16)
+            default: throw std::runtime_error("base_convert: unsupported source count");
+        }
+#undef BCF_CASE
+    }
 #ifndef CKKS_EMU
-    if (mma && ns <= BC_MMA_MAX_SRC) {
+    if (mode == BC_MMA && ns <= BC_MMA_MAX_SRC) {
         dim3 gm((1u << S.logn) / BCM_TILE, ((max_nt + 7) / 8 + BCM_TG_PER_CTA - 1) / BCM_TG_PER_CTA, nz * nb);
 #define BCM_CASE(n) case n: LAUNCH(k_base_convert_mma<n>, gm, dim3(BCM_TILE), st, S, out, in, tabs_dev, tab_zstride, in_zs, out_zs, nz, in_bs, out_bs); return;
         switch (ns) { BCM_CASE(1) BCM_CASE(2) BCM_CASE(3) BCM_CASE(4) BCM_CASE(5) BCM_CASE(6) BCM_CASE(7) BCM_CASE(8) }

@@ -37,7 +37,18 @@ struct BaseConvTable {
     // order, [target group of 8][diagonal pair j][k-step][lane] x 16 bytes, and 2^(8 d) mod q_t, [nt][16]
     const void* afrag;
     const u64* pow8;
+    // FP64 path (k_base_convert_fp): a target below CKKS_FP_LIMIT may be evaluated on the FP64 pipe as a sum of exact
+    // FP64 modular products; a source whose residues do not fit a double exactly (modulus >= 2^52) enters as two halves
+    unsigned char tfp[BC_MAX_TGT];     // 1: target t takes the FP64 path
+    u32 swide;                         // bit i: source i is split at 2^32
+    const double* hatf;                // [nt][ns][4]: hat, hat / q_t, hat 2^32 mod q_t, (hat 2^32 mod q_t) / q_t  (FP64 targets)
+    double tqinv[BC_MAX_TGT];          // 1 / q_t
+    double negDd[BC_MAX_TGT];          // negD as a double and its quotient by q_t
+    double negDq[BC_MAX_TGT];
 };
+// how launch_base_convert evaluates the sums
+// BC_FP: only source 0 of a table may be wide (branch-free source loop); BC_FP_GENERIC: any source (run-time mask)
+enum BcMode { BC_INT = 0, BC_MMA = 1, BC_FP = 2, BC_FP_GENERIC = 3 };
 // shape shared by all kernels: N coefficients per row, modulus table
 struct KShape {
     const ModConst* mc;
@@ -69,7 +80,7 @@ void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u
 // nz independent conversions: slice z reads in + z*in_zs, writes out + z*out_zs, with table tabs_dev[z*tab_zstride]
 // (device memory); every table of the launch has exactly `ns` sources and at most `max_nt` targets.  nb batch items
 // repeat the nz slices at in + b*in_bs / out + b*out_bs.
-void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns, int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st, bool mma = false, int nb = 1, size_t in_bs = 0, size_t out_bs = 0);
+void launch_base_convert(KShape S, u64* out, const u64* in, const BaseConvTable* tabs_dev, int tab_zstride, int ns, int max_nt, int nz, size_t in_zs, size_t out_zs, dev_stream st, int mode = BC_INT, int nb = 1, size_t in_bs = 0, size_t out_bs = 0);
 void launch_rescale_delta(KShape S, u64* delta, const u64* last, const LimbList& L, int last_mod, int npoly, PolyStride ps, dev_stream st);
 void launch_center_lift(KShape S, u64* out, const u64* in, const LimbList& L, int src_mod, int npoly, PolyStride ps, dev_stream st);
 void launch_sample_uniform(KShape S, u64* out, const LimbList& L, u64 seed, u64 stream, dev_stream st);

@@ -47,8 +47,8 @@ constexpr int kThreads = 256;
 #ifndef NTT_FP64
 #define NTT_FP64 1            // 0: every limb takes the integer path (A/B measurement)
 #endif
-// FP64 path bound: |x| < 5.1 q must stay below 2^53
-#define NTT_FP_LIMIT 1576258512130867ull     /* 1.4 * 2^50 */
+// FP64 path bound: |x| < 5.1 q must stay below 2^53 (CKKS_FP_LIMIT, common.cuh)
+#define NTT_FP_LIMIT CKKS_FP_LIMIT
 
 __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
 __device__ __forceinline__ bool use_fp(u64 q) { return NTT_FP64 && q < NTT_FP_LIMIT; }
@@ -181,26 +181,7 @@ __device__ __forceinline__ u64 canon4(u64 v, u64 q) {
 __device__ __forceinline__ u64 canon2(u64 v, u64 q) { return v >= q ? v - q : v; }
 
 // ============================================================================================ FP64 path
-// a * w mod q as an exact integer in (-2q, 2q): a any integer with |a| < 2^53, w < q < 2^51, wq = fl(w / q).
-//   h = fl(a w), l = a w - h (exact, FMA), c = rint(a wq) (quotient, off by at most 2), r = (h - c q) + l (both exact)
-__device__ __forceinline__ double modmul_fp(double a, double w, double wq, double q) {
-    const double h = fmul_rn(a, w);
-    const double l = ffma_rn(a, w, -h);
-    const double c = frint(fmul_rn(a, wq));
-    return fadd_rn(ffma_rn(-c, q, h), l);
-}
-// fold a lazy value (|x| < 2^53) to |x| <= q/2 (+ one q when the quotient estimate is off by one)
-__device__ __forceinline__ double fold_fp(double x, double q, double qinv) {
-    return ffma_rn(-frint(fmul_rn(x, qinv)), q, x);
-}
-// exact canonical residue in [0,q) as an integer
-__device__ __forceinline__ u64 canon_fp(double x, double q, double qinv) {
-    x = fold_fp(x, q, qinv);
-    x = x < 0.0 ? fadd_rn(x, q) : x;
-    x = x >= q ? fsub_rn(x, q) : x;
-    return (u64)d2ll_rn(x);
-}
-
+// modmul_fp / fold_fp / canon_fp: common.cuh (shared with the basis conversion)
 struct FpMod {
     double q, qinv, ninv, ninvq, w1n, w1nq;
 };

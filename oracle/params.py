@@ -104,7 +104,7 @@ class CKKSParams:
         return sum(math.log2(x) for x in self.q + self.p)
 
 
-def make_params(logn: int = 16, levels: int = 20, scale_bits: int = 50, q0_bits: int = 60, p_bits: int = 61,
+def make_params(logn: int = 16, levels: int = 20, scale_bits: int = 50, q0_bits: int = 60, p_bits: int = 50,
                 alpha: int = 0, dnum: int = 3, hamming_weight: int = 192, fresh_level: int = -1,
                 top_levels: int = 0, top_bits: int = 58) -> CKKSParams:
     """Deterministic parameter construction.  `levels` = L (number of scale primes).  With top_levels > 0 the highest

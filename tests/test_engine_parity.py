@@ -19,17 +19,23 @@ CASES = [
     pytest.param(("emu", 16, 5), id="emu-n16"),      # the two-round pass A (LOGR = 8) only exists at N = 2^16
     pytest.param(("cuda", 12, 6), id="cuda-n12", marks=pytest.mark.gpu),
     pytest.param(("cuda", 16, 5), id="cuda-n16", marks=pytest.mark.gpu),
-    # the benchmark's own parameter set (bench.py): 22 ciphertext primes, 7 special primes, dnum 3 (digits of 8 limbs, the
-    # last one ragged at the fresh level 14), Hamming weight 192 -- k_base_convert<7/8>, the 7-prime ModDown and the ragged
-    # ModUp are compared bit for bit here, not only through decoded bytes
+    # the benchmark's own parameter set (bench.py): 22 ciphertext primes, 9 special primes below 2^50, dnum 3 (digits of 8
+    # limbs, the last one ragged at the fresh level 14), Hamming weight 192 -- k_base_convert_fp<7/8/9/10>, the 9-prime
+    # ModDown and the ragged ModUp are compared bit for bit here, not only through decoded bytes
     pytest.param(("cuda", 16, 21, 192, 14), id="cuda-n16-bench", marks=pytest.mark.gpu),
+    # the round-1 chain: 61-bit special primes (integer-pipe NTT limbs, wide sources and integer targets in the basis
+    # conversion: k_base_convert_fp<NS, 1> and the 128-bit multiply-accumulate branch)
+    pytest.param(("emu", 12, 6, 64, -1, 5, 61), id="emu-n12-p61"),
+    pytest.param(("cuda", 16, 21, 192, 14, 5, 61), id="cuda-n16-bench-p61", marks=pytest.mark.gpu),
 ]
 
 
 class Pair:
-    def __init__(self, which, logn, levels, hw=64, fresh=-1, seed=5):
+    def __init__(self, which, logn, levels, hw=64, fresh=-1, seed=5, p_bits=None):
         mod = backend.use_emulation() if which == "emu" else backend.use_cuda()
         kw = dict(fresh_level=fresh) if fresh >= 0 else {}
+        if p_bits is not None:
+            kw["p_bits"] = p_bits
         self.eng = mod.Engine(logn=logn, levels=levels, dnum=3, hamming_weight=hw, seed=seed, **kw)
         self.params = make_params(logn=logn, levels=levels, dnum=3, hamming_weight=hw, **kw)
         self.orc = OracleCKKS(self.params, seed=seed)
