@@ -222,6 +222,98 @@ __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restric
     }
 }
 
+// The same inner product with the digit count and the number of batch items handled together as template parameters:
+// every digit word of NB items (and the addend / accumulator words) is requested before the first multiply-accumulate,
+// so a thread keeps up to NB * BETA + 2 BETA + 4 NB loads in flight instead of BETA (the run-time-sized loop above is
+// bound by the latency of its loads: ncu long_scoreboard 7.9 per issue, 2.1 TB/s).  Same arithmetic, same results.
+template <bool TENSOR, int NB, int BETA>
+__global__ void __launch_bounds__(TPB)
+k_ks_inner_mlp(KShape S, u64* __restrict__ acc, const u64* __restrict__ ext, const u64* __restrict__ own,
+               const u64* __restrict__ evk, const u32* __restrict__ perm, const GRID_CONST LimbList L,
+               const GRID_CONST LimbList ERow, int rows, int evk_rows, int nq, int alpha,
+               const u64* __restrict__ addend, const GRID_CONST ScalarList PmodQ, int accumulate,
+               const GRID_CONST KsBatch kb) {
+    static_assert(BETA >= 1 && BETA <= 4, "no intermediate reduction of the 128-bit sums below five digits");
+    const int row = blockIdx.y;
+    const ModConst m = S.mc[L.idx[row]];
+    const size_t er = ERow.idx[row];
+    const size_t N = (size_t)1 << S.logn;
+    const int jown = row < nq ? row / alpha : -1;
+    const bool qrow = row < nq;
+    FOR_THREADS {
+        const u32 k = blockIdx.x * TPB + threadIdx.x;
+        const u32 ks = perm ? ldg(perm + k) : k;
+        u64 e0[BETA], e1[BETA];
+#pragma unroll
+        for (int j = 0; j < BETA; j++) {
+            const u64* e = evk + ((size_t)j * 2 * evk_rows + er) * N + k;
+            e0[j] = ldg(e);
+            e1[j] = ldg(e + (size_t)evk_rows * N);
+        }
+        for (int b0 = 0; b0 < kb.nb; b0 += NB) {
+            u64 x[NB][BETA], p0[NB], p1[NB], p2[NB], p3[NB], c0[NB], c1[NB];
+#pragma unroll
+            for (int bi = 0; bi < NB; bi++) {
+                const int b = b0 + bi < kb.nb ? b0 + bi : kb.nb - 1;        // a short last group repeats its last item
+                const u64* xext = ext + b * kb.ext;
+                const u64* xown = own + b * kb.own;
+                const u64* xadd = addend ? addend + b * kb.addend : nullptr;
+                const u64* xacc = acc + b * kb.acc;
+                p0[bi] = p1[bi] = p2[bi] = p3[bi] = c0[bi] = c1[bi] = 0;
+#pragma unroll
+                for (int j = 0; j < BETA; j++) {
+                    if (j == jown) x[bi][j] = TENSOR ? 0 : xown[(size_t)row * N + ks];
+                    else x[bi][j] = xext[((size_t)j * rows + row) * N + ks];
+                }
+                if (TENSOR) {
+                    if (qrow) {
+                        p0[bi] = xown[(size_t)row * N + k];  p1[bi] = xown[((size_t)nq + row) * N + k];
+                        p2[bi] = xadd[(size_t)row * N + k];  p3[bi] = xadd[((size_t)nq + row) * N + k];
+                    }
+                } else if (xadd != nullptr && qrow) {
+                    p0[bi] = xadd[(size_t)row * N + k];
+                    p1[bi] = xadd[((size_t)nq + row) * N + k];
+                }
+                if (accumulate) {
+                    c0[bi] = xacc[(size_t)row * N + k];
+                    c1[bi] = xacc[((size_t)rows + row) * N + k];
+                }
+            }
+#pragma unroll
+            for (int bi = 0; bi < NB; bi++) {
+                if (b0 + bi >= kb.nb) break;
+                u64* xacc = acc + (b0 + bi) * kb.acc;
+                u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+#pragma unroll
+                for (int j = 0; j < BETA; j++) {
+                    const u64 xv = (TENSOR && j == jown) ? barrett_mul(p1[bi], p3[bi], m) : x[bi][j];
+                    mac128(h0, l0, xv, e0[j]);
+                    mac128(h1, l1, xv, e1[j]);
+                }
+                u64 r0 = barrett_reduce128(h0, l0, m), r1 = barrett_reduce128(h1, l1, m);
+                if (TENSOR) {
+                    if (qrow) {
+                        u64 hi = 0, lo = 0;
+                        mac128(hi, lo, p0[bi], p3[bi]);
+                        mac128(hi, lo, p1[bi], p2[bi]);
+                        r0 = add_mod(r0, shoup_mul(barrett_mul(p0[bi], p2[bi], m), PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+                        r1 = add_mod(r1, shoup_mul(barrett_reduce128(hi, lo, m), PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+                    }
+                } else if (addend != nullptr && qrow) {
+                    r0 = add_mod(r0, shoup_mul(p0[bi], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+                    r1 = add_mod(r1, shoup_mul(p1[bi], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+                }
+                if (accumulate) {
+                    r0 = add_mod(r0, c0[bi], m.q);
+                    r1 = add_mod(r1, c1[bi], m.q);
+                }
+                xacc[(size_t)row * N + k] = r0;
+                xacc[((size_t)rows + row) * N + k] = r1;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ fast basis conversion (spec S5)
 // in: coefficient-domain residues, source i in row T.srow[i]; out row T.orow[t] for target t.
 // One thread per coefficient computes ALL targets: y_i = x_i * hatinv_i mod s_i once, then for every target a
@@ -903,6 +995,25 @@ void launch_ks_inner(KShape S, u64* acc, const u64* ext, const u64* own, const u
     if (!L.n) return;
     if (beta > KS_MAX_BETA) throw std::runtime_error("ks_inner: too many digits");
     if (kb.nb < 1) kb.nb = 1;
+#ifndef KS_INNER_MLP
+#define KS_INNER_MLP 1        // 0: the run-time-sized kernel for every call (A/B)
+#endif
+    if (KS_INNER_MLP && beta <= 3) {
+        // digits and items-per-group as template parameters (loads of a whole group in flight together)
+#ifndef KS_INNER_NBMAX
+#define KS_INNER_NBMAX 2        /* items per group: 2 keeps 64 registers (4 CTAs per SM); 4 needs 125 and measured slower */
+#endif
+        const int nbg = (kb.nb >= 4 && KS_INNER_NBMAX >= 4) ? 4 : (kb.nb >= 2 && KS_INNER_NBMAX >= 2) ? 2 : 1;
+#define KSI(T, NBG, B) LAUNCH((k_ks_inner_mlp<T, NBG, B>), grid3(S, L.n), dim3(TPB), st, S, acc, ext, own, evk, perm, L, ERow, L.n, \
+                              evk_rows, nq, alpha, addend, PmodQ, accumulate, kb)
+#define KSI_B(T, NBG) do { if (beta == 1) KSI(T, NBG, 1); else if (beta == 2) KSI(T, NBG, 2); else KSI(T, NBG, 3); } while (0)
+#define KSI_N(T) do { if (nbg == 4) KSI_B(T, 4); else if (nbg == 2) KSI_B(T, 2); else KSI_B(T, 1); } while (0)
+        if (tensor) KSI_N(true); else KSI_N(false);
+#undef KSI_N
+#undef KSI_B
+#undef KSI
+        return;
+    }
     if (tensor)
         LAUNCH(k_ks_inner<true>, grid3(S, L.n), dim3(TPB), st, S, acc, ext, own, evk, perm, L, ERow, beta, L.n, evk_rows,
                nq, alpha, addend, PmodQ, accumulate, kb);
