@@ -82,14 +82,15 @@ __device__ __forceinline__ void mac128(u64& hi, u64& lo, u64 a, u64 b) {
 // The B200's full-rate FP64 pipe multiplies modulo a ~2^50 prime about three times as fast as the 64-bit integer
 // multiplier (profiles/r1_pipe_peaks.txt, profiles/r2_fp64_round.txt): the NTT butterflies of the scale primes (ntt.cu) and
 // the basis conversion towards them (kernels.cu: k_base_convert_fp) hold residues as exact integers in doubles.
-#define CKKS_FP_LIMIT 1576258512130867ull     /* 1.4 * 2^50: lazy values up to 5.1 q stay below 2^53 */
-// a * w mod q as an exact integer in (-2q, 2q): a any integer with |a| < 2^53, w < q < 2^51, wq = fl(w / q).
-//   h = fl(a w), l = a w - h (exact, FMA), c = rint(a wq) (quotient, off by at most 2), r = (h - c q) + l (both exact)
-//   |r| <= (0.5 + |a| 2^-52) q
-__device__ __forceinline__ double modmul_fp(double a, double w, double wq, double q) {
+#define CKKS_FP_LIMIT 1238489897526886ull     /* 1.1 * 2^50: lazy values up to 5.7 q stay below 2^53 = 7.27 q (tools/ntt_fp_bounds.py) */
+// a * w mod q as an exact integer: a any integer with |a| < 2^53, |w| < q < CKKS_FP_LIMIT, qinv = fl(1 / q).
+//   h = fl(a w), l = a w - h (exact, FMA), c = rint(h qinv) (quotient, three roundings off), r = (h - c q) + l (both exact)
+//   |r| <= (0.5 + 1.5 |a| 2^-52) q.  No companion word per twiddle: the quotient estimate comes from the product itself
+//   (half the table traffic of a Shoup-style w / q word, the same five FP64-pipe instructions and one rounding).
+__device__ __forceinline__ double modmul_fp(double a, double w, double q, double qinv) {
     const double h = fmul_rn(a, w);
     const double l = ffma_rn(a, w, -h);
-    const double c = frint(fmul_rn(a, wq));
+    const double c = frint(fmul_rn(h, qinv));
     return fadd_rn(ffma_rn(-c, q, h), l);
 }
 // fold a lazy value (|x| < 2^53) to |x| <= q/2 (+ one q when the quotient estimate is off by one)

@@ -190,7 +190,7 @@ Engine::Engine(const Params& P) : prm(P) {
     const int nm = nmod();
     std::vector<ModConst> mc(nm);
     std::vector<u64> fwd((size_t)nm * n), fwd_s((size_t)nm * n), inv((size_t)nm * n), inv_s((size_t)nm * n);
-    std::vector<double> fwd_d((size_t)nm * n), fwd_q((size_t)nm * n), inv_d((size_t)nm * n), inv_q((size_t)nm * n);
+    std::vector<double> fwd_d((size_t)nm * n), inv_d((size_t)nm * n);
     psi.resize(nm);
     Jroot.resize(nm);
     for (int i = 0; i < nm; i++) {
@@ -206,8 +206,8 @@ Engine::Engine(const Params& P) : prm(P) {
             const size_t k = bitrev_h(e, prm.logn);
             F[k] = pw; Fs[k] = shoup_h(pw, q);
             I[k] = ipw; Is[k] = shoup_h(ipw, q);
-            fwd_d[(size_t)i * n + k] = (double)pw;  fwd_q[(size_t)i * n + k] = (double)pw / (double)q;
-            inv_d[(size_t)i * n + k] = (double)ipw; inv_q[(size_t)i * n + k] = (double)ipw / (double)q;
+            fwd_d[(size_t)i * n + k] = (double)pw;
+            inv_d[(size_t)i * n + k] = (double)ipw;
             pw = mulmod_h(pw, psi[i], q);
             ipw = mulmod_h(ipw, ipsi, q);
         }
@@ -227,8 +227,8 @@ Engine::Engine(const Params& P) : prm(P) {
     d_inv = upload(this, inv, owned);
     d_inv_s = upload(this, inv_s, owned);
     d_mc = upload(this, mc, owned);
-    tabs = NttTables{d_fwd, d_fwd_s, d_inv, d_inv_s, upload(this, fwd_d, owned), upload(this, fwd_q, owned),
-                     upload(this, inv_d, owned), upload(this, inv_q, owned), d_mc, prm.logn, ntt_cluster};
+    tabs = NttTables{d_fwd, d_fwd_s, d_inv, d_inv_s, upload(this, fwd_d, owned), upload(this, inv_d, owned), d_mc,
+                     prm.logn, ntt_cluster};
     ks = KShape{d_mc, prm.logn};
     // canonical-embedding tables (spec S9)
     const size_t M = 2 * n, ns = n / 2;
@@ -1099,7 +1099,7 @@ BaseConvTable Engine::make_bc_table(const std::vector<int>& src, const std::vect
     T.hat = upload(this, hat, owned);           // exact size, freed with the engine
     {
         // FP64 path (kernels.cu: k_base_convert_fp): which targets take it, which sources are split, the constants as doubles
-        std::vector<double> hf((size_t)T.nt * T.ns * 4, 0.0);
+        std::vector<double> hf((size_t)T.nt * T.ns * 2, 0.0);
         T.swide = 0;
         for (int i = 0; i < T.ns; i++)
             if (mod[src[i]] >> 52) T.swide |= 1u << i;
@@ -1112,13 +1112,12 @@ BaseConvTable Engine::make_bc_table(const std::vector<int>& src, const std::vect
             T.tfp[t] = fp ? 1 : 0;
             T.tqinv[t] = 1.0 / (double)qt;
             T.negDd[t] = (double)T.negD[t];
-            T.negDq[t] = (double)T.negD[t] / (double)qt;
             if (!fp) continue;
             for (int i = 0; i < T.ns; i++) {
                 const u64 h = hat[(size_t)i * T.nt + t], h32 = mulmod_h(h, (1ull << 32) % qt, qt);
-                double* e = &hf[((size_t)t * T.ns + i) * 4];
-                e[0] = (double)h;   e[1] = (double)h / (double)qt;
-                e[2] = (double)h32; e[3] = (double)h32 / (double)qt;
+                double* e = &hf[((size_t)t * T.ns + i) * 2];
+                e[0] = (double)h;
+                e[1] = (double)h32;
             }
         }
         T.hatf = upload(this, hf, owned);

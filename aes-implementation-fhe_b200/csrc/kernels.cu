@@ -390,10 +390,10 @@ k_base_convert(KShape S, u64* __restrict__ out, const u64* __restrict__ in, cons
 #ifndef BC_FP_MIN_BLOCKS
 #define BC_FP_MIN_BLOCKS 4
 #endif
-struct BcFpTarget { double q, qinv, negD, negDq; };
+struct BcFpTarget { double q, qinv, negD, pad; };
 // sum_i y_i * hat_i mod q_t as a lazy double: products in groups of five (tree of exact additions), one fold between
-// groups.  Bounds in units of q_t <= 1.4 * 2^50 (2^53 = 5.71 q): a product of a narrow source is at most 0.85, of a half
-// of a wide source 0.5; first group (+ the high half of source 0) <= 4.75, later: 0.51 + 4.25 = 4.76; the caller may add
+// groups.  Bounds in units of q_t <= 1.1 * 2^50 (2^53 = 7.27 q): a product of a narrow source is at most 0.92, of a half
+// of a wide source 0.5; first group (+ the high half of source 0) <= 5.1, later: 0.51 + 4.6 = 5.11; the caller may add
 // one more product of a small operand (0.5).
 template <int NS, bool W0>
 __device__ __forceinline__ double bc_fp_sum(const double (&yl)[NS], double yh0, const double* hf, const double* hw, double q,
@@ -404,11 +404,11 @@ __device__ __forceinline__ double bc_fp_sum(const double (&yl)[NS], double yh0, 
         double r[5];
 #pragma unroll
         for (int j = 0; j < 5; j++)
-            r[j] = g0 + j < NS ? modmul_fp(yl[g0 + j], hf[2 * (g0 + j)], hf[2 * (g0 + j) + 1], q) : 0.0;
+            r[j] = g0 + j < NS ? modmul_fp(yl[g0 + j], hf[g0 + j], q, qinv) : 0.0;
         double p = fadd_rn(r[0], r[1]);
         if (g0 + 2 < NS) p = fadd_rn(p, g0 + 3 < NS ? fadd_rn(r[2], r[3]) : r[2]);
         if (g0 + 4 < NS) p = fadd_rn(p, r[4]);
-        if (g0 == 0) s = W0 ? fadd_rn(p, modmul_fp(yh0, hw[0], hw[1], q)) : p;
+        if (g0 == 0) s = W0 ? fadd_rn(p, modmul_fp(yh0, hw[0], q, qinv)) : p;
         else s = fadd_rn(fold_fp(s, q, qinv), p);
     }
     return s;
@@ -417,11 +417,11 @@ template <int NS, int GENERIC>
 __global__ void __launch_bounds__(TPB, BC_FP_MIN_BLOCKS)
 k_base_convert_fp(KShape S, u64* __restrict__ out, const u64* __restrict__ in, const BaseConvTable* __restrict__ tabs,
                   int tab_zstride, size_t in_zs, size_t out_zs, int nz, size_t in_bs, size_t out_bs) {
-    constexpr int HW = GENERIC ? 4 : 2;                 // doubles per (target, source)
+    constexpr int HW = GENERIC ? 2 : 1;                 // doubles per (target, source): hat (and hat 2^32 for wide sources)
     CKKS_SHARED u64 s_hat[BC_CHUNK * NS];
     CKKS_SHARED u64 s_r64[BC_CHUNK];
     CKKS_SHARED __align__(16) double s_hf[BC_CHUNK * NS * HW];
-    CKKS_SHARED __align__(16) double s_hw[BC_CHUNK * 2];             // source 0's second constant pair (GENERIC = 0)
+    CKKS_SHARED double s_hw[BC_CHUNK];                               // source 0's second constant (GENERIC = 0)
     CKKS_SHARED BcFpTarget s_tg[BC_CHUNK];
     CKKS_SHARED int s_nint;                                          // integer-pipe targets in this chunk
     const size_t N = (size_t)1 << S.logn;
@@ -435,16 +435,16 @@ k_base_convert_fp(KShape S, u64* __restrict__ out, const u64* __restrict__ in, c
         for (int e = threadIdx.x; e < cnt; e += TPB) {
             const int t = tbeg + e / NS, i = e % NS;
             s_hat[e] = ldg(T.hat + i * nt + t);
-            const double* h = T.hatf + ((size_t)t * NS + i) * 4;
+            const double* h = T.hatf + ((size_t)t * NS + i) * 2;
 #pragma unroll
             for (int c = 0; c < HW; c++) s_hf[e * HW + c] = ldg(h + c);
-            if (!GENERIC && i == 0) { s_hw[(t - tbeg) * 2] = ldg(h + 2); s_hw[(t - tbeg) * 2 + 1] = ldg(h + 3); }
+            if (!GENERIC && i == 0) s_hw[t - tbeg] = ldg(h + 1);
         }
         for (int t = tbeg + threadIdx.x; t < tend; t += TPB) {
             const ModConst m = S.mc[T.tgt[t]];
             s_r64[t - tbeg] = barrett_reduce128(1, 0, m);         // 2^64 mod q_t
             BcFpTarget g;
-            g.q = ull2d_rn(m.q); g.qinv = T.tqinv[t]; g.negD = T.negDd[t]; g.negDq = T.negDq[t];
+            g.q = ull2d_rn(m.q); g.qinv = T.tqinv[t]; g.negD = T.negDd[t]; g.pad = 0.0;
             s_tg[t - tbeg] = g;
         }
         if (threadIdx.x == 0) {
@@ -489,22 +489,22 @@ k_base_convert_fp(KShape S, u64* __restrict__ out, const u64* __restrict__ in, c
 #pragma unroll
                 for (int i = 0; i < NS; i++) {
                     if (wide >> i & 1) {
-                        a0 = fadd_rn(a0, modmul_fp(yl[i], hf[4 * i], hf[4 * i + 1], g.q));
-                        a1 = fadd_rn(a1, modmul_fp(yh[GENERIC ? i : 0], hf[4 * i + 2], hf[4 * i + 3], g.q));
+                        a0 = fadd_rn(a0, modmul_fp(yl[i], hf[2 * i], g.q, g.qinv));
+                        a1 = fadd_rn(a1, modmul_fp(yh[GENERIC ? i : 0], hf[2 * i + 1], g.q, g.qinv));
                     } else if (i & 1) {
-                        a1 = fadd_rn(a1, modmul_fp(yl[i], hf[4 * i], hf[4 * i + 1], g.q));
+                        a1 = fadd_rn(a1, modmul_fp(yl[i], hf[2 * i], g.q, g.qinv));
                     } else {
-                        a0 = fadd_rn(a0, modmul_fp(yl[i], hf[4 * i], hf[4 * i + 1], g.q));
+                        a0 = fadd_rn(a0, modmul_fp(yl[i], hf[2 * i], g.q, g.qinv));
                     }
                     if ((i & 3) == 3 && i + 1 < NS) { a0 = fold_fp(a0, g.q, g.qinv); a1 = fold_fp(a1, g.q, g.qinv); }
                 }
                 s = fadd_rn(fold_fp(a0, g.q, g.qinv), fold_fp(a1, g.q, g.qinv));
             } else if (wide & 1) {
-                s = bc_fp_sum<NS, true>(yl, yh[0], hf, s_hw + (t - tbeg) * 2, g.q, g.qinv);
+                s = bc_fp_sum<NS, true>(yl, yh[0], hf, s_hw + (t - tbeg), g.q, g.qinv);
             } else {
                 s = bc_fp_sum<NS, false>(yl, 0.0, hf, nullptr, g.q, g.qinv);
             }
-            if (exact) s = fadd_rn(s, modmul_fp(ud, g.negD, g.negDq, g.q));             // - u * D  (mod q_t)
+            if (exact) s = fadd_rn(s, modmul_fp(ud, g.negD, g.q, g.qinv));             // - u * D  (mod q_t)
             dst[(size_t)T.orow[t] * N + k] = canon_fp(s, g.q, g.qinv);
         }
         if (s_nint) {

@@ -41,10 +41,9 @@ struct BaseConvTable {
     // FP64 modular products; a source whose residues do not fit a double exactly (modulus >= 2^52) enters as two halves
     unsigned char tfp[BC_MAX_TGT];     // 1: target t takes the FP64 path
     u32 swide;                         // bit i: source i is split at 2^32
-    const double* hatf;                // [nt][ns][4]: hat, hat / q_t, hat 2^32 mod q_t, (hat 2^32 mod q_t) / q_t  (FP64 targets)
+    const double* hatf;                // [nt][ns][2]: hat, hat 2^32 mod q_t  (FP64 targets)
     double tqinv[BC_MAX_TGT];          // 1 / q_t
-    double negDd[BC_MAX_TGT];          // negD as a double and its quotient by q_t
-    double negDq[BC_MAX_TGT];
+    double negDd[BC_MAX_TGT];          // negD as a double
 };
 // how launch_base_convert evaluates the sums
 // BC_FP: only source 0 of a table may be wide (branch-free source loop); BC_FP_GENERIC: any source (run-time mask)

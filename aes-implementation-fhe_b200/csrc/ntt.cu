@@ -77,7 +77,8 @@ template <int MODE>
 __device__ __forceinline__ int tw_base(int r) {
     return MODE == 0 ? (1 << r) - 1 : MODE == 1 ? (16 << r) - 1 : (16 << r) - 16;
 }
-template <int MODE>
+// NOC (the FP64 path): no companion word exists -- modmul_fp takes its quotient estimate from the product itself.
+template <int MODE, bool NOC>
 struct TwLin {
     const u64* W;
     const u64* C;
@@ -85,7 +86,7 @@ struct TwLin {
     DEV_MEMBER void get(int r, int g, u64& w, u64& c) const {
         const int i = tw_base<MODE>(r) + (int)(xl << r) + g;
         w = W[i];
-        c = C[i];
+        c = NOC ? 0 : C[i];
     }
     DEV_MEMBER void get2(int r, int gh, u64& w0, u64& c0, u64& w1, u64& c1) const {
         get(r, 2 * gh, w0, c0);
@@ -93,17 +94,20 @@ struct TwLin {
     }
 };
 // TwGlobal: straight from the global table (read-only path), pairs as one 128-bit load.  Used by pass B, whose
-// per-thread twiddles (61 KB per tile) would cost a third of the resident CTAs if they were staged.
+// per-thread twiddles (30 KB per tile on the FP64 path, 61 KB with Shoup companions) would cost resident CTAs if they
+// were staged.
+template <bool NOC>
 struct TwGlobal {
     const u64* W;
     const u64* C;
     u32 X;
     DEV_MEMBER void get(int r, int g, u64& w, u64& c) const {
         w = ldg(W + (X << r) + g);
-        c = ldg(C + (X << r) + g);
+        c = NOC ? 0 : ldg(C + (X << r) + g);
     }
     DEV_MEMBER void get2(int r, int gh, u64& w0, u64& c0, u64& w1, u64& c1) const {
         ldg_pair(W + (X << r) + 2 * gh, w0, w1);
+        if (NOC) { c0 = c1 = 0; return; }
         ldg_pair(C + (X << r) + 2 * gh, c0, c1);
     }
 };
@@ -183,7 +187,7 @@ __device__ __forceinline__ u64 canon2(u64 v, u64 q) { return v >= q ? v - q : v;
 // ============================================================================================ FP64 path
 // modmul_fp / fold_fp / canon_fp: common.cuh (shared with the basis conversion)
 struct FpMod {
-    double q, qinv, ninv, ninvq, w1n, w1nq;
+    double q, qinv, ninv, w1n;
 };
 
 // Forward radix-16 block, 4 CT stages.  In: |x| <= 0.51 q.  A product of an input |a| = m q comes back with
@@ -201,7 +205,7 @@ __device__ __forceinline__ void fwd16_fp(double (&x)[16], const TW& tw, const Fp
         for (int i = 0; i < 8; i++) {
             const int g = i / span, k0 = g * 2 * span + (i % span), k1 = k0 + span;
             const double u = x[k0];
-            const double v = modmul_fp(x[k1], bits2d(w[g]), bits2d(wq[g]), m.q);
+            const double v = modmul_fp(x[k1], bits2d(w[g]), m.q, m.qinv);
             x[k0] = fadd_rn(u, v);
             x[k1] = fsub_rn(u, v);
         }
@@ -220,16 +224,16 @@ __device__ __forceinline__ void inv16_fp(double (&x)[16], const TW& tw, const Fp
             x[1] = fold_fp(x[1], m.q, m.qinv); x[9] = fold_fp(x[9], m.q, m.qinv);
         }
         u64 w[8], wq[8];
-        if (FINAL && s == 3) { w[0] = d2bits(m.w1n); wq[0] = d2bits(m.w1nq); }
+        if (FINAL && s == 3) w[0] = d2bits(m.w1n);
         else tw_stage(tw, 3 - s, w, wq);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int g = i / span, k0 = g * 2 * span + (i % span), k1 = k0 + span;
             const double u = x[k0], v = x[k1];
             double sum = fadd_rn(u, v);
-            if (FINAL && s == 3) sum = modmul_fp(sum, m.ninv, m.ninvq, m.q);
+            if (FINAL && s == 3) sum = modmul_fp(sum, m.ninv, m.q, m.qinv);
             x[k0] = sum;
-            x[k1] = modmul_fp(fsub_rn(u, v), bits2d(w[g]), bits2d(wq[g]), m.q);
+            x[k1] = modmul_fp(fsub_rn(u, v), bits2d(w[g]), m.q, m.qinv);
         }
     }
 }
@@ -239,9 +243,7 @@ __device__ __forceinline__ FpMod fp_mod(const ModConst& mc) {
     m.q = ull2d_rn(mc.q);
     m.qinv = fdiv_rn(1.0, m.q);
     m.ninv = ull2d_rn(mc.ninv);
-    m.ninvq = fdiv_rn(m.ninv, m.q);
     m.w1n = ull2d_rn(mc.w1n);
-    m.w1nq = fdiv_rn(m.w1n, m.q);
     return m;
 }
 
@@ -266,14 +268,14 @@ __device__ __forceinline__ void fwd_passA_body(const u64* __restrict__ src, u64*
     constexpr int NTW = LOGR == 8 ? 255 : 15;
     const u64 q = mc.q;
     const u64* W = (FP ? reinterpret_cast<const u64*>(T.fwd_d) : T.fwd) + (size_t)mod * N;
-    const u64* C = (FP ? reinterpret_cast<const u64*>(T.fwd_q) : T.fwd_s) + (size_t)mod * N;
+    const u64* C = FP ? nullptr : T.fwd_s + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
     u64* sd = sm;
     u64* tw = sm + 4096;
     u64* tc = tw + 256;
     FOR_THREADS {
         const int tid = threadIdx.x;
-        if (tid < NTW) { cp_async8(tw + tid, W + 1 + tid); cp_async8(tc + tid, C + 1 + tid); }
+        if (tid < NTW) { cp_async8(tw + tid, W + 1 + tid); if (!FP) cp_async8(tc + tid, C + 1 + tid); }
         if (LOGR == 8) {
             const int c = tid % TC, rr = tid / TC;
             const u64* s0 = src + (size_t)slimb * N + tile * TC + c;
@@ -290,7 +292,7 @@ __device__ __forceinline__ void fwd_passA_body(const u64* __restrict__ src, u64*
     if (LOGR == 8) {
         FOR_THREADS {
             const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
-            const TwLin<0> t1{tw, tc, 0u};
+            const TwLin<0, FP> t1{tw, tc, 0u};
             if (FP) {
                 double x[16];
 #pragma unroll
@@ -316,7 +318,7 @@ __device__ __forceinline__ void fwd_passA_body(const u64* __restrict__ src, u64*
         BLOCK_SYNC;
         FOR_THREADS {
             const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
-            const TwLin<1> t2{tw, tc, (u32)rr};
+            const TwLin<1, FP> t2{tw, tc, (u32)rr};
             u64* d0 = dst + (size_t)limb * N + tile * TC + c;
             if (FP) {
                 double x[16];
@@ -337,7 +339,7 @@ __device__ __forceinline__ void fwd_passA_body(const u64* __restrict__ src, u64*
     } else {
         FOR_THREADS {
             const int tid = threadIdx.x;
-            const TwLin<0> t1{tw, tc, 0u};
+            const TwLin<0, FP> t1{tw, tc, 0u};
             u64* d0 = dst + (size_t)limb * N + tid;
             if (FP) {
                 double x[16];
@@ -406,11 +408,11 @@ __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int
                                                u64* __restrict__ ep_out, u64 sv, u64 svs) {
     const u64 q = mc.q;
     const u64* W = (FP ? reinterpret_cast<const u64*>(T.fwd_d) : T.fwd) + (size_t)mod * N;
-    const u64* C = (FP ? reinterpret_cast<const u64*>(T.fwd_q) : T.fwd_s) + (size_t)mod * N;
+    const u64* C = FP ? nullptr : T.fwd_s + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
     FOR_THREADS {
         const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
-        const TwGlobal t1{W, C, Rn + (u32)(tile * 16 + row)};
+        const TwGlobal<FP> t1{W, C, Rn + (u32)(tile * 16 + row)};
         if (NTT_PREFETCH) tw_prefetch(W, C, 16u * (Rn + (u32)(tile * 16 + row)) + (u32)jj);
         if (FP) {
             double x[16];
@@ -431,7 +433,7 @@ __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int
     BLOCK_SYNC;
     FOR_THREADS {
         const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
-        const TwGlobal t2{W, C, 16u * (Rn + (u32)(tile * 16 + row)) + (u32)jj};
+        const TwGlobal<FP> t2{W, C, 16u * (Rn + (u32)(tile * 16 + row)) + (u32)jj};
         // each thread rewrites exactly the 16 slots it just read, so no barrier is needed before this store
         if (FP) {
             double x[16];
@@ -508,7 +510,7 @@ __device__ __forceinline__ void inv_passB_body(const u64* __restrict__ s_in, u64
                                                const u64* __restrict__ s_in2) {
     const u64 q = mc.q;
     const u64* W = (FP ? reinterpret_cast<const u64*>(T.inv_d) : T.inv) + (size_t)mod * N;
-    const u64* C = (FP ? reinterpret_cast<const u64*>(T.inv_q) : T.inv_s) + (size_t)mod * N;
+    const u64* C = FP ? nullptr : T.inv_s + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
     FOR_THREADS {
         if (MUL) {
@@ -528,7 +530,7 @@ __device__ __forceinline__ void inv_passB_body(const u64* __restrict__ s_in, u64
     BLOCK_SYNC;
     FOR_THREADS {
         const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
-        const TwGlobal t2{W, C, 16u * (Rn + (u32)(tile * 16 + row)) + (u32)jj};
+        const TwGlobal<FP> t2{W, C, 16u * (Rn + (u32)(tile * 16 + row)) + (u32)jj};
         if (FP) {
             double x[16];
 #pragma unroll
@@ -548,7 +550,7 @@ __device__ __forceinline__ void inv_passB_body(const u64* __restrict__ s_in, u64
     BLOCK_SYNC;
     FOR_THREADS {
         const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
-        const TwGlobal t1{W, C, Rn + (u32)(tile * 16 + row)};
+        const TwGlobal<FP> t1{W, C, Rn + (u32)(tile * 16 + row)};
         if (FP) {
             double x[16];
 #pragma unroll
@@ -613,14 +615,14 @@ __device__ __forceinline__ void inv_passA_body(u64* __restrict__ data, u64* sm, 
     constexpr int NTW = LOGR == 8 ? 255 : 15;
     const u64 q = mc.q;
     const u64* W = (FP ? reinterpret_cast<const u64*>(T.inv_d) : T.inv) + (size_t)mod * N;
-    const u64* C = (FP ? reinterpret_cast<const u64*>(T.inv_q) : T.inv_s) + (size_t)mod * N;
+    const u64* C = FP ? nullptr : T.inv_s + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
     u64* sd = sm;
     u64* tw = sm + 4096;
     u64* tc = tw + 256;
     FOR_THREADS {
         const int tid = threadIdx.x;
-        if (tid < NTW) { cp_async8(tw + tid, W + 1 + tid); cp_async8(tc + tid, C + 1 + tid); }
+        if (tid < NTW) { cp_async8(tw + tid, W + 1 + tid); if (!FP) cp_async8(tc + tid, C + 1 + tid); }
         if (LOGR == 8) {
             const int c = tid % TC, rr = tid / TC;
             const u64* s0 = data + (size_t)limb * N + tile * TC + c;
@@ -637,7 +639,7 @@ __device__ __forceinline__ void inv_passA_body(u64* __restrict__ data, u64* sm, 
     if (LOGR == 8) {
         FOR_THREADS {
             const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
-            const TwLin<1> t2{tw, tc, (u32)rr};
+            const TwLin<1, FP> t2{tw, tc, (u32)rr};
             if (FP) {
                 double x[16];
 #pragma unroll
@@ -657,7 +659,7 @@ __device__ __forceinline__ void inv_passA_body(u64* __restrict__ data, u64* sm, 
         BLOCK_SYNC;
         FOR_THREADS {
             const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
-            const TwLin<0> t1{tw, tc, 0u};
+            const TwLin<0, FP> t1{tw, tc, 0u};
             u64* d0 = data + (size_t)limb * N + tile * TC + c;
             if (FP) {
                 double x[16];
@@ -678,7 +680,7 @@ __device__ __forceinline__ void inv_passA_body(u64* __restrict__ data, u64* sm, 
     } else {
         FOR_THREADS {
             const int tid = threadIdx.x;
-            const TwLin<0> t1{tw, tc, 0u};
+            const TwLin<0, FP> t1{tw, tc, 0u};
             u64* d0 = data + (size_t)limb * N + tid;
             if (FP) {
                 double x[16];
@@ -736,7 +738,7 @@ __device__ __forceinline__ void fwd_cluster_body(const u64* __restrict__ src, u6
     cg::cluster_group cluster = cg::this_cluster();
     const u64 q = mc.q;
     const u64* W = (FP ? reinterpret_cast<const u64*>(T.fwd_d) : T.fwd) + (size_t)mod * N;
-    const u64* C = (FP ? reinterpret_cast<const u64*>(T.fwd_q) : T.fwd_s) + (size_t)mod * N;
+    const u64* C = FP ? nullptr : T.fwd_s + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
     u64* sd = sm;
     u64* tw = sm + kClData;
@@ -745,14 +747,14 @@ __device__ __forceinline__ void fwd_cluster_body(const u64* __restrict__ src, u6
     // ---- pass A: 32 columns x 256 rows
     {
         const int c = tid % 32, rr = tid / 32;                  // rr = 0..15
-        if (tid < 255) { cp_async8(tw + tid, W + 1 + tid); cp_async8(tc + tid, C + 1 + tid); }
+        if (tid < 255) { cp_async8(tw + tid, W + 1 + tid); if (!FP) cp_async8(tc + tid, C + 1 + tid); }
         const u64* s0 = src + (size_t)slimb * N + tile * 32 + c;
 #pragma unroll
         for (int k = 0; k < 16; k++) cp_async8(sd + (rr + 16 * k) * 32 + c, s0 + (size_t)(rr + 16 * k) * 256);
         cp_async_wait_all();
         __syncthreads();
-        const TwLin<0> t1{tw, tc, 0u};
-        const TwLin<1> t2{tw, tc, (u32)rr};
+        const TwLin<0, FP> t1{tw, tc, 0u};
+        const TwLin<1, FP> t2{tw, tc, (u32)rr};
         u64 y[16];
         if (FP) {
             double x[16];
@@ -796,8 +798,8 @@ __device__ __forceinline__ void fwd_cluster_body(const u64* __restrict__ src, u6
     {
         const int jj = tid % 16, row = tid / 16;                // row = 0..31
         const u32 Rn = (u32)(N >> 8);
-        const TwGlobal t1{W, C, Rn + (u32)(tile * 32 + row)};
-        const TwGlobal t2{W, C, 16u * (Rn + (u32)(tile * 32 + row)) + (u32)jj};
+        const TwGlobal<FP> t1{W, C, Rn + (u32)(tile * 32 + row)};
+        const TwGlobal<FP> t2{W, C, 16u * (Rn + (u32)(tile * 32 + row)) + (u32)jj};
         if (FP) {
             double x[16];
 #pragma unroll
@@ -882,7 +884,7 @@ __device__ __forceinline__ void inv_cluster_body(const u64* __restrict__ src, co
     cg::cluster_group cluster = cg::this_cluster();
     const u64 q = mc.q;
     const u64* W = (FP ? reinterpret_cast<const u64*>(T.inv_d) : T.inv) + (size_t)mod * N;
-    const u64* C = (FP ? reinterpret_cast<const u64*>(T.inv_q) : T.inv_s) + (size_t)mod * N;
+    const u64* C = FP ? nullptr : T.inv_s + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
     u64* sd = sm;
     u64* tw = sm + kClData;
@@ -892,7 +894,7 @@ __device__ __forceinline__ void inv_cluster_body(const u64* __restrict__ src, co
     {
         // ---- pass B^-1: 32 rows x 256 columns
         const size_t off = (size_t)slimb * N + (size_t)tile * 32 * 256;
-        if (tid < 255) { cp_async8(tw + tid, W + 1 + tid); cp_async8(tc + tid, C + 1 + tid); }
+        if (tid < 255) { cp_async8(tw + tid, W + 1 + tid); if (!FP) cp_async8(tc + tid, C + 1 + tid); }
         if (MUL) {
 #pragma unroll
             for (int k = 0; k < 16; k++)
@@ -905,8 +907,8 @@ __device__ __forceinline__ void inv_cluster_body(const u64* __restrict__ src, co
         __syncthreads();
         const int jj = tid % 16, row = tid / 16;
         const u32 Rn = (u32)(N >> 8);
-        const TwGlobal t2{W, C, 16u * (Rn + (u32)(tile * 32 + row)) + (u32)jj};
-        const TwGlobal t1{W, C, Rn + (u32)(tile * 32 + row)};
+        const TwGlobal<FP> t2{W, C, 16u * (Rn + (u32)(tile * 32 + row)) + (u32)jj};
+        const TwGlobal<FP> t1{W, C, Rn + (u32)(tile * 32 + row)};
         if (FP) {
             double x[16];
 #pragma unroll
@@ -945,8 +947,8 @@ __device__ __forceinline__ void inv_cluster_body(const u64* __restrict__ src, co
         // ---- pass A^-1: 32 columns x 256 rows, 1/N folded into the last stage
         if (!active) return;                                    // surplus cluster of a ragged batch: no global store
         const int c = tid % 32, rr = tid / 32;
-        const TwLin<1> t2{tw, tc, (u32)rr};
-        const TwLin<0> t1{tw, tc, 0u};
+        const TwLin<1, FP> t2{tw, tc, (u32)rr};
+        const TwLin<0, FP> t1{tw, tc, 0u};
         u64* d0 = dst + (size_t)limb * N + tile * 32 + c;
         if (FP) {
             double x[16];

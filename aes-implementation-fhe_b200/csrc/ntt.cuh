@@ -8,11 +8,9 @@ struct NttTables {
     const u64* fwd_s;
     const u64* inv;
     const u64* inv_s;
-    // FP64 path (scale primes): the same twiddles as doubles and their quotients by q
+    // FP64 path (moduli below CKKS_FP_LIMIT): the same twiddles as doubles (no companion: common.cuh modmul_fp)
     const double* fwd_d;
-    const double* fwd_q;
     const double* inv_d;
-    const double* inv_q;
     const ModConst* mc;
     int logn;
     int cluster;     // 0: two-pass kernels; 1: single-kernel (8-CTA cluster) forward transform at N = 2^16; 2: also the fused

@@ -1,6 +1,7 @@
 # bound propagation (units of q) for the FP64 radix-16 blocks; rho = q / 2^50, need every intermediate <= 8/rho
+# modmul_fp (common.cuh) estimates the quotient from the rounded product: |r| <= (0.5 + 1.5 |a| 2^-52) q
 def mm(a, rho):  # |modmul output| bound for |input| <= a (units of q)
-    return 0.5 + a * rho / 4 * 1.001 + 1e-9
+    return 0.5 + a * rho * 0.375 * 1.001 + 1e-9
 def fwd(rho, fold_at=()):
     x = [0.51] * 16; worst = 0
     for s in range(4):
@@ -25,7 +26,7 @@ def inv(rho, folds=None, final=False):
             x[k0] = mm(u + v, rho) if (final and s == 3) else u + v
             x[k1] = mm(u + v, rho)
     return worst, max(x), [round(t, 2) for t in x]
-for rho in (1.0, 1.2, 1.4):
+for rho in (1.0, 1.05, 1.1):
     print("rho", rho, "limit", 8 / rho)
     print("  fwd nofold", fwd(rho), " fold@2", fwd(rho, (2,)))
     print("  inv nofold", inv(rho)[:2])
