@@ -257,7 +257,68 @@ __device__ __forceinline__ u64 pro_lift(u64 x, u64 ql, const ModConst& mc) {
     const u64 h = ql >> 1;
     u64 t = x + h;
     t = t >= ql ? t - ql : t;
+    // (x + h) mod q_l and h itself are below q_l: when q_l < 2 q (every pair of ~2^50 scale primes, and q_0 above them)
+    // their residues modulo q are one conditional subtraction away -- no Barrett reduction per coefficient
+    if (ql < 2 * mc.q) {
+        const u64 r = t >= mc.q ? t - mc.q : t, hq = h >= mc.q ? h - mc.q : h;
+        return sub_mod(r, hq, mc.q);
+    }
     return sub_mod(barrett_reduce64(t, mc), barrett_reduce64(h, mc), mc.q);
+}
+// The two radix-16 rounds of pass A at N = 2^16 on a tile that already sits in shared memory (sd: [256 rows][16 columns],
+// tw / tc: table entries 1..255 and their companions); shared by the one-tile kernels and the pipelined persistent one.
+template <bool FP, bool PRO>
+__device__ __forceinline__ void fwd_passA8_compute(u64* sd, const u64* tw, const u64* tc, u64* __restrict__ dst, int limb,
+                                                   int tile, size_t N, const ModConst& mc, u64 ql) {
+    constexpr int TC = 16;
+    const u64 q = mc.q;
+    const FpMod fm = fp_mod(mc);
+    FOR_THREADS {
+        const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
+        const TwLin<0, FP> t1{tw, tc, 0u};
+        if (FP) {
+            double x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const u64 v = sd[(rr + 16 * k) * TC + c];
+                x[k] = ull2d_rn(PRO ? pro_lift(v, ql, mc) : v);
+            }
+            fwd16_fp(x, t1, fm);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sd[(rr + 16 * k) * TC + c] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+        } else {
+            u64 x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const u64 v = sd[(rr + 16 * k) * TC + c];
+                x[k] = PRO ? pro_lift(v, ql, mc) : v;
+            }
+            fwd16(x, t1, q);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sd[(rr + 16 * k) * TC + c] = x[k];
+        }
+    }
+    BLOCK_SYNC;
+    FOR_THREADS {
+        const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
+        const TwLin<1, FP> t2{tw, tc, (u32)rr};
+        u64* d0 = dst + (size_t)limb * N + tile * TC + c;
+        if (FP) {
+            double x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = bits2d(sd[(16 * rr + k) * TC + c]);
+            fwd16_fp(x, t2, fm);
+#pragma unroll
+            for (int k = 0; k < 16; k++) d0[(size_t)(16 * rr + k) * 256] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+        } else {
+            u64 x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = sd[(16 * rr + k) * TC + c];
+            fwd16(x, t2, q);
+#pragma unroll
+            for (int k = 0; k < 16; k++) d0[(size_t)(16 * rr + k) * 256] = x[k];   // lazy [0,4q)
+        }
+    }
 }
 template <int LOGR, bool FP, bool PRO>
 __device__ __forceinline__ void fwd_passA_body(const u64* __restrict__ src, u64* __restrict__ dst, u64* sm, int limb,
@@ -290,52 +351,7 @@ __device__ __forceinline__ void fwd_passA_body(const u64* __restrict__ src, u64*
     }
     BLOCK_SYNC;
     if (LOGR == 8) {
-        FOR_THREADS {
-            const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
-            const TwLin<0, FP> t1{tw, tc, 0u};
-            if (FP) {
-                double x[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const u64 v = sd[(rr + 16 * k) * TC + c];
-                    x[k] = ull2d_rn(PRO ? pro_lift(v, ql, mc) : v);
-                }
-                fwd16_fp(x, t1, fm);
-#pragma unroll
-                for (int k = 0; k < 16; k++) sd[(rr + 16 * k) * TC + c] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
-            } else {
-                u64 x[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const u64 v = sd[(rr + 16 * k) * TC + c];
-                    x[k] = PRO ? pro_lift(v, ql, mc) : v;
-                }
-                fwd16(x, t1, q);
-#pragma unroll
-                for (int k = 0; k < 16; k++) sd[(rr + 16 * k) * TC + c] = x[k];
-            }
-        }
-        BLOCK_SYNC;
-        FOR_THREADS {
-            const int c = threadIdx.x % TC, rr = threadIdx.x / TC;
-            const TwLin<1, FP> t2{tw, tc, (u32)rr};
-            u64* d0 = dst + (size_t)limb * N + tile * TC + c;
-            if (FP) {
-                double x[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = bits2d(sd[(16 * rr + k) * TC + c]);
-                fwd16_fp(x, t2, fm);
-#pragma unroll
-                for (int k = 0; k < 16; k++) d0[(size_t)(16 * rr + k) * 256] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
-            } else {
-                u64 x[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = sd[(16 * rr + k) * TC + c];
-                fwd16(x, t2, q);
-#pragma unroll
-                for (int k = 0; k < 16; k++) d0[(size_t)(16 * rr + k) * 256] = x[k];   // lazy [0,4q)
-            }
-        }
+        fwd_passA8_compute<FP, PRO>(sd, tw, tc, dst, limb, tile, N, mc, ql);
     } else {
         FOR_THREADS {
             const int tid = threadIdx.x;
@@ -396,6 +412,103 @@ ntt_fwd_passA_lift(const u64* __restrict__ src, u64* __restrict__ dst, const GRI
     const u64 ql = T.mc[pro_mod].q;
     if (use_fp(mc.q)) fwd_passA_body<LOGR, true, true>(src, dst, sm, limb, slimb, tile, N, mc, T, mod, ql);
     else fwd_passA_body<LOGR, false, true>(src, dst, sm, limb, slimb, tile, N, mc, T, mod, ql);
+}
+
+// ---------------------------------------------------------------------------------- pass A, persistent and pipelined
+// One launch of at most NTT_PIPE_BLOCKS CTAs per SM; a CTA walks the tiles t = blockIdx.x, + gridDim.x, ... of the whole
+// job (t = tile + 16 * (item + n * (slice + nz * batch))) with two shared-memory stages: while the two radix-16 rounds run
+// on one tile, the cp.async copies of the next tile (data and the 255 twiddles of ITS modulus) are in flight into the
+// other stage, so the load latency of a tile hides behind arithmetic of the SAME CTA instead of relying on the other
+// resident CTAs being in a different phase (the one-tile kernels run their load and arithmetic phases in lock-step
+// across a wave: ncu shows the FP64 pipe at 41-51 %).  Same arithmetic per tile: bit-identical results.
+#ifndef NTT_PIPE
+#define NTT_PIPE 0                 // 1: the persistent pipelined pass A (measured slower: DESIGN.md 8.2); 0: one-tile kernels
+#endif
+#ifndef NTT_PIPE_BLOCKS
+#define NTT_PIPE_BLOCKS 3          // 2 stages x 36 KB = 72 KB per CTA
+#endif
+constexpr int kPipeWords = 2 * kPassAWords;
+struct PassATile {
+    int limb, slimb, mod, tile;
+    bool valid;
+    const u64* src;
+    u64* dst;
+};
+__device__ __forceinline__ PassATile passA_tile(int t, const NttJob& J, const u64* src, u64* dst) {
+    PassATile P;
+    P.tile = t & 15;
+    const int rest = t >> 4;
+    const int y = rest % J.n;
+    const unsigned zbi = (unsigned)(rest / J.n);
+    const unsigned b = zbi / (unsigned)J.nz, z = zbi - b * (unsigned)J.nz;
+    P.valid = !(J.cnt[z] && y >= J.cnt[z]);
+    const int yy = P.valid ? y : 0;
+    P.limb = J.rows[z][yy];
+    P.slimb = J.srows[z][yy];
+    P.mod = J.mods[z][yy];
+    P.src = src + z * J.szs + b * J.sbs;
+    P.dst = dst + z * J.dzs + b * J.dbs;
+    return P;
+}
+// request tile P into the stage at `buf` (data [256][16], then the twiddles and, on the integer path, their companions)
+__device__ __forceinline__ void passA_issue(const PassATile& P, u64* buf, const NttTables& T, size_t N, bool inverse) {
+    if (!P.valid) return;
+    const bool fp = use_fp(T.mc[P.mod].q);
+    const u64* W = (inverse ? (fp ? reinterpret_cast<const u64*>(T.inv_d) : T.inv)
+                            : (fp ? reinterpret_cast<const u64*>(T.fwd_d) : T.fwd)) + (size_t)P.mod * N;
+    const u64* C = (inverse ? T.inv_s : T.fwd_s) + (size_t)P.mod * N;
+    u64* tw = buf + 4096;
+    u64* tc = tw + 256;
+    FOR_THREADS {
+        const int tid = threadIdx.x;
+        if (tid < 255) { cp_async8(tw + tid, W + 1 + tid); if (!fp) cp_async8(tc + tid, C + 1 + tid); }
+        const int c = tid % 16, rr = tid / 16;
+        const u64* s0 = P.src + (size_t)P.slimb * N + P.tile * 16 + c;
+        if (inverse) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) cp_async8(buf + (16 * rr + k) * 16 + c, s0 + (size_t)(16 * rr + k) * 256);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) cp_async8(buf + (rr + 16 * k) * 16 + c, s0 + (size_t)(rr + 16 * k) * 256);
+        }
+    }
+}
+template <bool PRO>
+__global__ void __launch_bounds__(kThreads, NTT_PIPE_BLOCKS)
+ntt_fwd_passA_pipe(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T, int pro_mod) {
+    DYN_SHARED_U64(sm, kPipeWords);
+    const size_t N = (size_t)1 << T.logn;
+    const int total = 16 * J.n * J.nz * J.nb;
+    const u64 ql = PRO ? T.mc[pro_mod].q : 0;
+    int t = blockIdx.x, stage = 0;
+    if (t < total) passA_issue(passA_tile(t, J, src, dst), sm, T, N, false);
+    for (; t < total; t += gridDim.x, stage ^= 1) {
+        FOR_THREADS { cp_async_wait_all(); }
+        BLOCK_SYNC;              // this tile has landed; every thread has left the previous tile's second round
+        if (t + (int)gridDim.x < total)
+            passA_issue(passA_tile(t + (int)gridDim.x, J, src, dst), sm + (stage ^ 1) * kPassAWords, T, N, false);
+        const PassATile P = passA_tile(t, J, src, dst);
+        if (!P.valid) continue;
+        u64* sd = sm + stage * kPassAWords;
+        const ModConst mc = T.mc[P.mod];
+        if (use_fp(mc.q)) fwd_passA8_compute<true, PRO>(sd, sd + 4096, sd + 4096 + 256, P.dst, P.limb, P.tile, N, mc, ql);
+        else fwd_passA8_compute<false, PRO>(sd, sd + 4096, sd + 4096 + 256, P.dst, P.limb, P.tile, N, mc, ql);
+    }
+}
+// CTAs of a persistent launch: NTT_PIPE_BLOCKS per SM, never more than there are tiles
+static int pipe_grid(int tiles) {
+#ifdef CKKS_EMU
+    const int slots = 6;
+#else
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int slots = sms * NTT_PIPE_BLOCKS;
+#endif
+    return tiles < slots ? tiles : slots;
 }
 
 // ============================================================================================ forward, pass B
@@ -1033,7 +1146,11 @@ void ntt_forward(const u64* src, u64* dst, const NttJob& J0, const NttTables& T,
     dim3 gridB(R / 16, J.n, nbz(J));
     if (T.logn == 16) {
         dim3 gridA(16, J.n, nbz(J));
-        LAUNCH(ntt_fwd_passA<8>, gridA, dim3(kThreads), st, src, dst, J, T);
+        if (NTT_PIPE)
+            LAUNCH_DYN(ntt_fwd_passA_pipe<false>, dim3(pipe_grid(16 * J.n * nbz(J))), dim3(kThreads), kPipeWords * sizeof(u64), st,
+                       src, dst, J, T, 0);
+        else
+            LAUNCH(ntt_fwd_passA<8>, gridA, dim3(kThreads), st, src, dst, J, T);
     } else if (T.logn == 12) {
         dim3 gridA(1, J.n, nbz(J));
         LAUNCH(ntt_fwd_passA<4>, gridA, dim3(kThreads), st, src, dst, J, T);
@@ -1062,11 +1179,15 @@ void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J0, const NttTabl
     dim3 gridB(R / 16, J.n, nbz(J));
     if (T.logn != 16 && T.logn != 12) throw std::runtime_error("ntt: only N = 2^16 and N = 2^12 are built");
     dim3 gridA(T.logn == 16 ? 16 : 1, J.n, nbz(J));
+    const dim3 gridP(pipe_grid(16 * J.n * nbz(J)));
+    const size_t smemP = kPipeWords * sizeof(u64);
     if (F.pro_mod >= 0) {
-        if (T.logn == 16) LAUNCH(ntt_fwd_passA_lift<8>, gridA, dim3(kThreads), st, src, dst, J, T, F.pro_mod);
+        if (T.logn == 16 && NTT_PIPE) LAUNCH_DYN(ntt_fwd_passA_pipe<true>, gridP, dim3(kThreads), smemP, st, src, dst, J, T, F.pro_mod);
+        else if (T.logn == 16) LAUNCH(ntt_fwd_passA_lift<8>, gridA, dim3(kThreads), st, src, dst, J, T, F.pro_mod);
         else LAUNCH(ntt_fwd_passA_lift<4>, gridA, dim3(kThreads), st, src, dst, J, T, F.pro_mod);
     } else {
-        if (T.logn == 16) LAUNCH(ntt_fwd_passA<8>, gridA, dim3(kThreads), st, src, dst, J, T);
+        if (T.logn == 16 && NTT_PIPE) LAUNCH_DYN(ntt_fwd_passA_pipe<false>, gridP, dim3(kThreads), smemP, st, src, dst, J, T, 0);
+        else if (T.logn == 16) LAUNCH(ntt_fwd_passA<8>, gridA, dim3(kThreads), st, src, dst, J, T);
         else LAUNCH(ntt_fwd_passA<4>, gridA, dim3(kThreads), st, src, dst, J, T);
     }
     if (F.ep_out) LAUNCH(ntt_fwd_passB_ep, gridB, dim3(kThreads), st, dst, J, T, F);
