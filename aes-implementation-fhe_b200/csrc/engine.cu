@@ -1102,7 +1102,7 @@ BaseConvTable Engine::make_bc_table(const std::vector<int>& src, const std::vect
         std::vector<double> hf((size_t)T.nt * T.ns * 2, 0.0);
         T.swide = 0;
         for (int i = 0; i < T.ns; i++)
-            if (mod[src[i]] >> 52) T.swide |= 1u << i;
+            if (mod[src[i]] >= CKKS_FP_LIMIT) T.swide |= 1u << i;      // y_i enters as two halves below 2^32
         int eligible = 0;
         for (int t = 0; t < T.nt; t++) {
             const u64 qt = mod[tgt[t]];

@@ -38,7 +38,7 @@ struct BaseConvTable {
     const void* afrag;
     const u64* pow8;
     // FP64 path (k_base_convert_fp): a target below CKKS_FP_LIMIT may be evaluated on the FP64 pipe as a sum of exact
-    // FP64 modular products; a source whose residues do not fit a double exactly (modulus >= 2^52) enters as two halves
+    // FP64 modular products; a source modulus at or above CKKS_FP_LIMIT (q_0, 61-bit special primes) enters as two halves below 2^32
     unsigned char tfp[BC_MAX_TGT];     // 1: target t takes the FP64 path
     u32 swide;                         // bit i: source i is split at 2^32
     const double* hatf;                // [nt][ns][2]: hat, hat 2^32 mod q_t  (FP64 targets)
