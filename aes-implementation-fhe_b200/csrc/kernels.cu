@@ -240,6 +240,10 @@ k_ks_inner_mlp(KShape S, u64* __restrict__ acc, const u64* __restrict__ ext, con
     const size_t N = (size_t)1 << S.logn;
     const int jown = row < nq ? row / alpha : -1;
     const bool qrow = row < nq;
+#ifndef KS_INNER_FP
+#define KS_INNER_FP 1         // 0: 128-bit integer multiply-accumulates on every row (A/B)
+#endif
+    const bool fprow = KS_INNER_FP && m.q < CKKS_FP_LIMIT;          // uniform over the CTA (one row per blockIdx.y)
     FOR_THREADS {
         const u32 k = blockIdx.x * TPB + threadIdx.x;
         const u32 ks = perm ? ldg(perm + k) : k;
@@ -249,6 +253,12 @@ k_ks_inner_mlp(KShape S, u64* __restrict__ acc, const u64* __restrict__ ext, con
             const u64* e = evk + ((size_t)j * 2 * evk_rows + er) * N + k;
             e0[j] = ldg(e);
             e1[j] = ldg(e + (size_t)evk_rows * N);
+        }
+        double ed0[BETA], ed1[BETA];
+        const double qd = ull2d_rn(m.q), qinv = fdiv_rn(1.0, qd);
+        if (fprow) {
+#pragma unroll
+            for (int j = 0; j < BETA; j++) { ed0[j] = ull2d_rn(e0[j]); ed1[j] = ull2d_rn(e1[j]); }
         }
         for (int b0 = 0; b0 < kb.nb; b0 += NB) {
             u64 x[NB][BETA], p0[NB], p1[NB], p2[NB], p3[NB], c0[NB], c1[NB];
@@ -283,14 +293,30 @@ k_ks_inner_mlp(KShape S, u64* __restrict__ acc, const u64* __restrict__ ext, con
             for (int bi = 0; bi < NB; bi++) {
                 if (b0 + bi >= kb.nb) break;
                 u64* xacc = acc + (b0 + bi) * kb.acc;
-                u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+                u64 r0, r1;
+                if (fprow) {
+                    // FP64 pipe: the digit words and the key words are below q < 2^50.2, every product an exact FP64
+                    // modular product (common.cuh), the sum of BETA <= 4 of them far below 2^53
+                    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                for (int j = 0; j < BETA; j++) {
-                    const u64 xv = (TENSOR && j == jown) ? barrett_mul(p1[bi], p3[bi], m) : x[bi][j];
-                    mac128(h0, l0, xv, e0[j]);
-                    mac128(h1, l1, xv, e1[j]);
+                    for (int j = 0; j < BETA; j++) {
+                        const double xd = ull2d_rn((TENSOR && j == jown) ? barrett_mul(p1[bi], p3[bi], m) : x[bi][j]);
+                        s0 = fadd_rn(s0, modmul_fp(xd, ed0[j], qd, qinv));
+                        s1 = fadd_rn(s1, modmul_fp(xd, ed1[j], qd, qinv));
+                    }
+                    r0 = canon_fp(s0, qd, qinv);
+                    r1 = canon_fp(s1, qd, qinv);
+                } else {
+                    u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+#pragma unroll
+                    for (int j = 0; j < BETA; j++) {
+                        const u64 xv = (TENSOR && j == jown) ? barrett_mul(p1[bi], p3[bi], m) : x[bi][j];
+                        mac128(h0, l0, xv, e0[j]);
+                        mac128(h1, l1, xv, e1[j]);
+                    }
+                    r0 = barrett_reduce128(h0, l0, m);
+                    r1 = barrett_reduce128(h1, l1, m);
                 }
-                u64 r0 = barrett_reduce128(h0, l0, m), r1 = barrett_reduce128(h1, l1, m);
                 if (TENSOR) {
                     if (qrow) {
                         u64 hi = 0, lo = 0;

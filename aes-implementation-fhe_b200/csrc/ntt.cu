@@ -111,6 +111,37 @@ struct TwGlobal {
         ldg_pair(C + (X << r) + 2 * gh, c0, c1);
     }
 };
+// TwRegs: the 15 twiddles of one radix-16 block held in registers, loaded ahead of the barrier that precedes the round
+// which uses them (FP64 path of pass B: the per-thread twiddles of the second round come from L2; requested after the first
+// round's stores they arrive during the barrier and the shared-memory exchange instead of stalling the first butterflies).
+#ifndef NTT_TW_PRELOAD
+#define NTT_TW_PRELOAD 1
+#endif
+struct TwRegs {
+    const u64* w;
+    DEV_MEMBER void get(int r, int g, u64& wo, u64& c) const { wo = w[(1 << r) - 1 + g]; c = 0; }
+    DEV_MEMBER void get2(int r, int gh, u64& w0, u64& c0, u64& w1, u64& c1) const {
+        w0 = w[(1 << r) - 1 + 2 * gh];
+        w1 = w[(1 << r) - 1 + 2 * gh + 1];
+        c0 = c1 = 0;
+    }
+};
+__device__ __forceinline__ void tw_preload(const TwGlobal<true>& t, u64 (&w)[15]) {
+    u64 c0, c1;
+    t.get(0, 0, w[0], c0);
+#pragma unroll
+    for (int r = 1; r < 4; r++)
+#pragma unroll
+        for (int gh = 0; gh < (1 << (r - 1)); gh++) t.get2(r, gh, w[(1 << r) - 1 + 2 * gh], c0, w[(1 << r) - 1 + 2 * gh + 1], c1);
+}
+// per-thread storage that outlives a barrier: a plain local array under nvcc, one row per emulated thread otherwise
+#ifdef CKKS_EMU
+#define PER_THREAD_ROWS kThreads
+#define PER_THREAD_ROW threadIdx.x
+#else
+#define PER_THREAD_ROWS 1
+#define PER_THREAD_ROW 0
+#endif
 #ifndef NTT_PREFETCH
 #define NTT_PREFETCH 0        // 0: off (default), 1: towards L1, 2: towards L2 -- measured slower on the B200 (profiles/r1_ab_prefetch.txt)
 #endif
@@ -523,6 +554,7 @@ __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int
     const u64* W = (FP ? reinterpret_cast<const u64*>(T.fwd_d) : T.fwd) + (size_t)mod * N;
     const u64* C = FP ? nullptr : T.fwd_s + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
+    u64 twpre[PER_THREAD_ROWS][15];
     FOR_THREADS {
         const int jj = threadIdx.x % 16, row = threadIdx.x / 16;
         const TwGlobal<FP> t1{W, C, Rn + (u32)(tile * 16 + row)};
@@ -534,6 +566,8 @@ __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int
             fwd16_fp(x, t1, fm);
 #pragma unroll
             for (int k = 0; k < 16; k++) sm[pad16(row * 256 + jj + 16 * k)] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+            if (NTT_TW_PRELOAD)
+                tw_preload(TwGlobal<true>{W, nullptr, 16u * (Rn + (u32)(tile * 16 + row)) + (u32)jj}, twpre[PER_THREAD_ROW]);
         } else {
             u64 x[16];
 #pragma unroll
@@ -552,7 +586,8 @@ __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int
             double x[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) x[k] = bits2d(sm[pad16(row * 256 + 16 * jj + k)]);
-            fwd16_fp(x, t2, fm);
+            if (NTT_TW_PRELOAD) fwd16_fp(x, TwRegs{twpre[PER_THREAD_ROW]}, fm);
+            else fwd16_fp(x, t2, fm);
 #pragma unroll
             for (int k = 0; k < 16; k++) sm[pad16(row * 256 + 16 * jj + k)] = canon_fp(x[k], fm.q, fm.qinv);
         } else {
@@ -625,7 +660,11 @@ __device__ __forceinline__ void inv_passB_body(const u64* __restrict__ s_in, u64
     const u64* W = (FP ? reinterpret_cast<const u64*>(T.inv_d) : T.inv) + (size_t)mod * N;
     const u64* C = FP ? nullptr : T.inv_s + (size_t)mod * N;
     const FpMod fm = fp_mod(mc);
+    u64 twpre[PER_THREAD_ROWS][15];
     FOR_THREADS {
+        if (FP && NTT_TW_PRELOAD)      // the first round's per-thread twiddles travel together with the data
+            tw_preload(TwGlobal<true>{W, nullptr, 16u * (Rn + (u32)(tile * 16 + threadIdx.x / 16)) + (u32)(threadIdx.x % 16)},
+                       twpre[PER_THREAD_ROW]);
         if (MUL) {
             // the transformed polynomial is the product of two NTT-domain rows (d2 = a1 * b1 of a ct x ct) formed on the fly
             u64 x[16], y[16];
@@ -648,7 +687,8 @@ __device__ __forceinline__ void inv_passB_body(const u64* __restrict__ s_in, u64
             double x[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) x[k] = ull2d_rn(sm[pad16(row * 256 + 16 * jj + k)]);
-            inv16_fp<false>(x, t2, fm);
+            if (NTT_TW_PRELOAD) inv16_fp<false>(x, TwRegs{twpre[PER_THREAD_ROW]}, fm);
+            else inv16_fp<false>(x, t2, fm);
 #pragma unroll
             for (int k = 0; k < 16; k++) sm[pad16(row * 256 + 16 * jj + k)] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
         } else {

@@ -432,7 +432,7 @@ def run_ours(args) -> None:
     roofline_ks = None
     if not dry and LOGN == 16:
         lb = C.c_float()
-        nl = LEVELS + 1 + 7
+        nl = LEVELS + 1 + len(eng.params()["p"])          # one key-switch working set: Q_L and the special primes
         _check(lib.ckks_bench_ntt(ptr, nl, 6, 0, 20, C.byref(lb)))
         large_batch = {"limbs_per_call": nl * 6, "us_per_call": lb.value * 1e3,
                        "achieved": nl * 6 * 2 * (1 << LOGN) * 8 / (lb.value * 1e-3) / 1e9}
@@ -463,12 +463,14 @@ def run_ours(args) -> None:
     roofline = {"bound": "hbm", "kernel": "ntt_fwd_passA/B + ntt_inv_passB/A (negacyclic NTT, N=2^16)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 # dram__bytes_read+write of the two NTT passes from the `ncu --set full` capture committed as
-                # profiles/r1_ncu_full_ntt_v3_126limbs.csv: 181 MB for 132.1 MB algorithmic (twiddle tables re-read)
-                "traffic": alg_bytes / max(pcalls.value, 1) * 1.37,
-                "traffic_source": "ncu --set full, profiles/r1_ncu_full_ntt_v3_126limbs.csv (ratio 1.37 x algorithmic)",
+                # profiles/r2_ncu_full_ntt_126limbs.csv.gz: 162 MB for 132.1 MB algorithmic (the twiddle tables; the
+                # round-1 kernels with Shoup-style companion words read 181 MB)
+                "traffic": alg_bytes / max(pcalls.value, 1) * 1.23,
+                "traffic_source": "ncu --set full, profiles/r2_ncu_full_ntt_126limbs.csv.gz (ratio 1.23 x algorithmic)",
                 "bound_note": "HBM roofline as the contract asks; achieved/frac are ALL NTT calls of one middle round at the "
                               "bench's batch size, each bracketed by a CUDA-event pair (lanes off for that leg); ncu: FP64 "
-                              "pipe 41-51 %, the kernel is bound by the 64-bit modular multiply rate, not by HBM",
+                              "pipe 45-50 %, conversion pipe 36-45 %: the kernel is bound by the FP64 modular multiply "
+                              "rate, not by HBM",
                 "large_batch": large_batch, "profiled_round_wall_ms": prof_wall * 1e3, "ntt_ms_per_round": pms.value,
                 "graph_round_ms": s_round * 1e3 if s_round else None,
                 "ntt_share_of_graph_round": (pms.value * 1e-3 / s_round) if s_round else None,
