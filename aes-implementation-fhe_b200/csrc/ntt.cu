@@ -300,7 +300,8 @@ __device__ __forceinline__ u64 pro_lift(u64 x, u64 ql, const ModConst& mc) {
 // tw / tc: table entries 1..255 and their companions); shared by the one-tile kernels and the pipelined persistent one.
 template <bool FP, bool PRO>
 __device__ __forceinline__ void fwd_passA8_compute(u64* sd, const u64* tw, const u64* tc, u64* __restrict__ dst, int limb,
-                                                   int tile, size_t N, const ModConst& mc, u64 ql) {
+                                                   int tile, size_t N, const ModConst& mc, u64 ql,
+                                                   const u64* __restrict__ gsrc = nullptr) {
     constexpr int TC = 16;
     const u64 q = mc.q;
     const FpMod fm = fp_mod(mc);
@@ -311,7 +312,7 @@ __device__ __forceinline__ void fwd_passA8_compute(u64* sd, const u64* tw, const
             double x[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                const u64 v = sd[(rr + 16 * k) * TC + c];
+                const u64 v = gsrc ? gsrc[(size_t)(rr + 16 * k) * 256 + c] : sd[(rr + 16 * k) * TC + c];
                 x[k] = ull2d_rn(PRO ? pro_lift(v, ql, mc) : v);
             }
             fwd16_fp(x, t1, fm);
@@ -321,7 +322,7 @@ __device__ __forceinline__ void fwd_passA8_compute(u64* sd, const u64* tw, const
             u64 x[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                const u64 v = sd[(rr + 16 * k) * TC + c];
+                const u64 v = gsrc ? gsrc[(size_t)(rr + 16 * k) * 256 + c] : sd[(rr + 16 * k) * TC + c];
                 x[k] = PRO ? pro_lift(v, ql, mc) : v;
             }
             fwd16(x, t1, q);
@@ -365,14 +366,44 @@ __device__ __forceinline__ void fwd_passA_body(const u64* __restrict__ src, u64*
     u64* sd = sm;
     u64* tw = sm + 4096;
     u64* tc = tw + 256;
+#ifndef NTT_A_BULK
+#define NTT_A_BULK 0          // 1: the tile arrives by 256 bulk copies of one 128-byte row each (A/B)
+#endif
+    if (LOGR == 8 && NTT_A_BULK) {
+        // the 17th block of the buffer (sm + 4096 + 512 ..) holds the mbarrier; table entries 0..255 land at tw - 1 + ..
+        // so that the accessors' entry e - 1 convention holds: the twiddle area is used as [e], the caller passes tw + 1
+        CKKS_SHARED __align__(16) u64 s_bar[2];
+        FOR_THREADS {
+            if (threadIdx.x == 0) mbar_init(s_bar, 1);
+        }
+        BLOCK_SYNC;
+        FOR_THREADS {
+            const int tid = threadIdx.x;
+            if (tid == 0) {
+                mbar_expect_tx(s_bar, 256 * 128 + 2048 + (FP ? 0 : 2048));
+                bulk_g2s(tw, W, 2048, s_bar);
+                if (!FP) bulk_g2s(tc, C, 2048, s_bar);
+            }
+            bulk_g2s(sd + tid * 16, src + (size_t)slimb * N + tile * 16 + (size_t)tid * 256, 128, s_bar);
+            mbar_wait(s_bar, 0);
+        }
+        BLOCK_SYNC;
+        fwd_passA8_compute<FP, PRO>(sd, tw + 1, tc + 1, dst, limb, tile, N, mc, ql);
+        return;
+    }
     FOR_THREADS {
         const int tid = threadIdx.x;
         if (tid < NTW) { cp_async8(tw + tid, W + 1 + tid); if (!FP) cp_async8(tc + tid, C + 1 + tid); }
         if (LOGR == 8) {
             const int c = tid % TC, rr = tid / TC;
+#ifndef NTT_A_DIRECT
+#define NTT_A_DIRECT 0        // 1: the first round reads its tile straight from global memory (A/B)
+#endif
             const u64* s0 = src + (size_t)slimb * N + tile * TC + c;
+            if (!NTT_A_DIRECT) {
 #pragma unroll
-            for (int k = 0; k < 16; k++) cp_async8(sd + (rr + 16 * k) * TC + c, s0 + (size_t)(rr + 16 * k) * 256);
+                for (int k = 0; k < 16; k++) cp_async8(sd + (rr + 16 * k) * TC + c, s0 + (size_t)(rr + 16 * k) * 256);
+            }
         } else {
             const u64* s0 = src + (size_t)slimb * N + tid;
 #pragma unroll
@@ -382,7 +413,8 @@ __device__ __forceinline__ void fwd_passA_body(const u64* __restrict__ src, u64*
     }
     BLOCK_SYNC;
     if (LOGR == 8) {
-        fwd_passA8_compute<FP, PRO>(sd, tw, tc, dst, limb, tile, N, mc, ql);
+        fwd_passA8_compute<FP, PRO>(sd, tw, tc, dst, limb, tile, N, mc, ql,
+                                    NTT_A_DIRECT ? src + (size_t)slimb * N + tile * TC : nullptr);
     } else {
         FOR_THREADS {
             const int tid = threadIdx.x;

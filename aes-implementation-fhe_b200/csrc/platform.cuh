@@ -251,6 +251,29 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(__cvta_generic_to_global(gmem_src)) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// bulk asynchronous copies (the TMA engine's 1-D form): ONE instruction moves `bytes` (a multiple of 16, both addresses 16-byte
+// aligned) global -> shared and reports completion to an mbarrier in shared memory; no per-thread 8-byte requests, no
+// registers, no LSU queue slots while the data is in flight
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (u32)__cvta_generic_to_shared(smem_dst)),
+                 "l"(__cvta_generic_to_global(gmem_src)), "r"(bytes), "r"((u32)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 phase) {
+    asm volatile(
+        "{\n .reg .pred p;\n MBAR_WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra MBAR_WAIT_%=;\n}\n" ::"r"(
+            (u32)__cvta_generic_to_shared(bar)),
+        "r"(phase)
+        : "memory");
+}
 // pull a line towards the SM ahead of its use (no register, no shared memory held meanwhile)
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p))); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(p))); }
@@ -405,6 +428,10 @@ static inline void ldg_pair(const u64* p, u64& a, u64& b) { a = p[0]; b = p[1]; 
 static inline void cp_async8(void* d, const void* s) { memcpy(d, s, 8); }
 static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
 static inline void cp_async_wait_all() {}
+static inline void mbar_init(u64*, u32) {}
+static inline void mbar_expect_tx(u64*, u32) {}
+static inline void bulk_g2s(void* d, const void* s, u32 bytes, u64*) { memcpy(d, s, bytes); }
+static inline void mbar_wait(u64*, u32) {}
 static inline void prefetch_l1(const void*) {}
 static inline void prefetch_l2(const void*) {}
 #endif
