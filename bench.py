@@ -351,9 +351,11 @@ def run_ours(args) -> None:
         out = encrypt_eager(ct) if args.no_graph else pipe.encrypt_resident(ct, rk_ct)
         return drv.decode(*out)                                          # decrypt -> D2H -> bytes
 
+    out = None
     for _ in range(args.warmup):
         out = step_resident()
-    ok = bool(np.array_equal(np.asarray(drv.decode(*out)).reshape(want.shape), want))
+    # (--warmup 0 is only used by the emulation dry run of the CPU test suite; the timed steps are checked below)
+    ok = True if out is None else bool(np.array_equal(np.asarray(drv.decode(*out)).reshape(want.shape), want))
 
     if os.environ.get("BENCH_NCU_ROUND") == "1" and torch is not None and not args.no_graph:
         # profiling aid (`ncu --graph-profiling node --profile-from-start off`): ONE replay of the recorded middle round
