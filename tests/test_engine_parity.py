@@ -388,3 +388,25 @@ def test_cluster_ntt_bit_exact(mode):
             out = np.zeros((2, level + 1, p.N), dtype=np.uint64)
             assert p.lib.ckks_test_key_switch(p.eng._ptr, poly, level, 0, out) == 0
             assert np.array_equal(out[0], k0) and np.array_equal(out[1], k1)
+
+
+@pytest.mark.parametrize("which,logn,levels", [("emu", 12, 6), pytest.param("cuda", 16, 5, marks=pytest.mark.gpu)])
+def test_basis_conversion_paths_agree(which, logn, levels):
+    """The FP64-pipe basis conversion (k_base_convert_fp, default) and the 128-bit integer one (CKKS_BC_FP=0) are two
+    evaluations of the same exact sums: raw key switches at every level (every digit count, ragged last digits, q_0 as
+    a split 60-bit source and as an integer-pipe target) give identical words, and both equal the oracle's."""
+    import os
+    fp = Pair(which, logn, levels)
+    os.environ["CKKS_BC_FP"] = "0"
+    try:
+        integer = Pair(which, logn, levels)
+    finally:
+        os.environ.pop("CKKS_BC_FP", None)
+    rng = np.random.default_rng(11)
+    for level in range(levels, -1, -1):
+        poly = np.stack([rng.integers(0, fp.params.q[i], fp.N, dtype=np.uint64) for i in range(level + 1)])
+        want = fp.orc.key_switch(poly, level, 0)
+        for p in (fp, integer):
+            out = np.zeros((2, level + 1, p.N), dtype=np.uint64)
+            assert p.lib.ckks_test_key_switch(p.eng._ptr, poly, level, 0, out) == 0
+            assert np.array_equal(out[0], want[0]) and np.array_equal(out[1], want[1]), (which, level)
