@@ -341,14 +341,32 @@ __device__ __forceinline__ void fwd_passA8_compute(u64* sd, const u64* tw, const
             for (int k = 0; k < 16; k++) x[k] = bits2d(sd[(16 * rr + k) * TC + c]);
             fwd16_fp(x, t2, fm);
 #pragma unroll
-            for (int k = 0; k < 16; k++) d0[(size_t)(16 * rr + k) * 256] = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+#ifndef NTT_A_BULKST
+#define NTT_A_BULKST 0        // 1: the transformed tile leaves through shared memory and 256 bulk stores of one row (A/B)
+#endif
+            for (int k = 0; k < 16; k++) {
+                const u64 v = d2bits(fold_fp(x[k], fm.q, fm.qinv));
+                if (NTT_A_BULKST) sd[(16 * rr + k) * TC + c] = v;      // the slots this thread has just read
+                else d0[(size_t)(16 * rr + k) * 256] = v;
+            }
         } else {
             u64 x[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) x[k] = sd[(16 * rr + k) * TC + c];
             fwd16(x, t2, q);
 #pragma unroll
-            for (int k = 0; k < 16; k++) d0[(size_t)(16 * rr + k) * 256] = x[k];   // lazy [0,4q)
+            for (int k = 0; k < 16; k++) {
+                if (NTT_A_BULKST) sd[(16 * rr + k) * TC + c] = x[k];
+                else d0[(size_t)(16 * rr + k) * 256] = x[k];   // lazy [0,4q)
+            }
+        }
+    }
+    if (NTT_A_BULKST) {
+        FOR_THREADS { fence_proxy_async(); }
+        BLOCK_SYNC;
+        FOR_THREADS {
+            bulk_s2g(dst + (size_t)limb * N + tile * TC + (size_t)threadIdx.x * 256, sd + threadIdx.x * TC, 128);
+            bulk_store_commit_wait_read();
         }
     }
 }

@@ -267,6 +267,18 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  "l"(__cvta_generic_to_global(gmem_src)), "r"(bytes), "r"((u32)__cvta_generic_to_shared(bar))
                  : "memory");
 }
+// shared -> global bulk store of `bytes` (multiple of 16, 16-byte aligned): issued by one thread, executed by the copy engine;
+// bulk_store_wait_read returns when the shared-memory source has been read (the global writes complete asynchronously)
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u32 bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gmem_dst)),
+                 "r"((u32)__cvta_generic_to_shared(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(u64* bar, u32 phase) {
     asm volatile(
         "{\n .reg .pred p;\n MBAR_WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra MBAR_WAIT_%=;\n}\n" ::"r"(
@@ -432,6 +444,9 @@ static inline void mbar_init(u64*, u32) {}
 static inline void mbar_expect_tx(u64*, u32) {}
 static inline void bulk_g2s(void* d, const void* s, u32 bytes, u64*) { memcpy(d, s, bytes); }
 static inline void mbar_wait(u64*, u32) {}
+static inline void bulk_s2g(void* d, const void* s, u32 bytes) { memcpy(d, s, bytes); }
+static inline void bulk_store_commit_wait_read() {}
+static inline void fence_proxy_async() {}
 static inline void prefetch_l1(const void*) {}
 static inline void prefetch_l2(const void*) {}
 #endif
