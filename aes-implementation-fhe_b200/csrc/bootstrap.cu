@@ -222,6 +222,30 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
             E.galois_key(E.galois_for_rotation(-R.giant));
             E.galois_perm(E.galois_for_rotation(-R.giant));
         }
+    // the inner sums of ALL rows first, on the parent stream: one launch per 8 rows reads every baby rotation once
+    // (CKKS_DIAG_ROWS=0: one launch per row, each re-reading the babies it uses)
+    const char* sw = getenv("CKKS_DIAG_ROWS");         // read per call: the A/B test flips it between two bootstraps
+    const bool fuse_rows = !sw || atoi(sw) != 0;
+    std::vector<u64*> inners(P.rows.size(), nullptr);
+    const bool pre = fuse_rows && P.babies.size() <= 16;
+    if (pre) {
+        std::vector<const Ct*> xs;
+        for (int i : P.babies) xs.push_back(baby[i]);
+        for (size_t r0 = 0; r0 < P.rows.size(); r0 += 8) {
+            const size_t r1 = std::min(P.rows.size(), r0 + 8);
+            std::vector<u64*> outs;
+            std::vector<std::vector<const Pt*>> ps_;
+            for (size_t ri = r0; ri < r1; ri++) {
+                inners[ri] = E.alloc((size_t)nb * 2 * ps);
+                outs.push_back(inners[ri]);
+                std::vector<const Pt*> row(P.babies.size(), nullptr);
+                for (const BsgsTerm& T : P.rows[ri].terms)
+                    row[std::find(P.babies.begin(), P.babies.end(), T.i) - P.babies.begin()] = T.pt;
+                ps_.push_back(row);
+            }
+            E.diag_mac_rows(outs, xs, ps_, P.level, nb);
+        }
+    }
     if (nl > 1) E.fork(nl);
     try {
         for (size_t ri = 0; ri < P.rows.size(); ri++) {
@@ -230,8 +254,8 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
             if (nl > 1) E.set_lane((int)(ri % nl));
             // inner = sum_i diag_i (.) baby_i in one fused multiply-accumulate, un-rescaled (scale S_l^2): one rescale
             // per matrix at the end
-            u64* inner = E.alloc((size_t)nb * 2 * ps);
-            for (size_t off = 0; off < R.terms.size(); off += 16) {
+            u64* inner = pre ? inners[ri] : E.alloc((size_t)nb * 2 * ps);
+            for (size_t off = 0; !pre && off < R.terms.size(); off += 16) {
                 std::vector<const Ct*> xs;
                 std::vector<const Pt*> ps_;
                 for (size_t t = off; t < std::min(R.terms.size(), off + 16); t++) {
@@ -246,7 +270,7 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
                 }
             }
             if (R.giant % (long)E.slots() == 0) {
-                if (!S.sum) { S.sum = inner; inner = nullptr; }
+                if (!S.sum) { S.sum = inner; inner = nullptr; if (pre) inners[ri] = nullptr; }
                 else launch_add(E.ks, S.sum, S.sum, inner, ll, 2 * nb, U, E.st);
             } else {
                 const u64 g = E.galois_for_rotation(-R.giant);
@@ -265,15 +289,16 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
                 }
                 launch_add(E.ks, S.sum, S.sum, S.rbuf, ll, 1, U0, E.st);
             }
-            if (inner) E.release(inner);
+            if (inner && !pre) E.release(inner);
         }
         for (int l = 0; l < nl; l++) {                 // lane scratch goes back to the lane it came from
             if (nl > 1) E.set_lane(l);
             if (LA[l].tmp) E.release(LA[l].tmp);
             if (LA[l].rbuf) E.release(LA[l].rbuf);
         }
-    } catch (...) { if (nl > 1) E.join(); throw; }
+    } catch (...) { if (nl > 1) E.join(); for (u64* p : inners) E.release(p); throw; }
     if (nl > 1) E.join();
+    for (u64* p : inners) E.release(p);                // born on the parent stream, returned to it (after the join)
     // combine the lanes' accumulators on the parent stream
     u64* accqp = nullptr;
     Ct* sum = A.keep(E.new_ct(2, P.level, nb));

@@ -242,6 +242,8 @@ class Engine {
              int nterms);
     Ct* lincomb(const std::vector<Ct*>& X, const double* coef, int n);
     void diag_mac(u64* out, const std::vector<const Ct*>& x, const std::vector<const Pt*>& p, int level, int nb = 1);
+    void diag_mac_rows(const std::vector<u64*>& out, const std::vector<const Ct*>& x,
+                       const std::vector<std::vector<const Pt*>>& p, int level, int nb = 1);
     const u64* const_table(const double* coef_re_im, int n, int scale_level, int level);
     Ct* drop_to(const Ct* a, int level);         // plain limb drop (scale unchanged): internal/bootstrap use
 

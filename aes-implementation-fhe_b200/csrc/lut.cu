@@ -39,7 +39,52 @@ struct DiagMacArgs {
     int nterms, rows;
 };
 
+#define DIAG_ROWS_MAX 8
+struct DiagRowsArgs {
+    const u64* x[16];                  // baby-step ciphertexts [nb][2][rows][N]
+    const u64* p[DIAG_ROWS_MAX][16];   // p[r][t]: diagonal of giant row r that multiplies baby t (null: none)
+    u64* out[DIAG_ROWS_MAX];           // inner sum of giant row r, [nb][2][rows][N]
+    int nx, nrows, rows, nz;           // nz = 2 * nb slices (batch item * 2 + polynomial)
+};
+
 namespace {
+
+// All inner sums of one BSGS matrix in one pass: out_r = sum_t x_t (.) p[r][t] for every giant row r.  A baby-step word is
+// loaded ONCE and multiplied into every row that uses it (the one-row kernel re-reads all babies per row: 8 x the traffic of
+// a radix-32 matrix); the nz slices of a coefficient block sit next to each other in the launch order, so the diagonals
+// (shared by the batch) come from L2 for all but the first of them.
+template <int NR>
+__global__ void __launch_bounds__(256)
+k_diag_mac_rows(KShape S, const GRID_CONST DiagRowsArgs G, const GRID_CONST LimbList L) {
+    const int row = blockIdx.y;
+    const ModConst m = S.mc[L.idx[row]];
+    const size_t N = (size_t)1 << S.logn, P = (size_t)G.rows << S.logn;
+    const unsigned cb = blockIdx.x / (unsigned)G.nz, z = blockIdx.x - cb * (unsigned)G.nz;
+    FOR_THREADS {
+        const size_t i = (size_t)row * N + cb * 256 + threadIdx.x;
+        u64 hi[NR], lo[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) hi[r] = lo[r] = 0;
+        for (int t = 0; t < G.nx; t++) {
+            const u64 xv = ldg(G.x[t] + z * P + i);
+            u64 pv[NR];
+#pragma unroll
+            for (int r = 0; r < NR; r++) {             // the row's diagonals are requested together, then multiplied
+                const u64* pp = G.p[r][t];
+                pv[r] = pp ? ldg(pp + i) : 0;
+            }
+#pragma unroll
+            for (int r = 0; r < NR; r++) mac128(hi[r], lo[r], xv, pv[r]);
+            if ((t & 3) == 3 && t + 1 < G.nx) {        // a row takes at most one product per baby: sums stay below 4 q^2
+#pragma unroll
+                for (int r = 0; r < NR; r++) { lo[r] = barrett_reduce128(hi[r], lo[r], m); hi[r] = 0; }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NR; r++)
+            if (r < G.nrows) G.out[r][z * P + i] = barrett_reduce128(hi[r], lo[r], m);
+    }
+}
 
 // out[poly][rows][N] = sum_t x_t[poly] * p_t   (BSGS inner sum of a linear transform, un-rescaled; blockIdx.z = poly)
 __global__ void __launch_bounds__(256)
@@ -245,6 +290,34 @@ void Engine::diag_mac(u64* out, const std::vector<const Ct*>& x, const std::vect
     G.rows = level + 1;
     // [nb][2] slices with uniform strides: blockIdx.z = batch item * 2 + polynomial
     LAUNCH(k_diag_mac, dim3((unsigned)(N() / 256), level + 1, 2 * nb), dim3(256), st, ks, out, G, limb_list(mods_q(level)));
+}
+
+// every inner sum of a BSGS matrix in one launch: out[r] = sum_t x[t] (.) p[r][t] (p[r][t] null: baby t is not in row r)
+void Engine::diag_mac_rows(const std::vector<u64*>& out, const std::vector<const Ct*>& x,
+                           const std::vector<std::vector<const Pt*>>& p, int level, int nb) {
+    if (x.empty() || x.size() > 16 || out.empty() || out.size() > DIAG_ROWS_MAX || p.size() != out.size())
+        throw std::runtime_error("diag_mac_rows: 1..16 babies, 1..8 rows");
+    DiagRowsArgs G;
+    memset(&G, 0, sizeof(G));
+    for (size_t t = 0; t < x.size(); t++) {
+        if (x[t]->level != level || x[t]->npoly != 2 || x[t]->nb != nb) throw std::runtime_error("diag_mac_rows: level mismatch");
+        G.x[t] = x[t]->d;
+    }
+    for (size_t r = 0; r < out.size(); r++) {
+        if (p[r].size() != x.size()) throw std::runtime_error("diag_mac_rows: one diagonal slot per baby");
+        for (size_t t = 0; t < x.size(); t++) {
+            if (p[r][t] && p[r][t]->level != level) throw std::runtime_error("diag_mac_rows: level mismatch");
+            G.p[r][t] = p[r][t] ? p[r][t]->d : nullptr;
+        }
+        G.out[r] = out[r];
+    }
+    G.nx = (int)x.size();
+    G.nrows = (int)out.size();
+    G.rows = level + 1;
+    G.nz = 2 * nb;
+    const dim3 grid((unsigned)(N() / 256) * (unsigned)G.nz, level + 1, 1);
+    if (G.nrows <= 4) LAUNCH(k_diag_mac_rows<4>, grid, dim3(256), st, ks, G, limb_list(mods_q(level)));
+    else LAUNCH(k_diag_mac_rows<DIAG_ROWS_MAX>, grid, dim3(256), st, ks, G, limb_list(mods_q(level)));
 }
 
 // sum_k c_k X_k: one fused multiply-accumulate and one rescale per distinct input level, partial sums added

@@ -60,6 +60,28 @@ def test_bootstrap_precision_and_levels(boot_ctx):
     assert ctx.bootstrap_stats()["count"] == 2
 
 
+def test_bootstrap_fused_inner_sums_are_bit_identical(boot_ctx, monkeypatch):
+    """All inner sums of a BSGS matrix in one launch (k_diag_mac_rows, every baby rotation read once) against one launch
+    per giant row (CKKS_DIAG_ROWS=0): the same ciphertext bit for bit, single and batched."""
+    which, ctx = boot_ctx
+    eng = ctx.engine
+    n = eng.slot_count
+    rng = np.random.default_rng(5)
+
+    def export(ct):
+        a = np.zeros((eng._lib.ckks_ct_batch(ct._h), ct.polynomial_count, ct.level + 1, 2 * n), dtype=np.uint64)
+        assert eng._lib.ckks_ct_export(eng._ptr, ct._h, a) == 0
+        return a
+
+    cts = [ctx.to_intt(ctx.encrypt(np.exp(2j * np.pi * rng.random(n))))]
+    cts.append(eng.encrypt(np.exp(2j * np.pi * rng.random((3, n))), level=5))
+    for ct in cts:
+        monkeypatch.setenv("CKKS_DIAG_ROWS", "0")
+        per_row = export(ctx.bootstrap(ct))
+        monkeypatch.delenv("CKKS_DIAG_ROWS")
+        assert np.array_equal(export(ctx.bootstrap(ct)), per_row)
+
+
 @pytest.mark.slow
 def test_engine_bootstrap_agrees_with_the_bootstrap_oracle(boot_ctx):
     """The same bootstrapping spec evaluated by the engine (fused BSGS sums, hoisted and double-hoisted
