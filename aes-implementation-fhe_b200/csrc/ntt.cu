@@ -58,14 +58,31 @@ __device__ __forceinline__ double bits2d(u64 x) { union { double d; u64 u; } c; 
 
 struct alignas(16) u64x2 { u64 a, b; };
 
-// blockIdx.z = batch item * nz + slice
+// Two-pass kernels: blockIdx.y = batch item * nz + slice, blockIdx.z = item of the job (limb) -- "limb-major": the CTAs of
+// item 0 of EVERY slice and batch item are scheduled first.  Item 0 of a job over Q_l is the q_0 limb, whose integer-path CTAs
+// run about twice as long as the FP64 ones: started first they overlap with the rest instead of forming the tail of the
+// launch (NTT_LIMB_MAJOR=0: the round-2 order, z = slice-major).  The cluster kernels keep (8, item, slice).
+#ifndef NTT_LIMB_MAJOR
+#define NTT_LIMB_MAJOR 1
+#endif
+#if NTT_LIMB_MAJOR
+#define BIDX_ITEM blockIdx.z
+#define BIDX_SLICE blockIdx.y
+#define NTT_GRID(x, n, zb) dim3((x), (zb), (n))
+#else
+#define BIDX_ITEM blockIdx.y
+#define BIDX_SLICE blockIdx.z
+#define NTT_GRID(x, n, zb) dim3((x), (n), (zb))
+#endif
 struct ZB { unsigned z, b; };
-__device__ __forceinline__ ZB zb_split(const NttJob& J) {
+__device__ __forceinline__ ZB zb_split_of(const NttJob& J, unsigned s) {
     ZB r;
-    r.b = blockIdx.z / (unsigned)J.nz;
-    r.z = blockIdx.z - r.b * (unsigned)J.nz;
+    r.b = s / (unsigned)J.nz;
+    r.z = s - r.b * (unsigned)J.nz;
     return r;
 }
+__device__ __forceinline__ ZB zb_split(const NttJob& J) { return zb_split_of(J, BIDX_SLICE); }
+__device__ __forceinline__ ZB zb_split_cluster(const NttJob& J) { return zb_split_of(J, blockIdx.z); }
 
 // ============================================================================================ twiddle accessors
 // A radix-16 block rooted at table index X needs, for r = 0..3, the 2^r entries (X << r) + g.  get(r, g) returns the
@@ -467,9 +484,9 @@ __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_A)
 ntt_fwd_passA(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
     CKKS_SHARED __align__(16) u64 sm[kPassAWords];
     const ZB zb = zb_split(J);
-    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
-    const int limb = J.rows[zb.z][blockIdx.y], slimb = J.srows[zb.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[zb.z][blockIdx.y];
+    if (J.cnt[zb.z] && BIDX_ITEM >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][BIDX_ITEM], slimb = J.srows[zb.z][BIDX_ITEM], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][BIDX_ITEM];
     const size_t N = (size_t)1 << T.logn;
     src += zb.z * J.szs + zb.b * J.sbs;
     dst += zb.z * J.dzs + zb.b * J.dbs;
@@ -483,9 +500,9 @@ __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_A)
 ntt_fwd_passA_lift(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T, int pro_mod) {
     CKKS_SHARED __align__(16) u64 sm[kPassAWords];
     const ZB zb = zb_split(J);
-    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
-    const int limb = J.rows[zb.z][blockIdx.y], slimb = J.srows[zb.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[zb.z][blockIdx.y];
+    if (J.cnt[zb.z] && BIDX_ITEM >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][BIDX_ITEM], slimb = J.srows[zb.z][BIDX_ITEM], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][BIDX_ITEM];
     const size_t N = (size_t)1 << T.logn;
     src += zb.z * J.szs + zb.b * J.sbs;
     dst += zb.z * J.dzs + zb.b * J.dbs;
@@ -669,9 +686,9 @@ __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_B)
 ntt_fwd_passB(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
     CKKS_SHARED u64 sm[kPassBData];
     const ZB zb = zb_split(J);
-    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
-    const int limb = J.rows[zb.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[zb.z][blockIdx.y];
+    if (J.cnt[zb.z] && BIDX_ITEM >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][BIDX_ITEM], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][BIDX_ITEM];
     const size_t N = (size_t)1 << T.logn;
     const u32 Rn = (u32)(N >> 8);
     data += zb.z * J.dzs + zb.b * J.dbs;
@@ -685,9 +702,9 @@ __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_B)
 ntt_fwd_passB_ep(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T, const GRID_CONST NttFuse F) {
     CKKS_SHARED u64 sm[kPassBData];
     const ZB zb = zb_split(J);
-    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
-    const int limb = J.rows[zb.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[zb.z][blockIdx.y];
+    if (J.cnt[zb.z] && BIDX_ITEM >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][BIDX_ITEM], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][BIDX_ITEM];
     const size_t N = (size_t)1 << T.logn;
     const u32 Rn = (u32)(N >> 8);
     data += zb.z * J.dzs + zb.b * J.dbs;
@@ -696,7 +713,7 @@ ntt_fwd_passB_ep(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T,
     u64* g = data + off;
     const u64* ep_a = F.ep_a + zb.z * F.ep_azs + zb.b * F.ep_abs + off;
     u64* ep_out = F.ep_out + zb.z * F.ep_ozs + zb.b * F.ep_obs + off;
-    const u64 sv = F.s.v[blockIdx.y], svs = F.s.vs[blockIdx.y];
+    const u64 sv = F.s.v[BIDX_ITEM], svs = F.s.vs[BIDX_ITEM];
     if (use_fp(mc.q)) fwd_passB_body<true, true>(g, sm, tile, Rn, mc, T, mod, N, ep_a, ep_out, sv, svs);
     else fwd_passB_body<false, true>(g, sm, tile, Rn, mc, T, mod, N, ep_a, ep_out, sv, svs);
 }
@@ -775,9 +792,9 @@ __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_B)
 ntt_inv_passB(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
     CKKS_SHARED u64 sm[kPassBData];
     const ZB zb = zb_split(J);
-    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
-    const int limb = J.rows[zb.z][blockIdx.y], slimb = J.srows[zb.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[zb.z][blockIdx.y];
+    if (J.cnt[zb.z] && BIDX_ITEM >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][BIDX_ITEM], slimb = J.srows[zb.z][BIDX_ITEM], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][BIDX_ITEM];
     const size_t N = (size_t)1 << T.logn;
     const u32 Rn = (u32)(N >> 8);
     src += zb.z * J.szs + zb.b * J.sbs;
@@ -794,9 +811,9 @@ ntt_inv_passB_mul(const u64* __restrict__ src, const u64* __restrict__ src2, u64
                   NttTables T) {
     CKKS_SHARED u64 sm[kPassBData];
     const ZB zb = zb_split(J);
-    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
-    const int limb = J.rows[zb.z][blockIdx.y], slimb = J.srows[zb.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[zb.z][blockIdx.y];
+    if (J.cnt[zb.z] && BIDX_ITEM >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][BIDX_ITEM], slimb = J.srows[zb.z][BIDX_ITEM], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][BIDX_ITEM];
     const size_t N = (size_t)1 << T.logn;
     const u32 Rn = (u32)(N >> 8);
     src += zb.z * J.szs + zb.b * J.sbs;
@@ -908,9 +925,9 @@ __global__ void __launch_bounds__(kThreads, NTT_MIN_BLOCKS_A)
 ntt_inv_passA(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T) {
     CKKS_SHARED __align__(16) u64 sm[kPassAWords];
     const ZB zb = zb_split(J);
-    if (J.cnt[zb.z] && blockIdx.y >= J.cnt[zb.z]) return;
-    const int limb = J.rows[zb.z][blockIdx.y], tile = blockIdx.x;
-    const int mod = J.mods[zb.z][blockIdx.y];
+    if (J.cnt[zb.z] && BIDX_ITEM >= J.cnt[zb.z]) return;
+    const int limb = J.rows[zb.z][BIDX_ITEM], tile = blockIdx.x;
+    const int mod = J.mods[zb.z][BIDX_ITEM];
     const size_t N = (size_t)1 << T.logn;
     data += zb.z * J.dzs + zb.b * J.dbs;
     const ModConst mc = T.mc[mod];
@@ -1058,7 +1075,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kClThreads, 2)
 ntt_fwd_cluster_fused(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T,
                       const GRID_CONST NttFuse F) {
     extern __shared__ __align__(16) u64 sm_cl[];
-    const ZB zb = zb_split(J);
+    const ZB zb = zb_split_cluster(J);
     bool active;
     const int y = cluster_item(J, zb, active);
     const int limb = J.rows[zb.z][y], slimb = J.srows[zb.z][y], tile = blockIdx.x;
@@ -1187,7 +1204,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kClThreads, 2)
 ntt_inv_cluster(const u64* __restrict__ src, const u64* __restrict__ src2, u64* __restrict__ dst, const GRID_CONST NttJob J,
                 NttTables T) {
     extern __shared__ __align__(16) u64 sm_cl[];
-    const ZB zb = zb_split(J);
+    const ZB zb = zb_split_cluster(J);
     bool active;
     const int y = cluster_item(J, zb, active);
     const int limb = J.rows[zb.z][y], slimb = J.srows[zb.z][y], tile = blockIdx.x;
@@ -1204,7 +1221,7 @@ ntt_inv_cluster(const u64* __restrict__ src, const u64* __restrict__ src2, u64* 
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kClThreads, 2)
 ntt_fwd_cluster(const u64* __restrict__ src, u64* __restrict__ dst, const GRID_CONST NttJob J, NttTables T) {
     extern __shared__ __align__(16) u64 sm_cl[];
-    const ZB zb = zb_split(J);
+    const ZB zb = zb_split_cluster(J);
     bool active;
     const int y = cluster_item(J, zb, active);
     const int limb = J.rows[zb.z][y], slimb = J.srows[zb.z][y], tile = blockIdx.x;
@@ -1233,16 +1250,16 @@ void ntt_forward(const u64* src, u64* dst, const NttJob& J0, const NttTables& T,
     }
 #endif
     const unsigned R = 1u << (T.logn - 8);
-    dim3 gridB(R / 16, J.n, nbz(J));
+    dim3 gridB = NTT_GRID(R / 16, J.n, nbz(J));
     if (T.logn == 16) {
-        dim3 gridA(16, J.n, nbz(J));
+        dim3 gridA = NTT_GRID(16, J.n, nbz(J));
         if (NTT_PIPE)
             LAUNCH_DYN(ntt_fwd_passA_pipe<false>, dim3(pipe_grid(16 * J.n * nbz(J))), dim3(kThreads), kPipeWords * sizeof(u64), st,
                        src, dst, J, T, 0);
         else
             LAUNCH(ntt_fwd_passA<8>, gridA, dim3(kThreads), st, src, dst, J, T);
     } else if (T.logn == 12) {
-        dim3 gridA(1, J.n, nbz(J));
+        dim3 gridA = NTT_GRID(1, J.n, nbz(J));
         LAUNCH(ntt_fwd_passA<4>, gridA, dim3(kThreads), st, src, dst, J, T);
     } else {
         throw std::runtime_error("ntt: only N = 2^16 and N = 2^12 are built");
@@ -1266,9 +1283,9 @@ void ntt_forward_fused(const u64* src, u64* dst, const NttJob& J0, const NttTabl
     }
 #endif
     const unsigned R = 1u << (T.logn - 8);
-    dim3 gridB(R / 16, J.n, nbz(J));
+    dim3 gridB = NTT_GRID(R / 16, J.n, nbz(J));
     if (T.logn != 16 && T.logn != 12) throw std::runtime_error("ntt: only N = 2^16 and N = 2^12 are built");
-    dim3 gridA(T.logn == 16 ? 16 : 1, J.n, nbz(J));
+    dim3 gridA = NTT_GRID(T.logn == 16 ? 16 : 1, J.n, nbz(J));
     const dim3 gridP(pipe_grid(16 * J.n * nbz(J)));
     const size_t smemP = kPipeWords * sizeof(u64);
     if (F.pro_mod >= 0) {
@@ -1297,14 +1314,14 @@ void ntt_inverse(const u64* src, u64* dst, const NttJob& J0, const NttTables& T,
     }
 #endif
     const unsigned R = 1u << (T.logn - 8);
-    dim3 gridB(R / 16, J.n, nbz(J));
+    dim3 gridB = NTT_GRID(R / 16, J.n, nbz(J));
     if (src2) LAUNCH(ntt_inv_passB_mul, gridB, dim3(kThreads), st, src, src2, dst, J, T);
     else LAUNCH(ntt_inv_passB, gridB, dim3(kThreads), st, src, dst, J, T);
     if (T.logn == 16) {
-        dim3 gridA(16, J.n, nbz(J));
+        dim3 gridA = NTT_GRID(16, J.n, nbz(J));
         LAUNCH(ntt_inv_passA<8>, gridA, dim3(kThreads), st, dst, J, T);
     } else if (T.logn == 12) {
-        dim3 gridA(1, J.n, nbz(J));
+        dim3 gridA = NTT_GRID(1, J.n, nbz(J));
         LAUNCH(ntt_inv_passA<4>, gridA, dim3(kThreads), st, dst, J, T);
     } else {
         throw std::runtime_error("ntt: only N = 2^16 and N = 2^12 are built");
