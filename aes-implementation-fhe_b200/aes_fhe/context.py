@@ -9,9 +9,12 @@ exposing `Engine`/`Ciphertext` through the `backend=` keyword (the reference har
 """
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
+
+STACK_BOOT = os.environ.get("AESFHE_STACK_BOOT", "1") != "0"      # both nibble planes through ONE batched bootstrap
 
 
 def _load_backend(backend):
@@ -185,6 +188,19 @@ class EngineContext:
         self._bs_total_s += time.perf_counter() - t0
         self._bs_count += 1
         return out
+
+    def bootstrap_pair(self, hi, lo, pre=None):
+        """Both nibble planes of a state through the bootstrap (reference mixcol_final.py:158-162: one after the other).
+        Fused mode on an engine with a batch dimension: the planes are stacked into ONE handle of 2 nb items, so every
+        launch of the bootstrap carries both (AESFHE_STACK_BOOT=0: two bootstraps on two stream lanes)."""
+        f = (lambda c: self.bootstrap(pre(c))) if pre else self.bootstrap
+        eng = self.engine
+        if (self.fused and STACK_BOOT and hasattr(eng, "batch_slice") and hi.level == lo.level
+                and getattr(hi, "batch", 1) == getattr(lo, "batch", 1)):
+            nb = hi.batch
+            out = f(eng.stack([hi, lo]))
+            return eng.batch_slice(out, 0, nb), eng.batch_slice(out, nb, nb)
+        return self.pair_map(f, (hi,), (lo,))
 
     def bootstrap_stats(self):
         avg = self._bs_total_s / self._bs_count if self._bs_count else 0.0

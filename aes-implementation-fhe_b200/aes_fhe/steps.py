@@ -500,8 +500,7 @@ class MixColFinal(_MixBase):
             acc = self._renorm_pair(*self._xor_pair(u, w), depth=0 if do_final_bootstrap else None)
             out_hi, out_lo = acc
             if do_final_bootstrap:
-                boot = lambda c: self.ctx.bootstrap(self.ctx.to_intt(c))
-                out_hi, out_lo = self.ctx.pair_map(boot, (out_hi,), (out_lo,))
+                out_hi, out_lo = self.ctx.bootstrap_pair(out_hi, out_lo, pre=self.ctx.to_intt)
             return out_hi, out_lo
         log("two", two), log("thr", thr)
         acc = self._xor_pair(two, thr)
@@ -515,8 +514,7 @@ class MixColFinal(_MixBase):
         log("acc3", acc)
         out_hi, out_lo = acc
         if do_final_bootstrap:
-            boot = lambda c: self.ctx.bootstrap(self.ctx.to_intt(c))
-            out_hi, out_lo = self.ctx.pair_map(boot, (out_hi,), (out_lo,))
+            out_hi, out_lo = self.ctx.bootstrap_pair(out_hi, out_lo, pre=self.ctx.to_intt)
             log("out", (out_hi, out_lo))
         return out_hi, out_lo
 
@@ -589,7 +587,7 @@ class InvMixColumnsFHE(_MixBase):
             u, w = self.ctx.lane_map(lambda f: f(), [(left,), (right,)])
             out_h, out_l = self._renorm_pair(*self._xor_pair(u, w), depth=0 if do_final_bootstrap else None)
             if do_final_bootstrap:
-                out_h, out_l = self.ctx.pair_map(self.ctx.bootstrap, (out_h,), (out_l,))
+                out_h, out_l = self.ctx.bootstrap_pair(out_h, out_l)
             return out_h, out_l
         acc = self._xor_pair(e14, e11)
         log("acc1", acc)
@@ -600,6 +598,6 @@ class InvMixColumnsFHE(_MixBase):
         acc = self._xor_pair(acc, e9)
         out_h, out_l = self._renorm_pair(*acc, depth=0 if do_final_bootstrap else None)
         if do_final_bootstrap:
-            out_h, out_l = self.ctx.pair_map(self.ctx.bootstrap, (out_h,), (out_l,))
+            out_h, out_l = self.ctx.bootstrap_pair(out_h, out_l)
         log("out", (out_h, out_l))
         return out_h, out_l

@@ -173,6 +173,9 @@ int ckks_ct_stack(ckks_engine* e, ckks_ct* const* items, int n, ckks_ct** out) {
         *out = H(e->E->stack(v));
     });
 }
+int ckks_ct_slice(ckks_engine* e, const ckks_ct* ct, int start, int count, ckks_ct** out) {
+    return guard([&] { *out = H(e->E->slice(C(ct), start, count)); });
+}
 int ckks_ct_item(ckks_engine* e, const ckks_ct* ct, int index, ckks_ct** out) {
     return guard([&] { *out = H(e->E->item(C(ct), index)); });
 }

@@ -594,20 +594,31 @@ int Engine::batch_of(const Ct* a, const Ct* b) const {
 Ct* Engine::stack(const std::vector<Ct*>& items) {
     if (items.empty()) throw std::runtime_error("stack: no ciphertexts");
     const Ct* f = items[0];
-    for (const Ct* c : items)
-        if (!c || c->nb != 1 || c->npoly != f->npoly || c->level != f->level)
-            throw std::runtime_error("stack: items must be unbatched ciphertexts of one shape");
-    Ct* r = new_ct(f->npoly, f->level, (int)items.size());
+    int nb = 0;
+    for (const Ct* c : items) {
+        if (!c || c->npoly != f->npoly || c->level != f->level)
+            throw std::runtime_error("stack: items must be ciphertexts of one shape");
+        nb += c->nb;
+    }
+    Ct* r = new_ct(f->npoly, f->level, nb);
     const size_t per = (size_t)f->npoly * (f->level + 1) * N();
-    for (size_t i = 0; i < items.size(); i++) dev::d2d(r->d + i * per, items[i]->d, per * sizeof(u64), st);
+    size_t at = 0;
+    for (const Ct* c : items) {                       // a batched item contributes all its items, in order
+        dev::d2d(r->d + at * per, c->d, (size_t)c->nb * per * sizeof(u64), st);
+        at += c->nb;
+    }
+    return r;
+}
+Ct* Engine::slice(const Ct* c, int start, int count) {
+    if (start < 0 || count < 1 || start + count > c->nb) throw std::runtime_error("slice: batch range out of bounds");
+    Ct* r = new_ct(c->npoly, c->level, count);
+    const size_t per = (size_t)c->npoly * (c->level + 1) * N();
+    dev::d2d(r->d, c->d + (size_t)start * per, (size_t)count * per * sizeof(u64), st);
     return r;
 }
 Ct* Engine::item(const Ct* c, int i) {
     if (i < 0 || i >= c->nb) throw std::runtime_error("item: batch index out of range");
-    Ct* r = new_ct(c->npoly, c->level, 1);
-    const size_t per = (size_t)c->npoly * (c->level + 1) * N();
-    dev::d2d(r->d, c->d + (size_t)i * per, per * sizeof(u64), st);
-    return r;
+    return slice(c, i, 1);
 }
 void Engine::free_ct(Ct* c) {
     if (!c) return;

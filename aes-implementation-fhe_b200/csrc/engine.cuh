@@ -114,7 +114,8 @@ class Engine {
     Ct* new_ct(int npoly, int level, int nb = 1);
     static size_t bstride(const Ct* c, size_t per_item) { return c->nb > 1 ? per_item : 0; }   // 0 broadcasts an nb = 1 operand
     int batch_of(const Ct* a, const Ct* b) const;   // common batch size of a binary operation (nb = 1 broadcasts)
-    Ct* stack(const std::vector<Ct*>& items);       // nb = 1 ciphertexts of one shape -> one batched ciphertext (copies)
+    Ct* stack(const std::vector<Ct*>& items);       // ciphertexts of one shape (batched ones contribute all their items) -> one batched ciphertext (copies)
+    Ct* slice(const Ct* c, int start, int count);   // copy of batch items start .. start + count - 1
     Ct* item(const Ct* c, int i);                   // copy of batch item i as an nb = 1 ciphertext
     void free_ct(Ct* c);
     void free_pt(Pt* p);

@@ -481,10 +481,14 @@ class Engine(LazyOps):
         return z if nb == 1 else z.reshape(nb, self.slot_count)
 
     def stack(self, cts: Sequence[Ciphertext]) -> Ciphertext:
-        """Unbatched ciphertexts of one shape -> one batched ciphertext (copies); every later operation on it runs
-        all items through one set of kernel launches."""
+        """Ciphertexts of one shape (a batched one contributes all its items) -> one batched ciphertext (copies); every
+        later operation on it runs all items through one set of kernel launches."""
         arr = (C.c_void_p * len(cts))(*[c._h for c in cts])
         return self._new(self._lib.ckks_ct_stack, arr, len(cts))
+
+    def batch_slice(self, ct: Ciphertext, start: int, count: int) -> Ciphertext:
+        """Items start .. start + count - 1 of a batched ciphertext as a batched ciphertext of their own (copies)."""
+        return self._new(self._lib.ckks_ct_slice, ct._h, int(start), int(count))
 
     def unstack(self, ct: Ciphertext) -> List[Ciphertext]:
         return [self._new(self._lib.ckks_ct_item, ct._h, i) for i in range(ct.batch)]

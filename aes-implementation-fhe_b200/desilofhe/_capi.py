@@ -77,6 +77,7 @@ def load():
         "ckks_encrypt_zeta16_batch": (i32, [vp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"), i32, i32, pp]),
         "ckks_ct_stack": (i32, [vp, pp, i32, pp]),
         "ckks_ct_item": (i32, [vp, vp, i32, pp]),
+        "ckks_ct_slice": (i32, [vp, vp, i32, i32, pp]),
         "ckks_ct_free": (None, [vp, vp]), "ckks_pt_free": (None, [vp, vp]),
         "ckks_ct_level": (i32, [vp]), "ckks_ct_npoly": (i32, [vp]), "ckks_pt_level": (i32, [vp]),
         "ckks_add": (i32, [vp, vp, vp, pp]), "ckks_sub": (i32, [vp, vp, vp, pp]),

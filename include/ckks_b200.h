@@ -102,8 +102,11 @@ int ckks_decrypt_zeta16(ckks_engine* e, const ckks_ct* ct, uint8_t* nibbles_out)
 int ckks_ct_batch(const ckks_ct* ct);
 int ckks_encrypt_batch(ckks_engine* e, const double* slots_re_im /* [nb][2 slot_count] */, int nb, int level, ckks_ct** out);
 int ckks_encrypt_zeta16_batch(ckks_engine* e, const uint8_t* nibbles /* [nb][slot_count] */, int nb, int level, ckks_ct** out);
-int ckks_ct_stack(ckks_engine* e, ckks_ct* const* items /* n unbatched ciphertexts of one shape */, int n, ckks_ct** out);
+int ckks_ct_stack(ckks_engine* e, ckks_ct* const* items /* n ciphertexts of one shape; a batched one contributes all its items */, int n, ckks_ct** out);
 int ckks_ct_item(ckks_engine* e, const ckks_ct* ct, int index, ckks_ct** out /* copy of one item, nb = 1 */);
+/* copy of items start .. start + count - 1.  With ckks_ct_stack: the two nibble planes of an AES state (reference
+ * mixcol_final.py:158-162 bootstraps them one after the other) go through ONE bootstrap of 2 nb items */
+int ckks_ct_slice(ckks_engine* e, const ckks_ct* ct, int start, int count, ckks_ct** out);
 void ckks_ct_free(ckks_engine* e, ckks_ct* ct);
 void ckks_pt_free(ckks_engine* e, ckks_pt* pt);
 int ckks_ct_level(const ckks_ct* ct);
