@@ -15,6 +15,10 @@ import time
 import numpy as np
 
 STACK_BOOT = os.environ.get("AESFHE_STACK_BOOT", "1") != "0"      # both nibble planes through ONE batched bootstrap
+# ... and through every other step that treats them alike (XOR4, renorm, ShiftRows, rotations).  Measured on the B200: no
+# gain (4 590 against 4 702 blocks/s with only the bootstrap stacked): those steps run at levels <= 5, where a launch of 4 pairs
+# is below one wave of CTAs and two concurrent stream lanes fill the device better than one launch of twice the size.
+STACK_PAIRS = os.environ.get("AESFHE_STACK_PAIRS", "0") != "0"
 
 
 def _load_backend(backend):
@@ -161,6 +165,51 @@ class EngineContext:
             return self.engine.pair_map(fn, first, second)
         return fn(*first), fn(*second)
 
+    def pair_apply(self, fn, hi_args, lo_args, stack=None):
+        """(fn(*hi_args), fn(*lo_args)) for a step that does the SAME thing to both nibble planes (XOR4, AddRoundKey,
+        renorm, ShiftRows, column rotations: reference pipeline.py / mixcol_final.py call them once per plane).
+        Fused mode on an engine with a batch dimension: each ciphertext argument pair is stacked into one handle of
+        2 nb items (hi items first), fn runs ONCE, and its result (a ciphertext or a list of them) is cut back into the
+        two planes, so every kernel launch carries both.  A plane pair that was cut from one stacked result is
+        re-stacked without a copy; an nb = 1 pair next to batched arguments (round keys) is repeated per item.
+        Anything else (stand-in backends, planes of different shapes, stacking switched off): two stream lanes.
+        `stack`: None = the AESFHE_STACK_PAIRS default (off, see above); the bootstrap passes AESFHE_STACK_BOOT (on)."""
+        eng = self.engine
+        is_ct = lambda x: hasattr(x, "level") and hasattr(x, "polynomial_count")
+        stack = STACK_PAIRS if stack is None else stack
+        if not (self.fused and stack and hasattr(eng, "batch_slice") and len(hi_args) == len(lo_args)):
+            return self.pair_map(fn, hi_args, lo_args)
+        cts = [(a, b) for a, b in zip(hi_args, lo_args) if is_ct(a) or is_ct(b)]
+        if not cts or any(not (is_ct(a) and is_ct(b)) or a.level != b.level or a.batch != b.batch
+                          or a.polynomial_count != b.polynomial_count for a, b in cts):
+            return self.pair_map(fn, hi_args, lo_args)
+        nb = max(a.batch for a, _ in cts)
+        if any(a.batch not in (1, nb) for a, _ in cts):
+            return self.pair_map(fn, hi_args, lo_args)
+        args = []
+        for a, b in zip(hi_args, lo_args):
+            if not is_ct(a):
+                if not (a is b or a == b):
+                    return self.pair_map(fn, hi_args, lo_args)
+                args.append(a)
+                continue
+            pa, pb = getattr(a, "_plane_of", None), getattr(b, "_plane_of", None)
+            if pa is not None and pb is not None and pa[0] is pb[0] and (pa[1], pb[1]) == (0, 1):
+                args.append(pa[0])
+            else:
+                args.append(eng.stack([a] * (nb // a.batch) + [b] * (nb // b.batch)))
+        out = fn(*args)
+
+        def cut(c):
+            h, l = eng.batch_slice(c, 0, nb), eng.batch_slice(c, nb, nb)
+            h._plane_of, l._plane_of = (c, 0), (c, 1)
+            return h, l
+
+        if isinstance(out, (list, tuple)):
+            halves = [cut(c) for c in out]
+            return [h for h, _ in halves], [l for _, l in halves]
+        return cut(out)
+
     def lane_map(self, fn, arg_tuples):
         """[fn(*a) for a in arg_tuples], each call on its own stream lane when the backend has lanes."""
         if self.fused and hasattr(self.engine, "lane_map"):
@@ -194,13 +243,7 @@ class EngineContext:
         Fused mode on an engine with a batch dimension: the planes are stacked into ONE handle of 2 nb items, so every
         launch of the bootstrap carries both (AESFHE_STACK_BOOT=0: two bootstraps on two stream lanes)."""
         f = (lambda c: self.bootstrap(pre(c))) if pre else self.bootstrap
-        eng = self.engine
-        if (self.fused and STACK_BOOT and hasattr(eng, "batch_slice") and hi.level == lo.level
-                and getattr(hi, "batch", 1) == getattr(lo, "batch", 1)):
-            nb = hi.batch
-            out = f(eng.stack([hi, lo]))
-            return eng.batch_slice(out, 0, nb), eng.batch_slice(out, nb, nb)
-        return self.pair_map(f, (hi,), (lo,))
+        return self.pair_apply(f, (hi,), (lo,), stack=STACK_BOOT)
 
     def bootstrap_stats(self):
         avg = self._bs_total_s / self._bs_count if self._bs_count else 0.0

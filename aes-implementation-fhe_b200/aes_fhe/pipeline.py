@@ -292,6 +292,8 @@ class RowMajorShiftRows:
         return out
 
     def apply(self, ct_hi, ct_lo) -> Pair:
+        if getattr(self.ctx, "fused", False):
+            return self.ctx.pair_apply(self._apply_one, (ct_hi,), (ct_lo,))
         return self._apply_one(ct_hi), self._apply_one(ct_lo)
 
 
@@ -346,7 +348,7 @@ class BatchedStateEncoder:
     def renorm(self, ct_hi, ct_lo, level=None) -> Pair:
         """encode(decode(hi, lo)) for the batched layout: every slot is snapped; stays on the device when it can."""
         if getattr(self.ctx, "device_renorm", False):
-            return self.ctx.pair_map(self.ctx.snap_zeta16, (ct_hi, level, 1), (ct_lo, level, 1))
+            return self.ctx.pair_apply(self.ctx.snap_zeta16, (ct_hi, level, 1), (ct_lo, level, 1))
         return self.encode(self.decode(ct_hi, ct_lo), level=level)
 
     def decode(self, ct_hi, ct_lo) -> np.ndarray:

@@ -75,7 +75,7 @@ class StateEncoder:
     def renorm(self, ct_hi, ct_lo, level=None) -> Pair:
         """encode(decode(hi, lo)): on the B200 engine without leaving the device (slots off the stride grid -> 1.0)."""
         if getattr(self.ctx, "device_renorm", False):
-            return self.ctx.pair_map(self.ctx.snap_zeta16, (ct_hi, level, self.stride), (ct_lo, level, self.stride))
+            return self.ctx.pair_apply(self.ctx.snap_zeta16, (ct_hi, level, self.stride), (ct_lo, level, self.stride))
         return self.encode(self.decode(ct_hi, ct_lo), level=level)
 
     def decode(self, ct_hi, ct_lo) -> np.ndarray:
@@ -207,7 +207,7 @@ class AddRoundKey:
     def __call__(self, ct_hi, ct_lo, key_hi, key_lo) -> Pair:
         ctx = self.xor4.ctx
         if getattr(ctx, "fused", False):      # the two nibble planes never interact inside XOR4: overlap them
-            return ctx.pair_map(self.xor4.apply, (ct_hi, key_hi), (ct_lo, key_lo))
+            return ctx.pair_apply(self.xor4.apply, (ct_hi, key_hi), (ct_lo, key_lo))
         return self.xor4.apply(ct_hi, key_hi), self.xor4.apply(ct_lo, key_lo)
 
 
@@ -339,6 +339,8 @@ class _MaskedRowRotate:
         return out
 
     def apply(self, ct_hi, ct_lo) -> Pair:
+        if getattr(self.ctx, "fused", False):
+            return self.ctx.pair_apply(self._apply_one, (ct_hi,), (ct_lo,))
         return self._apply_one(ct_hi), self._apply_one(ct_lo)
 
 
@@ -431,7 +433,7 @@ class _MixBase:
 
     def _rot_pair(self, pair: Pair, k_up: int) -> Pair:
         step = -4 * k_up * self.stride
-        return self.ctx.pair_map(self.ctx.rotate, (pair[0], step), (pair[1], step))
+        return self.ctx.pair_apply(self.ctx.rotate, (pair[0], step), (pair[1], step))
 
     def _col_shift_rowmajor(self, ct, k_up: int):
         return self.ctx.rotate(ct, -4 * k_up * self.stride)
@@ -439,12 +441,12 @@ class _MixBase:
     def _shifts(self, ct_hi, ct_lo):
         if getattr(self.ctx, "fused", False):      # rot1..3 of one ciphertext share one ModUp (hoisting)
             steps = [-4 * k * self.stride for k in (1, 2, 3)]
-            return list(zip(self.ctx.rotate_many(ct_hi, steps), self.ctx.rotate_many(ct_lo, steps)))
+            return list(zip(*self.ctx.pair_apply(self.ctx.rotate_many, (ct_hi, steps), (ct_lo, steps))))
         return [(self._col_shift_rowmajor(ct_hi, k), self._col_shift_rowmajor(ct_lo, k)) for k in (1, 2, 3)]
 
     def _xor_pair(self, a: Pair, b: Pair) -> Pair:
         if getattr(self.ctx, "fused", False):
-            return self.ctx.pair_map(self.xor4.apply, (a[0], b[0]), (a[1], b[1]))
+            return self.ctx.pair_apply(self.xor4.apply, (a[0], b[0]), (a[1], b[1]))
         return self.xor4.apply(a[0], b[0]), self.xor4.apply(a[1], b[1])
 
 
@@ -481,7 +483,7 @@ class MixColFinal(_MixBase):
             steps = [-4 * k * self.stride for k in (2, 3)]
             # rot2 / rot3 only feed XOR4s that run at XOR4_DEPTH: rotate the state there, not at its own level
             lo_hi, lo_lo = self.ctx.level_down(ct_hi, XOR4_DEPTH), self.ctx.level_down(ct_lo, XOR4_DEPTH)
-            r2, r3 = zip(self.ctx.rotate_many(lo_hi, steps), self.ctx.rotate_many(lo_lo, steps))
+            r2, r3 = zip(*self.ctx.pair_apply(self.ctx.rotate_many, (lo_hi, steps), (lo_lo, steps)))
         else:
             r1, r2, r3 = self._shifts(ct_hi, ct_lo)
             log("rotc1", r1), log("rotc2", r2), log("rotc3", r3), log("in", (ct_hi, ct_lo))

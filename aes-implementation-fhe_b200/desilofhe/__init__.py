@@ -63,7 +63,7 @@ class Ciphertext:
 
     On an `Engine(lazy=True)` a handle may stand for a deferred expression (`desilofhe/lazy.py`): level and batch size are
     known at once, the value is computed when `_h` is first needed."""
-    __slots__ = ("_eng", "_hraw", "ntt_form", "_lz", "_lvl", "_nb", "_memo", "__weakref__")
+    __slots__ = ("_eng", "_hraw", "ntt_form", "_lz", "_lvl", "_nb", "_memo", "_plane_of", "__weakref__")
 
     def __init__(self, eng: "Engine", handle: int, lazy=None, level: int = -1, batch: int = 1):
         self._eng = eng
