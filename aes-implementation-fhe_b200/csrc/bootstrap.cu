@@ -214,7 +214,10 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
     // are summed after the join.
     const size_t n = E.N();
     const int rows = P.level + 1 + E.K();
-    const int nl = (int)std::min<size_t>(P.rows.size(), 4);
+    // lanes for the giant rows: 2 (CKKS_BSGS_LANES).  With both nibble planes in one batched bootstrap every launch is several
+    // waves of CTAs; measured 1 / 2 / 3 / 4 / 8 lanes: 46.7 / 46.8 / 47.2 / 47.0 / 47.6 ms per pair and round
+    static const int max_lanes = getenv("CKKS_BSGS_LANES") ? std::max(1, atoi(getenv("CKKS_BSGS_LANES"))) : 2;
+    const int nl = (int)std::min<size_t>(P.rows.size(), (size_t)max_lanes);
     struct LaneAcc { u64* accqp = nullptr; u64* sum = nullptr; u64* tmp = nullptr; u64* rbuf = nullptr; };
     std::vector<LaneAcc> LA(nl);
     for (const BsgsRow& R : P.rows)
