@@ -493,15 +493,25 @@ Ct* Engine::bootstrap(Ct* a) {
     Ct* cj = A.keep(conjugate(t));
     Ct* re = A.keep(add(t, cj));
     Ct* im = A.keep(mul_i(A.keep(sub(t, cj)), -1));
-    // the two halves are independent: evaluate them on two stream lanes
-    fork(2);
-    try {
-        set_lane(0);
-        re = eval_mod(*this, A, re, B);
-        set_lane(1);
-        im = eval_mod(*this, A, im, B);
-    } catch (...) { join(); throw; }
-    join();
+    static const bool stack_halves = getenv("CKKS_EVALMOD_STACK") && atoi(getenv("CKKS_EVALMOD_STACK")) != 0;
+    if (stack_halves) {
+        // the two halves as ONE handle of 2 nb items: one EvalMod whose launches carry both
+        const int nb = re->nb;
+        Ct* both = A.keep(stack({re, im}));
+        both = eval_mod(*this, A, both, B);
+        re = A.keep(slice(both, 0, nb));
+        im = A.keep(slice(both, nb, nb));
+    } else {
+        // the two halves are independent: evaluate them on two stream lanes
+        fork(2);
+        try {
+            set_lane(0);
+            re = eval_mod(*this, A, re, B);
+            set_lane(1);
+            im = eval_mod(*this, A, im, B);
+        } catch (...) { join(); throw; }
+        join();
+    }
     t = A.keep(add(re, A.keep(mul_i(im, +1))));
     if (t->level < B.stc[0].level) throw std::runtime_error("bootstrap: level accounting is off");
     if (t->level > B.stc[0].level) t = level_down(t, B.stc[0].level);     // memoised on (and owned by) its parent
