@@ -243,7 +243,10 @@ class EngineContext:
         Fused mode on an engine with a batch dimension: the planes are stacked into ONE handle of 2 nb items, so every
         launch of the bootstrap carries both (AESFHE_STACK_BOOT=0: two bootstraps on two stream lanes)."""
         f = (lambda c: self.bootstrap(pre(c))) if pre else self.bootstrap
-        return self.pair_apply(f, (hi,), (lo,), stack=STACK_BOOT)
+        n0 = self._bs_count
+        out = self.pair_apply(f, (hi,), (lo,), stack=STACK_BOOT)
+        self._bs_count = n0 + 2          # the count is per nibble plane (engine_context.py:147-171), stacked or not
+        return out
 
     def bootstrap_stats(self):
         avg = self._bs_total_s / self._bs_count if self._bs_count else 0.0

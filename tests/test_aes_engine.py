@@ -176,6 +176,37 @@ def test_config5_batched_fips_round(boot_ctx):
     assert np.array_equal(drv.decode(*out), plain_round(blocks, rks[1]))
 
 
+def test_config5_round_with_both_planes_stacked(boot_ctx, monkeypatch):
+    """EngineContext.pair_apply: every step that treats the two nibble planes alike (AddRoundKey, XOR4, renorm, ShiftRows,
+    column rotations, bootstrap) runs ONCE on a handle holding both planes (AESFHE_STACK_PAIRS=1; the default stacks the
+    bootstrap only).  Same FIPS-197 bytes; round keys (nb = 1) are repeated per item, a plane pair cut from one stacked
+    result is re-stacked without a copy."""
+    which, ctx = boot_ctx
+    import aes_fhe.context as C
+    monkeypatch.setattr(C, "STACK_PAIRS", True)
+    pipe = make_pipe(ctx)
+    drv = aes_fhe.FipsDriver(pipe, batched=True)
+    eng = ctx.engine
+    stride = eng.slot_count // 16
+    rng = np.random.default_rng(77)
+    blocks = rng.integers(0, 256, (2, stride, 16), dtype=np.uint8)
+    rks = aes_fhe.expand_aes128_key(np.frombuffer(bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c"), dtype=np.uint8))
+    rk_ct = pipe._prepare_round_keys([drv._perm(rk) for rk in rks])
+    ct = pipe.encoder.encode(drv._perm(blocks))
+    k0 = eng.counters()
+    out = pipe.encrypt_round(*ct, *rk_ct[1])
+    k1 = eng.counters()
+    assert out[0].batch == 2 and out[0]._plane_of[0] is out[1]._plane_of[0]          # cut from one stacked handle
+    assert k1["bootstrap"] - k0["bootstrap"] == 4                                     # 2 pairs x 2 planes, one call
+    for p in range(2):
+        assert np.array_equal(drv.decode(*out)[p], plain_round(blocks[p], rks[1]))
+    # the default: only the bootstrap is stacked
+    monkeypatch.setattr(C, "STACK_PAIRS", False)
+    out = pipe.encrypt_round(*ct, *rk_ct[1])
+    for p in range(2):
+        assert np.array_equal(drv.decode(*out)[p], plain_round(blocks[p], rks[1]))
+
+
 def test_config5_many_pairs_in_one_batched_handle(boot_ctx):
     """configs[4]: "many ciphertexts" -- P ciphertext pairs travel as ONE batched handle pair (Ciphertext.batch = P), so every
     step of the round (LUTs, key switches, renorms, both bootstraps) runs all pairs through one set of kernel launches;

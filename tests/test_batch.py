@@ -76,6 +76,25 @@ def test_stack_unstack_and_decrypt(env):
         eng.add(env.bz, eng.stack(env.items_w[:2]))          # 3 items against 2: refused
 
 
+def test_stack_of_batched_handles_and_slices(env):
+    """ckks_ct_stack takes batched items (they contribute all their items, in order) and ckks_ct_slice cuts a range back out:
+    how the two nibble planes of an AES state travel through ONE bootstrap (aes_fhe EngineContext.pair_apply)."""
+    eng = env.eng
+    both = eng.stack([env.bz, env.items_w[0], env.bw])
+    assert both.batch == 2 * NB + 1
+    env.same(both, env.items_z + [env.items_w[0]] + env.items_w)
+    env.same(eng.batch_slice(both, 0, NB), env.items_z)
+    env.same(eng.batch_slice(both, NB + 1, NB), env.items_w)
+    env.same(eng.batch_slice(both, NB, 1), [env.items_w[0]])
+    # an operation on the stack is the operation on every item (the contract that makes the stacked bootstrap exact)
+    env.same(eng.batch_slice(eng.multiply(both, both, eng._rk), NB + 1, NB), [eng.multiply(c, c, eng._rk) for c in env.items_w])
+    for bad in ((-1, 1), (0, 0), (2 * NB, 2)):
+        with pytest.raises(RuntimeError):
+            eng.batch_slice(both, *bad)
+    with pytest.raises(RuntimeError):
+        eng.stack([env.bz, eng.level_down(env.items_w[0], env.bz.level - 1)])      # shapes differ: refused
+
+
 def test_batched_encryption_equals_consecutive_single_encryptions(env):
     a, b = env.new_engine(), env.new_engine()                  # same seed: same keys, encryption counters at 0
     cb = a.encrypt(env.z)
