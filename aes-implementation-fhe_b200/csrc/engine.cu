@@ -95,10 +95,22 @@ static u64 prime_nearest(double target, u64 step, std::set<u64>& used) {
     }
     throw std::runtime_error("no prime found");
 }
-static std::vector<double> canonical_scales(const std::vector<u64>& q, int top_scale_bits) {
+// Message ratio q_0 / S_0 of the chain (ModRaise, and the head-room the modulus-256 XOR outputs of the reference's table
+// need at level 0: SURVEY.md H3).  A chain whose q_0 is SMALLER than 2^(scale_bits + ratio) keeps the ratio by letting the
+// scale descend: S_l = 2^(scale_bits - drop 2^-l), drop = scale_bits + ratio - q0_bits.  The deviation from 2^scale_bits
+// doubles per level downwards (S_{l-1} = S_l^2 / q_l), so every q_l still sits next to 2^scale_bits, the levels >= 6 carry
+// 2^scale_bits within a fifth of a bit, and only S_2, S_1, S_0 give up 2.5, 5 and 10 bits (the XOR4 outputs that land
+// there tolerate 4e-3).  With q0_bits = 50 the whole chain, q_0 included, is below the FP64 limit: no kernel takes the
+// 64-bit integer path any more.  drop = 0 (q0_bits = scale_bits + ratio, the 60-bit q_0) is the uniform chain.
+static const int kRatioBits = 10;
+static double chain_drop(int scale_bits, int q0_bits) { return std::max(0, scale_bits + kRatioBits - q0_bits); }
+static double desired_scale(int scale_bits, double drop, int l) {
+    return drop > 0 ? pow(2.0, (double)scale_bits - drop * ldexp(1.0, -l)) : ldexp(1.0, scale_bits);
+}
+static std::vector<double> canonical_scales(const std::vector<u64>& q, double top_scale) {
     const int L = (int)q.size() - 1;
     std::vector<double> s(L + 1);
-    s[L] = ldexp(1.0, top_scale_bits);
+    s[L] = top_scale;
     for (int l = L; l >= 1; l--) s[l - 1] = s[l] * s[l] / (double)q[l];
     return s;
 }
@@ -123,9 +135,13 @@ Params default_params(int logn, int levels, int scale_bits, int q0_bits, int p_b
     std::vector<u64> reserve = primes_below(1ull << p_bits, step, 16, used);
     P.q.assign(nq, 0);
     P.q[0] = primes_below(1ull << q0_bits, step, 1, used)[0];
-    const double delta = ldexp(1.0, scale_bits), hi = ldexp(1.0, top_bits), cap = pow(2.0, 60.5);
-    double s = top_levels > 0 ? hi : delta;
+    const double hi = ldexp(1.0, top_bits), cap = pow(2.0, 60.5);
+    const double drop = chain_drop(scale_bits, q0_bits);
+    P.top_scale = top_levels > 0 ? hi : desired_scale(scale_bits, drop, levels);
+    P.scale_drop = (int)drop;
+    double s = P.top_scale;
     for (int l = levels; l >= 1; l--) {
+        const double delta = desired_scale(scale_bits, drop, l - 1);
         const double want = (top_levels > 0 && l - 1 > levels - top_levels) ? hi : delta;   // desired S_{l-1}
         const double next = std::max(want, s * s / cap);
         const double target = s * s / next;
@@ -185,7 +201,8 @@ Engine::Engine(const Params& P) : prm(P) {
     if (prm.alpha > BC_MAX_SRC || K() > BC_MAX_SRC) throw std::runtime_error("engine: digit too wide");
     if (L() + 1 + K() > BC_MAX_TGT) throw std::runtime_error("engine: too many conversion targets");
     if ((dnum()) > NTT_MAX_Z) throw std::runtime_error("engine: dnum too large");
-    scales = canonical_scales(prm.q, prm.top_levels > 0 ? prm.top_bits : prm.scale_bits);
+    scales = canonical_scales(prm.q, prm.top_scale > 0 ? prm.top_scale
+                                                        : ldexp(1.0, prm.top_levels > 0 ? prm.top_bits : prm.scale_bits));
     const size_t n = N();
     const int nm = nmod();
     std::vector<ModConst> mc(nm);
@@ -988,6 +1005,9 @@ Ct* Engine::encrypt_coeffs(const i64* coef, int level, int nb) {
 // secret-key decryption to slot values left ON THE DEVICE (nb x 2n doubles, caller releases)
 double* Engine::decrypt_to_dev(const Ct* c) {
     if (!has_sk) throw std::runtime_error("decrypt needs a secret key");
+    // spec S10: limb 0 alone carries the message when |m| S_l < q_0 / 2.  On a descending-scale chain (q_0 next to the scale
+    // primes) that only holds at level 0: align to level 0 first (memoised on the ciphertext, freed with it)
+    if (prm.scale_drop > 0 && c->level > 0) return decrypt_to_dev(level_down(const_cast<Ct*>(c), 0));
     const size_t n = N(), ns = slots();
     const int nb = c->nb;
     const size_t ps = (size_t)(c->level + 1) * n, cb = (size_t)c->npoly * ps;    // polynomial / batch strides of c

@@ -76,6 +76,8 @@ struct Params {
     std::vector<u64> q, p;                          // q_0..q_L ; p_0..p_{K-1}
     int scale_bits = 50;
     int top_levels = 0, top_bits = 0;               // S[L] = 2^top_bits when top_levels > 0 (see default_params)
+    double top_scale = 0;                           // S[L] as default_params chose it (0: 2^top_bits or 2^scale_bits)
+    int scale_drop = 0;                             // bits S_0 sits below 2^scale_bits (descending-scale chain, q_0 < 2^(scale_bits+10))
     int alpha = 1;                                  // q-limbs per key-switch digit
     int hamming = 192;
     int fresh_level = 0;                            // level of fresh encryptions (<= L)

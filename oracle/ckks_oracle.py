@@ -300,7 +300,10 @@ class OracleCKKS:
         return Ct(np.stack([c0, c1]), level, scale)
 
     def decrypt(self, ct: Ct) -> np.ndarray:
-        """Limb 0 only: |m*scale + e| < q0/2 at every level (spec S10)."""
+        """Limb 0 only: |m*scale + e| < q0/2 at every level (spec S10); a descending-scale chain (q_0 next to the scale
+        primes) aligns to level 0 first, where the scale is 2^10 below q_0."""
+        if getattr(self.P, "scale_drop", 0) > 0 and ct.level > 0:
+            ct = self.level_down(ct, 0)
         idx = [0]
         t = ct.c[0][:1]
         spow = self.sk_ntt[:1]

@@ -78,6 +78,7 @@ class CKKSParams:
     scales: List[float] = field(default_factory=list)   # canonical scale per level, S[L] = 2^scale_bits
     fresh_level: int = -1         # level of fresh encryptions (<= L)
     boot: dict = field(default_factory=dict)             # bootstrapping plan (see bootstrap.py)
+    scale_drop: int = 0           # bits S_0 sits below 2^scale_bits (descending-scale chain; decrypt aligns to level 0)
 
     @property
     def n(self) -> int:
@@ -104,6 +105,9 @@ class CKKSParams:
         return sum(math.log2(x) for x in self.q + self.p)
 
 
+RATIO_BITS = 10      # q_0 / S_0 (ModRaise message ratio, head-room of the modulus-256 XOR outputs at level 0)
+
+
 def make_params(logn: int = 16, levels: int = 20, scale_bits: int = 50, q0_bits: int = 60, p_bits: int = 50,
                 alpha: int = 0, dnum: int = 3, hamming_weight: int = 192, fresh_level: int = -1,
                 top_levels: int = 0, top_bits: int = 58) -> CKKSParams:
@@ -117,14 +121,21 @@ def make_params(logn: int = 16, levels: int = 20, scale_bits: int = 50, q0_bits:
     # special primes = the largest primes below 2^p_bits; reserve 16 so `used` protects them, cut to K below
     reserve = _primes_below(1 << p_bits, step, 16, used)
     q0 = _primes_below(1 << q0_bits, step, 1, used)[0]
-    delta = float(1 << scale_bits)
     hi = float(1 << top_bits)
     cap = math.pow(2.0, 60.5)
+    # a q_0 below 2^(scale_bits + 10) keeps the message ratio q_0 / S_0 = 2^10 by letting the scale descend:
+    # S_l = 2^(scale_bits - drop 2^-l) (engine.cu `desired_scale`; drop = 0 is the uniform chain)
+    drop = max(0, scale_bits + RATIO_BITS - q0_bits)
+
+    def desired(l):
+        return math.pow(2.0, scale_bits - drop * math.ldexp(1.0, -l)) if drop > 0 else math.ldexp(1.0, scale_bits)
+
     scales = [0.0] * nq
-    scales[levels] = hi if top_levels > 0 else delta
+    scales[levels] = hi if top_levels > 0 else desired(levels)
     q = [0] * nq
     q[0] = q0
     for l in range(levels, 0, -1):
+        delta = desired(l - 1)
         want = hi if (top_levels > 0 and l - 1 > levels - top_levels) else delta       # desired S_{l-1}
         nxt = max(want, scales[l] * scales[l] / cap)
         target = scales[l] * scales[l] / nxt
@@ -135,6 +146,7 @@ def make_params(logn: int = 16, levels: int = 20, scale_bits: int = 50, q0_bits:
     K = -(-(digit_bits + 1) // (p_bits - 1))
     p = reserve[:K]
     return CKKSParams(logn=logn, q=q, p=p, scale_bits=scale_bits, alpha=alpha, hamming_weight=hamming_weight,
-                      scales=scales, fresh_level=levels if fresh_level < 0 else min(fresh_level, levels))
+                      scales=scales, fresh_level=levels if fresh_level < 0 else min(fresh_level, levels),
+                      scale_drop=drop)
 
 

@@ -27,15 +27,21 @@ CASES = [
     # conversion: k_base_convert_fp<NS, 1> and the 128-bit multiply-accumulate branch)
     pytest.param(("emu", 12, 6, 64, -1, 5, 61), id="emu-n12-p61"),
     pytest.param(("cuda", 16, 21, 192, 14, 5, 61), id="cuda-n16-bench-p61", marks=pytest.mark.gpu),
+    # the descending-scale chain: q_0 next to 2^50 as well (S_0 = 2^40, S_l -> 2^50 upwards), every limb on the FP64 pipe,
+    # no wide source / integer target anywhere; decryption aligns to level 0 first (spec S10)
+    pytest.param(("emu", 12, 6, 64, -1, 5, None, 50), id="emu-n12-q50"),
+    pytest.param(("cuda", 16, 21, 192, 14, 5, None, 50), id="cuda-n16-bench-q50", marks=pytest.mark.gpu),
 ]
 
 
 class Pair:
-    def __init__(self, which, logn, levels, hw=64, fresh=-1, seed=5, p_bits=None):
+    def __init__(self, which, logn, levels, hw=64, fresh=-1, seed=5, p_bits=None, q0_bits=None):
         mod = backend.use_emulation() if which == "emu" else backend.use_cuda()
         kw = dict(fresh_level=fresh) if fresh >= 0 else {}
         if p_bits is not None:
             kw["p_bits"] = p_bits
+        if q0_bits is not None:
+            kw["q0_bits"] = q0_bits
         self.eng = mod.Engine(logn=logn, levels=levels, dnum=3, hamming_weight=hw, seed=seed, **kw)
         self.params = make_params(logn=logn, levels=levels, dnum=3, hamming_weight=hw, **kw)
         self.orc = OracleCKKS(self.params, seed=seed)
