@@ -1006,8 +1006,13 @@ Ct* Engine::encrypt_coeffs(const i64* coef, int level, int nb) {
 double* Engine::decrypt_to_dev(const Ct* c) {
     if (!has_sk) throw std::runtime_error("decrypt needs a secret key");
     // spec S10: limb 0 alone carries the message when |m| S_l < q_0 / 2.  On a descending-scale chain (q_0 next to the scale
-    // primes) that only holds at level 0: align to level 0 first (memoised on the ciphertext, freed with it)
-    if (prm.scale_drop > 0 && c->level > 0) return decrypt_to_dev(level_down(const_cast<Ct*>(c), 0));
+    // primes) that only holds at level 0: align to level 0 first
+    if (prm.scale_drop > 0 && c->level > 0) {
+        Ct* low = lowered_copy(c, 0);              // not memoised on c: a graph's output handle is rewritten by the next replay
+        double* zz = decrypt_to_dev(low);
+        free_ct(low);
+        return zz;
+    }
     const size_t n = N(), ns = slots();
     const int nb = c->nb;
     const size_t ps = (size_t)(c->level + 1) * n, cb = (size_t)c->npoly * ps;    // polynomial / batch strides of c
@@ -1494,6 +1499,13 @@ Ct* Engine::level_down(Ct* c, int target) {
                 dev::stream_wait(st, streams[kv.second->lane]);
             return kv.second;
         }
+    Ct* r = lowered_copy(c, target);
+    c->lowered.push_back(std::make_pair(target, r));
+    return r;
+}
+// the alignment itself (spec S6), not memoised: the caller owns the result
+Ct* Engine::lowered_copy(const Ct* c, int target) {
+    if (target >= c->level || target < 0) throw std::runtime_error("level_down: bad target");
     const size_t n = N();
     const int t1 = target + 1;
     std::vector<int> idx = mods_q(t1);
@@ -1509,7 +1521,6 @@ Ct* Engine::level_down(Ct* c, int target) {
     Ct* r = new_ct(c->npoly, target, c->nb);
     rescale_into(r->d, tmp, c->npoly, t1, c->nb);
     release(tmp);
-    c->lowered.push_back(std::make_pair(target, r));
     return r;
 }
 

@@ -230,6 +230,7 @@ class Engine {
     Ct* relinearize(const Ct* t);                // 3 -> 2 polynomials, same level
     Ct* rescale(const Ct* c);
     Ct* level_down(Ct* c, int target);           // memoised on c
+    Ct* lowered_copy(const Ct* c, int target);          // the same alignment, not memoised (caller owns it)
     Ct* mul_const(const Ct* a, double re, double im);   // consumes one level
     Ct* mul_plain(const Ct* a, const Pt* p);            // consumes one level; p at a.level
     Ct* mul_i(const Ct* a, int sign);                   // exact multiply by +-i, no level

@@ -37,9 +37,11 @@ __all__ = ["Engine", "CapturedCall", "Ciphertext", "Plaintext", "SecretKey", "Pu
 SUPPORTS_LAZY = True       # Engine(lazy=...) exists (the host mirror asks for lazy=False: it fuses by itself)
 
 # parameter sets (DESIGN.md "Parameters"): N = 2^16, q0 ~ 2^60, scale primes ~ 2^50, special primes just below 2^50 (every
-# limb but q_0 then runs on the FP64 pipe: NTT butterflies and basis conversion; p_bits=61 gives the round-1 chain with 7
-# special primes of 61 bits on the integer pipe)
-DEFAULTS = dict(logn=16, levels=21, scale_bits=50, q0_bits=60, p_bits=50, dnum=3, hamming_weight=192,
+# limb then runs on the FP64 pipe: NTT butterflies, basis conversion, inner products; p_bits=61 gives the round-1 chain with 7
+# special primes of 61 bits on the integer pipe).  q0_bits=50: the descending-scale chain -- q_0 next to the scale primes too,
+# S_0 = 2^40 rising to 2^50 with the deviation halving per level, message ratio q_0 / S_0 = 2^10 as before; q0_bits=60 is the
+# uniform chain (scale 2^50 everywhere, q_0 on the 64-bit integer pipe)
+DEFAULTS = dict(logn=16, levels=21, scale_bits=50, q0_bits=50, p_bits=50, dnum=3, hamming_weight=192,
                 top_levels=0, top_bits=58)
 TOP_LEVELS_BOOT = 0        # optional larger scale on the CoeffToSlot levels (top_levels=3 buys only 1.5x precision)
 FRESH_LEVEL_BOOT = 14      # fresh encryptions of the bootstrapping set: SubBytes needs 13 levels

@@ -40,6 +40,9 @@ for p in (str(ROOT), str(ROOT / "aes-implementation-fhe_b200")):
 import numpy as np
 
 LOGN, LEVELS, FRESH, DNUM, HW = 16, 21, 14, 3, 192
+# q_0: 60 = the uniform chain (scale 2^50 at every level, q_0 on the 64-bit integer pipe); 50 = the descending-scale chain
+# (q_0 next to the scale primes, S_0 = 2^40 rising to 2^50: every limb on the FP64 pipe).  DESIGN.md "Parameters".
+Q0_BITS = int(os.environ.get("BENCH_Q0_BITS", "50"))
 ROUNDS_PER_BLOCK = 10
 METRIC = "aes128_fhe_blocks_per_s"
 UNIT = "blocks/s (full AES-128 encryptions of 16-byte blocks, 2048 blocks per ciphertext pair)"
@@ -146,7 +149,7 @@ class CpuArm:
         self.cores = threads or os.cpu_count()
         self.ctx = aes_fhe.EngineContext(1, mode="cpu", thread_count=self.cores, backend=be, fused=False, logn=LOGN,
                                          levels=LEVELS, fresh_level=FRESH, dnum=DNUM, hamming_weight=HW, seed=1,
-                                         use_bootstrap=False)
+                                         q0_bits=Q0_BITS, use_bootstrap=False)
         co = aes_fhe.load_all_coeffs()
         self.x4 = aes_fhe.XOR4LUT(self.ctx, co["xor4"])
         self.enc = aes_fhe.StateEncoder(self.ctx)
@@ -208,7 +211,7 @@ def run_reference(args) -> None:
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": s_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "logn": LOGN, "levels": LEVELS, "fresh_level": FRESH, "dnum": DNUM},
+            "config": {"workload": WORKLOAD, "logn": LOGN, "levels": LEVELS, "fresh_level": FRESH, "dnum": DNUM, "q0_bits": Q0_BITS},
             "note": "the reference backend (closed desilofhe wheel) cannot run here; this is the oracle port of the same "
                     "CKKS arithmetic executing the reference's call sequence on the host CPU",
             "scaling_to_one_encryption": {"key_switches_per_step": arm.KS_PER_STEP, "key_switches_per_encryption": REF_KS_PER_ENCRYPTION,
@@ -259,7 +262,8 @@ def run_ours(args) -> None:
     # (synthetic benchmark keys: a fixed seed, so that every rank derives the same secret key).
     t_keys = time.perf_counter()
     ctx = aes_fhe.EngineContext(1, mode="gpu", device_id=local, thread_count=1, logn=LOGN, levels=LEVELS, seed=20261019,
-                                fresh_level=FRESH, dnum=DNUM, hamming_weight=HW, keys_external=(world > 1 and rank != 0))
+                                fresh_level=FRESH, dnum=DNUM, hamming_weight=HW, q0_bits=Q0_BITS,
+                                keys_external=(world > 1 and rank != 0))
     eng = ctx.engine
     key_bytes = 0
     if dist is not None:
@@ -512,7 +516,7 @@ def run_ours(args) -> None:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": s_step * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "logn": LOGN, "levels": LEVELS, "fresh_level": FRESH, "dnum": DNUM,
+                "config": {"workload": WORKLOAD, "logn": LOGN, "levels": LEVELS, "fresh_level": FRESH, "dnum": DNUM, "q0_bits": Q0_BITS,
                            "pairs_per_gpu": npairs, "blocks_per_step_per_gpu": npairs * stride, "cuda_graphs": graphs,
                            "capture_s": round(t_capture, 2), "evk_broadcast_bytes": key_bytes, "setup_s": round(t_keys, 2),
                            "l2": "working set (evaluation keys 87 MiB each, hundreds of live ciphertexts) exceeds the 126 MB L2; "

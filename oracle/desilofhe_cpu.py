@@ -63,14 +63,15 @@ class Engine:
     def __init__(self, *, mode: str = "cpu", use_bootstrap: bool = False, use_multiparty: bool = False,
                  thread_count: Optional[int] = None, device_id: int = 0, max_level: Optional[int] = None,
                  seed: int = 1, logn: int = 16, levels: int = 21, dnum: int = 3, hamming_weight: int = 192,
-                 fresh_level: int = -1, **_ignored):
+                 fresh_level: int = -1, q0_bits: int = 50, **_ignored):
         if thread_count:
             os.environ["OMP_NUM_THREADS"] = str(int(thread_count))
         if max_level is not None:
             levels = int(max_level)
         if fresh_level < 0:
             fresh_level = 14 if (use_bootstrap and levels > 14) else levels
-        self.prm = make_params(logn=logn, levels=levels, dnum=dnum, hamming_weight=hamming_weight, fresh_level=fresh_level)
+        self.prm = make_params(logn=logn, levels=levels, dnum=dnum, hamming_weight=hamming_weight, fresh_level=fresh_level,
+                               q0_bits=q0_bits)
         self.orc = OracleCKKS(self.prm, seed=seed)
         self.slot_count = self.orc.n
         self.use_bootstrap = use_bootstrap

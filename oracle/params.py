@@ -108,7 +108,7 @@ class CKKSParams:
 RATIO_BITS = 10      # q_0 / S_0 (ModRaise message ratio, head-room of the modulus-256 XOR outputs at level 0)
 
 
-def make_params(logn: int = 16, levels: int = 20, scale_bits: int = 50, q0_bits: int = 60, p_bits: int = 50,
+def make_params(logn: int = 16, levels: int = 20, scale_bits: int = 50, q0_bits: int = 50, p_bits: int = 50,
                 alpha: int = 0, dnum: int = 3, hamming_weight: int = 192, fresh_level: int = -1,
                 top_levels: int = 0, top_bits: int = 58) -> CKKSParams:
     """Deterministic parameter construction.  `levels` = L (number of scale primes).  With top_levels > 0 the highest
