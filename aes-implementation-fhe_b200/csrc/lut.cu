@@ -14,6 +14,9 @@
 #include "engine.cuh"
 
 #define LUT_MAX_BASIS 16
+#ifndef LUT_FP
+#define LUT_FP 1              // rows of FP64 moduli (below CKKS_FP_LIMIT) of the LUT / BSGS multiply-accumulates on the FP64 pipe
+#endif
 #define LINCOMB_MAX 128
 
 struct Lut2Args {
@@ -60,6 +63,36 @@ k_diag_mac_rows(KShape S, const GRID_CONST DiagRowsArgs G, const GRID_CONST Limb
     const ModConst m = S.mc[L.idx[row]];
     const size_t N = (size_t)1 << S.logn, P = (size_t)G.rows << S.logn;
     const unsigned cb = blockIdx.x / (unsigned)G.nz, z = blockIdx.x - cb * (unsigned)G.nz;
+    if (LUT_FP && m.q < CKKS_FP_LIMIT) {
+        // rows of FP64 moduli (every row of the default chain): exact modular products on the FP64 pipe, |r| <= 0.91 q each,
+        // folded every 4 babies so that a sum stays below 2^53 (the 128-bit integer multiply-accumulate below is 3 x slower)
+        const double qd = ull2d_rn(m.q), qinv = fdiv_rn(1.0, qd);
+        FOR_THREADS {
+            const size_t i = (size_t)row * N + cb * 256 + threadIdx.x;
+            double acc[NR];
+#pragma unroll
+            for (int r = 0; r < NR; r++) acc[r] = 0.0;
+            for (int t = 0; t < G.nx; t++) {
+                const double xv = ull2d_rn(ldg(G.x[t] + z * P + i));
+                u64 pv[NR];
+#pragma unroll
+                for (int r = 0; r < NR; r++) {
+                    const u64* pp = G.p[r][t];
+                    pv[r] = pp ? ldg(pp + i) : 0;
+                }
+#pragma unroll
+                for (int r = 0; r < NR; r++) acc[r] = fadd_rn(acc[r], modmul_fp(xv, ull2d_rn(pv[r]), qd, qinv));
+                if ((t & 3) == 3 && t + 1 < G.nx) {
+#pragma unroll
+                    for (int r = 0; r < NR; r++) acc[r] = fold_fp(acc[r], qd, qinv);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NR; r++)
+                if (r < G.nrows) G.out[r][z * P + i] = canon_fp(acc[r], qd, qinv);
+        }
+        return;
+    }
     FOR_THREADS {
         const size_t i = (size_t)row * N + cb * 256 + threadIdx.x;
         u64 hi[NR], lo[NR];
@@ -113,6 +146,43 @@ k_lut2(KShape S, u64* __restrict__ d, const GRID_CONST Lut2Args G, const GRID_CO
     const u64* cst = G.consts + ((size_t)(row * 2 + half) * G.nterms) * 2;
     const size_t zb = (size_t)blockIdx.z * 2 * P;       // offset of this batch item inside a batched basis element
     d += (size_t)blockIdx.z * 3 * P;
+    if (LUT_FP && m.q < CKKS_FP_LIMIT) {
+        // FP64 rows: the inner sums u = sum_q c_pq B_q and the tensor products A_p (x) u as exact FP64 modular products
+        // (|r| <= 0.91 q), sums folded every 4 terms / 4 groups; u is folded to |u| <= q/2 before it multiplies
+        const double qd = ull2d_rn(m.q), qinv = fdiv_rn(1.0, qd);
+        FOR_THREADS {
+            const size_t i = (size_t)row * N + blockIdx.x * 256 + threadIdx.x;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            int t = 0, groups = 0;
+            while (t < G.nterms) {
+                const int p = ldg(G.tp + t);
+                double u0 = 0.0, u1 = 0.0;
+                int cnt = 0;
+                for (; t < G.nterms && ldg(G.tp + t) == p; t++) {
+                    const int q = ldg(G.tq + t);
+                    const u64* bq = G.b[q] + (((G.bbm >> q) & 1u) ? zb : 0);
+                    const double c = ull2d_rn(ldg(cst + 2 * t));
+                    u0 = fadd_rn(u0, modmul_fp(ull2d_rn(ldg(bq + i)), c, qd, qinv));
+                    u1 = fadd_rn(u1, modmul_fp(ull2d_rn(ldg(bq + i + P)), c, qd, qinv));
+                    if ((++cnt & 3) == 0) { u0 = fold_fp(u0, qd, qinv); u1 = fold_fp(u1, qd, qinv); }
+                }
+                u0 = fold_fp(u0, qd, qinv);
+                u1 = fold_fp(u1, qd, qinv);
+                const u64* ap = G.a[p] + (((G.abm >> p) & 1u) ? zb : 0);
+                const double a0 = ull2d_rn(ldg(ap + i)), a1 = ull2d_rn(ldg(ap + i + P));
+                s0 = fadd_rn(s0, modmul_fp(a0, u0, qd, qinv));
+                s1 = fadd_rn(s1, fadd_rn(modmul_fp(a0, u1, qd, qinv), modmul_fp(a1, u0, qd, qinv)));
+                s2 = fadd_rn(s2, modmul_fp(a1, u1, qd, qinv));
+                if ((++groups & 1) == 0) {             // s1 takes two products per group: fold every 2 groups
+                    s0 = fold_fp(s0, qd, qinv); s1 = fold_fp(s1, qd, qinv); s2 = fold_fp(s2, qd, qinv);
+                }
+            }
+            d[i] = canon_fp(s0, qd, qinv);
+            d[i + P] = canon_fp(s1, qd, qinv);
+            d[i + 2 * P] = canon_fp(s2, qd, qinv);
+        }
+        return;
+    }
     FOR_THREADS {
         const size_t i = (size_t)row * N + blockIdx.x * 256 + threadIdx.x;
         u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0, h2 = 0, l2 = 0;
@@ -159,6 +229,20 @@ k_lincomb(KShape S, u64* __restrict__ out, const GRID_CONST LinCombArgs G, const
     const u64* cst = G.consts + ((size_t)(row * 2 + half) * G.nterms) * 2;
     const unsigned bi = blockIdx.z / (unsigned)G.npoly, kp = blockIdx.z - bi * (unsigned)G.npoly;
     const size_t zb = (size_t)bi * G.npoly * P;          // offset of this batch item inside a batched operand
+    if (LUT_FP && m.q < CKKS_FP_LIMIT) {
+        const double qd = ull2d_rn(m.q), qinv = fdiv_rn(1.0, qd);
+        FOR_THREADS {
+            const size_t i = kp * P + (size_t)row * N + blockIdx.x * 256 + threadIdx.x;
+            double acc = 0.0;
+            for (int t = 0; t < G.nterms; t++) {
+                const u64* xt = G.x[t] + (((G.xbm[t >> 6] >> (t & 63)) & 1ull) ? zb : 0);
+                acc = fadd_rn(acc, modmul_fp(ull2d_rn(ldg(xt + i)), ull2d_rn(ldg(cst + 2 * t)), qd, qinv));
+                if ((t & 3) == 3) acc = fold_fp(acc, qd, qinv);
+            }
+            out[zb + i] = canon_fp(acc, qd, qinv);
+        }
+        return;
+    }
     FOR_THREADS {
         const size_t i = kp * P + (size_t)row * N + blockIdx.x * 256 + threadIdx.x;
         u64 acc = 0;
