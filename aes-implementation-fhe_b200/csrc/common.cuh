@@ -98,9 +98,10 @@ __device__ __forceinline__ double fold_fp(double x, double q, double qinv) {
     return ffma_rn(-frint(fmul_rn(x, qinv)), q, x);
 }
 // exact canonical residue in [0,q) as an integer
+// The fold leaves |x| <= (1/2 + 2^-49) q (the quotient estimate x * qinv is within 2^-49 of x / q for |x| < 2^53, so it can
+// only round to the other neighbour next to a tie): ONE correction, +q for a negative value, lands in [0, q), and it is
+// done on the integer pipe after the conversion (the FP64 pipe, which bounds these kernels, keeps its three instructions).
 __device__ __forceinline__ u64 canon_fp(double x, double q, double qinv) {
-    x = fold_fp(x, q, qinv);
-    x = x < 0.0 ? fadd_rn(x, q) : x;
-    x = x >= q ? fsub_rn(x, q) : x;
-    return (u64)d2ll_rn(x);
+    const i64 r = d2ll_rn(fold_fp(x, q, qinv));
+    return (u64)(r < 0 ? r + (i64)d2ll_rn(q) : r);
 }
