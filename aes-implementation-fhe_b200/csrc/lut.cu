@@ -52,12 +52,14 @@ struct DiagRowsArgs {
 
 namespace {
 
+__device__ __forceinline__ double bits2dbl(u64 x) { union { double d; u64 u; } c; c.u = x; return c.d; }
+
 // All inner sums of one BSGS matrix in one pass: out_r = sum_t x_t (.) p[r][t] for every giant row r.  A baby-step word is
 // loaded ONCE and multiplied into every row that uses it (the one-row kernel re-reads all babies per row: 8 x the traffic of
 // a radix-32 matrix); the nz slices of a coefficient block sit next to each other in the launch order, so the diagonals
 // (shared by the batch) come from L2 for all but the first of them.
 template <int NR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_diag_mac_rows(KShape S, const GRID_CONST DiagRowsArgs G, const GRID_CONST LimbList L) {
     const int row = blockIdx.y;
     const ModConst m = S.mc[L.idx[row]];
@@ -72,6 +74,7 @@ k_diag_mac_rows(KShape S, const GRID_CONST DiagRowsArgs G, const GRID_CONST Limb
             double acc[NR];
 #pragma unroll
             for (int r = 0; r < NR; r++) acc[r] = 0.0;
+#pragma unroll 2
             for (int t = 0; t < G.nx; t++) {
                 const double xv = ull2d_rn(ldg(G.x[t] + z * P + i));
                 u64 pv[NR];
@@ -161,7 +164,7 @@ k_lut2(KShape S, u64* __restrict__ d, const GRID_CONST Lut2Args G, const GRID_CO
                 for (; t < G.nterms && ldg(G.tp + t) == p; t++) {
                     const int q = ldg(G.tq + t);
                     const u64* bq = G.b[q] + (((G.bbm >> q) & 1u) ? zb : 0);
-                    const double c = ull2d_rn(ldg(cst + 2 * t));
+                    const double c = bits2dbl(ldg(cst + 2 * t + 1));
                     u0 = fadd_rn(u0, modmul_fp(ull2d_rn(ldg(bq + i)), c, qd, qinv));
                     u1 = fadd_rn(u1, modmul_fp(ull2d_rn(ldg(bq + i + P)), c, qd, qinv));
                     if ((++cnt & 3) == 0) { u0 = fold_fp(u0, qd, qinv); u1 = fold_fp(u1, qd, qinv); }
@@ -236,7 +239,7 @@ k_lincomb(KShape S, u64* __restrict__ out, const GRID_CONST LinCombArgs G, const
             double acc = 0.0;
             for (int t = 0; t < G.nterms; t++) {
                 const u64* xt = G.x[t] + (((G.xbm[t >> 6] >> (t & 63)) & 1ull) ? zb : 0);
-                acc = fadd_rn(acc, modmul_fp(ull2d_rn(ldg(xt + i)), ull2d_rn(ldg(cst + 2 * t)), qd, qinv));
+                acc = fadd_rn(acc, modmul_fp(ull2d_rn(ldg(xt + i)), bits2dbl(ldg(cst + 2 * t + 1)), qd, qinv));
                 if ((t & 3) == 3) acc = fold_fp(acc, qd, qinv);
             }
             out[zb + i] = canon_fp(acc, qd, qinv);
@@ -279,6 +282,13 @@ const u64* Engine::const_table(const double* coef_re_im, int n, int scale_level,
             u64* p1 = &host[(((size_t)r * 2 + 1) * n + t) * 2];
             p0[0] = cp.v[r]; p0[1] = cp.vs[r];
             p1[0] = cm.v[r]; p1[1] = cm.vs[r];
+            if (LUT_FP && mod[idx[r]] < CKKS_FP_LIMIT) {
+                // FP64 rows read the constant as a double (no conversion per term in the kernels): the companion slot
+                // holds its bits instead of the Shoup word the integer rows use
+                const double d0 = (double)cp.v[r], d1 = (double)cm.v[r];
+                memcpy(&p0[1], &d0, 8);
+                memcpy(&p1[1], &d1, 8);
+            }
         }
     }
     u64* d = alloc(host.size());
