@@ -2,6 +2,7 @@
 # ncu --set full of the FP64 multiply-accumulate kernels
 set -x
 O=gpurun_out/r2final; mkdir -p $O
+python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "rc=$?" >> $O/smoke.log
 python -m pytest tests -m gpu -q --durations=8 > $O/gpu_tests.log 2>&1; echo "rc=$?" >> $O/gpu_tests.log
 python bench.py > $O/bench.json 2> $O/bench.err; echo "rc=$?" >> $O/bench.err
 python bench.py --impl reference > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
