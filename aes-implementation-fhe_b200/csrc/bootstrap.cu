@@ -281,16 +281,20 @@ static Ct* apply_linear(Engine& E, Arena& A, Ct* a, const LinearPlan& P) {
                 if (!S.rbuf) S.rbuf = E.alloc((size_t)nb * 2 * ps);
                 E.automorph(S.rbuf, inner, P.level + 1, 2 * nb, g);             // (sigma(c0), sigma(c1))
                 Decomp D = E.decompose(S.rbuf + ps, P.level, nullptr, nb, 2 * ps, 0);
-                if (!S.accqp) {
-                    S.accqp = E.alloc((size_t)nb * 2 * rows * n);
-                    E.ks_inner(D, key, nullptr, S.accqp, nullptr, false);
-                } else E.ks_inner(D, key, nullptr, S.accqp, nullptr, true);
+                // sigma_g(c0) joins the Q_l u P accumulator as P * sigma_g(c0) inside the inner product (exactly sigma_g(c0)
+                // after the one division by P); CKKS_KS_ADD_FUSE=0: a separate addition into the Q_l sum
+                const u64* c0 = E.fuse_ks_add ? S.rbuf : nullptr;
+                const bool first = !S.accqp;
+                if (first) S.accqp = E.alloc((size_t)nb * 2 * rows * n);
+                E.ks_inner(D, key, nullptr, S.accqp, c0, !first, false, 2 * ps, c0 ? 1 : 0);
                 E.release(D.ext);
-                if (!S.sum) {
-                    S.sum = E.alloc((size_t)nb * 2 * ps);
-                    dev::zero(S.sum, (size_t)nb * 2 * ps * sizeof(u64), E.st);
+                if (!c0) {
+                    if (!S.sum) {
+                        S.sum = E.alloc((size_t)nb * 2 * ps);
+                        dev::zero(S.sum, (size_t)nb * 2 * ps * sizeof(u64), E.st);
+                    }
+                    launch_add(E.ks, S.sum, S.sum, S.rbuf, ll, 1, U0, E.st);
                 }
-                launch_add(E.ks, S.sum, S.sum, S.rbuf, ll, 1, U0, E.st);
             }
             if (inner && !pre) E.release(inner);
         }

@@ -189,6 +189,7 @@ Engine::Engine(const Params& P) : prm(P) {
     arenas[0] = &main_arena;
     if (const char* v = getenv("CKKS_NTT_FUSE")) fuse_ntt = atoi(v) != 0;
     if (const char* v = getenv("CKKS_TENSOR_FUSE")) fuse_tensor = atoi(v) != 0;
+    if (const char* v = getenv("CKKS_KS_ADD_FUSE")) fuse_ks_add = atoi(v) != 0;
     if (const char* v = getenv("CKKS_BC_MMA")) bc_mode = atoi(v) != 0 ? BC_MMA : bc_mode;
     if (const char* v = getenv("CKKS_BC_FP")) bc_mode = atoi(v) != 0 ? BC_FP : (bc_mode == BC_FP ? BC_INT : bc_mode);
     if (const char* v = getenv("CKKS_BC_FP_INT_EVERY")) bc_fp_int_every = atoi(v);
@@ -1332,7 +1333,7 @@ Decomp Engine::decompose(const u64* d, int level, const u64* times, int nb, size
 // <digits, evk> (+ P * addend) into acc = [nb][2][level+1+K][N] over Q_level u P; with accumulate the result is added to
 // what acc already holds (several key switches sharing ONE ModDown)
 void Engine::ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64* acc, const u64* addend, bool accumulate,
-                      bool tensor, size_t addend_bs) {
+                      bool tensor, size_t addend_bs, int addend_mode) {
     const int level = D.level, nq = level + 1, rows = nq + K();
     std::vector<int> qp = mods_qp(level);
     LimbList ll = limb_list(qp);
@@ -1343,6 +1344,7 @@ void Engine::ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64*
     kb.ext = (size_t)D.beta * rows * N();
     kb.own = D.own_bs;
     kb.addend = addend_bs;
+    kb.addend_mode = addend_mode;
     launch_ks_inner(ks, acc, D.ext, D.own, evk->d, perm, ll, er, D.beta, nmod(), nq, prm.alpha, addend, sl_pmodq,
                     accumulate ? 1 : 0, st, tensor, kb);
     n_keyswitch += D.nb;
@@ -1392,17 +1394,20 @@ void Engine::ks_moddown(u64* acc, int level, int drop, u64* out, int nb) {
 // inner product with the key, then ONE division by P * q_{level-drop+1..level}: out is [nb][2][level+1-drop][N].
 // addend ([2][level+1][N] per item, e.g. the (d0, d1) of a tensor product) is folded in as P * addend before the division.
 void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out, const u64* addend, int drop,
-                      bool tensor, size_t addend_bs) {
+                      bool tensor, size_t addend_bs, int addend_mode) {
     const int rows = D.level + 1 + K();
     u64* acc = alloc((size_t)D.nb * 2 * rows * N());
-    ks_inner(D, evk, perm, acc, addend, false, tensor, addend_bs);
+    ks_inner(D, evk, perm, acc, addend, false, tensor, addend_bs, addend_mode);
     ks_moddown(acc, D.level, drop, out, D.nb);
     release(acc);
 }
 
-void Engine::key_switch(const u64* d, int level, const EvalKey* evk, u64* out, int nb, size_t d_bs) {
+void Engine::key_switch(const u64* d, int level, const EvalKey* evk, u64* out, int nb, size_t d_bs, const u64* c0_addend,
+                        size_t c0_bs) {
     Decomp D = decompose(d, level, nullptr, nb, d_bs, 0);
-    ks_apply(D, evk, nullptr, out);
+    // P * c0_addend enters the Q rows of the inner product: exactly c0_addend after the division by P (P x vanishes on the
+    // special limbs and ModDown((P x + w)) = x + ModDown(w)), bit-identical to adding it afterwards
+    ks_apply(D, evk, nullptr, out, c0_addend, 0, false, c0_bs, c0_addend ? 1 : 0);
     release(D.ext);
 }
 
@@ -1702,8 +1707,11 @@ Ct* Engine::apply_galois(const Ct* a, u64 g) {
     u64* t = alloc((size_t)nb * 2 * ps);
     automorph(t, a->d, l + 1, 2 * nb, g);
     Ct* r = new_ct(2, l, nb);
-    key_switch(t + ps, l, key, r->d, nb, 2 * ps);
-    launch_add(ks, r->d, r->d, t, limb_list(mods_q(l)), 1, psb(0, 0, 0, nb, 2 * ps, 2 * ps, 2 * ps), st);
+    if (fuse_ks_add) key_switch(t + ps, l, key, r->d, nb, 2 * ps, t, 2 * ps);       // sigma(c0) joins inside the inner product
+    else {
+        key_switch(t + ps, l, key, r->d, nb, 2 * ps);
+        launch_add(ks, r->d, r->d, t, limb_list(mods_q(l)), 1, psb(0, 0, 0, nb, 2 * ps, 2 * ps, 2 * ps), st);
+    }
     release(t);
     return r;
 }
@@ -1739,11 +1747,16 @@ std::vector<Ct*> Engine::rotate_hoisted(const Ct* a, const std::vector<long>& st
             const size_t i = work[w];
             const u64 g = galois_for_rotation(steps[i]);
             Ct* r = new_ct(2, l, nb);
-            ks_apply(D, galois_key(g), galois_perm(g), r->d);
-            u64* t = alloc((size_t)nb * ps);
-            automorph(t, a->d, l + 1, 1, g, psb(0, 0, 0, nb, ps, 2 * ps, 0));
-            launch_add(ks, r->d, r->d, t, ll, 1, psb(0, 0, 0, nb, 2 * ps, 2 * ps, ps), st);
-            release(t);
+            if (fuse_ks_add) {
+                // c0 is gathered through the same permutation as the digits and joins inside the inner product
+                ks_apply(D, galois_key(g), galois_perm(g), r->d, a->d, 0, false, 2 * ps, 2);
+            } else {
+                ks_apply(D, galois_key(g), galois_perm(g), r->d);
+                u64* t = alloc((size_t)nb * ps);
+                automorph(t, a->d, l + 1, 1, g, psb(0, 0, 0, nb, ps, 2 * ps, 0));
+                launch_add(ks, r->d, r->d, t, ll, 1, psb(0, 0, 0, nb, 2 * ps, 2 * ps, ps), st);
+                release(t);
+            }
             out[i] = r;
         }
     } catch (...) {

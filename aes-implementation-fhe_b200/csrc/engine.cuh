@@ -276,10 +276,13 @@ class Engine {
     // ext, acc and out are [nb][...] contiguous
     Decomp decompose(const u64* d, int level, const u64* times = nullptr, int nb = 1, size_t d_bs = 0, size_t times_bs = 0);
     void ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out /* [nb][2][level+1-drop][N] */,
-                  const u64* addend = nullptr, int drop = 0, bool tensor = false, size_t addend_bs = 0);
-    void key_switch(const u64* d, int level, const EvalKey* evk, u64* out, int nb = 1, size_t d_bs = 0);
+                  const u64* addend = nullptr, int drop = 0, bool tensor = false, size_t addend_bs = 0, int addend_mode = 0);
+    // c0_addend (optional): a polynomial [level+1][N] per item (stride c0_bs) that joins output polynomial 0 (KsBatch::addend_mode 1)
+    void key_switch(const u64* d, int level, const EvalKey* evk, u64* out, int nb = 1, size_t d_bs = 0,
+                    const u64* c0_addend = nullptr, size_t c0_bs = 0);
     void ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64* acc, const u64* addend, bool accumulate,
-                  bool tensor = false, size_t addend_bs = 0);
+                  bool tensor = false, size_t addend_bs = 0, int addend_mode = 0);
+    bool fuse_ks_add = true;               // CKKS_KS_ADD_FUSE=0: sigma(c0) + ks0 as a separate permutation / addition (A/B)
     void ks_moddown(u64* acc, int level, int drop, u64* out, int nb = 1);
     void automorph(u64* out, const u64* in, int rows, int npoly, u64 g);
     void automorph(u64* out, const u64* in, int rows, int npoly, u64 g, PolyStride ps);

@@ -209,8 +209,9 @@ __global__ void k_ks_inner(KShape S, u64* __restrict__ acc, const u64* __restric
                     r1 = add_mod(r1, shoup_mul(barrett_reduce128(hi, lo, m), PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
                 }
             } else if (xadd != nullptr && row < nq) {
-                r0 = add_mod(r0, shoup_mul(xadd[(size_t)row * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
-                r1 = add_mod(r1, shoup_mul(xadd[((size_t)nq + row) * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+                r0 = add_mod(r0, shoup_mul(xadd[(size_t)row * N + (kb.addend_mode == 2 ? ks : k)], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+                if (kb.addend_mode == 0)
+                    r1 = add_mod(r1, shoup_mul(xadd[((size_t)nq + row) * N + k], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
             }
             if (accumulate) {          // several key switches summed before ONE ModDown (giant steps of a linear transform)
                 r0 = add_mod(r0, xacc[(size_t)row * N + k], m.q);
@@ -281,8 +282,8 @@ k_ks_inner_mlp(KShape S, u64* __restrict__ acc, const u64* __restrict__ ext, con
                         p2[bi] = xadd[(size_t)row * N + k];  p3[bi] = xadd[((size_t)nq + row) * N + k];
                     }
                 } else if (xadd != nullptr && qrow) {
-                    p0[bi] = xadd[(size_t)row * N + k];
-                    p1[bi] = xadd[((size_t)nq + row) * N + k];
+                    p0[bi] = xadd[(size_t)row * N + (kb.addend_mode == 2 ? ks : k)];
+                    p1[bi] = kb.addend_mode == 0 ? xadd[((size_t)nq + row) * N + k] : 0;
                 }
                 if (accumulate) {
                     c0[bi] = xacc[(size_t)row * N + k];
@@ -327,7 +328,7 @@ k_ks_inner_mlp(KShape S, u64* __restrict__ acc, const u64* __restrict__ ext, con
                     }
                 } else if (addend != nullptr && qrow) {
                     r0 = add_mod(r0, shoup_mul(p0[bi], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
-                    r1 = add_mod(r1, shoup_mul(p1[bi], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
+                    if (kb.addend_mode == 0) r1 = add_mod(r1, shoup_mul(p1[bi], PmodQ.v[row], PmodQ.vs[row], m.q), m.q);
                 }
                 if (accumulate) {
                     r0 = add_mod(r0, c0[bi], m.q);

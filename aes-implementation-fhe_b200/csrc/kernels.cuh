@@ -72,6 +72,10 @@ void launch_permute(KShape S, u64* out, const u64* a, const u32* perm, int rows,
 struct KsBatch {
     int nb = 1;
     size_t acc = 0, ext = 0, own = 0, addend = 0;
+    // non-tensor addend: 0 = both polynomials ([2][nq][N]); 1 = polynomial 0 only (the c0 of a Galois map: c0' = sigma(c0)
+    // + ks0, the addition that used to be a launch of its own); 2 = polynomial 0 only, gathered through `perm` like the
+    // digits (hoisted rotations: the un-permuted input ciphertext is the addend, no permutation launch either)
+    int addend_mode = 0;
 };
 // acc[2][rows][N] = sum_j ext[j][rows][N] * evk[j][2][evk_rows][N]; ERow maps working row -> evk row.  The key is read
 // ONCE per coefficient and applied to every batch item (its HBM traffic is amortised over the batch).
