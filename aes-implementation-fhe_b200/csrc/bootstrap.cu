@@ -342,8 +342,7 @@ static Ct* cheb_eval(Engine& E, Arena& A, Ct* x, const std::vector<double>& coef
     T[1] = x;
     auto make = [&](int k) -> Ct* {
         const int a = (k + 1) / 2, b = k / 2;                    // T_{a+b} = 2 T_a T_b - T_{a-b}
-        Ct* prod = A.keep(E.mul(T.at(a), T.at(b)));
-        Ct* two = A.keep(E.add(prod, prod));
+        Ct* two = A.keep(E.mul(T.at(a), T.at(b), 2));            // 2 T_a T_b: the factor rides on the division's scalar
         return a == b ? A.keep(E.add_const(two, -1.0, 0.0)) : A.keep(E.sub(two, T.at(a - b)));
     };
     // baby steps T_2..T_m by generation (2^(g-1) < k <= 2^g only needs earlier generations): one stream lane per product
@@ -410,8 +409,7 @@ static Ct* cheb_eval(Engine& E, Arena& A, Ct* x, const std::vector<double>& coef
 static Ct* eval_mod(Engine& E, Arena& A, Ct* x, const BootPlan& B) {
     Ct* y = cheb_eval(E, A, x, B.cheb, B.m);
     for (int i = 0; i < B.r; i++) {
-        Ct* sq = A.keep(E.mul(y, y));
-        Ct* two = A.keep(E.add(sq, sq));
+        Ct* two = A.keep(E.mul(y, y, 2));
         y = A.keep(E.add_const(two, -1.0, 0.0));
     }
     return y;

@@ -190,6 +190,8 @@ Engine::Engine(const Params& P) : prm(P) {
     if (const char* v = getenv("CKKS_NTT_FUSE")) fuse_ntt = atoi(v) != 0;
     if (const char* v = getenv("CKKS_TENSOR_FUSE")) fuse_tensor = atoi(v) != 0;
     if (const char* v = getenv("CKKS_KS_ADD_FUSE")) fuse_ks_add = atoi(v) != 0;
+    if (const char* v = getenv("CKKS_MUL_FACTOR_FUSE")) fuse_mul_factor = atoi(v) != 0;
+    if (const char* v = getenv("CKKS_ALIGN_FUSE")) fuse_align = atoi(v) != 0;
     if (const char* v = getenv("CKKS_BC_MMA")) bc_mode = atoi(v) != 0 ? BC_MMA : bc_mode;
     if (const char* v = getenv("CKKS_BC_FP")) bc_mode = atoi(v) != 0 ? BC_FP : (bc_mode == BC_FP ? BC_INT : bc_mode);
     if (const char* v = getenv("CKKS_BC_FP_INT_EVERY")) bc_fp_int_every = atoi(v);
@@ -1224,8 +1226,8 @@ const BaseConvTable& Engine::moddown_table(int level, int drop) {
     return moddown_tabs[key];
 }
 // (P * q_{level-drop+1} .. q_level)^-1 mod q_i, i <= level - drop
-const ScalarList& Engine::moddown_inv(int level, int drop) {
-    const int key = level * 4 + drop;
+const ScalarList& Engine::moddown_inv(int level, int drop, int factor) {
+    const int key = (level * 4 + drop) * 4 + factor;
     auto it = moddown_invs.find(key);
     if (it != moddown_invs.end()) return it->second;
     std::vector<int> qi = mods_q(level - drop);
@@ -1235,7 +1237,7 @@ const ScalarList& Engine::moddown_inv(int level, int drop) {
         u64 pp = 1;
         for (u64 pk_ : prm.p) pp = mulmod_h(pp, pk_ % q, q);
         for (int j = level - drop + 1; j <= level; j++) pp = mulmod_h(pp, mod[j] % q, q);
-        inv[i] = invmod_h(pp, q);
+        inv[i] = mulmod_h(invmod_h(pp, q), (u64)factor % q, q);
     }
     scalar_list(inv, qi, moddown_invs[key]);
     return moddown_invs[key];
@@ -1351,7 +1353,7 @@ void Engine::ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64*
 }
 
 // ONE division of acc by P * q_{level-drop+1..level}: out is [nb][2][level+1-drop][N] (acc is used as scratch)
-void Engine::ks_moddown(u64* acc, int level, int drop, u64* out, int nb) {
+void Engine::ks_moddown(u64* acc, int level, int drop, u64* out, int nb, int factor) {
     const size_t n = N();
     const int nq = level + 1, rows = nq + K(), nout = nq - drop;
     if (nout < 1) throw LevelError("key switch: ciphertext level should be positive for this rescale");
@@ -1380,11 +1382,11 @@ void Engine::ks_moddown(u64* acc, int level, int drop, u64* out, int nb) {
         F.pro_mod = -1;
         F.ep_a = acc; F.ep_azs = (size_t)rows * n; F.ep_abs = (size_t)2 * rows * n;
         F.ep_out = out; F.ep_ozs = (size_t)nout * n; F.ep_obs = (size_t)2 * nout * n;
-        F.s = moddown_inv(level, drop);
+        F.s = moddown_inv(level, drop, factor);
         run_ntt_fused(conv, conv, J, F, 2L * nout * nb);
     } else {
         ntt_rows(conv, qi, qi, false, 2, (size_t)nout * n, nb, (size_t)2 * nout * n);
-        launch_sub_mul_scalar(ks, out, acc, conv, limb_list(qi), moddown_inv(level, drop), 2 * nb,
+        launch_sub_mul_scalar(ks, out, acc, conv, limb_list(qi), moddown_inv(level, drop, factor), 2 * nb,
                               PolyStride{(size_t)nout * n, (size_t)rows * n, (size_t)nout * n}, st);
     }
     release(conv);
@@ -1394,11 +1396,11 @@ void Engine::ks_moddown(u64* acc, int level, int drop, u64* out, int nb) {
 // inner product with the key, then ONE division by P * q_{level-drop+1..level}: out is [nb][2][level+1-drop][N].
 // addend ([2][level+1][N] per item, e.g. the (d0, d1) of a tensor product) is folded in as P * addend before the division.
 void Engine::ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out, const u64* addend, int drop,
-                      bool tensor, size_t addend_bs, int addend_mode) {
+                      bool tensor, size_t addend_bs, int addend_mode, int factor) {
     const int rows = D.level + 1 + K();
     u64* acc = alloc((size_t)D.nb * 2 * rows * N());
     ks_inner(D, evk, perm, acc, addend, false, tensor, addend_bs, addend_mode);
-    ks_moddown(acc, D.level, drop, out, D.nb);
+    ks_moddown(acc, D.level, drop, out, D.nb, factor);
     release(acc);
 }
 
@@ -1419,22 +1421,31 @@ void Engine::need_levels(int level, int need, const char* what) const {
 }
 
 // in: [nb][npoly][level+1][N] -> out: [nb][npoly][level][N]
-void Engine::rescale_into(u64* out, const u64* in, int npoly, int level, int nb) {
+// in_ps: polynomial stride of `in` (0: level + 1 limbs, contiguous); pre_k != 0: the division of pre_k * in (level alignment)
+void Engine::rescale_into(u64* out, const u64* in, int npoly, int level, int nb, size_t in_ps, u64 pre_k) {
     const size_t n = N();
     const int nl = level + 1;
+    if (!in_ps) in_ps = (size_t)nl * n;
+    if (pre_k && !fuse_ntt) throw std::runtime_error("rescale: the scalar rides on the fused epilogue only");
     if (npoly > NTT_MAX_Z) throw std::runtime_error("rescale: too many polynomials");
     u64* last = alloc((size_t)nb * npoly * n);
     {
         NttJob J;
         memset(&J, 0, sizeof(J));
         J.n = 1; J.nz = npoly;
-        J.szs = (size_t)nl * n;
+        J.szs = in_ps;
         J.dzs = n;
         J.nb = nb;
-        J.sbs = (size_t)npoly * nl * n;
+        J.sbs = (size_t)npoly * in_ps;
         J.dbs = (size_t)npoly * n;
         for (int z = 0; z < npoly; z++) { J.srows[z][0] = (unsigned char)level; J.rows[z][0] = 0; J.mods[z][0] = (unsigned char)level; }
         run_ntt(in, last, J, true, (long)npoly * nb);
+    }
+    if (pre_k) {                                               // k * INTT(x) = INTT(k x): the dropped limb only
+        std::vector<int> top(1, level);
+        ScalarList sk;
+        scalar_list(std::vector<u64>(1, pre_k), top, sk);
+        launch_mul_scalar(ks, last, last, limb_list(top), sk, npoly * nb, PolyStride{n, n, 0}, st);
     }
     std::vector<int> lo = mods_q(level - 1);
     LimbList ll = limb_list(lo);
@@ -1454,9 +1465,10 @@ void Engine::rescale_into(u64* out, const u64* in, int npoly, int level, int nb)
             for (int i = 0; i < level; i++) { J.srows[z][i] = 0; J.rows[z][i] = (unsigned char)i; J.mods[z][i] = (unsigned char)i; }
         NttFuse F;
         F.pro_mod = level;
-        F.ep_a = in; F.ep_azs = (size_t)nl * n; F.ep_abs = (size_t)npoly * nl * n;
+        F.ep_a = in; F.ep_azs = in_ps; F.ep_abs = (size_t)npoly * in_ps;
         F.ep_out = out; F.ep_ozs = (size_t)level * n; F.ep_obs = (size_t)npoly * level * n;
         F.s = sl_qinv[level];
+        F.ep_k = pre_k;
         run_ntt_fused(last, delta, J, F, (long)npoly * level * nb);
     } else {
         // [nb][npoly] slices with uniform strides: the batch folds into the polynomial count
@@ -1516,6 +1528,13 @@ Ct* Engine::lowered_copy(const Ct* c, int target) {
     std::vector<int> idx = mods_q(t1);
     const double kf = nearbyint(scales[target] * (double)mod[t1] / scales[c->level]);
     const u64 k = (u64)kf;
+    if (fuse_ntt && fuse_align && tabs.cluster < 2 && k) {
+        // the scalar rides on the division: k on the dropped limb after its inverse transform, k a in the epilogue; the
+        // aligned copy is never written at level target + 1 (bit-identical to the two steps below)
+        Ct* r = new_ct(c->npoly, target, c->nb);
+        rescale_into(r->d, c->d, c->npoly, t1, c->nb, (size_t)(c->level + 1) * n, k);
+        return r;
+    }
     std::vector<u64> kv(idx.size(), k);
     ScalarList sc;
     scalar_list(kv, idx, sc);
@@ -1596,7 +1615,17 @@ Ct* Engine::relinearize(const Ct* t) {
     return r;
 }
 
-Ct* Engine::mul(Ct* a, Ct* b) {
+// factor (1..3): the product times a small integer, folded into the scalar of the one division (2 a b of the Chebyshev
+// recurrences without an addition of its own); bit-identical to adding the product to itself
+Ct* Engine::mul(Ct* a, Ct* b, int factor) {
+    if (factor < 1 || factor > 3) throw std::runtime_error("multiply: factor must be 1, 2 or 3");
+    if (factor != 1 && !fuse_mul_factor) {                       // A/B: the product, then factor - 1 additions
+        Ct* p = mul(a, b, 1);
+        Ct* r = add(p, p);
+        if (factor == 3) { Ct* r3 = add(r, p); free_ct(r); r = r3; }
+        free_ct(p);
+        return r;
+    }
     if (a->npoly != 2 || b->npoly != 2) throw PolyCountError("multiply: operands should have 2 polynomials");
     if (!has_relin) throw std::runtime_error("multiply needs a relinearisation key");
     const int l = std::min(a->level, b->level);
@@ -1613,7 +1642,7 @@ Ct* Engine::mul(Ct* a, Ct* b) {
         Decomp D = decompose(a->d + ps, l, b->d + ps, nb, abs_, bbs);
         D.own = a->d;
         Ct* r = new_ct(2, l - 1, nb);
-        ks_apply(D, &relin, nullptr, r->d, b->d, 1, true, bbs);
+        ks_apply(D, &relin, nullptr, r->d, b->d, 1, true, bbs, 0, factor);
         release(D.ext);
         n_mul_cc += nb;
         return r;
@@ -1623,7 +1652,7 @@ Ct* Engine::mul(Ct* a, Ct* b) {
     // relinearisation and rescale in one division: (<digits(d2), rlk> + P (d0, d1)) / (P q_l)   (spec S6b)
     Decomp D = decompose(t + 2 * ps, l, nullptr, nb, 3 * ps, 0);
     Ct* r = new_ct(2, l - 1, nb);
-    ks_apply(D, &relin, nullptr, r->d, t, 1, false, 3 * ps);
+    ks_apply(D, &relin, nullptr, r->d, t, 1, false, 3 * ps, 0, factor);
     release(D.ext);
     release(t);
     n_mul_cc += nb;

@@ -225,7 +225,7 @@ class Engine {
     Ct* add(Ct* a, Ct* b);
     Ct* sub(Ct* a, Ct* b);
     Ct* negate(const Ct* a);
-    Ct* mul(Ct* a, Ct* b);                       // tensor + relinearise + rescale
+    Ct* mul(Ct* a, Ct* b, int factor = 1);                       // tensor + relinearise + rescale
     Ct* mul_norelin(Ct* a, Ct* b);               // tensor + rescale, 3 polynomials
     Ct* relinearize(const Ct* t);                // 3 -> 2 polynomials, same level
     Ct* rescale(const Ct* c);
@@ -276,14 +276,17 @@ class Engine {
     // ext, acc and out are [nb][...] contiguous
     Decomp decompose(const u64* d, int level, const u64* times = nullptr, int nb = 1, size_t d_bs = 0, size_t times_bs = 0);
     void ks_apply(const Decomp& D, const EvalKey* evk, const u32* perm, u64* out /* [nb][2][level+1-drop][N] */,
-                  const u64* addend = nullptr, int drop = 0, bool tensor = false, size_t addend_bs = 0, int addend_mode = 0);
+                  const u64* addend = nullptr, int drop = 0, bool tensor = false, size_t addend_bs = 0, int addend_mode = 0,
+                  int factor = 1);
     // c0_addend (optional): a polynomial [level+1][N] per item (stride c0_bs) that joins output polynomial 0 (KsBatch::addend_mode 1)
     void key_switch(const u64* d, int level, const EvalKey* evk, u64* out, int nb = 1, size_t d_bs = 0,
                     const u64* c0_addend = nullptr, size_t c0_bs = 0);
     void ks_inner(const Decomp& D, const EvalKey* evk, const u32* perm, u64* acc, const u64* addend, bool accumulate,
                   bool tensor = false, size_t addend_bs = 0, int addend_mode = 0);
+    bool fuse_align = true;                // CKKS_ALIGN_FUSE=0: level alignment as k_mul_scalar on every limb, then a rescale (A/B)
+    bool fuse_mul_factor = true;           // CKKS_MUL_FACTOR_FUSE=0: 2 a b of the Chebyshev recurrences as a product and an addition (A/B)
     bool fuse_ks_add = true;               // CKKS_KS_ADD_FUSE=0: sigma(c0) + ks0 as a separate permutation / addition (A/B)
-    void ks_moddown(u64* acc, int level, int drop, u64* out, int nb = 1);
+    void ks_moddown(u64* acc, int level, int drop, u64* out, int nb = 1, int factor = 1);
     void automorph(u64* out, const u64* in, int rows, int npoly, u64 g);
     void automorph(u64* out, const u64* in, int rows, int npoly, u64 g, PolyStride ps);
     const u32* galois_perm(u64 g);
@@ -295,7 +298,7 @@ class Engine {
     void scalar_list(const std::vector<u64>& vals, const std::vector<int>& mods, ScalarList& out) const;
     const BaseConvTable& modup_table(int level, int digit);
     const BaseConvTable& moddown_table(int level, int drop = 0);
-    const ScalarList& moddown_inv(int level, int drop);
+    const ScalarList& moddown_inv(int level, int drop, int factor = 1);
     const BaseConvTable* modup_tables_dev(int level);
     const BaseConvTable* moddown_table_dev(int level, int drop = 0);
     const std::vector<i64>& sk_host() const { return sk_coef; }
@@ -338,7 +341,7 @@ class Engine {
     double prof_ms = 0;
     ScalarList sl_pinv;                    // P^-1 mod q_i
     ScalarList sl_pmodq;                   // P mod q_i
-    std::map<int, ScalarList> moddown_invs; // (level, drop) -> (P q_dropped)^-1 mod q_i
+    std::map<int, ScalarList> moddown_invs; // (level, drop, factor) -> factor (P q_dropped)^-1 mod q_i
     std::vector<ScalarList> sl_qinv;       // [l]: q_l^-1 mod q_i, i < l
 
     EvalKey make_switch_key(u64 key_id, const u64* s_from_ntt);
@@ -346,7 +349,7 @@ class Engine {
                                 const std::vector<int>& tgt, const std::vector<int>& orow, bool exact = false);
     void encode_coeffs_dev(i64* out_dev, const double* z_host, double scale, int nb = 1);
     void encode_coeffs_from_dev(i64* out_dev, double* z_dev, double scale, bool check, int nb = 1);
-    void rescale_into(u64* out, const u64* in, int npoly, int level, int nb = 1);
+    void rescale_into(u64* out, const u64* in, int npoly, int level, int nb = 1, size_t in_ps = 0, u64 pre_k = 0);
     void need_levels(int level, int need, const char* what) const;
 };
 

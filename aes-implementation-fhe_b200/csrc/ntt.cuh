@@ -42,6 +42,7 @@ struct NttJob {
 //   epilogue (pass B, ep_out != null): instead of storing NTT(x), item i of slice z stores (a - NTT(x)) * s[i] into row
 //     rows[z][i] of ep_out + z*ep_ozs, a = the same row of ep_a + z*ep_azs (the tail of ModDown and of a rescale; the
 //     stand-alone kernel is k_sub_mul_scalar).
+//     With ep_k the scalar multiplication of a level alignment rides along: (ep_k * a - NTT(x)) * s[i].
 struct NttFuse {
     int pro_mod;
     const u64* ep_a;
@@ -49,6 +50,7 @@ struct NttFuse {
     size_t ep_azs, ep_ozs;
     size_t ep_abs = 0, ep_obs = 0;    // batch strides of ep_a / ep_out
     ScalarList s;
+    u64 ep_k = 0;                     // != 0: a is multiplied by this integer first, (k a - NTT(x)) * s (level alignment, spec S6)
 };
 
 void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st);
