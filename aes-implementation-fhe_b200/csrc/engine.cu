@@ -1469,6 +1469,7 @@ void Engine::rescale_into(u64* out, const u64* in, int npoly, int level, int nb,
         F.ep_out = out; F.ep_ozs = (size_t)level * n; F.ep_obs = (size_t)npoly * level * n;
         F.s = sl_qinv[level];
         F.ep_k = pre_k;
+        if (pre_k) scalar_list(std::vector<u64>((size_t)level, pre_k), lo, F.kl);
         run_ntt_fused(last, delta, J, F, (long)npoly * level * nb);
     } else {
         // [nb][npoly] slices with uniform strides: the batch folds into the polynomial count

@@ -616,7 +616,8 @@ static int pipe_grid(int tiles) {
 template <bool FP, bool EP>
 __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int tile, u32 Rn, const ModConst& mc,
                                                const NttTables& T, int mod, size_t N, const u64* __restrict__ ep_a,
-                                               u64* __restrict__ ep_out, u64 sv, u64 svs, u64 ep_k = 0) {
+                                               u64* __restrict__ ep_out, u64 sv, u64 svs, bool ep_k = false, u64 kv = 0,
+                                               u64 kvs = 0) {
     const u64 q = mc.q;
     const u64* W = (FP ? reinterpret_cast<const u64*>(T.fwd_d) : T.fwd) + (size_t)mod * N;
     const u64* C = FP ? nullptr : T.fwd_s + (size_t)mod * N;
@@ -674,9 +675,8 @@ __device__ __forceinline__ void fwd_passB_body(u64* __restrict__ g, u64* sm, int
 #pragma unroll
             for (int k = 0; k < 16; k++) a[k] = ep_a[k * 256 + threadIdx.x];
             if (ep_k) {                                         // level alignment: k a first (integer pipe, idle in the FP64 form)
-                const u64 kq = barrett_reduce64(ep_k, mc);
 #pragma unroll
-                for (int k = 0; k < 16; k++) a[k] = barrett_mul(a[k], kq, mc);
+                for (int k = 0; k < 16; k++) a[k] = shoup_mul(a[k], kv, kvs, q);
             }
 #pragma unroll
             for (int k = 0; k < 16; k++)
@@ -719,8 +719,10 @@ ntt_fwd_passB_ep(u64* __restrict__ data, const GRID_CONST NttJob J, NttTables T,
     const u64* ep_a = F.ep_a + zb.z * F.ep_azs + zb.b * F.ep_abs + off;
     u64* ep_out = F.ep_out + zb.z * F.ep_ozs + zb.b * F.ep_obs + off;
     const u64 sv = F.s.v[BIDX_ITEM], svs = F.s.vs[BIDX_ITEM];
-    if (use_fp(mc.q)) fwd_passB_body<true, true>(g, sm, tile, Rn, mc, T, mod, N, ep_a, ep_out, sv, svs, F.ep_k);
-    else fwd_passB_body<false, true>(g, sm, tile, Rn, mc, T, mod, N, ep_a, ep_out, sv, svs, F.ep_k);
+    const bool ek = F.ep_k != 0;
+    const u64 kv = ek ? F.kl.v[BIDX_ITEM] : 0, kvs = ek ? F.kl.vs[BIDX_ITEM] : 0;
+    if (use_fp(mc.q)) fwd_passB_body<true, true>(g, sm, tile, Rn, mc, T, mod, N, ep_a, ep_out, sv, svs, ek, kv, kvs);
+    else fwd_passB_body<false, true>(g, sm, tile, Rn, mc, T, mod, N, ep_a, ep_out, sv, svs, ek, kv, kvs);
 }
 
 // ============================================================================================ inverse, pass B^-1

@@ -51,6 +51,7 @@ struct NttFuse {
     size_t ep_abs = 0, ep_obs = 0;    // batch strides of ep_a / ep_out
     ScalarList s;
     u64 ep_k = 0;                     // != 0: a is multiplied by this integer first, (k a - NTT(x)) * s (level alignment, spec S6)
+    ScalarList kl;                    // ... as residues of item i's modulus with their Shoup companions (filled when ep_k != 0)
 };
 
 void ntt_forward(const u64* src, u64* dst, const NttJob& J, const NttTables& T, dev_stream st);

@@ -420,3 +420,38 @@ def test_basis_conversion_paths_agree(which, logn, levels):
             out = np.zeros((2, level + 1, p.N), dtype=np.uint64)
             assert p.lib.ckks_test_key_switch(p.eng._ptr, poly, level, 0, out) == 0
             assert np.array_equal(out[0], want[0]) and np.array_equal(out[1], want[1]), (which, level)
+
+
+@pytest.mark.parametrize("which,logn,levels", [("emu", 12, 6), pytest.param("cuda", 16, 5, marks=pytest.mark.gpu)])
+def test_level_alignment_on_the_rescale_epilogue(which, logn, levels):
+    """Level alignment with the integer scalar riding on the rescale (k on the dropped limb after its inverse transform, k a
+    inside the pass-B epilogue, NttFuse::ep_k; default) against k_mul_scalar on every limb followed by a rescale
+    (CKKS_ALIGN_FUSE=0): identical words at every target level, for a 2- and a 3-polynomial ciphertext and for a batched
+    handle, and equal to the oracle's alignment (spec S6)."""
+    import os
+    fused = Pair(which, logn, levels)
+    os.environ["CKKS_ALIGN_FUSE"] = "0"
+    try:
+        plain = Pair(which, logn, levels)
+    finally:
+        os.environ.pop("CKKS_ALIGN_FUSE", None)
+    rng = np.random.default_rng(17)
+    z = np.exp(2j * np.pi * rng.random(fused.n))
+    zb = np.exp(2j * np.pi * rng.random((3, fused.n)))
+    oc = fused.orc.encrypt(z)
+    made = []
+    for p in (fused, plain):                                          # the first encryption of each engine = the oracle's first
+        c = p.eng.encrypt(z)
+        made.append((c, p.eng.multiply(c, c), p.eng.encrypt(zb)))     # a 3-polynomial product one level down, a handle of 3
+    for target in range(levels - 1, -1, -1):
+        words = []
+        for p, (c, t3, b) in zip((fused, plain), made):
+            lb = p.eng.level_down(b, target)
+            nbw = np.zeros((3, 2, target + 1, p.N), dtype=np.uint64)
+            assert p.lib.ckks_ct_export(p.eng._ptr, lb._h, nbw) == 0
+            words.append((p.export(p.eng.level_down(c, target)),
+                          p.export(p.eng.level_down(t3, target)) if target < levels - 1 else None, nbw))
+        assert np.array_equal(words[0][0], words[1][0]), target
+        assert words[0][1] is None or np.array_equal(words[0][1], words[1][1]), target
+        assert np.array_equal(words[0][2], words[1][2]), target
+        assert np.array_equal(words[0][0], fused.orc.level_down(oc, target).c), target
