@@ -393,8 +393,14 @@ static Ct* cheb_eval(Engine& E, Arena& A, Ct* x, const std::vector<double>& coef
         } catch (...) { E.join(); throw; }
         E.join();
         Ct* Tg = get(g);
-        Ct* t = Q.ct ? A.keep(E.mul(Q.ct, Tg)) : nullptr;
-        if (Q.c0 != 0.0) {
+        // (Q + q_0) T_g: the quotient's constant term joins the quotient before the product (one addition on polynomial 0)
+        // instead of q_0 T_g as a constant product with its own rescale, alignment and addition (CKKS_CHEB_C0_FOLD=0)
+        static const bool fold_c0 = !getenv("CKKS_CHEB_C0_FOLD") || atoi(getenv("CKKS_CHEB_C0_FOLD")) != 0;
+        Ct* qct = Q.ct;
+        const bool folded = fold_c0 && qct && Q.c0 != 0.0;
+        if (folded) qct = A.keep(E.add_const(qct, Q.c0, 0.0));
+        Ct* t = qct ? A.keep(E.mul(qct, Tg)) : nullptr;
+        if (Q.c0 != 0.0 && !folded) {
             Ct* t2 = A.keep(E.mul_const(Tg, Q.c0, 0.0));
             t = t ? A.keep(E.add(t, t2)) : t2;
         }

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 from typing import Dict, List, Tuple
 
+import os
 import numpy as np
 from numpy.polynomial import chebyshev as Cheb
 
@@ -227,8 +228,13 @@ class BootstrapOracle:
             qc, q0 = rec(q)
             rc, r0 = rec(r)
             Tg = get(g)
+            # (q + q_0) T_g: the quotient's constant joins the quotient before the product (CKKS_CHEB_C0_FOLD=0: q_0 T_g as a
+            # constant product of its own), in lockstep with csrc/bootstrap.cu cheb_eval
+            folded = qc is not None and q0 != 0.0 and os.environ.get("CKKS_CHEB_C0_FOLD", "1") != "0"
+            if folded:
+                qc = o.add_const(qc, q0)
             t = o.mul_ct(qc, Tg) if qc is not None else None
-            if q0 != 0.0:
+            if q0 != 0.0 and not folded:
                 t2 = o.mul_const(Tg, q0)
                 t = t2 if t is None else o.add_ct(t, t2)
             if rc is not None:
